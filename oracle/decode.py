@@ -1,0 +1,224 @@
+"""Oracle (test infrastructure): ``vg view -j -K`` multipath-alignment JSON -> CSR.
+
+Restates ``get_all_alignments_one_read`` (reference json2csv.py:667-739),
+``BFS`` (:589-665) and ``metaalign2align`` (:551-587).
+
+Output ("Reads" interchange schema)
+    grp_nmates   uint8[G]      1 or 2 mates in the read group
+    grp_aln_off  int64[2G+1]   retained alignments of (group g, mate m) are
+                               [grp_aln_off[2g+m], grp_aln_off[2g+m+1])
+    mate_seq_len int32[2G]     len(sequence) of the mate (0 when absent)
+    aln_walk_off int64[A+1]    CSR offsets into the walk arrays
+    aln_read_len int32[A]      Alignment.len (sum of to_length along the route)
+    aln_bins     uint8[A,5]    round(x,2)*100 of score, identity, subst, indel,
+                               errors (255 = outside [0,1], a KeyError in the
+                               reference when used, Q7)
+    aln_stats    float64[A,5]  the five un-binned values
+    walk_node    int32[R]      dense node index
+    walk_alen    int32[R]      aligned bases on that node, or -(k+1) when the
+                               fp64 coverage must come from exc_cov[k]
+    walk_cov     float64[R]    coverage exactly as the reference accumulates it
+    exc_cov      float64[E]    see walk_alen
+    mate_names   list[str]     2G read names ('' when absent)
+"""
+import json
+
+import numpy as np
+
+
+def _to_len(sub):
+    return sum(int(e.get("to_length", 0)) for m in sub["path"]["mapping"] for e in m["edit"])
+
+
+def best_routes(aln):
+    """All best-scoring routes through the subpath DAG (json2csv.py:589-662).
+
+    Returns a list of (route, read_len, score).  The procedure is the
+    reference's FIFO relaxation, reproduced step for step because it is not a
+    topological DP (a metanode can be expanded before all its parents are)."""
+    sub = aln["subpath"]
+    starts = aln["start"]
+    want = len(aln["sequence"])
+    fifo = list(starts)
+    live = {}
+    for s in starts:
+        live[s] = [([s], _to_len(sub[s]), sub[s].get("score", 0))]
+    while fifo:
+        cur = fifo.pop(0)
+        if "next" not in sub[cur] or all(r[1] == want for r in live[cur]):
+            continue
+        for child in sub[cur]["next"]:
+            if child not in fifo:
+                fifo.append(child)
+            c_len = _to_len(sub[child])
+            c_score = sub[child].get("score", 0)
+            bucket = live.setdefault(child, [])
+            for route, rl, sc in live[cur]:
+                cand = (route + [child], rl + c_len, sc + c_score)
+                bucket = live[child]
+                if not bucket:
+                    bucket.append(cand)
+                elif cand[2] > bucket[0][2]:
+                    live[child] = [cand]
+                elif cand[2] == bucket[0][2]:
+                    bucket.append(cand)
+        live.pop(cur)
+    if len(live) > 1:
+        top = max(v[0][2] for v in live.values())
+        for k in [k for k, v in live.items() if v[0][2] < top]:
+            live.pop(k)
+    return [r for v in live.values() for r in v]
+
+
+def route_alignment(aln, route, read_len, score, node_len_of):
+    """One route -> walk, coverage and error ratios (json2csv.py:551-587)."""
+    walk, cov, alen = [], [], []
+    tot_al = tot_match = tot_indel = 0
+    for meta in route:
+        for m in aln["subpath"][meta]["path"]["mapping"]:
+            nid = int(m["position"]["node_id"])
+            n_al = n_match = 0
+            for e in m["edit"]:
+                f = int(e.get("from_length", 0))
+                t = int(e.get("to_length", 0))
+                tot_indel += abs(f - t)
+                n_al += min(f, t)
+                if f == t and "sequence" not in e:
+                    n_match += t
+            tot_al += n_al
+            tot_match += n_match
+            frac = n_al / node_len_of(nid)
+            if walk and walk[-1] == nid and cov[-1] < 1:
+                cov[-1] += frac
+                alen[-1] += n_al
+            else:
+                walk.append(nid)
+                cov.append(frac)
+                alen.append(n_al)
+    tot_subst = tot_al - tot_match
+    stats = (
+        float(score / read_len),
+        float(tot_match / tot_al),
+        float(tot_subst / read_len),
+        float(tot_indel / read_len),
+        float((tot_indel + tot_subst) / read_len),
+    )
+    return dict(walk=walk, cov=cov, alen=alen, read_len=read_len, stats=stats)
+
+
+def line_alignments(aln, node_len_of):
+    return [route_alignment(aln, r, rl, sc, node_len_of) for r, rl, sc in best_routes(aln)]
+
+
+def read_groups(lines, node_len_of, thr):
+    """Yield read groups (json2csv.py:667-739): list of 1 or 2 mates, each
+    dict(name, sequence, alns)."""
+    pending = None
+    it = iter(lines)
+    while True:
+        if pending is None:
+            raw = next(it, None)
+            if raw is None or raw == "":
+                return
+            first = json.loads(raw)
+        else:
+            first, pending = pending, None
+        name = first["name"]
+        pair = first.get("paired_read_name", "")
+        m1 = dict(name=name, sequence=first["sequence"], alns=[])
+        mates = [m1]
+        if "subpath" in first:
+            got = line_alignments(first, node_len_of)
+            if got[0]["stats"][0] >= thr:
+                m1["alns"] = got
+        for raw in it:
+            if raw == "":
+                break
+            aln = json.loads(raw)
+            if aln["name"] != name and aln["name"] != pair:
+                pending = aln
+                break
+            if "subpath" not in aln:
+                continue
+            if aln["sequence"] != m1["sequence"] and len(mates) == 1:
+                mates.append(dict(name=aln["name"], sequence=aln["sequence"], alns=[]))
+            got = line_alignments(aln, node_len_of)
+            best = got[0]["stats"][0]
+            tgt = m1 if aln["sequence"] == m1["sequence"] else mates[1]
+            if not tgt["alns"]:
+                if best >= thr:
+                    tgt["alns"] = tgt["alns"] + got
+            else:
+                have = tgt["alns"][0]["stats"][0]
+                if have < best:
+                    tgt["alns"] = got
+                elif have == best:
+                    tgt["alns"] = tgt["alns"] + got
+        yield mates
+
+
+def bin_of(x):
+    """Histogram key of a ratio: Python ``round(x, 2)`` (json2csv.py:335-339)."""
+    r = round(x, 2)
+    k = int(round(r * 100))
+    if 0 <= k <= 100 and k / 100 == r:
+        return k
+    return 255
+
+
+def decode_json(json_path, graph, thr=0.95):
+    node_index = graph["node_index"]
+    node_len = graph["node_len"]
+
+    def node_len_of(nid):
+        return int(node_len[node_index[nid]])        # KeyError like pangenome.nodes[nodeID]
+
+    with open(json_path, "r") as fh:
+        groups = list(read_groups(fh, node_len_of, thr))
+    return pack_groups(groups, graph)
+
+
+def pack_groups(groups, graph):
+    node_index = graph["node_index"]
+    node_len = graph["node_len"]
+    G = len(groups)
+    grp_nmates = np.zeros(G, np.uint8)
+    grp_aln_off = np.zeros(2 * G + 1, np.int64)
+    mate_seq_len = np.zeros(2 * G, np.int32)
+    mate_names = [""] * (2 * G)
+    walk_off = [0]
+    read_len, bins, stats = [], [], []
+    w_node, w_alen, w_cov, exc = [], [], [], []
+    for g, mates in enumerate(groups):
+        grp_nmates[g] = len(mates)
+        for m in range(2):
+            if m < len(mates):
+                mate = mates[m]
+                mate_seq_len[2 * g + m] = len(mate["sequence"])
+                mate_names[2 * g + m] = mate["name"]
+                for a in mate["alns"]:
+                    for nid, c, al in zip(a["walk"], a["cov"], a["alen"]):
+                        k = node_index[nid]
+                        w_node.append(k)
+                        w_cov.append(c)
+                        if al / int(node_len[k]) == c:
+                            w_alen.append(al)
+                        else:
+                            w_alen.append(-(len(exc) + 1))
+                            exc.append(c)
+                    walk_off.append(len(w_node))
+                    read_len.append(a["read_len"])
+                    stats.append(a["stats"])
+                    bins.append([bin_of(x) for x in a["stats"]])
+            grp_aln_off[2 * g + m + 1] = len(read_len)
+    A = len(read_len)
+    return dict(
+        grp_nmates=grp_nmates, grp_aln_off=grp_aln_off, mate_seq_len=mate_seq_len,
+        aln_walk_off=np.asarray(walk_off, np.int64),
+        aln_read_len=np.asarray(read_len, np.int32),
+        aln_bins=np.asarray(bins, np.uint8).reshape(A, 5),
+        aln_stats=np.asarray(stats, np.float64).reshape(A, 5),
+        walk_node=np.asarray(w_node, np.int32), walk_alen=np.asarray(w_alen, np.int32),
+        walk_cov=np.asarray(w_cov, np.float64), exc_cov=np.asarray(exc, np.float64),
+        mate_names=mate_names,
+    )

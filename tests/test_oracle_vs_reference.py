@@ -1,0 +1,105 @@
+"""Live differential test: the oracle against the unmodified reference on fresh random cases.
+Skipped where /root/reference is absent (the GPU box)."""
+import os
+import warnings
+
+import pytest
+
+import casegen
+import compare
+import refharness
+from oracle import abundance as oa
+from oracle import decode as od
+from oracle import graph as og
+from oracle import report as orp
+
+pytestmark = pytest.mark.skipif(not refharness.have_reference(), reason="reference not mounted")
+
+
+@pytest.mark.parametrize("seed", range(1000, 1040))
+def test_random_case(seed, tmp_path):
+    warnings.simplefilter("ignore")
+    gfa, js, pk = casegen.make_case(seed, str(tmp_path), n_groups=70, n_clusters=2 + seed % 5, n_strains=2 + seed % 4)
+    ref = refharness.run_json2csv(gfa, js, pk, 0.95, outdir=str(tmp_path))
+    g = og.load_graph(gfa, pk)
+    r = od.decode_json(js, g, 0.95)
+    orc = oa.AbundanceOracle(g, r).run()
+    compare.check_state_vs_reference(orc, ref, exact=True)
+    order = [g["strain_names"].index(s) for s in ref["species"]]
+    assert orp.gene_table_text(orc, order) == open(ref["prefix"] + "_gene_table.csv").read()
+    for k, hn in enumerate(orp.HIST_NAMES):
+        assert orp.hist_text(orc, k) == open(ref["prefix"] + "_" + hn + ".csv").read()
+    cl = orp.cluster_unassigned(orc)
+    for c, rc in zip(cl, ref["clusters"]):
+        assert c["reads_name"] == rc["reads_name"]
+        assert c["unassigned_paths"] == rc["unassigned_paths"]
+        assert c["unassigned_abund"] == rc["unassigned_abund"]
+        assert c["count"] == rc["count"] and c["count_norm"] == rc["count_norm"]
+    assert orp.unassigned_text(orc, cl, order) == open(ref["prefix"] + "_unassigned.csv").read()
+
+
+@pytest.mark.parametrize("thr", [0.0, 0.5, 0.9, 1.0])
+def test_threshold_sweep(thr, tmp_path):
+    gfa, js, pk = casegen.make_case(31337, str(tmp_path), n_groups=90, n_clusters=4, n_strains=3)
+    ref = refharness.run_json2csv(gfa, js, pk, thr)
+    g = og.load_graph(gfa, pk)
+    orc = oa.AbundanceOracle(g, od.decode_json(js, g, thr)).run()
+    compare.check_state_vs_reference(orc, ref, exact=True)
+
+
+def _tiny(tmp_path, lines, gfa_text, clusters):
+    import json
+    import pickle
+    gfa = tmp_path / "g.gfa"
+    gfa.write_text(gfa_text)
+    js = tmp_path / "r.json"
+    js.write_text("".join(json.dumps(ln) + "\n" for ln in lines))
+    pk = tmp_path / "c.pickle"
+    with open(pk, "wb") as fh:
+        pickle.dump(clusters, fh)
+    return str(gfa), str(js), str(pk)
+
+
+def _line(name, node, n, score, pair=None, seq=None):
+    ln = {"name": name, "sequence": seq or ("A" * n), "start": [0],
+          "subpath": [{"path": {"mapping": [{"position": {"node_id": str(node)},
+                                             "edit": [{"from_length": n, "to_length": n}]}]}, "score": score}]}
+    if pair:
+        ln["paired_read_name"] = pair
+    return ln
+
+
+GFA = "S\t1\tACGTACGTAC\nS\t2\tACGTA\nS\t3\tAAAA\nP\tNC_1.1_1\t1+,2+\t*\n"
+
+
+@pytest.mark.parametrize("which,exc", [("score_above_one", KeyError), ("node_on_no_path", IndexError),
+                                        ("no_cluster", TypeError), ("unknown_node", KeyError)])
+def test_error_quirks_match(which, exc, tmp_path):
+    """Q7 / Q10: the oracle raises the same exception class as the reference."""
+    clusters = {"Cluster_0": {"genes_list": ["NC_1.1_1"], "len_rep": 1}}
+    if which == "score_above_one":          # bonus score -> histogram KeyError (Q7); needs a pair to reach fill
+        lines = [_line("a", 1, 10, 15, "a", "A" * 10), _line("a", 2, 5, 5, "a", "C" * 5)]
+    elif which == "node_on_no_path":        # S4 bookkeeping on a node no path crosses
+        lines = [_line("a", 3, 4, 4)]
+    elif which == "no_cluster":             # path not in any cluster -> clusters[None]
+        clusters = {"Cluster_0": {"genes_list": [], "len_rep": 1}}
+        lines = [_line("a", 2, 5, 5, seq="AAAAA")]
+        gfa_text = GFA + "P\tNC_2.1_1\t2+,1+,3+\t*\n"
+        gfa, js, pk = _tiny(tmp_path, [{"name": "a", "sequence": "AAAAAAAAA", "start": [0], "subpath": [
+            {"path": {"mapping": [{"position": {"node_id": "2"}, "edit": [{"from_length": 5, "to_length": 5}]},
+                                  {"position": {"node_id": "3"}, "edit": [{"from_length": 4, "to_length": 4}]}]},
+             "score": 9}]}], gfa_text, clusters)
+        with pytest.raises(exc):
+            refharness.run_json2csv(gfa, js, pk, 0.95)
+        g = og.load_graph(gfa, pk)
+        with pytest.raises(exc):
+            oa.AbundanceOracle(g, od.decode_json(js, g, 0.95)).run()
+        return
+    else:
+        lines = [_line("a", 99, 4, 4)]
+    gfa, js, pk = _tiny(tmp_path, lines, GFA, clusters)
+    with pytest.raises(exc):
+        refharness.run_json2csv(gfa, js, pk, 0.95)
+    with pytest.raises(exc):
+        g = og.load_graph(gfa, pk)
+        oa.AbundanceOracle(g, od.decode_json(js, g, 0.95)).run()
