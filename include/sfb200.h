@@ -1,0 +1,199 @@
+/* sfb200.h -- C ABI of libsfb200.so, the B200 (sm_100a) abundance engine behind
+ * StrainFLAIR's `json2csv` / `compute_strains_abundance` hot path.
+ *
+ * The reference has no FFI layer: the path sits inside two
+ * Python functions.  Each entry point below names the reference code it
+ * replaces (file:line relative to the reference checkout).  The Python host
+ * (strainflair_b200/engine.py) binds these with ctypes; INTEGRATION.md shows the
+ * stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every array is a caller-owned DEVICE pointer (e.g. a torch tensor's
+ *     data_ptr()); sizes are int64_t; `stream` is a cudaStream_t passed as void*;
+ *   - the library never allocates, frees or synchronises, holds no global
+ *     mutable state, and is safe to call concurrently on distinct
+ *     streams/buffers;
+ *   - every call returns SFB_OK (0) or a negative SFB_E_* code; the message of
+ *     the last failure on the calling thread is sfb_last_error().
+ *   - accumulating calls (classify, pass1, pass2) ADD into the sfb_accum
+ *     arrays: zero them once per job, not per call, so that read shards can be
+ *     streamed through the same accumulators.
+ */
+#ifndef SFB200_H
+#define SFB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFB_ABI_VERSION 1
+
+/* ---- status codes ---------------------------------------------------- */
+#define SFB_OK            0
+#define SFB_E_ARG        -1   /* null pointer / negative size / limit exceeded */
+#define SFB_E_CUDA       -2   /* a CUDA runtime call or launch failed           */
+
+/* ---- encodings --------------------------------------------------------- */
+/* A match (json2csv.py:341-363 returns (path_id, position)) is one 32-bit code:
+ *   bits 0..29  slot = path_off[path_id] + position in the sentinel layout
+ *   bit  30     the reversed walk matched (json2csv.py:862), not the walk itself
+ * aln_match[a] holds, per retained alignment a:
+ *   SFB_MATCH_NONE                no colored path matches
+ *   bit 31 clear                  exactly one match, stored inline
+ *   bit 31 set                    several: (v & 0x7fffffff)*2 indexes match_buf,
+ *                                 where [0] = count n and [1..n] = the codes in
+ *                                 the reference's order (forward matches by
+ *                                 ascending path id / position, then reverse) */
+#define SFB_SLOT_MASK    0x3fffffffu
+#define SFB_MATCH_REV    0x40000000u
+#define SFB_MATCH_MULTI  0x80000000u
+#define SFB_MATCH_NONE   0xffffffffu
+#define SFB_MAX_SLOTS    0x3fffffff          /* n_slots limit (2^30-1)           */
+
+/* Per-mate pass-1 outcome, one nibble per mate in grp_code[g] (mate 0 = low
+ * nibble).  Leaves of the decision tree at json2csv.py:830-1053. */
+enum {
+    SFB_ABSENT = 0,          /* group has no such mate                              */
+    SFB_FILTERED = 1,        /* no alignment >= thr            (:834-845, :1013)    */
+    SFB_UNASSIGNED = 2,      /* no colored path, not recorded  (:868-910)           */
+    SFB_UNASSIGNED_BOOK = 3, /* no colored path, recorded in its cluster (:884,:903,:1037) */
+    SFB_DEFER = 4,           /* goes to pass 2                 (:927,:988,:1017,:1028) */
+    SFB_ASSIGN_SAME = 5,     /* unique, both mates on one path (:931-959)           */
+    SFB_ASSIGN_DIFF = 6,     /* unique after strain reduction  (:991-996)           */
+    SFB_MULTI_ALIGN = 7,     /* unresolvable multiple alignments (:935,:948,:998)   */
+    SFB_INCONSIST = 8,       /* no common strain               (:1000)              */
+    SFB_SE_COUNTED = 9       /* single-end unique: counted, never accumulated (:1047-1050) */
+};
+/* Per-mate pass-2 outcome in grp_code2[g] (json2csv.py:1085-1274). */
+enum {
+    SFB_P2_NONE = 0, SFB_P2_ASSIGNED = 1, SFB_P2_MULTI_ALIGN = 2, SFB_P2_SE_ASSIGNED = 3,
+    SFB_P2_UNASSIGNED = 4, SFB_P2_INCONSIST = 5
+};
+/* Index of each module-level counter of json2csv.py:743-790 in sfb_accum.counters. */
+enum {
+    SFB_C_NB_READS = 0, SFB_C_PAIRS, SFB_C_SINGLES, SFB_C_FILTERED, SFB_C_UNASSIGNED, SFB_C_ASSIGNED_U,
+    SFB_C_ASSIGNED_M, SFB_C_INCONSIST, SFB_C_INCONSIST_M, SFB_C_MULTI_ALIGN, SFB_C_SE, SFB_C_SAME_CP,
+    SFB_C_DIFF_CP, SFB_C_ONE_NOALIGN, SFB_C_ONE_NOCP, SFB_C_AMBIG_CP_RESOLVED, SFB_C_AMBIG_RESOLVED,
+    SFB_C_AMBIG_REDUCED, SFB_C_SE_M, SFB_C_SECOND_PASS,
+    SFB_C_BAD_BIN,        /* histogram key outside [0,1] was needed: the reference raises KeyError (Q7) */
+    SFB_C_MATCH_OVERFLOW, /* ints of match_buf that did not fit; grow match_cap and rerun          */
+    SFB_C_NO_PATH,        /* unassigned walk starts on a node no path crosses: IndexError (Q10)    */
+    SFB_C_NO_CLUSTER,     /* unassigned read recorded in cluster None: TypeError (Q10)             */
+    SFB_N_COUNTERS = 24
+};
+#define SFB_N_HIST 5          /* mappingscore, identityscore, subst, indel, errors (json2csv.py:335-339) */
+#define SFB_N_BINS 101
+#define SFB_TABLE_COLS 8      /* columns of sfb_path_reduce's table, see below */
+
+/* ---- graph: Pangenome (json2csv.py:203-319) as arrays ------------------- */
+/* Slots: path p occupies slots [path_off[p], path_off[p+1]-1); slot
+ * path_off[p+1]-1 is a sentinel (slot_node = -1) so that a walk running off the
+ * end of a path fails to compare (json2csv.py:360: the slice is shorter). */
+typedef struct sfb_graph {
+    int64_t n_nodes, n_paths, n_slots, n_strains, mask_words;
+    const int32_t*  slot_node;     /* [n_slots] dense node index, -1 on sentinels            */
+    const int32_t*  slot_len;      /* [n_slots] Node.len_sequence of that node (:104), 1 on sentinels */
+    const int32_t*  slot_path;     /* [n_slots] path id owning the slot                      */
+    const int32_t*  path_off;      /* [n_paths+1]                                            */
+    const int32_t*  occ_off;       /* [n_nodes+1] node -> occurrences (Node.traversed_path + position scan, :352-357) */
+    const int32_t*  occ_slot;      /* [n_slots-n_paths] slots of the node, ascending          */
+    const int64_t*  path_seq_len;  /* [n_paths] get_sequence_length (:220-221)               */
+    const int32_t*  path_nstrain;  /* [n_paths] len(path.strain_ids)                         */
+    const int32_t*  path_strain0;  /* [n_paths] first strain id of the path (histogram row, :334) */
+    const uint64_t* path_smask;    /* [n_paths*mask_words] bit s set iff strain s in path.strain_ids */
+    const int32_t*  path_cluster;  /* [n_paths] Path.cluster_id, -1 for None                 */
+} sfb_graph;
+
+/* ---- reads: decoded alignments (json2csv.py:551-739) as CSR -------------- */
+typedef struct sfb_reads {
+    int64_t n_groups, n_alns, n_records, n_exc;
+    const uint8_t* grp_nmates;    /* [G]     1 or 2 (len(mapped_paths), :828)                 */
+    const int64_t* grp_aln_off;   /* [2G+1]  retained alignments of (g, mate m): [off[2g+m], off[2g+m+1]) */
+    const int32_t* mate_seq_len;  /* [2G]    len(sequence)                                    */
+    const int64_t* aln_walk_off;  /* [A+1]                                                    */
+    const uint8_t* aln_bins;      /* [A*5]   round(x,2)*100 of the five ratios, 255 = outside [0,1] */
+    const int32_t* walk_node;     /* [R]     Alignment.mapped_nodes_id (dense node index)     */
+    const int32_t* walk_alen;     /* [R]     aligned bases: coverage = alen / node length (:574); or -(k+1): coverage = exc_cov[k] */
+    const double*  exc_cov;       /* [E]                                                      */
+} sfb_reads;
+
+/* ---- per-shard work arrays (outputs of match / classify) ----------------- */
+typedef struct sfb_work {
+    uint32_t* aln_match;          /* [A]   see encodings                                      */
+    int32_t*  match_buf;          /* [match_cap]                                              */
+    int64_t   match_cap;          /* ints; < 2^32                                             */
+    unsigned long long* cursor;   /* [2]   [0] match_buf fill (ints), [1] number of deferred groups; zero before sfb_match */
+    uint8_t*  grp_code;           /* [G]                                                      */
+    uint8_t*  grp_code2;          /* [G]   zero before sfb_pass2                              */
+    int32_t*  aln_assign;         /* [A]   >= 0: match code of the unique assignment (:945,:958,:996);
+                                           -1: none; <= -2: first alignment of a mate recorded as
+                                           unassigned in cluster -(v+2) (:884,:903,:1037)      */
+    int32_t*  deferred;           /* [G]   group ids going to pass 2 (unordered)              */
+} sfb_work;
+
+/* ---- accumulators (Path counters, json2csv.py:113-118, and histograms) ---- */
+typedef struct sfb_accum {
+    long long* uniq_reads;        /* [P]  total_mapped_unique_reads                           */
+    double*    uniq_norm;         /* [P]  total_mapped_unique_reads_normalized                */
+    double*    mult_reads;        /* [P]  total_mapped_mult_reads                             */
+    double*    mult_norm;         /* [P]  total_mapped_mult_reads_normalized                  */
+    unsigned*  mult_hits;         /* [P]  number of pass-2 additions (0 <=> the reference prints an int 0) */
+    double*    uniq_abund;        /* [n_slots] unique_mapped_abundances                       */
+    double*    mult_abund;        /* [n_slots] multiple_mapped_abundances                     */
+    unsigned long long* hist;     /* [5*n_strains*101]                                        */
+    long long* counters;          /* [SFB_N_COUNTERS]                                         */
+} sfb_accum;
+
+/* ---- entry points ------------------------------------------------------- */
+int         sfb_abi_version(void);
+const char* sfb_version(void);
+const char* sfb_last_error(void);
+
+/* Pangenome.get_matching_path on the walk and, if longer than one node, on the reversed
+ * walk (json2csv.py:341-363 with callers :855-866, :1024-1026, :1103-1114, :1231-1233). */
+int sfb_match(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_accum* acc, void* stream);
+
+/* Pass-1 decision tree per read group (json2csv.py:828-1053) including the per-read part
+ * of fill_abund_dist (:326-327, :333-339): counters, grp_code, aln_assign, deferred list,
+ * uniq_reads, uniq_norm, histograms. */
+int sfb_classify(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_accum* acc, void* stream);
+
+/* Node-level part of fill_abund_dist (json2csv.py:329-330) for every alignment with
+ * aln_assign >= 0: uniq_abund[slot+i] += cov[i]. */
+int sfb_pass1_scatter(const sfb_graph* g, const sfb_reads* r, const sfb_work* w, sfb_accum* acc, void* stream);
+
+/* Pass 2 (json2csv.py:1085-1274) over the deferred groups.  `uniq_reads_global` is the
+ * per-path unique count summed over ALL read shards (acc->uniq_reads when there is one). */
+int sfb_pass2(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_accum* acc,
+              const long long* uniq_reads_global, void* stream);
+
+/* Pangenome.print_gene_table's per-path reductions (json2csv.py:440-469) for paths
+ * [p_begin, p_end): table[(p-p_begin)*8 + k], k = 0 nb_uniq_mapped_normalized,
+ * 1 nb_multimapped, 2 nb_multimapped_normalized, 3 mean_abund_uniq, 4 mean_abund_uniq_nz,
+ * 5 mean_abund_multiple, 6 mean_abund_multiple_nz, 7 ratio_covered_nodes. */
+int sfb_path_reduce(const sfb_graph* g, const sfb_accum* acc, int64_t p_begin, int64_t p_end,
+                    double* table, void* stream);
+
+/* print_unassigned_info's per-cluster strain copy counts (json2csv.py:544):
+ * out[c*n_strains + s] = sum over clu_paths[clu_off[c]..clu_off[c+1]) of the copy count of s. */
+int sfb_cluster_strain_counts(int64_t n_clusters, int64_t n_strains, const int32_t* clu_off,
+                              const int32_t* clu_paths, const int32_t* pstr_off, const int32_t* pstr_id,
+                              const int32_t* pstr_cnt, long long* out, void* stream);
+
+/* compute_strains_abundance (compute_strains_abundance.py:52-69).
+ * Inputs per gene row p: CSR of its positive strain counts (row_off/row_strain/row_count) and
+ * mean_abund_multiple, mean_abund_multiple_nz, ratio_covered_nodes (NaN already 0, :50).
+ * ws_rows int32[2P], ws_vals double[2P], ws_counts double[4S] are scratch.
+ * out[s*5 + k]: 0 detected_genes (NaN when 0/0), 1 mean_abund, 2 mean_abund_nz,
+ * 3 median_abund, 4 median_abund_nz, thresholded and normalised to 100. */
+int sfb_strain_aggregate(int64_t n_rows, int64_t n_strains, const int32_t* row_off,
+                         const int32_t* row_strain, const double* row_count, const double* mam,
+                         const double* mam_nz, const double* ratio_cov, double thr, int32_t* ws_rows,
+                         double* ws_vals, double* ws_counts, double* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFB200_H */

@@ -1,0 +1,117 @@
+"""ctypes binding of libsfb200.so (include/sfb200.h).  There is no CPU fallback: if the
+library is missing or cannot be built, importing this module's users fails loudly."""
+import ctypes as C
+import os
+
+from . import build as _build
+
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+c_u8p = C.POINTER(C.c_uint8)
+c_u32p = C.POINTER(C.c_uint32)
+c_u64p = C.POINTER(C.c_uint64)
+c_f64p = C.POINTER(C.c_double)
+
+
+class SfbGraph(C.Structure):
+    _fields_ = [
+        ("n_nodes", C.c_int64), ("n_paths", C.c_int64), ("n_slots", C.c_int64), ("n_strains", C.c_int64),
+        ("mask_words", C.c_int64),
+        ("slot_node", C.c_void_p), ("slot_len", C.c_void_p), ("slot_path", C.c_void_p), ("path_off", C.c_void_p),
+        ("occ_off", C.c_void_p), ("occ_slot", C.c_void_p), ("path_seq_len", C.c_void_p),
+        ("path_nstrain", C.c_void_p), ("path_strain0", C.c_void_p), ("path_smask", C.c_void_p),
+        ("path_cluster", C.c_void_p),
+    ]
+
+
+class SfbReads(C.Structure):
+    _fields_ = [
+        ("n_groups", C.c_int64), ("n_alns", C.c_int64), ("n_records", C.c_int64), ("n_exc", C.c_int64),
+        ("grp_nmates", C.c_void_p), ("grp_aln_off", C.c_void_p), ("mate_seq_len", C.c_void_p),
+        ("aln_walk_off", C.c_void_p), ("aln_bins", C.c_void_p), ("walk_node", C.c_void_p),
+        ("walk_alen", C.c_void_p), ("exc_cov", C.c_void_p),
+    ]
+
+
+class SfbWork(C.Structure):
+    _fields_ = [
+        ("aln_match", C.c_void_p), ("match_buf", C.c_void_p), ("match_cap", C.c_int64), ("cursor", C.c_void_p),
+        ("grp_code", C.c_void_p), ("grp_code2", C.c_void_p), ("aln_assign", C.c_void_p), ("deferred", C.c_void_p),
+    ]
+
+
+class SfbAccum(C.Structure):
+    _fields_ = [
+        ("uniq_reads", C.c_void_p), ("uniq_norm", C.c_void_p), ("mult_reads", C.c_void_p), ("mult_norm", C.c_void_p),
+        ("mult_hits", C.c_void_p), ("uniq_abund", C.c_void_p), ("mult_abund", C.c_void_p), ("hist", C.c_void_p),
+        ("counters", C.c_void_p),
+    ]
+
+
+# mirrors of the enums in include/sfb200.h (checked against the header in tests/test_abi.py)
+COUNTER_NAMES = (
+    "NB_READS", "PAIRS", "SINGLES", "FILTERED", "UNASSIGNED", "ASSIGNED_U", "ASSIGNED_M", "INCONSIST", "INCONSIST_M",
+    "MULTI_ALIGN", "SE", "SAME_CP", "DIFF_CP", "ONE_NOALIGN", "ONE_NOCP", "AMBIG_CP_RESOLVED", "AMBIG_RESOLVED",
+    "AMBIG_REDUCED", "SE_M", "SECOND_PASS", "BAD_BIN", "MATCH_OVERFLOW", "NO_PATH", "NO_CLUSTER",
+)
+N_COUNTERS = 24
+N_HIST, N_BINS, TABLE_COLS = 5, 101, 8
+SLOT_MASK, MATCH_REV, MATCH_MULTI, MATCH_NONE = 0x3FFFFFFF, 0x40000000, 0x80000000, 0xFFFFFFFF
+MAX_SLOTS = 0x3FFFFFFF
+(ABSENT, FILTERED, UNASSIGNED, UNASSIGNED_BOOK, DEFER, ASSIGN_SAME, ASSIGN_DIFF, MULTI_ALIGN, INCONSIST,
+ SE_COUNTED) = range(10)
+ABI_VERSION = 1
+
+EXPORTS = ("sfb_abi_version", "sfb_version", "sfb_last_error", "sfb_match", "sfb_classify", "sfb_pass1_scatter",
+           "sfb_pass2", "sfb_path_reduce", "sfb_cluster_strain_counts", "sfb_strain_aggregate")
+
+
+class SfbError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load(build_if_missing=True):
+    """Returns the loaded library.  Builds it in-tree with nvcc when absent/stale and a compiler exists."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if build_if_missing:
+        try:
+            _build.build()
+        except Exception as e:          # no nvcc on this machine: use the prebuilt .so if there is one
+            if not os.path.exists(path):
+                raise SfbError(f"libsfb200.so is missing and could not be built: {e}") from e
+    if not os.path.exists(path):
+        raise SfbError(f"{path} not found; run `python -m strainflair_b200.build` (there is no CPU fallback)")
+    lib = C.CDLL(path)
+    lib.sfb_abi_version.restype = C.c_int
+    lib.sfb_version.restype = C.c_char_p
+    lib.sfb_last_error.restype = C.c_char_p
+    G, R, W, A = C.POINTER(SfbGraph), C.POINTER(SfbReads), C.POINTER(SfbWork), C.POINTER(SfbAccum)
+    vp, i64, f64 = C.c_void_p, C.c_int64, C.c_double
+    lib.sfb_match.argtypes = [G, R, W, A, vp]
+    lib.sfb_classify.argtypes = [G, R, W, A, vp]
+    lib.sfb_pass1_scatter.argtypes = [G, R, W, A, vp]
+    lib.sfb_pass2.argtypes = [G, R, W, A, vp, vp]
+    lib.sfb_path_reduce.argtypes = [G, A, i64, i64, vp, vp]
+    lib.sfb_cluster_strain_counts.argtypes = [i64, i64, vp, vp, vp, vp, vp, vp, vp]
+    lib.sfb_strain_aggregate.argtypes = [i64, i64, vp, vp, vp, vp, vp, vp, f64, vp, vp, vp, vp, vp]
+    for name in EXPORTS[3:]:
+        getattr(lib, name).restype = C.c_int
+    if lib.sfb_abi_version() != ABI_VERSION:
+        raise SfbError(f"ABI mismatch: library {lib.sfb_abi_version()}, binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise SfbError(f"libsfb200 error {rc}: {load().sfb_last_error().decode()}")

@@ -1,0 +1,332 @@
+"""Host orchestration of the abundance pass on one B200 (one process per GPU).
+
+PyTorch is used for device buffers, streams and (optionally) torch.distributed collectives only;
+every computation is a hand-written kernel of libsfb200.so called through ctypes (include/sfb200.h).
+
+Pipeline (reference json2csv.py:811-1279 + :399-474), per read shard:
+    match -> classify -> pass-1 scatter -> [sum uniq_reads over shards] -> pass 2
+    -> [sum accumulators over shards] -> path reduce
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .schema import Graph, Reads
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr() if t is not None and t.numel() else (t.data_ptr() if t is not None else 0))
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _to_dev(a, device, pin=False):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if pin:
+        t = t.pin_memory()
+    return t.to(device, non_blocking=True)
+
+
+class DeviceGraph:
+    """The graph in the device layout of include/sfb200.h: every path followed by one sentinel slot,
+    plus the node -> slot occurrence index that replaces Node.traversed_path and the position scan
+    (json2csv.py:352-357)."""
+
+    def __init__(self, graph: Graph, device):
+        self.graph = graph
+        self.device = torch.device(device)
+        P = graph.n_paths
+        T = graph.n_path_nodes
+        plen = np.diff(graph.path_off)
+        n_slots = T + P
+        if n_slots > _lib.MAX_SLOTS:
+            raise ValueError(f"graph too large for 30-bit slot codes: {n_slots} slots")
+        # plain position -> slot
+        self.slot_of_plain = (np.arange(T, dtype=np.int64) + np.repeat(np.arange(P, dtype=np.int64), plen))
+        slot_node = np.full(n_slots, -1, np.int32)
+        slot_node[self.slot_of_plain] = graph.path_nodes
+        slot_len = np.ones(n_slots, np.int32)
+        slot_len[self.slot_of_plain] = graph.node_len[graph.path_nodes]
+        slot_path = np.repeat(np.arange(P, dtype=np.int32), plen + 1)
+        path_off = (graph.path_off + np.arange(P + 1, dtype=np.int64)).astype(np.int32)
+        order = np.argsort(graph.path_nodes, kind="stable")
+        occ_slot = self.slot_of_plain[order].astype(np.int32)
+        occ_off = np.zeros(graph.n_nodes + 1, np.int64)
+        np.cumsum(np.bincount(graph.path_nodes, minlength=graph.n_nodes), out=occ_off[1:])
+        S = graph.n_strains
+        words = max(1, (S + 63) // 64)
+        smask = np.zeros((P, words), np.uint64)
+        owner = np.repeat(np.arange(P, dtype=np.int64), np.diff(graph.pstr_off))
+        sid = graph.pstr_id.astype(np.int64)
+        np.bitwise_or.at(smask, (owner, sid >> 6), np.left_shift(np.uint64(1), (sid & 63).astype(np.uint64)))
+        nstrain = np.diff(graph.pstr_off).astype(np.int32)
+        strain0 = np.zeros(P, np.int32)
+        has = nstrain > 0
+        strain0[has] = graph.pstr_id[graph.pstr_off[:-1][has]]
+        self.n_slots, self.n_paths, self.n_strains, self.mask_words = n_slots, P, S, words
+        self.path_off_host = path_off
+        d = self.device
+        self.t = dict(
+            slot_node=_to_dev(slot_node, d), slot_len=_to_dev(slot_len, d), slot_path=_to_dev(slot_path, d),
+            path_off=_to_dev(path_off, d), occ_off=_to_dev(occ_off.astype(np.int32), d), occ_slot=_to_dev(occ_slot, d),
+            path_seq_len=_to_dev(graph.path_seq_len, d), path_nstrain=_to_dev(nstrain, d),
+            path_strain0=_to_dev(strain0, d), path_smask=_to_dev(smask.view(np.int64), d),
+            path_cluster=_to_dev(graph.path_cluster, d),
+        )
+        self.c = _lib.SfbGraph(n_nodes=graph.n_nodes, n_paths=P, n_slots=n_slots, n_strains=S, mask_words=words,
+                               **{k: v.data_ptr() for k, v in self.t.items()})
+
+    def nbytes(self):
+        return sum(v.numel() * v.element_size() for v in self.t.values())
+
+
+READS_DEVICE_FIELDS = ("grp_nmates", "grp_aln_off", "mate_seq_len", "aln_walk_off", "aln_bins", "walk_node",
+                       "walk_alen", "exc_cov")
+
+
+class HostReads:
+    """Reads staged in pinned host memory (the e2e path copies from here every step)."""
+
+    def __init__(self, reads: Reads, pin=True):
+        self.reads = reads
+        self.t = {}
+        for k in READS_DEVICE_FIELDS:
+            t = torch.from_numpy(np.ascontiguousarray(getattr(reads, k)).reshape(-1))
+            self.t[k] = t.pin_memory() if (pin and t.numel()) else t
+        self.n_groups, self.n_alns, self.n_records = reads.n_groups, reads.n_alns, reads.n_records
+        self.n_exc = len(reads.exc_cov)
+
+    def nbytes(self):
+        return sum(v.numel() * v.element_size() for v in self.t.values())
+
+
+class DeviceReads:
+    def __init__(self, host: HostReads, device):
+        self.host = host
+        self.t = {k: v.to(device, non_blocking=True) for k, v in host.t.items()}
+        self.n_groups, self.n_alns, self.n_records, self.n_exc = host.n_groups, host.n_alns, host.n_records, host.n_exc
+        self.c = _lib.SfbReads(n_groups=self.n_groups, n_alns=self.n_alns, n_records=self.n_records, n_exc=self.n_exc,
+                               **{k: v.data_ptr() for k, v in self.t.items()})
+
+
+class Work:
+    """Per-shard work arrays (sfb_work)."""
+
+    def __init__(self, n_groups, n_alns, match_cap, device):
+        i32, u8 = torch.int32, torch.uint8
+        self.n_groups, self.n_alns = n_groups, n_alns
+        self.match_cap = int(max(2, match_cap))
+        self.t = dict(
+            aln_match=torch.empty(max(1, n_alns), dtype=i32, device=device),
+            match_buf=torch.empty(self.match_cap, dtype=i32, device=device),
+            cursor=torch.zeros(2, dtype=torch.int64, device=device),
+            grp_code=torch.zeros(max(1, n_groups), dtype=u8, device=device),
+            grp_code2=torch.zeros(max(1, n_groups), dtype=u8, device=device),
+            aln_assign=torch.empty(max(1, n_alns), dtype=i32, device=device),
+            deferred=torch.empty(max(1, n_groups), dtype=i32, device=device),
+        )
+        self.c = _lib.SfbWork(match_cap=self.match_cap, **{k: v.data_ptr() for k, v in self.t.items()})
+
+    def reset(self):
+        self.t["cursor"].zero_()
+        self.t["grp_code2"].zero_()
+
+
+class Accum:
+    """Accumulators (sfb_accum), one flat fp64 and one flat int64 allocation so that a shard
+    exchange is two collectives."""
+
+    def __init__(self, dg: DeviceGraph):
+        P, S, n_slots = dg.n_paths, dg.n_strains, dg.n_slots
+        dev = dg.device
+        self.P, self.S, self.n_slots = P, S, n_slots
+        # fp64 block: uniq_norm | mult_reads | mult_norm | uniq_abund | mult_abund
+        self.f64 = torch.zeros(3 * P + 2 * n_slots, dtype=torch.float64, device=dev)
+        # int64 block: uniq_reads | hist | counters | mult_hits (uint32 pairs packed in the tail)
+        self.n_hist = _lib.N_HIST * S * _lib.N_BINS
+        self.i64 = torch.zeros(P + self.n_hist + _lib.N_COUNTERS + (P + 1) // 2, dtype=torch.int64, device=dev)
+        f, i = self.f64, self.i64
+        self.uniq_norm, self.mult_reads, self.mult_norm = f[0:P], f[P:2 * P], f[2 * P:3 * P]
+        self.uniq_abund, self.mult_abund = f[3 * P:3 * P + n_slots], f[3 * P + n_slots:]
+        self.uniq_reads = i[0:P]
+        self.hist = i[P:P + self.n_hist]
+        self.counters = i[P + self.n_hist:P + self.n_hist + _lib.N_COUNTERS]
+        self.mult_hits = i[P + self.n_hist + _lib.N_COUNTERS:].view(torch.int32)
+        self.c = _lib.SfbAccum(
+            uniq_reads=self.uniq_reads.data_ptr(), uniq_norm=self.uniq_norm.data_ptr(),
+            mult_reads=self.mult_reads.data_ptr(), mult_norm=self.mult_norm.data_ptr(),
+            mult_hits=self.mult_hits.data_ptr(), uniq_abund=self.uniq_abund.data_ptr(),
+            mult_abund=self.mult_abund.data_ptr(), hist=self.hist.data_ptr(), counters=self.counters.data_ptr())
+
+    def zero(self):
+        self.f64.zero_()
+        self.i64.zero_()
+
+
+class Result:
+    """Host copy of everything the reports need; attribute names follow the oracle's."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+class MatchOverflow(RuntimeError):
+    pass
+
+
+class AbundanceEngine:
+    """One engine per process/GPU.  ``comm`` is an optional torch.distributed process group: when
+    given, ``run`` treats ``reads`` as this rank's shard of the read groups."""
+
+    def __init__(self, graph: Graph, device="cuda:0", comm=None):
+        if not torch.cuda.is_available():
+            raise _lib.SfbError("no CUDA device: the abundance engine has no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        self.graph = graph
+        self.dg = DeviceGraph(graph, self.device)
+        self.comm = comm
+        self.acc = Accum(self.dg)
+        self.table = torch.empty((max(1, graph.n_paths), _lib.TABLE_COLS), dtype=torch.float64, device=self.device)
+        self.work = None
+        self.match_cap_hint = 0
+        self.launches = 0
+
+    # ---- stages (each is one kernel launch through the C ABI) -----------------------------
+    def _work_for(self, dr):
+        cap = max(self.match_cap_hint, 2 * dr.n_alns + 1024)
+        if self.work is None or self.work.n_groups < dr.n_groups or self.work.n_alns < dr.n_alns \
+                or self.work.match_cap < cap:
+            self.work = None
+            self.work = Work(dr.n_groups, dr.n_alns, cap, self.device)
+        return self.work
+
+    def match(self, dr, work):
+        _lib.check(self.lib.sfb_match(C.byref(self.dg.c), C.byref(dr.c), C.byref(work.c), C.byref(self.acc.c), _stream()))
+        self.launches += 1
+
+    def classify(self, dr, work):
+        _lib.check(self.lib.sfb_classify(C.byref(self.dg.c), C.byref(dr.c), C.byref(work.c), C.byref(self.acc.c), _stream()))
+        self.launches += 1
+
+    def pass1_scatter(self, dr, work):
+        _lib.check(self.lib.sfb_pass1_scatter(C.byref(self.dg.c), C.byref(dr.c), C.byref(work.c), C.byref(self.acc.c), _stream()))
+        self.launches += 1
+
+    def pass2(self, dr, work, uniq_global=None):
+        u = self.acc.uniq_reads if uniq_global is None else uniq_global
+        _lib.check(self.lib.sfb_pass2(C.byref(self.dg.c), C.byref(dr.c), C.byref(work.c), C.byref(self.acc.c),
+                                      C.c_void_p(u.data_ptr()), _stream()))
+        self.launches += 1
+
+    def path_reduce(self, p_begin=0, p_end=None):
+        p_end = self.graph.n_paths if p_end is None else p_end
+        out = self.table[p_begin:p_end]
+        _lib.check(self.lib.sfb_path_reduce(C.byref(self.dg.c), C.byref(self.acc.c), p_begin, p_end,
+                                            C.c_void_p(out.data_ptr()), _stream()))
+        self.launches += 1
+        return out
+
+    # ---- the abundance pass ----------------------------------------------------------------
+    def run_device(self, dr: DeviceReads):
+        """Whole pass on reads already resident in HBM; leaves results on the device."""
+        import torch.distributed as dist
+        work = self._work_for(dr)
+        work.reset()
+        self.acc.zero()
+        self.match(dr, work)
+        self.classify(dr, work)
+        self.pass1_scatter(dr, work)
+        uniq_global = None
+        if self.comm is not None:
+            uniq_global = self.acc.uniq_reads.clone()
+            dist.all_reduce(uniq_global, group=self.comm)          # exact integer sum over shards
+        self.pass2(dr, work, uniq_global)
+        if self.comm is not None:
+            dist.all_reduce(self.acc.i64, group=self.comm)
+            dist.all_reduce(self.acc.f64, group=self.comm)
+        self.path_reduce()
+        return work
+
+    def run(self, reads, keep_codes=True):
+        """Public entry: host arrays in, host results out (H2D and D2H included)."""
+        host = reads if isinstance(reads, HostReads) else HostReads(reads)
+        for _ in range(3):
+            dr = DeviceReads(host, self.device)
+            work = self.run_device(dr)
+            res = self.fetch(work, dr, keep_codes)
+            over = int(res.counters_raw[_lib.COUNTER_NAMES.index("MATCH_OVERFLOW")])
+            if over == 0:
+                return res
+            self.match_cap_hint = int(work.t["cursor"][0].item()) + 1024   # exact need, rerun
+        raise MatchOverflow("match buffer still too small after regrowing")
+
+    def fetch(self, work, dr, keep_codes=True):
+        acc, dg = self.acc, self.dg
+        torch.cuda.current_stream().synchronize()
+        f64 = acc.f64.cpu().numpy()
+        i64 = acc.i64.cpu().numpy()
+        P, n_slots = acc.P, acc.n_slots
+        sl = dg.slot_of_plain
+        counters_raw = i64[P + acc.n_hist:P + acc.n_hist + _lib.N_COUNTERS].copy()
+        res = Result(
+            g=self.graph.as_dict(),
+            uniq_reads=i64[0:P].copy(),
+            hist=i64[P:P + acc.n_hist].reshape(_lib.N_HIST, acc.S, _lib.N_BINS).copy(),
+            counters_raw=counters_raw,
+            C={k: int(v) for k, v in zip(_lib.COUNTER_NAMES, counters_raw)},
+            mult_hits=i64[P + acc.n_hist + _lib.N_COUNTERS:].view(np.int32)[:P].copy(),
+            uniq_norm=f64[0:P].copy(), mult_reads=f64[P:2 * P].copy(), mult_norm=f64[2 * P:3 * P].copy(),
+            uniq_abund=f64[3 * P:3 * P + n_slots][sl], mult_abund=f64[3 * P + n_slots:][sl],
+            table=self.table[:P].cpu().numpy() if P else np.zeros((0, _lib.TABLE_COLS)),
+            n_deferred=int(work.t["cursor"][1].item()), match_fill=int(work.t["cursor"][0].item()),
+        )
+        if keep_codes:
+            res.grp_code = work.t["grp_code"][:dr.n_groups].cpu().numpy()
+            res.grp_code2 = work.t["grp_code2"][:dr.n_groups].cpu().numpy()
+            res.aln_assign = work.t["aln_assign"][:dr.n_alns].cpu().numpy()
+            res.aln_match = work.t["aln_match"][:dr.n_alns].cpu().numpy().view(np.uint32)
+            res.match_buf = work.t["match_buf"][:min(work.match_cap, max(0, res.match_fill))].cpu().numpy()
+        check_errors(res.C)
+        return res
+
+
+def check_errors(Cn):
+    """Bug-compatible error behaviour: same exception classes as the reference."""
+    if Cn["BAD_BIN"]:
+        raise KeyError("alignment ratio outside [0, 1] used as histogram key (json2csv.py:335-339)")
+    if Cn["NO_PATH"]:
+        raise IndexError("list index out of range")          # nodes[...].traversed_path[0], json2csv.py:875
+    if Cn["NO_CLUSTER"]:
+        raise TypeError("list indices must be integers or slices, not NoneType")   # clusters[None], json2csv.py:884
+
+
+def decode_matches(res, a):
+    """Match list of alignment ``a`` as [(path id, position, reversed)] (test helper)."""
+    v = int(res.aln_match[a])
+    g = res.g
+    if v == _lib.MATCH_NONE:
+        return []
+    if v & _lib.MATCH_MULTI:
+        base = (v & 0x7FFFFFFF) * 2
+        codes = [int(c) & 0xFFFFFFFF for c in res.match_buf[base + 1:base + 1 + int(res.match_buf[base])]]
+    else:
+        codes = [v]
+    out = []
+    for c in codes:
+        slot = c & _lib.SLOT_MASK
+        # slot -> (pid, pos) in the sentinel layout: path p starts at path_off[p] + p
+        starts = g["path_off"][:-1] + np.arange(len(g["path_off"]) - 1)
+        pid = int(np.searchsorted(starts, slot, side="right") - 1)
+        out.append((pid, int(slot - starts[pid]), bool(c & _lib.MATCH_REV)))
+    return out
+
+
+def abundance_pass(graph: Graph, reads: Reads, device="cuda:0") -> Result:
+    """One-call public API: decoded alignments + graph in, per-path abundances and counters out."""
+    return AbundanceEngine(graph, device).run(reads)

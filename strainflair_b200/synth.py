@@ -1,0 +1,233 @@
+"""Seeded synthetic pangenomes and alignments, generated directly as arrays.
+
+Graph family: ``n_clusters`` gene clusters, each a bubble chain of ``chain_len`` positions (a position is
+one node, or two alleles with probability ``bubble_p``); each cluster carries a few haplotype paths that
+differ from a founder at few bubbles, identical haplotypes are merged (as the reference merges P lines
+with identical content, json2csv.py:260-266) and each path is carried by 1-3 of ``n_strains`` strains.
+
+Reads: pairs of ``read_len`` bp placed on a haplotype path by coordinate, so that a walk is a contiguous
+run of path nodes with partial coverage on its two end nodes; 50 % reversed; a share of mates below the
+score threshold (no retained alignment), with a second tied alignment on a sibling haplotype, with one
+node swapped to the other allele (recombinant), and a share of single-end groups.
+"""
+import numpy as np
+
+from .schema import Graph, Reads
+
+CONFIGS = {
+    # name: (graph kwargs, reads kwargs) -- C3/C4/C5 of BASELINE.json, plus small test sizes
+    "tiny": (dict(n_clusters=40, chain_len=12, hap_lo=1, hap_hi=5, n_strains=6, bubble_p=0.4, flip_p=0.3),
+             dict(n_pairs=2000, read_len=60)),
+    "small": (dict(n_clusters=400, chain_len=40, hap_lo=1, hap_hi=8, n_strains=16, bubble_p=0.3, flip_p=0.15),
+              dict(n_pairs=50_000, read_len=150)),
+    "c3": (dict(n_clusters=10_000, chain_len=150, hap_lo=2, hap_hi=9, n_strains=64, bubble_p=0.33, flip_p=0.08),
+           dict(n_pairs=25_000_000, read_len=150)),
+    "c4": (dict(n_clusters=3_125, chain_len=150, hap_lo=16, hap_hi=16, n_strains=64, bubble_p=0.33, flip_p=0.006),
+           dict(n_pairs=25_000_000, read_len=150)),
+    "c5": (dict(n_clusters=100_000, chain_len=150, hap_lo=2, hap_hi=9, n_strains=64, bubble_p=0.33, flip_p=0.08),
+           dict(n_pairs=83_000_000, read_len=150)),
+}
+SEED0 = 20261019
+
+
+def make_graph(seed, n_clusters, chain_len=150, hap_lo=1, hap_hi=8, n_strains=64, bubble_p=0.3, flip_p=0.1,
+               max_node_len=63):
+    rng = np.random.default_rng(seed)
+    C, K, S = n_clusters, chain_len, n_strains
+    bubble = rng.random((C, K)) < bubble_p
+    width = 1 + bubble.astype(np.int64)
+    base = np.cumsum(width.reshape(-1)) - width.reshape(-1)          # node index of allele 0 at (c, k)
+    base = base.reshape(C, K)
+    n_nodes = int(width.sum())
+    node_len = rng.integers(1, max_node_len + 1, n_nodes).astype(np.int32)
+    n_hap = rng.integers(hap_lo, hap_hi + 1, C)
+    owner = np.repeat(np.arange(C), n_hap)                            # cluster of each raw haplotype
+    founder = (rng.random((C, K)) < 0.5) & bubble
+    flips = (rng.random((len(owner), K)) < flip_p) & bubble[owner]
+    allele = founder[owner] ^ flips
+    # merge identical haplotypes inside a cluster, keep first-seen order
+    key = np.concatenate([owner[:, None].astype(np.uint32).view(np.uint8).reshape(len(owner), 4),
+                          np.packbits(allele, axis=1)], axis=1)
+    _, first = np.unique(key, axis=0, return_index=True)
+    first.sort()
+    owner, allele = owner[first], allele[first]
+    P = len(owner)
+    path_nodes = (base[owner] + allele).astype(np.int32).reshape(-1)
+    path_off = np.arange(P + 1, dtype=np.int64) * K
+    seq_len = node_len[path_nodes].reshape(P, K).sum(axis=1).astype(np.int64)
+    # strains per path: 1..3 distinct ids, copy count 1 (2 with p = 0.02)
+    n_s = 1 + (rng.random(P) < 0.3) + (rng.random(P) < 0.1)
+    n_s = np.minimum(n_s, S)
+    s0 = rng.integers(0, S, P)
+    d1 = rng.integers(1, max(2, S // 2), P)
+    d2 = rng.integers(1, max(2, S // 2), P)
+    cand = np.stack([s0, (s0 + d1) % S, (s0 + d1 + d2) % S], axis=1)
+    if S < 4:                                                         # tiny strain sets: dedupe by construction
+        n_s = np.minimum(n_s, 1 + (S > 1))
+        cand[:, 1] = (s0 + 1) % S
+    take = np.arange(3)[None, :] < n_s[:, None]
+    pstr_id = cand[take].astype(np.int32)
+    pstr_off = np.concatenate(([0], np.cumsum(n_s))).astype(np.int64)
+    pstr_cnt = (1 + (rng.random(len(pstr_id)) < 0.02)).astype(np.int32)
+    # clusters: one gene per (path, strain, copy) -> the path id repeats in the cluster list (json2csv.py:317)
+    genes_per_path = np.add.reduceat(pstr_cnt, pstr_off[:-1]) if P else np.zeros(0, np.int64)
+    clu_paths = np.repeat(np.arange(P, dtype=np.int32), genes_per_path)
+    per_cluster = np.bincount(owner, weights=genes_per_path, minlength=C).astype(np.int64)
+    clu_off = np.concatenate(([0], np.cumsum(per_cluster))).astype(np.int64)
+    # header = strains in order of first appearance as the FIRST strain of a path (species_names, :268)
+    firsts = pstr_id[pstr_off[:-1]]
+    _, idx = np.unique(firsts, return_index=True)
+    header = [int(s) for s in firsts[np.sort(idx)]]
+    g = Graph(
+        node_ids=np.arange(1, n_nodes + 1, dtype=np.int64), node_len=node_len, path_off=path_off,
+        path_nodes=path_nodes, path_seq_len=seq_len, pstr_off=pstr_off, pstr_id=pstr_id, pstr_cnt=pstr_cnt,
+        path_cluster=owner.astype(np.int32), clu_off=clu_off, clu_paths=clu_paths,
+        strain_names=[f"NC_{100000 + i}.1" for i in range(S)], header_strains=header, path_names=None,
+        node_index=None,
+    )
+    g.chain_len = K
+    g.base = base
+    g.allele = allele
+    g.bubble = bubble
+    g.on_path = np.zeros(n_nodes, bool)
+    g.on_path[path_nodes] = True
+    return g
+
+
+def _python_round_bins(values):
+    """Histogram bin (Python round(x, 2) * 100) of each value, through the few distinct values."""
+    uniq, inv = np.unique(values, return_inverse=True)
+    table = np.array([int(round(round(float(v), 2) * 100)) if 0 <= round(float(v), 2) <= 1 else 255 for v in uniq],
+                     np.uint8)
+    return table[inv]
+
+
+def make_reads(graph, seed, n_pairs, read_len=150, p_same_path=0.95, p_low_score=0.03, p_tie=0.10,
+               p_recomb=0.01, p_single=0.02, p_exc=0.0, chunk=2_000_000):
+    """Returns Reads for ``n_pairs`` read groups (a ``p_single`` share of them single-end)."""
+    rng = np.random.default_rng(seed)
+    K = graph.chain_len
+    P = graph.n_paths
+    plen = graph.node_len[graph.path_nodes].reshape(P, K).astype(np.int64)
+    cum = np.zeros((P, K + 1), np.int64)
+    np.cumsum(plen, axis=1, out=cum[:, 1:])
+    seq_len = cum[:, -1]
+    BIG = int(seq_len.max()) + 1
+    flat_cum = (cum[:, :-1] + np.arange(P)[:, None] * BIG).reshape(-1)   # start coordinate of every path node
+    # siblings: paths of the same cluster are contiguous
+    clu = graph.path_cluster.astype(np.int64)
+    clu_first = np.searchsorted(clu, clu, side="left")
+    clu_size = np.searchsorted(clu, clu, side="right") - clu_first
+    parts = []
+    for g0 in range(0, n_pairs, chunk):
+        parts.append(_reads_chunk(graph, rng, min(chunk, n_pairs - g0), read_len, p_same_path, p_low_score, p_tie,
+                                  p_recomb, p_single, K, P, cum, seq_len, BIG, flat_cum, clu_first, clu_size))
+    out = _concat(parts)
+    if p_exc > 0 and len(out["walk_alen"]):
+        # a few records whose coverage is given as an explicit fp64 (merged-node case, json2csv.py:576-577)
+        n_exc = max(1, int(len(out["walk_alen"]) * p_exc))
+        pick = rng.choice(len(out["walk_alen"]), n_exc, replace=False)
+        out["exc_cov"] = rng.random(n_exc) * 1.5
+        out["walk_alen"][pick] = -(np.arange(n_exc, dtype=np.int32) + 1)
+    return Reads(**out, mate_names=None)
+
+
+def _reads_chunk(graph, rng, G, read_len, p_same, p_low, p_tie, p_recomb, p_single, K, P, cum, seq_len, BIG,
+                 flat_cum, clu_first, clu_size):
+    nm = np.where(rng.random(G) < p_single, 1, 2).astype(np.uint8)
+    # mate table: 2 per group, second masked out for singles
+    p1 = rng.integers(0, P, G)
+    same = rng.random(G) < p_same
+    p2 = np.where(same, p1, rng.integers(0, P, G))
+    path = np.stack([p1, p2], axis=1).reshape(-1)
+    room = np.maximum(seq_len[path] - read_len, 0)
+    x = (rng.random(2 * G) * (room + 1)).astype(np.int64)
+    x = np.minimum(x, room)
+    # mate 2 near mate 1 when on the same path (insert of 0..300 bp)
+    x1 = x[0::2]
+    near = np.minimum(x1 + rng.integers(0, 300, G), room[1::2])
+    x[1::2] = np.where(same, near, x[1::2])
+    present = np.ones(2 * G, bool)
+    present[1::2] = nm == 2
+    low = rng.random(2 * G) < p_low
+    n_aln = np.where(present & ~low, 1 + (rng.random(2 * G) < p_tie), 0).astype(np.int64)
+    # alignment table
+    mate_of = np.repeat(np.arange(2 * G), n_aln)
+    A = len(mate_of)
+    is_tie = np.zeros(A, bool)
+    starts = np.cumsum(n_aln) - n_aln
+    second = starts[n_aln == 2] + 1
+    is_tie[second] = True
+    ap = path[mate_of]
+    # tied alignment: same coordinates on a sibling haplotype of the cluster
+    sib = clu_first[ap] + (rng.integers(0, 1 << 30, A) % clu_size[ap])
+    ap = np.where(is_tie, sib, ap)
+    ax = np.minimum(x[mate_of], np.maximum(seq_len[ap] - read_len, 0))
+    rl = np.minimum(read_len, seq_len[ap])
+    s = np.searchsorted(flat_cum, ax + ap * BIG, side="right") - 1 - ap * K
+    e = np.searchsorted(flat_cum, ax + rl - 1 + ap * BIG, side="right") - 1 - ap * K
+    L = (e - s + 1).astype(np.int64)
+    woff = np.concatenate(([0], np.cumsum(L)))
+    R = int(woff[-1])
+    j = np.arange(R, dtype=np.int64) - np.repeat(woff[:-1], L)         # position inside the walk
+    a_of = np.repeat(np.arange(A), L)
+    k = s[a_of] + j                                                    # chain position
+    node = graph.path_nodes[ap[a_of] * K + k].astype(np.int32)
+    n_lo = cum[ap[a_of], k]
+    n_hi = cum[ap[a_of], k + 1]
+    alen = (np.minimum(n_hi, (ax + rl)[a_of]) - np.maximum(n_lo, ax[a_of])).astype(np.int32)
+    # recombinant: swap one node to the other allele where the position is a bubble
+    rec = rng.random(A) < p_recomb
+    jr = (rng.integers(0, 1 << 30, A) % L)
+    hit = rec[a_of] & (j == jr[a_of])
+    cl = graph.path_cluster[ap[a_of]]
+    is_b = graph.bubble[cl, k]
+    alt = graph.base[cl, k] + (1 - graph.allele[ap[a_of], k].astype(np.int64))
+    alt = np.where(is_b, alt, node)
+    swap = hit & is_b & graph.on_path[alt]       # a node no path crosses is an IndexError in the reference (Q10)
+    node = np.where(swap, alt, node).astype(np.int32)
+    # orientation: reverse the record order of half of the walks
+    rev = rng.random(A) < 0.5
+    src = np.where(rev[a_of], woff[:-1][a_of] + (L[a_of] - 1 - j), np.arange(R))
+    node, alen = node[src], alen[src]
+    # error ratios -> histogram bins
+    n_sub = rng.choice(np.array([0, 0, 0, 0, 1], np.int64), A)
+    rlA = rl.astype(np.float64)
+    stats = np.stack([(rlA - 5 * n_sub) / rlA, (rlA - n_sub) / rlA, n_sub / rlA, np.zeros(A), n_sub / rlA], axis=1)
+    bins = np.stack([_python_round_bins(stats[:, c]) for c in range(5)], axis=1)
+    grp_aln_off = np.concatenate(([0], np.cumsum(n_aln))).astype(np.int64)
+    return dict(
+        grp_nmates=nm, grp_aln_off=grp_aln_off, mate_seq_len=np.where(present, read_len, 0).astype(np.int32),
+        aln_walk_off=woff.astype(np.int64), aln_read_len=rl.astype(np.int32), aln_bins=bins,
+        walk_node=node, walk_alen=alen, exc_cov=np.zeros(0, np.float64),
+    )
+
+
+def _concat(parts):
+    if len(parts) == 1:
+        return parts[0]
+    out = {}
+    a_base = r_base = 0
+    offs_g, offs_a = [np.zeros(1, np.int64)], [np.zeros(1, np.int64)]
+    for p in parts:
+        offs_g.append(p["grp_aln_off"][1:] + a_base)
+        offs_a.append(p["aln_walk_off"][1:] + r_base)
+        a_base += int(p["grp_aln_off"][-1])
+        r_base += int(p["aln_walk_off"][-1])
+    out["grp_aln_off"] = np.concatenate(offs_g)
+    out["aln_walk_off"] = np.concatenate(offs_a)
+    for k in ("grp_nmates", "mate_seq_len", "aln_read_len", "aln_bins", "walk_node", "walk_alen", "exc_cov"):
+        out[k] = np.concatenate([p[k] for p in parts])
+    return out
+
+
+def make_config(name, scale=1.0, seed=None):
+    """Graph + reads of a named configuration; ``scale`` shrinks the number of pairs (bounded CPU samples)."""
+    gkw, rkw = CONFIGS[name]
+    idx = list(CONFIGS).index(name)
+    seed = SEED0 + idx if seed is None else seed
+    graph = make_graph(seed, **gkw)
+    rkw = dict(rkw)
+    rkw["n_pairs"] = max(1, int(rkw["n_pairs"] * scale))
+    reads = make_reads(graph, seed + 1000, **rkw)
+    return graph, reads

@@ -1,0 +1,159 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle on the same seeded inputs."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import compare
+from oracle import abundance as oa
+from oracle import decode as od
+from oracle import graph as og
+from oracle import report as orp
+from strainflair_b200 import engine, synth
+from strainflair_b200.schema import Graph, Reads
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def slot_to_plain(res, code):
+    """sentinel-layout match code -> plain slot (path_off[pid] + pos), like the oracle's aln_assign"""
+    g = res.g
+    slot = code & 0x3FFFFFFF
+    starts = g["path_off"][:-1] + np.arange(len(g["path_off"]) - 1)
+    pid = np.searchsorted(starts, slot, side="right") - 1
+    return slot - pid
+
+
+def check_against_oracle(graph, reads, res, orc, rel=compare.REL):
+    for k in oa.COUNTERS:
+        assert res.C[k] == orc.C[k], (k, res.C[k], orc.C[k])
+    assert np.array_equal(res.grp_code, orc.grp_code)
+    assert np.array_equal(res.grp_code2, orc.grp_code2)
+    assert np.array_equal(res.uniq_reads, np.asarray(orc.uniq_reads, np.int64))
+    assert np.array_equal(res.hist, orc.hist)
+    assert res.n_deferred == len(orc.deferred)
+    # unique assignments: same alignment, same start slot
+    mine = np.where(res.aln_assign >= 0, slot_to_plain(res, res.aln_assign.astype(np.int64)), -1)
+    assert np.array_equal(mine, orc.aln_assign)
+    # recorded unassigned reads
+    book = sorted((g, m) for g, m, _ in orc.book)
+    got = []
+    for g_ in np.flatnonzero(((res.grp_code & 15) == oa.UNASSIGNED_BOOK) | ((res.grp_code >> 4) == oa.UNASSIGNED_BOOK)):
+        for m in range(2):
+            if (int(res.grp_code[g_]) >> (4 * m)) & 15 == oa.UNASSIGNED_BOOK:
+                got.append((int(g_), m))
+    assert got == book
+    for g_, m, c in orc.book:
+        a = int(reads.grp_aln_off[2 * g_ + m])
+        assert -(int(res.aln_assign[a]) + 2) == c
+    for name in ("uniq_norm", "mult_reads", "mult_norm", "uniq_abund", "mult_abund"):
+        a = np.asarray(getattr(res, name), np.float64)
+        b = np.asarray(getattr(orc, name), np.float64)
+        assert a.shape == b.shape, name
+        err = np.abs(a - b)
+        tol = rel * np.maximum(np.abs(a), np.abs(b))
+        bad = np.flatnonzero(err > tol)
+        assert bad.size == 0, (name, bad[:5], a[bad[:5]], b[bad[:5]])
+    # zero pattern must be identical (decides the nz means and ratio_covered_nodes)
+    assert np.array_equal(res.uniq_abund > 0, orc.uniq_abund > 0)
+    assert np.array_equal(res.mult_abund > 0, orc.mult_abund > 0)
+    assert np.array_equal(res.mult_hits > 0, np.array([not isinstance(v, int) for v in orc.mult_reads]))
+    rows = orp.gene_rows(orc)
+    cols = ("nb_uniq_mapped_normalized", "nb_multimapped", "nb_multimapped_normalized", "mean_abund_uniq",
+            "mean_abund_uniq_nz", "mean_abund_multiple", "mean_abund_multiple_nz", "ratio_covered_nodes")
+    for p, row in enumerate(rows):
+        for k, c in enumerate(cols):
+            assert compare.close(res.table[p, k], row[c], rel), (p, c, res.table[p, k], row[c])
+
+
+@pytest.mark.parametrize("name,scale", [("tiny", 1.0), ("small", 0.2)])
+def test_synthetic_matches_oracle(name, scale):
+    need_gpu()
+    graph, reads = synth.make_config(name, scale=scale)
+    res = engine.abundance_pass(graph, reads)
+    orc = oa.AbundanceOracle(graph.as_dict(), reads.as_dict()).run()
+    check_against_oracle(graph, reads, res, orc)
+
+
+def test_explicit_coverage_records():
+    need_gpu()
+    gkw, rkw = synth.CONFIGS["tiny"]
+    graph = synth.make_graph(7, **gkw)
+    reads = synth.make_reads(graph, 8, n_pairs=3000, read_len=60, p_exc=0.05)
+    res = engine.abundance_pass(graph, reads)
+    orc = oa.AbundanceOracle(graph.as_dict(), reads.as_dict()).run()
+    check_against_oracle(graph, reads, res, orc)
+
+
+def test_match_lists_equal_oracle():
+    need_gpu()
+    graph, reads = synth.make_config("tiny")
+    res = engine.abundance_pass(graph, reads)
+    orc = oa.AbundanceOracle(graph.as_dict(), reads.as_dict())
+    for a in range(reads.n_alns):
+        mine = engine.decode_matches(res, a)
+        assert [(p, pos) for p, pos, _ in mine] == orc.match(a), a
+        # forward matches first, then reverse
+        flags = [rv for _, _, rv in mine]
+        assert flags == sorted(flags)
+
+
+def test_match_buffer_regrows():
+    need_gpu()
+    graph, reads = synth.make_config("tiny")
+    eng = engine.AbundanceEngine(graph)
+    eng._work_for = lambda dr, _orig=eng._work_for: _small_work(eng, dr)
+    res = eng.run(reads)
+    orc = oa.AbundanceOracle(graph.as_dict(), reads.as_dict()).run()
+    check_against_oracle(graph, reads, res, orc)
+
+
+def _small_work(eng, dr):
+    cap = max(eng.match_cap_hint, 16)
+    if eng.work is None or eng.work.match_cap < cap or eng.work.n_alns < dr.n_alns:
+        eng.work = engine.Work(dr.n_groups, dr.n_alns, cap, eng.device)
+    return eng.work
+
+
+@pytest.mark.parametrize("d", sorted(glob.glob(os.path.join(HERE, "golden", "case_*"))), ids=os.path.basename)
+def test_golden_cases_through_cuda(d):
+    """The reference's own outputs (tests/golden) reproduced by the CUDA path: ints exact, fp64 <= 1e-9."""
+    need_gpu()
+    with open(os.path.join(d, "expected.json")) as fh:
+        exp = json.load(fh)
+    g = og.load_graph(os.path.join(d, "graph.gfa"), os.path.join(d, "dict_clusters.pickle"))
+    r = od.decode_json(os.path.join(d, "reads.json"), g, exp["params"]["thr"])
+    graph, reads = Graph.from_dict(g), Reads.from_dict(r)
+    res = engine.abundance_pass(graph, reads)
+    compare.check_state_vs_reference(res, exp, exact=False)
+
+
+def test_empty_and_degenerate_inputs():
+    need_gpu()
+    graph, reads = synth.make_config("tiny")
+    empty = reads.slice_groups(0, 0)
+    res = engine.abundance_pass(graph, empty)
+    assert res.C["NB_READS"] == 0 and not res.uniq_abund.any()
+    one = reads.slice_groups(5, 6)
+    res = engine.abundance_pass(graph, one)
+    orc = oa.AbundanceOracle(graph.as_dict(), one.as_dict()).run()
+    check_against_oracle(graph, one, res, orc)
+
+
+def test_error_quirks_raise_like_reference():
+    need_gpu()
+    graph, reads = synth.make_config("tiny")
+    bad = Reads.from_dict(reads.as_dict())
+    bad.aln_bins = bad.aln_bins.copy()
+    bad.aln_bins[:, 0] = 255
+    with pytest.raises(KeyError):
+        engine.abundance_pass(graph, bad)
