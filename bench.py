@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""Benchmark of the abundance pass (BASELINE.json metric: aligned reads/s through the abundance pass,
+plus % of the HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c3] [--impl ours|reference]
+
+One process per GPU (torchrun for N > 1).  A step is one full abundance pass
+(match -> classify -> pass-1 scatter -> [allreduce] -> pass 2 -> [allreduce] -> path reduce) over this rank's
+shard of the synthetic workload; every rank holds a full-size shard (weak scaling).  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "aligned_reads_per_s_abundance_pass"
+UNIT = "reads/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="c3", help="synthetic workload (strainflair_b200/synth.py CONFIGS)")
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the config's read pairs per rank")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample-pairs", type=int, default=160_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(args):
+    from strainflair_b200 import synth
+    gkw, rkw = synth.CONFIGS[args.config]
+    pairs = int(rkw["n_pairs"] * args.scale)
+    return (f"{args.config}: synthetic {pairs} read pairs/GPU ({rkw['read_len']} bp) over a "
+            f"{gkw['n_clusters']}-cluster x {gkw['chain_len']}-position bubble-chain pangenome, {gkw['n_strains']} strains")
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (the reference is Python and cannot travel to the GPU box)
+# ------------------------------------------------------------------------------------------------
+def cpu_port_rate(graph_d, reads_d, cores, repeats=1):
+    """Times the oracle's abundance pass (decode excluded, like the GPU arm) on ``cores`` processes.
+    Returns (reads/s, records/s, seconds per pass)."""
+    from oracle import abundance as oa
+    from oracle import parallel as op
+    n_reads = int(reads_d["grp_nmates"].sum())
+    n_rec = len(reads_d["walk_node"])
+    best = None
+    if cores <= 1:
+        idx = oa.AbundanceOracle.build_index(graph_d)
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            oa.AbundanceOracle(graph_d, reads_d, index=idx).run()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    else:
+        po = op.ParallelOracle(graph_d, reads_d, cores=cores)
+        try:
+            for _ in range(repeats):
+                t0 = time.perf_counter()
+                po.run()
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+        finally:
+            po.close()
+    return n_reads / best, n_rec / best, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from strainflair_b200 import synth
+    gkw, rkw = synth.CONFIGS[args.config]
+    idx = list(synth.CONFIGS).index(args.config)
+    graph = synth.make_graph(synth.SEED0 + idx, **gkw)
+    cores = len(os.sched_getaffinity(0))
+    pairs = min(args.cpu_sample_pairs, int(rkw["n_pairs"] * args.scale))
+    reads = synth.make_reads(graph, synth.SEED0 + idx + 1000, n_pairs=pairs, read_len=rkw["read_len"])
+    gd, rd = graph.as_dict(), reads.as_dict()
+    from oracle import abundance as oa
+    from oracle import parallel as op
+    n_reads = int(rd["grp_nmates"].sum())
+    po = op.ParallelOracle(gd, rd, cores=cores) if cores > 1 else None
+    index = oa.AbundanceOracle.build_index(gd)
+
+    def step():
+        if po is not None:
+            po.run()
+        else:
+            oa.AbundanceOracle(gd, rd, index=index).run()
+
+    try:
+        for _ in range(args.warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        dt = time.perf_counter() - t0
+    finally:
+        if po is not None:
+            po.close()
+    value = n_reads * args.steps / dt
+    sample = f"first {pairs} read pairs of the workload per step, oracle port (Python), decode excluded"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32/f64", "data": "synthetic",
+        "config": {"workload": workload_name(args)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "records_per_s": len(rd["walk_node"]) * args.steps / dt,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from strainflair_b200 import synth
+    gkw, rkw = synth.CONFIGS[args.config]
+    idx = list(synth.CONFIGS).index(args.config)
+    graph = synth.make_graph(synth.SEED0 + idx, **gkw)
+    pairs = max(1, int(rkw["n_pairs"] * args.scale))
+
+    # CPU baseline first (forks workers; do it before CUDA is initialised)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = len(os.sched_getaffinity(0))
+        sp = min(args.cpu_sample_pairs, pairs)
+        sample = synth.make_reads(graph, synth.SEED0 + idx + 1000, n_pairs=sp, read_len=rkw["read_len"])
+        rate, rec_rate, secs = cpu_port_rate(graph.as_dict(), sample.as_dict(), cores)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "records_per_s": rec_rate,
+               "sample": f"first {sp} read pairs of the workload, oracle port (Python) sharded over {cores} processes, "
+                         f"decode excluded, {secs:.1f} s"}
+        del sample
+
+    import torch
+    import torch.distributed as dist
+    from strainflair_b200 import _lib, engine, roofline
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    comm = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+        comm = dist.group.WORLD
+
+    t_gen = time.perf_counter()
+    reads = synth.make_reads(graph, synth.SEED0 + idx + 1000 + 7919 * rank, n_pairs=pairs, read_len=rkw["read_len"])
+    t_gen = time.perf_counter() - t_gen
+    eng = engine.AbundanceEngine(graph, device, comm=comm)
+    host = engine.HostReads(reads, pin=True)
+    dr = engine.DeviceReads(host, device)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    # warm-up (also settles the match-buffer capacity)
+    for _ in range(max(args.warmup, 1)):
+        work = eng.run_device(dr)
+        torch.cuda.synchronize()
+        over = int(eng.acc.counters[_lib.COUNTER_NAMES.index("MATCH_OVERFLOW")].item())
+        if over:
+            eng.match_cap_hint = int(work.t["cursor"][0].item()) + 1024
+    stats = eng.fetch(work, dr, keep_codes=False)
+    assert stats.C["MATCH_OVERFLOW"] == 0
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = eng.launches
+    marks_all = []
+    barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        marks = []
+        eng.run_device(dr, marks)
+        marks_all.append(marks)
+    ev1.record()
+    torch.cuda.synchronize()
+    barrier()
+    sampler.stop_flag = True
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launches - launches0
+    # per-stage device time (CUDA events on the launching stream)
+    stage_ms = {}
+    for marks in marks_all:
+        for (_, e_prev), (name, e) in zip(marks[:-1], marks[1:]):
+            stage_ms[name] = stage_ms.get(name, 0.0) + e_prev.elapsed_time(e) / args.steps
+
+    n_reads = stats.C["NB_READS"] if world == 1 else None
+    local_reads = int(reads.grp_nmates.sum())
+    tot = torch.tensor([ms, float(local_reads), float(reads.n_records), float(reads.n_alns)], dtype=torch.float64, device=device)
+    if world > 1:
+        mx = tot.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        ms = float(mx[0].item())
+    total_reads, total_records, total_alns = float(tot[1].item()), float(tot[2].item()), float(tot[3].item())
+    value = total_reads * args.steps / (ms * 1e-3)
+
+    # end to end: pinned host buffers -> device -> kernels -> results on the host, every step
+    e2e = None
+    if not args.no_e2e:
+        eng.run(host, keep_codes=False)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res = eng.run(host, keep_codes=False)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        d2h = eng.acc.f64.numel() * 8 + eng.acc.i64.numel() * 8 + eng.table.numel() * 8 + 16
+        e2e = {"value": total_reads * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": host.nbytes(),
+               "d2h_bytes_per_step": d2h, "ms_per_step": dt / args.steps * 1e3}
+
+    if rank == 0:
+        by = roofline.kernel_bytes(reads.n_groups, reads.n_alns, reads.n_records, graph.n_paths, eng.dg.n_slots,
+                                   stats.C, stats.match_fill, stats.n_deferred, graph.n_strains)
+        kernels = {k: v for k, v in stage_ms.items() if k in by}
+        top = max(kernels, key=kernels.get)
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                peaks = json.load(fh)
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = by[top] / (kernels[top] * 1e-3) / 1e9
+        whole = by["total"] / (sum(kernels.values()) * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32/f64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "l2": "inputs (GBs of walk arrays) exceed the 126 MB L2",
+                       "parallelism": f"read groups sharded over {world} GPU(s), graph replicated",
+                       "groups_per_gpu": reads.n_groups, "alignments_per_gpu": reads.n_alns,
+                       "records_per_gpu": reads.n_records, "paths": graph.n_paths, "nodes": graph.n_nodes,
+                       "slots": eng.dg.n_slots, "deferred_groups": stats.n_deferred,
+                       "mean_candidates_per_alignment": stats.C["ST_CAND"] / max(1, reads.n_alns),
+                       "mean_matches_per_alignment": stats.C["ST_TUPLES"] / max(1, reads.n_alns)},
+            "records_per_s": total_records * args.steps / (ms * 1e-3),
+            "alignments_per_s": total_alns * args.steps / (ms * 1e-3),
+            "gpu_launches": launches,
+            "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
+            "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
+                         "algorithmic_bytes": by[top], "kernel_ms": kernels[top],
+                         "whole_pass": {"achieved": whole, "frac": whole / peak, "algorithmic_bytes": by["total"]},
+                         "per_kernel": {k: {"ms": round(kernels[k], 4), "GBps": by[k] / (kernels[k] * 1e-3) / 1e9,
+                                            "frac": by[k] / (kernels[k] * 1e-3) / 1e9 / peak} for k in kernels}},
+            "clocks": sampler.summary(),
+            "e2e": e2e,
+            "cpu_baseline": cpu,
+            "gen_seconds": round(t_gen, 1),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

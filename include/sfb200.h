@@ -81,7 +81,15 @@ enum {
     SFB_C_MATCH_OVERFLOW, /* ints of match_buf that did not fit; grow match_cap and rerun          */
     SFB_C_NO_PATH,        /* unassigned walk starts on a node no path crosses: IndexError (Q10)    */
     SFB_C_NO_CLUSTER,     /* unassigned read recorded in cluster None: TypeError (Q10)             */
-    SFB_N_COUNTERS = 24
+    /* work statistics (feed the roofline arithmetic of bench.py; not part of the reference) */
+    SFB_C_ST_CAND,        /* match: candidate occurrences tested                                   */
+    SFB_C_ST_COMPARES,    /* match: path-node compares executed                                    */
+    SFB_C_ST_TUPLES,      /* match: (path, position) matches found                                 */
+    SFB_C_ST_P1_RECORDS,  /* pass 1: alignment-node records added to uniq_abund                    */
+    SFB_C_ST_P2_APPLIED,  /* pass 2: (read, candidate path) redistributions                        */
+    SFB_C_ST_P2_RECORDS,  /* pass 2: alignment-node records added to mult_abund                    */
+    SFB_C_ST_HIST,        /* histogram updates (reads on single-strain paths)                      */
+    SFB_N_COUNTERS = 32
 };
 #define SFB_N_HIST 5          /* mappingscore, identityscore, subst, indel, errors (json2csv.py:335-339) */
 #define SFB_N_BINS 101

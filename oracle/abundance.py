@@ -36,7 +36,18 @@ class _Mate:
 
 
 class AbundanceOracle:
-    def __init__(self, graph, reads):
+    @staticmethod
+    def build_index(graph):
+        """node -> slots where it occurs, ascending (== ascending pid, then position); the array form of
+        Node.traversed_path + the position scan of json2csv.py:352-357.  Reusable across read shards."""
+        path_nodes, path_off = graph["path_nodes"], graph["path_off"]
+        P = len(path_off) - 1
+        order = np.argsort(path_nodes, kind="stable")
+        cnt = np.bincount(path_nodes, minlength=len(graph["node_len"]))
+        return dict(occ_off=np.concatenate(([0], np.cumsum(cnt))).astype(np.int64), occ_slot=order.astype(np.int64),
+                    slot_pid=np.repeat(np.arange(P, dtype=np.int64), np.diff(path_off)))
+
+    def __init__(self, graph, reads, index=None):
         self.g = graph
         self.r = reads
         g = graph
@@ -46,13 +57,8 @@ class AbundanceOracle:
         self.P, self.T, self.S = P, T, S
         self.path_off = g["path_off"]
         self.path_nodes = g["path_nodes"]
-        # node -> slots where it occurs, ascending (== ascending pid, then position)
-        order = np.argsort(self.path_nodes, kind="stable")
-        Nn = len(g["node_len"])
-        cnt = np.bincount(self.path_nodes, minlength=Nn)
-        self.occ_off = np.concatenate(([0], np.cumsum(cnt))).astype(np.int64)
-        self.occ_slot = order.astype(np.int64)
-        self.slot_pid = np.repeat(np.arange(P, dtype=np.int64), np.diff(self.path_off))
+        index = self.build_index(g) if index is None else index
+        self.occ_off, self.occ_slot, self.slot_pid = index["occ_off"], index["occ_slot"], index["slot_pid"]
         # accumulators
         self.uniq_reads = [0] * P
         self.uniq_norm = [0] * P

@@ -53,8 +53,9 @@ COUNTER_NAMES = (
     "NB_READS", "PAIRS", "SINGLES", "FILTERED", "UNASSIGNED", "ASSIGNED_U", "ASSIGNED_M", "INCONSIST", "INCONSIST_M",
     "MULTI_ALIGN", "SE", "SAME_CP", "DIFF_CP", "ONE_NOALIGN", "ONE_NOCP", "AMBIG_CP_RESOLVED", "AMBIG_RESOLVED",
     "AMBIG_REDUCED", "SE_M", "SECOND_PASS", "BAD_BIN", "MATCH_OVERFLOW", "NO_PATH", "NO_CLUSTER",
+    "ST_CAND", "ST_COMPARES", "ST_TUPLES", "ST_P1_RECORDS", "ST_P2_APPLIED", "ST_P2_RECORDS", "ST_HIST",
 )
-N_COUNTERS = 24
+N_COUNTERS = 32
 N_HIST, N_BINS, TABLE_COLS = 5, 101, 8
 SLOT_MASK, MATCH_REV, MATCH_MULTI, MATCH_NONE = 0x3FFFFFFF, 0x40000000, 0x80000000, 0xFFFFFFFF
 MAX_SLOTS = 0x3FFFFFFF

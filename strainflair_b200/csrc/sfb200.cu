@@ -36,17 +36,24 @@ int check_launch(const char* what) {
 // =============================================================================================
 constexpr int kMatchLocal = 8;   // matches kept in registers before spilling to a second sweep
 
+struct MatchStats {
+    int cand, cmp;
+};
+
 template <bool kEmit>
 __device__ __forceinline__ int match_sweep(const sfb_graph& g, const sfb_reads& r, i64 w0, int L, uint32_t* keep,
-                                           int32_t* out) {
+                                           int32_t* out, MatchStats& st) {
     int n = 0;
     const int first = r.walk_node[w0];
     // forward: occurrences of walk[0], then compare walk[1..]
     for (int o = g.occ_off[first], oe = g.occ_off[first + 1]; o < oe; ++o) {
         const int s = g.occ_slot[o];
         bool ok = true;
-        for (int i = 1; i < L; ++i)
+        int i = 1;
+        for (; i < L; ++i)
             if (g.slot_node[s + i] != r.walk_node[w0 + i]) { ok = false; break; }   // sentinel (-1) stops overruns
+        st.cand += 1;
+        st.cmp += min(i, L - 1);
         if (ok) {
             if (kEmit) out[n] = s; else if (n < kMatchLocal) keep[n] = (uint32_t)s;
             ++n;
@@ -57,8 +64,11 @@ __device__ __forceinline__ int match_sweep(const sfb_graph& g, const sfb_reads& 
         for (int o = g.occ_off[last], oe = g.occ_off[last + 1]; o < oe; ++o) {
             const int s = g.occ_slot[o];
             bool ok = true;
-            for (int i = 1; i < L; ++i)
+            int i = 1;
+            for (; i < L; ++i)
                 if (g.slot_node[s + i] != r.walk_node[w0 + L - 1 - i]) { ok = false; break; }
+            st.cand += 1;
+            st.cmp += min(i, L - 1);
             if (ok) {
                 const uint32_t code = (uint32_t)s | SFB_MATCH_REV;
                 if (kEmit) out[n] = (int32_t)code; else if (n < kMatchLocal) keep[n] = code;
@@ -70,51 +80,75 @@ __device__ __forceinline__ int match_sweep(const sfb_graph& g, const sfb_reads& 
 }
 
 __global__ void __launch_bounds__(256) k_match(sfb_graph g, sfb_reads r, sfb_work w, long long* counters) {
-    const i64 a = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = a < r.n_alns;
-    uint32_t keep[kMatchLocal];
-    int n = 0, L = 0;
-    i64 w0 = 0;
-    if (live) {
-        w0 = r.aln_walk_off[a];
-        L = (int)(r.aln_walk_off[a + 1] - w0);
-        if (L > 0) n = match_sweep<false>(g, r, w0, L, keep, nullptr);
-    }
-    // warp-aggregated claim of match_buf space: [count, codes...] padded to an even number of ints
-    const unsigned need = n > 1 ? (unsigned)((n + 2) & ~1) : 0u;
-    unsigned incl = need;
+    __shared__ BlockCounters sc;
+    block_counters_zero(sc);
+    __syncthreads();
+    MatchStats st{0, 0};
+    int tuples = 0;
+    const i64 n_round = (r.n_alns + 255) & ~(i64)255;
+    for (i64 a = (i64)blockIdx.x * blockDim.x + threadIdx.x; a < n_round; a += (i64)gridDim.x * blockDim.x) {
+        const bool live = a < r.n_alns;
+        uint32_t keep[kMatchLocal];
+        int n = 0, L = 0;
+        i64 w0 = 0;
+        if (live) {
+            w0 = r.aln_walk_off[a];
+            L = (int)(r.aln_walk_off[a + 1] - w0);
+            if (L > 0) n = match_sweep<false>(g, r, w0, L, keep, nullptr, st);
+            tuples += n;
+        }
+        // warp-aggregated claim of match_buf space: [count, codes...] padded to an even number of ints
+        const unsigned need = n > 1 ? (unsigned)((n + 2) & ~1) : 0u;
+        unsigned incl = need;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane_id() >= d) incl += t;
-    }
-    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-    u64 base = 0;
-    if (total) {
-        if (lane_id() == 31) base = atomicAdd(w.cursor, (u64)total);
-        base = __shfl_sync(0xffffffffu, base, 31);
-    }
-    if (!live) return;
-    if (n == 0) {
-        w.aln_match[a] = SFB_MATCH_NONE;
-    } else if (n == 1) {
-        w.aln_match[a] = keep[0];
-    } else {
-        const u64 pos = base + (incl - need);
-        if (pos + need <= (u64)w.match_cap) {
-            int32_t* out = w.match_buf + pos;
-            out[0] = n;
-            if (n <= kMatchLocal) {
-                for (int k = 0; k < n; ++k) out[1 + k] = (int32_t)keep[k];
-            } else {
-                match_sweep<true>(g, r, w0, L, nullptr, out + 1);
-            }
-            w.aln_match[a] = SFB_MATCH_MULTI | (uint32_t)(pos >> 1);
-        } else {
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane_id() >= d) incl += t;
+        }
+        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+        u64 base = 0;
+        if (total) {
+            if (lane_id() == 31) base = atomicAdd(w.cursor, (u64)total);
+            base = __shfl_sync(0xffffffffu, base, 31);
+        }
+        if (!live) continue;
+        if (n == 0) {
             w.aln_match[a] = SFB_MATCH_NONE;
-            atomicAdd((u64*)&counters[SFB_C_MATCH_OVERFLOW], (u64)need);
+        } else if (n == 1) {
+            w.aln_match[a] = keep[0];
+        } else {
+            const u64 pos = base + (incl - need);
+            if (pos + need <= (u64)w.match_cap) {
+                int32_t* out = w.match_buf + pos;
+                out[0] = n;
+                if (n <= kMatchLocal) {
+                    for (int k = 0; k < n; ++k) out[1 + k] = (int32_t)keep[k];
+                } else {
+                    MatchStats scratch{0, 0};
+                    match_sweep<true>(g, r, w0, L, nullptr, out + 1, scratch);
+                }
+                w.aln_match[a] = SFB_MATCH_MULTI | (uint32_t)(pos >> 1);
+            } else {
+                w.aln_match[a] = SFB_MATCH_NONE;
+                SFB_COUNT(sc, SFB_C_MATCH_OVERFLOW, (int)need);
+            }
         }
     }
+    // statistics: warp tree, then one shared-memory add per warp, one global add per block
+    int c0 = st.cand, c1 = st.cmp, c2 = tuples;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        c0 += __shfl_xor_sync(0xffffffffu, c0, d);
+        c1 += __shfl_xor_sync(0xffffffffu, c1, d);
+        c2 += __shfl_xor_sync(0xffffffffu, c2, d);
+    }
+    if (lane_id() == 0) {
+        SFB_COUNT(sc, SFB_C_ST_CAND, c0);
+        SFB_COUNT(sc, SFB_C_ST_COMPARES, c1);
+        SFB_COUNT(sc, SFB_C_ST_TUPLES, c2);
+    }
+    __syncthreads();
+    block_counters_flush(sc, counters);
 }
 
 // =============================================================================================
@@ -130,6 +164,7 @@ struct Dev {
 __device__ __forceinline__ void hist_add(const Dev& d, BlockCounters& sc, int pid, i64 a) {
     if (d.g.path_nstrain[pid] != 1) return;                       // json2csv.py:333 / :1246
     const int s = d.g.path_strain0[pid];
+    SFB_COUNT(sc, SFB_C_ST_HIST, 1);
     for (int k = 0; k < SFB_N_HIST; ++k) {
         const int b = d.r.aln_bins[a * SFB_N_HIST + k];
         if (b >= SFB_N_BINS) { SFB_COUNT(sc, SFB_C_BAD_BIN, 1); continue; }
@@ -212,7 +247,8 @@ __global__ void __launch_bounds__(128) k_classify(Dev d) {
     __shared__ BlockCounters sc;
     block_counters_zero(sc);
     __syncthreads();
-    const i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const i64 n_round = (d.r.n_groups + 127) & ~(i64)127;
+    for (i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x; g < n_round; g += (i64)gridDim.x * blockDim.x) {
     bool defer = false;
     if (g < d.r.n_groups) {
         const int nm = d.r.grp_nmates[g];
@@ -361,6 +397,7 @@ __global__ void __launch_bounds__(128) k_classify(Dev d) {
         base = __shfl_sync(0xffffffffu, base, leader);
         if (defer) d.w.deferred[base + __popc(ballot & ((1u << lane_id()) - 1))] = (int32_t)g;
     }
+    }
     __syncthreads();
     block_counters_flush(sc, d.acc.counters);
 }
@@ -370,10 +407,16 @@ __global__ void __launch_bounds__(128) k_classify(Dev d) {
 // =============================================================================================
 constexpr int kTileAlns = 256;
 
-__global__ void __launch_bounds__(256) k_pass1_scatter(sfb_graph g, sfb_reads r, sfb_work w, double* uniq_abund) {
+__global__ void __launch_bounds__(256) k_pass1_scatter(sfb_graph g, sfb_reads r, sfb_work w, double* uniq_abund,
+                                                       long long* counters) {
     __shared__ int s_off[kTileAlns + 1];
     __shared__ int32_t s_code[kTileAlns];
-    const i64 a_lo = (i64)blockIdx.x * kTileAlns;
+    __shared__ int s_done;
+    if (threadIdx.x == 0) s_done = 0;
+    __syncthreads();
+    int done = 0;
+    for (i64 tile = blockIdx.x; tile * kTileAlns < r.n_alns; tile += gridDim.x) {
+    const i64 a_lo = tile * kTileAlns;
     const int na = (int)min((i64)kTileAlns, r.n_alns - a_lo);
     const i64 r_lo = r.aln_walk_off[a_lo];
     for (int j = threadIdx.x; j <= na; j += blockDim.x) s_off[j] = (int)(r.aln_walk_off[a_lo + j] - r_lo);
@@ -392,7 +435,15 @@ __global__ void __launch_bounds__(256) k_pass1_scatter(sfb_graph g, sfb_reads r,
         const int L = s_off[lo + 1] - s_off[lo];
         const double cov = record_cov(g, r, r_lo + k, (uint32_t)code, i, L);
         atomicAdd(&uniq_abund[((uint32_t)code & SFB_SLOT_MASK) + i], cov);
+        ++done;
     }
+    __syncthreads();
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) done += __shfl_xor_sync(0xffffffffu, done, d);
+    if (lane_id() == 0 && done) atomicAdd(&s_done, done);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_done) atomicAdd((u64*)&counters[SFB_C_ST_P1_RECORDS], (u64)s_done);
 }
 
 // =============================================================================================
@@ -400,8 +451,8 @@ __global__ void __launch_bounds__(256) k_pass1_scatter(sfb_graph g, sfb_reads r,
 // =============================================================================================
 // json2csv.py:1155-1158 (and :1207-1210, :1265-1268); `times` > 1 when the strain reduction
 // duplicated the candidate (Q4): the reference adds the same terms `times` times.
-__device__ __forceinline__ void apply_multi(const Dev& d, i64 a, uint32_t code, int pid, int seq_len, double ratio,
-                                            int times) {
+__device__ __forceinline__ void apply_multi(const Dev& d, BlockCounters& sc, i64 a, uint32_t code, int pid,
+                                            int seq_len, double ratio, int times) {
     const double tr = ratio * (double)times;
     atomicAdd(&d.acc.mult_reads[pid], tr);
     atomicAdd(&d.acc.mult_norm[pid], (ratio * (double)seq_len / (double)d.g.path_seq_len[pid]) * (double)times);
@@ -411,6 +462,8 @@ __device__ __forceinline__ void apply_multi(const Dev& d, i64 a, uint32_t code, 
     const uint32_t slot0 = code & SFB_SLOT_MASK;
     for (int i = 0; i < L; ++i)
         atomicAdd(&d.acc.mult_abund[slot0 + i], (record_cov(d.g, d.r, w0 + i, code, i, L) * ratio) * (double)times);
+    SFB_COUNT(sc, SFB_C_ST_P2_APPLIED, 1);
+    SFB_COUNT(sc, SFB_C_ST_P2_RECORDS, L);
 }
 
 __device__ __forceinline__ double ratio_of(long long u, long long total, int n) {
@@ -433,7 +486,7 @@ __device__ __forceinline__ int pass2_single(const Dev& d, BlockCounters& sc, con
         for (int k = 0; k < n; ++k) {
             const uint32_t c = match_get(d.w, a, k);
             const int p = d.g.slot_path[c & SFB_SLOT_MASK];
-            apply_multi(d, a, c, p, mt.seq_len, ratio_of(U[p], total, n), 1);
+            apply_multi(d, sc, a, c, p, mt.seq_len, ratio_of(U[p], total, n), 1);
         }
     }
     if (hit) {
@@ -496,7 +549,7 @@ __global__ void __launch_bounds__(128) k_pass2(Dev d, const long long* __restric
                             code[k] = SFB_P2_ASSIGNED;
                             for_tuples(d.g, d.w, mt[k], [&](int, uint32_t c, int p, int aloc) {
                                 if (count_pid(d.g, d.w, mt[1 - k], p) > 0)
-                                    apply_multi(d, mt[k].a0 + aloc, c, p, mt[k].seq_len, ratio_of(U[p], total, n_inter), 1);
+                                    apply_multi(d, sc, mt[k].a0 + aloc, c, p, mt[k].seq_len, ratio_of(U[p], total, n_inter), 1);
                                 return true;
                             });
                         }
@@ -528,7 +581,7 @@ __global__ void __launch_bounds__(128) k_pass2(Dev d, const long long* __restric
                                 for_tuples(d.g, d.w, mt[k], [&](int, uint32_t c, int p, int aloc) {
                                     const int times = strain_mult(d, mt, p);
                                     if (times)
-                                        apply_multi(d, mt[k].a0 + aloc, c, p, mt[k].seq_len, ratio_of(U[p], tot, nn), times);
+                                        apply_multi(d, sc, mt[k].a0 + aloc, c, p, mt[k].seq_len, ratio_of(U[p], tot, nn), times);
                                     return true;
                                 });
                             }
@@ -807,6 +860,7 @@ static int check_accum(const sfb_accum* a) {
     } while (0)
 
 static inline unsigned blocks_for(i64 n, int per) { return (unsigned)((n + per - 1) / per); }
+constexpr int kSMs = 148;   // B200: persistent grids are sized in multiples of the SM count
 
 extern "C" {
 
@@ -820,7 +874,8 @@ int sfb_match(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_accum* ac
     SFB_TRY(check_work(w));
     SFB_TRY(check_accum(acc));
     if (r->n_alns == 0) return SFB_OK;
-    k_match<<<blocks_for(r->n_alns, 256), 256, 0, (cudaStream_t)stream>>>(*g, *r, *w, acc->counters);
+    const unsigned grid = (unsigned)min((i64)kSMs * 8, (i64)blocks_for(r->n_alns, 256));
+    k_match<<<grid, 256, 0, (cudaStream_t)stream>>>(*g, *r, *w, acc->counters);
     return check_launch("k_match");
 }
 
@@ -831,7 +886,8 @@ int sfb_classify(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_accum*
     SFB_TRY(check_accum(acc));
     if (r->n_groups == 0) return SFB_OK;
     Dev d{*g, *r, *w, *acc};
-    k_classify<<<blocks_for(r->n_groups, 128), 128, 0, (cudaStream_t)stream>>>(d);
+    const unsigned grid = (unsigned)min((i64)kSMs * 16, (i64)blocks_for(r->n_groups, 128));
+    k_classify<<<grid, 128, 0, (cudaStream_t)stream>>>(d);
     return check_launch("k_classify");
 }
 
@@ -841,7 +897,8 @@ int sfb_pass1_scatter(const sfb_graph* g, const sfb_reads* r, const sfb_work* w,
     SFB_TRY(check_work(w));
     SFB_TRY(check_accum(acc));
     if (r->n_alns == 0) return SFB_OK;
-    k_pass1_scatter<<<blocks_for(r->n_alns, kTileAlns), 256, 0, (cudaStream_t)stream>>>(*g, *r, *w, acc->uniq_abund);
+    const unsigned grid = (unsigned)min((i64)kSMs * 8, (i64)blocks_for(r->n_alns, kTileAlns));
+    k_pass1_scatter<<<grid, 256, 0, (cudaStream_t)stream>>>(*g, *r, *w, acc->uniq_abund, acc->counters);
     return check_launch("k_pass1_scatter");
 }
 
@@ -854,7 +911,7 @@ int sfb_pass2(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_accum* ac
     SFB_REQUIRE(uniq_reads_global, "uniq_reads_global is null");
     if (r->n_groups == 0) return SFB_OK;
     Dev d{*g, *r, *w, *acc};
-    const unsigned grid = (unsigned)min((i64)148 * 16, (i64)blocks_for(r->n_groups, 128));
+    const unsigned grid = (unsigned)min((i64)kSMs * 16, (i64)blocks_for(r->n_groups, 128));
     k_pass2<<<grid, 128, 0, (cudaStream_t)stream>>>(d, uniq_reads_global);
     return check_launch("k_pass2");
 }

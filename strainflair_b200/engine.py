@@ -16,10 +16,6 @@ from . import _lib
 from .schema import Graph, Reads
 
 
-def _ptr(t):
-    return C.c_void_p(t.data_ptr() if t is not None and t.numel() else (t.data_ptr() if t is not None else 0))
-
-
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -233,24 +229,41 @@ class AbundanceEngine:
         return out
 
     # ---- the abundance pass ----------------------------------------------------------------
-    def run_device(self, dr: DeviceReads):
-        """Whole pass on reads already resident in HBM; leaves results on the device."""
+    def run_device(self, dr: DeviceReads, marks=None):
+        """Whole pass on reads already resident in HBM; leaves results on the device.
+        ``marks``: optional list that receives (stage name, CUDA event recorded after the stage)."""
         import torch.distributed as dist
+
+        def mark(name):
+            if marks is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append((name, ev))
+
         work = self._work_for(dr)
+        mark("start")
         work.reset()
         self.acc.zero()
+        mark("zero")
         self.match(dr, work)
+        mark("match")
         self.classify(dr, work)
+        mark("classify")
         self.pass1_scatter(dr, work)
+        mark("pass1_scatter")
         uniq_global = None
         if self.comm is not None:
             uniq_global = self.acc.uniq_reads.clone()
             dist.all_reduce(uniq_global, group=self.comm)          # exact integer sum over shards
+            mark("allreduce_uniq")
         self.pass2(dr, work, uniq_global)
+        mark("pass2")
         if self.comm is not None:
             dist.all_reduce(self.acc.i64, group=self.comm)
             dist.all_reduce(self.acc.f64, group=self.comm)
+            mark("allreduce_accum")
         self.path_reduce()
+        mark("path_reduce")
         return work
 
     def run(self, reads, keep_codes=True):

@@ -103,7 +103,7 @@ def _python_round_bins(values):
 
 
 def make_reads(graph, seed, n_pairs, read_len=150, p_same_path=0.95, p_low_score=0.03, p_tie=0.10,
-               p_recomb=0.01, p_single=0.02, p_exc=0.0, chunk=2_000_000):
+               p_recomb=0.01, p_single=0.02, p_exc=0.0, chunk=1_000_000, threads=8):
     """Returns Reads for ``n_pairs`` read groups (a ``p_single`` share of them single-end)."""
     rng = np.random.default_rng(seed)
     K = graph.chain_len
@@ -118,10 +118,20 @@ def make_reads(graph, seed, n_pairs, read_len=150, p_same_path=0.95, p_low_score
     clu = graph.path_cluster.astype(np.int64)
     clu_first = np.searchsorted(clu, clu, side="left")
     clu_size = np.searchsorted(clu, clu, side="right") - clu_first
-    parts = []
-    for g0 in range(0, n_pairs, chunk):
-        parts.append(_reads_chunk(graph, rng, min(chunk, n_pairs - g0), read_len, p_same_path, p_low_score, p_tie,
-                                  p_recomb, p_single, K, P, cum, seq_len, BIG, flat_cum, clu_first, clu_size))
+    # every chunk has its own generator (seed, chunk index): the result does not depend on the thread count
+    starts = list(range(0, n_pairs, chunk))
+
+    def one(ci):
+        crng = np.random.default_rng([seed, ci])
+        return _reads_chunk(graph, crng, min(chunk, n_pairs - starts[ci]), read_len, p_same_path, p_low_score,
+                            p_tie, p_recomb, p_single, K, P, cum, seq_len, BIG, flat_cum, clu_first, clu_size)
+
+    if len(starts) > 1 and threads > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            parts = list(ex.map(one, range(len(starts))))
+    else:
+        parts = [one(ci) for ci in range(len(starts))]
     out = _concat(parts)
     if p_exc > 0 and len(out["walk_alen"]):
         # a few records whose coverage is given as an explicit fp64 (merged-node case, json2csv.py:576-577)
