@@ -212,12 +212,15 @@ def run_ours(args):
             dist.barrier()
 
     # warm-up (also settles the match-buffer capacity)
-    for _ in range(max(args.warmup, 1)):
+    done = 0
+    while done < max(args.warmup, 1):
         work = eng.run_device(dr)
         torch.cuda.synchronize()
         over = int(eng.acc.counters[_lib.COUNTER_NAMES.index("MATCH_OVERFLOW")].item())
-        if over:
+        if over:                              # grow the match buffer to the exact need; not a warm-up step
             eng.match_cap_hint = int(work.t["cursor"][0].item()) + 1024
+            continue
+        done += 1
     stats = eng.fetch(work, dr, keep_codes=False)
     assert stats.C["MATCH_OVERFLOW"] == 0
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SFB_ABI_VERSION 1
+#define SFB_ABI_VERSION 2
 
 /* ---- status codes ---------------------------------------------------- */
 #define SFB_OK            0
@@ -36,16 +36,15 @@ extern "C" {
 #define SFB_E_CUDA       -2   /* a CUDA runtime call or launch failed           */
 
 /* ---- encodings --------------------------------------------------------- */
-/* A match (json2csv.py:341-363 returns (path_id, position)) is one 32-bit code:
- *   bits 0..29  slot = path_off[path_id] + position in the sentinel layout
- *   bit  30     the reversed walk matched (json2csv.py:862), not the walk itself
- * aln_match[a] holds, per retained alignment a:
- *   SFB_MATCH_NONE                no colored path matches
- *   bit 31 clear                  exactly one match, stored inline
- *   bit 31 set                    several: (v & 0x7fffffff)*2 indexes match_buf,
- *                                 where [0] = count n and [1..n] = the codes in
- *                                 the reference's order (forward matches by
- *                                 ascending path id / position, then reverse) */
+/* A match (json2csv.py:341-363 returns (path_id, position)) is a pair of 32-bit words (code, path id):
+ *   code bits 0..29  slot = path_off[path_id] + position in the sentinel layout
+ *   code bit  30     the reversed walk matched (json2csv.py:862), not the walk itself
+ * aln_match holds one pair (x, y) per retained alignment:
+ *   x == SFB_MATCH_NONE           no colored path matches
+ *   x bit 31 clear                exactly one match: x = code, y = path id
+ *   x bit 31 set                  y matches, stored as consecutive (code, path id) pairs of match_buf
+ *                                 starting at pair index (x & 0x7fffffff), in the reference's order
+ *                                 (forward matches by ascending path id / position, then reverse) */
 #define SFB_SLOT_MASK    0x3fffffffu
 #define SFB_MATCH_REV    0x40000000u
 #define SFB_MATCH_MULTI  0x80000000u
@@ -78,7 +77,7 @@ enum {
     SFB_C_DIFF_CP, SFB_C_ONE_NOALIGN, SFB_C_ONE_NOCP, SFB_C_AMBIG_CP_RESOLVED, SFB_C_AMBIG_RESOLVED,
     SFB_C_AMBIG_REDUCED, SFB_C_SE_M, SFB_C_SECOND_PASS,
     SFB_C_BAD_BIN,        /* histogram key outside [0,1] was needed: the reference raises KeyError (Q7) */
-    SFB_C_MATCH_OVERFLOW, /* ints of match_buf that did not fit; grow match_cap and rerun          */
+    SFB_C_MATCH_OVERFLOW, /* match_buf pairs / app_buf items that did not fit; grow the buffer and rerun */
     SFB_C_NO_PATH,        /* unassigned walk starts on a node no path crosses: IndexError (Q10)    */
     SFB_C_NO_CLUSTER,     /* unassigned read recorded in cluster None: TypeError (Q10)             */
     /* work statistics (feed the roofline arithmetic of bench.py; not part of the reference) */
@@ -129,16 +128,21 @@ typedef struct sfb_reads {
 
 /* ---- per-shard work arrays (outputs of match / classify) ----------------- */
 typedef struct sfb_work {
-    uint32_t* aln_match;          /* [A]   see encodings                                      */
-    int32_t*  match_buf;          /* [match_cap]                                              */
-    int64_t   match_cap;          /* ints; < 2^32                                             */
-    unsigned long long* cursor;   /* [2]   [0] match_buf fill (ints), [1] number of deferred groups; zero before sfb_match */
+    uint32_t* aln_match;          /* [2A]  one (x, y) pair per alignment, see encodings (8-byte aligned) */
+    int32_t*  match_buf;          /* [2*match_cap] (code, path id) pairs (8-byte aligned)     */
+    int64_t   match_cap;          /* pairs; < 2^31                                            */
+    unsigned long long* cursor;   /* [4]   [0] match_buf fill (pairs), [1] deferred groups, [2] app_buf fill;
+                                           zero before sfb_match                              */
     uint8_t*  grp_code;           /* [G]                                                      */
     uint8_t*  grp_code2;          /* [G]   zero before sfb_pass2                              */
     int32_t*  aln_assign;         /* [A]   >= 0: match code of the unique assignment (:945,:958,:996);
                                            -1: none; <= -2: first alignment of a mate recorded as
                                            unassigned in cluster -(v+2) (:884,:903,:1037)      */
     int32_t*  deferred;           /* [G]   group ids going to pass 2 (unordered)              */
+    void*     app_buf;            /* [app_cap] 16-byte pass-2 work items {int32 alignment, uint32 code, double
+                                           share}: scratch between the two kernels of sfb_pass2; the number
+                                           of matches of a shard (<= A + match_cap) always suffices     */
+    int64_t   app_cap;
 } sfb_work;
 
 /* ---- accumulators (Path counters, json2csv.py:113-118, and histograms) ---- */

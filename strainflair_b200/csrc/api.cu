@@ -1,0 +1,145 @@
+// C ABI of libsfb200.so (include/sfb200.h): argument checks and kernel launches.  No allocation, no
+// synchronisation, no global mutable state (the last-error string is thread-local).
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace sfb {
+
+static thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(SFB_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    return SFB_OK;
+}
+
+int launch_match(const sfb_graph*, const sfb_reads*, sfb_work*, sfb_accum*, cudaStream_t);
+int launch_classify(const Dev&, cudaStream_t);
+int launch_pass2_resolve(const Dev&, const long long*, cudaStream_t);
+int launch_pass1_scatter(const sfb_graph*, const sfb_reads*, const sfb_work*, sfb_accum*, cudaStream_t);
+int launch_pass2_scatter(const sfb_graph*, const sfb_reads*, const sfb_work*, sfb_accum*, cudaStream_t);
+int launch_path_reduce(const sfb_graph*, const sfb_accum*, i64, i64, double*, cudaStream_t);
+int launch_cluster_counts(i64, i64, const int32_t*, const int32_t*, const int32_t*, const int32_t*, const int32_t*,
+                          long long*, cudaStream_t);
+int launch_strain_aggregate(i64, i64, const int32_t*, const int32_t*, const double*, const double*, const double*,
+                            const double*, double, int32_t*, double*, double*, double*, cudaStream_t);
+
+static int check_graph(const sfb_graph* g) {
+    SFB_REQUIRE(g, "graph is null");
+    SFB_REQUIRE(g->n_nodes >= 0 && g->n_paths >= 0 && g->n_slots >= 0 && g->n_strains >= 0, "negative size");
+    SFB_REQUIRE(g->n_slots <= SFB_MAX_SLOTS, "n_slots exceeds 2^30-1");
+    SFB_REQUIRE(g->mask_words >= 1 && g->mask_words * 64 >= g->n_strains, "mask_words too small");
+    SFB_REQUIRE(g->slot_node && g->slot_len && g->slot_path && g->path_off && g->occ_off && g->occ_slot &&
+                    g->path_seq_len && g->path_nstrain && g->path_strain0 && g->path_smask && g->path_cluster,
+                "null graph array");
+    return SFB_OK;
+}
+static int check_reads(const sfb_reads* r) {
+    SFB_REQUIRE(r, "reads is null");
+    SFB_REQUIRE(r->n_groups >= 0 && r->n_alns >= 0 && r->n_records >= 0 && r->n_exc >= 0, "negative size");
+    SFB_REQUIRE(r->n_groups < 0x7fffffffLL && r->n_alns < 0x7fffffffLL, "more than 2^31-1 groups/alignments in one shard");
+    SFB_REQUIRE(r->grp_aln_off && r->aln_walk_off, "null reads array");
+    SFB_REQUIRE(r->n_groups == 0 || (r->grp_nmates && r->mate_seq_len), "null reads array");
+    SFB_REQUIRE(r->n_alns == 0 || (r->aln_bins && r->walk_node && r->walk_alen), "null reads array");
+    SFB_REQUIRE(r->n_exc == 0 || r->exc_cov, "exc_cov is null");
+    return SFB_OK;
+}
+static int check_work(const sfb_work* w) {
+    SFB_REQUIRE(w, "work is null");
+    SFB_REQUIRE(w->aln_match && w->cursor && w->grp_code && w->grp_code2 && w->aln_assign && w->deferred,
+                "null work array");
+    SFB_REQUIRE(w->match_cap >= 0 && w->match_cap < 0x7fffffffLL && (w->match_cap == 0 || w->match_buf),
+                "bad match buffer");
+    SFB_REQUIRE(w->app_cap >= 0 && (w->app_cap == 0 || w->app_buf), "bad application buffer");
+    return SFB_OK;
+}
+static int check_accum(const sfb_accum* a) {
+    SFB_REQUIRE(a, "accum is null");
+    SFB_REQUIRE(a->uniq_reads && a->uniq_norm && a->mult_reads && a->mult_norm && a->mult_hits && a->uniq_abund &&
+                    a->mult_abund && a->hist && a->counters,
+                "null accumulator");
+    return SFB_OK;
+}
+static int check_all(const sfb_graph* g, const sfb_reads* r, const sfb_work* w, const sfb_accum* a) {
+    SFB_TRY(check_graph(g));
+    SFB_TRY(check_reads(r));
+    SFB_TRY(check_work(w));
+    return check_accum(a);
+}
+
+}  // namespace sfb
+
+using namespace sfb;
+
+extern "C" {
+
+int sfb_abi_version(void) { return SFB_ABI_VERSION; }
+const char* sfb_version(void) { return "sfb200 0.2 (sm_100a)"; }
+const char* sfb_last_error(void) { return g_err; }
+
+int sfb_match(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_accum* acc, void* stream) {
+    SFB_TRY(check_all(g, r, w, acc));
+    return launch_match(g, r, w, acc, (cudaStream_t)stream);
+}
+
+int sfb_classify(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_accum* acc, void* stream) {
+    SFB_TRY(check_all(g, r, w, acc));
+    Dev d{*g, *r, *w, *acc};
+    return launch_classify(d, (cudaStream_t)stream);
+}
+
+int sfb_pass1_scatter(const sfb_graph* g, const sfb_reads* r, const sfb_work* w, sfb_accum* acc, void* stream) {
+    SFB_TRY(check_all(g, r, w, acc));
+    return launch_pass1_scatter(g, r, w, acc, (cudaStream_t)stream);
+}
+
+int sfb_pass2(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_accum* acc, const long long* uniq_reads_global,
+              void* stream) {
+    SFB_TRY(check_all(g, r, w, acc));
+    SFB_REQUIRE(uniq_reads_global, "uniq_reads_global is null");
+    Dev d{*g, *r, *w, *acc};
+    SFB_TRY(launch_pass2_resolve(d, uniq_reads_global, (cudaStream_t)stream));
+    return launch_pass2_scatter(g, r, w, acc, (cudaStream_t)stream);
+}
+
+int sfb_path_reduce(const sfb_graph* g, const sfb_accum* acc, int64_t p_begin, int64_t p_end, double* table,
+                    void* stream) {
+    SFB_TRY(check_graph(g));
+    SFB_TRY(check_accum(acc));
+    SFB_REQUIRE(0 <= p_begin && p_begin <= p_end && p_end <= g->n_paths, "bad path range");
+    SFB_REQUIRE(table || p_begin == p_end, "table is null");
+    return launch_path_reduce(g, acc, p_begin, p_end, table, (cudaStream_t)stream);
+}
+
+int sfb_cluster_strain_counts(int64_t n_clusters, int64_t n_strains, const int32_t* clu_off, const int32_t* clu_paths,
+                              const int32_t* pstr_off, const int32_t* pstr_id, const int32_t* pstr_cnt, long long* out,
+                              void* stream) {
+    SFB_REQUIRE(n_clusters >= 0 && n_strains >= 0, "negative size");
+    if (n_clusters == 0 || n_strains == 0) return SFB_OK;
+    SFB_REQUIRE(clu_off && clu_paths && pstr_off && pstr_id && pstr_cnt && out, "null array");
+    return launch_cluster_counts(n_clusters, n_strains, clu_off, clu_paths, pstr_off, pstr_id, pstr_cnt, out,
+                                 (cudaStream_t)stream);
+}
+
+int sfb_strain_aggregate(int64_t n_rows, int64_t n_strains, const int32_t* row_off, const int32_t* row_strain,
+                         const double* row_count, const double* mam, const double* mam_nz, const double* ratio_cov,
+                         double thr, int32_t* ws_rows, double* ws_vals, double* ws_counts, double* out, void* stream) {
+    SFB_REQUIRE(n_rows >= 0 && n_strains >= 0, "negative size");
+    if (n_strains == 0) return SFB_OK;
+    SFB_REQUIRE(out && ws_counts, "null output");
+    SFB_REQUIRE(n_rows == 0 || (row_off && row_strain && row_count && mam && mam_nz && ratio_cov && ws_rows && ws_vals),
+                "null array");
+    return launch_strain_aggregate(n_rows, n_strains, row_off, row_strain, row_count, mam, mam_nz, ratio_cov, thr,
+                                   ws_rows, ws_vals, ws_counts, out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

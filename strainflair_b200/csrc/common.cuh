@@ -13,99 +13,63 @@ typedef unsigned long long u64;
 int fail(int code, const char* fmt, ...);
 int check_launch(const char* what);
 
-#define SFB_REQUIRE(cond, msg)                                        \
-    do {                                                              \
+#define SFB_REQUIRE(cond, msg)                                               \
+    do {                                                                     \
         if (!(cond)) return ::sfb::fail(SFB_E_ARG, "%s: %s", __func__, msg); \
+    } while (0)
+#define SFB_TRY(x)                     \
+    do {                               \
+        int rc_ = (x);                 \
+        if (rc_ != SFB_OK) return rc_; \
     } while (0)
 
 constexpr int kWarp = 32;
+constexpr int kSMs = 148;   // B200: persistent grids are sized in multiples of the SM count
+
+static inline unsigned blocks_for(i64 n, int per) { return (unsigned)((n + per - 1) / per); }
+
+struct Dev {
+    sfb_graph g;
+    sfb_reads r;
+    sfb_work w;
+    sfb_accum acc;
+};
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
-// ---- match list accessors (encoding in sfb200.h) ---------------------------
-__device__ __forceinline__ int match_count(const sfb_work& w, i64 a) {
-    const uint32_t v = w.aln_match[a];
-    if (v == SFB_MATCH_NONE) return 0;
-    if (!(v & SFB_MATCH_MULTI)) return 1;
-    return w.match_buf[(size_t)(v & 0x7fffffffu) * 2];
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
 }
-__device__ __forceinline__ uint32_t match_get(const sfb_work& w, i64 a, int k) {
-    const uint32_t v = w.aln_match[a];
-    if (!(v & SFB_MATCH_MULTI)) return v;
-    return (uint32_t)w.match_buf[(size_t)(v & 0x7fffffffu) * 2 + 1 + k];
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
 }
-
-// Coverage of walk record `rec` (position i of an L-node walk matched at `code`):
-// aligned bases / node length, the node being the path node the walk position maps to
-// (the reversed walk reads the path backwards), json2csv.py:574.
-__device__ __forceinline__ double record_cov(const sfb_graph& g, const sfb_reads& r, i64 rec, uint32_t code,
-                                             int i, int L) {
-    const int alen = r.walk_alen[rec];
-    if (alen < 0) return r.exc_cov[-(i64)alen - 1];
-    const uint32_t slot0 = code & SFB_SLOT_MASK;
-    const uint32_t s = (code & SFB_MATCH_REV) ? slot0 + (uint32_t)(L - 1 - i) : slot0 + (uint32_t)i;
-    return (double)alen / (double)g.slot_len[s];
-}
-
-// A mate of a read group: its retained alignments [a0, a0+na) and the total number of
-// (path, position) match tuples over them ("colored_match", json2csv.py:851-866).
-struct Mate {
-    i64 a0;
-    int na;
-    int nt;
-    int seq_len;
-    int m;   // mate slot inside the group
-};
-
-__device__ __forceinline__ void mate_load(const sfb_reads& r, const sfb_work& w, i64 g, int m, Mate& out) {
-    out.m = m;
-    out.a0 = r.grp_aln_off[2 * g + m];
-    out.na = (int)(r.grp_aln_off[2 * g + m + 1] - out.a0);
-    out.seq_len = r.mate_seq_len[2 * g + m];
-    out.nt = 0;
-}
-__device__ __forceinline__ void mate_count_tuples(const sfb_work& w, Mate& mt) {
-    int n = 0;
-    for (int j = 0; j < mt.na; ++j) n += match_count(w, mt.a0 + j);
-    mt.nt = n;
-}
-
-// Visit tuples in colored_match order: f(index, code, path id, local alignment index); stop when f returns false.
-template <class F>
-__device__ __forceinline__ void for_tuples(const sfb_graph& g, const sfb_work& w, const Mate& mt, F f) {
-    int idx = 0;
-    for (int j = 0; j < mt.na; ++j) {
-        const int c = match_count(w, mt.a0 + j);
-        for (int k = 0; k < c; ++k, ++idx) {
-            const uint32_t code = match_get(w, mt.a0 + j, k);
-            if (!f(idx, code, g.slot_path[code & SFB_SLOT_MASK], j)) return;
-        }
+// inclusive prefix sum over the warp
+__device__ __forceinline__ unsigned warp_scan(unsigned v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane_id() >= d) v += t;
     }
+    return v;
 }
-// list_path_id.count(pid) (json2csv.py:932)
-__device__ __forceinline__ int count_pid(const sfb_graph& g, const sfb_work& w, const Mate& mt, int pid) {
-    int n = 0;
-    for_tuples(g, w, mt, [&](int, uint32_t, int p, int) { n += (p == pid); return true; });
-    return n;
-}
-// true iff no tuple before index i carries pid
-__device__ __forceinline__ bool first_of_pid(const sfb_graph& g, const sfb_work& w, const Mate& mt, int i, int pid) {
-    bool first = true;
-    for_tuples(g, w, mt, [&](int j, uint32_t, int p, int) {
-        if (j >= i) return false;
-        if (p == pid) { first = false; return false; }
-        return true;
-    });
-    return first;
+// Reserve `need` items per lane on a global cursor with ONE atomic per warp; returns this lane's start.
+// Must be called by all 32 lanes.
+__device__ __forceinline__ u64 warp_claim(unsigned long long* cursor, unsigned need) {
+    const unsigned incl = warp_scan(need);
+    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+    u64 base = 0;
+    if (total) {
+        if (lane_id() == 31) base = atomicAdd(cursor, (u64)total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+    }
+    return base + (incl - need);
 }
 
-// Strain-set algebra on the per-path bitmasks, one 64-bit word at a time.
-__device__ __forceinline__ u64 mate_strain_union(const sfb_graph& g, const sfb_work& w, const Mate& mt, int word) {
-    u64 u = 0;
-    for_tuples(g, w, mt, [&](int, uint32_t, int p, int) { u |= g.path_smask[(size_t)p * g.mask_words + word]; return true; });
-    return u;
-}
-
+// ---- block-local counters: shared-memory adds, one global add per counter per block ---------
 struct BlockCounters {
     int v[SFB_N_COUNTERS];
 };
@@ -117,5 +81,146 @@ __device__ __forceinline__ void block_counters_flush(BlockCounters& sc, long lon
         if (sc.v[i]) atomicAdd((u64*)&counters[i], (u64)(long long)sc.v[i]);
 }
 #define SFB_COUNT(sc, which, n) atomicAdd(&(sc).v[which], (n))
+
+// ---- match records (encoding in sfb200.h) -----------------------------------------------------
+__device__ __forceinline__ uint2 match_word(const sfb_work& w, i64 a) {
+    return reinterpret_cast<const uint2*>(w.aln_match)[a];
+}
+__device__ __forceinline__ int match_count(uint2 m) {
+    if (m.x == SFB_MATCH_NONE) return 0;
+    return (m.x & SFB_MATCH_MULTI) ? (int)m.y : 1;
+}
+// k-th match of an alignment as (code, path id)
+__device__ __forceinline__ uint2 match_get(const sfb_work& w, uint2 m, int k) {
+    if (!(m.x & SFB_MATCH_MULTI)) return m;
+    return reinterpret_cast<const uint2*>(w.match_buf)[(size_t)(m.x & 0x7fffffffu) + k];
+}
+
+// Coverage of walk record `rec` (position i of an L-node walk matched at `code`): aligned bases / node
+// length, the node being the path node the walk position maps to (a reversed walk reads the path
+// backwards), json2csv.py:574; or the explicit fp64 when the decoder had to merge mappings (:576-577).
+__device__ __forceinline__ double record_cov(const sfb_graph& g, const sfb_reads& r, i64 rec, uint32_t code, int i,
+                                             int L) {
+    const int alen = r.walk_alen[rec];
+    if (alen < 0) return r.exc_cov[-(i64)alen - 1];
+    const uint32_t slot0 = code & SFB_SLOT_MASK;
+    const uint32_t s = (code & SFB_MATCH_REV) ? slot0 + (uint32_t)(L - 1 - i) : slot0 + (uint32_t)i;
+    return (double)alen / (double)g.slot_len[s];
+}
+
+// A mate of a read group: its retained alignments [a0, a0+na) (json2csv.py:686-739).
+struct Mate {
+    i64 a0;
+    int na;
+    int seq_len;
+};
+__device__ __forceinline__ void mate_load(const sfb_reads& r, i64 g, int m, Mate& out) {
+    out.a0 = r.grp_aln_off[2 * g + m];
+    out.na = (int)(r.grp_aln_off[2 * g + m + 1] - out.a0);
+    out.seq_len = r.mate_seq_len[2 * g + m];
+}
+
+// ---- views of a group's match tuples ("colored_match", json2csv.py:851-866) ---------------------
+// Tuple i of mate k = (code, path id, local alignment index), in the reference's order.
+constexpr int kCap = 32;   // tuples per mate held in thread-local memory by the fast view
+
+struct LocalView {
+    int n[2];
+    int pid_[2][kCap];
+    uint32_t code_[2][kCap];
+    unsigned char aloc_[2][kCap];
+    __device__ __forceinline__ int nt(int k) const { return n[k]; }
+    __device__ __forceinline__ int pid(int k, int i) const { return pid_[k][i]; }
+    __device__ __forceinline__ uint32_t code(int k, int i) const { return code_[k][i]; }
+    __device__ __forceinline__ int aloc(int k, int i) const { return aloc_[k][i]; }
+    // false when the group does not fit (then use GlobalView)
+    __device__ __forceinline__ bool load(const sfb_work& w, const Mate* mt) {
+        for (int k = 0; k < 2; ++k) {
+            int c = 0;
+            if (mt[k].na > 255) return false;
+            for (int j = 0; j < mt[k].na; ++j) {
+                const uint2 m = match_word(w, mt[k].a0 + j);
+                const int cnt = match_count(m);
+                if (c + cnt > kCap) return false;
+                for (int e = 0; e < cnt; ++e, ++c) {
+                    const uint2 t = match_get(w, m, e);
+                    code_[k][c] = t.x;
+                    pid_[k][c] = (int)t.y;
+                    aloc_[k][c] = (unsigned char)j;
+                }
+            }
+            n[k] = c;
+        }
+        return true;
+    }
+};
+
+// Same interface straight from global memory, for groups with very many matches (any size).
+struct GlobalView {
+    const sfb_work* w;
+    Mate mt[2];
+    int n[2];
+    __device__ __forceinline__ void init(const sfb_work& w_, const Mate* m) {
+        w = &w_;
+        for (int k = 0; k < 2; ++k) {
+            mt[k] = m[k];
+            int c = 0;
+            for (int j = 0; j < m[k].na; ++j) c += match_count(match_word(w_, m[k].a0 + j));
+            n[k] = c;
+        }
+    }
+    __device__ __forceinline__ uint2 at(int k, int i, int& j) const {
+        for (j = 0; j < mt[k].na; ++j) {
+            const uint2 m = match_word(*w, mt[k].a0 + j);
+            const int c = match_count(m);
+            if (i < c) return match_get(*w, m, i);
+            i -= c;
+        }
+        return make_uint2(0, 0);
+    }
+    __device__ __forceinline__ int nt(int k) const { return n[k]; }
+    __device__ __forceinline__ int pid(int k, int i) const { int j; return (int)at(k, i, j).y; }
+    __device__ __forceinline__ uint32_t code(int k, int i) const { int j; return at(k, i, j).x; }
+    __device__ __forceinline__ int aloc(int k, int i) const { int j; at(k, i, j); return j; }
+};
+
+// list_path_id.count(pid) (json2csv.py:932)
+template <class V>
+__device__ __forceinline__ int count_pid(const V& v, int k, int p) {
+    int n = 0;
+    for (int i = 0; i < v.nt(k); ++i) n += v.pid(k, i) == p;
+    return n;
+}
+// tuple i is the first of mate k carrying its path id
+template <class V>
+__device__ __forceinline__ bool first_of_pid(const V& v, int k, int i) {
+    const int p = v.pid(k, i);
+    for (int j = 0; j < i; ++j)
+        if (v.pid(k, j) == p) return false;
+    return true;
+}
+// strains common to both mates' candidate paths, one 64-bit word of the bitmasks (json2csv.py:964-972)
+template <class V>
+__device__ __forceinline__ u64 common_strains(const sfb_graph& g, const V& v, int word) {
+    u64 u[2] = {0, 0};
+    for (int k = 0; k < 2; ++k)
+        for (int i = 0; i < v.nt(k); ++i) u[k] |= g.path_smask[(size_t)v.pid(k, i) * g.mask_words + word];
+    return u[0] & u[1];
+}
+// how many times path p appears in the strain-reduced list (once per common strain it carries, Q4)
+template <class V>
+__device__ __forceinline__ int strain_times(const sfb_graph& g, const V& v, int p) {
+    int m = 0;
+    for (int word = 0; word < (int)g.mask_words; ++word)
+        m += __popcll(g.path_smask[(size_t)p * g.mask_words + word] & common_strains(g, v, word));
+    return m;
+}
+
+// pass-2 work item: add weight * cov[i] to mult_abund[slot + i] for every record of alignment `aln`
+struct __align__(16) App {
+    int32_t aln;
+    uint32_t code;
+    double weight;
+};
 
 }  // namespace sfb

@@ -1,0 +1,473 @@
+// Per-read-group logic: k_classify (pass-1 decision tree, json2csv.py:828-1053) and k_pass2_resolve
+// (pass-2 candidate selection and ratios, json2csv.py:1085-1274).
+//
+// One thread per read group.  A group's match tuples are first gathered into thread-local arrays
+// (LocalView: one coalesced 8-byte word per alignment, one contiguous list per multi-matched
+// alignment); the set logic then runs on registers/L1 instead of chasing global memory.  Groups with
+// more than kCap tuples per mate take the same code through GlobalView.
+#include "common.cuh"
+
+namespace sfb {
+
+// ---- shared pieces --------------------------------------------------------------------------
+__device__ __forceinline__ void hist_add(const Dev& d, BlockCounters& sc, int pid, i64 a) {
+    if (d.g.path_nstrain[pid] != 1) return;                       // json2csv.py:333 / :1246
+    const int s = d.g.path_strain0[pid];
+    SFB_COUNT(sc, SFB_C_ST_HIST, 1);
+    for (int k = 0; k < SFB_N_HIST; ++k) {
+        const int b = d.r.aln_bins[a * SFB_N_HIST + k];
+        if (b >= SFB_N_BINS) { SFB_COUNT(sc, SFB_C_BAD_BIN, 1); continue; }
+        atomicAdd(&d.acc.hist[((size_t)k * d.g.n_strains + s) * SFB_N_BINS + b], 1ull);
+    }
+}
+
+// fill_abund_dist, per-read part (json2csv.py:326-327, 333-339); the node loop (:329-330) is k_pass1_scatter
+__device__ __forceinline__ void assign_unique(const Dev& d, BlockCounters& sc, i64 a, uint32_t code, int pid,
+                                              int seq_len) {
+    d.w.aln_assign[a] = (int32_t)code;
+    atomicAdd((u64*)&d.acc.uniq_reads[pid], 1ull);
+    atomicAdd(&d.acc.uniq_norm[pid], (double)seq_len / (double)d.g.path_seq_len[pid]);
+    hist_add(d, sc, pid, a);
+}
+
+// cluster of the first path through the walk's first node (json2csv.py:875,901,1036); -1 = None, -2 = no path
+__device__ __forceinline__ int first_cluster(const Dev& d, i64 a) {
+    const int n0 = d.r.walk_node[d.r.aln_walk_off[a]];
+    const int o = d.g.occ_off[n0];
+    if (o == d.g.occ_off[n0 + 1]) return -2;
+    return d.g.path_cluster[d.g.slot_path[d.g.occ_slot[o]]];
+}
+__device__ __forceinline__ void book(const Dev& d, BlockCounters& sc, const Mate& mt, int cluster) {
+    if (cluster < 0) { SFB_COUNT(sc, SFB_C_NO_CLUSTER, 1); return; }
+    d.w.aln_assign[mt.a0] = -(cluster + 2);
+}
+
+// Strain reduction (json2csv.py:964-986): size of each mate's reduced list (a tuple counts once per
+// common strain its path carries) and whether any common strain exists.
+struct StrainCut {
+    bool any;
+    int n_new[2];
+    u64 common0;   // the common-strain word when mask_words == 1
+};
+template <class V>
+__device__ __forceinline__ StrainCut strain_cut(const sfb_graph& g, const V& v) {
+    StrainCut c;
+    c.any = false;
+    c.n_new[0] = c.n_new[1] = 0;
+    c.common0 = 0;
+    for (int word = 0; word < (int)g.mask_words; ++word) {
+        const u64 common = common_strains(g, v, word);
+        if (word == 0) c.common0 = common;
+        if (!common) continue;
+        c.any = true;
+        for (int k = 0; k < 2; ++k)
+            for (int i = 0; i < v.nt(k); ++i)
+                c.n_new[k] += __popcll(g.path_smask[(size_t)v.pid(k, i) * g.mask_words + word] & common);
+    }
+    return c;
+}
+template <class V>
+__device__ __forceinline__ int times_of(const sfb_graph& g, const V& v, const StrainCut& c, int p) {
+    if (g.mask_words == 1) return __popcll(g.path_smask[p] & c.common0);
+    return strain_times(g, v, p);
+}
+
+// =============================================================================================
+// classify
+// =============================================================================================
+// both mates have colored paths (json2csv.py:918-1000)
+template <class V>
+__device__ __forceinline__ void classify_pair(const Dev& d, BlockCounters& sc, const V& v, const Mate* mt, int* code,
+                                              bool& defer) {
+    int n_inter = 0, p_inter = -1;
+    for (int i = 0; i < v.nt(0); ++i)
+        if (first_of_pid(v, 0, i) && count_pid(v, 1, v.pid(0, i)) > 0) {
+            if (n_inter++ == 0) p_inter = v.pid(0, i);
+        }
+    if (n_inter > 1) {
+        SFB_COUNT(sc, SFB_C_SECOND_PASS, 2);
+        defer = true;
+        code[0] = code[1] = SFB_DEFER;
+        return;
+    }
+    if (n_inter == 1) {
+        for (int k = 0; k < 2; ++k) {
+            if (count_pid(v, k, p_inter) > 1) {
+                SFB_COUNT(sc, SFB_C_MULTI_ALIGN, 1);
+                code[k] = SFB_MULTI_ALIGN;
+                continue;
+            }
+            for (int i = 0; i < v.nt(k); ++i)
+                if (v.pid(k, i) == p_inter) {
+                    assign_unique(d, sc, mt[k].a0 + v.aloc(k, i), v.code(k, i), p_inter, mt[k].seq_len);
+                    break;
+                }
+            SFB_COUNT(sc, SFB_C_ASSIGNED_U, 1);
+            SFB_COUNT(sc, SFB_C_SAME_CP, 1);
+            if (v.nt(k) > 1) SFB_COUNT(sc, SFB_C_AMBIG_CP_RESOLVED, 1);
+            code[k] = SFB_ASSIGN_SAME;
+        }
+        return;
+    }
+    // no common path: intersect strains (json2csv.py:961-1000)
+    const StrainCut cut = strain_cut(d.g, v);
+    if (!cut.any) {
+        SFB_COUNT(sc, SFB_C_INCONSIST, 2);
+        code[0] = code[1] = SFB_INCONSIST;
+        return;
+    }
+    for (int k = 0; k < 2; ++k) {
+        const int nn = cut.n_new[k];
+        if (nn < v.nt(k)) SFB_COUNT(sc, nn == 1 ? SFB_C_AMBIG_RESOLVED : SFB_C_AMBIG_REDUCED, 1);
+        if (nn > 1) {
+            SFB_COUNT(sc, SFB_C_SECOND_PASS, 1);
+            defer = true;
+            code[k] = SFB_DEFER;
+            continue;
+        }
+        for (int i = 0; i < v.nt(k); ++i) {      // exactly one tuple survives, once
+            const int p = v.pid(k, i);
+            if (times_of(d.g, v, cut, p) == 0) continue;
+            if (count_pid(v, k, p) == 1) {
+                assign_unique(d, sc, mt[k].a0 + v.aloc(k, i), v.code(k, i), p, mt[k].seq_len);
+                SFB_COUNT(sc, SFB_C_ASSIGNED_U, 1);
+                SFB_COUNT(sc, SFB_C_DIFF_CP, 1);
+                code[k] = SFB_ASSIGN_DIFF;
+            } else {
+                SFB_COUNT(sc, SFB_C_MULTI_ALIGN, 1);
+                code[k] = SFB_MULTI_ALIGN;
+            }
+            break;
+        }
+    }
+}
+
+// single-end style (json2csv.py:1003-1050)
+__device__ __forceinline__ int classify_single(const Dev& d, BlockCounters& sc, const Mate& mt, bool& defer) {
+    SFB_COUNT(sc, SFB_C_SINGLES, 1);
+    if (mt.na == 0) { SFB_COUNT(sc, SFB_C_FILTERED, 1); return SFB_FILTERED; }
+    if (mt.na > 1) { SFB_COUNT(sc, SFB_C_SECOND_PASS, 1); defer = true; return SFB_DEFER; }
+    const int n = match_count(match_word(d.w, mt.a0));
+    if (n > 1) { SFB_COUNT(sc, SFB_C_SECOND_PASS, 1); defer = true; return SFB_DEFER; }
+    if (n == 0) {
+        SFB_COUNT(sc, SFB_C_UNASSIGNED, 1);
+        const int c = first_cluster(d, mt.a0);
+        if (c == -2) SFB_COUNT(sc, SFB_C_NO_PATH, 1); else book(d, sc, mt, c);
+        return SFB_UNASSIGNED_BOOK;
+    }
+    SFB_COUNT(sc, SFB_C_ASSIGNED_U, 1);      // counted, never accumulated (json2csv.py:1047-1053, Q1)
+    SFB_COUNT(sc, SFB_C_SE, 1);
+    return SFB_SE_COUNTED;
+}
+
+// both mates aligned, neither has a colored path (json2csv.py:868-891)
+__device__ __forceinline__ void classify_both_unassigned(const Dev& d, BlockCounters& sc, const Mate* mt, int* code) {
+    SFB_COUNT(sc, SFB_C_UNASSIGNED, 2);
+    int n_common = 0, common = 0;
+    bool bad = false;
+    for (int i = 0; i < mt[0].na; ++i) {
+        const int ci = first_cluster(d, mt[0].a0 + i);
+        bad |= ci == -2;
+        bool seen = false;
+        for (int j = 0; j < i; ++j) seen |= first_cluster(d, mt[0].a0 + j) == ci;
+        if (seen) continue;
+        bool other = false;
+        for (int j = 0; j < mt[1].na; ++j) other |= first_cluster(d, mt[1].a0 + j) == ci;
+        if (other) { ++n_common; common = ci; }
+    }
+    for (int j = 0; j < mt[1].na; ++j) bad |= first_cluster(d, mt[1].a0 + j) == -2;
+    code[0] = code[1] = SFB_UNASSIGNED;
+    if (bad) { SFB_COUNT(sc, SFB_C_NO_PATH, 1); return; }
+    if (n_common > 1) return;
+    for (int k = 0; k < 2; ++k) {
+        int len = mt[k].na, cl = first_cluster(d, mt[k].a0);
+        if (n_common == 1) {
+            len = 0;
+            for (int j = 0; j < mt[k].na; ++j) len += first_cluster(d, mt[k].a0 + j) == common;
+            cl = common;
+        }
+        if (len == 1) { book(d, sc, mt[k], cl); code[k] = SFB_UNASSIGNED_BOOK; }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_classify(Dev d) {
+    __shared__ BlockCounters sc;
+    block_counters_zero(sc);
+    __syncthreads();
+    const i64 n_round = (d.r.n_groups + 127) & ~(i64)127;
+    for (i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x; g < n_round; g += (i64)gridDim.x * blockDim.x) {
+        bool defer = false;
+        if (g < d.r.n_groups) {
+            const int nm = d.r.grp_nmates[g];
+            Mate mt[2];
+            mate_load(d.r, g, 0, mt[0]);
+            mate_load(d.r, g, 1, mt[1]);
+            for (int k = 0; k < 2; ++k)
+                for (int j = 0; j < mt[k].na; ++j) d.w.aln_assign[mt[k].a0 + j] = -1;
+            int code[2] = {SFB_ABSENT, SFB_ABSENT};
+            SFB_COUNT(sc, SFB_C_NB_READS, nm);
+            int single = nm == 1 ? 0 : -1;       // mate handled single-end style, -1 = none
+            if (nm == 2) {
+                SFB_COUNT(sc, SFB_C_PAIRS, 1);
+                if (mt[0].na == 0 && mt[1].na == 0) {
+                    SFB_COUNT(sc, SFB_C_FILTERED, 2);
+                    code[0] = code[1] = SFB_FILTERED;
+                } else if (mt[0].na == 0 || mt[1].na == 0) {
+                    SFB_COUNT(sc, SFB_C_FILTERED, 1);
+                    SFB_COUNT(sc, SFB_C_ONE_NOALIGN, 1);
+                    const int gone = mt[0].na == 0 ? 0 : 1;
+                    code[gone] = SFB_FILTERED;
+                    single = 1 - gone;
+                } else {
+                    LocalView lv;
+                    GlobalView gv;
+                    const bool fits = lv.load(d.w, mt);
+                    if (!fits) gv.init(d.w, mt);
+                    const int nt0 = fits ? lv.nt(0) : gv.nt(0), nt1 = fits ? lv.nt(1) : gv.nt(1);
+                    if (nt0 == 0 && nt1 == 0) {
+                        classify_both_unassigned(d, sc, mt, code);
+                    } else if (nt0 == 0 || nt1 == 0) {
+                        // one mate without colored path (json2csv.py:895-916)
+                        SFB_COUNT(sc, SFB_C_UNASSIGNED, 1);
+                        SFB_COUNT(sc, SFB_C_ONE_NOCP, 1);
+                        const int gone = nt0 == 0 ? 0 : 1;
+                        code[gone] = SFB_UNASSIGNED;
+                        bool bad = false;
+                        for (int j = 0; j < mt[gone].na; ++j) bad |= first_cluster(d, mt[gone].a0 + j) == -2;
+                        if (bad) {
+                            SFB_COUNT(sc, SFB_C_NO_PATH, 1);
+                        } else if (mt[gone].na == 1) {
+                            book(d, sc, mt[gone], first_cluster(d, mt[gone].a0));
+                            code[gone] = SFB_UNASSIGNED_BOOK;
+                        }
+                        single = 1 - gone;
+                    } else if (fits) {
+                        classify_pair(d, sc, lv, mt, code, defer);
+                    } else {
+                        classify_pair(d, sc, gv, mt, code, defer);
+                    }
+                }
+            }
+            if (single >= 0) code[single] = classify_single(d, sc, mt[single], defer);
+            d.w.grp_code[g] = (uint8_t)(code[0] | (code[1] << 4));
+        }
+        // warp-aggregated append to the deferred list
+        const u64 pos = warp_claim(d.w.cursor + 1, defer ? 1u : 0u);
+        if (defer) d.w.deferred[pos] = (int32_t)g;
+    }
+    __syncthreads();
+    block_counters_flush(sc, d.acc.counters);
+}
+
+// =============================================================================================
+// pass 2, resolve: which (alignment, path position) pairs receive which share
+// =============================================================================================
+enum { kNone = 0, kInter = 1, kStrain = 2, kSingle = 3 };
+
+struct Plan {
+    int mode[2];
+    int napp[2];
+    int n_inter;
+    long long total_inter;
+    long long total_strain[2];
+    int nn[2];
+    StrainCut cut;
+};
+
+__device__ __forceinline__ double ratio_of(long long u, long long total, int n) {
+    return total == 0 ? 1.0 / (double)n : (double)u / (double)total;        // json2csv.py:1151-1154
+}
+
+// json2csv.py:1123-1217: decide per mate; counters and grp_code2 here, the additions in p2_emit
+template <class V>
+__device__ __forceinline__ void p2_decide_pair(const Dev& d, BlockCounters& sc, const V& v, const long long* U,
+                                               Plan& pl, int* code) {
+    pl.n_inter = 0;
+    pl.total_inter = 0;
+    for (int i = 0; i < v.nt(0); ++i)
+        if (first_of_pid(v, 0, i) && count_pid(v, 1, v.pid(0, i)) > 0) {
+            ++pl.n_inter;
+            pl.total_inter += U[v.pid(0, i)];
+        }
+    if (pl.n_inter >= 1) {
+        for (int k = 0; k < 2; ++k) {
+            bool simple = true;      // every common path has exactly one tuple in this mate
+            for (int i = 0; i < v.nt(k) && simple; ++i) {
+                const int p = v.pid(k, i);
+                if (count_pid(v, 1 - k, p) > 0 && count_pid(v, k, p) != 1) simple = false;
+            }
+            if (!simple) {
+                SFB_COUNT(sc, SFB_C_MULTI_ALIGN, 1);
+                code[k] = SFB_P2_MULTI_ALIGN;
+                continue;
+            }
+            SFB_COUNT(sc, SFB_C_ASSIGNED_M, 1);
+            code[k] = SFB_P2_ASSIGNED;
+            pl.mode[k] = kInter;
+            pl.napp[k] = pl.n_inter;
+        }
+        return;
+    }
+    pl.cut = strain_cut(d.g, v);
+    if (!pl.cut.any) {
+        SFB_COUNT(sc, SFB_C_INCONSIST_M, (v.nt(0) == 1 || v.nt(1) == 1) ? 1 : 2);
+        code[0] = code[1] = SFB_P2_INCONSIST;
+        return;
+    }
+    for (int k = 0; k < 2; ++k) {
+        pl.nn[k] = pl.cut.n_new[k];
+        if (pl.nn[k] <= 1) continue;          // handled in pass 1 (json2csv.py:1185)
+        bool simple = true;
+        long long tot = 0;
+        int napp = 0;
+        for (int i = 0; i < v.nt(k); ++i) {
+            const int p = v.pid(k, i);
+            const int times = times_of(d.g, v, pl.cut, p);
+            if (times == 0) continue;
+            if (count_pid(v, k, p) != 1) { simple = false; break; }
+            tot += U[p] * times;
+            ++napp;
+        }
+        if (!simple) {
+            SFB_COUNT(sc, SFB_C_MULTI_ALIGN, 1);
+            code[k] = SFB_P2_MULTI_ALIGN;
+            continue;
+        }
+        SFB_COUNT(sc, SFB_C_ASSIGNED_M, 1);
+        code[k] = SFB_P2_ASSIGNED;
+        pl.mode[k] = kStrain;
+        pl.napp[k] = napp;
+        pl.total_strain[k] = tot;
+    }
+}
+
+// json2csv.py:1155-1156 (and :1207-1208, :1265-1266) + the work item for the node loop (:1157-1158)
+__device__ __forceinline__ void emit_app(const Dev& d, App* out, i64 a, uint32_t code, int pid, int seq_len,
+                                         double ratio, int times) {
+    atomicAdd(&d.acc.mult_reads[pid], ratio * (double)times);
+    atomicAdd(&d.acc.mult_norm[pid], (ratio * (double)seq_len / (double)d.g.path_seq_len[pid]) * (double)times);
+    atomicAdd(&d.acc.mult_hits[pid], (unsigned)times);
+    App app;
+    app.aln = (int32_t)a;
+    app.code = code;
+    app.weight = ratio * (double)times;
+    *out = app;
+}
+
+template <class V>
+__device__ __forceinline__ void p2_emit(const Dev& d, BlockCounters& sc, const V& v, const Mate* mt,
+                                        const long long* U, const Plan& pl, App* out) {
+    for (int k = 0; k < 2; ++k) {
+        if (pl.mode[k] == kInter) {
+            for (int i = 0; i < v.nt(k); ++i) {
+                const int p = v.pid(k, i);
+                if (count_pid(v, 1 - k, p) > 0)
+                    emit_app(d, out++, mt[k].a0 + v.aloc(k, i), v.code(k, i), p, mt[k].seq_len,
+                             ratio_of(U[p], pl.total_inter, pl.n_inter), 1);
+            }
+        } else if (pl.mode[k] == kStrain) {
+            for (int i = 0; i < v.nt(k); ++i) {
+                const int p = v.pid(k, i);
+                const int times = times_of(d.g, v, pl.cut, p);
+                if (times)
+                    emit_app(d, out++, mt[k].a0 + v.aloc(k, i), v.code(k, i), p, mt[k].seq_len,
+                             ratio_of(U[p], pl.total_strain[k], pl.nn[k]), times);
+            }
+        } else if (pl.mode[k] == kSingle) {
+            // every alignment separately (json2csv.py:1230-1268)
+            int i = 0;
+            while (i < v.nt(k)) {
+                const int j = v.aloc(k, i);
+                int e = i;
+                long long total = 0;
+                for (; e < v.nt(k) && v.aloc(k, e) == j; ++e) {
+                    total += U[v.pid(k, e)];
+                    hist_add(d, sc, v.pid(k, e), mt[k].a0 + j);
+                }
+                for (int t = i; t < e; ++t)
+                    emit_app(d, out++, mt[k].a0 + j, v.code(k, t), v.pid(k, t), mt[k].seq_len,
+                             ratio_of(U[v.pid(k, t)], total, e - i), 1);
+                i = e;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_pass2_resolve(Dev d, const long long* __restrict__ U) {
+    __shared__ BlockCounters sc;
+    block_counters_zero(sc);
+    __syncthreads();
+    const i64 n_def = (i64)d.w.cursor[1];
+    const i64 n_round = (n_def + 127) & ~(i64)127;
+    App* apps = reinterpret_cast<App*>(d.w.app_buf);
+    for (i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x; q < n_round; q += (i64)gridDim.x * blockDim.x) {
+        const bool live = q < n_def;
+        LocalView lv;
+        GlobalView gv;
+        Mate mt[2];
+        Plan pl;
+        pl.mode[0] = pl.mode[1] = kNone;
+        pl.napp[0] = pl.napp[1] = 0;
+        bool fits = true;
+        i64 g = 0;
+        int code[2] = {SFB_P2_NONE, SFB_P2_NONE};
+        if (live) {
+            g = d.w.deferred[q];
+            const int nm = d.r.grp_nmates[g];
+            mate_load(d.r, g, 0, mt[0]);
+            mate_load(d.r, g, 1, mt[1]);
+            fits = lv.load(d.w, mt);
+            if (!fits) gv.init(d.w, mt);
+            const int nt0 = fits ? lv.nt(0) : gv.nt(0), nt1 = fits ? lv.nt(1) : gv.nt(1);
+            int single = nm == 1 ? 0 : -1;
+            if (nm == 2) {
+                if (mt[0].na == 0 || mt[1].na == 0) single = mt[0].na == 0 ? 1 : 0;          // json2csv.py:1088-1093
+                else if (nt0 == 0 || nt1 == 0) single = nt0 == 0 ? 1 : 0;                    // :1117-1122
+                else if (fits) p2_decide_pair(d, sc, lv, U, pl, code);
+                else p2_decide_pair(d, sc, gv, U, pl, code);
+            }
+            if (single >= 0) {
+                const int nts = single == 0 ? nt0 : nt1;
+                pl.mode[single] = kSingle;
+                pl.napp[single] = nts;
+                if (nts > 0) {
+                    SFB_COUNT(sc, SFB_C_ASSIGNED_M, 1);
+                    SFB_COUNT(sc, SFB_C_SE_M, 1);
+                    code[single] = SFB_P2_SE_ASSIGNED;
+                } else {
+                    SFB_COUNT(sc, SFB_C_UNASSIGNED, 1);
+                    code[single] = SFB_P2_UNASSIGNED;
+                }
+            }
+            d.w.grp_code2[g] = (uint8_t)(code[0] | (code[1] << 4));
+        }
+        const unsigned need = (unsigned)(pl.napp[0] + pl.napp[1]);
+        const u64 pos = warp_claim(d.w.cursor + 2, need);
+        if (live && need) {
+            SFB_COUNT(sc, SFB_C_ST_P2_APPLIED, (int)need);
+            if (pos + need <= (u64)d.w.app_cap) {
+                if (fits) p2_emit(d, sc, lv, mt, U, pl, apps + pos);
+                else p2_emit(d, sc, gv, mt, U, pl, apps + pos);
+            } else {
+                SFB_COUNT(sc, SFB_C_MATCH_OVERFLOW, (int)need);
+            }
+        }
+    }
+    __syncthreads();
+    block_counters_flush(sc, d.acc.counters);
+}
+
+int launch_classify(const Dev& d, cudaStream_t st) {
+    if (d.r.n_groups == 0) return SFB_OK;
+    const unsigned grid = (unsigned)min((i64)kSMs * 16, (i64)blocks_for(d.r.n_groups, 128));
+    k_classify<<<grid, 128, 0, st>>>(d);
+    return check_launch("k_classify");
+}
+int launch_pass2_resolve(const Dev& d, const long long* U, cudaStream_t st) {
+    if (d.r.n_groups == 0) return SFB_OK;
+    const unsigned grid = (unsigned)min((i64)kSMs * 16, (i64)blocks_for(d.r.n_groups, 128));
+    k_pass2_resolve<<<grid, 128, 0, st>>>(d, U);
+    return check_launch("k_pass2_resolve");
+}
+
+}  // namespace sfb

@@ -116,16 +116,19 @@ class Work:
         i32, u8 = torch.int32, torch.uint8
         self.n_groups, self.n_alns = n_groups, n_alns
         self.match_cap = int(max(2, match_cap))
+        self.app_cap = int(n_alns + self.match_cap)     # >= number of matches of the shard
         self.t = dict(
-            aln_match=torch.empty(max(1, n_alns), dtype=i32, device=device),
-            match_buf=torch.empty(self.match_cap, dtype=i32, device=device),
-            cursor=torch.zeros(2, dtype=torch.int64, device=device),
+            aln_match=torch.empty(max(1, n_alns), dtype=torch.int64, device=device),      # (x, y) pairs
+            match_buf=torch.empty(self.match_cap, dtype=torch.int64, device=device),       # (code, pid) pairs
+            app_buf=torch.empty(2 * self.app_cap, dtype=torch.int64, device=device),       # 16-byte items
+            cursor=torch.zeros(4, dtype=torch.int64, device=device),
             grp_code=torch.zeros(max(1, n_groups), dtype=u8, device=device),
             grp_code2=torch.zeros(max(1, n_groups), dtype=u8, device=device),
             aln_assign=torch.empty(max(1, n_alns), dtype=i32, device=device),
             deferred=torch.empty(max(1, n_groups), dtype=i32, device=device),
         )
-        self.c = _lib.SfbWork(match_cap=self.match_cap, **{k: v.data_ptr() for k, v in self.t.items()})
+        self.c = _lib.SfbWork(match_cap=self.match_cap, app_cap=self.app_cap,
+                              **{k: v.data_ptr() for k, v in self.t.items()})
 
     def reset(self):
         self.t["cursor"].zero_()
@@ -195,7 +198,7 @@ class AbundanceEngine:
 
     # ---- stages (each is one kernel launch through the C ABI) -----------------------------
     def _work_for(self, dr):
-        cap = max(self.match_cap_hint, 2 * dr.n_alns + 1024)
+        cap = max(self.match_cap_hint, 2 * dr.n_alns + 1024)      # (code, path id) pairs for multi-matched alignments
         if self.work is None or self.work.n_groups < dr.n_groups or self.work.n_alns < dr.n_alns \
                 or self.work.match_cap < cap:
             self.work = None
@@ -303,8 +306,9 @@ class AbundanceEngine:
             res.grp_code = work.t["grp_code"][:dr.n_groups].cpu().numpy()
             res.grp_code2 = work.t["grp_code2"][:dr.n_groups].cpu().numpy()
             res.aln_assign = work.t["aln_assign"][:dr.n_alns].cpu().numpy()
-            res.aln_match = work.t["aln_match"][:dr.n_alns].cpu().numpy().view(np.uint32)
-            res.match_buf = work.t["match_buf"][:min(work.match_cap, max(0, res.match_fill))].cpu().numpy()
+            res.aln_match = work.t["aln_match"][:dr.n_alns].cpu().numpy().view(np.uint32).reshape(-1, 2)
+            res.match_buf = work.t["match_buf"][:min(work.match_cap, max(0, res.match_fill))].cpu().numpy() \
+                .view(np.uint32).reshape(-1, 2)
         check_errors(res.C)
         return res
 
@@ -321,23 +325,16 @@ def check_errors(Cn):
 
 def decode_matches(res, a):
     """Match list of alignment ``a`` as [(path id, position, reversed)] (test helper)."""
-    v = int(res.aln_match[a])
-    g = res.g
-    if v == _lib.MATCH_NONE:
+    x, y = (int(v) for v in res.aln_match[a])
+    if x == _lib.MATCH_NONE:
         return []
-    if v & _lib.MATCH_MULTI:
-        base = (v & 0x7FFFFFFF) * 2
-        codes = [int(c) & 0xFFFFFFFF for c in res.match_buf[base + 1:base + 1 + int(res.match_buf[base])]]
+    if x & _lib.MATCH_MULTI:
+        base = x & 0x7FFFFFFF
+        pairs = [(int(c), int(p)) for c, p in res.match_buf[base:base + y]]
     else:
-        codes = [v]
-    out = []
-    for c in codes:
-        slot = c & _lib.SLOT_MASK
-        # slot -> (pid, pos) in the sentinel layout: path p starts at path_off[p] + p
-        starts = g["path_off"][:-1] + np.arange(len(g["path_off"]) - 1)
-        pid = int(np.searchsorted(starts, slot, side="right") - 1)
-        out.append((pid, int(slot - starts[pid]), bool(c & _lib.MATCH_REV)))
-    return out
+        pairs = [(x, y)]
+    starts = res.g["path_off"][:-1] + np.arange(len(res.g["path_off"]) - 1)   # sentinel layout: path p starts at path_off[p] + p
+    return [(pid, int((c & _lib.SLOT_MASK) - starts[pid]), bool(c & _lib.MATCH_REV)) for c, pid in pairs]
 
 
 def abundance_pass(graph: Graph, reads: Reads, device="cuda:0") -> Result:

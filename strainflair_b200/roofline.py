@@ -8,7 +8,7 @@ The per-launch work statistics come from the ST_* counters the kernels maintain.
     cand     candidate occurrences tested by match        (ST_CAND)
     cmp      path-node compares executed by match          (ST_COMPARES)
     tuples   matches found                                 (ST_TUPLES)
-    fill     ints written to match_buf
+    fill     (code, path id) pairs written to match_buf (alignments with several matches)
     r1       records added in pass 1                       (ST_P1_RECORDS)
     n1       unique assignments (ASSIGN_SAME + ASSIGN_DIFF leaves)
     hist     histogram-updating reads                      (ST_HIST)
@@ -25,20 +25,20 @@ def kernel_bytes(n_groups, n_alns, n_records, n_paths, n_slots, C, match_fill, n
     n1 = C["SAME_CP"] + C["DIFF_CP"]
     out = {}
     # match: walk offsets (8) + walk nodes (4/record) + occurrence ranges (2 ints per orientation)
-    #        + occurrence slots (4/candidate) + compared path nodes (4/compare) + result word + multi lists
-    out["match"] = 8 * A + 4 * R + 16 * A + 4 * cand + 4 * cmp_ + 4 * A + 4 * match_fill
+    #        + occurrence slots (4/candidate) + compared path nodes (4/compare) + slot->path (4/match)
+    #        + result pair (8) + multi lists (8/pair)
+    out["match"] = 8 * A + 4 * R + 16 * A + 4 * cand + 4 * cmp_ + 4 * tuples + 8 * A + 8 * match_fill
     # classify: per group nmates(1) + 2 alignment offsets(16) + 2 seq_len(8) + code(1); per alignment
-    #           aln_match(4) + aln_assign(4); multi lists (4/int) + slot->path (4/tuple); per unique
-    #           assignment uniq_reads RMW(16) + uniq_norm RMW(16) + path_seq_len(8) + 5 bins;
-    #           per histogram read 5 RMW(16); deferred list (4)
-    out["classify"] = 26 * G + 8 * A + 4 * match_fill + 4 * tuples + 45 * n1 + 80 * hist + 4 * n_deferred
+    #           aln_match(8) + aln_assign(4); multi lists (8/pair); per unique assignment uniq_reads RMW(16)
+    #           + uniq_norm RMW(16) + path_seq_len(8) + 5 bins; per histogram read 5 RMW(16); deferred list (4)
+    out["classify"] = 26 * G + 12 * A + 8 * match_fill + 45 * n1 + 80 * hist + 4 * n_deferred
     # pass-1 scatter: walk offsets(8) + aln_assign(4) per alignment; per added record alen(4) + node length(4)
     #                 + fp64 RMW(16)
     out["pass1_scatter"] = 12 * A + 24 * r1
-    # pass 2: deferred id(4) + group header(26) per deferred group; per redistribution: match code(4) +
-    #         slot->path(4) + uniq_reads gather(8) + 3 RMW (mult_reads, mult_norm 16 each, mult_hits 8)
-    #         + path_seq_len(8) + walk offsets(16); per record alen(4) + node length(4) + RMW(16)
-    out["pass2"] = 30 * n_deferred + 80 * app + 24 * r2
+    # pass 2: deferred id(4) + group header(26) per deferred group; per redistribution: match pair(8) +
+    #         uniq_reads gather(8) + 3 RMW (mult_reads, mult_norm 16 each, mult_hits 8) + path_seq_len(8)
+    #         + work item write+read(32) + walk offsets(16); per record alen(4) + node length(4) + RMW(16)
+    out["pass2"] = 30 * n_deferred + 112 * app + 24 * r2
     # path reduce: two fp64 slot arrays in, 8 fp64 + 3 counters per path
     out["path_reduce"] = 16 * n_slots + (8 * 8 + 4 * 8 + 8) * n_paths
     out["total"] = sum(out.values())

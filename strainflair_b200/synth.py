@@ -20,11 +20,15 @@ CONFIGS = {
              dict(n_pairs=2000, read_len=60)),
     "small": (dict(n_clusters=400, chain_len=40, hap_lo=1, hap_hi=8, n_strains=16, bubble_p=0.3, flip_p=0.15),
               dict(n_pairs=50_000, read_len=150)),
-    "c3": (dict(n_clusters=10_000, chain_len=150, hap_lo=2, hap_hi=9, n_strains=64, bubble_p=0.33, flip_p=0.08),
+    # C3: 2 M nodes, ~50 k paths, ~7.4 M path positions; independent alleles on every second position give
+    # ~2 matching paths per alignment and ~30 % of the groups deferred to pass 2
+    "c3": (dict(n_clusters=8_900, chain_len=150, hap_lo=2, hap_hi=9, n_strains=64, bubble_p=0.5, flip_p=0.5),
            dict(n_pairs=25_000_000, read_len=150)),
-    "c4": (dict(n_clusters=3_125, chain_len=150, hap_lo=16, hap_hi=16, n_strains=64, bubble_p=0.33, flip_p=0.006),
+    # C4: 16 near-identical haplotypes per cluster: ~8+ candidate paths per read, most groups deferred
+    "c4": (dict(n_clusters=3_125, chain_len=150, hap_lo=16, hap_hi=16, n_strains=64, bubble_p=0.33, flip_p=0.02),
            dict(n_pairs=25_000_000, read_len=150)),
-    "c5": (dict(n_clusters=100_000, chain_len=150, hap_lo=2, hap_hi=9, n_strains=64, bubble_p=0.33, flip_p=0.08),
+    # C5: 20 M nodes, 1e9 alignment-node records over all ranks (sharded by read group)
+    "c5": (dict(n_clusters=89_000, chain_len=150, hap_lo=2, hap_hi=9, n_strains=64, bubble_p=0.5, flip_p=0.5),
            dict(n_pairs=83_000_000, read_len=150)),
 }
 SEED0 = 20261019

@@ -70,7 +70,7 @@ def test_struct_sizes_are_pointer_and_int64_multiples():
         assert ctypes.sizeof(st) % 8 == 0
     assert ctypes.sizeof(_lib.SfbGraph) == 8 * 16
     assert ctypes.sizeof(_lib.SfbReads) == 8 * 12
-    assert ctypes.sizeof(_lib.SfbWork) == 8 * 8
+    assert ctypes.sizeof(_lib.SfbWork) == 8 * 10
     assert ctypes.sizeof(_lib.SfbAccum) == 8 * 9
 
 
@@ -83,7 +83,10 @@ def test_argument_validation_needs_no_gpu():
     a = _lib.SfbAccum()
     rc = lib.sfb_match(ctypes.byref(g), ctypes.byref(r), ctypes.byref(w), ctypes.byref(a), None)
     assert rc == -1
-    assert b"null" in lib.sfb_last_error()
+    assert lib.sfb_last_error().startswith(b"check_graph")
+    g.mask_words = 1
+    rc = lib.sfb_match(ctypes.byref(g), ctypes.byref(r), ctypes.byref(w), ctypes.byref(a), None)
+    assert rc == -1 and b"null" in lib.sfb_last_error()
     with pytest.raises(_lib.SfbError):
         _lib.check(rc)
 
