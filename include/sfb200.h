@@ -205,6 +205,25 @@ int sfb_strain_aggregate(int64_t n_rows, int64_t n_strains, const int32_t* row_o
                          const double* mam_nz, const double* ratio_cov, double thr, int32_t* ws_rows,
                          double* ws_vals, double* ws_counts, double* out, void* stream);
 
+/* ---- host-side alignment decoder (no GPU involved) ------------------------------------------
+ * get_all_alignments_one_read + BFS + metaalign2align (json2csv.py:551-739) over a whole
+ * `vg view -j -K` JSON file, multi-threaded, one parse per line (the reference parses deferred reads
+ * twice).  node_ids[k] is the GFA id of dense node k, node_len[k] its length.  The handle owns the
+ * Reads arrays of sfb_reads plus names/statistics; sizes: which = 0 groups, 1 alignments, 2 records,
+ * 3 explicit coverages, 4 bytes of names.  sfb_decoded_copy(which): 0 grp_nmates u8[G],
+ * 1 grp_aln_off i64[2G+1], 2 mate_seq_len i32[2G], 3 aln_walk_off i64[A+1], 4 aln_read_len i32[A],
+ * 5 aln_bins u8[5A], 6 aln_stats f64[5A], 7 walk_node i32[R], 8 walk_alen i32[R], 9 walk_cov f64[R],
+ * 10 exc_cov f64[E], 11 name_off i64[2G+1], 12 names bytes.
+ * sfb_decoded_error: 0 ok, 1 malformed JSON (ValueError), 2 KeyError, 3 ZeroDivisionError,
+ * 4 IndexError, 5 I/O, 6 TypeError/ValueError of int() -- the exception the reference raises. */
+typedef struct sfb_decoded sfb_decoded;
+sfb_decoded* sfb_decode_json(const char* path, const int64_t* node_ids, const int32_t* node_len, int64_t n_nodes,
+                             double thr, int n_threads, int64_t block_bytes);
+int          sfb_decoded_error(const sfb_decoded* d, const char** msg);
+int64_t      sfb_decoded_size(const sfb_decoded* d, int which);
+int          sfb_decoded_copy(const sfb_decoded* d, int which, void* dst);
+void         sfb_decoded_free(sfb_decoded* d);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,7 +65,8 @@ MAX_SLOTS = 0x3FFFFFFF
 ABI_VERSION = 2
 
 EXPORTS = ("sfb_abi_version", "sfb_version", "sfb_last_error", "sfb_match", "sfb_classify", "sfb_pass1_scatter",
-           "sfb_pass2", "sfb_path_reduce", "sfb_cluster_strain_counts", "sfb_strain_aggregate")
+           "sfb_pass2", "sfb_path_reduce", "sfb_cluster_strain_counts", "sfb_strain_aggregate",
+           "sfb_decode_json", "sfb_decoded_error", "sfb_decoded_size", "sfb_decoded_copy", "sfb_decoded_free")
 
 
 class SfbError(RuntimeError):
@@ -106,8 +107,18 @@ def load(build_if_missing=True):
     lib.sfb_path_reduce.argtypes = [G, A, i64, i64, vp, vp]
     lib.sfb_cluster_strain_counts.argtypes = [i64, i64, vp, vp, vp, vp, vp, vp, vp]
     lib.sfb_strain_aggregate.argtypes = [i64, i64, vp, vp, vp, vp, vp, vp, f64, vp, vp, vp, vp, vp]
-    for name in EXPORTS[3:]:
+    for name in EXPORTS[3:10]:
         getattr(lib, name).restype = C.c_int
+    lib.sfb_decode_json.argtypes = [C.c_char_p, vp, vp, i64, f64, C.c_int, i64]
+    lib.sfb_decode_json.restype = C.c_void_p
+    lib.sfb_decoded_error.argtypes = [vp, C.POINTER(C.c_char_p)]
+    lib.sfb_decoded_error.restype = C.c_int
+    lib.sfb_decoded_size.argtypes = [vp, C.c_int]
+    lib.sfb_decoded_size.restype = C.c_int64
+    lib.sfb_decoded_copy.argtypes = [vp, C.c_int, vp]
+    lib.sfb_decoded_copy.restype = C.c_int
+    lib.sfb_decoded_free.argtypes = [vp]
+    lib.sfb_decoded_free.restype = None
     if lib.sfb_abi_version() != ABI_VERSION:
         raise SfbError(f"ABI mismatch: library {lib.sfb_abi_version()}, binding {ABI_VERSION}")
     _lib = lib

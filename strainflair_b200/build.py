@@ -5,13 +5,13 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SOURCES = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "match.cu", "group.cu", "scatter.cu", "reduce.cu")]
+SOURCES = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "match.cu", "group.cu", "scatter.cu", "reduce.cu", "decode.cpp")]
 HEADERS = [os.path.join(HERE, "csrc", "common.cuh"), os.path.join(ROOT, "include", "sfb200.h")]
 LIB = os.path.join(HERE, "libsfb200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared",
+    "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC,-pthread", "-shared", "-cudart", "shared",
 ]
 
 

@@ -1,0 +1,105 @@
+"""Drop-in command lines: ``json2csv`` and ``compute_strains_abundance`` with the reference's flags, file names,
+stdout lines and exit codes (json2csv.py:1281-1356, compute_strains_abundance.py:9-72)."""
+import getopt
+import sys
+import time
+
+
+def _usage_json2csv():
+    print(f"Usage: python {sys.argv[0]} -g graph_file_name (gfa) -m mapped_file_name (json) -p dictionary_file_name "
+          f"(pickle) -t alignment_score_threshold -o prefix_output_files_name -f")
+
+
+def run_json2csv(graph_file, mapping_file, pickle_file, prefix, thr=0.95, device="cuda:0", timings=None):
+    """The whole json2csv job; returns (graph, reads, result)."""
+    from . import decode, engine, gfa, report
+    t = {}
+    t0 = time.perf_counter()
+    print("Load the pangenome graph")
+    graph = gfa.load_graph(graph_file, pickle_file)
+    t["graph_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    print("Parsing Alignment: first pass")
+    reads = decode.decode_json(mapping_file, graph, thr)
+    t["decode_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    eng = engine.AbundanceEngine(graph, device)
+    print("Parsing Alignment: second pass")
+    res = eng.run(reads)
+    t["abundance_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    clusters = report.cluster_records(graph, reads, res)
+    gene_csv = prefix + "_gene_table.csv"
+    print(f"Print gene-level results to file {gene_csv}")
+    report.write_gene_table(gene_csv, graph, res)
+    for k, name in enumerate(report.HIST_FILES):
+        print(f"Print {name} distribution results to file {prefix + '_' + name + '.csv'}")
+        report.write_histogram(prefix + "_" + name + ".csv", graph, res, k)
+    print(f"Print cluster-level unassigned reads distribution results to file {prefix + '_unassigned.csv'}")
+    report.write_unassigned(prefix + "_unassigned.csv", graph, clusters, engine.cluster_strain_counts(graph, device))
+    report.write_clusters_pickle("allclusters.pickle", clusters)        # current directory, as json2csv.py:1344 (Q11)
+    for line in report.summary_lines(res.C, thr, prefix):
+        print(line)
+    t["report_s"] = time.perf_counter() - t0
+    if timings is not None:
+        timings.update(t)
+    return graph, reads, res
+
+
+def json2csv_main():
+    graph_file = pickle_file = mapping_file = prefix = None
+    thr = 0.95
+    try:
+        opts, _ = getopt.getopt(sys.argv[1:], "hg:p:o:m:t:")     # no "f": -f is rejected, as in the reference (Q2)
+    except getopt.GetoptError as err:
+        print(err)
+        _usage_json2csv()
+        sys.exit(2)
+    for o, a in opts:
+        if o == "-h":
+            _usage_json2csv()
+        elif o == "-g":
+            graph_file = a
+        elif o == "-m":
+            mapping_file = a
+        elif o == "-p":
+            pickle_file = a
+        elif o == "-o":
+            prefix = a
+        elif o == "-t":
+            thr = float(a)
+    if not graph_file or not pickle_file or not mapping_file:
+        _usage_json2csv()
+        sys.exit()
+    if prefix is None:
+        raise TypeError("unsupported operand type(s) for +: 'NoneType' and 'str'")     # json2csv.py:1325
+    run_json2csv(graph_file, mapping_file, pickle_file, prefix, thr)
+
+
+def _usage_strains():
+    print(f"Usage: python {sys.argv[0]} -i input_file (csv) -o out_file -t thr")
+
+
+def compute_strains_abundance_main():
+    input_file = out_file = None
+    thr = 0.5
+    try:
+        opts, _ = getopt.getopt(sys.argv[1:], "hi:o:t:")
+    except getopt.GetoptError as err:
+        print(err)
+        _usage_strains()
+        sys.exit(2)
+    for o, a in opts:
+        if o == "-h":
+            _usage_strains()
+        elif o == "-i":
+            input_file = a
+        elif o == "-o":
+            out_file = a
+        elif o == "-t":
+            thr = float(a)
+    if not input_file or not out_file:
+        _usage_strains()
+        sys.exit()
+    from . import strains
+    strains.compute_strains_abundance(input_file, out_file, thr)

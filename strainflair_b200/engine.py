@@ -340,3 +340,43 @@ def decode_matches(res, a):
 def abundance_pass(graph: Graph, reads: Reads, device="cuda:0") -> Result:
     """One-call public API: decoded alignments + graph in, per-path abundances and counters out."""
     return AbundanceEngine(graph, device).run(reads)
+
+
+def cluster_strain_counts(graph: Graph, device="cuda:0"):
+    """Strain copy counts per cluster (print_unassigned_info, json2csv.py:544) -> int64[C, S] on the host."""
+    lib = _lib.load()
+    if not torch.cuda.is_available():
+        raise _lib.SfbError("no CUDA device: the abundance engine has no CPU fallback")
+    dev = torch.device(device)
+    C_, S = graph.n_clusters, graph.n_strains
+    out = torch.zeros((max(1, C_), max(1, S)), dtype=torch.int64, device=dev)
+    if C_ and S:
+        t = [_to_dev(a.astype(np.int32), dev) for a in (graph.clu_off, graph.clu_paths, graph.pstr_off, graph.pstr_id,
+                                                         graph.pstr_cnt)]
+        _lib.check(lib.sfb_cluster_strain_counts(C_, S, *[C.c_void_p(x.data_ptr()) for x in t],
+                                                 C.c_void_p(out.data_ptr()), _stream()))
+        torch.cuda.current_stream().synchronize()
+    return out[:C_, :S].cpu().numpy()
+
+
+def strain_aggregate(row_off, row_strain, row_count, mam, mam_nz, ratio_cov, n_strains, thr, device="cuda:0"):
+    """compute_strains_abundance.py:52-69 on the device.  Inputs: CSR of the positive strain counts of each
+    gene row + three gene-table columns (NaN already replaced by 0).  Returns float64[S, 5]."""
+    lib = _lib.load()
+    if not torch.cuda.is_available():
+        raise _lib.SfbError("no CUDA device: the abundance engine has no CPU fallback")
+    dev = torch.device(device)
+    P, S = len(mam), int(n_strains)
+    out = torch.zeros((max(1, S), 5), dtype=torch.float64, device=dev)
+    if S:
+        d = lambda a, dt: _to_dev(np.ascontiguousarray(a, dt), dev)    # noqa: E731
+        t_off, t_str, t_cnt = d(row_off, np.int32), d(row_strain, np.int32), d(row_count, np.float64)
+        t_mam, t_nz, t_cov = d(mam, np.float64), d(mam_nz, np.float64), d(ratio_cov, np.float64)
+        ws_rows = torch.empty(max(1, P), dtype=torch.int32, device=dev)
+        ws_vals = torch.empty(max(1, 3 * P), dtype=torch.float64, device=dev)
+        ws_counts = torch.empty(4 * S, dtype=torch.float64, device=dev)
+        p = lambda x: C.c_void_p(x.data_ptr())                        # noqa: E731
+        _lib.check(lib.sfb_strain_aggregate(P, S, p(t_off), p(t_str), p(t_cnt), p(t_mam), p(t_nz), p(t_cov), float(thr),
+                                            p(ws_rows), p(ws_vals), p(ws_counts), p(out), _stream()))
+        torch.cuda.current_stream().synchronize()
+    return out[:S].cpu().numpy()

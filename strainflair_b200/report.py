@@ -1,0 +1,223 @@
+"""Output files of ``json2csv`` from the engine's results (host side).
+
+File formats and cell formatting follow the reference byte for byte where it is deterministic:
+gene table (json2csv.py:399-474), five error-distribution tables (:515-526), per-cluster unassigned report
+(:528-549, with ``Cluster.min_strains_inference`` :149-201), ``allclusters.pickle`` (:1338-1344) and the
+stdout summary (:1346-1356).  The only free choice is the order of the strain columns, which in the
+reference is a ``set`` iteration order: here it is first-seen order.
+"""
+import math
+import pickle
+import warnings
+
+import numpy as np
+
+from . import _lib
+from .decode import mate_name
+
+GENE_COLS = ("cluster", "seq_len", "nb_uniq_mapped", "nb_uniq_mapped_normalized", "nb_multimapped",
+             "nb_multimapped_normalized", "mean_abund_uniq", "mean_abund_uniq_nz", "mean_abund_multiple",
+             "mean_abund_multiple_nz", "ratio_covered_nodes")
+HIST_FILES = ("mappingscore_freq", "identityscore_freq", "subst_freq", "indel_freq", "errors_freq")
+
+
+def _f(x):
+    """str() of a Python/numpy float as the reference's f-strings print it."""
+    x = float(x)
+    return "nan" if math.isnan(x) else repr(x)
+
+
+def gene_table_lines(graph, res):
+    """Yields the gene table line by line.  Typing quirks kept: counters never touched print as the int 0
+    (json2csv.py:114-118), touched ones as floats."""
+    names = graph.strain_names
+    keys = list(graph.header_strains)
+    yield "".join(f"{names[s]};" for s in keys) + ";".join(GENE_COLS) + "\n"
+    t = res.table
+    po, pid, pcnt = graph.pstr_off, graph.pstr_id, graph.pstr_cnt
+    for p in range(graph.n_paths):
+        cnt = dict.fromkeys(keys, 0)
+        for e in range(int(po[p]), int(po[p + 1])):
+            s = int(pid[e])
+            if s not in cnt:
+                keys.append(s)              # strain seen only on duplicate P lines: ragged row (Q5, :413-418)
+            cnt[s] = int(pcnt[e])
+        uniq = int(res.uniq_reads[p])
+        multi_touched = int(res.mult_hits[p]) > 0
+        c = int(graph.path_cluster[p])
+        cells = [
+            "None" if c < 0 else str(c),
+            str(int(graph.path_seq_len[p])),
+            str(uniq),
+            _f(t[p, 0]) if uniq else "0",
+            _f(t[p, 1]) if multi_touched else str(uniq),
+            _f(t[p, 2]) if (uniq or multi_touched) else "0",
+            _f(t[p, 3]), _f(t[p, 4]), _f(t[p, 5]), _f(t[p, 6]), _f(t[p, 7]),
+        ]
+        yield "".join(f"{cnt[s]};" for s in keys) + ";".join(cells) + "\n"
+
+
+def write_gene_table(path, graph, res):
+    with open(path, "w") as fh:
+        fh.writelines(gene_table_lines(graph, res))
+
+
+def write_histogram(path, graph, res, which):
+    with open(path, "w") as fh:
+        fh.write("Strain;" + ";".join(str(i / 100) for i in range(101)) + "\n")
+        for s in graph.header_strains:
+            fh.write(f"{graph.strain_names[s]}" + "".join(f";{int(v)}" for v in res.hist[which, s]) + "\n")
+
+
+# ---- unassigned reads ---------------------------------------------------------------------------------
+def booked_events(reads, res):
+    """(group, mate, cluster) of every read recorded as unassigned, in read order
+    (json2csv.py:884-891, 903-910, 1037-1044)."""
+    code = res.grp_code
+    lo, hi = code & 15, code >> 4
+    out = []
+    for g in np.flatnonzero((lo == _lib.UNASSIGNED_BOOK) | (hi == _lib.UNASSIGNED_BOOK)):
+        for m, c in ((0, lo[g]), (1, hi[g])):
+            if c == _lib.UNASSIGNED_BOOK:
+                a = int(reads.grp_aln_off[2 * g + m])
+                out.append((int(g), m, -(int(res.aln_assign[a]) + 2)))
+    return out
+
+
+def cluster_records(graph, reads, res):
+    """Per-cluster unassigned-read records; node ids are the GFA's (the reference keeps ``int(node_id)``)."""
+    clusters = [dict(reads_name=[], unassigned_paths=[], unassigned_abund={}, count=0, count_norm=0)
+                for _ in range(graph.n_clusters)]
+    wo = reads.aln_walk_off
+    for g, m, cid in booked_events(reads, res):
+        a = int(reads.grp_aln_off[2 * g + m])
+        lo, hi = int(wo[a]), int(wo[a + 1])
+        dense = reads.walk_node[lo:hi]
+        walk = [int(v) for v in graph.node_ids[dense]]
+        alen = reads.walk_alen[lo:hi]
+        cov = np.where(alen >= 0, alen, 0) / graph.node_len[dense]
+        neg = alen < 0
+        if neg.any():
+            cov[neg] = reads.exc_cov[-alen[neg].astype(np.int64) - 1]
+        rec = clusters[cid]
+        rec["reads_name"].append(mate_name(reads, g, m))
+        rec["unassigned_paths"].append(walk)
+        rec["count"] += 1
+        rec["count_norm"] += 1 / int(reads.aln_read_len[a])
+        ab = rec["unassigned_abund"]
+        for node, v in zip(walk, cov):
+            ab[node] = ab.get(node, 0) + float(v)
+    return clusters
+
+
+def _oriented(walk):
+    if len(walk) == 1:
+        return walk
+    rising = sum(1 for a, b in zip(walk, walk[1:]) if b - a > 0)
+    return walk if rising / (len(walk) - 1) > 0.5 else walk[::-1]          # json2csv.py:63-71
+
+
+def _relation(a, b):
+    """1 if the two walks agree around a shared node, -1 if they share a node but disagree, 0 if disjoint
+    (json2csv.py:83-97; the pivot is the first element of the set intersection, as there)."""
+    shared = list(set(a) & set(b))
+    if not shared:
+        return 0
+    pivot = shared[0]
+    pos_b = [j for j, v in enumerate(b) if v == pivot]
+    for i in (i for i, v in enumerate(a) if v == pivot):
+        for j in pos_b:
+            left, right = min(i, j), min(len(a) - i, len(b) - j)
+            if a[i - left:i + right] == b[j - left:j + right]:
+                return 1
+    return -1
+
+
+def min_strains(walks):
+    """Lower bounds on the number of strains explaining a cluster's unassigned reads (json2csv.py:149-201):
+    (max clique of the incompatibility graph, reads kept by the support filter, max clique among them,
+    mean per-node support of the kept reads)."""
+    import networkx as nx
+    import scipy.signal
+    walks = [_oriented(w) for w in walks]
+    n = len(walks)
+    conflict = nx.Graph()
+    conflict.add_nodes_from(range(n))
+    friends = [[] for _ in range(n)]
+    for i in range(n):
+        for j in range(i + 1, n):
+            rel = _relation(walks[i], walks[j])
+            if rel < 0:
+                conflict.add_edge(i, j)
+            elif rel > 0:
+                friends[i].append(j)
+                friends[j].append(i)
+    biggest = lambda gr: max((len(c) for c in nx.clique.find_cliques(gr)), default=0)   # noqa: E731
+    before = biggest(conflict)
+    kept = []
+    for i in range(n):
+        mine = set(walks[i])
+        proper = [r for r in friends[i] if not (mine <= set(walks[r]) or set(walks[r]) <= mine)]
+        keep = False
+        if len(proper) >= 2:
+            support = [1] * len(walks[i])
+            for r in friends[i]:
+                for node in walks[r]:
+                    if node in mine:
+                        support[walks[i].index(node)] += 1
+            keep = len(scipy.signal.find_peaks(-np.asarray(support))[0]) == 0
+        if keep:
+            kept.append(walks[i])
+        else:
+            conflict.remove_node(i)
+    after = biggest(conflict)
+    tally = {}
+    for w in kept:
+        for node in w:
+            tally[node] = tally.get(node, 0) + 1
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        support = np.mean(list(tally.values()))
+    return before, len(kept), after, support
+
+
+def write_unassigned(path, graph, clusters, strain_counts):
+    """strain_counts: int64[C, S] from sfb_cluster_strain_counts."""
+    keys = list(graph.header_strains)
+    with open(path, "w") as fh:
+        fh.write("Clusters;" + "".join(f"{graph.strain_names[s]};" for s in keys)
+                 + "nb_reads_unfilt;min_strains_unfilt;nb_reads_afterfilt;min_strains;mean_abund\n")
+        for cid, rec in enumerate(clusters):
+            before = kept = after = support = 0
+            if rec["count"] != 0:
+                before, kept, after, support = min_strains(rec["unassigned_paths"])
+            fh.write(f"Cluster_{cid};" + "".join(f"{int(strain_counts[cid, s])};" for s in keys)
+                     + f"{len(rec['unassigned_paths'])};{before};{kept};{after};{support}\n")
+
+
+def write_clusters_pickle(path, clusters):
+    obj = {f"cluster_{i}": dict(reads_name=c["reads_name"], unassigned_paths=c["unassigned_paths"],
+                                unassigned_abund=dict(c["unassigned_abund"])) for i, c in enumerate(clusters)}
+    with open(path, "wb") as fh:
+        pickle.dump(obj, fh)
+
+
+def summary_lines(C, thr, prefix):
+    nb = C["NB_READS"]
+    unused = C["FILTERED"] + C["UNASSIGNED"] + C["INCONSIST"] + C["INCONSIST_M"] + C["MULTI_ALIGN"]
+    used = C["ASSIGNED_U"] + C["ASSIGNED_M"]
+    return [
+        f"Done, csv results are in {prefix}_gene_table.csv, and error distribution are in {prefix}_X_freq.csv",
+        f"{nb} reads processed ({C['PAIRS']} pairs, {nb - C['PAIRS'] * 2} singles).",
+        f"{C['FILTERED']} reads did not met the user-defined mapping score threshold of {thr}.",
+        f"{C['UNASSIGNED']} reads could not be assigned to any colored path / gene.",
+        f"{C['INCONSIST'] + C['INCONSIST_M']} reads have been dropped for inconsistancies of strain assignation "
+        f"between two reads of the same pair (paired-end only).",
+        f"{C['AMBIG_CP_RESOLVED']} colored path and {C['AMBIG_RESOLVED']} strain assignation ambiguities resolved, "
+        f"and {C['AMBIG_REDUCED']} strain assignation ambiguities reduced (paired-end only).",
+        f"{C['MULTI_ALIGN']} reads shown multiple alignments that could not be resolved.",
+        f"In total, {unused} reads were not used.",
+        f"{C['ASSIGNED_U']} reads have been assigned during the first step (unique mapping).",
+        f"{C['ASSIGNED_M']} reads have been assigned during the second step (multiple mapping).",
+        f"In total, {used} ({used / nb * 100}%) reads were used.",          # ZeroDivisionError on an empty file, as :1356
+    ]

@@ -1,0 +1,140 @@
+"""CPU-only tests of the host side: GFA loader and native JSON decoder against the oracle's, on the golden
+fixtures (which hold the reference's outputs) and on fresh random cases; CLI argument handling."""
+import glob
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import casegen
+from oracle import decode as od
+from oracle import graph as og
+from strainflair_b200 import decode, gfa
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CASES = sorted(glob.glob(os.path.join(HERE, "golden", "case_*")))
+GRAPH_ARRAYS = ("node_ids", "node_len", "path_off", "path_nodes", "path_seq_len", "pstr_off", "pstr_id", "pstr_cnt",
+                "path_cluster", "clu_off", "clu_paths")
+READS_ARRAYS = ("grp_nmates", "grp_aln_off", "mate_seq_len", "aln_walk_off", "aln_read_len", "aln_bins", "walk_node",
+                "walk_alen", "exc_cov")
+
+
+def same_graph(a, b):
+    for k in GRAPH_ARRAYS:
+        assert np.array_equal(getattr(a, k), b[k]), k
+    assert a.strain_names == b["strain_names"] and a.header_strains == b["header_strains"]
+    assert a.path_names == b["path_names"]
+
+
+def same_reads(r, ro):
+    for k in READS_ARRAYS:
+        assert np.array_equal(getattr(r, k), ro[k]), k
+    assert np.array_equal(r.walk_cov, ro["walk_cov"])          # bit-exact fp64 coverages
+    assert np.array_equal(r.aln_stats, ro["aln_stats"])
+    assert [decode.mate_name(r, i // 2, i % 2) for i in range(2 * r.n_groups)] == ro["mate_names"]
+
+
+@pytest.mark.parametrize("d", CASES, ids=os.path.basename)
+def test_loader_and_decoder_match_oracle_on_golden(d):
+    files = [os.path.join(d, f) for f in ("graph.gfa", "reads.json", "dict_clusters.pickle")]
+    g = gfa.load_graph(files[0], files[2])
+    go = og.load_graph(files[0], files[2])
+    same_graph(g, go)
+    for thr, threads, block in ((0.95, 0, 0), (0.5, 3, 700), (0.0, 1, 4096), (1.0, 2, 100_000)):
+        same_reads(decode.decode_json(files[1], g, thr, threads=threads or None, block_bytes=block, want_cov=True),
+                   od.decode_json(files[1], go, thr))
+
+
+@pytest.mark.parametrize("seed", range(500, 530))
+def test_decoder_matches_oracle_on_random_cases(seed, tmp_path):
+    a, b, c = casegen.make_case(seed, str(tmp_path), n_groups=70, n_clusters=2 + seed % 4, n_strains=2 + seed % 3)
+    g = gfa.load_graph(a, c)
+    go = og.load_graph(a, c)
+    same_graph(g, go)
+    same_reads(decode.decode_json(b, g, 0.95, threads=1 + seed % 4, block_bytes=[0, 300, 5000][seed % 3], want_cov=True),
+               od.decode_json(b, go, 0.95))
+
+
+def _write(tmp_path, lines):
+    p = tmp_path / "r.json"
+    p.write_text("".join(json.dumps(x) + "\n" if not isinstance(x, str) else x for x in lines))
+    return str(p)
+
+
+GFA = "S\t1\tACGTACGTAC\nS\t2\tACGTA\nS\t3\tAAAA\nP\tNC_1.1_1\t1+,2+\t*\n"
+
+
+def _line(name, node, n, score=None, **extra):
+    ln = {"name": name, "sequence": "A" * n, "start": [0], "subpath": [
+        {"path": {"mapping": [{"position": {"node_id": str(node)}, "edit": [{"from_length": n, "to_length": n}]}]}}]}
+    if score is not None:
+        ln["subpath"][0]["score"] = score
+    ln.update(extra)
+    return ln
+
+
+@pytest.mark.parametrize("which,exc", [("unknown_node", KeyError), ("bad_json", ValueError), ("zero_len", ZeroDivisionError),
+                                        ("no_sequence", KeyError), ("next_out_of_range", IndexError)])
+def test_decoder_errors_match_oracle(which, exc, tmp_path):
+    (tmp_path / "g.gfa").write_text(GFA)
+    g = gfa.load_graph(str(tmp_path / "g.gfa"))
+    go = og.load_graph(str(tmp_path / "g.gfa"))
+    if which == "unknown_node":
+        lines = [_line("a", 99, 4, 4)]
+    elif which == "bad_json":
+        lines = [_line("a", 1, 4, 4), "{not json\n"]
+    elif which == "zero_len":
+        ln = _line("a", 1, 4, 4)
+        ln["subpath"][0]["path"]["mapping"][0]["edit"] = [{"from_length": 3}]
+        lines = [ln]
+    elif which == "no_sequence":
+        ln = _line("a", 1, 4, 4)
+        del ln["sequence"]
+        lines = [ln]
+    else:
+        ln = _line("a", 1, 4, 4)
+        ln["subpath"][0]["next"] = [7]
+        ln["sequence"] = "A" * 9
+        lines = [ln]
+    p = _write(tmp_path, lines)
+    with pytest.raises(exc):
+        od.decode_json(p, go, 0.95)
+    with pytest.raises(exc):
+        decode.decode_json(p, g, 0.95)
+
+
+def test_decoder_handles_int_and_string_fields(tmp_path):
+    """vg writes 64-bit ints as strings and 32-bit ints as numbers; the reference int()s both (json2csv.py:562-567)."""
+    (tmp_path / "g.gfa").write_text(GFA)
+    g = gfa.load_graph(str(tmp_path / "g.gfa"))
+    go = og.load_graph(str(tmp_path / "g.gfa"))
+    ln = _line("r", 1, 6, 6)
+    ln["subpath"][0]["path"]["mapping"][0]["position"] = {"node_id": 1, "offset": "2", "is_reverse": True}
+    ln["subpath"][0]["path"]["mapping"][0]["edit"] = [{"from_length": "3", "to_length": "3"},
+                                                      {"from_length": 3, "to_length": 3, "sequence": "TTT"}]
+    ln["mapping_quality"] = 60
+    ln["quality"] = "ISEhISEh"
+    ln["annotation"] = {"nested": [1, {"a": [True, None, "x\\\"y"]}]}
+    p = _write(tmp_path, [ln])
+    same_reads(decode.decode_json(p, g, 0.5, want_cov=True), od.decode_json(p, go, 0.5))
+
+
+def _cli(args, cwd):
+    return subprocess.run([sys.executable, "-m", "strainflair_b200"] + args, cwd=cwd, capture_output=True, text=True,
+                          env=dict(os.environ, PYTHONPATH=ROOT))
+
+
+def test_cli_flag_handling_matches_reference(tmp_path):
+    """-f is rejected with exit code 2 (Q2); missing inputs print the usage and exit 0 (json2csv.py:1295-1323)."""
+    r = _cli(["json2csv", "-f"], str(tmp_path))
+    assert r.returncode == 2 and "option -f not recognized" in r.stdout and "Usage:" in r.stdout
+    r = _cli(["json2csv", "-g", "x.gfa"], str(tmp_path))
+    assert r.returncode == 0 and r.stdout.startswith("Usage:")
+    r = _cli(["compute_strains_abundance", "-x"], str(tmp_path))
+    assert r.returncode == 2 and "option -x not recognized" in r.stdout
+    r = _cli(["compute_strains_abundance", "-i", "a.csv"], str(tmp_path))
+    assert r.returncode == 0 and r.stdout.startswith("Usage:")
