@@ -136,8 +136,8 @@ int sfb_strain_aggregate(int64_t n_rows, int64_t n_strains, const int32_t* row_o
     SFB_REQUIRE(n_rows >= 0 && n_strains >= 0, "negative size");
     if (n_strains == 0) return SFB_OK;
     SFB_REQUIRE(out && ws_counts, "null output");
-    SFB_REQUIRE(n_rows == 0 || (row_off && row_strain && row_count && mam && mam_nz && ratio_cov && ws_rows && ws_vals),
-                "null array");
+    // row_strain / row_count may be null when no row has a positive count
+    SFB_REQUIRE(n_rows == 0 || (row_off && mam && mam_nz && ratio_cov && ws_rows && ws_vals), "null array");
     return launch_strain_aggregate(n_rows, n_strains, row_off, row_strain, row_count, mam, mam_nz, ratio_cov, thr,
                                    ws_rows, ws_vals, ws_counts, out, (cudaStream_t)stream);
 }

@@ -67,6 +67,11 @@ def check_csv_by_column(mine_text, ref_text, sep=";", exact=True, key_col=None):
     assert sorted(mh) == sorted(rh), (mh, rh)
     assert len(mr) == len(rr), (len(mr), len(rr))
     idx = [mh.index(c) for c in rh]
+    if key_col is not None:          # rows may come in another order too (strain rows follow the column order, Q6)
+        k_m, k_r = mh.index(key_col), rh.index(key_col)
+        assert sorted(r[k_m] for r in mr) == sorted(r[k_r] for r in rr)
+        by_key = {r[k_m]: r for r in mr}
+        mr = [by_key[r[k_r]] for r in rr]
     for i, (a, b) in enumerate(zip(mr, rr)):
         assert len(a) == len(b) == len(rh), ("ragged row", i)
         for j, c in enumerate(rh):

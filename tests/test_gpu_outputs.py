@@ -66,7 +66,7 @@ def test_json2csv_cli_reproduces_reference_files(d, tmp_path):
         assert r2.returncode != 0 and "Expected" in r2.stderr
     else:
         assert r2.returncode == 0, r2.stderr[-2000:]
-        compare.check_csv_by_column((tmp_path / "prof.csv").read_text(), t["strains_profile"], sep=",", exact=False)
+        compare.check_csv_by_column((tmp_path / "prof.csv").read_text(), t["strains_profile"], sep=",", exact=False, key_col="")
 
 
 @pytest.mark.parametrize("d", [c for c in CASES], ids=os.path.basename)
@@ -84,8 +84,8 @@ def test_strain_kernel_on_reference_gene_table(d, tmp_path):
         cols, counts, table = orp.read_gene_table(str(p))
         prof = orp.strain_profile(cols, counts, table, thr)
         compare.check_csv_by_column((tmp_path / f"prof{thr}.csv").read_text(), orp.strain_profile_text(cols, prof),
-                                    sep=",", exact=False)
-    compare.check_csv_by_column((tmp_path / "prof0.5.csv").read_text(), t["strains_profile"], sep=",", exact=False)
+                                    sep=",", exact=False, key_col="")
+    compare.check_csv_by_column((tmp_path / "prof0.5.csv").read_text(), t["strains_profile"], sep=",", exact=False, key_col="")
 
 
 def test_strain_kernel_random_tables():
