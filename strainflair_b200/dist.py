@@ -1,0 +1,62 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed; NCCL on GPUs, gloo in the CPU tests).
+
+Read groups shard contiguously over the ranks (pairs are never split); the graph is replicated.  The abundance
+pass has exactly two exchange steps:
+
+1. after pass 1: all-reduce(SUM) of ``uniq_reads`` int64[P] -- the only quantity pass 2 needs from other shards
+   (json2csv.py:1141,1194,1243); exact, independent of the sharding;
+2. after pass 2: per-path scalars, histograms and counters are all-reduced; the two fp64 slot arrays are
+   reduce-scattered onto a path-partitioned layout (rank k receives the slots of its contiguous path range),
+   each rank reduces its own paths, and the small per-path table is all-gathered.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_groups, world, rank):
+    """Contiguous range of read groups owned by ``rank``."""
+    return n_groups * rank // world, n_groups * (rank + 1) // world
+
+
+def path_partition(path_off_slots, world):
+    """Split paths into ``world`` contiguous ranges of roughly equal slot count.  ``path_off_slots`` is the
+    int array [P+1] of first slots (device layout).  Returns int64[world+1] path boundaries."""
+    P = len(path_off_slots) - 1
+    n_slots = int(path_off_slots[-1])
+    targets = (np.arange(1, world, dtype=np.int64) * n_slots) // world
+    cuts = np.searchsorted(np.asarray(path_off_slots[:-1], np.int64), targets, side="left")
+    return np.concatenate(([0], np.minimum(cuts, P), [P])).astype(np.int64)
+
+
+def all_reduce_sum(t, group):
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def reduce_scatter_ranges(t, bounds, group):
+    """In place: after the call ``t[bounds[k]:bounds[k+1]]`` on rank k holds the sum over ranks of that range
+    (other ranges are left with partial sums).  One reduce per destination, issued back to back."""
+    world = dist.get_world_size(group)
+    works = []
+    for k in range(world):
+        lo, hi = int(bounds[k]), int(bounds[k + 1])
+        if hi > lo:
+            works.append(dist.reduce(t[lo:hi], dst=dist.get_global_rank(group, k) if group is not None else k,
+                                     op=dist.ReduceOp.SUM, group=group, async_op=True))
+    for w in works:
+        w.wait()
+    return t
+
+
+def all_gather_rows(local_rows, row_bounds, group):
+    """local_rows: [n_k, C] on each rank (n_k = row_bounds[k+1]-row_bounds[k]); returns the full [N, C] on every rank."""
+    world = dist.get_world_size(group)
+    counts = [int(row_bounds[k + 1] - row_bounds[k]) for k in range(world)]
+    width = local_rows.shape[1]
+    pad = max(counts) if counts else 0
+    send = torch.zeros((pad, width), dtype=local_rows.dtype, device=local_rows.device)
+    send[:local_rows.shape[0]] = local_rows
+    recv = torch.empty((world, pad, width), dtype=local_rows.dtype, device=local_rows.device)
+    dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=group)
+    return torch.cat([recv[k, :counts[k]] for k in range(world)], dim=0)

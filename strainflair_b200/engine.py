@@ -192,6 +192,12 @@ class AbundanceEngine:
         self.comm = comm
         self.acc = Accum(self.dg)
         self.table = torch.empty((max(1, graph.n_paths), _lib.TABLE_COLS), dtype=torch.float64, device=self.device)
+        self.world = 1 if comm is None else torch.distributed.get_world_size(comm)
+        self.rank = 0 if comm is None else torch.distributed.get_rank(comm)
+        if comm is not None:
+            from . import dist as sfdist
+            self.path_bounds = sfdist.path_partition(self.dg.path_off_host, self.world)
+            self.slot_bounds = self.dg.path_off_host.astype(np.int64)[self.path_bounds]
         self.work = None
         self.match_cap_hint = 0
         self.launches = 0
@@ -236,6 +242,7 @@ class AbundanceEngine:
         """Whole pass on reads already resident in HBM; leaves results on the device.
         ``marks``: optional list that receives (stage name, CUDA event recorded after the stage)."""
         import torch.distributed as dist
+        from . import dist as sfdist
 
         def mark(name):
             if marks is not None:
@@ -261,11 +268,21 @@ class AbundanceEngine:
             mark("allreduce_uniq")
         self.pass2(dr, work, uniq_global)
         mark("pass2")
-        if self.comm is not None:
-            dist.all_reduce(self.acc.i64, group=self.comm)
-            dist.all_reduce(self.acc.f64, group=self.comm)
-            mark("allreduce_accum")
-        self.path_reduce()
+        if self.comm is None:
+            self.path_reduce()
+            mark("path_reduce")
+            return work
+        # exchange 2: small per-path state everywhere, slot arrays onto the path-partitioned layout
+        P = self.acc.P
+        dist.all_reduce(self.acc.i64, group=self.comm)
+        dist.all_reduce(self.acc.f64[:3 * P], group=self.comm)
+        sfdist.reduce_scatter_ranges(self.acc.uniq_abund, self.slot_bounds, self.comm)
+        sfdist.reduce_scatter_ranges(self.acc.mult_abund, self.slot_bounds, self.comm)
+        mark("reduce_accum")
+        p0, p1 = int(self.path_bounds[self.rank]), int(self.path_bounds[self.rank + 1])
+        mine = self.path_reduce(p0, p1)
+        full = sfdist.all_gather_rows(mine, self.path_bounds, self.comm)
+        self.table[:P].copy_(full)
         mark("path_reduce")
         return work
 
@@ -284,6 +301,14 @@ class AbundanceEngine:
 
     def fetch(self, work, dr, keep_codes=True):
         acc, dg = self.acc, self.dg
+        if self.comm is not None and getattr(self, "gather_slots", True):
+            # the host copy wants whole slot arrays: complete them from their owners (not part of the pass)
+            import torch.distributed as dist
+            for arr in (acc.uniq_abund, acc.mult_abund):
+                for k in range(self.world):
+                    lo, hi = int(self.slot_bounds[k]), int(self.slot_bounds[k + 1])
+                    if hi > lo:
+                        dist.broadcast(arr[lo:hi], src=dist.get_global_rank(self.comm, k), group=self.comm)
         torch.cuda.current_stream().synchronize()
         f64 = acc.f64.cpu().numpy()
         i64 = acc.i64.cpu().numpy()

@@ -1,0 +1,45 @@
+"""Worker of tests/test_gpu_multi.py: run under torchrun with one rank per GPU."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from strainflair_b200 import dist as sfdist   # noqa: E402
+from strainflair_b200 import engine, synth    # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    graph, reads = synth.make_config("small", scale=0.4)
+    g0, g1 = sfdist.shard_bounds(reads.n_groups, world, rank)
+    eng = engine.AbundanceEngine(graph, dev, comm=dist.group.WORLD)
+    res = eng.run(reads.slice_groups(g0, g1))
+    if rank == 0:
+        single = engine.AbundanceEngine(graph, dev).run(reads)
+        for k in ("NB_READS", "PAIRS", "SINGLES", "FILTERED", "UNASSIGNED", "ASSIGNED_U", "ASSIGNED_M", "INCONSIST",
+                  "MULTI_ALIGN", "SE", "SAME_CP", "DIFF_CP", "SE_M", "SECOND_PASS", "AMBIG_CP_RESOLVED"):
+            assert res.C[k] == single.C[k], (k, res.C[k], single.C[k])
+        assert np.array_equal(res.uniq_reads, single.uniq_reads)
+        assert np.array_equal(res.hist, single.hist)
+        assert np.array_equal(res.mult_hits, single.mult_hits)
+        for name in ("uniq_norm", "mult_reads", "mult_norm", "uniq_abund", "mult_abund", "table"):
+            a, b = getattr(res, name), getattr(single, name)
+            ok = np.abs(a - b) <= 1e-9 * np.maximum(np.abs(a), np.abs(b))
+            ok |= np.isnan(a) & np.isnan(b)
+            assert ok.all(), name
+        assert np.array_equal(res.uniq_abund > 0, single.uniq_abund > 0)
+        print(f"MGPU_OK world={world} groups={reads.n_groups}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
