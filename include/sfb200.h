@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SFB_ABI_VERSION 2
+#define SFB_ABI_VERSION 3
 
 /* ---- status codes ---------------------------------------------------- */
 #define SFB_OK            0
@@ -131,7 +131,8 @@ typedef struct sfb_work {
     uint32_t* aln_match;          /* [2A]  one (x, y) pair per alignment, see encodings (8-byte aligned) */
     int32_t*  match_buf;          /* [2*match_cap] (code, path id) pairs (8-byte aligned)     */
     int64_t   match_cap;          /* pairs; < 2^31                                            */
-    unsigned long long* cursor;   /* [4]   [0] match_buf fill (pairs), [1] deferred groups, [2] app_buf fill;
+    unsigned long long* cursor;   /* [8]   [0] match_buf fill (pairs), [1] deferred groups, [2] app_buf fill,
+                                           [3]/[4] groups handed to the generic kernels of classify / pass 2;
                                            zero before sfb_match                              */
     uint8_t*  grp_code;           /* [G]                                                      */
     uint8_t*  grp_code2;          /* [G]   zero before sfb_pass2                              */
@@ -139,6 +140,7 @@ typedef struct sfb_work {
                                            -1: none; <= -2: first alignment of a mate recorded as
                                            unassigned in cluster -(v+2) (:884,:903,:1037)      */
     int32_t*  deferred;           /* [G]   group ids going to pass 2 (unordered)              */
+    int32_t*  slow;               /* [G]   scratch: groups outside the register fast path     */
     void*     app_buf;            /* [app_cap] 16-byte pass-2 work items {int32 alignment, uint32 code, double
                                            share}: scratch between the two kernels of sfb_pass2; the number
                                            of matches of a shard (<= A + match_cap) always suffices     */

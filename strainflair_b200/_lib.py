@@ -37,7 +37,7 @@ class SfbWork(C.Structure):
     _fields_ = [
         ("aln_match", C.c_void_p), ("match_buf", C.c_void_p), ("match_cap", C.c_int64), ("cursor", C.c_void_p),
         ("grp_code", C.c_void_p), ("grp_code2", C.c_void_p), ("aln_assign", C.c_void_p), ("deferred", C.c_void_p),
-        ("app_buf", C.c_void_p), ("app_cap", C.c_int64),
+        ("slow", C.c_void_p), ("app_buf", C.c_void_p), ("app_cap", C.c_int64),
     ]
 
 
@@ -62,7 +62,7 @@ SLOT_MASK, MATCH_REV, MATCH_MULTI, MATCH_NONE = 0x3FFFFFFF, 0x40000000, 0x800000
 MAX_SLOTS = 0x3FFFFFFF
 (ABSENT, FILTERED, UNASSIGNED, UNASSIGNED_BOOK, DEFER, ASSIGN_SAME, ASSIGN_DIFF, MULTI_ALIGN, INCONSIST,
  SE_COUNTED) = range(10)
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 EXPORTS = ("sfb_abi_version", "sfb_version", "sfb_last_error", "sfb_match", "sfb_classify", "sfb_pass1_scatter",
            "sfb_pass2", "sfb_path_reduce", "sfb_cluster_strain_counts", "sfb_strain_aggregate",

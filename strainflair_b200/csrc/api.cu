@@ -55,7 +55,7 @@ static int check_reads(const sfb_reads* r) {
 }
 static int check_work(const sfb_work* w) {
     SFB_REQUIRE(w, "work is null");
-    SFB_REQUIRE(w->aln_match && w->cursor && w->grp_code && w->grp_code2 && w->aln_assign && w->deferred,
+    SFB_REQUIRE(w->aln_match && w->cursor && w->grp_code && w->grp_code2 && w->aln_assign && w->deferred && w->slow,
                 "null work array");
     SFB_REQUIRE(w->match_cap >= 0 && w->match_cap < 0x7fffffffLL && (w->match_cap == 0 || w->match_buf),
                 "bad match buffer");

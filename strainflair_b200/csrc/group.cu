@@ -6,6 +6,7 @@
 // alignment); the set logic then runs on registers/L1 instead of chasing global memory.  Groups with
 // more than kCap tuples per mate take the same code through GlobalView.
 #include "common.cuh"
+#include "group_fast.cuh"
 
 namespace sfb {
 
@@ -23,7 +24,7 @@ __device__ __forceinline__ void hist_add(const Dev& d, BlockCounters& sc, int pi
 
 // fill_abund_dist, per-read part (json2csv.py:326-327, 333-339); the node loop (:329-330) is k_pass1_scatter
 __device__ __forceinline__ void assign_unique(const Dev& d, BlockCounters& sc, i64 a, uint32_t code, int pid,
-                                              int seq_len) {
+                                           int seq_len) {
     d.w.aln_assign[a] = (int32_t)code;
     atomicAdd((u64*)&d.acc.uniq_reads[pid], 1ull);
     atomicAdd(&d.acc.uniq_norm[pid], (double)seq_len / (double)d.g.path_seq_len[pid]);
@@ -142,6 +143,86 @@ __device__ __forceinline__ void classify_pair(const Dev& d, BlockCounters& sc, c
     }
 }
 
+
+// ---- register fast path of classify_pair (see group_fast.cuh) ---------------------------------
+__device__ __forceinline__ void strain_mate_fast(const Dev& d, BlockCounters& sc, const Mate& mt, const RegMate& R,
+                                                 const u64* sw, u64 common, unsigned dup, int& code, bool& defer) {
+    int nn = 0;
+    unsigned sel = 0;
+#pragma unroll
+    for (int i = 0; i < kR; ++i) {
+        const int t = __popcll(sw[i] & common);
+        nn += t;
+        sel |= (unsigned)(t > 0) << i;
+    }
+    if (nn < R.n) SFB_COUNT(sc, nn == 1 ? SFB_C_AMBIG_RESOLVED : SFB_C_AMBIG_REDUCED, 1);
+    if (nn > 1) {
+        SFB_COUNT(sc, SFB_C_SECOND_PASS, 1);
+        defer = true;
+        code = SFB_DEFER;
+        return;
+    }
+    const int i = __ffs(sel) - 1;            // the one tuple that survives, once
+    if ((dup >> i) & 1u) {
+        SFB_COUNT(sc, SFB_C_MULTI_ALIGN, 1);
+        code = SFB_MULTI_ALIGN;
+        return;
+    }
+    assign_unique(d, sc, mt.a0 + (i >= R.c0), reg_pick(R.code, i), reg_pick(R.pid, i), mt.seq_len);
+    SFB_COUNT(sc, SFB_C_ASSIGNED_U, 1);
+    SFB_COUNT(sc, SFB_C_DIFF_CP, 1);
+    code = SFB_ASSIGN_DIFF;
+}
+
+__device__ __forceinline__ void classify_pair_fast(const Dev& d, BlockCounters& sc, const Mate* mt, const RegMate& A,
+                                                   const RegMate& B, int* code, bool& defer) {
+    const PairMasks pm = pair_masks(A, B);
+    const unsigned inter0 = pm.in_other[0] & pm.first[0];
+    const int n_inter = __popc(inter0);
+    if (n_inter > 1) {
+        SFB_COUNT(sc, SFB_C_SECOND_PASS, 2);
+        defer = true;
+        code[0] = code[1] = SFB_DEFER;
+        return;
+    }
+    if (n_inter == 1) {
+        const int i0 = __ffs(inter0) - 1;
+        const int p = reg_pick(A.pid, i0);
+        unsigned jm = 0;
+#pragma unroll
+        for (int j = 0; j < kR; ++j) jm |= (unsigned)(B.pid[j] == p) << j;
+        const int j0 = __ffs(jm) - 1;
+        const bool multi[2] = {((pm.dup[0] >> i0) & 1u) != 0, __popc(jm) > 1};
+        const int idx[2] = {i0, j0};
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const RegMate& R = k ? B : A;
+            if (multi[k]) {
+                SFB_COUNT(sc, SFB_C_MULTI_ALIGN, 1);
+                code[k] = SFB_MULTI_ALIGN;
+                continue;
+            }
+            assign_unique(d, sc, mt[k].a0 + (idx[k] >= R.c0), reg_pick(R.code, idx[k]), p, mt[k].seq_len);
+            SFB_COUNT(sc, SFB_C_ASSIGNED_U, 1);
+            SFB_COUNT(sc, SFB_C_SAME_CP, 1);
+            if (R.n > 1) SFB_COUNT(sc, SFB_C_AMBIG_CP_RESOLVED, 1);
+            code[k] = SFB_ASSIGN_SAME;
+        }
+        return;
+    }
+    u64 s0[kR], s1[kR];
+    strain_words(d.g, A, s0);
+    strain_words(d.g, B, s1);
+    const u64 common = or_all(s0) & or_all(s1);
+    if (!common) {
+        SFB_COUNT(sc, SFB_C_INCONSIST, 2);
+        code[0] = code[1] = SFB_INCONSIST;
+        return;
+    }
+    strain_mate_fast(d, sc, mt[0], A, s0, common, pm.dup[0], code[0], defer);
+    strain_mate_fast(d, sc, mt[1], B, s1, common, pm.dup[1], code[1], defer);
+}
+
 // single-end style (json2csv.py:1003-1050)
 __device__ __forceinline__ int classify_single(const Dev& d, BlockCounters& sc, const Mate& mt, bool& defer) {
     SFB_COUNT(sc, SFB_C_SINGLES, 1);
@@ -190,13 +271,47 @@ __device__ __forceinline__ void classify_both_unassigned(const Dev& d, BlockCoun
     }
 }
 
+// Generic handling of a pair whose mates both have alignments (json2csv.py:847-1000); `single` is set
+// when one mate has no colored path and the other continues single-end style.
+__device__ __forceinline__ void classify_aligned_pair_generic(const Dev& d, BlockCounters& sc, const Mate* mt, int* code,
+                                                              bool& defer, int& single) {
+    LocalView lv;
+    GlobalView gv;
+    const bool fits = lv.load(d.w, mt);
+    if (!fits) gv.init(d.w, mt);
+    const int nt0 = fits ? lv.nt(0) : gv.nt(0), nt1 = fits ? lv.nt(1) : gv.nt(1);
+    if (nt0 == 0 && nt1 == 0) {
+        classify_both_unassigned(d, sc, mt, code);
+    } else if (nt0 == 0 || nt1 == 0) {
+        // one mate without colored path (json2csv.py:895-916)
+        SFB_COUNT(sc, SFB_C_UNASSIGNED, 1);
+        SFB_COUNT(sc, SFB_C_ONE_NOCP, 1);
+        const int gone = nt0 == 0 ? 0 : 1;
+        code[gone] = SFB_UNASSIGNED;
+        bool bad = false;
+        for (int j = 0; j < mt[gone].na; ++j) bad |= first_cluster(d, mt[gone].a0 + j) == -2;
+        if (bad) {
+            SFB_COUNT(sc, SFB_C_NO_PATH, 1);
+        } else if (mt[gone].na == 1) {
+            book(d, sc, mt[gone], first_cluster(d, mt[gone].a0));
+            code[gone] = SFB_UNASSIGNED_BOOK;
+        }
+        single = 1 - gone;
+    } else if (fits) {
+        classify_pair(d, sc, lv, mt, code, defer);
+    } else {
+        classify_pair(d, sc, gv, mt, code, defer);
+    }
+}
+
+// Fast kernel: everything except aligned pairs that do not fit the register path, which go to w.slow.
 __global__ void __launch_bounds__(128) k_classify(Dev d) {
     __shared__ BlockCounters sc;
     block_counters_zero(sc);
     __syncthreads();
     const i64 n_round = (d.r.n_groups + 127) & ~(i64)127;
     for (i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x; g < n_round; g += (i64)gridDim.x * blockDim.x) {
-        bool defer = false;
+        bool defer = false, slow = false;
         if (g < d.r.n_groups) {
             const int nm = d.r.grp_nmates[g];
             Mate mt[2];
@@ -219,39 +334,48 @@ __global__ void __launch_bounds__(128) k_classify(Dev d) {
                     code[gone] = SFB_FILTERED;
                     single = 1 - gone;
                 } else {
-                    LocalView lv;
-                    GlobalView gv;
-                    const bool fits = lv.load(d.w, mt);
-                    if (!fits) gv.init(d.w, mt);
-                    const int nt0 = fits ? lv.nt(0) : gv.nt(0), nt1 = fits ? lv.nt(1) : gv.nt(1);
-                    if (nt0 == 0 && nt1 == 0) {
-                        classify_both_unassigned(d, sc, mt, code);
-                    } else if (nt0 == 0 || nt1 == 0) {
-                        // one mate without colored path (json2csv.py:895-916)
-                        SFB_COUNT(sc, SFB_C_UNASSIGNED, 1);
-                        SFB_COUNT(sc, SFB_C_ONE_NOCP, 1);
-                        const int gone = nt0 == 0 ? 0 : 1;
-                        code[gone] = SFB_UNASSIGNED;
-                        bool bad = false;
-                        for (int j = 0; j < mt[gone].na; ++j) bad |= first_cluster(d, mt[gone].a0 + j) == -2;
-                        if (bad) {
-                            SFB_COUNT(sc, SFB_C_NO_PATH, 1);
-                        } else if (mt[gone].na == 1) {
-                            book(d, sc, mt[gone], first_cluster(d, mt[gone].a0));
-                            code[gone] = SFB_UNASSIGNED_BOOK;
-                        }
-                        single = 1 - gone;
-                    } else if (fits) {
-                        classify_pair(d, sc, lv, mt, code, defer);
-                    } else {
-                        classify_pair(d, sc, gv, mt, code, defer);
-                    }
+                    RegMate A, B;
+                    const bool quick = d.g.mask_words == 1 && reg_load(d.w, mt[0], -2, A) && reg_load(d.w, mt[1], -32, B) &&
+                                       A.n > 0 && B.n > 0;
+                    if (quick) classify_pair_fast(d, sc, mt, A, B, code, defer);
+                    else slow = true;
                 }
             }
+            if (!slow) {
+                if (single >= 0) code[single] = classify_single(d, sc, mt[single], defer);
+                d.w.grp_code[g] = (uint8_t)(code[0] | (code[1] << 4));
+            }
+        }
+        // warp-aggregated appends: deferred groups (pass 2) and groups for the generic kernel
+        const u64 pos = warp_claim(d.w.cursor + 1, defer ? 1u : 0u);
+        if (defer) d.w.deferred[pos] = (int32_t)g;
+        const u64 spos = warp_claim(d.w.cursor + 3, slow ? 1u : 0u);
+        if (slow) d.w.slow[spos] = (int32_t)g;
+    }
+    __syncthreads();
+    block_counters_flush(sc, d.acc.counters);
+}
+
+__global__ void __launch_bounds__(128) k_classify_slow(Dev d) {
+    __shared__ BlockCounters sc;
+    block_counters_zero(sc);
+    __syncthreads();
+    const i64 n_slow = (i64)d.w.cursor[3];
+    const i64 n_round = (n_slow + 127) & ~(i64)127;
+    for (i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x; q < n_round; q += (i64)gridDim.x * blockDim.x) {
+        bool defer = false;
+        i64 g = 0;
+        if (q < n_slow) {
+            g = d.w.slow[q];
+            Mate mt[2];
+            mate_load(d.r, g, 0, mt[0]);
+            mate_load(d.r, g, 1, mt[1]);
+            int code[2] = {SFB_ABSENT, SFB_ABSENT};
+            int single = -1;
+            classify_aligned_pair_generic(d, sc, mt, code, defer, single);
             if (single >= 0) code[single] = classify_single(d, sc, mt[single], defer);
             d.w.grp_code[g] = (uint8_t)(code[0] | (code[1] << 4));
         }
-        // warp-aggregated append to the deferred list
         const u64 pos = warp_claim(d.w.cursor + 1, defer ? 1u : 0u);
         if (defer) d.w.deferred[pos] = (int32_t)g;
     }
@@ -343,7 +467,7 @@ __device__ __forceinline__ void p2_decide_pair(const Dev& d, BlockCounters& sc, 
 
 // json2csv.py:1155-1156 (and :1207-1208, :1265-1266) + the work item for the node loop (:1157-1158)
 __device__ __forceinline__ void emit_app(const Dev& d, App* out, i64 a, uint32_t code, int pid, int seq_len,
-                                         double ratio, int times) {
+                                      double ratio, int times) {
     atomicAdd(&d.acc.mult_reads[pid], ratio * (double)times);
     atomicAdd(&d.acc.mult_norm[pid], (ratio * (double)seq_len / (double)d.g.path_seq_len[pid]) * (double)times);
     atomicAdd(&d.acc.mult_hits[pid], (unsigned)times);
@@ -393,6 +517,131 @@ __device__ __forceinline__ void p2_emit(const Dev& d, BlockCounters& sc, const V
     }
 }
 
+
+// ---- register fast path of pass 2 (see group_fast.cuh) -----------------------------------------
+struct FastPlan {
+    int mode[2];
+    unsigned sel[2];          // tuples that receive a share
+    int n_inter;
+    long long total_inter;
+    long long total_strain[2];
+    int nn[2];
+    u64 common;
+    long long total_single[2];   // per alignment of the single-end mate
+};
+
+__device__ __forceinline__ void p2_fast_decide_pair(const Dev& d, BlockCounters& sc, const RegMate& A, const RegMate& B,
+                                                    const long long* U, FastPlan& pl, int* code) {
+    const PairMasks pm = pair_masks(A, B);
+    const unsigned inter0 = pm.in_other[0] & pm.first[0];
+    pl.n_inter = __popc(inter0);
+    if (pl.n_inter >= 1) {
+        long long total = 0;
+        for (unsigned rest = inter0; rest; rest &= rest - 1) total += U[reg_pick(A.pid, __ffs(rest) - 1)];
+        pl.total_inter = total;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (pm.in_other[k] & pm.dup[k]) {       // a common path with several tuples in this mate
+                SFB_COUNT(sc, SFB_C_MULTI_ALIGN, 1);
+                code[k] = SFB_P2_MULTI_ALIGN;
+                continue;
+            }
+            SFB_COUNT(sc, SFB_C_ASSIGNED_M, 1);
+            code[k] = SFB_P2_ASSIGNED;
+            pl.mode[k] = kInter;
+            pl.sel[k] = pm.in_other[k];
+        }
+        return;
+    }
+    u64 s0[kR], s1[kR];
+    strain_words(d.g, A, s0);
+    strain_words(d.g, B, s1);
+    pl.common = or_all(s0) & or_all(s1);
+    if (!pl.common) {
+        SFB_COUNT(sc, SFB_C_INCONSIST_M, (A.n == 1 || B.n == 1) ? 1 : 2);
+        code[0] = code[1] = SFB_P2_INCONSIST;
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const RegMate& R = k ? B : A;
+        const u64* sw = k ? s1 : s0;
+        int nn = 0;
+        unsigned sel = 0;
+        long long tot = 0;
+#pragma unroll
+        for (int i = 0; i < kR; ++i) {
+            const int t = __popcll(sw[i] & pl.common);
+            nn += t;
+            sel |= (unsigned)(t > 0) << i;
+        }
+        pl.nn[k] = nn;
+        if (nn <= 1) continue;                       // handled in pass 1 (json2csv.py:1185)
+        if (sel & pm.dup[k]) {
+            SFB_COUNT(sc, SFB_C_MULTI_ALIGN, 1);
+            code[k] = SFB_P2_MULTI_ALIGN;
+            continue;
+        }
+        for (unsigned rest = sel; rest; rest &= rest - 1) {
+            const int i = __ffs(rest) - 1;
+            tot += U[reg_pick(R.pid, i)] * __popcll(reg_pick(sw, i) & pl.common);
+        }
+        SFB_COUNT(sc, SFB_C_ASSIGNED_M, 1);
+        code[k] = SFB_P2_ASSIGNED;
+        pl.mode[k] = kStrain;
+        pl.sel[k] = sel;
+        pl.total_strain[k] = tot;
+    }
+}
+
+__device__ __forceinline__ void p2_fast_single(const Dev& d, BlockCounters& sc, const RegMate& R, const long long* U,
+                                               FastPlan& pl, int k) {
+    long long t0 = 0, t1 = 0;
+    for (int i = 0; i < R.n; ++i) {
+        const long long u = U[reg_pick(R.pid, i)];
+        if (i < R.c0) t0 += u; else t1 += u;
+    }
+    pl.total_single[0] = t0;
+    pl.total_single[1] = t1;
+    pl.mode[k] = kSingle;
+    pl.sel[k] = (1u << R.n) - 1u;
+}
+
+__device__ __forceinline__ App* p2_fast_emit(const Dev& d, BlockCounters& sc, const Mate& mt, const RegMate& R, int mode,
+                                             unsigned sel, const FastPlan& pl, int k, const long long* U, App* out) {
+    for (unsigned rest = sel; rest; rest &= rest - 1) {
+        const int i = __ffs(rest) - 1;
+        const int pid = reg_pick(R.pid, i);
+        const long long u = U[pid];
+        const int second = i >= R.c0;
+        double w;
+        int times = 1;
+        if (mode == kInter) {
+            w = ratio_of(u, pl.total_inter, pl.n_inter);
+        } else if (mode == kStrain) {
+            times = __popcll(d.g.path_smask[pid] & pl.common);
+            w = ratio_of(u, pl.total_strain[k], pl.nn[k]);
+        } else {
+            hist_add(d, sc, pid, mt.a0 + second);                                  // json2csv.py:1246-1252
+            w = ratio_of(u, pl.total_single[second], second ? R.n - R.c0 : R.c0);
+        }
+        emit_app(d, out++, mt.a0 + second, reg_pick(R.code, i), pid, mt.seq_len, w, times);
+    }
+    return out;
+}
+
+// single-end bookkeeping shared by both resolve kernels (json2csv.py:1270-1274)
+__device__ __forceinline__ int p2_single_outcome(BlockCounters& sc, int n_tuples) {
+    if (n_tuples > 0) {
+        SFB_COUNT(sc, SFB_C_ASSIGNED_M, 1);
+        SFB_COUNT(sc, SFB_C_SE_M, 1);
+        return SFB_P2_SE_ASSIGNED;
+    }
+    SFB_COUNT(sc, SFB_C_UNASSIGNED, 1);
+    return SFB_P2_UNASSIGNED;
+}
+
+// Fast kernel over the deferred groups; groups that do not fit the register path go to w.slow (cursor[4]).
 __global__ void __launch_bounds__(128) k_pass2_resolve(Dev d, const long long* __restrict__ U) {
     __shared__ BlockCounters sc;
     block_counters_zero(sc);
@@ -402,6 +651,67 @@ __global__ void __launch_bounds__(128) k_pass2_resolve(Dev d, const long long* _
     App* apps = reinterpret_cast<App*>(d.w.app_buf);
     for (i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x; q < n_round; q += (i64)gridDim.x * blockDim.x) {
         const bool live = q < n_def;
+        RegMate A, B;
+        FastPlan fp;
+        fp.mode[0] = fp.mode[1] = kNone;
+        fp.sel[0] = fp.sel[1] = 0;
+        Mate mt[2];
+        bool slow = false;
+        i64 g = 0;
+        unsigned need = 0;
+        if (live) {
+            g = d.w.deferred[q];
+            const int nm = d.r.grp_nmates[g];
+            mate_load(d.r, g, 0, mt[0]);
+            mate_load(d.r, g, 1, mt[1]);
+            const bool quick = d.g.mask_words == 1 && reg_load(d.w, mt[0], -2, A) && reg_load(d.w, mt[1], -32, B);
+            if (!quick) {
+                slow = true;
+            } else {
+                int code[2] = {SFB_P2_NONE, SFB_P2_NONE};
+                int single = nm == 1 ? 0 : -1;
+                if (nm == 2) {
+                    if (mt[0].na == 0 || mt[1].na == 0) single = mt[0].na == 0 ? 1 : 0;      // json2csv.py:1088-1093
+                    else if (A.n == 0 || B.n == 0) single = A.n == 0 ? 1 : 0;                // :1117-1122
+                    else p2_fast_decide_pair(d, sc, A, B, U, fp, code);
+                }
+                if (single == 0) {
+                    p2_fast_single(d, sc, A, U, fp, 0);
+                    code[0] = p2_single_outcome(sc, A.n);
+                } else if (single == 1) {
+                    p2_fast_single(d, sc, B, U, fp, 1);
+                    code[1] = p2_single_outcome(sc, B.n);
+                }
+                d.w.grp_code2[g] = (uint8_t)(code[0] | (code[1] << 4));
+                need = (unsigned)(__popc(fp.sel[0]) + __popc(fp.sel[1]));
+            }
+        }
+        const u64 pos = warp_claim(d.w.cursor + 2, need);
+        if (live && need) {
+            SFB_COUNT(sc, SFB_C_ST_P2_APPLIED, (int)need);
+            if (pos + need <= (u64)d.w.app_cap) {
+                App* out = p2_fast_emit(d, sc, mt[0], A, fp.mode[0], fp.sel[0], fp, 0, U, apps + pos);
+                p2_fast_emit(d, sc, mt[1], B, fp.mode[1], fp.sel[1], fp, 1, U, out);
+            } else {
+                SFB_COUNT(sc, SFB_C_MATCH_OVERFLOW, (int)need);
+            }
+        }
+        const u64 spos = warp_claim(d.w.cursor + 4, slow ? 1u : 0u);
+        if (slow) d.w.slow[spos] = (int32_t)g;
+    }
+    __syncthreads();
+    block_counters_flush(sc, d.acc.counters);
+}
+
+__global__ void __launch_bounds__(128) k_pass2_resolve_slow(Dev d, const long long* __restrict__ U) {
+    __shared__ BlockCounters sc;
+    block_counters_zero(sc);
+    __syncthreads();
+    const i64 n_slow = (i64)d.w.cursor[4];
+    const i64 n_round = (n_slow + 127) & ~(i64)127;
+    App* apps = reinterpret_cast<App*>(d.w.app_buf);
+    for (i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x; q < n_round; q += (i64)gridDim.x * blockDim.x) {
+        const bool live = q < n_slow;
         LocalView lv;
         GlobalView gv;
         Mate mt[2];
@@ -412,7 +722,7 @@ __global__ void __launch_bounds__(128) k_pass2_resolve(Dev d, const long long* _
         i64 g = 0;
         int code[2] = {SFB_P2_NONE, SFB_P2_NONE};
         if (live) {
-            g = d.w.deferred[q];
+            g = d.w.slow[q];
             const int nm = d.r.grp_nmates[g];
             mate_load(d.r, g, 0, mt[0]);
             mate_load(d.r, g, 1, mt[1]);
@@ -421,8 +731,8 @@ __global__ void __launch_bounds__(128) k_pass2_resolve(Dev d, const long long* _
             const int nt0 = fits ? lv.nt(0) : gv.nt(0), nt1 = fits ? lv.nt(1) : gv.nt(1);
             int single = nm == 1 ? 0 : -1;
             if (nm == 2) {
-                if (mt[0].na == 0 || mt[1].na == 0) single = mt[0].na == 0 ? 1 : 0;          // json2csv.py:1088-1093
-                else if (nt0 == 0 || nt1 == 0) single = nt0 == 0 ? 1 : 0;                    // :1117-1122
+                if (mt[0].na == 0 || mt[1].na == 0) single = mt[0].na == 0 ? 1 : 0;
+                else if (nt0 == 0 || nt1 == 0) single = nt0 == 0 ? 1 : 0;
                 else if (fits) p2_decide_pair(d, sc, lv, U, pl, code);
                 else p2_decide_pair(d, sc, gv, U, pl, code);
             }
@@ -430,14 +740,7 @@ __global__ void __launch_bounds__(128) k_pass2_resolve(Dev d, const long long* _
                 const int nts = single == 0 ? nt0 : nt1;
                 pl.mode[single] = kSingle;
                 pl.napp[single] = nts;
-                if (nts > 0) {
-                    SFB_COUNT(sc, SFB_C_ASSIGNED_M, 1);
-                    SFB_COUNT(sc, SFB_C_SE_M, 1);
-                    code[single] = SFB_P2_SE_ASSIGNED;
-                } else {
-                    SFB_COUNT(sc, SFB_C_UNASSIGNED, 1);
-                    code[single] = SFB_P2_UNASSIGNED;
-                }
+                code[single] = p2_single_outcome(sc, nts);
             }
             d.w.grp_code2[g] = (uint8_t)(code[0] | (code[1] << 4));
         }
@@ -461,13 +764,17 @@ int launch_classify(const Dev& d, cudaStream_t st) {
     if (d.r.n_groups == 0) return SFB_OK;
     const unsigned grid = (unsigned)min((i64)kSMs * 16, (i64)blocks_for(d.r.n_groups, 128));
     k_classify<<<grid, 128, 0, st>>>(d);
-    return check_launch("k_classify");
+    SFB_TRY(check_launch("k_classify"));
+    k_classify_slow<<<kSMs * 4, 128, 0, st>>>(d);          // usually a few percent of the groups
+    return check_launch("k_classify_slow");
 }
 int launch_pass2_resolve(const Dev& d, const long long* U, cudaStream_t st) {
     if (d.r.n_groups == 0) return SFB_OK;
     const unsigned grid = (unsigned)min((i64)kSMs * 16, (i64)blocks_for(d.r.n_groups, 128));
     k_pass2_resolve<<<grid, 128, 0, st>>>(d, U);
-    return check_launch("k_pass2_resolve");
+    SFB_TRY(check_launch("k_pass2_resolve"));
+    k_pass2_resolve_slow<<<kSMs * 4, 128, 0, st>>>(d, U);
+    return check_launch("k_pass2_resolve_slow");
 }
 
 }  // namespace sfb

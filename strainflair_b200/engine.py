@@ -121,7 +121,8 @@ class Work:
             aln_match=torch.empty(max(1, n_alns), dtype=torch.int64, device=device),      # (x, y) pairs
             match_buf=torch.empty(self.match_cap, dtype=torch.int64, device=device),       # (code, pid) pairs
             app_buf=torch.empty(2 * self.app_cap, dtype=torch.int64, device=device),       # 16-byte items
-            cursor=torch.zeros(4, dtype=torch.int64, device=device),
+            cursor=torch.zeros(8, dtype=torch.int64, device=device),
+            slow=torch.empty(max(1, n_groups), dtype=i32, device=device),
             grp_code=torch.zeros(max(1, n_groups), dtype=u8, device=device),
             grp_code2=torch.zeros(max(1, n_groups), dtype=u8, device=device),
             aln_assign=torch.empty(max(1, n_alns), dtype=i32, device=device),

@@ -84,6 +84,30 @@ def test_synthetic_matches_oracle(name, scale):
     check_against_oracle(graph, reads, res, orc)
 
 
+@pytest.mark.parametrize("n_hap,flip", [(16, 0.02), (40, 0.01)])
+def test_many_candidate_paths_take_the_generic_kernels(n_hap, flip):
+    """More than 8 (LocalView) and more than 32 (GlobalView) match tuples per mate."""
+    need_gpu()
+    graph = synth.make_graph(11, n_clusters=12, chain_len=20, hap_lo=n_hap, hap_hi=n_hap, n_strains=9, bubble_p=0.4,
+                             flip_p=flip)
+    reads = synth.make_reads(graph, 12, n_pairs=1500, read_len=100, p_tie=0.3)
+    res = engine.abundance_pass(graph, reads)
+    orc = oa.AbundanceOracle(graph.as_dict(), reads.as_dict()).run()
+    per_mate = res.C["ST_TUPLES"] / max(1, reads.n_alns)
+    assert per_mate > (8 if n_hap == 16 else 20), per_mate
+    check_against_oracle(graph, reads, res, orc)
+
+
+def test_more_than_64_strains_uses_multiword_masks():
+    need_gpu()
+    graph = synth.make_graph(21, n_clusters=30, chain_len=14, hap_lo=1, hap_hi=6, n_strains=150, bubble_p=0.4, flip_p=0.3)
+    reads = synth.make_reads(graph, 22, n_pairs=2500, read_len=80, p_same_path=0.6)
+    res = engine.abundance_pass(graph, reads)
+    orc = oa.AbundanceOracle(graph.as_dict(), reads.as_dict()).run()
+    assert orc.C["DIFF_CP"] > 0 and orc.C["INCONSIST"] > 0
+    check_against_oracle(graph, reads, res, orc)
+
+
 def test_explicit_coverage_records():
     need_gpu()
     gkw, rkw = synth.CONFIGS["tiny"]
