@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SFB_ABI_VERSION 3
+#define SFB_ABI_VERSION 4
 
 /* ---- status codes ---------------------------------------------------- */
 #define SFB_OK            0
@@ -105,7 +105,11 @@ typedef struct sfb_graph {
     const int32_t*  slot_path;     /* [n_slots] path id owning the slot                      */
     const int32_t*  path_off;      /* [n_paths+1]                                            */
     const int32_t*  occ_off;       /* [n_nodes+1] node -> occurrences (Node.traversed_path + position scan, :352-357) */
-    const int32_t*  occ_slot;      /* [n_slots-n_paths] slots of the node, ascending          */
+    const int32_t*  occ_pair;      /* [2*(n_slots-n_paths)] per occurrence, ascending by slot: (slot, node of
+                                      slot+1) -- the successor lets a candidate be rejected without touching
+                                      slot_node (8-byte aligned)                                          */
+    const int32_t*  blk_path;      /* [(n_slots+63)/64] path id owning slot 64*b (slot -> path without the
+                                      n_slots-sized slot_path gather)                                     */
     const int64_t*  path_seq_len;  /* [n_paths] get_sequence_length (:220-221)               */
     const int32_t*  path_nstrain;  /* [n_paths] len(path.strain_ids)                         */
     const int32_t*  path_strain0;  /* [n_paths] first strain id of the path (histogram row, :334) */

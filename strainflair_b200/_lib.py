@@ -18,7 +18,7 @@ class SfbGraph(C.Structure):
         ("n_nodes", C.c_int64), ("n_paths", C.c_int64), ("n_slots", C.c_int64), ("n_strains", C.c_int64),
         ("mask_words", C.c_int64),
         ("slot_node", C.c_void_p), ("slot_len", C.c_void_p), ("slot_path", C.c_void_p), ("path_off", C.c_void_p),
-        ("occ_off", C.c_void_p), ("occ_slot", C.c_void_p), ("path_seq_len", C.c_void_p),
+        ("occ_off", C.c_void_p), ("occ_pair", C.c_void_p), ("blk_path", C.c_void_p), ("path_seq_len", C.c_void_p),
         ("path_nstrain", C.c_void_p), ("path_strain0", C.c_void_p), ("path_smask", C.c_void_p),
         ("path_cluster", C.c_void_p),
     ]
@@ -62,7 +62,7 @@ SLOT_MASK, MATCH_REV, MATCH_MULTI, MATCH_NONE = 0x3FFFFFFF, 0x40000000, 0x800000
 MAX_SLOTS = 0x3FFFFFFF
 (ABSENT, FILTERED, UNASSIGNED, UNASSIGNED_BOOK, DEFER, ASSIGN_SAME, ASSIGN_DIFF, MULTI_ALIGN, INCONSIST,
  SE_COUNTED) = range(10)
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 EXPORTS = ("sfb_abi_version", "sfb_version", "sfb_last_error", "sfb_match", "sfb_classify", "sfb_pass1_scatter",
            "sfb_pass2", "sfb_path_reduce", "sfb_cluster_strain_counts", "sfb_strain_aggregate",
@@ -77,7 +77,7 @@ _lib = None
 
 
 def lib_path():
-    return _build.LIB
+    return os.environ.get("SFB200_LIB", _build.LIB)
 
 
 def load(build_if_missing=True):
@@ -86,7 +86,7 @@ def load(build_if_missing=True):
     if _lib is not None:
         return _lib
     path = lib_path()
-    if build_if_missing:
+    if build_if_missing and "SFB200_LIB" not in os.environ:
         try:
             _build.build()
         except Exception as e:          # no nvcc on this machine: use the prebuilt .so if there is one

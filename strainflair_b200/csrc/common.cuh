@@ -28,6 +28,21 @@ constexpr int kSMs = 148;   // B200: persistent grids are sized in multiples of 
 
 static inline unsigned blocks_for(i64 n, int per) { return (unsigned)((n + per - 1) / per); }
 
+// Grid of a persistent kernel: every SM filled with as many CTAs as are resident at once (one wave), never
+// more CTAs than there is work.  The occupancy is queried once per kernel.
+template <class K>
+static inline unsigned persistent_grid(K kernel, int block, i64 work_blocks, int* cache) {
+    if (*cache == 0) {
+        int per_sm = 0, dev = 0, sms = kSMs;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+        *cache = per_sm * sms;
+    }
+    const i64 g = work_blocks < (i64)*cache ? work_blocks : (i64)*cache;
+    return (unsigned)(g < 1 ? 1 : g);
+}
+
 struct Dev {
     sfb_graph g;
     sfb_reads r;

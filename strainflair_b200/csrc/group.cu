@@ -36,7 +36,7 @@ __device__ __forceinline__ int first_cluster(const Dev& d, i64 a) {
     const int n0 = d.r.walk_node[d.r.aln_walk_off[a]];
     const int o = d.g.occ_off[n0];
     if (o == d.g.occ_off[n0 + 1]) return -2;
-    return d.g.path_cluster[d.g.slot_path[d.g.occ_slot[o]]];
+    return d.g.path_cluster[d.g.slot_path[d.g.occ_pair[2 * (size_t)o]]];
 }
 __device__ __forceinline__ void book(const Dev& d, BlockCounters& sc, const Mate& mt, int cluster) {
     if (cluster < 0) { SFB_COUNT(sc, SFB_C_NO_CLUSTER, 1); return; }
@@ -762,18 +762,22 @@ __global__ void __launch_bounds__(128) k_pass2_resolve_slow(Dev d, const long lo
 
 int launch_classify(const Dev& d, cudaStream_t st) {
     if (d.r.n_groups == 0) return SFB_OK;
-    const unsigned grid = (unsigned)min((i64)kSMs * 16, (i64)blocks_for(d.r.n_groups, 128));
+    static int c_fast = 0, c_slow = 0;
+    const unsigned grid = persistent_grid(k_classify, 128, blocks_for(d.r.n_groups, 128), &c_fast);
     k_classify<<<grid, 128, 0, st>>>(d);
     SFB_TRY(check_launch("k_classify"));
-    k_classify_slow<<<kSMs * 4, 128, 0, st>>>(d);          // usually a few percent of the groups
+    const unsigned grid2 = persistent_grid(k_classify_slow, 128, blocks_for(d.r.n_groups, 128), &c_slow);
+    k_classify_slow<<<grid2, 128, 0, st>>>(d);             // usually a few percent of the groups
     return check_launch("k_classify_slow");
 }
 int launch_pass2_resolve(const Dev& d, const long long* U, cudaStream_t st) {
     if (d.r.n_groups == 0) return SFB_OK;
-    const unsigned grid = (unsigned)min((i64)kSMs * 16, (i64)blocks_for(d.r.n_groups, 128));
+    static int c_fast = 0, c_slow = 0;
+    const unsigned grid = persistent_grid(k_pass2_resolve, 128, blocks_for(d.r.n_groups, 128), &c_fast);
     k_pass2_resolve<<<grid, 128, 0, st>>>(d, U);
     SFB_TRY(check_launch("k_pass2_resolve"));
-    k_pass2_resolve_slow<<<kSMs * 4, 128, 0, st>>>(d, U);
+    const unsigned grid2 = persistent_grid(k_pass2_resolve_slow, 128, blocks_for(d.r.n_groups, 128), &c_slow);
+    k_pass2_resolve_slow<<<grid2, 128, 0, st>>>(d, U);
     return check_launch("k_pass2_resolve_slow");
 }
 

@@ -1,12 +1,11 @@
 // k_match: Pangenome.get_matching_path (json2csv.py:341-363) for the walk and, if longer than one node,
 // the reversed walk (callers :855-866, :1024-1026, :1103-1114, :1231-1233).
 //
-// One thread per retained alignment.  The node -> slot occurrence index replaces Node.traversed_path and
-// the linear position scan; a candidate is rejected at its first differing node, and the sentinel slot
-// after every path rejects walks that run off the path end.  The index and the path slots are L2-resident
-// gathers (tens of MB), the walk arrays stream from HBM once.  Output: 8 bytes per alignment, plus one
-// (code, path id) pair per match for alignments with several matches, in space claimed with one atomic
-// per warp.
+// The node -> (slot, successor) occurrence index replaces Node.traversed_path and the linear position scan; a
+// candidate is rejected by the successor stored in the index or at its first differing node, and the sentinel
+// slot after every path rejects walks that run off the path end.  The walk arrays stream from HBM once; the index
+// is gathered (partly L2 resident).  Output: 8 bytes per alignment, plus one (code, path id) pair per match for
+// alignments with several matches, in space claimed with one atomic per warp.
 #include "common.cuh"
 
 namespace sfb {
@@ -17,85 +16,235 @@ struct MatchStats {
     int cand, cmp;
 };
 
+// slot -> path id through the 64-slot block table and at most a few steps along path_off (both small, cache resident)
+__device__ __forceinline__ int path_of_slot(const sfb_graph& g, int s) {
+    int p = g.blk_path[s >> 6];
+    while (g.path_off[p + 1] <= s) ++p;
+    return p;
+}
+
+// One orientation: candidates are the occurrences of `anchor` (= the first node of the oriented walk); `second` is the
+// oriented walk's second node and step = +1 (walk as is) or -1 (reversed walk, read from its last record backwards).
 template <bool kEmit>
-__device__ __forceinline__ int match_sweep(const sfb_graph& g, const sfb_reads& r, i64 w0, int L, uint2* keep,
-                                           uint2* out, MatchStats& st) {
-    int n = 0;
-    const int first = r.walk_node[w0];
-    for (int o = g.occ_off[first], oe = g.occ_off[first + 1]; o < oe; ++o) {
-        const int s = g.occ_slot[o];
-        int i = 1;
-        for (; i < L; ++i)
-            if (g.slot_node[s + i] != r.walk_node[w0 + i]) break;      // sentinel (-1) stops overruns
+__device__ __forceinline__ int sweep_one(const sfb_graph& g, const sfb_reads& r, i64 w_first, int step, int L, int anchor,
+                                         int second, uint32_t flag, int n, uint2* keep, uint2* out, MatchStats& st) {
+    const int2* occ = reinterpret_cast<const int2*>(g.occ_pair);
+    for (int o = g.occ_off[anchor], oe = g.occ_off[anchor + 1]; o < oe; ++o) {
+        const int2 e = occ[o];
         st.cand += 1;
-        st.cmp += min(i, L - 1);
-        if (i >= L) {
-            const uint2 t = make_uint2((uint32_t)s, (uint32_t)g.slot_path[s]);
-            if (kEmit) out[n] = t; else if (n < kKeep) keep[n] = t;
-            ++n;
-        }
-    }
-    if (L > 1) {   // reversed walk: occurrences of walk[L-1], then walk[L-2] ...
-        const int last = r.walk_node[w0 + L - 1];
-        for (int o = g.occ_off[last], oe = g.occ_off[last + 1]; o < oe; ++o) {
-            const int s = g.occ_slot[o];
-            int i = 1;
+        if (L > 1) {
+            st.cmp += 1;
+            if (e.y != second) continue;                  // successor differs (or path end, -1): rejected from the index
+            int i = 2;
             for (; i < L; ++i)
-                if (g.slot_node[s + i] != r.walk_node[w0 + L - 1 - i]) break;
-            st.cand += 1;
-            st.cmp += min(i, L - 1);
-            if (i >= L) {
-                const uint2 t = make_uint2((uint32_t)s | SFB_MATCH_REV, (uint32_t)g.slot_path[s]);
-                if (kEmit) out[n] = t; else if (n < kKeep) keep[n] = t;
-                ++n;
-            }
+                if (g.slot_node[e.x + i] != r.walk_node[w_first + (i64)step * i]) break;   // sentinel stops overruns
+            st.cmp += min(i, L - 1) - 1;
+            if (i < L) continue;
         }
+        const uint2 t = make_uint2((uint32_t)e.x | flag, (uint32_t)path_of_slot(g, e.x));
+        if (kEmit) out[n] = t; else if (n < kKeep) keep[n] = t;
+        ++n;
     }
     return n;
 }
 
-__global__ void __launch_bounds__(256) k_match(sfb_graph g, sfb_reads r, sfb_work w, long long* counters) {
+template <bool kEmit>
+__device__ __forceinline__ int match_sweep(const sfb_graph& g, const sfb_reads& r, i64 w0, int L, uint2* keep,
+                                           uint2* out, MatchStats& st) {
+    const int first = r.walk_node[w0];
+    if (L == 1) return sweep_one<kEmit>(g, r, w0, 1, 1, first, 0, 0u, 0, keep, out, st);
+    const int last = r.walk_node[w0 + L - 1];
+    int n = sweep_one<kEmit>(g, r, w0, 1, L, first, r.walk_node[w0 + 1], 0u, 0, keep, out, st);
+    // reversed walk (json2csv.py:861-866): starts at walk[L-1], continues with walk[L-2] ...
+    return sweep_one<kEmit>(g, r, w0 + L - 1, -1, L, last, r.walk_node[w0 + L - 2], SFB_MATCH_REV, n, keep, out, st);
+}
+
+// Candidate-parallel kernel, two phases per warp pass (the kernel is bound by memory latency, so the structure
+// minimises dependent round trips and keeps lanes dense):
+//   A  A warp takes 32 consecutive alignments (coalesced loads of their offsets and end nodes) and lays all their
+//      candidate occurrences -- forward ones first, then reverse, per alignment -- on one index line; it walks that
+//      line 64 candidates at a time, one lane = one candidate whatever alignment it belongs to, loads the
+//      (slot, successor) pairs and keeps the candidates whose successor equals the walk's second node.  Survivors
+//      are compacted (ballot) into a shared-memory list, in candidate order.
+//   B  The list is drained 32 survivors at a time, all lanes busy: the remaining walk positions are fetched
+//      together and compared, matches get their path id and their rank inside their alignment (ballot +
+//      __match_any over the owner lane; candidate order = the reference's match order) and are staged in shared
+//      memory, kKeep per alignment; longer lists are redone serially by the owner lane.
+#ifndef SFB_MATCH_KU
+#define SFB_MATCH_KU 4
+#endif
+#ifndef SFB_MATCH_WIN
+#define SFB_MATCH_WIN 2
+#endif
+#ifndef SFB_MATCH_MINBLK
+#define SFB_MATCH_MINBLK 5      /* 48 registers: measured best occupancy / spill trade-off (profiles/README.md) */
+#endif
+constexpr int kWarpsPerBlock = 8;
+constexpr int kU = SFB_MATCH_KU;    // compare positions fetched together (walks of up to kU + 2 nodes need no loop)
+constexpr int kWin = SFB_MATCH_WIN; // windows of 32 candidates per phase-A trip
+constexpr int kSurv = 32 * kWin + 96;   // survivor list entries per warp
+
+__global__ void __launch_bounds__(256, SFB_MATCH_MINBLK) k_match(sfb_graph g, sfb_reads r, sfb_work w, long long* counters) {
     __shared__ BlockCounters sc;
+    __shared__ uint2 s_stage[kWarpsPerBlock][32][kKeep];
+    __shared__ uint2 s_surv[kWarpsPerBlock][kSurv];
+    __shared__ int s_cnt[kWarpsPerBlock][32];
     block_counters_zero(sc);
     __syncthreads();
     MatchStats st{0, 0};
     int tuples = 0;
     uint2* aln_match = reinterpret_cast<uint2*>(w.aln_match);
     uint2* match_buf = reinterpret_cast<uint2*>(w.match_buf);
-    const i64 n_round = (r.n_alns + 255) & ~(i64)255;
-    for (i64 a = (i64)blockIdx.x * blockDim.x + threadIdx.x; a < n_round; a += (i64)gridDim.x * blockDim.x) {
+    const int2* occ = reinterpret_cast<const int2*>(g.occ_pair);
+    const int wi = threadIdx.x >> 5, lane = lane_id();
+    const unsigned below = (1u << lane) - 1u;
+    const int last_slot = (int)g.n_slots - 1;
+    const i64 n_round = (r.n_alns + 31) & ~(i64)31;
+    for (i64 base = ((i64)blockIdx.x * kWarpsPerBlock + wi) * 32; base < n_round;
+         base += (i64)gridDim.x * kWarpsPerBlock * 32) {
+        const i64 a = base + lane;
         const bool live = a < r.n_alns;
-        uint2 keep[kKeep];
-        int n = 0, L = 0;
         i64 w0 = 0;
+        int L = 0, second = 0, penult = 0, fo = 0, fcnt = 0, ro = 0, rcnt = 0;
         if (live) {
             w0 = r.aln_walk_off[a];
             L = (int)(r.aln_walk_off[a + 1] - w0);
-            if (L > 0) n = match_sweep<false>(g, r, w0, L, keep, nullptr, st);
-            tuples += n;
+            if (L > 0) {
+                const int first = r.walk_node[w0];
+                fo = g.occ_off[first];
+                fcnt = g.occ_off[first + 1] - fo;
+                if (L > 1) {
+                    const int last = r.walk_node[w0 + L - 1];
+                    second = r.walk_node[w0 + 1];
+                    penult = r.walk_node[w0 + L - 2];
+                    ro = g.occ_off[last];
+                    rcnt = g.occ_off[last + 1] - ro;
+                }
+            }
         }
+        const unsigned cnt = (unsigned)(fcnt + rcnt);
+        const unsigned incl = warp_scan(cnt);
+        const unsigned excl = incl - cnt;
+        const int total = (int)__shfl_sync(0xffffffffu, incl, 31);
+        s_cnt[wi][lane] = 0;
+        __syncwarp();
+        int t = 0, nsurv = 0;
+        while (t < total) {
+            // ---- phase A: successor filter, two windows of 32 candidates per trip ----
+            while (t < total && nsurv <= kSurv - 32 * kWin) {
+                int2 e[kWin];
+                int own[kWin];
+                bool rv[kWin], in[kWin];
+                int succ[kWin], oL[kWin];
+#pragma unroll
+                for (int u = 0; u < kWin; ++u) {
+                    const int c = t + 32 * u + lane;
+                    int j = 0;                 // owner of candidate c: the largest lane j with excl_j <= c
+#pragma unroll
+                    for (int step = 16; step > 0; step >>= 1) {
+                        const unsigned x = __shfl_sync(0xffffffffu, excl, (j + step) & 31);
+                        if (j + step < 32 && (int)x <= c) j += step;
+                    }
+                    const int k = c - (int)__shfl_sync(0xffffffffu, excl, j);
+                    const int o_fcnt = __shfl_sync(0xffffffffu, fcnt, j);
+                    const int o_fo = __shfl_sync(0xffffffffu, fo, j);
+                    const int o_ro = __shfl_sync(0xffffffffu, ro, j);
+                    const int o_second = __shfl_sync(0xffffffffu, second, j);
+                    const int o_penult = __shfl_sync(0xffffffffu, penult, j);
+                    oL[u] = __shfl_sync(0xffffffffu, L, j);
+                    own[u] = j;
+                    rv[u] = k >= o_fcnt;
+                    in[u] = c < total;
+                    succ[u] = rv[u] ? o_penult : o_second;
+                    e[u] = in[u] ? occ[rv[u] ? o_ro + (k - o_fcnt) : o_fo + k] : make_int2(0, 0);
+                }
+#pragma unroll
+                for (int u = 0; u < kWin; ++u) {
+                    const bool keep = in[u] && (oL[u] == 1 || e[u].y == succ[u]);   // else rejected from the index
+                    if (in[u]) { st.cand += 1; st.cmp += oL[u] > 1; }
+                    const unsigned ball = __ballot_sync(0xffffffffu, keep);
+                    if (keep)
+                        s_surv[wi][nsurv + __popc(ball & below)] =
+                            make_uint2((uint32_t)e[u].x | (rv[u] ? SFB_MATCH_REV : 0u), (uint32_t)own[u]);
+                    nsurv += __popc(ball);
+                }
+                t += 32 * kWin;
+            }
+            __syncwarp();
+            // ---- phase B: full compare of the survivors, 32 at a time ----
+            for (int b = 0; b < nsurv; b += 32) {
+                const bool valid = b + lane < nsurv;
+                const uint2 sv = valid ? s_surv[wi][b + lane] : make_uint2(0u, 0u);
+                const int j = (int)sv.y;
+                const int slot = (int)(sv.x & SFB_SLOT_MASK);
+                const bool rev = (sv.x & SFB_MATCH_REV) != 0;
+                const int o_L = __shfl_sync(0xffffffffu, L, j);
+                const i64 o_w0 = __shfl_sync(0xffffffffu, w0, j);
+                bool matched = false;
+                int pid = 0;
+                if (valid) {
+                    const i64 wf = rev ? o_w0 + o_L - 1 : o_w0;
+                    const int step = rev ? -1 : 1;
+                    pid = g.blk_path[slot >> 6];                       // issued with the compare loads
+                    int pn[kU], wn[kU];
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) {
+                        const int i = u + 2;
+                        pn[u] = wn[u] = 0;
+                        if (i < o_L) {
+                            pn[u] = g.slot_node[min(slot + i, last_slot)];   // sentinel (-1) stops overruns
+                            wn[u] = r.walk_node[wf + (i64)step * i];
+                        }
+                    }
+                    int bad = o_L;                   // first differing position
+#pragma unroll
+                    for (int u = kU - 1; u >= 0; --u)
+                        if (u + 2 < o_L && pn[u] != wn[u]) bad = u + 2;
+                    for (int i = kU + 2; i < o_L && bad == o_L; ++i)                 // walks longer than kU + 2 nodes
+                        if (g.slot_node[min(slot + i, last_slot)] != r.walk_node[wf + (i64)step * i]) bad = i;
+                    if (o_L > 2) st.cmp += min(bad, o_L - 1) - 1;
+                    matched = bad >= o_L;
+                    if (matched)
+                        while (g.path_off[pid + 1] <= slot) ++pid;
+                }
+                const unsigned ball = __ballot_sync(0xffffffffu, matched);
+                const unsigned same = __match_any_sync(0xffffffffu, valid ? j : 32 + lane);
+                const int before = valid ? s_cnt[wi][j] : 0;
+                const int rank = before + __popc(ball & same & below);
+                if (matched && rank < kKeep) s_stage[wi][j][rank] = make_uint2(sv.x, (uint32_t)pid);
+                __syncwarp();
+                if (matched && (ball & same & ~below & ~(1u << lane)) == 0) s_cnt[wi][j] = rank + 1;   // last match of its alignment here
+                __syncwarp();
+            }
+            nsurv = 0;
+        }
+        __syncwarp();
+        const int n = s_cnt[wi][lane];
+        tuples += n;
         const unsigned need = n > 1 ? (unsigned)n : 0u;
         const u64 pos = warp_claim(w.cursor, need);
-        if (!live) continue;
-        if (n == 0) {
-            aln_match[a] = make_uint2(SFB_MATCH_NONE, 0u);
-        } else if (n == 1) {
-            aln_match[a] = keep[0];
-        } else if (pos + need <= (u64)w.match_cap) {
-            if (n <= kKeep) {
-                for (int k = 0; k < n; ++k) match_buf[pos + k] = keep[k];
+        if (live) {
+            if (n == 0) {
+                aln_match[a] = make_uint2(SFB_MATCH_NONE, 0u);
+            } else if (n == 1) {
+                aln_match[a] = s_stage[wi][lane][0];
+            } else if (pos + need <= (u64)w.match_cap) {
+                if (n <= kKeep) {
+                    for (int q = 0; q < n; ++q) match_buf[pos + q] = s_stage[wi][lane][q];
+                } else {
+                    MatchStats scratch{0, 0};
+                    match_sweep<true>(g, r, w0, L, nullptr, match_buf + pos, scratch);
+                }
+                aln_match[a] = make_uint2(SFB_MATCH_MULTI | (uint32_t)pos, (uint32_t)n);
             } else {
-                MatchStats scratch{0, 0};
-                match_sweep<true>(g, r, w0, L, nullptr, match_buf + pos, scratch);
+                aln_match[a] = make_uint2(SFB_MATCH_NONE, 0u);
+                SFB_COUNT(sc, SFB_C_MATCH_OVERFLOW, (int)need);
             }
-            aln_match[a] = make_uint2(SFB_MATCH_MULTI | (uint32_t)pos, (uint32_t)n);
-        } else {
-            aln_match[a] = make_uint2(SFB_MATCH_NONE, 0u);
-            SFB_COUNT(sc, SFB_C_MATCH_OVERFLOW, (int)need);
         }
+        __syncwarp();
     }
     const int c0 = warp_sum(st.cand), c1 = warp_sum(st.cmp), c2 = warp_sum(tuples);
-    if (lane_id() == 0) {
+    if (lane == 0) {
         SFB_COUNT(sc, SFB_C_ST_CAND, c0);
         SFB_COUNT(sc, SFB_C_ST_COMPARES, c1);
         SFB_COUNT(sc, SFB_C_ST_TUPLES, c2);
@@ -106,7 +255,8 @@ __global__ void __launch_bounds__(256) k_match(sfb_graph g, sfb_reads r, sfb_wor
 
 int launch_match(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_accum* acc, cudaStream_t st) {
     if (r->n_alns == 0) return SFB_OK;
-    const unsigned grid = (unsigned)min((i64)kSMs * 8, (i64)blocks_for(r->n_alns, 256));
+    static int cache = 0;
+    const unsigned grid = persistent_grid(k_match, 256, blocks_for(r->n_alns, 256), &cache);   // a warp per 32 alignments
     k_match<<<grid, 256, 0, st>>>(*g, *r, *w, acc->counters);
     return check_launch("k_match");
 }

@@ -113,13 +113,16 @@ __global__ void __launch_bounds__(kTile) k_pass2_scatter(sfb_graph g, sfb_reads 
 
 int launch_pass1_scatter(const sfb_graph* g, const sfb_reads* r, const sfb_work* w, sfb_accum* acc, cudaStream_t st) {
     if (r->n_alns == 0) return SFB_OK;
-    const unsigned grid = (unsigned)min((i64)kSMs * 8, (i64)blocks_for(r->n_alns, kTile));
+    static int cache = 0;
+    const unsigned grid = persistent_grid(k_pass1_scatter, kTile, blocks_for(r->n_alns, kTile), &cache);
     k_pass1_scatter<<<grid, kTile, 0, st>>>(*g, *r, *w, acc->uniq_abund, acc->counters);
     return check_launch("k_pass1_scatter");
 }
 int launch_pass2_scatter(const sfb_graph* g, const sfb_reads* r, const sfb_work* w, sfb_accum* acc, cudaStream_t st) {
     if (r->n_alns == 0 || w->app_cap == 0) return SFB_OK;
-    k_pass2_scatter<<<kSMs * 8, kTile, 0, st>>>(*g, *r, *w, acc->mult_abund, acc->counters);
+    static int cache = 0;
+    const unsigned grid = persistent_grid(k_pass2_scatter, kTile, blocks_for(w->app_cap, kTile), &cache);
+    k_pass2_scatter<<<grid, kTile, 0, st>>>(*g, *r, *w, acc->mult_abund, acc->counters);
     return check_launch("k_pass2_scatter");
 }
 

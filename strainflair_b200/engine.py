@@ -51,6 +51,10 @@ class DeviceGraph:
         path_off = (graph.path_off + np.arange(P + 1, dtype=np.int64)).astype(np.int32)
         order = np.argsort(graph.path_nodes, kind="stable")
         occ_slot = self.slot_of_plain[order].astype(np.int32)
+        occ_pair = np.empty((T, 2), np.int32)
+        occ_pair[:, 0] = occ_slot
+        occ_pair[:, 1] = slot_node[occ_slot.astype(np.int64) + 1]      # successor on the path (-1 at the path end)
+        blk_path = slot_path[::64].copy()
         occ_off = np.zeros(graph.n_nodes + 1, np.int64)
         np.cumsum(np.bincount(graph.path_nodes, minlength=graph.n_nodes), out=occ_off[1:])
         S = graph.n_strains
@@ -68,7 +72,7 @@ class DeviceGraph:
         d = self.device
         self.t = dict(
             slot_node=_to_dev(slot_node, d), slot_len=_to_dev(slot_len, d), slot_path=_to_dev(slot_path, d),
-            path_off=_to_dev(path_off, d), occ_off=_to_dev(occ_off.astype(np.int32), d), occ_slot=_to_dev(occ_slot, d),
+            path_off=_to_dev(path_off, d), occ_off=_to_dev(occ_off.astype(np.int32), d), occ_pair=_to_dev(occ_pair.reshape(-1), d), blk_path=_to_dev(blk_path, d),
             path_seq_len=_to_dev(graph.path_seq_len, d), path_nstrain=_to_dev(nstrain, d),
             path_strain0=_to_dev(strain0, d), path_smask=_to_dev(smask.view(np.int64), d),
             path_cluster=_to_dev(graph.path_cluster, d),

@@ -25,9 +25,9 @@ def kernel_bytes(n_groups, n_alns, n_records, n_paths, n_slots, C, match_fill, n
     n1 = C["SAME_CP"] + C["DIFF_CP"]
     out = {}
     # match: walk offsets (8) + walk nodes (4/record) + occurrence ranges (2 ints per orientation)
-    #        + occurrence slots (4/candidate) + compared path nodes (4/compare) + slot->path (4/match)
-    #        + result pair (8) + multi lists (8/pair)
-    out["match"] = 8 * A + 4 * R + 16 * A + 4 * cand + 4 * cmp_ + 4 * tuples + 8 * A + 8 * match_fill
+    #        + (slot, successor) pairs (8/candidate; the first compare is served by the pair)
+    #        + further compared path nodes (4/compare) + slot->path (8/match) + result pair (8) + multi lists (8/pair)
+    out["match"] = 8 * A + 4 * R + 16 * A + 8 * cand + 4 * max(0, cmp_ - cand) + 8 * tuples + 8 * A + 8 * match_fill
     # classify: per group nmates(1) + 2 alignment offsets(16) + 2 seq_len(8) + code(1); per alignment
     #           aln_match(8) + aln_assign(4); multi lists (8/pair); per unique assignment uniq_reads RMW(16)
     #           + uniq_norm RMW(16) + path_seq_len(8) + 5 bins; per histogram read 5 RMW(16); deferred list (4)
@@ -42,4 +42,8 @@ def kernel_bytes(n_groups, n_alns, n_records, n_paths, n_slots, C, match_fill, n
     # path reduce: two fp64 slot arrays in, 8 fp64 + 3 counters per path
     out["path_reduce"] = 16 * n_slots + (8 * 8 + 4 * 8 + 8) * n_paths
     out["total"] = sum(out.values())
+    # SURVEY.md section 8d's closed form, with the realised c (compares/record), m (slot RMWs/record) and
+    # candidates+matches per alignment: R(8 + 4c + 16m) + A(24 + 8(cand+matches)/A) + 16G + 20T + 8(S+11)P
+    out["survey_total"] = (8 * R + 4 * cmp_ + 16 * (r1 + r2)) + (24 * A + 8 * (cand + tuples)) + 16 * G \
+        + 20 * n_slots + 8 * (n_strains + 11) * n_paths
     return out
