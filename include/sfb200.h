@@ -126,7 +126,8 @@ typedef struct sfb_reads {
     const int64_t* aln_walk_off;  /* [A+1]                                                    */
     const uint8_t* aln_bins;      /* [A*5]   round(x,2)*100 of the five ratios, 255 = outside [0,1] */
     const int32_t* walk_node;     /* [R]     Alignment.mapped_nodes_id (dense node index)     */
-    const int32_t* walk_alen;     /* [R]     aligned bases: coverage = alen / node length (:574); or -(k+1): coverage = exc_cov[k] */
+    const int32_t* walk_alen;     /* [R]     >= 0: aligned bases (low 16 bits) | node length << 16, coverage = their
+                                             ratio in fp64 (:574); < 0: -(k+1), coverage = exc_cov[k]          */
     const double*  exc_cov;       /* [E]                                                      */
 } sfb_reads;
 
@@ -186,6 +187,12 @@ int sfb_pass1_scatter(const sfb_graph* g, const sfb_reads* r, const sfb_work* w,
  * per-path unique count summed over ALL read shards (acc->uniq_reads when there is one). */
 int sfb_pass2(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_accum* acc,
               const long long* uniq_reads_global, void* stream);
+
+/* The two halves of sfb_pass2, for callers that want to time or overlap them: candidate selection, ratios and
+ * per-path counters (json2csv.py:1127-1156 and twins) into w->app_buf, then the node loops (:1157-1158). */
+int sfb_pass2_resolve(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_accum* acc,
+                      const long long* uniq_reads_global, void* stream);
+int sfb_pass2_scatter(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_accum* acc, void* stream);
 
 /* Pangenome.print_gene_table's per-path reductions (json2csv.py:440-469) for paths
  * [p_begin, p_end): table[(p-p_begin)*8 + k], k = 0 nb_uniq_mapped_normalized,

@@ -77,10 +77,9 @@ class AbundanceOracle:
         if "walk_cov" in reads:
             self.walk_cov = reads["walk_cov"]
         else:
-            al = reads["walk_alen"]
-            ln = g["node_len"][reads["walk_node"]]
-            cov = np.where(al >= 0, al, 0) / ln
+            al = reads["walk_alen"].astype(np.int64)
             neg = al < 0
+            cov = np.where(neg, 0, al & 0xFFFF) / np.where(neg, 1, al >> 16)      # aligned bases / node length
             cov[neg] = reads["exc_cov"][-al[neg] - 1]
             self.walk_cov = cov
 

@@ -15,8 +15,9 @@ Output ("Reads" interchange schema)
                                reference when used, Q7)
     aln_stats    float64[A,5]  the five un-binned values
     walk_node    int32[R]      dense node index
-    walk_alen    int32[R]      aligned bases on that node, or -(k+1) when the
-                               fp64 coverage must come from exc_cov[k]
+    walk_alen    int32[R]      aligned bases on that node in the low 16 bits and the
+                               node length in the high bits (coverage = their ratio),
+                               or -(k+1) when the fp64 coverage must come from exc_cov[k]
     walk_cov     float64[R]    coverage exactly as the reference accumulates it
     exc_cov      float64[E]    see walk_alen
     mate_names   list[str]     2G read names ('' when absent)
@@ -201,8 +202,9 @@ def pack_groups(groups, graph):
                         k = node_index[nid]
                         w_node.append(k)
                         w_cov.append(c)
-                        if al / int(node_len[k]) == c:
-                            w_alen.append(al)
+                        nl = int(node_len[k])
+                        if 0 <= al <= 0xFFFF and 1 <= nl <= 0x7FFF and al / nl == c:
+                            w_alen.append(al | (nl << 16))
                         else:
                             w_alen.append(-(len(exc) + 1))
                             exc.append(c)

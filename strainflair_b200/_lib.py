@@ -65,7 +65,7 @@ MAX_SLOTS = 0x3FFFFFFF
 ABI_VERSION = 4
 
 EXPORTS = ("sfb_abi_version", "sfb_version", "sfb_last_error", "sfb_match", "sfb_classify", "sfb_pass1_scatter",
-           "sfb_pass2", "sfb_path_reduce", "sfb_cluster_strain_counts", "sfb_strain_aggregate",
+           "sfb_pass2", "sfb_pass2_resolve", "sfb_pass2_scatter", "sfb_path_reduce", "sfb_cluster_strain_counts", "sfb_strain_aggregate",
            "sfb_decode_json", "sfb_decoded_error", "sfb_decoded_size", "sfb_decoded_copy", "sfb_decoded_free")
 
 
@@ -104,10 +104,12 @@ def load(build_if_missing=True):
     lib.sfb_classify.argtypes = [G, R, W, A, vp]
     lib.sfb_pass1_scatter.argtypes = [G, R, W, A, vp]
     lib.sfb_pass2.argtypes = [G, R, W, A, vp, vp]
+    lib.sfb_pass2_resolve.argtypes = [G, R, W, A, vp, vp]
+    lib.sfb_pass2_scatter.argtypes = [G, R, W, A, vp]
     lib.sfb_path_reduce.argtypes = [G, A, i64, i64, vp, vp]
     lib.sfb_cluster_strain_counts.argtypes = [i64, i64, vp, vp, vp, vp, vp, vp, vp]
     lib.sfb_strain_aggregate.argtypes = [i64, i64, vp, vp, vp, vp, vp, vp, f64, vp, vp, vp, vp, vp]
-    for name in EXPORTS[3:10]:
+    for name in EXPORTS[3:12]:
         getattr(lib, name).restype = C.c_int
     lib.sfb_decode_json.argtypes = [C.c_char_p, vp, vp, i64, f64, C.c_int, i64]
     lib.sfb_decode_json.restype = C.c_void_p

@@ -111,6 +111,19 @@ int sfb_pass2(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_accum* ac
     return launch_pass2_scatter(g, r, w, acc, (cudaStream_t)stream);
 }
 
+int sfb_pass2_resolve(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_accum* acc,
+                      const long long* uniq_reads_global, void* stream) {
+    SFB_TRY(check_all(g, r, w, acc));
+    SFB_REQUIRE(uniq_reads_global, "uniq_reads_global is null");
+    Dev d{*g, *r, *w, *acc};
+    return launch_pass2_resolve(d, uniq_reads_global, (cudaStream_t)stream);
+}
+
+int sfb_pass2_scatter(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_accum* acc, void* stream) {
+    SFB_TRY(check_all(g, r, w, acc));
+    return launch_pass2_scatter(g, r, w, acc, (cudaStream_t)stream);
+}
+
 int sfb_path_reduce(const sfb_graph* g, const sfb_accum* acc, int64_t p_begin, int64_t p_end, double* table,
                     void* stream) {
     SFB_TRY(check_graph(g));

@@ -111,16 +111,13 @@ __device__ __forceinline__ uint2 match_get(const sfb_work& w, uint2 m, int k) {
     return reinterpret_cast<const uint2*>(w.match_buf)[(size_t)(m.x & 0x7fffffffu) + k];
 }
 
-// Coverage of walk record `rec` (position i of an L-node walk matched at `code`): aligned bases / node
-// length, the node being the path node the walk position maps to (a reversed walk reads the path
-// backwards), json2csv.py:574; or the explicit fp64 when the decoder had to merge mappings (:576-577).
-__device__ __forceinline__ double record_cov(const sfb_graph& g, const sfb_reads& r, i64 rec, uint32_t code, int i,
-                                             int L) {
-    const int alen = r.walk_alen[rec];
-    if (alen < 0) return r.exc_cov[-(i64)alen - 1];
-    const uint32_t slot0 = code & SFB_SLOT_MASK;
-    const uint32_t s = (code & SFB_MATCH_REV) ? slot0 + (uint32_t)(L - 1 - i) : slot0 + (uint32_t)i;
-    return (double)alen / (double)g.slot_len[s];
+// Coverage of walk record `rec`: aligned bases / node length (json2csv.py:574), both packed by the decoder
+// in one int so that the scatter kernels never touch the graph; or the explicit fp64 when the decoder had to
+// merge mappings (:576-577).  The reference adds cov[i] to slot position+i whatever the orientation (Q3).
+__device__ __forceinline__ double record_cov(const sfb_reads& r, i64 rec) {
+    const int v = r.walk_alen[rec];
+    if (v < 0) return r.exc_cov[-(i64)v - 1];
+    return (double)(v & 0xffff) / (double)(v >> 16);        // aligned bases / node length, IEEE division
 }
 
 // A mate of a read group: its retained alignments [a0, a0+na) (json2csv.py:686-739).

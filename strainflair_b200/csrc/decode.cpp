@@ -683,8 +683,10 @@ sfb_decoded* sfb_decode_json(const char* path, const int64_t* node_ids, const in
         fh = nullptr;
         // coverage encoding: integer aligned length when alen/len reproduces the reference's fp64, else explicit
         for (size_t r = 0; r < D->walk_node.size(); ++r) {
-            const double plain = (double)D->walk_alen[r] / (double)node_len[D->walk_node[r]];
-            if (plain != D->walk_cov[r]) {
+            const int32_t al = D->walk_alen[r], nl = node_len[D->walk_node[r]];
+            if (al >= 0 && al <= 0xFFFF && nl >= 1 && nl <= 0x7FFF && (double)al / (double)nl == D->walk_cov[r]) {
+                D->walk_alen[r] = al | (nl << 16);          // aligned bases | node length << 16
+            } else {
                 D->exc_cov.push_back(D->walk_cov[r]);
                 D->walk_alen[r] = -(int32_t)D->exc_cov.size();
             }

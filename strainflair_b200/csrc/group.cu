@@ -304,8 +304,14 @@ __device__ __forceinline__ void classify_aligned_pair_generic(const Dev& d, Bloc
     }
 }
 
+#ifndef SFB_CLS_MINBLK
+#define SFB_CLS_MINBLK 8      /* 80 registers; measured, see profiles/README.md */
+#endif
+#ifndef SFB_P2_MINBLK
+#define SFB_P2_MINBLK 6       /* 64 registers */
+#endif
 // Fast kernel: everything except aligned pairs that do not fit the register path, which go to w.slow.
-__global__ void __launch_bounds__(128) k_classify(Dev d) {
+__global__ void __launch_bounds__(128, SFB_CLS_MINBLK) k_classify(Dev d) {
     __shared__ BlockCounters sc;
     block_counters_zero(sc);
     __syncthreads();
@@ -642,7 +648,7 @@ __device__ __forceinline__ int p2_single_outcome(BlockCounters& sc, int n_tuples
 }
 
 // Fast kernel over the deferred groups; groups that do not fit the register path go to w.slow (cursor[4]).
-__global__ void __launch_bounds__(128) k_pass2_resolve(Dev d, const long long* __restrict__ U) {
+__global__ void __launch_bounds__(128, SFB_P2_MINBLK) k_pass2_resolve(Dev d, const long long* __restrict__ U) {
     __shared__ BlockCounters sc;
     block_counters_zero(sc);
     __syncthreads();

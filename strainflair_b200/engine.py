@@ -222,7 +222,7 @@ class AbundanceEngine:
 
     def classify(self, dr, work):
         _lib.check(self.lib.sfb_classify(C.byref(self.dg.c), C.byref(dr.c), C.byref(work.c), C.byref(self.acc.c), _stream()))
-        self.launches += 1
+        self.launches += 2       # register-path kernel + generic kernel
 
     def pass1_scatter(self, dr, work):
         _lib.check(self.lib.sfb_pass1_scatter(C.byref(self.dg.c), C.byref(dr.c), C.byref(work.c), C.byref(self.acc.c), _stream()))
@@ -232,6 +232,16 @@ class AbundanceEngine:
         u = self.acc.uniq_reads if uniq_global is None else uniq_global
         _lib.check(self.lib.sfb_pass2(C.byref(self.dg.c), C.byref(dr.c), C.byref(work.c), C.byref(self.acc.c),
                                       C.c_void_p(u.data_ptr()), _stream()))
+        self.launches += 3
+
+    def pass2_resolve(self, dr, work, uniq_global=None):
+        u = self.acc.uniq_reads if uniq_global is None else uniq_global
+        _lib.check(self.lib.sfb_pass2_resolve(C.byref(self.dg.c), C.byref(dr.c), C.byref(work.c), C.byref(self.acc.c),
+                                              C.c_void_p(u.data_ptr()), _stream()))
+        self.launches += 2
+
+    def pass2_scatter(self, dr, work):
+        _lib.check(self.lib.sfb_pass2_scatter(C.byref(self.dg.c), C.byref(dr.c), C.byref(work.c), C.byref(self.acc.c), _stream()))
         self.launches += 1
 
     def path_reduce(self, p_begin=0, p_end=None):
@@ -271,8 +281,10 @@ class AbundanceEngine:
             uniq_global = self.acc.uniq_reads.clone()
             dist.all_reduce(uniq_global, group=self.comm)          # exact integer sum over shards
             mark("allreduce_uniq")
-        self.pass2(dr, work, uniq_global)
-        mark("pass2")
+        self.pass2_resolve(dr, work, uniq_global)
+        mark("pass2_resolve")
+        self.pass2_scatter(dr, work)
+        mark("pass2_scatter")
         if self.comm is None:
             self.path_reduce()
             mark("path_reduce")

@@ -94,11 +94,11 @@ def cluster_records(graph, reads, res):
         lo, hi = int(wo[a]), int(wo[a + 1])
         dense = reads.walk_node[lo:hi]
         walk = [int(v) for v in graph.node_ids[dense]]
-        alen = reads.walk_alen[lo:hi]
-        cov = np.where(alen >= 0, alen, 0) / graph.node_len[dense]
-        neg = alen < 0
+        packed = reads.walk_alen[lo:hi].astype(np.int64)
+        neg = packed < 0
+        cov = np.where(neg, 0, packed & 0xFFFF) / np.where(neg, 1, packed >> 16)     # aligned bases / node length
         if neg.any():
-            cov[neg] = reads.exc_cov[-alen[neg].astype(np.int64) - 1]
+            cov[neg] = reads.exc_cov[-packed[neg] - 1]
         rec = clusters[cid]
         rec["reads_name"].append(mate_name(reads, g, m))
         rec["unassigned_paths"].append(walk)

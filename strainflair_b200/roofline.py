@@ -32,16 +32,18 @@ def kernel_bytes(n_groups, n_alns, n_records, n_paths, n_slots, C, match_fill, n
     #           aln_match(8) + aln_assign(4); multi lists (8/pair); per unique assignment uniq_reads RMW(16)
     #           + uniq_norm RMW(16) + path_seq_len(8) + 5 bins; per histogram read 5 RMW(16); deferred list (4)
     out["classify"] = 26 * G + 12 * A + 8 * match_fill + 45 * n1 + 80 * hist + 4 * n_deferred
-    # pass-1 scatter: walk offsets(8) + aln_assign(4) per alignment; per added record alen(4) + node length(4)
-    #                 + fp64 RMW(16)
-    out["pass1_scatter"] = 12 * A + 24 * r1
+    # pass-1 scatter: walk offsets(8) + aln_assign(4) per alignment; per added record the packed
+    #                 aligned/node-length word(4) + fp64 RMW(16)
+    out["pass1_scatter"] = 12 * A + 20 * r1
     # pass 2: deferred id(4) + group header(26) per deferred group; per redistribution: match pair(8) +
     #         uniq_reads gather(8) + 3 RMW (mult_reads, mult_norm 16 each, mult_hits 8) + path_seq_len(8)
     #         + work item write+read(32) + walk offsets(16); per record alen(4) + node length(4) + RMW(16)
-    out["pass2"] = 30 * n_deferred + 112 * app + 24 * r2
+    out["pass2_resolve"] = 30 * n_deferred + 96 * app          # incl. the 16-byte work item write
+    out["pass2_scatter"] = 16 * app + 16 * app + 20 * r2          # work item read + walk offsets; packed record(4) + RMW(16)
+    out["pass2"] = out["pass2_resolve"] + out["pass2_scatter"]
     # path reduce: two fp64 slot arrays in, 8 fp64 + 3 counters per path
     out["path_reduce"] = 16 * n_slots + (8 * 8 + 4 * 8 + 8) * n_paths
-    out["total"] = sum(out.values())
+    out["total"] = sum(v for k, v in out.items() if k != "pass2")
     # SURVEY.md section 8d's closed form, with the realised c (compares/record), m (slot RMWs/record) and
     # candidates+matches per alignment: R(8 + 4c + 16m) + A(24 + 8(cand+matches)/A) + 16G + 20T + 8(S+11)P
     out["survey_total"] = (8 * R + 4 * cmp_ + 16 * (r1 + r2)) + (24 * A + 8 * (cand + tuples)) + 16 * G \

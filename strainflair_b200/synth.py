@@ -204,6 +204,7 @@ def _reads_chunk(graph, rng, G, read_len, p_same, p_low, p_tie, p_recomb, p_sing
     rev = rng.random(A) < 0.5
     src = np.where(rev[a_of], woff[:-1][a_of] + (L[a_of] - 1 - j), np.arange(R))
     node, alen = node[src], alen[src]
+    alen = (alen | (graph.node_len[node].astype(np.int32) << 16)).astype(np.int32)    # aligned bases | node length << 16
     # error ratios -> histogram bins
     n_sub = rng.choice(np.array([0, 0, 0, 0, 1], np.int64), A)
     rlA = rl.astype(np.float64)

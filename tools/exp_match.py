@@ -13,15 +13,17 @@ reads = synth.make_reads(graph, synth.SEED0 + 1002, n_pairs=int(rkw["n_pairs"] *
 eng = engine.AbundanceEngine(graph, "cuda:0")
 dr = engine.DeviceReads(engine.HostReads(reads), eng.device)
 work = eng._work_for(dr)
-for stage in ("match",):
-    fn = getattr(eng, stage)
-    for _ in range(3):
-        work.reset(); eng.acc.zero(); fn(dr, work)
+stages = ("match", "classify", "pass1_scatter", "pass2_resolve", "pass2_scatter")
+tot = {k: 0.0 for k in stages}
+for it in range(8):
+    work.reset(); eng.acc.zero()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(stages) + 1)]
+    evs[0].record()
+    for k, st in enumerate(stages):
+        getattr(eng, st)(dr, work)
+        evs[k + 1].record()
     torch.cuda.synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    t = 0.0
-    for _ in range(5):
-        work.reset(); eng.acc.zero()
-        ev[0].record(); fn(dr, work); ev[1].record(); torch.cuda.synchronize()
-        t += ev[0].elapsed_time(ev[1])
-    print(os.environ.get("SFB200_LIB", "default"), stage, "ms", round(t / 5, 4), "alns", reads.n_alns, flush=True)
+    if it >= 3:
+        for k, st in enumerate(stages):
+            tot[st] += evs[k].elapsed_time(evs[k + 1]) / 5
+print(os.path.basename(os.environ.get("SFB200_LIB", "default")), {k: round(v, 4) for k, v in tot.items()}, "alns", reads.n_alns, flush=True)
