@@ -76,6 +76,46 @@ def cpu_port_rate(graph_d, reads_d, cores, repeats=1):
     return n_reads / best, n_rec / best, best
 
 
+def decode_rates(graph, synth, idx, rkw, n_pairs):
+    """JSON -> CSR decode throughput on a sample written to a temporary directory."""
+    import shutil
+    import tempfile
+    from oracle import decode as od
+    from strainflair_b200 import decode
+    tmp = tempfile.mkdtemp(prefix="sfb_decode_")
+    try:
+        sample = synth.make_reads(graph, synth.SEED0 + idx + 1000, n_pairs=n_pairs, read_len=rkw["read_len"])
+        gf, js, pk = synth.export_files(graph, sample, tmp)
+        n_lines = sum(1 for _ in open(js))
+        size = os.path.getsize(js)
+        best = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            got = decode.decode_json(js, graph, 0.95)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        assert got.n_alns == sample.n_alns
+        # Python decoder (the reference's json.loads + BFS + metaalign2align, restated) on the first lines, one core
+        head = os.path.join(tmp, "head.json")
+        n_head = 0
+        with open(js) as src, open(head, "w") as dst:
+            for ln in src:
+                if n_head >= 20_000 and ln.startswith('{"name": "r') and "/1" in ln[:24]:
+                    break
+                dst.write(ln)
+                n_head += 1
+        gd = graph.as_dict()
+        gd["node_index"] = {int(v): k for k, v in enumerate(graph.node_ids)}
+        t0 = time.perf_counter()
+        od.decode_json(head, gd, 0.95)
+        dt_py = time.perf_counter() - t0
+        return {"native_lines_per_s": n_lines / best, "native_MBps": size / best / 1e6,
+                "native_threads": len(os.sched_getaffinity(0)), "lines": n_lines,
+                "python_port_lines_per_s": n_head / dt_py, "python_port_cores": 1}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -187,6 +227,11 @@ def run_ours(args):
                "sample": f"first {sp} read pairs of the workload, oracle port (Python) sharded over {cores} processes, "
                          f"decode excluded, {secs:.1f} s"}
         del sample
+
+    # decode, reported separately (north_star): native streaming decoder on all cores vs the oracle's Python decoder
+    dec = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        dec = decode_rates(graph, synth, idx, rkw, min(40_000, pairs))
 
     import torch
     import torch.distributed as dist
@@ -324,6 +369,7 @@ def run_ours(args):
             "clocks": sampler.summary(),
             "e2e": e2e,
             "cpu_baseline": cpu,
+            "decode": dec,
             "gen_seconds": round(t_gen, 1),
         }
         print(json.dumps(line), flush=True)

@@ -7,6 +7,7 @@
 // The reference re-parses ~30 % of the file in its second pass and runs on one thread; here every line is
 // parsed once, lines are decoded in parallel, and only the (cheap) grouping is sequential.
 #include <algorithm>
+#include <chrono>
 #include <atomic>
 #include <cmath>
 #include <cstdint>
@@ -168,6 +169,7 @@ struct Aln {            // one decoded Alignment (json2csv.py:122-134)
     std::vector<double> cov;
     int32_t read_len;
     double stats[5];
+    uint8_t bins[5];
 };
 struct Line {
     const char* name; size_t name_n;
@@ -466,6 +468,7 @@ void route_to_aln(const Line& ln, const Route& rt, const NodeTable& nt, Aln& a) 
     a.stats[2] = (double)tot_subst / rl;
     a.stats[3] = (double)tot_indel / rl;
     a.stats[4] = (double)(tot_indel + tot_subst) / rl;
+    for (int k = 0; k < 5; ++k) a.bins[k] = bin_of(a.stats[k]);      // here, in the parallel phase (snprintf is slow)
 }
 
 void decode_line(Line& ln, const NodeTable& nt) {
@@ -546,7 +549,7 @@ void emit_group(sfb_decoded& D, const std::vector<MateAcc>& mates) {
                 D.aln_read_len.push_back(a->read_len);
                 for (int k = 0; k < 5; ++k) {
                     D.aln_stats.push_back(a->stats[k]);
-                    D.aln_bins.push_back(bin_of(a->stats[k]));
+                    D.aln_bins.push_back(a->bins[k]);
                 }
             }
         } else {
@@ -617,21 +620,31 @@ sfb_decoded* sfb_decode_json(const char* path, const int64_t* node_ids, const in
     try {
         fh = fopen(path, "rb");
         if (!fh) throw Fail{E_IO, std::string("cannot open ") + path};
-        if (block_bytes <= 0) block_bytes = 256ll << 20;
+        if (block_bytes <= 0) block_bytes = 64ll << 20;
+        fseek(fh, 0, SEEK_END);
+        long long remaining = ftell(fh);
+        fseek(fh, 0, SEEK_SET);
+        auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        const bool trace = getenv("SFB_DECODE_TRACE") != nullptr;
+        double t_read = 0, t_par = 0, t_grp = 0, t0 = now();
         NodeTable nt{node_ids, node_len, n_nodes, {}, {}};
         nt.build();
+        if (trace) fprintf(stderr, "[decode] node table %.3f s\n", now() - t0);
         std::vector<Line> carry;                 // decoded lines of a group cut by the block boundary
         std::string buf, tail;
         bool eof = false;
         while (!eof) {
             // one block: leftover partial line + fresh bytes, cut at the last newline
+            t0 = now();
             buf.swap(tail);
             tail.clear();
             const size_t have = buf.size();
-            buf.resize(have + (size_t)block_bytes);
-            const size_t got = fread(&buf[have], 1, (size_t)block_bytes, fh);
+            const size_t want = (size_t)std::min<long long>(block_bytes, std::max<long long>(remaining, 0));
+            buf.resize(have + want);                       // (value-initialises: keep blocks modest)
+            const size_t got = want ? fread(&buf[have], 1, want, fh) : 0;
             buf.resize(have + got);
-            eof = got < (size_t)block_bytes;
+            remaining -= (long long)got;
+            eof = remaining <= 0 || got < want;
             if (!eof) {
                 const size_t cut = buf.rfind('\n');
                 if (cut == std::string::npos) {
@@ -648,6 +661,8 @@ sfb_decoded* sfb_decode_json(const char* path, const int64_t* node_ids, const in
                 spans.emplace_back(p, q);
                 p = q + 1;
             }
+            t_read += now() - t0;
+            t0 = now();
             std::vector<Line> lines(carry.size() + spans.size());
             for (size_t i = 0; i < carry.size(); ++i) lines[i] = std::move(carry[i]);
             const size_t base = carry.size();
@@ -673,12 +688,16 @@ sfb_decoded* sfb_decode_json(const char* path, const int64_t* node_ids, const in
             for (int t = 1; t < T; ++t) pool.emplace_back(work);
             work();
             for (auto& th : pool) th.join();
+            t_par += now() - t0;
+            t0 = now();
             const size_t used = group_lines(*D, lines, thr, eof);
             for (size_t i = used; i < lines.size(); ++i) {
                 lines[i].detach();
                 carry.push_back(std::move(lines[i]));
             }
+            t_grp += now() - t0;
         }
+        if (trace) fprintf(stderr, "[decode] read+split %.3f s, parse+route (parallel) %.3f s, group+emit %.3f s\n", t_read, t_par, t_grp);
         fclose(fh);
         fh = nullptr;
         // coverage encoding: integer aligned length when alen/len reproduces the reference's fp64, else explicit

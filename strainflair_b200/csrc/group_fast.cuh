@@ -11,7 +11,10 @@
 
 namespace sfb {
 
-constexpr int kR = 8;
+#ifndef SFB_KR
+#define SFB_KR 8
+#endif
+constexpr int kR = SFB_KR;
 
 struct RegMate {
     int n;            // tuples

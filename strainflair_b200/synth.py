@@ -207,8 +207,10 @@ def _reads_chunk(graph, rng, G, read_len, p_same, p_low, p_tie, p_recomb, p_sing
     alen = (alen | (graph.node_len[node].astype(np.int32) << 16)).astype(np.int32)    # aligned bases | node length << 16
     # error ratios -> histogram bins
     n_sub = rng.choice(np.array([0, 0, 0, 0, 1], np.int64), A)
+    n_sub[second] = n_sub[second - 1]            # retained alignments of a mate are tied: same score
     rlA = rl.astype(np.float64)
-    stats = np.stack([(rlA - 5 * n_sub) / rlA, (rlA - n_sub) / rlA, n_sub / rlA, np.zeros(A), n_sub / rlA], axis=1)
+    pen = np.maximum(1, rl // 50)                # score penalty of a substitution; keeps the score above 0.95
+    stats = np.stack([(rl - pen * n_sub) / rlA, (rlA - n_sub) / rlA, n_sub / rlA, np.zeros(A), n_sub / rlA], axis=1)
     bins = np.stack([_python_round_bins(stats[:, c]) for c in range(5)], axis=1)
     grp_aln_off = np.concatenate(([0], np.cumsum(n_aln))).astype(np.int64)
     return dict(
@@ -246,3 +248,71 @@ def make_config(name, scale=1.0, seed=None):
     rkw["n_pairs"] = max(1, int(rkw["n_pairs"] * scale))
     reads = make_reads(graph, seed + 1000, **rkw)
     return graph, reads
+
+
+def export_files(graph, reads, outdir, prefix="synth"):
+    """Writes the configuration as the files the command lines take: <prefix>.gfa, <prefix>.json
+    (`vg view -j -K` style, one subpath per alignment) and <prefix>_clusters.pickle.  Decoding the JSON
+    with thr = 0.95 gives back ``reads`` array for array (explicit-coverage records excepted)."""
+    import json
+    import os
+    import pickle
+    os.makedirs(outdir, exist_ok=True)
+    rng = np.random.default_rng(12345)
+    names = graph.strain_names
+    gfa = os.path.join(outdir, prefix + ".gfa")
+    lut = np.frombuffer(b"ACGT", np.uint8)
+    with open(gfa, "w") as fh:
+        fh.write("H\tVN:Z:1.0\n")
+        seq = lut[rng.integers(0, 4, int(graph.node_len.sum()))].tobytes().decode()
+        off = np.concatenate(([0], np.cumsum(graph.node_len)))
+        for k in range(graph.n_nodes):
+            fh.write(f"S\t{int(graph.node_ids[k])}\t{seq[off[k]:off[k + 1]]}\n")
+        genes = [[] for _ in range(graph.n_clusters)]
+        gene_no = 0
+        for p in range(graph.n_paths):
+            nodes = ",".join(f"{int(graph.node_ids[n])}+" for n in graph.path_nodes[graph.path_off[p]:graph.path_off[p + 1]])
+            for e in range(int(graph.pstr_off[p]), int(graph.pstr_off[p + 1])):
+                for _ in range(int(graph.pstr_cnt[e])):
+                    gene_no += 1
+                    name = f"{names[int(graph.pstr_id[e])]}_{gene_no}"
+                    fh.write(f"P\t{name}\t{nodes}\t*\n")
+                    if graph.path_cluster[p] >= 0:
+                        genes[int(graph.path_cluster[p])].append(name)
+    pk = os.path.join(outdir, prefix + "_clusters.pickle")
+    with open(pk, "wb") as fh:
+        pickle.dump({f"Cluster_{c}": {"genes_list": g, "len_rep": 0} for c, g in enumerate(genes)}, fh)
+    js = os.path.join(outdir, prefix + ".json")
+    ids = graph.node_ids
+    with open(js, "w") as fh:
+        for g in range(reads.n_groups):
+            nm = int(reads.grp_nmates[g])
+            for m in range(nm):
+                name = f"r{g}/{m + 1}" if nm == 2 else f"r{g}"
+                pair = f"r{g}/{2 - m}" if nm == 2 else None
+                rl = int(reads.mate_seq_len[2 * g + m])
+                seq = "AC"[m] * rl
+                a0, a1 = int(reads.grp_aln_off[2 * g + m]), int(reads.grp_aln_off[2 * g + m + 1])
+                lines = []
+                for a in range(a0, a1):
+                    w0, w1 = int(reads.aln_walk_off[a]), int(reads.aln_walk_off[a + 1])
+                    sub = int(reads.aln_bins[a, 0]) < 100          # one substitution (see _reads_chunk)
+                    maps = []
+                    for r_ in range(w0, w1):
+                        al = int(reads.walk_alen[r_]) & 0xFFFF
+                        edits = [{"from_length": al, "to_length": al}]
+                        if sub and r_ == w0 and al >= 1:
+                            edits = ([{"from_length": al - 1, "to_length": al - 1}] if al > 1 else []) + \
+                                    [{"from_length": 1, "to_length": 1, "sequence": "T"}]
+                        maps.append({"position": {"node_id": str(int(ids[reads.walk_node[r_]]))}, "edit": edits})
+                    lines.append({"name": name, "sequence": seq, "start": [0], "mapping_quality": 60,
+                                  "subpath": [{"path": {"mapping": maps}, "score": rl - max(1, rl // 50) * int(sub)}]})
+                if not lines:                                     # present, but below the score threshold
+                    lines.append({"name": name, "sequence": seq, "start": [0], "subpath": [
+                        {"path": {"mapping": [{"position": {"node_id": str(int(ids[0]))},
+                                               "edit": [{"from_length": rl, "to_length": rl}]}]}, "score": rl // 2}]})
+                for ln in lines:
+                    if pair:
+                        ln["paired_read_name"] = pair
+                    fh.write(json.dumps(ln) + "\n")
+    return gfa, js, pk

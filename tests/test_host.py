@@ -138,3 +138,21 @@ def test_cli_flag_handling_matches_reference(tmp_path):
     assert r.returncode == 2 and "option -x not recognized" in r.stdout
     r = _cli(["compute_strains_abundance", "-i", "a.csv"], str(tmp_path))
     assert r.returncode == 0 and r.stdout.startswith("Usage:")
+
+
+def test_synthetic_workload_round_trips_through_files(tmp_path):
+    """The bench workload is defined on arrays; exported as GFA/JSON/pickle and decoded again it must be the
+    same arrays (so the arrays mean what the reference would read from those files)."""
+    from strainflair_b200 import synth
+    for name, scale in (("tiny", 1.0), ("small", 0.04)):
+        g, r = synth.make_config(name, scale=scale)
+        gf, js, pk = synth.export_files(g, r, str(tmp_path / name))
+        g2 = gfa.load_graph(gf, pk)
+        for k in ("node_len", "path_off", "path_nodes", "path_seq_len", "pstr_off", "pstr_cnt", "path_cluster",
+                  "clu_off", "clu_paths"):
+            assert np.array_equal(getattr(g, k), getattr(g2, k)), k
+        assert [g.strain_names[s] for s in g.pstr_id] == [g2.strain_names[s] for s in g2.pstr_id]
+        r2 = decode.decode_json(js, g2, 0.95)
+        for k in ("grp_nmates", "grp_aln_off", "mate_seq_len", "aln_walk_off", "aln_read_len", "aln_bins", "walk_node",
+                  "walk_alen"):
+            assert np.array_equal(getattr(r, k), getattr(r2, k)), (name, k)

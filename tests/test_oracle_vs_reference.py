@@ -103,3 +103,19 @@ def test_error_quirks_match(which, exc, tmp_path):
     with pytest.raises(exc):
         g = og.load_graph(gfa, pk)
         oa.AbundanceOracle(g, od.decode_json(js, g, 0.95)).run()
+
+
+def test_reference_on_exported_synthetic_workload(tmp_path):
+    """The unmodified reference on the bench generator's workload (exported to files) equals the oracle on the
+    generator's arrays: the synthetic arrays mean what the reference would compute from the files."""
+    from strainflair_b200 import synth
+    g, r = synth.make_config("small", scale=0.05)
+    gf, js, pk = synth.export_files(g, r, str(tmp_path))
+    ref = refharness.run_json2csv(gf, js, pk, 0.95)
+    go = og.load_graph(gf, pk)
+    orc = oa.AbundanceOracle(go, od.decode_json(js, go, 0.95)).run()
+    compare.check_state_vs_reference(orc, ref, exact=True)
+    orc2 = oa.AbundanceOracle(g.as_dict(), r.as_dict()).run()          # straight from the arrays
+    assert orc2.C == orc.C and orc2.uniq_reads == orc.uniq_reads
+    import numpy as np
+    assert np.array_equal(orc2.uniq_abund, orc.uniq_abund) and np.array_equal(orc2.mult_abund, orc.mult_abund)
