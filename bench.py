@@ -86,15 +86,21 @@ def decode_rates(graph, synth, idx, rkw, n_pairs):
     try:
         sample = synth.make_reads(graph, synth.SEED0 + idx + 1000, n_pairs=n_pairs, read_len=rkw["read_len"])
         gf, js, pk = synth.export_files(graph, sample, tmp)
-        n_lines = sum(1 for _ in open(js))
-        size = os.path.getsize(js)
+        # the sample repeated 8 times (every copy starts a new read group): a file big enough to amortise start-up
+        big = os.path.join(tmp, "big.json")
+        with open(big, "wb") as dst:
+            blob = open(js, "rb").read()
+            for _ in range(8):
+                dst.write(blob)
+        n_lines = 8 * blob.count(b"\n")
+        size = os.path.getsize(big)
         best = None
-        for _ in range(3):
+        for _ in range(2):
             t0 = time.perf_counter()
-            got = decode.decode_json(js, graph, 0.95)
+            got = decode.decode_json(big, graph, 0.95)
             dt = time.perf_counter() - t0
             best = dt if best is None else min(best, dt)
-        assert got.n_alns == sample.n_alns
+        assert got.n_alns == 8 * sample.n_alns
         # Python decoder (the reference's json.loads + BFS + metaalign2align, restated) on the first lines, one core
         head = os.path.join(tmp, "head.json")
         n_head = 0

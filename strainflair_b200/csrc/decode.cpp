@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <memory>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -631,29 +632,37 @@ sfb_decoded* sfb_decode_json(const char* path, const int64_t* node_ids, const in
         nt.build();
         if (trace) fprintf(stderr, "[decode] node table %.3f s\n", now() - t0);
         std::vector<Line> carry;                 // decoded lines of a group cut by the block boundary
-        std::string buf, tail;
+        std::unique_ptr<char[]> block;            // raw storage: no zero fill of the read buffer
+        std::string tail;                         // partial last line of the previous block
         bool eof = false;
         while (!eof) {
             // one block: leftover partial line + fresh bytes, cut at the last newline
             t0 = now();
-            buf.swap(tail);
-            tail.clear();
-            const size_t have = buf.size();
+            const size_t have = tail.size();
             const size_t want = (size_t)std::min<long long>(block_bytes, std::max<long long>(remaining, 0));
-            buf.resize(have + want);                       // (value-initialises: keep blocks modest)
-            const size_t got = want ? fread(&buf[have], 1, want, fh) : 0;
-            buf.resize(have + got);
+            block.reset(new char[have + want + 1]);
+            if (have) memcpy(block.get(), tail.data(), have);
+            const size_t got = want ? fread(block.get() + have, 1, want, fh) : 0;
             remaining -= (long long)got;
             eof = remaining <= 0 || got < want;
+            size_t len = have + got;
+            tail.clear();
             if (!eof) {
-                const size_t cut = buf.rfind('\n');
-                if (cut == std::string::npos) {
-                    tail.swap(buf);               // no complete line yet: keep accumulating
+                size_t cut = len;
+                while (cut > 0 && block[cut - 1] != '\n') --cut;
+                if (cut == 0) {                    // no complete line yet: keep accumulating
+                    tail.assign(block.get(), len);
                     continue;
                 }
-                tail.assign(buf, cut + 1, std::string::npos);
-                buf.resize(cut + 1);
+                tail.assign(block.get() + cut, len - cut);
+                len = cut;
             }
+            struct View {
+                const char* p;
+                size_t n;
+                const char* data() const { return p; }
+                size_t size() const { return n; }
+            } buf{block.get(), len};
             std::vector<std::pair<size_t, size_t>> spans;
             for (size_t p = 0; p < buf.size();) {
                 const void* nl = memchr(buf.data() + p, '\n', buf.size() - p);
