@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SFB_ABI_VERSION 4
+#define SFB_ABI_VERSION 5
 
 /* ---- status codes ---------------------------------------------------- */
 #define SFB_OK            0
@@ -101,8 +101,6 @@ enum {
 typedef struct sfb_graph {
     int64_t n_nodes, n_paths, n_slots, n_strains, mask_words;
     const int32_t*  slot_node;     /* [n_slots] dense node index, -1 on sentinels            */
-    const int32_t*  slot_len;      /* [n_slots] Node.len_sequence of that node (:104), 1 on sentinels */
-    const int32_t*  slot_path;     /* [n_slots] path id owning the slot                      */
     const int32_t*  path_off;      /* [n_paths+1]                                            */
     const int32_t*  occ_off;       /* [n_nodes+1] node -> occurrences (Node.traversed_path + position scan, :352-357) */
     const int32_t*  occ_pair;      /* [2*(n_slots-n_paths)] per occurrence, ascending by slot: (slot, node of

@@ -17,7 +17,7 @@ class SfbGraph(C.Structure):
     _fields_ = [
         ("n_nodes", C.c_int64), ("n_paths", C.c_int64), ("n_slots", C.c_int64), ("n_strains", C.c_int64),
         ("mask_words", C.c_int64),
-        ("slot_node", C.c_void_p), ("slot_len", C.c_void_p), ("slot_path", C.c_void_p), ("path_off", C.c_void_p),
+        ("slot_node", C.c_void_p), ("path_off", C.c_void_p),
         ("occ_off", C.c_void_p), ("occ_pair", C.c_void_p), ("blk_path", C.c_void_p), ("path_seq_len", C.c_void_p),
         ("path_nstrain", C.c_void_p), ("path_strain0", C.c_void_p), ("path_smask", C.c_void_p),
         ("path_cluster", C.c_void_p),
@@ -62,7 +62,7 @@ SLOT_MASK, MATCH_REV, MATCH_MULTI, MATCH_NONE = 0x3FFFFFFF, 0x40000000, 0x800000
 MAX_SLOTS = 0x3FFFFFFF
 (ABSENT, FILTERED, UNASSIGNED, UNASSIGNED_BOOK, DEFER, ASSIGN_SAME, ASSIGN_DIFF, MULTI_ALIGN, INCONSIST,
  SE_COUNTED) = range(10)
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 EXPORTS = ("sfb_abi_version", "sfb_version", "sfb_last_error", "sfb_match", "sfb_classify", "sfb_pass1_scatter",
            "sfb_pass2", "sfb_pass2_resolve", "sfb_pass2_scatter", "sfb_path_reduce", "sfb_cluster_strain_counts", "sfb_strain_aggregate",

@@ -38,7 +38,7 @@ static int check_graph(const sfb_graph* g) {
     SFB_REQUIRE(g->n_nodes >= 0 && g->n_paths >= 0 && g->n_slots >= 0 && g->n_strains >= 0, "negative size");
     SFB_REQUIRE(g->n_slots <= SFB_MAX_SLOTS, "n_slots exceeds 2^30-1");
     SFB_REQUIRE(g->mask_words >= 1 && g->mask_words * 64 >= g->n_strains, "mask_words too small");
-    SFB_REQUIRE(g->slot_node && g->slot_len && g->slot_path && g->path_off && g->occ_off && g->occ_pair && g->blk_path &&
+    SFB_REQUIRE(g->slot_node && g->path_off && g->occ_off && g->occ_pair && g->blk_path &&
                     g->path_seq_len && g->path_nstrain && g->path_strain0 && g->path_smask && g->path_cluster,
                 "null graph array");
     return SFB_OK;

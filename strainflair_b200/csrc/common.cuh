@@ -120,6 +120,13 @@ __device__ __forceinline__ double record_cov(const sfb_reads& r, i64 rec) {
     return (double)(v & 0xffff) / (double)(v >> 16);        // aligned bases / node length, IEEE division
 }
 
+// slot -> path id through the 64-slot block table and at most a few steps along path_off (both small, cache resident)
+__device__ __forceinline__ int path_of_slot(const sfb_graph& g, int s) {
+    int p = g.blk_path[s >> 6];
+    while (g.path_off[p + 1] <= s) ++p;
+    return p;
+}
+
 // A mate of a read group: its retained alignments [a0, a0+na) (json2csv.py:686-739).
 struct Mate {
     i64 a0;

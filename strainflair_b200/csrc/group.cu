@@ -36,7 +36,7 @@ __device__ __forceinline__ int first_cluster(const Dev& d, i64 a) {
     const int n0 = d.r.walk_node[d.r.aln_walk_off[a]];
     const int o = d.g.occ_off[n0];
     if (o == d.g.occ_off[n0 + 1]) return -2;
-    return d.g.path_cluster[d.g.slot_path[d.g.occ_pair[2 * (size_t)o]]];
+    return d.g.path_cluster[path_of_slot(d.g, d.g.occ_pair[2 * (size_t)o])];
 }
 __device__ __forceinline__ void book(const Dev& d, BlockCounters& sc, const Mate& mt, int cluster) {
     if (cluster < 0) { SFB_COUNT(sc, SFB_C_NO_CLUSTER, 1); return; }

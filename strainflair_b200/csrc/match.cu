@@ -16,13 +16,6 @@ struct MatchStats {
     int cand, cmp;
 };
 
-// slot -> path id through the 64-slot block table and at most a few steps along path_off (both small, cache resident)
-__device__ __forceinline__ int path_of_slot(const sfb_graph& g, int s) {
-    int p = g.blk_path[s >> 6];
-    while (g.path_off[p + 1] <= s) ++p;
-    return p;
-}
-
 // One orientation: candidates are the occurrences of `anchor` (= the first node of the oriented walk); `second` is the
 // oriented walk's second node and step = +1 (walk as is) or -1 (reversed walk, read from its last record backwards).
 template <bool kEmit>

@@ -45,8 +45,6 @@ class DeviceGraph:
         self.slot_of_plain = (np.arange(T, dtype=np.int64) + np.repeat(np.arange(P, dtype=np.int64), plen))
         slot_node = np.full(n_slots, -1, np.int32)
         slot_node[self.slot_of_plain] = graph.path_nodes
-        slot_len = np.ones(n_slots, np.int32)
-        slot_len[self.slot_of_plain] = graph.node_len[graph.path_nodes]
         slot_path = np.repeat(np.arange(P, dtype=np.int32), plen + 1)
         path_off = (graph.path_off + np.arange(P + 1, dtype=np.int64)).astype(np.int32)
         order = np.argsort(graph.path_nodes, kind="stable")
@@ -71,8 +69,7 @@ class DeviceGraph:
         self.path_off_host = path_off
         d = self.device
         self.t = dict(
-            slot_node=_to_dev(slot_node, d), slot_len=_to_dev(slot_len, d), slot_path=_to_dev(slot_path, d),
-            path_off=_to_dev(path_off, d), occ_off=_to_dev(occ_off.astype(np.int32), d), occ_pair=_to_dev(occ_pair.reshape(-1), d), blk_path=_to_dev(blk_path, d),
+            slot_node=_to_dev(slot_node, d), path_off=_to_dev(path_off, d), occ_off=_to_dev(occ_off.astype(np.int32), d), occ_pair=_to_dev(occ_pair.reshape(-1), d), blk_path=_to_dev(blk_path, d),
             path_seq_len=_to_dev(graph.path_seq_len, d), path_nstrain=_to_dev(nstrain, d),
             path_strain0=_to_dev(strain0, d), path_smask=_to_dev(smask.view(np.int64), d),
             path_cluster=_to_dev(graph.path_cluster, d),

@@ -68,7 +68,7 @@ def test_leaf_codes_match_oracle():
 def test_struct_sizes_are_pointer_and_int64_multiples():
     for st in (_lib.SfbGraph, _lib.SfbReads, _lib.SfbWork, _lib.SfbAccum):
         assert ctypes.sizeof(st) % 8 == 0
-    assert ctypes.sizeof(_lib.SfbGraph) == 8 * 17
+    assert ctypes.sizeof(_lib.SfbGraph) == 8 * 15
     assert ctypes.sizeof(_lib.SfbReads) == 8 * 12
     assert ctypes.sizeof(_lib.SfbWork) == 8 * 11
     assert ctypes.sizeof(_lib.SfbAccum) == 8 * 9
