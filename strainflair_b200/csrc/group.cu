@@ -362,6 +362,8 @@ __global__ void __launch_bounds__(128, SFB_CLS_MINBLK) k_classify(Dev d) {
     block_counters_flush(sc, d.acc.counters);
 }
 
+// Generic kernel: one thread per group of the slow list (measured faster than a warp per group for pass 1, where
+// most of the work is a handful of set tests; pass 2 is the other way round, see group_warp.cuh).
 __global__ void __launch_bounds__(128) k_classify_slow(Dev d) {
     __shared__ BlockCounters sc;
     block_counters_zero(sc);
@@ -709,62 +711,7 @@ __global__ void __launch_bounds__(128, SFB_P2_MINBLK) k_pass2_resolve(Dev d, con
     block_counters_flush(sc, d.acc.counters);
 }
 
-__global__ void __launch_bounds__(128) k_pass2_resolve_slow(Dev d, const long long* __restrict__ U) {
-    __shared__ BlockCounters sc;
-    block_counters_zero(sc);
-    __syncthreads();
-    const i64 n_slow = (i64)d.w.cursor[4];
-    const i64 n_round = (n_slow + 127) & ~(i64)127;
-    App* apps = reinterpret_cast<App*>(d.w.app_buf);
-    for (i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x; q < n_round; q += (i64)gridDim.x * blockDim.x) {
-        const bool live = q < n_slow;
-        LocalView lv;
-        GlobalView gv;
-        Mate mt[2];
-        Plan pl;
-        pl.mode[0] = pl.mode[1] = kNone;
-        pl.napp[0] = pl.napp[1] = 0;
-        bool fits = true;
-        i64 g = 0;
-        int code[2] = {SFB_P2_NONE, SFB_P2_NONE};
-        if (live) {
-            g = d.w.slow[q];
-            const int nm = d.r.grp_nmates[g];
-            mate_load(d.r, g, 0, mt[0]);
-            mate_load(d.r, g, 1, mt[1]);
-            fits = lv.load(d.w, mt);
-            if (!fits) gv.init(d.w, mt);
-            const int nt0 = fits ? lv.nt(0) : gv.nt(0), nt1 = fits ? lv.nt(1) : gv.nt(1);
-            int single = nm == 1 ? 0 : -1;
-            if (nm == 2) {
-                if (mt[0].na == 0 || mt[1].na == 0) single = mt[0].na == 0 ? 1 : 0;
-                else if (nt0 == 0 || nt1 == 0) single = nt0 == 0 ? 1 : 0;
-                else if (fits) p2_decide_pair(d, sc, lv, U, pl, code);
-                else p2_decide_pair(d, sc, gv, U, pl, code);
-            }
-            if (single >= 0) {
-                const int nts = single == 0 ? nt0 : nt1;
-                pl.mode[single] = kSingle;
-                pl.napp[single] = nts;
-                code[single] = p2_single_outcome(sc, nts);
-            }
-            d.w.grp_code2[g] = (uint8_t)(code[0] | (code[1] << 4));
-        }
-        const unsigned need = (unsigned)(pl.napp[0] + pl.napp[1]);
-        const u64 pos = warp_claim(d.w.cursor + 2, need);
-        if (live && need) {
-            SFB_COUNT(sc, SFB_C_ST_P2_APPLIED, (int)need);
-            if (pos + need <= (u64)d.w.app_cap) {
-                if (fits) p2_emit(d, sc, lv, mt, U, pl, apps + pos);
-                else p2_emit(d, sc, gv, mt, U, pl, apps + pos);
-            } else {
-                SFB_COUNT(sc, SFB_C_MATCH_OVERFLOW, (int)need);
-            }
-        }
-    }
-    __syncthreads();
-    block_counters_flush(sc, d.acc.counters);
-}
+#include "group_warp.cuh"
 
 int launch_classify(const Dev& d, cudaStream_t st) {
     if (d.r.n_groups == 0) return SFB_OK;
