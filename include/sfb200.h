@@ -156,7 +156,7 @@ typedef struct sfb_accum {
     double*    uniq_norm;         /* [P]  total_mapped_unique_reads_normalized                */
     double*    mult_reads;        /* [P]  total_mapped_mult_reads                             */
     double*    mult_norm;         /* [P]  total_mapped_mult_reads_normalized                  */
-    unsigned*  mult_hits;         /* [P]  number of pass-2 additions (0 <=> the reference prints an int 0) */
+    unsigned*  mult_hits;         /* [P]  non-zero once pass 2 added to the path (0 <=> the reference prints an int 0) */
     double*    uniq_abund;        /* [n_slots] unique_mapped_abundances                       */
     double*    mult_abund;        /* [n_slots] multiple_mapped_abundances                     */
     unsigned long long* hist;     /* [5*n_strains*101]                                        */

@@ -478,7 +478,7 @@ __device__ __forceinline__ void emit_app(const Dev& d, App* out, i64 a, uint32_t
                                       double ratio, int times) {
     atomicAdd(&d.acc.mult_reads[pid], ratio * (double)times);
     atomicAdd(&d.acc.mult_norm[pid], (ratio * (double)seq_len / (double)d.g.path_seq_len[pid]) * (double)times);
-    atomicAdd(&d.acc.mult_hits[pid], (unsigned)times);
+    d.acc.mult_hits[pid] = 1u;           // "touched" flag: same value from every writer, no atomic needed
     App app;
     app.aln = (int32_t)a;
     app.code = code;

@@ -201,6 +201,8 @@ class AbundanceEngine:
             self.path_bounds = sfdist.path_partition(self.dg.path_off_host, self.world)
             self.slot_bounds = self.dg.path_off_host.astype(np.int64)[self.path_bounds]
         self.work = None
+        self.side = torch.cuda.Stream(device=self.device)     # pass-1 scatter runs beside the uniq exchange + pass-2 resolve
+        self.overlap = True
         self.match_cap_hint = 0
         self.launches = 0
 
@@ -271,8 +273,16 @@ class AbundanceEngine:
         mark("match")
         self.classify(dr, work)
         mark("classify")
-        self.pass1_scatter(dr, work)
-        mark("pass1_scatter")
+        # the node loop of pass 1 only writes uniq_abund, which nothing reads before the path reduction:
+        # it overlaps with the exchange of uniq_reads and with the pass-2 resolve kernels on a second stream
+        main = torch.cuda.current_stream()
+        if self.overlap:
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side):
+                self.pass1_scatter(dr, work)
+        else:
+            self.pass1_scatter(dr, work)
+            mark("pass1_scatter")
         uniq_global = None
         if self.comm is not None:
             uniq_global = self.acc.uniq_reads.clone()
@@ -280,6 +290,8 @@ class AbundanceEngine:
             mark("allreduce_uniq")
         self.pass2_resolve(dr, work, uniq_global)
         mark("pass2_resolve")
+        if self.overlap:
+            main.wait_stream(self.side)
         self.pass2_scatter(dr, work)
         mark("pass2_scatter")
         if self.comm is None:
