@@ -255,7 +255,7 @@ def run_ours(args):
     t_gen = time.perf_counter() - t_gen
     eng = engine.AbundanceEngine(graph, device, comm=comm)
     host = engine.HostReads(reads, pin=True)
-    dr = engine.DeviceReads(host, device)
+    dr = eng.upload(host)
     torch.cuda.synchronize()
 
     def barrier():
@@ -313,19 +313,19 @@ def run_ours(args):
     # end to end: pinned host buffers -> device -> kernels -> results on the host, every step
     e2e = None
     if not args.no_e2e:
-        eng.run(host, keep_codes=False)
+        eng.run(host, keep_codes=False, keep_slots=False)
         barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            res = eng.run(host, keep_codes=False)
+            res = eng.run(host, keep_codes=False, keep_slots=False)   # what the reports need: table, counters, histograms
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-        d2h = eng.acc.f64.numel() * 8 + eng.acc.i64.numel() * 8 + eng.table.numel() * 8 + 16
+        d2h = eng.d2h_bytes(keep_slots=False)
         e2e = {"value": total_reads * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": host.nbytes(),
                "d2h_bytes_per_step": d2h, "ms_per_step": dt / args.steps * 1e3}
 

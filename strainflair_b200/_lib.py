@@ -33,6 +33,15 @@ class SfbReads(C.Structure):
     ]
 
 
+class SfbWire(C.Structure):
+    _fields_ = [
+        ("n_groups", C.c_int64), ("n_alns", C.c_int64), ("n_records", C.c_int64), ("n_exc", C.c_int64),
+        ("grp_nmates", C.c_void_p), ("mate_naln", C.c_void_p), ("mate_seq_len", C.c_void_p), ("aln_len", C.c_void_p),
+        ("aln_bins", C.c_void_p), ("walk_node", C.c_void_p), ("walk_al", C.c_void_p), ("exc_idx", C.c_void_p),
+        ("exc_cov", C.c_void_p),
+    ]
+
+
 class SfbWork(C.Structure):
     _fields_ = [
         ("aln_match", C.c_void_p), ("match_buf", C.c_void_p), ("match_cap", C.c_int64), ("cursor", C.c_void_p),
@@ -64,7 +73,7 @@ MAX_SLOTS = 0x3FFFFFFF
  SE_COUNTED) = range(10)
 ABI_VERSION = 5
 
-EXPORTS = ("sfb_abi_version", "sfb_version", "sfb_last_error", "sfb_match", "sfb_classify", "sfb_pass1_scatter",
+EXPORTS = ("sfb_abi_version", "sfb_version", "sfb_last_error", "sfb_expand_reads", "sfb_match", "sfb_classify", "sfb_pass1_scatter",
            "sfb_pass2", "sfb_pass2_resolve", "sfb_pass2_scatter", "sfb_path_reduce", "sfb_cluster_strain_counts", "sfb_strain_aggregate",
            "sfb_decode_json", "sfb_decoded_error", "sfb_decoded_size", "sfb_decoded_copy", "sfb_decoded_free")
 
@@ -100,6 +109,7 @@ def load(build_if_missing=True):
     lib.sfb_last_error.restype = C.c_char_p
     G, R, W, A = C.POINTER(SfbGraph), C.POINTER(SfbReads), C.POINTER(SfbWork), C.POINTER(SfbAccum)
     vp, i64, f64 = C.c_void_p, C.c_int64, C.c_double
+    lib.sfb_expand_reads.argtypes = [C.POINTER(SfbWire), vp, vp, vp, vp, vp, vp, vp]
     lib.sfb_match.argtypes = [G, R, W, A, vp]
     lib.sfb_classify.argtypes = [G, R, W, A, vp]
     lib.sfb_pass1_scatter.argtypes = [G, R, W, A, vp]
@@ -109,7 +119,7 @@ def load(build_if_missing=True):
     lib.sfb_path_reduce.argtypes = [G, A, i64, i64, vp, vp]
     lib.sfb_cluster_strain_counts.argtypes = [i64, i64, vp, vp, vp, vp, vp, vp, vp]
     lib.sfb_strain_aggregate.argtypes = [i64, i64, vp, vp, vp, vp, vp, vp, f64, vp, vp, vp, vp, vp]
-    for name in EXPORTS[3:12]:
+    for name in EXPORTS[3:13]:
         getattr(lib, name).restype = C.c_int
     lib.sfb_decode_json.argtypes = [C.c_char_p, vp, vp, i64, f64, C.c_int, i64]
     lib.sfb_decode_json.restype = C.c_void_p

@@ -25,7 +25,7 @@ def run_json2csv(graph_file, mapping_file, pickle_file, prefix, thr=0.95, device
     t0 = time.perf_counter()
     eng = engine.AbundanceEngine(graph, device)
     print("Parsing Alignment: second pass")
-    res = eng.run(reads)
+    res = eng.run(reads, keep_codes=True, keep_slots=False)
     t["abundance_s"] = time.perf_counter() - t0
     t0 = time.perf_counter()
     clusters = report.cluster_records(graph, reads, res)

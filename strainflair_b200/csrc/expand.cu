@@ -1,0 +1,115 @@
+// sfb_expand_reads: compact transfer ("wire") layout of a read shard -> the arrays the kernels consume.
+//
+// The end-to-end path is bound by the host->device copy (PCIe, ~55 GB/s): CSR offsets travel as 1-byte counts and
+// become int64 offsets by a device prefix sum; read lengths travel as 16 bits; per record only the aligned bases
+// travel (16 bits) and the node length is gathered from the graph on the device.  3.7 GB -> 2.3 GB per C3 shard.
+#include "common.cuh"
+
+namespace sfb {
+
+constexpr int kScanBlock = 256;
+constexpr int kScanItems = 16;                       // per thread
+constexpr int kScanTile = kScanBlock * kScanItems;   // 4096 counts per CTA
+
+__device__ __forceinline__ i64 block_excl_scan(i64 v, i64* s_warp, i64& block_total) {
+    // exclusive scan of one value per thread over a 256-thread block
+    i64 incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const i64 t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane_id() >= d) incl += t;
+    }
+    if (lane_id() == 31) s_warp[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    i64 base = 0, total = 0;
+    for (int wi = 0; wi < kScanBlock / 32; ++wi) {
+        if (wi < (int)(threadIdx.x >> 5)) base += s_warp[wi];
+        total += s_warp[wi];
+    }
+    __syncthreads();
+    block_total = total;
+    return base + incl - v;
+}
+
+// pass 1: sum of each tile of 4096 counts
+__global__ void __launch_bounds__(kScanBlock) k_scan_partials(const uint8_t* cnt, i64 n, i64* partial) {
+    __shared__ i64 s_warp[kScanBlock / 32];
+    const i64 lo = (i64)blockIdx.x * kScanTile + (i64)threadIdx.x * kScanItems;
+    i64 s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i)
+        if (lo + i < n) s += cnt[lo + i];
+    i64 total;
+    block_excl_scan(s, s_warp, total);
+    if (threadIdx.x == 0) partial[blockIdx.x] = total;
+}
+// pass 2: exclusive scan of the tile sums, one CTA
+__global__ void __launch_bounds__(kScanBlock) k_scan_tiles(i64* partial, i64 n_tiles) {
+    __shared__ i64 s_warp[kScanBlock / 32];
+    i64 carry = 0;
+    for (i64 base = 0; base < n_tiles; base += kScanBlock) {
+        const i64 i = base + threadIdx.x;
+        const i64 v = i < n_tiles ? partial[i] : 0;
+        i64 total;
+        const i64 ex = block_excl_scan(v, s_warp, total);
+        if (i < n_tiles) partial[i] = carry + ex;
+        carry += total;
+    }
+}
+// pass 3: offsets inside the tile + tile base; off[n] = total
+__global__ void __launch_bounds__(kScanBlock) k_scan_write(const uint8_t* cnt, i64 n, const i64* partial, i64* off) {
+    __shared__ i64 s_warp[kScanBlock / 32];
+    const i64 lo = (i64)blockIdx.x * kScanTile + (i64)threadIdx.x * kScanItems;
+    int c[kScanItems];
+    i64 s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        c[i] = lo + i < n ? cnt[lo + i] : 0;
+        s += c[i];
+    }
+    i64 total;
+    i64 run = partial[blockIdx.x] + block_excl_scan(s, s_warp, total);
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        if (lo + i < n) off[lo + i] = run;
+        run += c[i];
+        if (lo + i == n - 1) off[n] = run;
+    }
+}
+
+__global__ void k_expand_seq_len(const uint16_t* in, i64 n, int32_t* out) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) out[i] = in[i];
+}
+// packed coverage word of every record: aligned bases | node length << 16 (see record_cov)
+__global__ void k_expand_walk(const uint16_t* al, const int32_t* node, const int32_t* node_len, i64 n, int32_t* out) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+        out[i] = (int32_t)al[i] | (node_len[node[i]] << 16);
+}
+__global__ void k_apply_exceptions(const i64* exc_idx, i64 n_exc, int32_t* walk_alen) {
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < n_exc; k += (i64)gridDim.x * blockDim.x)
+        walk_alen[exc_idx[k]] = -(int32_t)(k + 1);
+}
+
+static int scan_u8(const uint8_t* cnt, i64 n, i64* off, i64* scratch, cudaStream_t st) {
+    if (n == 0) {
+        cudaMemsetAsync(off, 0, sizeof(i64), st);
+        return SFB_OK;
+    }
+    const i64 tiles = (n + kScanTile - 1) / kScanTile;
+    k_scan_partials<<<(unsigned)tiles, kScanBlock, 0, st>>>(cnt, n, scratch);
+    k_scan_tiles<<<1, kScanBlock, 0, st>>>(scratch, tiles);
+    k_scan_write<<<(unsigned)tiles, kScanBlock, 0, st>>>(cnt, n, scratch, off);
+    return check_launch("scan_u8");
+}
+
+int launch_expand(const sfb_wire* w, const int32_t* node_len, i64* grp_aln_off, int32_t* mate_seq_len, i64* aln_walk_off,
+                  int32_t* walk_alen, i64* scratch, cudaStream_t st) {
+    SFB_TRY(scan_u8(w->mate_naln, 2 * w->n_groups, grp_aln_off, scratch, st));
+    SFB_TRY(scan_u8(w->aln_len, w->n_alns, aln_walk_off, scratch, st));
+    if (w->n_groups) k_expand_seq_len<<<kSMs * 4, 256, 0, st>>>(w->mate_seq_len, 2 * w->n_groups, mate_seq_len);
+    if (w->n_records) k_expand_walk<<<kSMs * 8, 256, 0, st>>>(w->walk_al, w->walk_node, node_len, w->n_records, walk_alen);
+    if (w->n_exc) k_apply_exceptions<<<blocks_for(w->n_exc, 256), 256, 0, st>>>((const i64*)w->exc_idx, w->n_exc, walk_alen);
+    return check_launch("expand_reads");
+}
+
+}  // namespace sfb

@@ -85,29 +85,101 @@ READS_DEVICE_FIELDS = ("grp_nmates", "grp_aln_off", "mate_seq_len", "aln_walk_of
                        "walk_alen", "exc_cov")
 
 
-class HostReads:
-    """Reads staged in pinned host memory (the e2e path copies from here every step)."""
+WIRE_FIELDS = ("grp_nmates", "mate_naln", "mate_seq_len", "aln_len", "aln_bins", "walk_node", "walk_al", "exc_idx",
+               "exc_cov")
 
-    def __init__(self, reads: Reads, pin=True):
+
+def wire_arrays(reads: Reads):
+    """Compact transfer layout (include/sfb200.h, sfb_wire) of a read shard, or None when it does not apply
+    (a mate with > 255 alignments, a walk of > 255 nodes, a read of > 65535 bases)."""
+    naln = np.diff(reads.grp_aln_off)
+    alen = np.diff(reads.aln_walk_off)
+    if (naln.size and naln.max() > 255) or (alen.size and alen.max() > 255) or \
+            (reads.mate_seq_len.size and reads.mate_seq_len.max() > 0xFFFF):
+        return None
+    v = reads.walk_alen
+    neg = np.flatnonzero(v < 0)
+    al = (v & 0xFFFF).astype(np.uint16)
+    al[neg] = 0xFFFF
+    exc_idx = np.zeros(len(reads.exc_cov), np.int64)
+    exc_idx[-v[neg].astype(np.int64) - 1] = neg
+    return dict(grp_nmates=reads.grp_nmates, mate_naln=naln.astype(np.uint8),
+                mate_seq_len=reads.mate_seq_len.astype(np.uint16), aln_len=alen.astype(np.uint8),
+                aln_bins=reads.aln_bins.reshape(-1), walk_node=reads.walk_node, walk_al=al, exc_idx=exc_idx,
+                exc_cov=reads.exc_cov)
+
+
+def _layout(arrays):
+    """Offsets of the arrays inside one arena (256-byte aligned), and the arena size."""
+    offs, pos = {}, 0
+    for k, a in arrays.items():
+        offs[k] = (pos, a.nbytes)
+        pos += (a.nbytes + 255) & ~255
+    return offs, max(pos, 256)
+
+
+class HostReads:
+    """Reads staged in ONE pinned host arena, so that the upload of a shard is a single DMA at full PCIe rate
+    (the end-to-end path copies from here every step).  ``wire``: use the compact transfer layout when the shard
+    allows it (offsets as 1-byte counts, 16-bit lengths; expanded on the device by sfb_expand_reads)."""
+
+    def __init__(self, reads: Reads, pin=True, wire=True):
         self.reads = reads
-        self.t = {}
-        for k in READS_DEVICE_FIELDS:
-            t = torch.from_numpy(np.ascontiguousarray(getattr(reads, k)).reshape(-1))
-            self.t[k] = t.pin_memory() if (pin and t.numel()) else t
+        arrays = wire_arrays(reads) if wire else None
+        self.wire = arrays is not None
+        if arrays is None:
+            arrays = {k: np.ascontiguousarray(getattr(reads, k)).reshape(-1) for k in READS_DEVICE_FIELDS}
+        self.offs, self.size = _layout(arrays)
+        self.arena = torch.empty(self.size, dtype=torch.uint8)
+        if pin:
+            self.arena = self.arena.pin_memory()
+        view = self.arena.numpy()
+        for k, (o, n) in self.offs.items():
+            if n:
+                view[o:o + n] = np.ascontiguousarray(arrays[k]).reshape(-1).view(np.uint8)
         self.n_groups, self.n_alns, self.n_records = reads.n_groups, reads.n_alns, reads.n_records
         self.n_exc = len(reads.exc_cov)
 
     def nbytes(self):
-        return sum(v.numel() * v.element_size() for v in self.t.values())
+        return sum(n for _, n in self.offs.values())
 
 
 class DeviceReads:
-    def __init__(self, host: HostReads, device):
+    """Device copy of a HostReads arena (one DMA), expanded on the device when it is in the transfer layout.
+    ``arena`` / ``wide``: existing device buffers to reuse."""
+
+    def __init__(self, host: HostReads, device, arena=None, wide=None, node_len=None):
         self.host = host
-        self.t = {k: v.to(device, non_blocking=True) for k, v in host.t.items()}
-        self.n_groups, self.n_alns, self.n_records, self.n_exc = host.n_groups, host.n_alns, host.n_records, host.n_exc
-        self.c = _lib.SfbReads(n_groups=self.n_groups, n_alns=self.n_alns, n_records=self.n_records, n_exc=self.n_exc,
-                               **{k: v.data_ptr() for k, v in self.t.items()})
+        if arena is None or arena.numel() < host.size:
+            arena = torch.empty(host.size, dtype=torch.uint8, device=device)
+        self.arena = arena
+        self.arena[:host.size].copy_(host.arena, non_blocking=True)
+        base = self.arena.data_ptr()
+        G, A, R, E = host.n_groups, host.n_alns, host.n_records, host.n_exc
+        self.n_groups, self.n_alns, self.n_records, self.n_exc = G, A, R, E
+        ptr = {k: (base + o if n else 0) for k, (o, n) in host.offs.items()}
+        self.wide = wide
+        if not host.wire:
+            self.c = _lib.SfbReads(n_groups=G, n_alns=A, n_records=R, n_exc=E, **ptr)
+            return
+        # expanded arrays (one device allocation, reused across steps)
+        need = 8 * (2 * G + 1) + 4 * 2 * G + 8 * (A + 1) + 4 * R + 8 * (max(2 * G, A) // 4096 + 2) + 5 * 256
+        if wide is None or wide.numel() < need:
+            wide = torch.empty(need, dtype=torch.uint8, device=device)
+        self.wide = wide
+        p, out = wide.data_ptr(), {}
+        for k, n in (("grp_aln_off", 8 * (2 * G + 1)), ("aln_walk_off", 8 * (A + 1)), ("scratch", 8 * (max(2 * G, A) // 4096 + 2)),
+                     ("mate_seq_len", 8 * G), ("walk_alen", 4 * R)):
+            out[k] = p
+            p += (n + 255) & ~255
+        w = _lib.SfbWire(n_groups=G, n_alns=A, n_records=R, n_exc=E, **ptr)
+        _lib.check(_lib.load().sfb_expand_reads(C.byref(w), C.c_void_p(node_len.data_ptr()), C.c_void_p(out["grp_aln_off"]),
+                                                C.c_void_p(out["mate_seq_len"]), C.c_void_p(out["aln_walk_off"]),
+                                                C.c_void_p(out["walk_alen"]), C.c_void_p(out["scratch"]), _stream()))
+        self.c = _lib.SfbReads(n_groups=G, n_alns=A, n_records=R, n_exc=E, grp_nmates=ptr["grp_nmates"],
+                               grp_aln_off=out["grp_aln_off"], mate_seq_len=out["mate_seq_len"] if G else 0,
+                               aln_walk_off=out["aln_walk_off"], aln_bins=ptr["aln_bins"], walk_node=ptr["walk_node"],
+                               walk_alen=out["walk_alen"] if R else 0, exc_cov=ptr["exc_cov"])
 
 
 class Work:
@@ -191,6 +263,7 @@ class AbundanceEngine:
         torch.cuda.set_device(self.device)
         self.graph = graph
         self.dg = DeviceGraph(graph, self.device)
+        self.node_len = _to_dev(graph.node_len, self.device)
         self.comm = comm
         self.acc = Accum(self.dg)
         self.table = torch.empty((max(1, graph.n_paths), _lib.TABLE_COLS), dtype=torch.float64, device=self.device)
@@ -312,34 +385,57 @@ class AbundanceEngine:
         mark("path_reduce")
         return work
 
-    def run(self, reads, keep_codes=True):
-        """Public entry: host arrays in, host results out (H2D and D2H included)."""
+    def upload(self, host: HostReads):
+        """H2D of a staged shard (+ device-side expansion of the transfer layout), reusing the device buffers."""
+        dr = DeviceReads(host, self.device, getattr(self, "_arena", None), getattr(self, "_wide", None), self.node_len)
+        self._arena, self._wide = dr.arena, dr.wide
+        return dr
+
+    def run(self, reads, keep_codes=True, keep_slots=True):
+        """Public entry: host arrays in, host results out (H2D and D2H included).  The reports need the
+        per-path table, counters and histograms; ``keep_slots`` also brings the two per-node accumulator
+        arrays back, ``keep_codes`` the per-group leaf codes, assignments and match lists."""
         host = reads if isinstance(reads, HostReads) else HostReads(reads)
         for _ in range(3):
-            dr = DeviceReads(host, self.device)
+            dr = self.upload(host)
             work = self.run_device(dr)
-            res = self.fetch(work, dr, keep_codes)
+            res = self.fetch(work, dr, keep_codes, keep_slots)
             over = int(res.counters_raw[_lib.COUNTER_NAMES.index("MATCH_OVERFLOW")])
             if over == 0:
                 return res
-            self.match_cap_hint = int(work.t["cursor"][0].item()) + 1024   # exact need, rerun
+            self.match_cap_hint = res.match_fill + 1024                    # exact need, rerun
         raise MatchOverflow("match buffer still too small after regrowing")
 
-    def fetch(self, work, dr, keep_codes=True):
+    def fetch(self, work, dr, keep_codes=True, keep_slots=True):
         acc, dg = self.acc, self.dg
-        if self.comm is not None and getattr(self, "gather_slots", True):
-            # the host copy wants whole slot arrays: complete them from their owners (not part of the pass)
+        P, n_slots = acc.P, acc.n_slots
+        if keep_slots and self.comm is not None:
+            # whole slot arrays are wanted on the host: complete them from their owner ranks (not part of the pass)
             import torch.distributed as dist
             for arr in (acc.uniq_abund, acc.mult_abund):
                 for k in range(self.world):
                     lo, hi = int(self.slot_bounds[k]), int(self.slot_bounds[k + 1])
                     if hi > lo:
                         dist.broadcast(arr[lo:hi], src=dist.get_global_rank(self.comm, k), group=self.comm)
+        # small results through pinned staging buffers (one D2H each)
+        if getattr(self, "_stage", None) is None:
+            self._stage = dict(
+                f=torch.empty(3 * P, dtype=torch.float64).pin_memory(),
+                i=torch.empty(acc.i64.numel(), dtype=torch.int64).pin_memory(),
+                t=torch.empty((max(1, P), _lib.TABLE_COLS), dtype=torch.float64).pin_memory(),
+                c=torch.empty(8, dtype=torch.int64).pin_memory())
+        st = self._stage
+        st["f"].copy_(acc.f64[:3 * P], non_blocking=True)
+        st["i"].copy_(acc.i64, non_blocking=True)
+        st["t"].copy_(self.table, non_blocking=True)
+        st["c"].copy_(work.t["cursor"], non_blocking=True)
+        slots = None
+        if keep_slots:
+            if getattr(self, "_plain_idx", None) is None:
+                self._plain_idx = torch.from_numpy(dg.slot_of_plain).to(self.device)
+            slots = (acc.uniq_abund[self._plain_idx].cpu(), acc.mult_abund[self._plain_idx].cpu())   # sentinels dropped on device
         torch.cuda.current_stream().synchronize()
-        f64 = acc.f64.cpu().numpy()
-        i64 = acc.i64.cpu().numpy()
-        P, n_slots = acc.P, acc.n_slots
-        sl = dg.slot_of_plain
+        f64, i64 = st["f"].numpy(), st["i"].numpy()
         counters_raw = i64[P + acc.n_hist:P + acc.n_hist + _lib.N_COUNTERS].copy()
         res = Result(
             g=self.graph.as_dict(),
@@ -349,10 +445,11 @@ class AbundanceEngine:
             C={k: int(v) for k, v in zip(_lib.COUNTER_NAMES, counters_raw)},
             mult_hits=i64[P + acc.n_hist + _lib.N_COUNTERS:].view(np.int32)[:P].copy(),
             uniq_norm=f64[0:P].copy(), mult_reads=f64[P:2 * P].copy(), mult_norm=f64[2 * P:3 * P].copy(),
-            uniq_abund=f64[3 * P:3 * P + n_slots][sl], mult_abund=f64[3 * P + n_slots:][sl],
-            table=self.table[:P].cpu().numpy() if P else np.zeros((0, _lib.TABLE_COLS)),
-            n_deferred=int(work.t["cursor"][1].item()), match_fill=int(work.t["cursor"][0].item()),
+            table=st["t"].numpy()[:P].copy() if P else np.zeros((0, _lib.TABLE_COLS)),
+            n_deferred=int(st["c"][1]), match_fill=int(st["c"][0]),
         )
+        if slots is not None:
+            res.uniq_abund, res.mult_abund = slots[0].numpy(), slots[1].numpy()
         if keep_codes:
             res.grp_code = work.t["grp_code"][:dr.n_groups].cpu().numpy()
             res.grp_code2 = work.t["grp_code2"][:dr.n_groups].cpu().numpy()
@@ -362,6 +459,11 @@ class AbundanceEngine:
                 .view(np.uint32).reshape(-1, 2)
         check_errors(res.C)
         return res
+
+    def d2h_bytes(self, keep_slots=False):
+        """Bytes read back per pass by ``fetch`` (without the optional per-group codes)."""
+        n = (3 * self.acc.P + self.acc.i64.numel() + self.table.numel() + 8) * 8
+        return n + (2 * 8 * self.graph.n_path_nodes if keep_slots else 0)
 
 
 def check_errors(Cn):

@@ -182,3 +182,34 @@ def test_error_quirks_raise_like_reference():
     bad.aln_bins[:, 0] = 255
     with pytest.raises(KeyError):
         engine.abundance_pass(graph, bad)
+
+
+def test_transfer_layout_expands_to_the_same_arrays():
+    """sfb_expand_reads(wire(reads)) == the wide arrays, bit for bit (offset scans across tile boundaries,
+    explicit coverages, widened lengths)."""
+    need_gpu()
+    gkw, _ = synth.CONFIGS["small"]
+    graph = synth.make_graph(3, **gkw)
+    reads = synth.make_reads(graph, 4, n_pairs=30_000, read_len=150, p_exc=0.01)
+    eng = engine.AbundanceEngine(graph)
+    host = engine.HostReads(reads, wire=True)
+    assert host.wire and host.nbytes() < 0.7 * engine.HostReads(reads, wire=False).nbytes()
+    dr = eng.upload(host)
+    torch.cuda.synchronize()
+
+    # read the expanded arrays back through the pointers of the sfb_reads struct
+    def view(ptr, n, dt):
+        nbytes = n * torch.empty(0, dtype=dt).element_size()
+        off = ptr - dr.wide.data_ptr()
+        return dr.wide[off:off + nbytes].view(dt).cpu().numpy()
+
+    G, A, R = reads.n_groups, reads.n_alns, reads.n_records
+    assert np.array_equal(view(dr.c.grp_aln_off, 2 * G + 1, torch.int64), reads.grp_aln_off)
+    assert np.array_equal(view(dr.c.aln_walk_off, A + 1, torch.int64), reads.aln_walk_off)
+    assert np.array_equal(view(dr.c.mate_seq_len, 2 * G, torch.int32), reads.mate_seq_len)
+    assert np.array_equal(view(dr.c.walk_alen, R, torch.int32), reads.walk_alen)
+    # and the pass gives the same result from either layout
+    a = eng.run(engine.HostReads(reads, wire=True))
+    b = eng.run(engine.HostReads(reads, wire=False))
+    assert a.C == b.C and np.array_equal(a.uniq_reads, b.uniq_reads) and np.array_equal(a.grp_code, b.grp_code)
+    assert np.allclose(a.mult_abund, b.mult_abund, rtol=1e-12, atol=0)

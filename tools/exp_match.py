@@ -11,7 +11,7 @@ gkw, rkw = synth.CONFIGS["c3"]
 graph = synth.make_graph(synth.SEED0 + 2, **gkw)
 reads = synth.make_reads(graph, synth.SEED0 + 1002, n_pairs=int(rkw["n_pairs"] * scale), read_len=150)
 eng = engine.AbundanceEngine(graph, "cuda:0")
-dr = engine.DeviceReads(engine.HostReads(reads), eng.device)
+dr = eng.upload(engine.HostReads(reads))
 work = eng._work_for(dr)
 stages = ("match", "classify", "pass1_scatter", "pass2_resolve", "pass2_scatter")
 tot = {k: 0.0 for k in stages}
