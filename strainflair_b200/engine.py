@@ -148,12 +148,21 @@ class DeviceReads:
     """Device copy of a HostReads arena (one DMA), expanded on the device when it is in the transfer layout.
     ``arena`` / ``wide``: existing device buffers to reuse."""
 
-    def __init__(self, host: HostReads, device, arena=None, wide=None, node_len=None):
+    def __init__(self, host: HostReads, device, arena=None, wide=None, node_len=None, expand=True):
         self.host = host
         if arena is None or arena.numel() < host.size:
             arena = torch.empty(host.size, dtype=torch.uint8, device=device)
         self.arena = arena
-        self.arena[:host.size].copy_(host.arena, non_blocking=True)
+        self.arena[:host.size].copy_(host.arena, non_blocking=True)          # the one H2D copy of the shard
+        self.device, self.wide, self.node_len = device, wide, node_len
+        self.n_groups, self.n_alns, self.n_records, self.n_exc = host.n_groups, host.n_alns, host.n_records, host.n_exc
+        self.c = None
+        if expand:
+            self.expand()
+
+    def expand(self):
+        """Build the sfb_reads view (device-side expansion of the transfer layout, on the current stream)."""
+        host, device, wide, node_len = self.host, self.device, self.wide, self.node_len
         base = self.arena.data_ptr()
         G, A, R, E = host.n_groups, host.n_alns, host.n_records, host.n_exc
         self.n_groups, self.n_alns, self.n_records, self.n_exc = G, A, R, E
@@ -367,11 +376,18 @@ class AbundanceEngine:
             main.wait_stream(self.side)
         self.pass2_scatter(dr, work)
         mark("pass2_scatter")
+        self._finish_pass(mark)
+        return work
+
+    def _finish_pass(self, mark=lambda name: None):
+        """Exchange 2 (multi-GPU) and the per-path reduction."""
+        import torch.distributed as dist
+        from . import dist as sfdist
         if self.comm is None:
             self.path_reduce()
             mark("path_reduce")
-            return work
-        # exchange 2: small per-path state everywhere, slot arrays onto the path-partitioned layout
+            return
+        # small per-path state everywhere, slot arrays onto the path-partitioned layout
         P = self.acc.P
         dist.all_reduce(self.acc.i64, group=self.comm)
         dist.all_reduce(self.acc.f64[:3 * P], group=self.comm)
@@ -383,13 +399,65 @@ class AbundanceEngine:
         full = sfdist.all_gather_rows(mine, self.path_bounds, self.comm)
         self.table[:P].copy_(full)
         mark("path_reduce")
-        return work
 
     def upload(self, host: HostReads):
         """H2D of a staged shard (+ device-side expansion of the transfer layout), reusing the device buffers."""
         dr = DeviceReads(host, self.device, getattr(self, "_arena", None), getattr(self, "_wide", None), self.node_len)
         self._arena, self._wide = dr.arena, dr.wide
         return dr
+
+    def run_stream(self, shards):
+        """End-to-end pass over a data set staged as several HostReads shards (read groups split contiguously):
+        the H2D copy of shard k+1 overlaps with match / classify / pass-1 scatter of shard k; pass 2 runs once
+        every shard has contributed to ``uniq_reads``.  Device buffers are kept across calls.  Returns the
+        per-path results (no per-group codes)."""
+        import torch.distributed as dist
+        if getattr(self, "_copy", None) is None:
+            self._copy = torch.cuda.Stream(device=self.device)
+            self._slots = {}
+        main = torch.cuda.current_stream()
+        for attempt in range(3):
+            self.acc.zero()
+            self._copy.wait_stream(main)            # buffers of the previous call are free again
+            live = []
+            for k, host in enumerate(shards):
+                slot = self._slots.setdefault(k, {})
+                with torch.cuda.stream(self._copy):
+                    dr = DeviceReads(host, self.device, slot.get("arena"), slot.get("wide"), self.node_len, expand=False)
+                    arrived = torch.cuda.Event()
+                    arrived.record(self._copy)
+                slot["arena"] = dr.arena
+                main.wait_event(arrived)
+                dr.expand()
+                slot["wide"] = dr.wide
+                cap = max(slot.get("cap", 0), 2 * dr.n_alns + 1024)
+                work = slot.get("work")
+                if work is None or work.n_groups < dr.n_groups or work.n_alns < dr.n_alns or work.match_cap < cap:
+                    work = slot["work"] = Work(dr.n_groups, dr.n_alns, cap, self.device)
+                work.reset()
+                self.match(dr, work)
+                self.classify(dr, work)
+                self.side.wait_stream(main)
+                with torch.cuda.stream(self.side):
+                    self.pass1_scatter(dr, work)
+                live.append((dr, work))
+            uniq_global = None
+            if self.comm is not None:
+                uniq_global = self.acc.uniq_reads.clone()
+                dist.all_reduce(uniq_global, group=self.comm)
+            for dr, work in live:
+                self.pass2_resolve(dr, work, uniq_global)
+            main.wait_stream(self.side)
+            for dr, work in live:
+                self.pass2_scatter(dr, work)
+            self._finish_pass()
+            res = self.fetch(live[-1][1], live[-1][0], keep_codes=False, keep_slots=False)
+            if res.C["MATCH_OVERFLOW"] == 0:
+                res.n_deferred = sum(int(w.t["cursor"][1].item()) for _, w in live)
+                return res
+            for k, (dr, work) in enumerate(live):   # grow every shard's match buffer to its exact need, rerun
+                self._slots[k]["cap"] = int(work.t["cursor"][0].item()) + 1024
+        raise MatchOverflow("match buffer still too small after regrowing")
 
     def run(self, reads, keep_codes=True, keep_slots=True):
         """Public entry: host arrays in, host results out (H2D and D2H included).  The reports need the

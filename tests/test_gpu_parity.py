@@ -213,3 +213,23 @@ def test_transfer_layout_expands_to_the_same_arrays():
     b = eng.run(engine.HostReads(reads, wire=False))
     assert a.C == b.C and np.array_equal(a.uniq_reads, b.uniq_reads) and np.array_equal(a.grp_code, b.grp_code)
     assert np.allclose(a.mult_abund, b.mult_abund, rtol=1e-12, atol=0)
+
+
+def test_streamed_shards_equal_single_pass():
+    """run_stream (uploads overlapped with kernels, shards accumulated into the same arrays) == run."""
+    need_gpu()
+    from strainflair_b200 import dist as sfdist
+    graph, reads = synth.make_config("small", scale=0.5)
+    eng = engine.AbundanceEngine(graph)
+    one = eng.run(reads, keep_codes=False)
+    for k in (1, 3, 7):
+        shards = [engine.HostReads(reads.slice_groups(*sfdist.shard_bounds(reads.n_groups, k, i))) for i in range(k)]
+        for _ in range(2):                                   # second call reuses the device buffers
+            many = eng.run_stream(shards)
+            for name in oa.COUNTERS:
+                assert many.C[name] == one.C[name], (k, name)
+            assert np.array_equal(many.uniq_reads, one.uniq_reads) and np.array_equal(many.hist, one.hist)
+            assert many.n_deferred == one.n_deferred
+            ok = np.abs(many.table - one.table) <= 1e-9 * np.maximum(np.abs(many.table), np.abs(one.table))
+            assert (ok | (np.isnan(many.table) & np.isnan(one.table))).all()
+            assert np.allclose(many.mult_reads, one.mult_reads, rtol=1e-9, atol=0)
