@@ -353,6 +353,12 @@ def run_ours(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = by[top] / (kernels[top] * 1e-3) / 1e9
+        traffic = None
+        try:                      # DRAM bytes per launch of that kernel from the committed ncu capture of this workload
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+                traffic = json.load(fh).get(f"{args.config}@{args.scale}", {}).get(top)
+        except Exception:
+            pass
         whole = by["total"] / (sum(kernels.values()) * 1e-3) / 1e9
         survey = by["survey_total"] / (sum(kernels.values()) * 1e-3) / 1e9
         line = {
@@ -371,7 +377,7 @@ def run_ours(args):
             "gpu_launches": launches,
             "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes": by[top], "kernel_ms": kernels[top],
                          "whole_pass": {"achieved": whole, "frac": whole / peak, "algorithmic_bytes": by["total"]},
