@@ -8,6 +8,10 @@
 // parsed once, lines are decoded in parallel, and only the (cheap) grouping is sequential.
 #include <algorithm>
 #include <chrono>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <atomic>
 #include <cmath>
 #include <cstdint>
@@ -184,21 +188,6 @@ struct Line {
     std::vector<Edit> edits;
     std::vector<Aln> alns;          // filled by decode_line
     Fail fail{E_NONE, ""};
-    std::vector<char> own;          // backing store once the line outlives its file block (a vector, not a
-                                    // string: moving a short std::string moves its bytes)
-    void detach() {                 // copy name / pair / sequence out of the block buffer
-        std::vector<char> s;
-        s.reserve(name_n + pair_n + seq_n + 1);
-        const size_t o1 = name_n, o2 = name_n + pair_n;
-        if (name) s.insert(s.end(), name, name + name_n);
-        if (pair) s.insert(s.end(), pair, pair + pair_n);
-        if (seq) s.insert(s.end(), seq, seq + seq_n);
-        s.push_back('\0');
-        own.swap(s);
-        if (name) name = own.data();
-        if (pair) pair = own.data() + o1;
-        if (seq) seq = own.data() + o2;
-    }
 };
 
 void parse_line(const char* b, const char* e, Line& ln) {
@@ -497,7 +486,7 @@ struct sfb_decoded {
     std::string names;
     int err_kind = E_NONE;
     std::string err_msg;
-    double seconds_parse = 0, seconds_group = 0;
+    int64_t n_alns = 0, n_recs = 0;          // running totals (the per-alignment / per-record arrays are filled in parallel)
 };
 
 namespace {
@@ -533,7 +522,13 @@ struct MateAcc {
     std::vector<const Aln*> alns;
 };
 
-void emit_group(sfb_decoded& D, const std::vector<MateAcc>& mates) {
+struct EmitItem {       // one retained alignment: where its data goes
+    const Aln* a;
+    int64_t aln, rec;
+};
+
+// serial part of the output: group / mate scalars, names, offsets; the bulky arrays are filled by fill_items
+void emit_group(sfb_decoded& D, const std::vector<MateAcc>& mates, std::vector<EmitItem>& items) {
     D.grp_nmates.push_back((uint8_t)mates.size());
     for (int m = 0; m < 2; ++m) {
         if ((size_t)m < mates.size()) {
@@ -541,30 +536,54 @@ void emit_group(sfb_decoded& D, const std::vector<MateAcc>& mates) {
             D.mate_seq_len.push_back((int32_t)mt.seq_n);
             unescape_into(D.names, mt.name, mt.name_n);
             for (const Aln* a : mt.alns) {
-                for (size_t i = 0; i < a->node.size(); ++i) {
-                    D.walk_node.push_back(a->node[i]);
-                    D.walk_cov.push_back(a->cov[i]);
-                    D.walk_alen.push_back(a->alen[i]);      // re-encoded against walk_cov at the end
-                }
-                D.aln_walk_off.push_back((int64_t)D.walk_node.size());
-                D.aln_read_len.push_back(a->read_len);
-                for (int k = 0; k < 5; ++k) {
-                    D.aln_stats.push_back(a->stats[k]);
-                    D.aln_bins.push_back(a->bins[k]);
-                }
+                items.push_back(EmitItem{a, D.n_alns, D.n_recs});
+                D.n_alns += 1;
+                D.n_recs += (int64_t)a->node.size();
+                D.aln_walk_off.push_back(D.n_recs);
             }
         } else {
             D.mate_seq_len.push_back(0);
         }
         D.name_off.push_back((int64_t)D.names.size());
-        D.grp_aln_off.push_back((int64_t)D.aln_read_len.size());
+        D.grp_aln_off.push_back(D.n_alns);
     }
 }
 
-// get_all_alignments_one_read over already decoded lines (json2csv.py:667-739)
+struct Exc {            // a record whose coverage has to be shipped as fp64
+    int64_t rec;
+    double cov;
+};
+
+// parallel part: alignment and record arrays (already sized), packed coverage words, exceptions per thread
+void fill_items(sfb_decoded& D, const std::vector<EmitItem>& items, size_t lo, size_t hi, const int32_t* node_len,
+                std::vector<Exc>& exc) {
+    for (size_t q = lo; q < hi; ++q) {
+        const EmitItem& it = items[q];
+        const Aln& a = *it.a;
+        D.aln_read_len[it.aln] = a.read_len;
+        for (int k = 0; k < 5; ++k) {
+            D.aln_stats[it.aln * 5 + k] = a.stats[k];
+            D.aln_bins[it.aln * 5 + k] = a.bins[k];
+        }
+        for (size_t i = 0; i < a.node.size(); ++i) {
+            const int64_t r = it.rec + (int64_t)i;
+            const int32_t al = a.alen[i], nl = node_len[a.node[i]];
+            D.walk_node[r] = a.node[i];
+            D.walk_cov[r] = a.cov[i];
+            // aligned bases | node length << 16 when that reproduces the reference's fp64, else an explicit entry
+            if (al >= 0 && al <= 0xFFFF && nl >= 1 && nl <= 0x7FFF && (double)al / (double)nl == a.cov[i]) {
+                D.walk_alen[r] = al | (nl << 16);
+            } else {
+                D.walk_alen[r] = 0;
+                exc.push_back(Exc{r, a.cov[i]});
+            }
+        }
+    }
+}
+
 // Returns the index of the first line NOT consumed: when `eof` is false the last group of the block may
 // continue in the next block, so it is left for the caller to carry over.
-size_t group_lines(sfb_decoded& D, std::vector<Line>& lines, double thr, bool eof) {
+size_t group_lines(sfb_decoded& D, std::vector<Line>& lines, double thr, bool eof, std::vector<EmitItem>& items) {
     size_t i = 0;
     const size_t n = lines.size();
     while (i < n) {
@@ -604,7 +623,7 @@ size_t group_lines(sfb_decoded& D, std::vector<Line>& lines, double thr, bool eo
             }
         }
         if (j == n && !eof) return i;
-        emit_group(D, mates);
+        emit_group(D, mates, items);
         i = j;
     }
     return n;
@@ -617,108 +636,112 @@ extern "C" {
 sfb_decoded* sfb_decode_json(const char* path, const int64_t* node_ids, const int32_t* node_len, int64_t n_nodes,
                              double thr, int n_threads, int64_t block_bytes) {
     sfb_decoded* D = new sfb_decoded();
-    FILE* fh = nullptr;
+    int fd = -1;
+    const char* data = nullptr;
+    size_t size = 0;
     try {
-        fh = fopen(path, "rb");
-        if (!fh) throw Fail{E_IO, std::string("cannot open ") + path};
+        fd = open(path, O_RDONLY);
+        if (fd < 0) throw Fail{E_IO, std::string("cannot open ") + path};
+        struct stat sb;
+        if (fstat(fd, &sb) != 0) throw Fail{E_IO, "fstat failed"};
+        size = (size_t)sb.st_size;
+        if (size) {
+            void* m = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m == MAP_FAILED) throw Fail{E_IO, "mmap failed"};
+            data = (const char*)m;
+            madvise(m, size, MADV_SEQUENTIAL);
+        }
         if (block_bytes <= 0) block_bytes = 64ll << 20;
-        fseek(fh, 0, SEEK_END);
-        long long remaining = ftell(fh);
-        fseek(fh, 0, SEEK_SET);
         auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         const bool trace = getenv("SFB_DECODE_TRACE") != nullptr;
-        double t_read = 0, t_par = 0, t_grp = 0, t0 = now();
+        double t_par = 0, t_grp = 0, t_fill = 0, t0;
         NodeTable nt{node_ids, node_len, n_nodes, {}, {}};
         nt.build();
-        if (trace) fprintf(stderr, "[decode] node table %.3f s\n", now() - t0);
-        std::vector<Line> carry;                 // decoded lines of a group cut by the block boundary
-        std::unique_ptr<char[]> block;            // raw storage: no zero fill of the read buffer
-        std::string tail;                         // partial last line of the previous block
-        bool eof = false;
-        while (!eof) {
-            // one block: leftover partial line + fresh bytes, cut at the last newline
-            t0 = now();
-            const size_t have = tail.size();
-            const size_t want = (size_t)std::min<long long>(block_bytes, std::max<long long>(remaining, 0));
-            block.reset(new char[have + want + 1]);
-            if (have) memcpy(block.get(), tail.data(), have);
-            const size_t got = want ? fread(block.get() + have, 1, want, fh) : 0;
-            remaining -= (long long)got;
-            eof = remaining <= 0 || got < want;
-            size_t len = have + got;
-            tail.clear();
-            if (!eof) {
-                size_t cut = len;
-                while (cut > 0 && block[cut - 1] != '\n') --cut;
-                if (cut == 0) {                    // no complete line yet: keep accumulating
-                    tail.assign(block.get(), len);
-                    continue;
+        const int T = std::max(1, n_threads);
+        std::vector<Line> carry;                 // decoded lines of a group cut by the block boundary (they point into the map)
+        std::vector<std::vector<Exc>> exc(T);
+        size_t pos = 0;
+        bool eof = size == 0;
+        while (!eof || !carry.empty()) {
+            // one block of whole lines
+            size_t end = std::min(size, pos + (size_t)block_bytes);
+            if (end < size) {
+                size_t cut = end;
+                while (cut > pos && data[cut - 1] != '\n') --cut;
+                if (cut == pos) {                  // a line longer than the block: take it whole
+                    const void* nl = memchr(data + end, '\n', size - end);
+                    cut = nl ? (size_t)((const char*)nl - data) + 1 : size;
                 }
-                tail.assign(block.get() + cut, len - cut);
-                len = cut;
+                end = cut;
             }
-            struct View {
-                const char* p;
-                size_t n;
-                const char* data() const { return p; }
-                size_t size() const { return n; }
-            } buf{block.get(), len};
+            eof = end >= size;
             std::vector<std::pair<size_t, size_t>> spans;
-            for (size_t p = 0; p < buf.size();) {
-                const void* nl = memchr(buf.data() + p, '\n', buf.size() - p);
-                const size_t q = nl ? (size_t)((const char*)nl - buf.data()) : buf.size();
+            for (size_t p = pos; p < end;) {
+                const void* nl = memchr(data + p, '\n', end - p);
+                const size_t q = nl ? (size_t)((const char*)nl - data) : end;
                 spans.emplace_back(p, q);
                 p = q + 1;
             }
-            t_read += now() - t0;
+            pos = end;
             t0 = now();
             std::vector<Line> lines(carry.size() + spans.size());
             for (size_t i = 0; i < carry.size(); ++i) lines[i] = std::move(carry[i]);
             const size_t base = carry.size();
             carry.clear();
-            const int T = std::max(1, std::min<int>(n_threads, (int)std::max<size_t>(1, spans.size() / 64)));
-            std::atomic<size_t> next{0};
-            auto work = [&] {
-                for (;;) {
-                    const size_t lo = next.fetch_add(256);
-                    if (lo >= spans.size()) return;
-                    const size_t hi = std::min(spans.size(), lo + 256);
-                    for (size_t i = lo; i < hi; ++i) {
-                        try {
-                            parse_line(buf.data() + spans[i].first, buf.data() + spans[i].second, lines[base + i]);
-                            decode_line(lines[base + i], nt);
-                        } catch (const Fail& f) {
-                            lines[base + i].fail = f;
-                        }
+            auto run_parallel = [&](size_t n_items, size_t grain, auto&& body) {
+                const int use = (int)std::max<size_t>(1, std::min<size_t>((size_t)T, n_items / grain + 1));
+                std::atomic<size_t> next{0};
+                auto work = [&](int tid) {
+                    for (;;) {
+                        const size_t lo = next.fetch_add(grain);
+                        if (lo >= n_items) return;
+                        body(lo, std::min(n_items, lo + grain), tid);
+                    }
+                };
+                std::vector<std::thread> pool;
+                for (int t = 1; t < use; ++t) pool.emplace_back(work, t);
+                work(0);
+                for (auto& th : pool) th.join();
+            };
+            run_parallel(spans.size(), 256, [&](size_t lo, size_t hi, int) {
+                for (size_t i = lo; i < hi; ++i) {
+                    try {
+                        parse_line(data + spans[i].first, data + spans[i].second, lines[base + i]);
+                        decode_line(lines[base + i], nt);
+                    } catch (const Fail& f) {
+                        lines[base + i].fail = f;
                     }
                 }
-            };
-            std::vector<std::thread> pool;
-            for (int t = 1; t < T; ++t) pool.emplace_back(work);
-            work();
-            for (auto& th : pool) th.join();
+            });
             t_par += now() - t0;
             t0 = now();
-            const size_t used = group_lines(*D, lines, thr, eof);
-            for (size_t i = used; i < lines.size(); ++i) {
-                lines[i].detach();
-                carry.push_back(std::move(lines[i]));
-            }
+            std::vector<EmitItem> items;
+            const size_t used = group_lines(*D, lines, thr, eof, items);
             t_grp += now() - t0;
+            t0 = now();
+            D->aln_read_len.resize((size_t)D->n_alns);
+            D->aln_stats.resize((size_t)D->n_alns * 5);
+            D->aln_bins.resize((size_t)D->n_alns * 5);
+            D->walk_node.resize((size_t)D->n_recs);
+            D->walk_alen.resize((size_t)D->n_recs);
+            D->walk_cov.resize((size_t)D->n_recs);
+            run_parallel(items.size(), 512, [&](size_t lo, size_t hi, int tid) { fill_items(*D, items, lo, hi, node_len, exc[tid]); });
+            for (size_t i = used; i < lines.size(); ++i) carry.push_back(std::move(lines[i]));
+            if (eof && used == lines.size()) carry.clear();
+            t_fill += now() - t0;
+            if (eof && carry.empty()) break;
+            if (eof && !carry.empty() && spans.empty()) throw Fail{E_IO, "internal: unconsumed lines at end of file"};
         }
-        if (trace) fprintf(stderr, "[decode] read+split %.3f s, parse+route (parallel) %.3f s, group+emit %.3f s\n", t_read, t_par, t_grp);
-        fclose(fh);
-        fh = nullptr;
-        // coverage encoding: integer aligned length when alen/len reproduces the reference's fp64, else explicit
-        for (size_t r = 0; r < D->walk_node.size(); ++r) {
-            const int32_t al = D->walk_alen[r], nl = node_len[D->walk_node[r]];
-            if (al >= 0 && al <= 0xFFFF && nl >= 1 && nl <= 0x7FFF && (double)al / (double)nl == D->walk_cov[r]) {
-                D->walk_alen[r] = al | (nl << 16);          // aligned bases | node length << 16
-            } else {
-                D->exc_cov.push_back(D->walk_cov[r]);
-                D->walk_alen[r] = -(int32_t)D->exc_cov.size();
-            }
+        // explicit coverages in record order (deterministic whatever the thread count)
+        std::vector<Exc> all;
+        for (auto& v : exc) all.insert(all.end(), v.begin(), v.end());
+        std::sort(all.begin(), all.end(), [](const Exc& x, const Exc& y) { return x.rec < y.rec; });
+        for (const Exc& e : all) {
+            D->exc_cov.push_back(e.cov);
+            D->walk_alen[(size_t)e.rec] = -(int32_t)D->exc_cov.size();
         }
+        if (trace)
+            fprintf(stderr, "[decode] parse+route (parallel) %.3f s, group %.3f s, fill (parallel) %.3f s\n", t_par, t_grp, t_fill);
     } catch (const Fail& f) {
         D->err_kind = f.kind;
         D->err_msg = f.msg;
@@ -726,7 +749,8 @@ sfb_decoded* sfb_decode_json(const char* path, const int64_t* node_ids, const in
         D->err_kind = E_IO;
         D->err_msg = ex.what();
     }
-    if (fh) fclose(fh);
+    if (data) munmap((void*)data, size);
+    if (fd >= 0) close(fd);
     return D;
 }
 
