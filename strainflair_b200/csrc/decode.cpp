@@ -56,6 +56,19 @@ inline void str(Cur& c, const char*& b, size_t& n) {
     ++c.p;
 }
 inline double num(Cur& c) {
+    // plain integers (almost every number of a vg alignment) without strtod
+    const char* p = c.p;
+    bool neg = false;
+    if (p < c.e && *p == '-') { neg = true; ++p; }
+    if (p < c.e && *p >= '0' && *p <= '9') {
+        long long v = 0;
+        int digits = 0;
+        while (p < c.e && *p >= '0' && *p <= '9' && digits < 18) { v = v * 10 + (*p - '0'); ++p; ++digits; }
+        if (p >= c.e || (*p != '.' && *p != 'e' && *p != 'E' && !(*p >= '0' && *p <= '9'))) {
+            c.p = p;
+            return neg ? -(double)v : (double)v;
+        }
+    }
     char* end = nullptr;
     const double v = strtod(c.p, &end);
     if (end == c.p) bad("expected number");
@@ -410,8 +423,14 @@ void best_routes(const Line& ln, std::vector<Route>& out) {
 
 // Python round(x, 2) -> histogram key index, 255 when outside the table (json2csv.py:269-273, 335-339)
 inline uint8_t bin_of(double x) {
+    // away from a rounding tie the nearest multiple of 0.01 is unambiguous; x * 100 is exact to ~1e-14 here
+    const double y = x * 100.0, f = std::floor(y), frac = y - f;
+    if (std::fabs(frac - 0.5) > 1e-6 && y > -1e6 && y < 1e6) {
+        const long k = (long)(frac > 0.5 ? f + 1.0 : f);
+        return (k < 0 || k > 100) ? (uint8_t)255 : (uint8_t)k;
+    }
     char buf[64];
-    snprintf(buf, sizeof buf, "%.2f", x);          // glibc: exact decimal expansion, round-half-even
+    snprintf(buf, sizeof buf, "%.2f", x);          // glibc: exact decimal expansion, round-half-even (= Python round)
     const double r = strtod(buf, nullptr);
     const long k = lround(r * 100.0);
     if (k < 0 || k > 100 || (double)k / 100.0 != r) return 255;
