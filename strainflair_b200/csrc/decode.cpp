@@ -747,6 +747,10 @@ sfb_decoded* sfb_decode_json(const char* path, const int64_t* node_ids, const in
             run_parallel(items.size(), 512, [&](size_t lo, size_t hi, int tid) { fill_items(*D, items, lo, hi, node_len, exc[tid]); });
             for (size_t i = used; i < lines.size(); ++i) carry.push_back(std::move(lines[i]));
             if (eof && used == lines.size()) carry.clear();
+            // release the per-line heap blocks from the worker threads (millions of frees, otherwise serial)
+            run_parallel(lines.size(), 1024, [&](size_t lo, size_t hi, int) {
+                for (size_t i = lo; i < hi; ++i) { Line dead; std::swap(dead, lines[i]); }
+            });
             t_fill += now() - t0;
             if (eof && carry.empty()) break;
             if (eof && !carry.empty() && spans.empty()) throw Fail{E_IO, "internal: unconsumed lines at end of file"};
