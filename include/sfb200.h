@@ -106,8 +106,9 @@ typedef struct sfb_graph {
     const int32_t*  occ_pair;      /* [2*(n_slots-n_paths)] per occurrence, ascending by slot: (slot, node of
                                       slot+1) -- the successor lets a candidate be rejected without touching
                                       slot_node (8-byte aligned)                                          */
-    const int32_t*  blk_path;      /* [(n_slots+63)/64] path id owning slot 64*b (slot -> path without the
-                                      n_slots-sized slot_path gather)                                     */
+    const int32_t*  blk_path;      /* [2*((n_slots+63)/64)] per block of 64 slots: (path id owning slot 64*b, first
+                                      slot inside the block where the next path starts | INT_MAX if none | -1 if
+                                      several paths start there): slot -> path with one 8-byte load         */
     const int64_t*  path_seq_len;  /* [n_paths] get_sequence_length (:220-221)               */
     const int32_t*  path_nstrain;  /* [n_paths] len(path.strain_ids)                         */
     const int32_t*  path_strain0;  /* [n_paths] first strain id of the path (histogram row, :334) */

@@ -120,11 +120,16 @@ __device__ __forceinline__ double record_cov(const sfb_reads& r, i64 rec) {
     return (double)(v & 0xffff) / (double)(v >> 16);        // aligned bases / node length, IEEE division
 }
 
-// slot -> path id through the 64-slot block table and at most a few steps along path_off (both small, cache resident)
-__device__ __forceinline__ int path_of_slot(const sfb_graph& g, int s) {
-    int p = g.blk_path[s >> 6];
+// slot -> path id from the 64-slot block table: one 8-byte load; path_off is only walked for blocks in which several
+// paths start (paths shorter than 64 nodes)
+__device__ __forceinline__ int path_of_block(const sfb_graph& g, int2 e, int s) {
+    int p = e.x;
+    if (e.y >= 0) return p + (s >= e.y);
     while (g.path_off[p + 1] <= s) ++p;
     return p;
+}
+__device__ __forceinline__ int path_of_slot(const sfb_graph& g, int s) {
+    return path_of_block(g, reinterpret_cast<const int2*>(g.blk_path)[s >> 6], s);
 }
 
 // A mate of a read group: its retained alignments [a0, a0+na) (json2csv.py:686-739).

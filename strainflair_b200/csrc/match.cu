@@ -175,10 +175,11 @@ __global__ void __launch_bounds__(256, SFB_MATCH_MINBLK) k_match(sfb_graph g, sf
                 const i64 o_w0 = __shfl_sync(0xffffffffu, w0, j);
                 bool matched = false;
                 int pid = 0;
+                int2 blk = make_int2(0, 0);
                 if (valid) {
                     const i64 wf = rev ? o_w0 + o_L - 1 : o_w0;
                     const int step = rev ? -1 : 1;
-                    pid = g.blk_path[slot >> 6];                       // issued with the compare loads
+                    blk = reinterpret_cast<const int2*>(g.blk_path)[slot >> 6];   // issued with the compare loads
                     int pn[kU], wn[kU];
 #pragma unroll
                     for (int u = 0; u < kU; ++u) {
@@ -197,8 +198,7 @@ __global__ void __launch_bounds__(256, SFB_MATCH_MINBLK) k_match(sfb_graph g, sf
                         if (g.slot_node[min(slot + i, last_slot)] != r.walk_node[wf + (i64)step * i]) bad = i;
                     if (o_L > 2) st.cmp += min(bad, o_L - 1) - 1;
                     matched = bad >= o_L;
-                    if (matched)
-                        while (g.path_off[pid + 1] <= slot) ++pid;
+                    if (matched) pid = path_of_block(g, blk, slot);
                 }
                 const unsigned ball = __ballot_sync(0xffffffffu, matched);
                 const unsigned same = __match_any_sync(0xffffffffu, valid ? j : 32 + lane);

@@ -52,7 +52,18 @@ class DeviceGraph:
         occ_pair = np.empty((T, 2), np.int32)
         occ_pair[:, 0] = occ_slot
         occ_pair[:, 1] = slot_node[occ_slot.astype(np.int64) + 1]      # successor on the path (-1 at the path end)
-        blk_path = slot_path[::64].copy()
+        # slot -> path table per block of 64 slots: (path of the block's first slot, first slot inside the block where
+        # the next path starts | INT_MAX when none | -1 when several paths start in the block: walk path_off then)
+        n_blk = (n_slots + 63) // 64
+        blk_lo = np.arange(n_blk, dtype=np.int64) * 64
+        starts = path_off[:-1].astype(np.int64)
+        first = np.searchsorted(starts, blk_lo, side="right")               # index of the first path start > block start
+        last = np.searchsorted(starts, blk_lo + 63, side="right")           # starts <= block end
+        nxt = np.full(n_blk, 0x7FFFFFFF, np.int64)
+        one = (last - first) == 1
+        nxt[one] = starts[first[one]]
+        nxt[(last - first) > 1] = -1
+        blk_path = np.stack([slot_path[::64][:n_blk].astype(np.int64), nxt], axis=1).astype(np.int32)
         occ_off = np.zeros(graph.n_nodes + 1, np.int64)
         np.cumsum(np.bincount(graph.path_nodes, minlength=graph.n_nodes), out=occ_off[1:])
         S = graph.n_strains
@@ -69,7 +80,7 @@ class DeviceGraph:
         self.path_off_host = path_off
         d = self.device
         self.t = dict(
-            slot_node=_to_dev(slot_node, d), path_off=_to_dev(path_off, d), occ_off=_to_dev(occ_off.astype(np.int32), d), occ_pair=_to_dev(occ_pair.reshape(-1), d), blk_path=_to_dev(blk_path, d),
+            slot_node=_to_dev(slot_node, d), path_off=_to_dev(path_off, d), occ_off=_to_dev(occ_off.astype(np.int32), d), occ_pair=_to_dev(occ_pair.reshape(-1), d), blk_path=_to_dev(blk_path.reshape(-1), d),
             path_seq_len=_to_dev(graph.path_seq_len, d), path_nstrain=_to_dev(nstrain, d),
             path_strain0=_to_dev(strain0, d), path_smask=_to_dev(smask.view(np.int64), d),
             path_cluster=_to_dev(graph.path_cluster, d),
