@@ -260,6 +260,21 @@ int64_t      sfb_decoded_size(const sfb_decoded* d, int which);
 int          sfb_decoded_copy(const sfb_decoded* d, int which, void* dst);
 void         sfb_decoded_free(sfb_decoded* d);
 
+/* ---- host-side GFA loader (no GPU involved) ------------------------------------------------
+ * Pangenome.build_pangenome + canonical + get_accession_number (json2csv.py:46-81, 223-298) over a memory-mapped
+ * GFA.  sfb_gfa_size(which): 0 nodes, 1 paths, 2 path nodes, 3 (path, strain) entries, 4 strains, 5 bytes of strain
+ * names, 6 P lines, 7 bytes of gene names, 8 header strains, 9 index of the strain standing for None (-1 if none).
+ * sfb_gfa_copy(which): 0 node_ids i64, 1 node_len i32, 2 path_off i64[P+1], 3 path_nodes i32, 4 pstr_off i64[P+1],
+ * 5 pstr_id i32, 6 pstr_cnt i32, 7 header i32, 8 strain_off i64[S+1], 9 strain names, 10 gene_off i64[n+1],
+ * 11 gene names, 12 gene_pid i32[n] (P line -> path id).  sfb_gfa_error: 0 ok, 2 KeyError (path node without S line),
+ * 4 IndexError (short line), 5 I/O, 6 ValueError (int()). */
+typedef struct sfb_gfa sfb_gfa;
+sfb_gfa*     sfb_load_gfa(const char* path);
+int          sfb_gfa_error(const sfb_gfa* g, const char** msg);
+int64_t      sfb_gfa_size(const sfb_gfa* g, int which);
+int          sfb_gfa_copy(const sfb_gfa* g, int which, void* dst);
+void         sfb_gfa_free(sfb_gfa* g);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,7 +75,8 @@ ABI_VERSION = 5
 
 EXPORTS = ("sfb_abi_version", "sfb_version", "sfb_last_error", "sfb_expand_reads", "sfb_match", "sfb_classify", "sfb_pass1_scatter",
            "sfb_pass2", "sfb_pass2_resolve", "sfb_pass2_scatter", "sfb_path_reduce", "sfb_cluster_strain_counts", "sfb_strain_aggregate",
-           "sfb_decode_json", "sfb_decoded_error", "sfb_decoded_size", "sfb_decoded_copy", "sfb_decoded_free")
+           "sfb_decode_json", "sfb_decoded_error", "sfb_decoded_size", "sfb_decoded_copy", "sfb_decoded_free",
+           "sfb_load_gfa", "sfb_gfa_error", "sfb_gfa_size", "sfb_gfa_copy", "sfb_gfa_free")
 
 
 class SfbError(RuntimeError):
@@ -131,6 +132,16 @@ def load(build_if_missing=True):
     lib.sfb_decoded_copy.restype = C.c_int
     lib.sfb_decoded_free.argtypes = [vp]
     lib.sfb_decoded_free.restype = None
+    lib.sfb_load_gfa.argtypes = [C.c_char_p]
+    lib.sfb_load_gfa.restype = C.c_void_p
+    lib.sfb_gfa_error.argtypes = [vp, C.POINTER(C.c_char_p)]
+    lib.sfb_gfa_error.restype = C.c_int
+    lib.sfb_gfa_size.argtypes = [vp, C.c_int]
+    lib.sfb_gfa_size.restype = C.c_int64
+    lib.sfb_gfa_copy.argtypes = [vp, C.c_int, vp]
+    lib.sfb_gfa_copy.restype = C.c_int
+    lib.sfb_gfa_free.argtypes = [vp]
+    lib.sfb_gfa_free.restype = None
     if lib.sfb_abi_version() != ABI_VERSION:
         raise SfbError(f"ABI mismatch: library {lib.sfb_abi_version()}, binding {ABI_VERSION}")
     _lib = lib

@@ -1,111 +1,64 @@
 """GFA + cluster pickle -> Graph arrays (host side, one pass per graph).
 
-Reproduces what the reference's ``Pangenome.build_pangenome`` and ``fill_clusters_info`` build
-(json2csv.py:223-319) in the array schema of ``strainflair_b200.schema.Graph``:
+The GFA is parsed by the native loader of libsfb200.so (csrc/gfa.cpp), which reproduces what the reference's
+``Pangenome.build_pangenome`` builds (json2csv.py:223-298) in the array schema of ``strainflair_b200.schema.Graph``:
 
-* ``S`` lines give node lengths (ids are arbitrary positive ints -> dense indices in first-seen order);
+* ``S`` lines give node lengths (ids are arbitrary ints -> dense indices in first-seen order);
 * ``P`` lines are canonicalised (json2csv.py:46-61), merged when their canonical node string is equal
   (:260-266, strain copy counts add up) and numbered in first-seen order;
 * the strain of a path is the accession found in its name (:73-81); the header of the gene table lists
-  only strains that created a path (``species_names``, :268), which is what makes Q5's ragged rows;
-* the pickle maps ``Cluster_<k>`` -> gene names -> path ids (:310-318, last writer wins, duplicates kept).
+  only strains that created a path (``species_names``, :268), which is what makes Q5's ragged rows.
+
+The cluster pickle (a Python pickle) is read here: ``Cluster_<k>`` -> gene names -> path ids
+(``fill_clusters_info``, :300-319: last writer wins, duplicates kept).
 """
+import ctypes as C
+import os
 import pickle
-import re
 
 import numpy as np
 
+from . import _lib
 from .schema import Graph
 
-_ACCESSION = re.compile(r"[a-zA-Z]+_?[a-zA-Z]*[0-9]+")
-_FLIP = {"+": "-", "-": "+"}
+_ERRORS = {2: KeyError, 4: IndexError, 5: OSError, 6: ValueError}
 
 
-def strain_of_name(name):
-    head = name.rsplit("_", 1)[0] if "_" in name else ""
-    for part in head.split("|"):
-        if _ACCESSION.match(part):
-            return part
-    return None
+def load_graph(gfa_path, pickle_path=None) -> Graph:
+    lib = _lib.load()
+    h = lib.sfb_load_gfa(os.fsencode(gfa_path))
+    try:
+        msg = C.c_char_p()
+        kind = lib.sfb_gfa_error(h, C.byref(msg))
+        if kind:
+            raise _ERRORS.get(kind, RuntimeError)((msg.value or b"").decode(errors="replace"))
+        size = [int(lib.sfb_gfa_size(h, k)) for k in range(10)]
 
+        def take(which, n, dt):
+            out = np.empty(n, dt)
+            if n:
+                lib.sfb_gfa_copy(h, which, out.ctypes.data)
+            return out
 
-def _canonical(field):
-    toks = field.split(",")
-    if len(toks) == 1:
-        return toks[0][:-1] + "+", toks
-    if int(toks[0][:-1]) < int(toks[-1][:-1]):
-        return field, toks
-    toks = [t[:-1] + _FLIP.get(t[-1], "+") for t in reversed(toks)]
-    return ",".join(toks), toks
-
-
-def load_graph(gfa_path, pickle_path=None, progress=None) -> Graph:
-    node_index = {}
-    node_ids, node_len = [], []
-    seen = {}
-    path_names = {}
-    path_chunks = []            # per path: int32 array of dense nodes
-    path_strains = []           # per path: {strain index: copies}, insertion ordered
-    strains = {}
-    strain_names = []
-    header = []
-    in_header = set()
-    with open(gfa_path, "r") as fh:
-        for n_line, raw in enumerate(fh):
-            if progress is not None and n_line % 10000 == 0:
-                progress(fh)
-            f = raw.strip().split("\t")
-            kind = f[0]
-            if kind == "S":
-                nid = int(f[1])
-                k = node_index.get(nid)
-                if k is None:
-                    node_index[nid] = len(node_ids)
-                    node_ids.append(nid)
-                    node_len.append(len(f[2]))
-                else:
-                    node_len[k] = len(f[2])
-            elif kind == "P":
-                key, toks = _canonical(f[2])
-                acc = strain_of_name(f[1])
-                sid = strains.get(acc)
-                if sid is None:
-                    sid = strains[acc] = len(strain_names)
-                    strain_names.append(acc)
-                pid = seen.get(key)
-                if pid is not None:
-                    d = path_strains[pid]
-                    d[sid] = d.get(sid, 0) + 1
-                    path_names[f[1]] = pid
-                    continue
-                if sid not in in_header:
-                    in_header.add(sid)
-                    header.append(sid)
-                pid = len(path_chunks)
-                path_chunks.append(np.fromiter((node_index[int(t[:-1])] for t in toks), np.int32, count=len(toks)))
-                path_strains.append({sid: 1})
-                seen[key] = pid
-                path_names[f[1]] = pid
-    P = len(path_chunks)
-    path_off = np.zeros(P + 1, np.int64)
-    if P:
-        np.cumsum([len(c) for c in path_chunks], out=path_off[1:])
-    path_nodes = np.concatenate(path_chunks) if P else np.zeros(0, np.int32)
-    node_len = np.asarray(node_len, np.int32)
+        N, P, T, E, S, sbytes, n_genes, gbytes, n_header, none_idx = size
+        node_ids, node_len = take(0, N, np.int64), take(1, N, np.int32)
+        path_off, path_nodes = take(2, P + 1, np.int64), take(3, T, np.int32)
+        pstr_off, pstr_id, pstr_cnt = take(4, P + 1, np.int64), take(5, E, np.int32), take(6, E, np.int32)
+        header = [int(s) for s in take(7, n_header, np.int32)]
+        s_off, s_blob = take(8, S + 1, np.int64), take(9, sbytes, np.uint8).tobytes()
+        strain_names = [s_blob[int(s_off[i]):int(s_off[i + 1])].decode() for i in range(S)]
+        if none_idx >= 0:
+            strain_names[none_idx] = None                     # name without accession (Q14)
+        g_off, g_blob, g_pid = take(10, n_genes + 1, np.int64), take(11, gbytes, np.uint8).tobytes(), take(12, n_genes, np.int32)
+        path_names = {g_blob[int(g_off[i]):int(g_off[i + 1])].decode(): int(g_pid[i]) for i in range(n_genes)}
+    finally:
+        lib.sfb_gfa_free(h)
     csum = np.concatenate(([0], np.cumsum(node_len[path_nodes], dtype=np.int64)))
-    seq_len = csum[path_off[1:]] - csum[path_off[:-1]]
-    pstr_off = np.zeros(P + 1, np.int64)
-    pstr_id, pstr_cnt = [], []
-    for p, d in enumerate(path_strains):
-        pstr_id.extend(d.keys())
-        pstr_cnt.extend(d.values())
-        pstr_off[p + 1] = len(pstr_id)
     g = Graph(
-        node_ids=np.asarray(node_ids, np.int64), node_len=node_len, path_off=path_off, path_nodes=path_nodes,
-        path_seq_len=seq_len, pstr_off=pstr_off, pstr_id=np.asarray(pstr_id, np.int32),
-        pstr_cnt=np.asarray(pstr_cnt, np.int32), path_cluster=np.full(P, -1, np.int32),
-        clu_off=np.zeros(1, np.int64), clu_paths=np.zeros(0, np.int32), strain_names=strain_names,
-        header_strains=header, path_names=path_names, node_index=node_index,
+        node_ids=node_ids, node_len=node_len, path_off=path_off, path_nodes=path_nodes,
+        path_seq_len=csum[path_off[1:]] - csum[path_off[:-1]], pstr_off=pstr_off, pstr_id=pstr_id, pstr_cnt=pstr_cnt,
+        path_cluster=np.full(P, -1, np.int32), clu_off=np.zeros(1, np.int64), clu_paths=np.zeros(0, np.int32),
+        strain_names=strain_names, header_strains=header, path_names=path_names, node_index=None,
     )
     if pickle_path is not None:
         attach_clusters(g, pickle_path)

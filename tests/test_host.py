@@ -156,3 +156,32 @@ def test_synthetic_workload_round_trips_through_files(tmp_path):
         for k in ("grp_nmates", "grp_aln_off", "mate_seq_len", "aln_walk_off", "aln_read_len", "aln_bins", "walk_node",
                   "walk_alen"):
             assert np.array_equal(getattr(r, k), getattr(r2, k)), (name, k)
+
+
+@pytest.mark.parametrize("which,exc", [("path_before_segment", KeyError), ("short_line", IndexError), ("bad_id", ValueError)])
+def test_gfa_errors_match_oracle(which, exc, tmp_path):
+    text = {"path_before_segment": "P\tNC_1.1_1\t1+,2+\t*\nS\t1\tAC\nS\t2\tA\n",
+            "short_line": "S\t1\n", "bad_id": "S\tx1\tACGT\n"}[which]
+    p = tmp_path / "g.gfa"
+    p.write_text(text)
+    with pytest.raises(exc):
+        og.load_graph(str(p))
+    with pytest.raises(exc):
+        gfa.load_graph(str(p))
+
+
+def test_gfa_corner_cases_match_oracle(tmp_path):
+    """Orientation flips, single-node paths, names without accession (None strain, Q14), duplicate content from
+    several strains, re-declared segments, CRLF and trailing blanks, W/L/H lines ignored."""
+    text = ("H\tVN:Z:1.0\r\n"
+            "S\t10\tACGTAC\nS\t7\tAC\nS\t3\tA\nS\t10\tACG\n"          # node 10 re-declared: length 3
+            "P\tNC_000913.3_12\t10+,7+,3+\t*\n"                               # reversed into 3-,7-,10-
+            "P\tgi|55|ref|NZ_CP1.1|_9\t3-,7-,10-\t*\n"                        # same content, another strain
+            "P\tnoaccession\t7+\t*\n"                                         # single node, no '_' -> None strain
+            "P\tplasmid_x_1\t7-\t*\n"                                         # single node forced '+': same path, None again
+            "P\tNC_000913.3_13\t3+,7+\t*  \n"
+            "P\tAB12|zz_4\t3+,7-\t*\n"                                        # same nodes, other signs: a distinct path
+            "L\t3\t+\t7\t+\t0M\nW\tx\t1\tc\t0\t5\t>3>7\n\n")
+    p = tmp_path / "g.gfa"
+    p.write_text(text)
+    same_graph(gfa.load_graph(str(p)), og.load_graph(str(p)))
