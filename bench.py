@@ -333,8 +333,8 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-        d2h = eng.d2h_bytes(keep_slots=False)
-        e2e = {"value": total_reads * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "shards": args.e2e_shards,
+        d2h = eng.d2h_bytes(keep_slots=False) * world
+        e2e = {"value": total_reads * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "shards": args.e2e_shards,
                "d2h_bytes_per_step": d2h, "ms_per_step": dt / args.steps * 1e3}
 
     if rank == 0:

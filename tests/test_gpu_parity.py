@@ -175,13 +175,38 @@ def test_empty_and_degenerate_inputs():
 
 
 def test_error_quirks_raise_like_reference():
+    """Q7 / Q10: same exception classes as the reference (and as the oracle on the same arrays)."""
     need_gpu()
     graph, reads = synth.make_config("tiny")
     bad = Reads.from_dict(reads.as_dict())
     bad.aln_bins = bad.aln_bins.copy()
-    bad.aln_bins[:, 0] = 255
+    bad.aln_bins[:, 0] = 255                       # score outside [0, 1] used as a histogram key
     with pytest.raises(KeyError):
         engine.abundance_pass(graph, bad)
+    with pytest.raises(KeyError):
+        oa.AbundanceOracle(graph.as_dict(), bad.as_dict()).run()
+    # an unassigned read is recorded in the cluster of the first path through its first node: cluster None -> TypeError
+    g2 = Graph.from_dict(graph.as_dict())
+    g2.path_cluster = np.full_like(graph.path_cluster, -1)
+    orc = oa.AbundanceOracle(graph.as_dict(), reads.as_dict()).run()
+    assert orc.book, "the configuration must record some unassigned reads"
+    with pytest.raises(TypeError):
+        engine.abundance_pass(g2, reads)
+    with pytest.raises(TypeError):
+        oa.AbundanceOracle(g2.as_dict(), reads.as_dict()).run()
+    # ... and a first node that no path crosses -> IndexError
+    g3 = synth.make_graph(5, n_clusters=6, chain_len=10, hap_lo=1, hap_hi=2, n_strains=3, bubble_p=0.6, flip_p=0.0)
+    off_path = np.flatnonzero(~g3.on_path)
+    assert off_path.size, "needs a node outside every path"
+    r3 = synth.make_reads(g3, 6, n_pairs=50, read_len=40)
+    r3 = Reads.from_dict(r3.as_dict())
+    r3.walk_node = r3.walk_node.copy()
+    single = np.flatnonzero(np.diff(r3.aln_walk_off) >= 1)
+    r3.walk_node[r3.aln_walk_off[single]] = off_path[0]          # every walk now starts on that node: nothing matches
+    with pytest.raises(IndexError):
+        engine.abundance_pass(g3, r3)
+    with pytest.raises(IndexError):
+        oa.AbundanceOracle(g3.as_dict(), r3.as_dict()).run()
 
 
 def test_transfer_layout_expands_to_the_same_arrays():
