@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SFB_ABI_VERSION 5
+#define SFB_ABI_VERSION 6
 
 /* ---- status codes ---------------------------------------------------- */
 #define SFB_OK            0
@@ -180,6 +180,13 @@ typedef struct sfb_accum {
     double*    mult_abund;        /* [n_slots] multiple_mapped_abundances                     */
     unsigned long long* hist;     /* [5*n_strains*101]                                        */
     long long* counters;          /* [SFB_N_COUNTERS]                                         */
+    int64_t    det_stride;        /* 0: fp64 RED.ADD straight into the five fp64 arrays (order of the additions, hence
+                                     the last bits, vary from run to run).  > 0: order-independent accumulation --
+                                     every array has three planes, plane k of x at x + k*det_stride doubles; a term
+                                     is split into multiples of 2^-16, 2^-40 and 2^-64, each plane's sums are exact
+                                     in fp64 (up to 2^29 terms), so the result does not depend on thread order,
+                                     sharding or GPU count; sfb_accum_collapse folds the planes before
+                                     sfb_path_reduce                                                         */
 } sfb_accum;
 
 /* ---- entry points ------------------------------------------------------- */
@@ -216,6 +223,9 @@ int sfb_pass2(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_accum* ac
 int sfb_pass2_resolve(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_accum* acc,
                       const long long* uniq_reads_global, void* stream);
 int sfb_pass2_scatter(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_accum* acc, void* stream);
+
+/* Order-independent mode only (acc->det_stride > 0): x[i] = (plane0 + plane1) + plane2 for the n doubles at x. */
+int sfb_accum_collapse(double* x, int64_t n, int64_t det_stride, void* stream);
 
 /* Pangenome.print_gene_table's per-path reductions (json2csv.py:440-469) for paths
  * [p_begin, p_end): table[(p-p_begin)*8 + k], k = 0 nb_uniq_mapped_normalized,

@@ -54,7 +54,7 @@ class SfbAccum(C.Structure):
     _fields_ = [
         ("uniq_reads", C.c_void_p), ("uniq_norm", C.c_void_p), ("mult_reads", C.c_void_p), ("mult_norm", C.c_void_p),
         ("mult_hits", C.c_void_p), ("uniq_abund", C.c_void_p), ("mult_abund", C.c_void_p), ("hist", C.c_void_p),
-        ("counters", C.c_void_p),
+        ("counters", C.c_void_p), ("det_stride", C.c_int64),
     ]
 
 
@@ -71,10 +71,10 @@ SLOT_MASK, MATCH_REV, MATCH_MULTI, MATCH_NONE = 0x3FFFFFFF, 0x40000000, 0x800000
 MAX_SLOTS = 0x3FFFFFFF
 (ABSENT, FILTERED, UNASSIGNED, UNASSIGNED_BOOK, DEFER, ASSIGN_SAME, ASSIGN_DIFF, MULTI_ALIGN, INCONSIST,
  SE_COUNTED) = range(10)
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 EXPORTS = ("sfb_abi_version", "sfb_version", "sfb_last_error", "sfb_expand_reads", "sfb_match", "sfb_classify", "sfb_pass1_scatter",
-           "sfb_pass2", "sfb_pass2_resolve", "sfb_pass2_scatter", "sfb_path_reduce", "sfb_cluster_strain_counts", "sfb_strain_aggregate",
+           "sfb_pass2", "sfb_pass2_resolve", "sfb_pass2_scatter", "sfb_accum_collapse", "sfb_path_reduce", "sfb_cluster_strain_counts", "sfb_strain_aggregate",
            "sfb_decode_json", "sfb_decoded_error", "sfb_decoded_size", "sfb_decoded_copy", "sfb_decoded_free",
            "sfb_load_gfa", "sfb_gfa_error", "sfb_gfa_size", "sfb_gfa_copy", "sfb_gfa_free")
 
@@ -117,10 +117,11 @@ def load(build_if_missing=True):
     lib.sfb_pass2.argtypes = [G, R, W, A, vp, vp]
     lib.sfb_pass2_resolve.argtypes = [G, R, W, A, vp, vp]
     lib.sfb_pass2_scatter.argtypes = [G, R, W, A, vp]
+    lib.sfb_accum_collapse.argtypes = [vp, i64, i64, vp]
     lib.sfb_path_reduce.argtypes = [G, A, i64, i64, vp, vp]
     lib.sfb_cluster_strain_counts.argtypes = [i64, i64, vp, vp, vp, vp, vp, vp, vp]
     lib.sfb_strain_aggregate.argtypes = [i64, i64, vp, vp, vp, vp, vp, vp, f64, vp, vp, vp, vp, vp]
-    for name in EXPORTS[3:13]:
+    for name in EXPORTS[3:14]:
         getattr(lib, name).restype = C.c_int
     lib.sfb_decode_json.argtypes = [C.c_char_p, vp, vp, i64, f64, C.c_int, i64]
     lib.sfb_decode_json.restype = C.c_void_p

@@ -23,7 +23,7 @@ def run_json2csv(graph_file, mapping_file, pickle_file, prefix, thr=0.95, device
     reads = decode.decode_json(mapping_file, graph, thr)
     t["decode_s"] = time.perf_counter() - t0
     t0 = time.perf_counter()
-    eng = engine.AbundanceEngine(graph, device)
+    eng = engine.AbundanceEngine(graph, device, deterministic=True)     # files out: bit-reproducible from run to run
     print("Parsing Alignment: second pass")
     res = eng.run(reads, keep_codes=True, keep_slots=False)
     t["abundance_s"] = time.perf_counter() - t0

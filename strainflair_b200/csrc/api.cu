@@ -28,6 +28,7 @@ int launch_pass2_resolve(const Dev&, const long long*, cudaStream_t);
 int launch_pass1_scatter(const sfb_graph*, const sfb_reads*, const sfb_work*, sfb_accum*, cudaStream_t);
 int launch_pass2_scatter(const sfb_graph*, const sfb_reads*, const sfb_work*, sfb_accum*, cudaStream_t);
 int launch_expand(const sfb_wire*, const int32_t*, i64*, int32_t*, i64*, int32_t*, i64*, cudaStream_t);
+int launch_collapse(double*, i64, i64, cudaStream_t);
 int launch_path_reduce(const sfb_graph*, const sfb_accum*, i64, i64, double*, cudaStream_t);
 int launch_cluster_counts(i64, i64, const int32_t*, const int32_t*, const int32_t*, const int32_t*, const int32_t*,
                           long long*, cudaStream_t);
@@ -68,6 +69,7 @@ static int check_accum(const sfb_accum* a) {
     SFB_REQUIRE(a->uniq_reads && a->uniq_norm && a->mult_reads && a->mult_norm && a->mult_hits && a->uniq_abund &&
                     a->mult_abund && a->hist && a->counters,
                 "null accumulator");
+    SFB_REQUIRE(a->det_stride >= 0, "negative det_stride");
     return SFB_OK;
 }
 static int check_all(const sfb_graph* g, const sfb_reads* r, const sfb_work* w, const sfb_accum* a) {
@@ -136,6 +138,12 @@ int sfb_pass2_resolve(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_a
 int sfb_pass2_scatter(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_accum* acc, void* stream) {
     SFB_TRY(check_all(g, r, w, acc));
     return launch_pass2_scatter(g, r, w, acc, (cudaStream_t)stream);
+}
+
+int sfb_accum_collapse(double* x, int64_t n, int64_t det_stride, void* stream) {
+    SFB_REQUIRE(n >= 0 && det_stride >= n, "bad sizes");
+    SFB_REQUIRE(x || n == 0, "null array");
+    return launch_collapse(x, n, det_stride, (cudaStream_t)stream);
 }
 
 int sfb_path_reduce(const sfb_graph* g, const sfb_accum* acc, int64_t p_begin, int64_t p_end, double* table,

@@ -120,6 +120,21 @@ __device__ __forceinline__ double record_cov(const sfb_reads& r, i64 rec) {
     return (double)(v & 0xffff) / (double)(v >> 16);        // aligned bases / node length, IEEE division
 }
 
+// fp64 accumulation: plain RED, or (det_stride > 0) three exact partial sums, see sfb_accum in sfb200.h.  v >= 0.
+__device__ __forceinline__ void acc_add(double* p, i64 det_stride, double v) {
+    if (det_stride == 0) {
+        atomicAdd(p, v);
+        return;
+    }
+    const double c0 = floor(v * 0x1p16) * 0x1p-16;      // every step below is exact in fp64
+    const double r0 = v - c0;
+    const double c1 = floor(r0 * 0x1p40) * 0x1p-40;
+    const double c2 = rint((r0 - c1) * 0x1p64) * 0x1p-64;
+    if (c0 != 0.0) atomicAdd(p, c0);
+    if (c1 != 0.0) atomicAdd(p + det_stride, c1);
+    if (c2 != 0.0) atomicAdd(p + 2 * det_stride, c2);
+}
+
 // slot -> path id from the 64-slot block table: one 8-byte load; path_off is only walked for blocks in which several
 // paths start (paths shorter than 64 nodes)
 __device__ __forceinline__ int path_of_block(const sfb_graph& g, int2 e, int s) {

@@ -27,7 +27,7 @@ __device__ __forceinline__ void assign_unique(const Dev& d, BlockCounters& sc, i
                                            int seq_len) {
     d.w.aln_assign[a] = (int32_t)code;
     atomicAdd((u64*)&d.acc.uniq_reads[pid], 1ull);
-    atomicAdd(&d.acc.uniq_norm[pid], (double)seq_len / (double)d.g.path_seq_len[pid]);
+    acc_add(&d.acc.uniq_norm[pid], d.acc.det_stride, (double)seq_len / (double)d.g.path_seq_len[pid]);
     hist_add(d, sc, pid, a);
 }
 
@@ -476,8 +476,9 @@ __device__ __forceinline__ void p2_decide_pair(const Dev& d, BlockCounters& sc, 
 // json2csv.py:1155-1156 (and :1207-1208, :1265-1266) + the work item for the node loop (:1157-1158)
 __device__ __forceinline__ void emit_app(const Dev& d, App* out, i64 a, uint32_t code, int pid, int seq_len,
                                       double ratio, int times) {
-    atomicAdd(&d.acc.mult_reads[pid], ratio * (double)times);
-    atomicAdd(&d.acc.mult_norm[pid], (ratio * (double)seq_len / (double)d.g.path_seq_len[pid]) * (double)times);
+    acc_add(&d.acc.mult_reads[pid], d.acc.det_stride, ratio * (double)times);
+    acc_add(&d.acc.mult_norm[pid], d.acc.det_stride,
+            (ratio * (double)seq_len / (double)d.g.path_seq_len[pid]) * (double)times);
     d.acc.mult_hits[pid] = 1u;           // "touched" flag: same value from every writer, no atomic needed
     App app;
     app.aln = (int32_t)a;

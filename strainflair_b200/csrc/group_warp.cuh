@@ -111,8 +111,9 @@ __global__ void __launch_bounds__(128) k_pass2_resolve_slow(Dev d, const long lo
         const unsigned sel = __ballot_sync(0xffffffffu, take);
         if (take) {
             const int pid = M.pid;
-            atomicAdd(&d.acc.mult_reads[pid], ratio * (double)times);
-            atomicAdd(&d.acc.mult_norm[pid], (ratio * (double)mt.seq_len / (double)d.g.path_seq_len[pid]) * (double)times);
+            acc_add(&d.acc.mult_reads[pid], d.acc.det_stride, ratio * (double)times);
+            acc_add(&d.acc.mult_norm[pid], d.acc.det_stride,
+                    (ratio * (double)mt.seq_len / (double)d.g.path_seq_len[pid]) * (double)times);
             d.acc.mult_hits[pid] = 1u;       // "touched" flag, see emit_app
             App app;
             app.aln = (int32_t)(mt.a0 + M.aloc);

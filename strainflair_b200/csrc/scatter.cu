@@ -10,7 +10,8 @@
 
 namespace sfb {
 
-__global__ void __launch_bounds__(256) k_pass1_scatter(sfb_reads r, sfb_work w, double* uniq_abund, long long* counters) {
+__global__ void __launch_bounds__(256) k_pass1_scatter(sfb_reads r, sfb_work w, double* uniq_abund, i64 det_stride,
+                                                       long long* counters) {
     int done = 0;
     for (i64 a = (i64)blockIdx.x * blockDim.x + threadIdx.x; a < r.n_alns; a += (i64)gridDim.x * blockDim.x) {
         const int32_t code = w.aln_assign[a];
@@ -18,13 +19,14 @@ __global__ void __launch_bounds__(256) k_pass1_scatter(sfb_reads r, sfb_work w, 
         const i64 w0 = r.aln_walk_off[a];
         const int L = (int)(r.aln_walk_off[a + 1] - w0);
         double* dst = uniq_abund + ((uint32_t)code & SFB_SLOT_MASK);
-        for (int i = 0; i < L; ++i) atomicAdd(dst + i, record_cov(r, w0 + i));
+        for (int i = 0; i < L; ++i) acc_add(dst + i, det_stride, record_cov(r, w0 + i));
         done += L;
     }
     done = warp_sum(done);
     if (lane_id() == 0 && done) atomicAdd((u64*)&counters[SFB_C_ST_P1_RECORDS], (u64)done);
 }
-__global__ void __launch_bounds__(256) k_pass2_scatter(sfb_reads r, sfb_work w, double* mult_abund, long long* counters) {
+__global__ void __launch_bounds__(256) k_pass2_scatter(sfb_reads r, sfb_work w, double* mult_abund, i64 det_stride,
+                                                       long long* counters) {
     const App* apps = reinterpret_cast<const App*>(w.app_buf);
     const i64 n_app = min((i64)w.cursor[2], (i64)w.app_cap);
     int done = 0;
@@ -33,25 +35,35 @@ __global__ void __launch_bounds__(256) k_pass2_scatter(sfb_reads r, sfb_work w, 
         const i64 w0 = r.aln_walk_off[app.aln];
         const int L = (int)(r.aln_walk_off[app.aln + 1] - w0);
         double* dst = mult_abund + (app.code & SFB_SLOT_MASK);
-        for (int i = 0; i < L; ++i) atomicAdd(dst + i, record_cov(r, w0 + i) * app.weight);
+        for (int i = 0; i < L; ++i) acc_add(dst + i, det_stride, record_cov(r, w0 + i) * app.weight);
         done += L;
     }
     done = warp_sum(done);
     if (lane_id() == 0 && done) atomicAdd((u64*)&counters[SFB_C_ST_P2_RECORDS], (u64)done);
 }
 
+__global__ void k_collapse(double* x, i64 n, i64 stride) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+        x[i] = (x[i] + x[i + stride]) + x[i + 2 * stride];
+}
+int launch_collapse(double* x, i64 n, i64 stride, cudaStream_t st) {
+    if (n == 0) return SFB_OK;
+    k_collapse<<<kSMs * 8, 256, 0, st>>>(x, n, stride);
+    return check_launch("k_collapse");
+}
+
 int launch_pass1_scatter(const sfb_graph* g, const sfb_reads* r, const sfb_work* w, sfb_accum* acc, cudaStream_t st) {
     if (r->n_alns == 0) return SFB_OK;
     static int cache = 0;
     const unsigned grid = persistent_grid(k_pass1_scatter, 256, blocks_for(r->n_alns, 256), &cache);
-    k_pass1_scatter<<<grid, 256, 0, st>>>(*r, *w, acc->uniq_abund, acc->counters);
+    k_pass1_scatter<<<grid, 256, 0, st>>>(*r, *w, acc->uniq_abund, acc->det_stride, acc->counters);
     return check_launch("k_pass1_scatter");
 }
 int launch_pass2_scatter(const sfb_graph* g, const sfb_reads* r, const sfb_work* w, sfb_accum* acc, cudaStream_t st) {
     if (r->n_alns == 0 || w->app_cap == 0) return SFB_OK;
     static int cache = 0;
     const unsigned grid = persistent_grid(k_pass2_scatter, 256, blocks_for(w->app_cap, 256), &cache);
-    k_pass2_scatter<<<grid, 256, 0, st>>>(*r, *w, acc->mult_abund, acc->counters);
+    k_pass2_scatter<<<grid, 256, 0, st>>>(*r, *w, acc->mult_abund, acc->det_stride, acc->counters);
     return check_launch("k_pass2_scatter");
 }
 

@@ -233,12 +233,16 @@ class Accum:
     """Accumulators (sfb_accum), one flat fp64 and one flat int64 allocation so that a shard
     exchange is two collectives."""
 
-    def __init__(self, dg: DeviceGraph):
+    def __init__(self, dg: DeviceGraph, deterministic=False):
         P, S, n_slots = dg.n_paths, dg.n_strains, dg.n_slots
         dev = dg.device
         self.P, self.S, self.n_slots = P, S, n_slots
-        # fp64 block: uniq_norm | mult_reads | mult_norm | uniq_abund | mult_abund
-        self.f64 = torch.zeros(3 * P + 2 * n_slots, dtype=torch.float64, device=dev)
+        # fp64 block: uniq_norm | mult_reads | mult_norm | uniq_abund | mult_abund; in the order-independent mode
+        # three such planes (exact partial sums of multiples of 2^-16 / 2^-40 / 2^-64, see sfb200.h)
+        self.F = 3 * P + 2 * n_slots
+        self.planes = 3 if deterministic else 1
+        self.f64_all = torch.zeros(self.planes * self.F, dtype=torch.float64, device=dev)
+        self.f64 = self.f64_all[:self.F]
         # int64 block: uniq_reads | hist | counters | mult_hits (uint32 pairs packed in the tail)
         self.n_hist = _lib.N_HIST * S * _lib.N_BINS
         self.i64 = torch.zeros(P + self.n_hist + _lib.N_COUNTERS + (P + 1) // 2, dtype=torch.int64, device=dev)
@@ -253,11 +257,15 @@ class Accum:
             uniq_reads=self.uniq_reads.data_ptr(), uniq_norm=self.uniq_norm.data_ptr(),
             mult_reads=self.mult_reads.data_ptr(), mult_norm=self.mult_norm.data_ptr(),
             mult_hits=self.mult_hits.data_ptr(), uniq_abund=self.uniq_abund.data_ptr(),
-            mult_abund=self.mult_abund.data_ptr(), hist=self.hist.data_ptr(), counters=self.counters.data_ptr())
+            mult_abund=self.mult_abund.data_ptr(), hist=self.hist.data_ptr(), counters=self.counters.data_ptr(),
+            det_stride=self.F if deterministic else 0)
 
     def zero(self):
-        self.f64.zero_()
+        self.f64_all.zero_()
         self.i64.zero_()
+
+    def plane(self, k):
+        return self.f64_all[k * self.F:(k + 1) * self.F]
 
 
 class Result:
@@ -275,7 +283,7 @@ class AbundanceEngine:
     """One engine per process/GPU.  ``comm`` is an optional torch.distributed process group: when
     given, ``run`` treats ``reads`` as this rank's shard of the read groups."""
 
-    def __init__(self, graph: Graph, device="cuda:0", comm=None):
+    def __init__(self, graph: Graph, device="cuda:0", comm=None, deterministic=False):
         if not torch.cuda.is_available():
             raise _lib.SfbError("no CUDA device: the abundance engine has no CPU fallback")
         self.lib = _lib.load()
@@ -285,7 +293,8 @@ class AbundanceEngine:
         self.dg = DeviceGraph(graph, self.device)
         self.node_len = _to_dev(graph.node_len, self.device)
         self.comm = comm
-        self.acc = Accum(self.dg)
+        self.deterministic = deterministic      # order-independent fp64 sums: bit-identical across runs / shards / GPUs
+        self.acc = Accum(self.dg, deterministic)
         self.table = torch.empty((max(1, graph.n_paths), _lib.TABLE_COLS), dtype=torch.float64, device=self.device)
         self.world = 1 if comm is None else torch.distributed.get_world_size(comm)
         self.rank = 0 if comm is None else torch.distributed.get_rank(comm)
@@ -334,6 +343,11 @@ class AbundanceEngine:
 
     def pass2_scatter(self, dr, work):
         _lib.check(self.lib.sfb_pass2_scatter(C.byref(self.dg.c), C.byref(dr.c), C.byref(work.c), C.byref(self.acc.c), _stream()))
+        self.launches += 1
+
+    def collapse(self):
+        acc = self.acc
+        _lib.check(self.lib.sfb_accum_collapse(C.c_void_p(acc.f64_all.data_ptr()), acc.F, acc.F, _stream()))
         self.launches += 1
 
     def path_reduce(self, p_begin=0, p_end=None):
@@ -394,16 +408,24 @@ class AbundanceEngine:
         """Exchange 2 (multi-GPU) and the per-path reduction."""
         import torch.distributed as dist
         from . import dist as sfdist
+        acc = self.acc
         if self.comm is None:
+            if acc.planes > 1:
+                self.collapse()
             self.path_reduce()
             mark("path_reduce")
             return
-        # small per-path state everywhere, slot arrays onto the path-partitioned layout
-        P = self.acc.P
-        dist.all_reduce(self.acc.i64, group=self.comm)
-        dist.all_reduce(self.acc.f64[:3 * P], group=self.comm)
-        sfdist.reduce_scatter_ranges(self.acc.uniq_abund, self.slot_bounds, self.comm)
-        sfdist.reduce_scatter_ranges(self.acc.mult_abund, self.slot_bounds, self.comm)
+        # small per-path state everywhere, slot arrays onto the path-partitioned layout (every plane: the partial
+        # sums of the order-independent mode are exact, so the cross-rank sums are too)
+        P, n_slots = acc.P, acc.n_slots
+        dist.all_reduce(acc.i64, group=self.comm)
+        for k in range(acc.planes):
+            pl = acc.plane(k)
+            dist.all_reduce(pl[:3 * P], group=self.comm)
+            sfdist.reduce_scatter_ranges(pl[3 * P:3 * P + n_slots], self.slot_bounds, self.comm)
+            sfdist.reduce_scatter_ranges(pl[3 * P + n_slots:], self.slot_bounds, self.comm)
+        if acc.planes > 1:
+            self.collapse()
         mark("reduce_accum")
         p0, p1 = int(self.path_bounds[self.rank]), int(self.path_bounds[self.rank + 1])
         mine = self.path_reduce(p0, p1)
@@ -569,9 +591,9 @@ def decode_matches(res, a):
     return [(pid, int((c & _lib.SLOT_MASK) - starts[pid]), bool(c & _lib.MATCH_REV)) for c, pid in pairs]
 
 
-def abundance_pass(graph: Graph, reads: Reads, device="cuda:0") -> Result:
+def abundance_pass(graph: Graph, reads: Reads, device="cuda:0", deterministic=False) -> Result:
     """One-call public API: decoded alignments + graph in, per-path abundances and counters out."""
-    return AbundanceEngine(graph, device).run(reads)
+    return AbundanceEngine(graph, device, deterministic=deterministic).run(reads)
 
 
 def cluster_strain_counts(graph: Graph, device="cuda:0"):

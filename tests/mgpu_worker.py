@@ -37,6 +37,14 @@ def main():
             assert ok.all(), name
         assert np.array_equal(res.uniq_abund > 0, single.uniq_abund > 0)
         print(f"MGPU_OK world={world} groups={reads.n_groups}")
+    # order-independent mode: bit-identical whatever the number of GPUs
+    eng_d = engine.AbundanceEngine(graph, dev, comm=dist.group.WORLD, deterministic=True)
+    res_d = eng_d.run(reads.slice_groups(g0, g1))
+    if rank == 0:
+        single_d = engine.AbundanceEngine(graph, dev, deterministic=True).run(reads)
+        for name in ("uniq_norm", "mult_reads", "mult_norm", "uniq_abund", "mult_abund", "table"):
+            assert np.array_equal(getattr(res_d, name), getattr(single_d, name), equal_nan=True), name
+        print("MGPU_DET_OK")
     dist.barrier()
     dist.destroy_process_group()
 

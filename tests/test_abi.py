@@ -71,7 +71,7 @@ def test_struct_sizes_are_pointer_and_int64_multiples():
     assert ctypes.sizeof(_lib.SfbGraph) == 8 * 15
     assert ctypes.sizeof(_lib.SfbReads) == 8 * 12
     assert ctypes.sizeof(_lib.SfbWork) == 8 * 11
-    assert ctypes.sizeof(_lib.SfbAccum) == 8 * 9
+    assert ctypes.sizeof(_lib.SfbAccum) == 8 * 10
 
 
 def test_argument_validation_needs_no_gpu():

@@ -258,3 +258,27 @@ def test_streamed_shards_equal_single_pass():
             ok = np.abs(many.table - one.table) <= 1e-9 * np.maximum(np.abs(many.table), np.abs(one.table))
             assert (ok | (np.isnan(many.table) & np.isnan(one.table))).all()
             assert np.allclose(many.mult_reads, one.mult_reads, rtol=1e-9, atol=0)
+
+
+def test_order_independent_mode_is_bit_reproducible():
+    """deterministic=True: fp64 sums do not depend on thread order or on how the reads are sharded (bit-identical
+    across runs and across run / run_stream with any number of shards), and still match the oracle to 1e-9."""
+    need_gpu()
+    from strainflair_b200 import dist as sfdist
+    graph, reads = synth.make_config("small", scale=0.5)
+    eng = engine.AbundanceEngine(graph, deterministic=True)
+    a = eng.run(reads)
+    b = eng.run(reads)
+    for name in ("uniq_norm", "mult_reads", "mult_norm", "uniq_abund", "mult_abund", "table"):
+        x, y = getattr(a, name), getattr(b, name)
+        assert np.array_equal(x, y, equal_nan=True), name
+    for k in (2, 5):
+        shards = [engine.HostReads(reads.slice_groups(*sfdist.shard_bounds(reads.n_groups, k, i))) for i in range(k)]
+        c = eng.run_stream(shards)
+        for name in ("uniq_norm", "mult_reads", "mult_norm", "table"):
+            assert np.array_equal(getattr(a, name), getattr(c, name), equal_nan=True), (k, name)
+    orc = oa.AbundanceOracle(graph.as_dict(), reads.as_dict()).run()
+    check_against_oracle(graph, reads, a, orc)
+    # the default mode gives the same numbers up to the order of the additions
+    fast = engine.AbundanceEngine(graph).run(reads)
+    assert np.allclose(fast.mult_abund, a.mult_abund, rtol=1e-12, atol=0)
