@@ -4,8 +4,14 @@
 //   grouping and best-score filter   get_all_alignments_one_read   json2csv.py:667-739
 //   best routes through the subpath DAG   BFS                      json2csv.py:589-665
 //   walk / coverage / error ratios   metaalign2align               json2csv.py:551-587
-// The reference re-parses ~30 % of the file in its second pass and runs on one thread; here every line is
-// parsed once, lines are decoded in parallel, and only the (cheap) grouping is sequential.
+// The reference re-parses ~30 % of the file in its second pass and runs on one thread.  Here the file is mapped
+// and cut into blocks of whole lines; per block
+//   A  (parallel over lines)    parse + best routes + walks, into per-thread arenas that are reused (no per-line heap)
+//   B  (serial, a few compares per line)   read-group boundaries and the reference's error order
+//   C  (parallel over groups)   which lines' alignments a mate keeps (best score, ties), sizes
+//   D  (serial prefix sums)     output offsets
+//   E  (parallel over groups)   fill the output arrays of the block (allocated once, exact size, not zero-filled)
+// A group cut by the end of a block is decoded again at the start of the next one.
 #include <algorithm>
 #include <chrono>
 #include <fcntl.h>
@@ -18,7 +24,6 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <deque>
 #include <memory>
 #include <string>
 #include <thread>
@@ -42,7 +47,7 @@ struct Cur {
     const char* e;
 };
 inline void ws(Cur& c) {
-    while (c.p < c.e && (*c.p == ' ' || *c.p == '\t' || *c.p == '\r' || *c.p == '\n')) ++c.p;
+    while (c.p < c.e && (unsigned char)*c.p <= ' ' && (*c.p == ' ' || *c.p == '\t' || *c.p == '\r' || *c.p == '\n')) ++c.p;
 }
 [[noreturn]] void bad(const char* what) { throw Fail{E_JSON, std::string("malformed JSON: ") + what}; }
 
@@ -50,8 +55,20 @@ inline void ws(Cur& c) {
 inline void str(Cur& c, const char*& b, size_t& n) {
     if (c.p >= c.e || *c.p != '"') bad("expected string");
     b = ++c.p;
-    while (c.p < c.e && *c.p != '"') c.p += (*c.p == '\\') ? 2 : 1;
-    if (c.p >= c.e) bad("unterminated string");
+    {   // keys and most values are short and hold no escape: scan them in line
+        const char* p = b;
+        const char* lim = (c.e - b) > 24 ? b + 24 : c.e;
+        while (p < lim && *p != '"' && *p != '\\') ++p;
+        if (p < lim && *p == '"') { n = (size_t)(p - b); c.p = p + 1; return; }
+    }
+    for (const char* p = b;;) {
+        const char* q = p < c.e ? (const char*)memchr(p, '"', (size_t)(c.e - p)) : nullptr;
+        if (!q) bad("unterminated string");
+        const char* r = q;                       // an odd run of backslashes in front escapes the quote
+        while (r > b && r[-1] == '\\') --r;
+        if (((q - r) & 1) == 0) { c.p = q; break; }
+        p = q + 1;
+    }
     n = (size_t)(c.p - b);
     ++c.p;
 }
@@ -116,6 +133,12 @@ inline long long int_like(Cur& c) {
     if (c.p < c.e && *c.p == '"') {
         const char* b; size_t n;
         str(c, b, n);
+        if (n >= 1 && n <= 18) {                 // plain digits: the usual case
+            long long v = 0;
+            size_t i = 0;
+            for (; i < n && b[i] >= '0' && b[i] <= '9'; ++i) v = v * 10 + (b[i] - '0');
+            if (i == n) return v;
+        }
         char* end = nullptr;
         const long long v = strtoll(b, &end, 10);
         if (end != b + n) throw Fail{E_TYPE, "invalid literal for int()"};
@@ -172,42 +195,38 @@ struct Edit {
 struct Mapping {
     long long node;
     bool has_edit;
-    uint32_t e0, e1;     // range in Line::edits
+    uint32_t e0, e1;     // range in Parsed::edits
 };
 struct Sub {
-    uint32_t m0, m1;     // range in Line::maps
+    uint32_t m0, m1;     // range in Parsed::maps
+    uint32_t n0, n1;     // range in Parsed::nexts
     double score;
     bool has_next;
-    std::vector<int> next;
-    long long to_len;
 };
-struct Aln {            // one decoded Alignment (json2csv.py:122-134)
-    std::vector<int32_t> node;      // dense node index
-    std::vector<int32_t> alen;
-    std::vector<double> cov;
-    int32_t read_len;
-    double stats[5];
-    uint8_t bins[5];
-};
-struct Line {
+struct Parsed {          // the fields of one line that the decode needs; per thread, storage reused line after line
     const char* name; size_t name_n;
     const char* pair; size_t pair_n;
     const char* seq; size_t seq_n;
-    bool has_seq, has_subpath;
-    std::vector<int> start;
-    bool has_start;
+    bool has_seq, has_subpath, has_start;
+    std::vector<int> start, nexts;
     std::vector<Sub> subs;
     std::vector<Mapping> maps;
     std::vector<Edit> edits;
-    std::vector<Aln> alns;          // filled by decode_line
-    Fail fail{E_NONE, ""};
+    void reset() {
+        name = pair = seq = nullptr;
+        name_n = pair_n = seq_n = 0;
+        has_seq = has_subpath = has_start = false;
+        start.clear();
+        nexts.clear();
+        subs.clear();
+        maps.clear();
+        edits.clear();
+    }
 };
 
-void parse_line(const char* b, const char* e, Line& ln) {
+void parse_line(const char* b, const char* e, Parsed& ln) {
     Cur c{b, e};
-    ln.name = ln.pair = ln.seq = nullptr;
-    ln.name_n = ln.pair_n = ln.seq_n = 0;
-    ln.has_seq = ln.has_subpath = ln.has_start = false;
+    ln.reset();
     bool has_name = false;
     object(c, [&](const char* k, size_t n) {
         if (is(k, n, "name")) { str(c, ln.name, ln.name_n); has_name = true; return true; }
@@ -223,15 +242,16 @@ void parse_line(const char* b, const char* e, Line& ln) {
             array(c, [&] {
                 Sub sp;
                 sp.m0 = sp.m1 = (uint32_t)ln.maps.size();
+                sp.n0 = sp.n1 = (uint32_t)ln.nexts.size();
                 sp.score = 0.0;
                 sp.has_next = false;
-                sp.to_len = 0;
                 bool has_path = false, has_mapping = false;
                 object(c, [&](const char* k2, size_t n2) {
                     if (is(k2, n2, "score")) { ws(c); sp.score = num(c); return true; }
                     if (is(k2, n2, "next")) {
                         sp.has_next = true;
-                        array(c, [&] { sp.next.push_back((int)int_like(c)); });
+                        array(c, [&] { ln.nexts.push_back((int)int_like(c)); });
+                        sp.n1 = (uint32_t)ln.nexts.size();
                         return true;
                     }
                     if (is(k2, n2, "path")) {
@@ -284,7 +304,7 @@ void parse_line(const char* b, const char* e, Line& ln) {
                 });
                 sp.m1 = (uint32_t)ln.maps.size();
                 if (!has_path || !has_mapping) sp.m0 = sp.m1 = UINT32_MAX;   // KeyError when used
-                ln.subs.push_back(std::move(sp));
+                ln.subs.push_back(sp);
             });
             return true;
         }
@@ -297,38 +317,35 @@ struct NodeTable {
     const int64_t* ids;
     const int32_t* len;
     int64_t n;
-    std::vector<int32_t> direct;                 // id -> dense+1 when ids are small
+    struct Slot { int32_t dense1, len; };        // dense index + 1 (0: no such node) and the node's length, one cache line access
+    std::vector<Slot> direct;                    // by id when ids are small
     std::unordered_map<int64_t, int32_t> sparse;
     void build() {
         int64_t mx = -1;
         bool neg = false;
         for (int64_t i = 0; i < n; ++i) { mx = std::max(mx, ids[i]); neg |= ids[i] < 0; }
         if (!neg && mx < 8 * n + 1024) {
-            direct.assign((size_t)mx + 1, 0);
-            for (int64_t i = 0; i < n; ++i) direct[(size_t)ids[i]] = (int32_t)i + 1;
+            direct.assign((size_t)mx + 1, Slot{0, 0});
+            for (int64_t i = 0; i < n; ++i) direct[(size_t)ids[i]] = Slot{(int32_t)i + 1, len[i]};
         } else {
             sparse.reserve((size_t)n * 2);
             for (int64_t i = 0; i < n; ++i) sparse[ids[i]] = (int32_t)i;
         }
     }
-    int32_t find(long long id) const {
+    int32_t find(long long id, int32_t& node_len) const {
         if (!direct.empty()) {
-            if (id < 0 || (size_t)id >= direct.size() || direct[(size_t)id] == 0) throw Fail{E_KEY, std::to_string(id)};
-            return direct[(size_t)id] - 1;
+            if (id < 0 || (size_t)id >= direct.size() || direct[(size_t)id].dense1 == 0) throw Fail{E_KEY, std::to_string(id)};
+            node_len = direct[(size_t)id].len;
+            return direct[(size_t)id].dense1 - 1;
         }
         auto it = sparse.find(id);
         if (it == sparse.end()) throw Fail{E_KEY, std::to_string(id)};
+        node_len = len[it->second];
         return it->second;
     }
 };
 
-struct Route {
-    std::vector<int> path;
-    long long read_len;
-    double score;
-};
-
-inline long long sub_to_len(const Line& ln, int s) {
+inline long long sub_to_len(const Parsed& ln, int s) {
     if (s < 0 || (size_t)s >= ln.subs.size()) throw Fail{E_INDEX, "list index out of range"};
     const Sub& sp = ln.subs[s];
     if (sp.m0 == UINT32_MAX) throw Fail{E_KEY, "'path'"};
@@ -341,85 +358,112 @@ inline long long sub_to_len(const Line& ln, int s) {
 }
 
 // BFS (json2csv.py:589-662): FIFO relaxation keeping, per end metanode, the best-scoring routes.  The
-// reference's dict of live routes is insertion ordered; `order` + `slot` reproduce that ordering.
-void best_routes(const Line& ln, std::vector<Route>& out) {
-    if (!ln.has_start) throw Fail{E_KEY, "'start'"};
-    if (!ln.has_seq) throw Fail{E_KEY, "'sequence'"};
+// reference's dict of live routes is insertion ordered: `order` (entries in insertion order, dead ones
+// flagged) + `slot` (metanode -> live entry) reproduce that ordering.  All storage is per thread and reused.
+struct Route {
+    uint32_t p0, pn;       // metanodes of the route: range in Router::paths
+    long long read_len;
+    double score;
+};
+struct Router {
     struct Entry {
         int key;
         bool alive;
-        std::vector<Route> routes;
+        std::vector<uint32_t> routes;    // indices into `routes`
     };
     std::vector<Entry> order;
-    std::unordered_map<int, int> slot;       // key -> index in order (alive entries only)
-    std::deque<int> fifo(ln.start.begin(), ln.start.end());
-    for (int s : ln.start) {
-        Route r{{s}, sub_to_len(ln, s), ln.subs[s].score};
-        auto it = slot.find(s);
-        if (it == slot.end()) {
-            slot[s] = (int)order.size();
-            order.push_back(Entry{s, true, {r}});
-        } else {
-            order[it->second].routes = {r};
-        }
+    size_t n_order = 0;
+    std::vector<int> slot, fifo;
+    std::vector<Route> routes;
+    std::vector<int> paths;
+    std::vector<uint32_t> best;          // result: indices into `routes`
+
+    int add_entry(int key) {
+        if (n_order == order.size()) order.emplace_back();
+        Entry& en = order[n_order];
+        en.key = key;
+        en.alive = true;
+        en.routes.clear();
+        return (int)n_order++;
     }
-    const long long want = (long long)ln.seq_n;
-    while (!fifo.empty()) {
-        const int cur = fifo.front();
-        fifo.pop_front();
-        if (cur < 0 || (size_t)cur >= ln.subs.size()) throw Fail{E_INDEX, "list index out of range"};
-        const Sub& sp = ln.subs[cur];
-        if (!sp.has_next) continue;
-        auto itc = slot.find(cur);
-        if (itc == slot.end()) throw Fail{E_KEY, std::to_string(cur)};
-        bool all_done = true;
-        for (const Route& r : order[itc->second].routes) all_done &= r.read_len == want;
-        if (all_done) continue;
-        for (int child : sp.next) {
-            if (std::find(fifo.begin(), fifo.end(), child) == fifo.end()) fifo.push_back(child);
-            const long long c_len = sub_to_len(ln, child);
-            const double c_score = ln.subs[child].score;
-            auto itk = slot.find(child);
-            if (itk == slot.end()) {
-                slot[child] = (int)order.size();
-                order.push_back(Entry{child, true, {}});
-                itk = slot.find(child);
-            }
-            const int ci = itk->second;
-            const int pi = slot.find(cur)->second;
-            const size_t n_parent = order[pi].routes.size();      // child == cur would grow it while iterating
-            for (size_t q = 0; q < n_parent; ++q) {
-                Route nr = order[pi].routes[q];
-                nr.path.push_back(child);
-                nr.read_len += c_len;
-                nr.score += c_score;
-                std::vector<Route>& bucket = order[ci].routes;
-                if (bucket.empty()) bucket.push_back(std::move(nr));
-                else if (nr.score > bucket[0].score) { bucket.clear(); bucket.push_back(std::move(nr)); }
-                else if (nr.score == bucket[0].score) bucket.push_back(std::move(nr));
-            }
-        }
-        auto itp = slot.find(cur);
-        order[itp->second].alive = false;
-        order[itp->second].routes.clear();
-        slot.erase(itp);
+    uint32_t extend(uint32_t parent, int child, long long c_len, double c_score) {
+        const Route pr = routes[parent];
+        const uint32_t p0 = (uint32_t)paths.size();
+        paths.resize(p0 + pr.pn + 1);
+        std::copy(paths.begin() + pr.p0, paths.begin() + pr.p0 + pr.pn, paths.begin() + p0);
+        paths[p0 + pr.pn] = child;
+        routes.push_back(Route{p0, pr.pn + 1, pr.read_len + c_len, pr.score + c_score});
+        return (uint32_t)routes.size() - 1;
     }
-    size_t alive = 0;
-    double top = 0.0;
-    bool first = true;
-    for (const Entry& en : order)
-        if (en.alive) {
+
+    void run(const Parsed& ln) {
+        if (!ln.has_start) throw Fail{E_KEY, "'start'"};
+        if (!ln.has_seq) throw Fail{E_KEY, "'sequence'"};
+        n_order = 0;
+        routes.clear();
+        paths.clear();
+        best.clear();
+        fifo.assign(ln.start.begin(), ln.start.end());
+        slot.assign(ln.subs.size(), -1);
+        size_t head = 0;
+        for (int s : ln.start) {
+            const long long len = sub_to_len(ln, s);            // also the range check of s
+            paths.push_back(s);
+            routes.push_back(Route{(uint32_t)paths.size() - 1, 1, len, ln.subs[s].score});
+            if (slot[s] < 0) slot[s] = add_entry(s);
+            order[slot[s]].routes.assign(1, (uint32_t)routes.size() - 1);
+        }
+        const long long want = (long long)ln.seq_n;
+        while (head < fifo.size()) {
+            const int cur = fifo[head++];
+            if (cur < 0 || (size_t)cur >= ln.subs.size()) throw Fail{E_INDEX, "list index out of range"};
+            const Sub& sp = ln.subs[cur];
+            if (!sp.has_next) continue;
+            if (slot[cur] < 0) throw Fail{E_KEY, std::to_string(cur)};
+            bool all_done = true;
+            for (uint32_t r : order[slot[cur]].routes) all_done &= routes[r].read_len == want;
+            if (all_done) continue;
+            for (uint32_t ni = sp.n0; ni < sp.n1; ++ni) {
+                const int child = ln.nexts[ni];
+                if (std::find(fifo.begin() + head, fifo.end(), child) == fifo.end()) fifo.push_back(child);
+                const long long c_len = sub_to_len(ln, child);
+                const double c_score = ln.subs[child].score;
+                if (slot[child] < 0) slot[child] = add_entry(child);
+                const int ci = slot[child], pi = slot[cur];
+                const size_t n_parent = order[pi].routes.size();      // child == cur would grow it while iterating
+                for (size_t q = 0; q < n_parent && q < order[pi].routes.size(); ++q) {
+                    const uint32_t nr = extend(order[pi].routes[q], child, c_len, c_score);
+                    std::vector<uint32_t>& bucket = order[ci].routes;
+                    if (bucket.empty()) bucket.push_back(nr);
+                    else if (routes[nr].score > routes[bucket[0]].score) bucket.assign(1, nr);
+                    else if (routes[nr].score == routes[bucket[0]].score) bucket.push_back(nr);
+                }
+            }
+            Entry& done = order[slot[cur]];
+            done.alive = false;
+            done.routes.clear();
+            slot[cur] = -1;
+        }
+        size_t alive = 0;
+        double top = 0.0;
+        bool first = true;
+        for (size_t i = 0; i < n_order; ++i) {
+            const Entry& en = order[i];
+            if (!en.alive) continue;
             ++alive;
             if (en.routes.empty()) throw Fail{E_INDEX, "list index out of range"};
-            if (first || en.routes[0].score > top) top = en.routes[0].score;
+            const double sc = routes[en.routes[0]].score;
+            if (first || sc > top) top = sc;
             first = false;
         }
-    for (const Entry& en : order) {
-        if (!en.alive) continue;
-        if (alive > 1 && en.routes[0].score < top) continue;
-        for (const Route& r : en.routes) out.push_back(r);
+        for (size_t i = 0; i < n_order; ++i) {
+            const Entry& en = order[i];
+            if (!en.alive) continue;
+            if (alive > 1 && routes[en.routes[0]].score < top) continue;
+            for (uint32_t r : en.routes) best.push_back(r);
+        }
     }
-}
+};
 
 // Python round(x, 2) -> histogram key index, 255 when outside the table (json2csv.py:269-273, 335-339)
 inline uint8_t bin_of(double x) {
@@ -437,15 +481,51 @@ inline uint8_t bin_of(double x) {
     return (uint8_t)k;
 }
 
-// metaalign2align (json2csv.py:551-587)
-void route_to_aln(const Line& ln, const Route& rt, const NodeTable& nt, Aln& a) {
+// ---- per-thread results of phase A -------------------------------------------------------------------
+struct AlnOut {          // one decoded Alignment (json2csv.py:122-134); its records are [rec0, rec0 + nrec) of the arena
+    uint32_t rec0, nrec;
+    int32_t read_len;
+    double stats[5];
+    uint8_t bins[5];
+};
+struct Arena {
+    std::vector<AlnOut> alns;
+    std::vector<int32_t> node, alen;     // dense node index, aligned bases
+    std::vector<double> cov;
+    std::vector<Fail> fails;
+    std::vector<char> text;              // read names (raw JSON bytes), packed: phase B compares them without touching the file again
+    void clear() { alns.clear(); node.clear(); alen.clear(); cov.clear(); fails.clear(); text.clear(); }
+};
+struct LineOut {
+    const char* line;        // start of the line in the file
+    const char* seq;
+    uint32_t seq_n;
+    uint32_t name_off, name_n, pair_off, pair_n;     // in arena[tid].text
+    uint32_t aln0, naln;     // in arena[tid].alns
+    int32_t fail;            // index in arena[tid].fails, -1: none
+    uint16_t tid;
+    bool has_name, has_seq, has_subpath;
+};
+struct Worker {
+    Parsed parsed;
+    Router router;
+    Arena arena;
+    std::vector<uint32_t> sel, s0, s1;   // phase C: lines whose alignments the mates keep
+    std::string text;
+};
+
+// metaalign2align (json2csv.py:551-587), appended to the arena
+void route_to_aln(const Parsed& ln, const Router& rt, const Route& route, const NodeTable& nt, Arena& ar) {
+    AlnOut a;
+    a.rec0 = (uint32_t)ar.node.size();
     long long tot_al = 0, tot_match = 0, tot_indel = 0;
-    for (int meta : rt.path) {
-        const Sub& sp = ln.subs[meta];
+    for (uint32_t pi = route.p0; pi < route.p0 + route.pn; ++pi) {
+        const Sub& sp = ln.subs[rt.paths[pi]];
         for (uint32_t m = sp.m0; m < sp.m1; ++m) {
             const Mapping& mp = ln.maps[m];
             if (mp.node == -2) throw Fail{E_KEY, "'position'"};
-            const int32_t dense = nt.find(mp.node);
+            int32_t nl = 0;
+            const int32_t dense = nt.find(mp.node, nl);
             if (!mp.has_edit) throw Fail{E_KEY, "'edit'"};
             long long n_al = 0, n_match = 0;
             for (uint32_t e = mp.e0; e < mp.e1; ++e) {
@@ -456,56 +536,106 @@ void route_to_aln(const Line& ln, const Route& rt, const NodeTable& nt, Aln& a) 
             }
             tot_al += n_al;
             tot_match += n_match;
-            if (nt.len[dense] == 0) throw Fail{E_ZERODIV, "division by zero"};
-            const double frac = (double)n_al / (double)nt.len[dense];
-            if (!a.node.empty() && a.node.back() == dense && a.cov.back() < 1.0) {
-                a.cov.back() += frac;
-                a.alen.back() += (int32_t)n_al;
+            if (nl == 0) throw Fail{E_ZERODIV, "division by zero"};
+            const double frac = (double)n_al / (double)nl;
+            if (ar.node.size() > a.rec0 && ar.node.back() == dense && ar.cov.back() < 1.0) {
+                ar.cov.back() += frac;
+                ar.alen.back() += (int32_t)n_al;
             } else {
-                a.node.push_back(dense);
-                a.cov.push_back(frac);
-                a.alen.push_back((int32_t)n_al);
+                ar.node.push_back(dense);
+                ar.cov.push_back(frac);
+                ar.alen.push_back((int32_t)n_al);
             }
         }
     }
-    const double rl = (double)rt.read_len;
-    if (rt.read_len == 0 || tot_al == 0) throw Fail{E_ZERODIV, "division by zero"};
+    const double rl = (double)route.read_len;
+    if (route.read_len == 0 || tot_al == 0) throw Fail{E_ZERODIV, "division by zero"};
     const long long tot_subst = tot_al - tot_match;
-    a.read_len = (int32_t)rt.read_len;
-    a.stats[0] = rt.score / rl;
+    a.nrec = (uint32_t)ar.node.size() - a.rec0;
+    a.read_len = (int32_t)route.read_len;
+    a.stats[0] = route.score / rl;
     a.stats[1] = (double)tot_match / (double)tot_al;
     a.stats[2] = (double)tot_subst / rl;
     a.stats[3] = (double)tot_indel / rl;
     a.stats[4] = (double)(tot_indel + tot_subst) / rl;
-    for (int k = 0; k < 5; ++k) a.bins[k] = bin_of(a.stats[k]);      // here, in the parallel phase (snprintf is slow)
+    for (int k = 0; k < 5; ++k) a.bins[k] = bin_of(a.stats[k]);
+    ar.alns.push_back(a);
 }
 
-void decode_line(Line& ln, const NodeTable& nt) {
-    if (!ln.has_subpath) return;
-    std::vector<Route> routes;
-    best_routes(ln, routes);
-    ln.alns.resize(routes.size());
-    for (size_t i = 0; i < routes.size(); ++i) route_to_aln(ln, routes[i], nt, ln.alns[i]);
-    if (ln.alns.empty()) throw Fail{E_INDEX, "list index out of range"};
+void decode_line(const char* b, const char* e, Worker& w, int tid, const NodeTable& nt, LineOut& out) {
+    Arena& ar = w.arena;
+    out.line = b;
+    out.fail = -1;
+    out.tid = (uint16_t)tid;
+    out.aln0 = (uint32_t)ar.alns.size();
+    out.naln = 0;
+    const size_t rec_mark = ar.node.size();
+    try {
+        parse_line(b, e, w.parsed);
+        if (w.parsed.has_subpath) {
+            w.router.run(w.parsed);
+            for (uint32_t r : w.router.best) route_to_aln(w.parsed, w.router, w.router.routes[r], nt, ar);
+            if (w.router.best.empty()) throw Fail{E_INDEX, "list index out of range"};
+            out.naln = (uint32_t)ar.alns.size() - out.aln0;
+        }
+    } catch (const Fail& f) {
+        ar.alns.resize(out.aln0);
+        ar.node.resize(rec_mark);
+        ar.alen.resize(rec_mark);
+        ar.cov.resize(rec_mark);
+        out.naln = 0;
+        out.fail = (int32_t)ar.fails.size();
+        ar.fails.push_back(f);
+    }
+    const Parsed& p = w.parsed;
+    out.seq = p.seq;
+    out.seq_n = (uint32_t)p.seq_n;
+    out.has_name = p.name != nullptr;
+    out.name_off = (uint32_t)ar.text.size();
+    out.name_n = (uint32_t)p.name_n;
+    if (p.name_n) ar.text.insert(ar.text.end(), p.name, p.name + p.name_n);
+    out.pair_off = (uint32_t)ar.text.size();
+    out.pair_n = (uint32_t)p.pair_n;
+    if (p.pair_n) ar.text.insert(ar.text.end(), p.pair, p.pair + p.pair_n);
+    out.has_seq = p.has_seq;
+    out.has_subpath = p.has_subpath;
 }
+
+// ---- output --------------------------------------------------------------------------------------------
+template <class T>
+struct Buf {             // exact-size, uninitialised storage
+    T* p = nullptr;
+    size_t n = 0;
+    Buf() = default;
+    Buf(const Buf&) = delete;
+    Buf& operator=(const Buf&) = delete;
+    Buf(Buf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    Buf& operator=(Buf&& o) noexcept { std::swap(p, o.p); std::swap(n, o.n); return *this; }
+    ~Buf() { free(p); }
+    void alloc(size_t count) {
+        free(p);
+        n = count;
+        p = count ? (T*)malloc(count * sizeof(T)) : nullptr;
+        if (count && !p) throw Fail{E_IO, "out of memory"};
+    }
+};
+struct OutBlock {        // the decoded read groups of one block of the file; offsets are global
+    int64_t G = 0, A = 0, R = 0, NB = 0;
+    Buf<uint8_t> grp_nmates, aln_bins;
+    Buf<int64_t> grp_aln_off, aln_walk_off, name_off;     // [2G], [A], [2G]: the END offsets (the leading 0 is implicit)
+    Buf<int32_t> mate_seq_len, aln_read_len, walk_node, walk_alen;
+    Buf<double> aln_stats;
+    Buf<char> names;
+};
 
 }  // namespace
 
 struct sfb_decoded {
-    std::vector<uint8_t> grp_nmates;
-    std::vector<int64_t> grp_aln_off{0};
-    std::vector<int32_t> mate_seq_len;
-    std::vector<int64_t> aln_walk_off{0};
-    std::vector<int32_t> aln_read_len;
-    std::vector<uint8_t> aln_bins;
-    std::vector<double> aln_stats;
-    std::vector<int32_t> walk_node, walk_alen;
-    std::vector<double> walk_cov, exc_cov;
-    std::vector<int64_t> name_off{0};
-    std::string names;
+    std::vector<OutBlock> blocks;
+    std::vector<double> exc_cov;
     int err_kind = E_NONE;
     std::string err_msg;
-    int64_t n_alns = 0, n_recs = 0;          // running totals (the per-alignment / per-record arrays are filled in parallel)
+    int64_t n_groups = 0, n_alns = 0, n_recs = 0, n_name_bytes = 0;
 };
 
 namespace {
@@ -534,118 +664,185 @@ void unescape_into(std::string& out, const char* b, size_t n) {
         }
     }
 }
-
-struct MateAcc {
-    const char* name; size_t name_n;
-    const char* seq; size_t seq_n;
-    std::vector<const Aln*> alns;
-};
-
-struct EmitItem {       // one retained alignment: where its data goes
-    const Aln* a;
-    int64_t aln, rec;
-};
-
-// serial part of the output: group / mate scalars, names, offsets; the bulky arrays are filled by fill_items
-void emit_group(sfb_decoded& D, const std::vector<MateAcc>& mates, std::vector<EmitItem>& items) {
-    D.grp_nmates.push_back((uint8_t)mates.size());
-    for (int m = 0; m < 2; ++m) {
-        if ((size_t)m < mates.size()) {
-            const MateAcc& mt = mates[m];
-            D.mate_seq_len.push_back((int32_t)mt.seq_n);
-            unescape_into(D.names, mt.name, mt.name_n);
-            for (const Aln* a : mt.alns) {
-                items.push_back(EmitItem{a, D.n_alns, D.n_recs});
-                D.n_alns += 1;
-                D.n_recs += (int64_t)a->node.size();
-                D.aln_walk_off.push_back(D.n_recs);
-            }
-        } else {
-            D.mate_seq_len.push_back(0);
-        }
-        D.name_off.push_back((int64_t)D.names.size());
-        D.grp_aln_off.push_back(D.n_alns);
-    }
+// length of the unescaped name / the name itself (names without a backslash, i.e. all real ones, are copied as they are)
+inline size_t name_len(const char* b, size_t n, std::string& tmp) {
+    if (!n || !memchr(b, '\\', n)) return n;
+    tmp.clear();
+    unescape_into(tmp, b, n);
+    return tmp.size();
+}
+inline void name_put(const char* b, size_t n, std::string& tmp, char* dst) {
+    if (!n) return;
+    if (!memchr(b, '\\', n)) { memcpy(dst, b, n); return; }
+    tmp.clear();
+    unescape_into(tmp, b, n);
+    memcpy(dst, tmp.data(), tmp.size());
 }
 
-struct Exc {            // a record whose coverage has to be shipped as fp64
+struct Group {           // a read group: lines [l0, l1) of the block
+    uint32_t l0, l1;
+    uint32_t mate1_line;             // the line that opened the second mate
+    uint32_t sel_off, n_sel[2];      // kept lines per mate: worker[tid].sel[sel_off ...], mate 0 first
+    uint32_t n_aln[2], n_rec, name_bytes[2];
+    uint16_t tid;
+    uint8_t nm;
+    int64_t aln_base, rec_base, name_base;     // global offsets (phase D)
+};
+
+constexpr size_t kPiece = 256u << 10;      // bytes of the file one work item of phase A covers (at most)
+
+struct Exc {             // a record whose coverage has to be shipped as fp64
     int64_t rec;
     double cov;
 };
 
-// parallel part: alignment and record arrays (already sized), packed coverage words, exceptions per thread
-void fill_items(sfb_decoded& D, const std::vector<EmitItem>& items, size_t lo, size_t hi, const int32_t* node_len,
-                std::vector<Exc>& exc) {
-    for (size_t q = lo; q < hi; ++q) {
-        const EmitItem& it = items[q];
-        const Aln& a = *it.a;
-        D.aln_read_len[it.aln] = a.read_len;
-        for (int k = 0; k < 5; ++k) {
-            D.aln_stats[it.aln * 5 + k] = a.stats[k];
-            D.aln_bins[it.aln * 5 + k] = a.bins[k];
-        }
-        for (size_t i = 0; i < a.node.size(); ++i) {
-            const int64_t r = it.rec + (int64_t)i;
-            const int32_t al = a.alen[i], nl = node_len[a.node[i]];
-            D.walk_node[r] = a.node[i];
-            D.walk_cov[r] = a.cov[i];
-            // aligned bases | node length << 16 when that reproduces the reference's fp64, else an explicit entry
-            if (al >= 0 && al <= 0xFFFF && nl >= 1 && nl <= 0x7FFF && (double)al / (double)nl == a.cov[i]) {
-                D.walk_alen[r] = al | (nl << 16);
-            } else {
-                D.walk_alen[r] = 0;
-                exc.push_back(Exc{r, a.cov[i]});
-            }
-        }
-    }
-}
-
-// Returns the index of the first line NOT consumed: when `eof` is false the last group of the block may
-// continue in the next block, so it is left for the caller to carry over.
-size_t group_lines(sfb_decoded& D, std::vector<Line>& lines, double thr, bool eof, std::vector<EmitItem>& items) {
-    size_t i = 0;
+// Phase B (json2csv.py:667-739, the loop structure): read-group boundaries.  Throws what the reference would
+// raise first.  Returns the index of the first line NOT consumed: when `eof` is false the last group of the
+// block may continue in the next block.
+size_t find_groups(const std::vector<LineOut>& lines, const std::vector<Worker>& workers, bool eof, std::vector<Group>& groups) {
     const size_t n = lines.size();
+    auto fail_of = [&](const LineOut& ln) -> const Fail& { return workers[ln.tid].arena.fails[(size_t)ln.fail]; };
+    auto text_of = [&](const LineOut& ln, uint32_t off) { return workers[ln.tid].arena.text.data() + off; };
+    size_t i = 0;
     while (i < n) {
-        Line& first = lines[i];
-        if (first.fail.kind) throw first.fail;
+        const LineOut& first = lines[i];
+        if (first.fail >= 0) throw fail_of(first);
         if (!first.has_seq) throw Fail{E_KEY, "'sequence'"};
-        std::vector<MateAcc> mates(1);
-        mates[0] = MateAcc{first.name, first.name_n, first.seq, first.seq_n, {}};
-        if (first.has_subpath && first.alns[0].stats[0] >= thr)
-            for (const Aln& a : first.alns) mates[0].alns.push_back(&a);
+        const char* f_name = text_of(first, first.name_off);
+        const char* f_pair = text_of(first, first.pair_off);
         size_t j = i + 1;
         for (; j < n; ++j) {
-            Line& ln = lines[j];
-            if (ln.fail.kind && ln.fail.kind == E_JSON) throw ln.fail;      // json.loads comes before the name test
-            if (!ln.name && !ln.fail.kind) throw Fail{E_KEY, "'name'"};
-            if (!same(ln.name, ln.name_n, first.name, first.name_n) &&
-                !same(ln.name, ln.name_n, first.pair ? first.pair : "", first.pair_n))
-                break;
-            if (ln.fail.kind) throw ln.fail;
+            const LineOut& ln = lines[j];
+            if (ln.fail >= 0 && fail_of(ln).kind == E_JSON) throw fail_of(ln);      // json.loads comes before the name test
+            if (!ln.has_name && ln.fail < 0) throw Fail{E_KEY, "'name'"};
+            const char* l_name = text_of(ln, ln.name_off);
+            if (!same(l_name, ln.name_n, f_name, first.name_n) && !same(l_name, ln.name_n, f_pair, first.pair_n)) break;
+            if (ln.fail >= 0) throw fail_of(ln);
             if (!ln.has_subpath) continue;
             if (!ln.has_seq) throw Fail{E_KEY, "'sequence'"};
-            const bool is_first_seq = same(ln.seq, ln.seq_n, mates[0].seq, mates[0].seq_n);
-            if (!is_first_seq && mates.size() == 1) mates.push_back(MateAcc{ln.name, ln.name_n, ln.seq, ln.seq_n, {}});
-            MateAcc& tgt = is_first_seq ? mates[0] : mates[1];
-            const double best = ln.alns[0].stats[0];
-            if (tgt.alns.empty()) {
-                if (best >= thr)
-                    for (const Aln& a : ln.alns) tgt.alns.push_back(&a);
-            } else {
-                const double have = tgt.alns[0]->stats[0];
-                if (have < best) {
-                    tgt.alns.clear();
-                    for (const Aln& a : ln.alns) tgt.alns.push_back(&a);
-                } else if (have == best) {
-                    for (const Aln& a : ln.alns) tgt.alns.push_back(&a);
-                }
-            }
         }
         if (j == n && !eof) return i;
-        emit_group(D, mates, items);
+        Group g{};
+        g.l0 = (uint32_t)i;
+        g.l1 = (uint32_t)j;
+        groups.push_back(g);
         i = j;
     }
     return n;
+}
+
+// Phase C (json2csv.py:684-737): the alignments a mate keeps are those of the lines with the best score seen,
+// provided the first line seen for the mate passes the threshold ... exactly the reference's update rule.
+void select_group(Group& g, const std::vector<LineOut>& lines, std::vector<Worker>& workers, int tid, double thr) {
+    Worker& w = workers[tid];
+    auto score_of = [&](uint32_t li) { const LineOut& ln = lines[li]; return workers[ln.tid].arena.alns[ln.aln0].stats[0]; };
+    const LineOut& first = lines[g.l0];
+    std::vector<uint32_t>* sel[2] = {&w.s0, &w.s1};
+    w.s0.clear();
+    w.s1.clear();
+    if (first.has_subpath && score_of(g.l0) >= thr) w.s0.push_back(g.l0);
+    g.nm = 1;
+    g.mate1_line = g.l0;
+    for (uint32_t j = g.l0 + 1; j < g.l1; ++j) {
+        const LineOut& ln = lines[j];
+        if (!ln.has_subpath) continue;
+        const bool is_first_seq = same(ln.seq, ln.seq_n, first.seq, first.seq_n);
+        if (!is_first_seq && g.nm == 1) { g.nm = 2; g.mate1_line = j; }
+        std::vector<uint32_t>& tgt = *sel[is_first_seq ? 0 : 1];
+        const double best = score_of(j);
+        if (tgt.empty()) {
+            if (best >= thr) tgt.push_back(j);
+        } else {
+            const double have = score_of(tgt[0]);
+            if (have < best) tgt.assign(1, j);
+            else if (have == best) tgt.push_back(j);
+        }
+    }
+    g.tid = (uint16_t)tid;
+    g.sel_off = (uint32_t)w.sel.size();
+    g.n_rec = 0;
+    for (int m = 0; m < 2; ++m) {
+        g.n_sel[m] = (uint32_t)sel[m]->size();
+        g.n_aln[m] = 0;
+        for (uint32_t li : *sel[m]) {
+            const LineOut& ln = lines[li];
+            w.sel.push_back(li);
+            g.n_aln[m] += ln.naln;
+            const Arena& ar = workers[ln.tid].arena;
+            for (uint32_t a = 0; a < ln.naln; ++a) g.n_rec += ar.alns[ln.aln0 + a].nrec;
+        }
+    }
+    auto raw_name = [&](const LineOut& ln) { return workers[ln.tid].arena.text.data() + ln.name_off; };
+    g.name_bytes[0] = (uint32_t)name_len(raw_name(first), first.name_n, w.text);
+    const LineOut& second = lines[g.mate1_line];
+    g.name_bytes[1] = g.nm == 2 ? (uint32_t)name_len(raw_name(second), second.name_n, w.text) : 0u;
+}
+
+// Phase E: the group's part of the output arrays.  `gi` is the group's index inside the block; b0/r0/n0 the block's bases.
+void fill_group(const Group& g, size_t gi, OutBlock& ob, int64_t a0, int64_t r0, int64_t n0, const std::vector<LineOut>& lines,
+                std::vector<Worker>& workers, int tid, const int32_t* node_len, std::vector<Exc>& exc) {
+    Worker& me = workers[tid];
+    const uint32_t* sel = workers[g.tid].sel.data() + g.sel_off;
+    ob.grp_nmates.p[gi] = g.nm;
+    int64_t aln = g.aln_base, rec = g.rec_base, nb = g.name_base;
+    for (int m = 0; m < 2; ++m) {
+        if (m < (int)g.nm) {
+            const LineOut& src = lines[m == 0 ? g.l0 : g.mate1_line];
+            ob.mate_seq_len.p[2 * gi + m] = (int32_t)src.seq_n;
+            name_put(workers[src.tid].arena.text.data() + src.name_off, src.name_n, me.text, ob.names.p + (nb - n0));
+            nb += g.name_bytes[m];
+            for (uint32_t s = 0; s < g.n_sel[m]; ++s) {
+                const LineOut& ln = lines[*sel++];
+                const Arena& ar = workers[ln.tid].arena;
+                for (uint32_t k = 0; k < ln.naln; ++k) {
+                    const AlnOut& a = ar.alns[ln.aln0 + k];
+                    const int64_t la = aln - a0;
+                    ob.aln_read_len.p[la] = a.read_len;
+                    for (int q = 0; q < 5; ++q) {
+                        ob.aln_stats.p[la * 5 + q] = a.stats[q];
+                        ob.aln_bins.p[la * 5 + q] = a.bins[q];
+                    }
+                    for (uint32_t i = 0; i < a.nrec; ++i) {
+                        const int64_t lr = rec - r0 + i;
+                        const int32_t nd = ar.node[a.rec0 + i], al = ar.alen[a.rec0 + i], nl = node_len[nd];
+                        const double cov = ar.cov[a.rec0 + i];
+                        ob.walk_node.p[lr] = nd;
+                        // aligned bases | node length << 16 when that reproduces the reference's fp64, else an explicit entry
+                        if (al >= 0 && al <= 0xFFFF && nl >= 1 && nl <= 0x7FFF && (double)al / (double)nl == cov) {
+                            ob.walk_alen.p[lr] = al | (nl << 16);
+                        } else {
+                            ob.walk_alen.p[lr] = 0;
+                            exc.push_back(Exc{rec + i, cov});
+                        }
+                    }
+                    rec += a.nrec;
+                    ob.aln_walk_off.p[la] = rec;
+                    aln += 1;
+                }
+            }
+        } else {
+            ob.mate_seq_len.p[2 * gi + m] = 0;
+        }
+        ob.grp_aln_off.p[2 * gi + m] = aln;
+        ob.name_off.p[2 * gi + m] = nb;
+    }
+}
+
+template <class F>
+void run_parallel(int T, size_t n_items, size_t grain, F&& body) {
+    const int use = (int)std::max<size_t>(1, std::min<size_t>((size_t)T, (n_items + grain - 1) / grain));
+    std::atomic<size_t> next{0};
+    auto work = [&](int tid) {
+        for (;;) {
+            const size_t lo = next.fetch_add(grain);
+            if (lo >= n_items) return;
+            body(lo, std::min(n_items, lo + grain), tid);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < use; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
 }
 
 }  // namespace
@@ -673,15 +870,17 @@ sfb_decoded* sfb_decode_json(const char* path, const int64_t* node_ids, const in
         if (block_bytes <= 0) block_bytes = 64ll << 20;
         auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         const bool trace = getenv("SFB_DECODE_TRACE") != nullptr;
-        double t_par = 0, t_grp = 0, t_fill = 0, t0;
+        double t_a = 0, t_b = 0, t_c = 0, t_e = 0, t0;
         NodeTable nt{node_ids, node_len, n_nodes, {}, {}};
         nt.build();
-        const int T = std::max(1, n_threads);
-        std::vector<Line> carry;                 // decoded lines of a group cut by the block boundary (they point into the map)
-        std::vector<std::vector<Exc>> exc(T);
+        const int T = std::max(1, std::min(n_threads, 4096));
+        std::vector<Worker> workers((size_t)T);
+        std::vector<std::vector<Exc>> exc((size_t)T);
+        std::vector<size_t> cuts, line_base;     // a block is cut into pieces of whole lines; first line of every piece
+        std::vector<LineOut> lines;
+        std::vector<Group> groups;
         size_t pos = 0;
-        bool eof = size == 0;
-        while (!eof || !carry.empty()) {
+        while (pos < size) {
             // one block of whole lines
             size_t end = std::min(size, pos + (size_t)block_bytes);
             if (end < size) {
@@ -693,78 +892,116 @@ sfb_decoded* sfb_decode_json(const char* path, const int64_t* node_ids, const in
                 }
                 end = cut;
             }
-            eof = end >= size;
-            std::vector<std::pair<size_t, size_t>> spans;
-            for (size_t p = pos; p < end;) {
-                const void* nl = memchr(data + p, '\n', end - p);
-                const size_t q = nl ? (size_t)((const char*)nl - data) : end;
-                spans.emplace_back(p, q);
-                p = q + 1;
-            }
-            pos = end;
+            const bool eof = end >= size;
+            // A: decode the lines (count them first, so that every piece knows where its lines go)
             t0 = now();
-            std::vector<Line> lines(carry.size() + spans.size());
-            for (size_t i = 0; i < carry.size(); ++i) lines[i] = std::move(carry[i]);
-            const size_t base = carry.size();
-            carry.clear();
-            auto run_parallel = [&](size_t n_items, size_t grain, auto&& body) {
-                const int use = (int)std::max<size_t>(1, std::min<size_t>((size_t)T, n_items / grain + 1));
-                std::atomic<size_t> next{0};
-                auto work = [&](int tid) {
-                    for (;;) {
-                        const size_t lo = next.fetch_add(grain);
-                        if (lo >= n_items) return;
-                        body(lo, std::min(n_items, lo + grain), tid);
+            cuts.clear();
+            const size_t piece = std::min(kPiece, std::max<size_t>(1024, (size_t)block_bytes / 64));
+            for (size_t p = pos; p < end;) {
+                cuts.push_back(p);
+                size_t q = std::min(end, p + piece);
+                if (q < end) {
+                    const void* nl = memchr(data + q, '\n', end - q);
+                    q = nl ? (size_t)((const char*)nl - data) + 1 : end;
+                }
+                p = q;
+            }
+            const size_t n_pieces = cuts.size();
+            cuts.push_back(end);
+            line_base.assign(n_pieces + 1, 0);
+            run_parallel(T, n_pieces, 1, [&](size_t lo, size_t hi, int) {
+                for (size_t c = lo; c < hi; ++c) {
+                    size_t count = 0;
+                    for (size_t p = cuts[c]; p < cuts[c + 1]; ++count) {
+                        const void* nl = memchr(data + p, '\n', cuts[c + 1] - p);
+                        p = nl ? (size_t)((const char*)nl - data) + 1 : cuts[c + 1];
                     }
-                };
-                std::vector<std::thread> pool;
-                for (int t = 1; t < use; ++t) pool.emplace_back(work, t);
-                work(0);
-                for (auto& th : pool) th.join();
-            };
-            run_parallel(spans.size(), 256, [&](size_t lo, size_t hi, int) {
-                for (size_t i = lo; i < hi; ++i) {
-                    try {
-                        parse_line(data + spans[i].first, data + spans[i].second, lines[base + i]);
-                        decode_line(lines[base + i], nt);
-                    } catch (const Fail& f) {
-                        lines[base + i].fail = f;
+                    line_base[c + 1] = count;
+                }
+            });
+            for (size_t c = 0; c < n_pieces; ++c) line_base[c + 1] += line_base[c];
+            const size_t n_lines = line_base[n_pieces];
+            for (Worker& w : workers) { w.arena.clear(); w.sel.clear(); }
+            lines.resize(n_lines);
+            run_parallel(T, n_pieces, 1, [&](size_t lo, size_t hi, int tid) {
+                for (size_t c = lo; c < hi; ++c) {
+                    size_t i = line_base[c];
+                    for (size_t p = cuts[c]; p < cuts[c + 1]; ++i) {
+                        const void* nl = memchr(data + p, '\n', cuts[c + 1] - p);
+                        const size_t q = nl ? (size_t)((const char*)nl - data) : cuts[c + 1];
+                        decode_line(data + p, data + q, workers[(size_t)tid], tid, nt, lines[i]);
+                        p = q + 1;
                     }
                 }
             });
-            t_par += now() - t0;
+            t_a += now() - t0;
+            // B: groups
             t0 = now();
-            std::vector<EmitItem> items;
-            const size_t used = group_lines(*D, lines, thr, eof, items);
-            t_grp += now() - t0;
+            groups.clear();
+            const size_t used = find_groups(lines, workers, eof, groups);
+            t_b += now() - t0;
+            if (used == 0 && !eof) {               // one read group larger than the block: widen the block
+                block_bytes *= 2;
+                continue;
+            }
+            // C: what every mate keeps
             t0 = now();
-            D->aln_read_len.resize((size_t)D->n_alns);
-            D->aln_stats.resize((size_t)D->n_alns * 5);
-            D->aln_bins.resize((size_t)D->n_alns * 5);
-            D->walk_node.resize((size_t)D->n_recs);
-            D->walk_alen.resize((size_t)D->n_recs);
-            D->walk_cov.resize((size_t)D->n_recs);
-            run_parallel(items.size(), 512, [&](size_t lo, size_t hi, int tid) { fill_items(*D, items, lo, hi, node_len, exc[tid]); });
-            for (size_t i = used; i < lines.size(); ++i) carry.push_back(std::move(lines[i]));
-            if (eof && used == lines.size()) carry.clear();
-            // release the per-line heap blocks from the worker threads (millions of frees, otherwise serial)
-            run_parallel(lines.size(), 1024, [&](size_t lo, size_t hi, int) {
-                for (size_t i = lo; i < hi; ++i) { Line dead; std::swap(dead, lines[i]); }
+            run_parallel(T, groups.size(), 512, [&](size_t lo, size_t hi, int tid) {
+                for (size_t g = lo; g < hi; ++g) select_group(groups[g], lines, workers, tid, thr);
             });
-            t_fill += now() - t0;
-            if (eof && carry.empty()) break;
-            if (eof && !carry.empty() && spans.empty()) throw Fail{E_IO, "internal: unconsumed lines at end of file"};
-        }
-        // explicit coverages in record order (deterministic whatever the thread count)
-        std::vector<Exc> all;
-        for (auto& v : exc) all.insert(all.end(), v.begin(), v.end());
-        std::sort(all.begin(), all.end(), [](const Exc& x, const Exc& y) { return x.rec < y.rec; });
-        for (const Exc& e : all) {
-            D->exc_cov.push_back(e.cov);
-            D->walk_alen[(size_t)e.rec] = -(int32_t)D->exc_cov.size();
+            // D: offsets
+            OutBlock ob;
+            ob.G = (int64_t)groups.size();
+            int64_t aln = D->n_alns, rec = D->n_recs, nb = D->n_name_bytes;
+            for (Group& g : groups) {
+                g.aln_base = aln;
+                g.rec_base = rec;
+                g.name_base = nb;
+                aln += g.n_aln[0] + g.n_aln[1];
+                rec += g.n_rec;
+                nb += g.name_bytes[0] + g.name_bytes[1];
+            }
+            ob.A = aln - D->n_alns;
+            ob.R = rec - D->n_recs;
+            ob.NB = nb - D->n_name_bytes;
+            t_c += now() - t0;
+            // E: fill
+            t0 = now();
+            ob.grp_nmates.alloc((size_t)ob.G);
+            ob.grp_aln_off.alloc((size_t)ob.G * 2);
+            ob.name_off.alloc((size_t)ob.G * 2);
+            ob.mate_seq_len.alloc((size_t)ob.G * 2);
+            ob.aln_walk_off.alloc((size_t)ob.A);
+            ob.aln_read_len.alloc((size_t)ob.A);
+            ob.aln_bins.alloc((size_t)ob.A * 5);
+            ob.aln_stats.alloc((size_t)ob.A * 5);
+            ob.walk_node.alloc((size_t)ob.R);
+            ob.walk_alen.alloc((size_t)ob.R);
+            ob.names.alloc((size_t)ob.NB);
+            const int64_t a0 = D->n_alns, r0 = D->n_recs, n0 = D->n_name_bytes;
+            run_parallel(T, groups.size(), 512, [&](size_t lo, size_t hi, int tid) {
+                for (size_t g = lo; g < hi; ++g)
+                    fill_group(groups[g], g, ob, a0, r0, n0, lines, workers, tid, node_len, exc[(size_t)tid]);
+            });
+            // explicit coverages in record order (deterministic whatever the thread count)
+            std::vector<Exc> all;
+            for (auto& v : exc) { all.insert(all.end(), v.begin(), v.end()); v.clear(); }
+            std::sort(all.begin(), all.end(), [](const Exc& x, const Exc& y) { return x.rec < y.rec; });
+            for (const Exc& e : all) {
+                D->exc_cov.push_back(e.cov);
+                ob.walk_alen.p[(size_t)(e.rec - r0)] = -(int32_t)D->exc_cov.size();
+            }
+            D->n_groups += ob.G;
+            D->n_alns = aln;
+            D->n_recs = rec;
+            D->n_name_bytes = nb;
+            D->blocks.push_back(std::move(ob));
+            t_e += now() - t0;
+            pos = used < n_lines ? (size_t)(lines[used].line - data) : end;
         }
         if (trace)
-            fprintf(stderr, "[decode] parse+route (parallel) %.3f s, group %.3f s, fill (parallel) %.3f s\n", t_par, t_grp, t_fill);
+            fprintf(stderr, "[decode] A lines (parallel) %.3f s, B groups %.3f s, C+D select (parallel) %.3f s, E fill (parallel) %.3f s, %zu blocks\n",
+                    t_a, t_b, t_c, t_e, D->blocks.size());
     } catch (const Fail& f) {
         D->err_kind = f.kind;
         D->err_msg = f.msg;
@@ -784,37 +1021,50 @@ int sfb_decoded_error(const sfb_decoded* D, const char** msg) {
 
 int64_t sfb_decoded_size(const sfb_decoded* D, int which) {
     switch (which) {
-        case 0: return (int64_t)D->grp_nmates.size();
-        case 1: return (int64_t)D->aln_read_len.size();
-        case 2: return (int64_t)D->walk_node.size();
+        case 0: return D->n_groups;
+        case 1: return D->n_alns;
+        case 2: return D->n_recs;
         case 3: return (int64_t)D->exc_cov.size();
-        case 4: return (int64_t)D->names.size();
+        case 4: return D->n_name_bytes;
         default: return -1;
     }
 }
 
 // which: 0 grp_nmates u8[G], 1 grp_aln_off i64[2G+1], 2 mate_seq_len i32[2G], 3 aln_walk_off i64[A+1],
 // 4 aln_read_len i32[A], 5 aln_bins u8[5A], 6 aln_stats f64[5A], 7 walk_node i32[R], 8 walk_alen i32[R],
-// 9 walk_cov f64[R], 10 exc_cov f64[E], 11 name_off i64[2G+1], 12 names bytes
+// 9 walk_cov f64[R] (rebuilt from 8 and 10), 10 exc_cov f64[E], 11 name_off i64[2G+1], 12 names bytes
 int sfb_decoded_copy(const sfb_decoded* D, int which, void* dst) {
-#define SFB_CP(v) memcpy(dst, (v).data(), (v).size() * sizeof((v)[0])); return 0
-    switch (which) {
-        case 0: SFB_CP(D->grp_nmates);
-        case 1: SFB_CP(D->grp_aln_off);
-        case 2: SFB_CP(D->mate_seq_len);
-        case 3: SFB_CP(D->aln_walk_off);
-        case 4: SFB_CP(D->aln_read_len);
-        case 5: SFB_CP(D->aln_bins);
-        case 6: SFB_CP(D->aln_stats);
-        case 7: SFB_CP(D->walk_node);
-        case 8: SFB_CP(D->walk_alen);
-        case 9: SFB_CP(D->walk_cov);
-        case 10: SFB_CP(D->exc_cov);
-        case 11: SFB_CP(D->name_off);
-        case 12: memcpy(dst, D->names.data(), D->names.size()); return 0;
-        default: return -1;
+    char* out = (char*)dst;
+    auto lead0 = [&] { const int64_t z = 0; memcpy(out, &z, sizeof z); out += sizeof z; };
+    auto put = [&](const void* p, size_t bytes) { if (bytes) memcpy(out, p, bytes); out += bytes; };
+    if (which == 1 || which == 3 || which == 11) lead0();
+    if (which == 10) { put(D->exc_cov.data(), D->exc_cov.size() * sizeof(double)); return 0; }
+    if (which < 0 || which > 12) return -1;
+    for (const OutBlock& b : D->blocks) {
+        switch (which) {
+            case 0: put(b.grp_nmates.p, b.grp_nmates.n); break;
+            case 1: put(b.grp_aln_off.p, b.grp_aln_off.n * 8); break;
+            case 2: put(b.mate_seq_len.p, b.mate_seq_len.n * 4); break;
+            case 3: put(b.aln_walk_off.p, b.aln_walk_off.n * 8); break;
+            case 4: put(b.aln_read_len.p, b.aln_read_len.n * 4); break;
+            case 5: put(b.aln_bins.p, b.aln_bins.n); break;
+            case 6: put(b.aln_stats.p, b.aln_stats.n * 8); break;
+            case 7: put(b.walk_node.p, b.walk_node.n * 4); break;
+            case 8: put(b.walk_alen.p, b.walk_alen.n * 4); break;
+            case 9: {
+                double* o = (double*)out;
+                for (size_t i = 0; i < b.walk_alen.n; ++i) {
+                    const int32_t v = b.walk_alen.p[i];
+                    o[i] = v < 0 ? D->exc_cov[(size_t)(-(int64_t)v - 1)] : (double)(v & 0xFFFF) / (double)(v >> 16);
+                }
+                out += b.walk_alen.n * 8;
+                break;
+            }
+            case 11: put(b.name_off.p, b.name_off.n * 8); break;
+            case 12: put(b.names.p, b.names.n); break;
+        }
     }
-#undef SFB_CP
+    return 0;
 }
 
 void sfb_decoded_free(sfb_decoded* D) { delete D; }
