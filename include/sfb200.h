@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SFB_ABI_VERSION 6
+#define SFB_ABI_VERSION 7
 
 /* ---- status codes ---------------------------------------------------- */
 #define SFB_OK            0
@@ -131,21 +131,27 @@ typedef struct sfb_reads {
 } sfb_reads;
 
 /* ---- compact transfer layout of a read shard ------------------------------
- * What the host copies to the device for the end-to-end path: counts instead of offsets, 16-bit read lengths,
- * 16-bit aligned bases per record (0xffff where the coverage is explicit: record exc_idx[k] gets exc_cov[k]).
- * Usable when no mate has more than 255 retained alignments, no walk more than 255 nodes, no read more than
- * 65535 bases.  sfb_expand_reads turns it into the arrays of sfb_reads on the device. */
+ * What the host copies to the device for the end-to-end path (PCIe is its bound): counts instead of offsets, 16-bit
+ * read lengths; per alignment the first node of the walk, per record two bytes: the step to the next node id as a
+ * signed byte (walks follow the graph, whose ids are locally consecutive; -128 = the id is in the wide list) and the
+ * aligned bases as one byte (255 = the coverage is explicit: record exc_idx[k] gets exc_cov[k]; any record may be
+ * shipped that way).  Usable when no mate has more than 255 retained alignments, no walk more than 255 nodes, no
+ * read more than 65535 bases.  sfb_expand_reads turns it into the arrays of sfb_reads on the device. */
 typedef struct sfb_wire {
-    int64_t n_groups, n_alns, n_records, n_exc;
+    int64_t n_groups, n_alns, n_records, n_exc, n_wide;
     const uint8_t*  grp_nmates;   /* [G]  */
     const uint8_t*  mate_naln;    /* [2G] retained alignments per mate slot           */
     const uint16_t* mate_seq_len; /* [2G] */
     const uint8_t*  aln_len;      /* [A]  nodes per walk                              */
     const uint8_t*  aln_bins;     /* [5A] */
-    const int32_t*  walk_node;    /* [R]  */
-    const uint16_t* walk_al;      /* [R]  aligned bases, 0xffff = explicit coverage   */
-    const int64_t*  exc_idx;      /* [E]  record index of explicit coverage k         */
+    const int32_t*  aln_node0;    /* [A]  first node of the walk                      */
+    const int8_t*   walk_step;    /* [R]  node id minus the previous node id of the walk (unused for a walk's first
+                                          record); -128: the id is wide_node[k] where wide_idx[k] is this record  */
+    const uint8_t*  walk_al;      /* [R]  aligned bases, 255 = explicit coverage      */
+    const int64_t*  exc_idx;      /* [E]  record index of explicit coverage k, ascending */
     const double*   exc_cov;      /* [E]  */
+    const int64_t*  wide_idx;     /* [W]  record indices of the wide steps, ascending */
+    const int32_t*  wide_node;    /* [W]  */
 } sfb_wire;
 
 /* ---- per-shard work arrays (outputs of match / classify) ----------------- */
@@ -195,10 +201,11 @@ const char* sfb_version(void);
 const char* sfb_last_error(void);
 
 /* Device-side expansion of the transfer layout: grp_aln_off[2G+1] and aln_walk_off[A+1] by prefix sums of the
- * counts, mate_seq_len[2G] widened, walk_alen[R] = aligned | node_len[walk_node] << 16 (or -(k+1)).
- * node_len: int32[n_nodes] on the device.  scratch: int64[max(2G, A)/4096 + 2]. */
+ * counts, mate_seq_len[2G] widened, walk_node[R] by summing the steps along every walk, walk_alen[R] = aligned |
+ * node_len[walk_node] << 16 (or -(k+1)).  node_len: int32[n_nodes] on the device.
+ * scratch: int64[max(2G, A)/4096 + 2]. */
 int sfb_expand_reads(const sfb_wire* w, const int32_t* node_len, int64_t* grp_aln_off, int32_t* mate_seq_len,
-                     int64_t* aln_walk_off, int32_t* walk_alen, int64_t* scratch, void* stream);
+                     int64_t* aln_walk_off, int32_t* walk_node, int32_t* walk_alen, int64_t* scratch, void* stream);
 
 /* Pangenome.get_matching_path on the walk and, if longer than one node, on the reversed
  * walk (json2csv.py:341-363 with callers :855-866, :1024-1026, :1103-1114, :1231-1233). */

@@ -1,8 +1,10 @@
 // sfb_expand_reads: compact transfer ("wire") layout of a read shard -> the arrays the kernels consume.
 //
 // The end-to-end path is bound by the host->device copy (PCIe, ~55 GB/s): CSR offsets travel as 1-byte counts and
-// become int64 offsets by a device prefix sum; read lengths travel as 16 bits; per record only the aligned bases
-// travel (16 bits) and the node length is gathered from the graph on the device.  3.7 GB -> 2.3 GB per C3 shard.
+// become int64 offsets by a device prefix sum; read lengths travel as 16 bits; per record two bytes travel: the step
+// from the previous node id of the walk (walks follow the graph, ids are locally consecutive) and the aligned bases;
+// node ids are rebuilt by summing the steps along every walk and the node length is gathered from the graph on the
+// device.  3.7 GB -> 1.4 GB per C3 shard.
 #include "common.cuh"
 
 namespace sfb {
@@ -80,10 +82,33 @@ __global__ void __launch_bounds__(kScanBlock) k_scan_write(const uint8_t* cnt, i
 __global__ void k_expand_seq_len(const uint16_t* in, i64 n, int32_t* out) {
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) out[i] = in[i];
 }
-// packed coverage word of every record: aligned bases | node length << 16 (see record_cov)
-__global__ void k_expand_walk(const uint16_t* al, const int32_t* node, const int32_t* node_len, i64 n, int32_t* out) {
-    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
-        out[i] = (int32_t)al[i] | (node_len[node[i]] << 16);
+// Node ids and packed coverage words (aligned bases | node length << 16, see record_cov) of every record.
+// One thread per walk: a walk is a handful of records, the threads of a warp cover one contiguous stretch.
+__global__ void __launch_bounds__(256) k_expand_walks(sfb_wire w, const i64* __restrict__ walk_off,
+                                                      const int32_t* __restrict__ node_len, int32_t* __restrict__ walk_node,
+                                                      int32_t* __restrict__ walk_alen) {
+    for (i64 a = (i64)blockIdx.x * blockDim.x + threadIdx.x; a < w.n_alns; a += (i64)gridDim.x * blockDim.x) {
+        const i64 lo = walk_off[a], hi = walk_off[a + 1];
+        int32_t node = w.aln_node0[a];
+        for (i64 r = lo; r < hi; ++r) {
+            if (r > lo) {
+                const int step = w.walk_step[r];
+                if (step != -128) {
+                    node += step;
+                } else {                         // wide step: binary search of the record in the (short) list
+                    i64 x = 0, y = w.n_wide;
+                    while (x < y) {
+                        const i64 mid = (x + y) >> 1;
+                        if (w.wide_idx[mid] < r) x = mid + 1;
+                        else y = mid;
+                    }
+                    node = w.wide_node[x];
+                }
+            }
+            walk_node[r] = node;
+            walk_alen[r] = (int32_t)w.walk_al[r] | (node_len[node] << 16);       // 255: replaced by k_apply_exceptions
+        }
+    }
 }
 __global__ void k_apply_exceptions(const i64* exc_idx, i64 n_exc, int32_t* walk_alen) {
     for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < n_exc; k += (i64)gridDim.x * blockDim.x)
@@ -103,11 +128,11 @@ static int scan_u8(const uint8_t* cnt, i64 n, i64* off, i64* scratch, cudaStream
 }
 
 int launch_expand(const sfb_wire* w, const int32_t* node_len, i64* grp_aln_off, int32_t* mate_seq_len, i64* aln_walk_off,
-                  int32_t* walk_alen, i64* scratch, cudaStream_t st) {
+                  int32_t* walk_node, int32_t* walk_alen, i64* scratch, cudaStream_t st) {
     SFB_TRY(scan_u8(w->mate_naln, 2 * w->n_groups, grp_aln_off, scratch, st));
     SFB_TRY(scan_u8(w->aln_len, w->n_alns, aln_walk_off, scratch, st));
     if (w->n_groups) k_expand_seq_len<<<kSMs * 4, 256, 0, st>>>(w->mate_seq_len, 2 * w->n_groups, mate_seq_len);
-    if (w->n_records) k_expand_walk<<<kSMs * 8, 256, 0, st>>>(w->walk_al, w->walk_node, node_len, w->n_records, walk_alen);
+    if (w->n_records) k_expand_walks<<<kSMs * 8, 256, 0, st>>>(*w, aln_walk_off, node_len, walk_node, walk_alen);
     if (w->n_exc) k_apply_exceptions<<<blocks_for(w->n_exc, 256), 256, 0, st>>>((const i64*)w->exc_idx, w->n_exc, walk_alen);
     return check_launch("expand_reads");
 }

@@ -102,22 +102,45 @@ WIRE_FIELDS = ("grp_nmates", "mate_naln", "mate_seq_len", "aln_len", "aln_bins",
 
 def wire_arrays(reads: Reads):
     """Compact transfer layout (include/sfb200.h, sfb_wire) of a read shard, or None when it does not apply
-    (a mate with > 255 alignments, a walk of > 255 nodes, a read of > 65535 bases)."""
+    (a mate with > 255 alignments, a walk of > 255 nodes, a read of > 65535 bases, or so many records needing an
+    explicit coverage / a wide node step that the plain layout is smaller)."""
     naln = np.diff(reads.grp_aln_off)
     alen = np.diff(reads.aln_walk_off)
     if (naln.size and naln.max() > 255) or (alen.size and alen.max() > 255) or \
             (reads.mate_seq_len.size and reads.mate_seq_len.max() > 0xFFFF):
         return None
+    R = reads.n_records
     v = reads.walk_alen
-    neg = np.flatnonzero(v < 0)
-    al = (v & 0xFFFF).astype(np.uint16)
-    al[neg] = 0xFFFF
-    exc_idx = np.zeros(len(reads.exc_cov), np.int64)
-    exc_idx[-v[neg].astype(np.int64) - 1] = neg
+    # aligned bases in one byte; 255 = explicit coverage: the records that already have one, and those whose aligned
+    # length does not fit (their fp64 coverage is the same ratio, computed here as the device would)
+    low = v & 0xFFFF
+    big = np.flatnonzero((v >= 0) & (low >= 255))
+    old = np.flatnonzero(v < 0)
+    al = low.astype(np.uint8)
+    exc_idx = np.concatenate([old, big])
+    exc_cov = np.concatenate([reads.exc_cov[-v[old].astype(np.int64) - 1],
+                              low[big].astype(np.float64) / (v[big] >> 16).astype(np.float64)])
+    order = np.argsort(exc_idx, kind="stable")
+    exc_idx, exc_cov = exc_idx[order].astype(np.int64), exc_cov[order]
+    al[exc_idx] = 255
+    # node ids as steps along the walk
+    node = reads.walk_node
+    start = reads.aln_walk_off[:-1][alen > 0]
+    step = np.zeros(R, np.int64)
+    if R:
+        step[1:] = node[1:].astype(np.int64) - node[:-1]
+        step[start] = 0
+    wide_idx = np.flatnonzero((step < -127) | (step > 127))
+    step[wide_idx] = -128
+    if 16 * len(exc_idx) + 12 * len(wide_idx) > 2 * R:
+        return None
+    node0 = np.zeros(reads.n_alns, np.int32)
+    node0[alen > 0] = node[start]
     return dict(grp_nmates=reads.grp_nmates, mate_naln=naln.astype(np.uint8),
                 mate_seq_len=reads.mate_seq_len.astype(np.uint16), aln_len=alen.astype(np.uint8),
-                aln_bins=reads.aln_bins.reshape(-1), walk_node=reads.walk_node, walk_al=al, exc_idx=exc_idx,
-                exc_cov=reads.exc_cov)
+                aln_bins=reads.aln_bins.reshape(-1), aln_node0=node0, walk_step=step.astype(np.int8), walk_al=al,
+                exc_idx=exc_idx, exc_cov=exc_cov, wide_idx=wide_idx.astype(np.int64),
+                wide_node=node[wide_idx].astype(np.int32))
 
 
 def _layout(arrays):
@@ -149,7 +172,8 @@ class HostReads:
             if n:
                 view[o:o + n] = np.ascontiguousarray(arrays[k]).reshape(-1).view(np.uint8)
         self.n_groups, self.n_alns, self.n_records = reads.n_groups, reads.n_alns, reads.n_records
-        self.n_exc = len(reads.exc_cov)
+        self.n_exc = len(arrays["exc_cov"])
+        self.n_wide = len(arrays["wide_idx"]) if self.wire else 0
 
     def nbytes(self):
         return sum(n for _, n in self.offs.values())
@@ -183,23 +207,25 @@ class DeviceReads:
             self.c = _lib.SfbReads(n_groups=G, n_alns=A, n_records=R, n_exc=E, **ptr)
             return
         # expanded arrays (one device allocation, reused across steps)
-        need = 8 * (2 * G + 1) + 4 * 2 * G + 8 * (A + 1) + 4 * R + 8 * (max(2 * G, A) // 4096 + 2) + 5 * 256
+        need = 8 * (2 * G + 1) + 4 * 2 * G + 8 * (A + 1) + 8 * R + 8 * (max(2 * G, A) // 4096 + 2) + 6 * 256
         if wide is None or wide.numel() < need:
             wide = torch.empty(need, dtype=torch.uint8, device=device)
         self.wide = wide
         p, out = wide.data_ptr(), {}
         for k, n in (("grp_aln_off", 8 * (2 * G + 1)), ("aln_walk_off", 8 * (A + 1)), ("scratch", 8 * (max(2 * G, A) // 4096 + 2)),
-                     ("mate_seq_len", 8 * G), ("walk_alen", 4 * R)):
+                     ("mate_seq_len", 8 * G), ("walk_node", 4 * R), ("walk_alen", 4 * R)):
             out[k] = p
             p += (n + 255) & ~255
-        w = _lib.SfbWire(n_groups=G, n_alns=A, n_records=R, n_exc=E, **ptr)
+        w = _lib.SfbWire(n_groups=G, n_alns=A, n_records=R, n_exc=E, n_wide=host.n_wide, **ptr)
         _lib.check(_lib.load().sfb_expand_reads(C.byref(w), C.c_void_p(node_len.data_ptr()), C.c_void_p(out["grp_aln_off"]),
                                                 C.c_void_p(out["mate_seq_len"]), C.c_void_p(out["aln_walk_off"]),
-                                                C.c_void_p(out["walk_alen"]), C.c_void_p(out["scratch"]), _stream()))
+                                                C.c_void_p(out["walk_node"]), C.c_void_p(out["walk_alen"]),
+                                                C.c_void_p(out["scratch"]), _stream()))
         self.c = _lib.SfbReads(n_groups=G, n_alns=A, n_records=R, n_exc=E, grp_nmates=ptr["grp_nmates"],
                                grp_aln_off=out["grp_aln_off"], mate_seq_len=out["mate_seq_len"] if G else 0,
-                               aln_walk_off=out["aln_walk_off"], aln_bins=ptr["aln_bins"], walk_node=ptr["walk_node"],
-                               walk_alen=out["walk_alen"] if R else 0, exc_cov=ptr["exc_cov"])
+                               aln_walk_off=out["aln_walk_off"], aln_bins=ptr["aln_bins"],
+                               walk_node=out["walk_node"] if R else 0, walk_alen=out["walk_alen"] if R else 0,
+                               exc_cov=ptr["exc_cov"])
 
 
 class Work:

@@ -209,30 +209,59 @@ def test_error_quirks_raise_like_reference():
         oa.AbundanceOracle(g3.as_dict(), r3.as_dict()).run()
 
 
-def test_transfer_layout_expands_to_the_same_arrays():
-    """sfb_expand_reads(wire(reads)) == the wide arrays, bit for bit (offset scans across tile boundaries,
-    explicit coverages, widened lengths)."""
+@pytest.mark.parametrize("shuffle_ids", [False, True])
+def test_transfer_layout_expands_to_the_same_arrays(shuffle_ids):
+    """sfb_expand_reads(wire(reads)) == the wide arrays, bit for bit (offset scans across tile boundaries, node ids
+    from steps incl. wide ones, explicit coverages, widened lengths)."""
     need_gpu()
     gkw, _ = synth.CONFIGS["small"]
     graph = synth.make_graph(3, **gkw)
     reads = synth.make_reads(graph, 4, n_pairs=30_000, read_len=150, p_exc=0.01)
+    if shuffle_ids:
+        # long nodes (aligned lengths that do not fit a byte) and a sprinkle of far-away node ids (wide steps);
+        # the walks no longer follow the graph, which the expansion does not care about
+        rng = np.random.default_rng(5)
+        graph.node_len[:] = np.minimum(graph.node_len.astype(np.int64) * 40, 0x7FFF)
+        hit = rng.random(reads.n_records) < 0.03
+        reads.walk_node[hit] = rng.integers(0, graph.n_nodes, int(hit.sum()))
+        keep = reads.walk_alen >= 0
+        al = np.where(rng.random(reads.n_records) < 0.03, rng.integers(255, 600, reads.n_records),
+                      rng.integers(0, 255, reads.n_records))
+        reads.walk_alen[keep] = (al | (graph.node_len[reads.walk_node].astype(np.int64) << 16))[keep].astype(np.int32)
     eng = engine.AbundanceEngine(graph)
     host = engine.HostReads(reads, wire=True)
-    assert host.wire and host.nbytes() < 0.7 * engine.HostReads(reads, wire=False).nbytes()
+    assert host.wire and host.nbytes() < (0.7 if shuffle_ids else 0.45) * engine.HostReads(reads, wire=False).nbytes()
+    assert (host.n_wide > 0) == shuffle_ids and host.n_exc > len(reads.exc_cov) * shuffle_ids
     dr = eng.upload(host)
     torch.cuda.synchronize()
 
     # read the expanded arrays back through the pointers of the sfb_reads struct
     def view(ptr, n, dt):
         nbytes = n * torch.empty(0, dtype=dt).element_size()
-        off = ptr - dr.wide.data_ptr()
-        return dr.wide[off:off + nbytes].view(dt).cpu().numpy()
+        buf = dr.wide if dr.wide.data_ptr() <= ptr < dr.wide.data_ptr() + dr.wide.numel() else dr.arena
+        off = ptr - buf.data_ptr()
+        return buf[off:off + nbytes].view(dt).cpu().numpy()
 
     G, A, R = reads.n_groups, reads.n_alns, reads.n_records
     assert np.array_equal(view(dr.c.grp_aln_off, 2 * G + 1, torch.int64), reads.grp_aln_off)
     assert np.array_equal(view(dr.c.aln_walk_off, A + 1, torch.int64), reads.aln_walk_off)
     assert np.array_equal(view(dr.c.mate_seq_len, 2 * G, torch.int32), reads.mate_seq_len)
-    assert np.array_equal(view(dr.c.walk_alen, R, torch.int32), reads.walk_alen)
+    assert np.array_equal(view(dr.c.walk_node, R, torch.int32), reads.walk_node)
+
+    def coverage(word, exc):
+        word = word.astype(np.int64)
+        neg = word < 0
+        cov = np.where(neg, 0, word & 0xFFFF) / np.where(neg, 1, word >> 16)
+        cov[neg] = exc[-word[neg] - 1]
+        return cov
+
+    exc_dev = view(dr.c.exc_cov, host.n_exc, torch.float64) if host.n_exc else np.zeros(0)
+    got = view(dr.c.walk_alen, R, torch.int32)
+    assert np.array_equal(coverage(got, exc_dev), coverage(reads.walk_alen, reads.exc_cov))
+    fits = (reads.walk_alen >= 0) & ((reads.walk_alen & 0xFFFF) < 255)
+    assert np.array_equal(got[fits], reads.walk_alen[fits])
+    if shuffle_ids:
+        return
     # and the pass gives the same result from either layout
     a = eng.run(engine.HostReads(reads, wire=True))
     b = eng.run(engine.HostReads(reads, wire=False))

@@ -185,3 +185,36 @@ def test_gfa_corner_cases_match_oracle(tmp_path):
     p = tmp_path / "g.gfa"
     p.write_text(text)
     same_graph(gfa.load_graph(str(p)), og.load_graph(str(p)))
+
+
+def test_transfer_layout_round_trip_on_host():
+    """engine.wire_arrays holds everything needed to rebuild the shard (what sfb_expand_reads does on the device)."""
+    from strainflair_b200 import engine, synth
+    gkw, _ = synth.CONFIGS["tiny"]
+    graph = synth.make_graph(11, **gkw)
+    reads = synth.make_reads(graph, 12, n_pairs=3000, read_len=150, p_exc=0.02)
+    rng = np.random.default_rng(1)
+    hit = rng.random(reads.n_records) < 0.05
+    reads.walk_node[hit] = rng.integers(0, graph.n_nodes, int(hit.sum()))          # far-away ids: wide steps
+    w = engine.wire_arrays(reads)
+    assert len(w["wide_idx"]) > 0 and w["walk_step"].dtype == np.int8 and w["walk_al"].dtype == np.uint8
+    assert np.array_equal(np.concatenate([[0], np.cumsum(w["mate_naln"], dtype=np.int64)]), reads.grp_aln_off)
+    off = np.concatenate([[0], np.cumsum(w["aln_len"], dtype=np.int64)])
+    assert np.array_equal(off, reads.aln_walk_off)
+    node = np.empty(reads.n_records, np.int64)
+    wide = dict(zip(w["wide_idx"].tolist(), w["wide_node"].tolist()))
+    for a in range(reads.n_alns):
+        cur = int(w["aln_node0"][a])
+        for r in range(off[a], off[a + 1]):
+            if r > off[a]:
+                cur = wide[r] if w["walk_step"][r] == -128 else cur + int(w["walk_step"][r])
+            node[r] = cur
+    assert np.array_equal(node, reads.walk_node)
+    assert np.all(np.diff(w["exc_idx"]) > 0) and np.all(w["walk_al"][w["exc_idx"]] == 255)
+    plain = np.setdiff1d(np.arange(reads.n_records), w["exc_idx"])
+    assert np.array_equal(w["walk_al"][plain], (reads.walk_alen[plain] & 0xFFFF))
+    old = reads.walk_alen[w["exc_idx"]]
+    assert np.array_equal(w["exc_cov"][old < 0], reads.exc_cov[-old[old < 0].astype(np.int64) - 1])
+    # a shard whose exceptions would outweigh the saving falls back to the plain layout
+    reads.walk_node[:] = rng.integers(0, graph.n_nodes, reads.n_records)
+    assert engine.wire_arrays(reads) is None
