@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SFB_ABI_VERSION 7
+#define SFB_ABI_VERSION 8
 
 /* ---- status codes ---------------------------------------------------- */
 #define SFB_OK            0
@@ -131,23 +131,36 @@ typedef struct sfb_reads {
 } sfb_reads;
 
 /* ---- compact transfer layout of a read shard ------------------------------
- * What the host copies to the device for the end-to-end path (PCIe is its bound): counts instead of offsets, 16-bit
- * read lengths; per alignment the first node of the walk, per record two bytes: the step to the next node id as a
- * signed byte (walks follow the graph, whose ids are locally consecutive; -128 = the id is in the wide list) and the
- * aligned bases as one byte (255 = the coverage is explicit: record exc_idx[k] gets exc_cov[k]; any record may be
- * shipped that way).  Usable when no mate has more than 255 retained alignments, no walk more than 255 nodes, no
- * read more than 65535 bases.  sfb_expand_reads turns it into the arrays of sfb_reads on the device. */
+ * What the host copies to the device for the end-to-end path (PCIe is its bound).  Everything travels in the
+ * smallest form that the common case allows, with a short list of exceptions beside it:
+ *   offsets            as 1-byte counts (prefix sums on the device)
+ *   read lengths       one common value + the mates that differ (or 16 bits per mate)
+ *   histogram bins     one byte per alignment: index into a dictionary of the shard's frequent 5-tuples
+ *   node ids           per alignment the first node; per record the step to the next id as a signed byte (walks
+ *                      follow the graph, whose ids are locally consecutive)
+ *   aligned bases      one byte for the first and for the last record of a walk; the records in between cover
+ *                      their node completely (aligned bases = node length, gathered on the device)
+ *   anything else      explicit fp64 coverage of the record (exc_idx / exc_cov): any record may be shipped that way
+ * Usable when no mate has more than 255 retained alignments, no walk more than 255 nodes, no read more than
+ * 65535 bases.  sfb_expand_reads turns it into the arrays of sfb_reads on the device. */
 typedef struct sfb_wire {
-    int64_t n_groups, n_alns, n_records, n_exc, n_wide;
+    int64_t n_groups, n_alns, n_records, n_exc, n_wide, n_seq_exc, n_bins_exc;
+    int64_t seq_len_common;       /* used when mate_seq_len is NULL                   */
     const uint8_t*  grp_nmates;   /* [G]  */
     const uint8_t*  mate_naln;    /* [2G] retained alignments per mate slot           */
-    const uint16_t* mate_seq_len; /* [2G] */
+    const uint16_t* mate_seq_len; /* [2G] or NULL: seq_len_common for every present mate but the listed ones */
+    const int64_t*  seq_exc_idx;  /* [n_seq_exc] mate slot (2 * group + mate)         */
+    const int32_t*  seq_exc_val;  /* [n_seq_exc] */
     const uint8_t*  aln_len;      /* [A]  nodes per walk                              */
-    const uint8_t*  aln_bins;     /* [5A] */
+    const uint8_t*  aln_code;     /* [A]  index into bins_dict, 255 = listed          */
+    const uint8_t*  bins_dict;    /* [255*5] */
+    const int64_t*  bins_exc_idx; /* [n_bins_exc] alignment                           */
+    const uint8_t*  bins_exc_val; /* [n_bins_exc*5] */
     const int32_t*  aln_node0;    /* [A]  first node of the walk                      */
+    const uint8_t*  aln_al_first; /* [A]  aligned bases of the walk's first record, 255 = explicit coverage */
+    const uint8_t*  aln_al_last;  /* [A]  ... of its last record (walks of two records or more)            */
     const int8_t*   walk_step;    /* [R]  node id minus the previous node id of the walk (unused for a walk's first
                                           record); -128: the id is wide_node[k] where wide_idx[k] is this record  */
-    const uint8_t*  walk_al;      /* [R]  aligned bases, 255 = explicit coverage      */
     const int64_t*  exc_idx;      /* [E]  record index of explicit coverage k, ascending */
     const double*   exc_cov;      /* [E]  */
     const int64_t*  wide_idx;     /* [W]  record indices of the wide steps, ascending */
@@ -200,12 +213,12 @@ int         sfb_abi_version(void);
 const char* sfb_version(void);
 const char* sfb_last_error(void);
 
-/* Device-side expansion of the transfer layout: grp_aln_off[2G+1] and aln_walk_off[A+1] by prefix sums of the
- * counts, mate_seq_len[2G] widened, walk_node[R] by summing the steps along every walk, walk_alen[R] = aligned |
- * node_len[walk_node] << 16 (or -(k+1)).  node_len: int32[n_nodes] on the device.
- * scratch: int64[max(2G, A)/4096 + 2]. */
-int sfb_expand_reads(const sfb_wire* w, const int32_t* node_len, int64_t* grp_aln_off, int32_t* mate_seq_len,
-                     int64_t* aln_walk_off, int32_t* walk_node, int32_t* walk_alen, int64_t* scratch, void* stream);
+/* Device-side expansion of the transfer layout.  `dst` is the view the kernels will use: its grp_aln_off[2G+1],
+ * mate_seq_len[2G], aln_walk_off[A+1], aln_bins[5A], walk_node[R] and walk_alen[R] point at caller-allocated device
+ * buffers that this call fills (prefix sums of the counts, widened lengths, dictionary look-ups, node ids summed
+ * along every walk, walk_alen = aligned | node_len[walk_node] << 16 or -(k+1)); its other members are not used.
+ * node_len: int32[n_nodes] on the device.  scratch: int64[max(2G, A)/4096 + 2]. */
+int sfb_expand_reads(const sfb_wire* w, const int32_t* node_len, const sfb_reads* dst, int64_t* scratch, void* stream);
 
 /* Pangenome.get_matching_path on the walk and, if longer than one node, on the reversed
  * walk (json2csv.py:341-363 with callers :855-866, :1024-1026, :1103-1114, :1231-1233). */

@@ -13,6 +13,12 @@ c_u64p = C.POINTER(C.c_uint64)
 c_f64p = C.POINTER(C.c_double)
 
 
+# arrays of the transfer layout, in struct order
+WIRE_ARRAYS = ("grp_nmates", "mate_naln", "mate_seq_len", "seq_exc_idx", "seq_exc_val", "aln_len", "aln_code", "bins_dict",
+               "bins_exc_idx", "bins_exc_val", "aln_node0", "aln_al_first", "aln_al_last", "walk_step", "exc_idx", "exc_cov",
+               "wide_idx", "wide_node")
+
+
 class SfbGraph(C.Structure):
     _fields_ = [
         ("n_nodes", C.c_int64), ("n_paths", C.c_int64), ("n_slots", C.c_int64), ("n_strains", C.c_int64),
@@ -34,13 +40,9 @@ class SfbReads(C.Structure):
 
 
 class SfbWire(C.Structure):
-    _fields_ = [
-        ("n_groups", C.c_int64), ("n_alns", C.c_int64), ("n_records", C.c_int64), ("n_exc", C.c_int64),
-        ("n_wide", C.c_int64),
-        ("grp_nmates", C.c_void_p), ("mate_naln", C.c_void_p), ("mate_seq_len", C.c_void_p), ("aln_len", C.c_void_p),
-        ("aln_bins", C.c_void_p), ("aln_node0", C.c_void_p), ("walk_step", C.c_void_p), ("walk_al", C.c_void_p),
-        ("exc_idx", C.c_void_p), ("exc_cov", C.c_void_p), ("wide_idx", C.c_void_p), ("wide_node", C.c_void_p),
-    ]
+    _fields_ = [(k, C.c_int64) for k in ("n_groups", "n_alns", "n_records", "n_exc", "n_wide", "n_seq_exc", "n_bins_exc",
+                                         "seq_len_common")] + \
+               [(k, C.c_void_p) for k in WIRE_ARRAYS]
 
 
 class SfbWork(C.Structure):
@@ -72,7 +74,7 @@ SLOT_MASK, MATCH_REV, MATCH_MULTI, MATCH_NONE = 0x3FFFFFFF, 0x40000000, 0x800000
 MAX_SLOTS = 0x3FFFFFFF
 (ABSENT, FILTERED, UNASSIGNED, UNASSIGNED_BOOK, DEFER, ASSIGN_SAME, ASSIGN_DIFF, MULTI_ALIGN, INCONSIST,
  SE_COUNTED) = range(10)
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 EXPORTS = ("sfb_abi_version", "sfb_version", "sfb_last_error", "sfb_expand_reads", "sfb_match", "sfb_classify", "sfb_pass1_scatter",
            "sfb_pass2", "sfb_pass2_resolve", "sfb_pass2_scatter", "sfb_accum_collapse", "sfb_path_reduce", "sfb_cluster_strain_counts", "sfb_strain_aggregate",
@@ -111,7 +113,7 @@ def load(build_if_missing=True):
     lib.sfb_last_error.restype = C.c_char_p
     G, R, W, A = C.POINTER(SfbGraph), C.POINTER(SfbReads), C.POINTER(SfbWork), C.POINTER(SfbAccum)
     vp, i64, f64 = C.c_void_p, C.c_int64, C.c_double
-    lib.sfb_expand_reads.argtypes = [C.POINTER(SfbWire), vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.sfb_expand_reads.argtypes = [C.POINTER(SfbWire), vp, R, vp, vp]
     lib.sfb_match.argtypes = [G, R, W, A, vp]
     lib.sfb_classify.argtypes = [G, R, W, A, vp]
     lib.sfb_pass1_scatter.argtypes = [G, R, W, A, vp]

@@ -27,7 +27,7 @@ int launch_classify(const Dev&, cudaStream_t);
 int launch_pass2_resolve(const Dev&, const long long*, cudaStream_t);
 int launch_pass1_scatter(const sfb_graph*, const sfb_reads*, const sfb_work*, sfb_accum*, cudaStream_t);
 int launch_pass2_scatter(const sfb_graph*, const sfb_reads*, const sfb_work*, sfb_accum*, cudaStream_t);
-int launch_expand(const sfb_wire*, const int32_t*, i64*, int32_t*, i64*, int32_t*, int32_t*, i64*, cudaStream_t);
+int launch_expand(const sfb_wire*, const int32_t*, const sfb_reads*, i64*, cudaStream_t);
 int launch_collapse(double*, i64, i64, cudaStream_t);
 int launch_path_reduce(const sfb_graph*, const sfb_accum*, i64, i64, double*, cudaStream_t);
 int launch_cluster_counts(i64, i64, const int32_t*, const int32_t*, const int32_t*, const int32_t*, const int32_t*,
@@ -89,18 +89,20 @@ int sfb_abi_version(void) { return SFB_ABI_VERSION; }
 const char* sfb_version(void) { return "sfb200 0.2 (sm_100a)"; }
 const char* sfb_last_error(void) { return g_err; }
 
-int sfb_expand_reads(const sfb_wire* w, const int32_t* node_len, int64_t* grp_aln_off, int32_t* mate_seq_len,
-                     int64_t* aln_walk_off, int32_t* walk_node, int32_t* walk_alen, int64_t* scratch, void* stream) {
-    SFB_REQUIRE(w, "wire is null");
-    SFB_REQUIRE(w->n_groups >= 0 && w->n_alns >= 0 && w->n_records >= 0 && w->n_exc >= 0 && w->n_wide >= 0, "negative size");
-    SFB_REQUIRE(grp_aln_off && aln_walk_off && scratch, "null output");
-    SFB_REQUIRE(w->n_groups == 0 || (w->grp_nmates && w->mate_naln && w->mate_seq_len && mate_seq_len), "null array");
-    SFB_REQUIRE(w->n_alns == 0 || (w->aln_len && w->aln_bins && w->aln_node0), "null array");
-    SFB_REQUIRE(w->n_records == 0 || (w->walk_step && w->walk_al && walk_node && walk_alen && node_len), "null array");
+int sfb_expand_reads(const sfb_wire* w, const int32_t* node_len, const sfb_reads* dst, int64_t* scratch, void* stream) {
+    SFB_REQUIRE(w && dst, "wire or destination is null");
+    SFB_REQUIRE(w->n_groups >= 0 && w->n_alns >= 0 && w->n_records >= 0 && w->n_exc >= 0 && w->n_wide >= 0 &&
+                    w->n_seq_exc >= 0 && w->n_bins_exc >= 0, "negative size");
+    SFB_REQUIRE(dst->grp_aln_off && dst->aln_walk_off && scratch, "null output");
+    SFB_REQUIRE(w->n_groups == 0 || (w->grp_nmates && w->mate_naln && dst->mate_seq_len), "null array");
+    SFB_REQUIRE(w->n_seq_exc == 0 || (w->seq_exc_idx && w->seq_exc_val), "null array");
+    SFB_REQUIRE(w->n_alns == 0 || (w->aln_len && w->aln_code && w->bins_dict && w->aln_node0 && w->aln_al_first &&
+                                   w->aln_al_last && dst->aln_bins), "null array");
+    SFB_REQUIRE(w->n_bins_exc == 0 || (w->bins_exc_idx && w->bins_exc_val), "null array");
+    SFB_REQUIRE(w->n_records == 0 || (w->walk_step && dst->walk_node && dst->walk_alen && node_len), "null array");
     SFB_REQUIRE(w->n_exc == 0 || (w->exc_idx && w->exc_cov), "null array");
     SFB_REQUIRE(w->n_wide == 0 || (w->wide_idx && w->wide_node), "null array");
-    return launch_expand(w, node_len, (i64*)grp_aln_off, mate_seq_len, (i64*)aln_walk_off, walk_node, walk_alen,
-                         (i64*)scratch, (cudaStream_t)stream);
+    return launch_expand(w, node_len, dst, (i64*)scratch, (cudaStream_t)stream);
 }
 
 int sfb_match(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_accum* acc, void* stream) {

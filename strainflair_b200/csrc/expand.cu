@@ -2,9 +2,10 @@
 //
 // The end-to-end path is bound by the host->device copy (PCIe, ~55 GB/s): CSR offsets travel as 1-byte counts and
 // become int64 offsets by a device prefix sum; read lengths travel as 16 bits; per record two bytes travel: the step
-// from the previous node id of the walk (walks follow the graph, ids are locally consecutive) and the aligned bases;
-// node ids are rebuilt by summing the steps along every walk and the node length is gathered from the graph on the
-// device.  3.7 GB -> 1.4 GB per C3 shard.
+// from the previous node id of the walk (walks follow the graph, ids are locally consecutive); aligned bases only for
+// the two end records of a walk (the others cover their node); histogram bins as a dictionary index; one common read
+// length.  Node ids are rebuilt by summing the steps along every walk, node lengths are gathered from the graph on
+// the device.  3.7 GB -> 0.8 GB per C3 shard.
 #include "common.cuh"
 
 namespace sfb {
@@ -79,8 +80,29 @@ __global__ void __launch_bounds__(kScanBlock) k_scan_write(const uint8_t* cnt, i
     }
 }
 
-__global__ void k_expand_seq_len(const uint16_t* in, i64 n, int32_t* out) {
-    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) out[i] = in[i];
+__global__ void k_expand_seq_len(sfb_wire w, int32_t* out) {
+    const i64 n = 2 * w.n_groups;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+        out[i] = w.mate_seq_len ? (int32_t)w.mate_seq_len[i] : ((i & 1) < w.grp_nmates[i >> 1] ? (int32_t)w.seq_len_common : 0);
+}
+__global__ void k_apply_seq_exceptions(sfb_wire w, int32_t* out) {
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < w.n_seq_exc; k += (i64)gridDim.x * blockDim.x)
+        out[w.seq_exc_idx[k]] = w.seq_exc_val[k];
+}
+// histogram bins of every alignment from the shard's dictionary of 5-tuples
+__global__ void __launch_bounds__(256) k_expand_bins(sfb_wire w, uint8_t* out) {
+    __shared__ uint8_t s_dict[256 * SFB_N_HIST];
+    for (int i = threadIdx.x; i < 255 * SFB_N_HIST; i += blockDim.x) s_dict[i] = w.bins_dict[i];
+    __syncthreads();
+    for (i64 a = (i64)blockIdx.x * blockDim.x + threadIdx.x; a < w.n_alns; a += (i64)gridDim.x * blockDim.x) {
+        const int code = w.aln_code[a];
+#pragma unroll
+        for (int k = 0; k < SFB_N_HIST; ++k) out[a * SFB_N_HIST + k] = code < 255 ? s_dict[code * SFB_N_HIST + k] : (uint8_t)255;
+    }
+}
+__global__ void k_apply_bins_exceptions(sfb_wire w, uint8_t* out) {
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < w.n_bins_exc; k += (i64)gridDim.x * blockDim.x)
+        for (int q = 0; q < SFB_N_HIST; ++q) out[w.bins_exc_idx[k] * SFB_N_HIST + q] = w.bins_exc_val[k * SFB_N_HIST + q];
 }
 // Node ids and packed coverage words (aligned bases | node length << 16, see record_cov) of every record.
 // One thread per walk: a walk is a handful of records, the threads of a warp cover one contiguous stretch.
@@ -105,8 +127,12 @@ __global__ void __launch_bounds__(256) k_expand_walks(sfb_wire w, const i64* __r
                     node = w.wide_node[x];
                 }
             }
+            const int32_t nl = node_len[node];
+            // first / last record: the shipped byte; in between the node is covered completely.  Records with an
+            // explicit coverage (byte 255, or listed) are overwritten by k_apply_exceptions.
+            const int32_t al = r == lo ? (int32_t)w.aln_al_first[a] : (r == hi - 1 ? (int32_t)w.aln_al_last[a] : (nl & 0xFFFF));
             walk_node[r] = node;
-            walk_alen[r] = (int32_t)w.walk_al[r] | (node_len[node] << 16);       // 255: replaced by k_apply_exceptions
+            walk_alen[r] = al | (nl << 16);
         }
     }
 }
@@ -127,11 +153,19 @@ static int scan_u8(const uint8_t* cnt, i64 n, i64* off, i64* scratch, cudaStream
     return check_launch("scan_u8");
 }
 
-int launch_expand(const sfb_wire* w, const int32_t* node_len, i64* grp_aln_off, int32_t* mate_seq_len, i64* aln_walk_off,
-                  int32_t* walk_node, int32_t* walk_alen, i64* scratch, cudaStream_t st) {
+int launch_expand(const sfb_wire* w, const int32_t* node_len, const sfb_reads* dst, i64* scratch, cudaStream_t st) {
+    i64* grp_aln_off = const_cast<i64*>((const i64*)dst->grp_aln_off);
+    i64* aln_walk_off = const_cast<i64*>((const i64*)dst->aln_walk_off);
+    int32_t* mate_seq_len = const_cast<int32_t*>(dst->mate_seq_len);
+    uint8_t* aln_bins = const_cast<uint8_t*>(dst->aln_bins);
+    int32_t* walk_node = const_cast<int32_t*>(dst->walk_node);
+    int32_t* walk_alen = const_cast<int32_t*>(dst->walk_alen);
     SFB_TRY(scan_u8(w->mate_naln, 2 * w->n_groups, grp_aln_off, scratch, st));
     SFB_TRY(scan_u8(w->aln_len, w->n_alns, aln_walk_off, scratch, st));
-    if (w->n_groups) k_expand_seq_len<<<kSMs * 4, 256, 0, st>>>(w->mate_seq_len, 2 * w->n_groups, mate_seq_len);
+    if (w->n_groups) k_expand_seq_len<<<kSMs * 4, 256, 0, st>>>(*w, mate_seq_len);
+    if (w->n_seq_exc) k_apply_seq_exceptions<<<blocks_for(w->n_seq_exc, 256), 256, 0, st>>>(*w, mate_seq_len);
+    if (w->n_alns) k_expand_bins<<<kSMs * 8, 256, 0, st>>>(*w, aln_bins);
+    if (w->n_bins_exc) k_apply_bins_exceptions<<<blocks_for(w->n_bins_exc, 256), 256, 0, st>>>(*w, aln_bins);
     if (w->n_records) k_expand_walks<<<kSMs * 8, 256, 0, st>>>(*w, aln_walk_off, node_len, walk_node, walk_alen);
     if (w->n_exc) k_apply_exceptions<<<blocks_for(w->n_exc, 256), 256, 0, st>>>((const i64*)w->exc_idx, w->n_exc, walk_alen);
     return check_launch("expand_reads");

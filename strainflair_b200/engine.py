@@ -100,47 +100,85 @@ WIRE_FIELDS = ("grp_nmates", "mate_naln", "mate_seq_len", "aln_len", "aln_bins",
                "exc_cov")
 
 
+def _bins_dictionary(bins):
+    """(dict u8[255, 5], code u8[A], listed alignments, their bins): the 255 most frequent 5-tuples of a sample."""
+    A = len(bins)
+    key = np.zeros(A, np.int64)
+    for k in range(5):
+        key |= bins[:, k].astype(np.int64) << (8 * k)
+    sample = key[:: max(1, A // 2_000_000)]
+    uniq, cnt = np.unique(sample, return_counts=True)
+    top = np.sort(uniq[np.argsort(-cnt, kind="stable")[:255]])
+    table = np.zeros((255, 5), np.uint8)
+    for k in range(5):
+        table[:len(top), k] = (top >> (8 * k)) & 0xFF
+    pos = np.searchsorted(top, key)
+    pos[pos >= len(top)] = 0
+    hit = top[pos] == key if len(top) else np.zeros(A, bool)
+    code = np.where(hit, pos, 255).astype(np.uint8)
+    listed = np.flatnonzero(~hit)
+    return table, code, listed, bins[listed]
+
+
 def wire_arrays(reads: Reads):
-    """Compact transfer layout (include/sfb200.h, sfb_wire) of a read shard, or None when it does not apply
-    (a mate with > 255 alignments, a walk of > 255 nodes, a read of > 65535 bases, or so many records needing an
-    explicit coverage / a wide node step that the plain layout is smaller)."""
+    """Compact transfer layout (include/sfb200.h, sfb_wire) of a read shard: (arrays, seq_len_common), or None when
+    it does not apply (a mate with > 255 alignments, a walk of > 255 nodes, a read of > 65535 bases, or so many
+    records needing an explicit coverage / a wide node step that the plain layout is smaller)."""
     naln = np.diff(reads.grp_aln_off)
     alen = np.diff(reads.aln_walk_off)
     if (naln.size and naln.max() > 255) or (alen.size and alen.max() > 255) or \
             (reads.mate_seq_len.size and reads.mate_seq_len.max() > 0xFFFF):
         return None
-    R = reads.n_records
+    G, A, R = reads.n_groups, reads.n_alns, reads.n_records
+    some = alen > 0
+    first = reads.aln_walk_off[:-1][some]
+    last = reads.aln_walk_off[1:][some] - 1
+    # aligned bases: a byte for the first and the last record of a walk, the node length in between; everything
+    # else is shipped as an explicit fp64 coverage (the same ratio, computed here as the device would)
     v = reads.walk_alen
-    # aligned bases in one byte; 255 = explicit coverage: the records that already have one, and those whose aligned
-    # length does not fit (their fp64 coverage is the same ratio, computed here as the device would)
-    low = v & 0xFFFF
-    big = np.flatnonzero((v >= 0) & (low >= 255))
-    old = np.flatnonzero(v < 0)
-    al = low.astype(np.uint8)
-    exc_idx = np.concatenate([old, big])
-    exc_cov = np.concatenate([reads.exc_cov[-v[old].astype(np.int64) - 1],
-                              low[big].astype(np.float64) / (v[big] >> 16).astype(np.float64)])
-    order = np.argsort(exc_idx, kind="stable")
-    exc_idx, exc_cov = exc_idx[order].astype(np.int64), exc_cov[order]
-    al[exc_idx] = 255
+    low, nl = v & 0xFFFF, v >> 16
+    edge = np.zeros(R, bool)
+    edge[first] = True
+    edge[last] = True
+    listed = (v < 0) | np.where(edge, low >= 255, low != nl)
+    exc_idx = np.flatnonzero(listed)
+    ve = v[exc_idx]
+    exc_cov = np.where(ve < 0, reads.exc_cov[np.where(ve < 0, -ve.astype(np.int64) - 1, 0)] if len(reads.exc_cov) else 0.0,
+                       (ve & 0xFFFF) / np.maximum(ve >> 16, 1))
+    al = np.where(listed, 255, low).astype(np.uint8)
+    al_first, al_last = np.zeros(A, np.uint8), np.zeros(A, np.uint8)
+    al_first[some] = al[first]
+    al_last[some] = np.where(last > first, al[last], 0)
     # node ids as steps along the walk
     node = reads.walk_node
-    start = reads.aln_walk_off[:-1][alen > 0]
     step = np.zeros(R, np.int64)
     if R:
         step[1:] = node[1:].astype(np.int64) - node[:-1]
-        step[start] = 0
+        step[first] = 0
     wide_idx = np.flatnonzero((step < -127) | (step > 127))
     step[wide_idx] = -128
     if 16 * len(exc_idx) + 12 * len(wide_idx) > 2 * R:
         return None
-    node0 = np.zeros(reads.n_alns, np.int32)
-    node0[alen > 0] = node[start]
-    return dict(grp_nmates=reads.grp_nmates, mate_naln=naln.astype(np.uint8),
-                mate_seq_len=reads.mate_seq_len.astype(np.uint16), aln_len=alen.astype(np.uint8),
-                aln_bins=reads.aln_bins.reshape(-1), aln_node0=node0, walk_step=step.astype(np.int8), walk_al=al,
-                exc_idx=exc_idx, exc_cov=exc_cov, wide_idx=wide_idx.astype(np.int64),
-                wide_node=node[wide_idx].astype(np.int32))
+    node0 = np.zeros(A, np.int32)
+    node0[some] = node[first]
+    # read lengths: the most frequent one + the mates that differ, when that is smaller than 16 bits per mate
+    present = (np.arange(2 * G) & 1) < np.repeat(reads.grp_nmates, 2)
+    lens = reads.mate_seq_len[present]
+    common = int(np.bincount(lens).argmax()) if len(lens) else 0
+    seq_exc = np.flatnonzero(np.where(present, reads.mate_seq_len != common, reads.mate_seq_len != 0))
+    seq16 = np.zeros(0, np.uint16)
+    if 12 * len(seq_exc) > 4 * G:
+        seq16, seq_exc = reads.mate_seq_len.astype(np.uint16), seq_exc[:0]
+    table, code, bins_listed, bins_val = _bins_dictionary(reads.aln_bins.reshape(-1, 5))
+    arrays = dict(grp_nmates=reads.grp_nmates, mate_naln=naln.astype(np.uint8), mate_seq_len=seq16,
+                  seq_exc_idx=seq_exc.astype(np.int64), seq_exc_val=reads.mate_seq_len[seq_exc].astype(np.int32),
+                  aln_len=alen.astype(np.uint8), aln_code=code, bins_dict=table.reshape(-1),
+                  bins_exc_idx=bins_listed.astype(np.int64), bins_exc_val=np.ascontiguousarray(bins_val).reshape(-1),
+                  aln_node0=node0, aln_al_first=al_first, aln_al_last=al_last, walk_step=step.astype(np.int8),
+                  exc_idx=exc_idx.astype(np.int64), exc_cov=exc_cov.astype(np.float64),
+                  wide_idx=wide_idx.astype(np.int64), wide_node=node[wide_idx].astype(np.int32))
+    assert tuple(arrays) == _lib.WIRE_ARRAYS
+    return arrays, common
 
 
 def _layout(arrays):
@@ -159,8 +197,9 @@ class HostReads:
 
     def __init__(self, reads: Reads, pin=True, wire=True):
         self.reads = reads
-        arrays = wire_arrays(reads) if wire else None
-        self.wire = arrays is not None
+        packed = wire_arrays(reads) if wire else None
+        self.wire = packed is not None
+        arrays, self.seq_len_common = packed if packed else (None, 0)
         if arrays is None:
             arrays = {k: np.ascontiguousarray(getattr(reads, k)).reshape(-1) for k in READS_DEVICE_FIELDS}
         self.offs, self.size = _layout(arrays)
@@ -173,7 +212,8 @@ class HostReads:
                 view[o:o + n] = np.ascontiguousarray(arrays[k]).reshape(-1).view(np.uint8)
         self.n_groups, self.n_alns, self.n_records = reads.n_groups, reads.n_alns, reads.n_records
         self.n_exc = len(arrays["exc_cov"])
-        self.n_wide = len(arrays["wide_idx"]) if self.wire else 0
+        self.n_wide, self.n_seq_exc, self.n_bins_exc = \
+            (len(arrays[k]) if self.wire else 0 for k in ("wide_idx", "seq_exc_idx", "bins_exc_idx"))
 
     def nbytes(self):
         return sum(n for _, n in self.offs.values())
@@ -207,25 +247,24 @@ class DeviceReads:
             self.c = _lib.SfbReads(n_groups=G, n_alns=A, n_records=R, n_exc=E, **ptr)
             return
         # expanded arrays (one device allocation, reused across steps)
-        need = 8 * (2 * G + 1) + 4 * 2 * G + 8 * (A + 1) + 8 * R + 8 * (max(2 * G, A) // 4096 + 2) + 6 * 256
+        need = 8 * (2 * G + 1) + 4 * 2 * G + 8 * (A + 1) + 5 * A + 8 * R + 8 * (max(2 * G, A) // 4096 + 2) + 7 * 256
         if wide is None or wide.numel() < need:
             wide = torch.empty(need, dtype=torch.uint8, device=device)
         self.wide = wide
         p, out = wide.data_ptr(), {}
         for k, n in (("grp_aln_off", 8 * (2 * G + 1)), ("aln_walk_off", 8 * (A + 1)), ("scratch", 8 * (max(2 * G, A) // 4096 + 2)),
-                     ("mate_seq_len", 8 * G), ("walk_node", 4 * R), ("walk_alen", 4 * R)):
+                     ("mate_seq_len", 8 * G), ("aln_bins", 5 * A), ("walk_node", 4 * R), ("walk_alen", 4 * R)):
             out[k] = p
             p += (n + 255) & ~255
-        w = _lib.SfbWire(n_groups=G, n_alns=A, n_records=R, n_exc=E, n_wide=host.n_wide, **ptr)
-        _lib.check(_lib.load().sfb_expand_reads(C.byref(w), C.c_void_p(node_len.data_ptr()), C.c_void_p(out["grp_aln_off"]),
-                                                C.c_void_p(out["mate_seq_len"]), C.c_void_p(out["aln_walk_off"]),
-                                                C.c_void_p(out["walk_node"]), C.c_void_p(out["walk_alen"]),
-                                                C.c_void_p(out["scratch"]), _stream()))
+        w = _lib.SfbWire(n_groups=G, n_alns=A, n_records=R, n_exc=E, n_wide=host.n_wide, n_seq_exc=host.n_seq_exc,
+                         n_bins_exc=host.n_bins_exc, seq_len_common=host.seq_len_common, **ptr)
         self.c = _lib.SfbReads(n_groups=G, n_alns=A, n_records=R, n_exc=E, grp_nmates=ptr["grp_nmates"],
                                grp_aln_off=out["grp_aln_off"], mate_seq_len=out["mate_seq_len"] if G else 0,
-                               aln_walk_off=out["aln_walk_off"], aln_bins=ptr["aln_bins"],
+                               aln_walk_off=out["aln_walk_off"], aln_bins=out["aln_bins"] if A else 0,
                                walk_node=out["walk_node"] if R else 0, walk_alen=out["walk_alen"] if R else 0,
                                exc_cov=ptr["exc_cov"])
+        _lib.check(_lib.load().sfb_expand_reads(C.byref(w), C.c_void_p(node_len.data_ptr()), C.byref(self.c),
+                                                C.c_void_p(out["scratch"]), _stream()))
 
 
 class Work:

@@ -10,6 +10,8 @@ import json
 import pickle
 import random
 
+import numpy as np
+
 
 def make_graph(rng, n_clusters=4, n_strains=4, first_node=1):
     """Returns dict(nodes={id: len}, plines=[(name, [(id, sign)])], clusters={...}, strains=[...])."""
@@ -263,3 +265,34 @@ def make_case(seed, outdir, n_groups=60, n_clusters=4, n_strains=4):
     write_json(lines, js)
     write_pickle(graph, pk)
     return gfa, js, pk
+
+
+def stress_transfer_layout(graph, reads, rng, variant):
+    """Bend a synthetic shard (in place) so that it exercises the exception lists of the transfer layout.
+    The walks may stop following the graph: the expansion does not care."""
+    R, A = reads.n_records, reads.n_alns
+    keep = reads.walk_alen >= 0
+    if variant == "wide_steps":
+        hit = rng.random(R) < 0.05
+        reads.walk_node[hit] = rng.integers(0, graph.n_nodes, int(hit.sum()))          # far-away node ids
+        edge = np.zeros(R, bool)
+        edge[reads.aln_walk_off[:-1]] = True
+        edge[reads.aln_walk_off[1:] - 1] = True
+        nl = graph.node_len[reads.walk_node].astype(np.int64)
+        al = np.where(edge, np.minimum(reads.walk_alen & 0xFFFF, nl), nl)
+        reads.walk_alen[keep] = (al | (nl << 16))[keep].astype(np.int32)
+    elif variant == "long_nodes":
+        graph.node_len[:] = np.minimum(graph.node_len.astype(np.int64) * 40, 0x7FFF)   # aligned lengths beyond a byte
+        edge = np.zeros(R, bool)
+        edge[reads.aln_walk_off[:-1]] = True
+        edge[reads.aln_walk_off[1:] - 1] = True
+        nl = graph.node_len[reads.walk_node].astype(np.int64)
+        al = np.where(edge, rng.integers(0, 255, R), nl)
+        al = np.where(rng.random(R) < 0.05, rng.integers(255, 600, R), al)
+        reads.walk_alen[keep] = (al | (nl << 16))[keep].astype(np.int32)
+    elif variant == "ragged_lengths":
+        present = reads.mate_seq_len > 0
+        reads.mate_seq_len[present] = rng.integers(50, 151, int(present.sum()))
+        some = rng.random(A) < 0.3                                                      # and > 255 distinct bin tuples
+        reads.aln_bins[some] = rng.integers(0, 101, (int(some.sum()), 5))
+        reads.aln_bins[rng.random(A) < 0.2, 2] = 255

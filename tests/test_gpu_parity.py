@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 import torch
 
+import casegen
 import compare
 from oracle import abundance as oa
 from oracle import decode as od
@@ -209,29 +210,19 @@ def test_error_quirks_raise_like_reference():
         oa.AbundanceOracle(g3.as_dict(), r3.as_dict()).run()
 
 
-@pytest.mark.parametrize("shuffle_ids", [False, True])
-def test_transfer_layout_expands_to_the_same_arrays(shuffle_ids):
+@pytest.mark.parametrize("variant", ["plain", "wide_steps", "long_nodes", "ragged_lengths"])
+def test_transfer_layout_expands_to_the_same_arrays(variant):
     """sfb_expand_reads(wire(reads)) == the wide arrays, bit for bit (offset scans across tile boundaries, node ids
-    from steps incl. wide ones, explicit coverages, widened lengths)."""
+    from steps incl. wide ones, bins from the dictionary, explicit coverages, read lengths)."""
     need_gpu()
     gkw, _ = synth.CONFIGS["small"]
     graph = synth.make_graph(3, **gkw)
     reads = synth.make_reads(graph, 4, n_pairs=30_000, read_len=150, p_exc=0.01)
-    if shuffle_ids:
-        # long nodes (aligned lengths that do not fit a byte) and a sprinkle of far-away node ids (wide steps);
-        # the walks no longer follow the graph, which the expansion does not care about
-        rng = np.random.default_rng(5)
-        graph.node_len[:] = np.minimum(graph.node_len.astype(np.int64) * 40, 0x7FFF)
-        hit = rng.random(reads.n_records) < 0.03
-        reads.walk_node[hit] = rng.integers(0, graph.n_nodes, int(hit.sum()))
-        keep = reads.walk_alen >= 0
-        al = np.where(rng.random(reads.n_records) < 0.03, rng.integers(255, 600, reads.n_records),
-                      rng.integers(0, 255, reads.n_records))
-        reads.walk_alen[keep] = (al | (graph.node_len[reads.walk_node].astype(np.int64) << 16))[keep].astype(np.int32)
+    casegen.stress_transfer_layout(graph, reads, np.random.default_rng(5), variant)
     eng = engine.AbundanceEngine(graph)
     host = engine.HostReads(reads, wire=True)
-    assert host.wire and host.nbytes() < (0.7 if shuffle_ids else 0.45) * engine.HostReads(reads, wire=False).nbytes()
-    assert (host.n_wide > 0) == shuffle_ids and host.n_exc > len(reads.exc_cov) * shuffle_ids
+    assert host.wire and host.nbytes() < (0.25 if variant == "plain" else 0.6) * engine.HostReads(reads, wire=False).nbytes()
+    assert (host.n_wide > 0) == (variant == "wide_steps") and (host.n_bins_exc > 0) == (variant == "ragged_lengths")
     dr = eng.upload(host)
     torch.cuda.synchronize()
 
@@ -247,6 +238,7 @@ def test_transfer_layout_expands_to_the_same_arrays(shuffle_ids):
     assert np.array_equal(view(dr.c.aln_walk_off, A + 1, torch.int64), reads.aln_walk_off)
     assert np.array_equal(view(dr.c.mate_seq_len, 2 * G, torch.int32), reads.mate_seq_len)
     assert np.array_equal(view(dr.c.walk_node, R, torch.int32), reads.walk_node)
+    assert np.array_equal(view(dr.c.aln_bins, 5 * A, torch.uint8).reshape(A, 5), reads.aln_bins)
 
     def coverage(word, exc):
         word = word.astype(np.int64)
@@ -258,9 +250,8 @@ def test_transfer_layout_expands_to_the_same_arrays(shuffle_ids):
     exc_dev = view(dr.c.exc_cov, host.n_exc, torch.float64) if host.n_exc else np.zeros(0)
     got = view(dr.c.walk_alen, R, torch.int32)
     assert np.array_equal(coverage(got, exc_dev), coverage(reads.walk_alen, reads.exc_cov))
-    fits = (reads.walk_alen >= 0) & ((reads.walk_alen & 0xFFFF) < 255)
-    assert np.array_equal(got[fits], reads.walk_alen[fits])
-    if shuffle_ids:
+    assert np.array_equal(got[got >= 0], reads.walk_alen[got >= 0])
+    if variant != "plain":
         return
     # and the pass gives the same result from either layout
     a = eng.run(engine.HostReads(reads, wire=True))

@@ -187,34 +187,65 @@ def test_gfa_corner_cases_match_oracle(tmp_path):
     same_graph(gfa.load_graph(str(p)), og.load_graph(str(p)))
 
 
-def test_transfer_layout_round_trip_on_host():
+def _expand_on_host(w, common, n_nodes_len):
+    """numpy restatement of sfb_expand_reads (csrc/expand.cu)."""
+    G, A = len(w["grp_nmates"]), len(w["aln_len"])
+    grp_aln_off = np.concatenate([[0], np.cumsum(w["mate_naln"], dtype=np.int64)])
+    off = np.concatenate([[0], np.cumsum(w["aln_len"], dtype=np.int64)])
+    if len(w["mate_seq_len"]):
+        seq = w["mate_seq_len"].astype(np.int32)
+    else:
+        seq = np.where((np.arange(2 * G) & 1) < np.repeat(w["grp_nmates"], 2), common, 0).astype(np.int32)
+        seq[w["seq_exc_idx"]] = w["seq_exc_val"]
+    bins = np.full((A, 5), 255, np.uint8)
+    known = w["aln_code"] < 255
+    bins[known] = w["bins_dict"].reshape(255, 5)[w["aln_code"][known]]
+    bins[w["bins_exc_idx"]] = w["bins_exc_val"].reshape(-1, 5)
+    R = int(off[-1])
+    node, word = np.empty(R, np.int32), np.empty(R, np.int32)
+    wide = dict(zip(w["wide_idx"].tolist(), w["wide_node"].tolist()))
+    for a in range(A):
+        cur = int(w["aln_node0"][a])
+        for r in range(off[a], off[a + 1]):
+            if r > off[a]:
+                cur = wide[r] if w["walk_step"][r] == -128 else cur + int(w["walk_step"][r])
+            nl = int(n_nodes_len[cur])
+            al = int(w["aln_al_first"][a]) if r == off[a] else int(w["aln_al_last"][a]) if r == off[a + 1] - 1 else nl & 0xFFFF
+            node[r], word[r] = cur, np.int64(al | (nl << 16)).astype(np.int32)
+    word[w["exc_idx"]] = -(np.arange(len(w["exc_idx"]), dtype=np.int32) + 1)
+    return grp_aln_off, off, seq, bins, node, word
+
+
+def _coverage(word, exc):
+    word = word.astype(np.int64)
+    neg = word < 0
+    cov = np.where(neg, 0, word & 0xFFFF) / np.where(neg, 1, word >> 16)
+    cov[neg] = exc[-word[neg] - 1]
+    return cov
+
+
+@pytest.mark.parametrize("variant", ["plain", "wide_steps", "long_nodes", "ragged_lengths"])
+def test_transfer_layout_round_trip_on_host(variant):
     """engine.wire_arrays holds everything needed to rebuild the shard (what sfb_expand_reads does on the device)."""
     from strainflair_b200 import engine, synth
     gkw, _ = synth.CONFIGS["tiny"]
     graph = synth.make_graph(11, **gkw)
     reads = synth.make_reads(graph, 12, n_pairs=3000, read_len=150, p_exc=0.02)
     rng = np.random.default_rng(1)
-    hit = rng.random(reads.n_records) < 0.05
-    reads.walk_node[hit] = rng.integers(0, graph.n_nodes, int(hit.sum()))          # far-away ids: wide steps
-    w = engine.wire_arrays(reads)
-    assert len(w["wide_idx"]) > 0 and w["walk_step"].dtype == np.int8 and w["walk_al"].dtype == np.uint8
-    assert np.array_equal(np.concatenate([[0], np.cumsum(w["mate_naln"], dtype=np.int64)]), reads.grp_aln_off)
-    off = np.concatenate([[0], np.cumsum(w["aln_len"], dtype=np.int64)])
-    assert np.array_equal(off, reads.aln_walk_off)
-    node = np.empty(reads.n_records, np.int64)
-    wide = dict(zip(w["wide_idx"].tolist(), w["wide_node"].tolist()))
-    for a in range(reads.n_alns):
-        cur = int(w["aln_node0"][a])
-        for r in range(off[a], off[a + 1]):
-            if r > off[a]:
-                cur = wide[r] if w["walk_step"][r] == -128 else cur + int(w["walk_step"][r])
-            node[r] = cur
+    casegen.stress_transfer_layout(graph, reads, rng, variant)
+    w, common = engine.wire_arrays(reads)
+    assert (len(w["wide_idx"]) > 0) == (variant == "wide_steps")
+    assert (len(w["mate_seq_len"]) > 0) == (variant == "ragged_lengths") and (len(w["bins_exc_idx"]) > 0) == (variant == "ragged_lengths")
+    assert np.all(np.diff(w["exc_idx"]) > 0) and np.all(np.diff(w["wide_idx"]) > 0)
+    grp_aln_off, off, seq, bins, node, word = _expand_on_host(w, common, graph.node_len)
+    assert np.array_equal(grp_aln_off, reads.grp_aln_off) and np.array_equal(off, reads.aln_walk_off)
+    assert np.array_equal(seq, reads.mate_seq_len) and np.array_equal(bins, reads.aln_bins)
     assert np.array_equal(node, reads.walk_node)
-    assert np.all(np.diff(w["exc_idx"]) > 0) and np.all(w["walk_al"][w["exc_idx"]] == 255)
-    plain = np.setdiff1d(np.arange(reads.n_records), w["exc_idx"])
-    assert np.array_equal(w["walk_al"][plain], (reads.walk_alen[plain] & 0xFFFF))
-    old = reads.walk_alen[w["exc_idx"]]
-    assert np.array_equal(w["exc_cov"][old < 0], reads.exc_cov[-old[old < 0].astype(np.int64) - 1])
-    # a shard whose exceptions would outweigh the saving falls back to the plain layout
-    reads.walk_node[:] = rng.integers(0, graph.n_nodes, reads.n_records)
-    assert engine.wire_arrays(reads) is None
+    assert np.array_equal(_coverage(word, w["exc_cov"]), _coverage(reads.walk_alen, reads.exc_cov))
+    unlisted = np.setdiff1d(np.arange(reads.n_records), w["exc_idx"])
+    assert np.array_equal(word[unlisted], reads.walk_alen[unlisted])
+    if variant == "plain":
+        assert len(w["exc_idx"]) < len(reads.exc_cov) + 0.01 * reads.n_records
+        # a shard whose exceptions would outweigh the saving falls back to the plain layout
+        reads.walk_node[:] = rng.integers(0, graph.n_nodes, reads.n_records)
+        assert engine.wire_arrays(reads) is None

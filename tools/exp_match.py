@@ -20,6 +20,10 @@ for it in range(8):
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(stages) + 1)]
     evs[0].record()
     for k, st in enumerate(stages):
+        if st == "pass2_resolve" and os.environ.get("SFB_EXP_SORT"):
+            n_def = int(work.t["cursor"][1].item())
+            work.t["deferred"][:n_def] = torch.sort(work.t["deferred"][:n_def]).values
+            evs[k].record()
         getattr(eng, st)(dr, work)
         evs[k + 1].record()
     torch.cuda.synchronize()
