@@ -290,6 +290,19 @@ int64_t      sfb_decoded_size(const sfb_decoded* d, int which);
 int          sfb_decoded_copy(const sfb_decoded* d, int which, void* dst);
 void         sfb_decoded_free(sfb_decoded* d);
 
+/* ---- host-side packer of the transfer layout (no GPU involved) ----------------------------
+ * sfb_wire_pack: `host_reads` holds HOST pointers; returns the arrays of sfb_wire for that shard (multi-threaded, the
+ * result does not depend on n_threads).  sfb_packed_status: 0 ok, 1 the layout does not apply (a mate with more than
+ * 255 alignments, a walk of more than 255 nodes, a read of more than 65535 bases, or so many exceptions that the plain
+ * arrays are smaller): ship the sfb_reads arrays as they are; 5 out of memory.  sfb_packed_size(which): bytes of array
+ * `which` (0..17, the order of the pointers in sfb_wire; 0 bytes = NULL pointer), 100: seq_len_common. */
+typedef struct sfb_packed sfb_packed;
+sfb_packed*  sfb_wire_pack(const sfb_reads* host_reads, int n_threads);
+int          sfb_packed_status(const sfb_packed* p, const char** msg);
+int64_t      sfb_packed_size(const sfb_packed* p, int which);
+int          sfb_packed_copy(const sfb_packed* p, int which, void* dst);
+void         sfb_packed_free(sfb_packed* p);
+
 /* ---- host-side GFA loader (no GPU involved) ------------------------------------------------
  * Pangenome.build_pangenome + canonical + get_accession_number (json2csv.py:46-81, 223-298) over a memory-mapped
  * GFA.  sfb_gfa_size(which): 0 nodes, 1 paths, 2 path nodes, 3 (path, strain) entries, 4 strains, 5 bytes of strain

@@ -14,6 +14,7 @@ c_f64p = C.POINTER(C.c_double)
 
 
 # arrays of the transfer layout, in struct order
+WIRE_DTYPES = ("u1", "u1", "u2", "i8", "i4", "u1", "u1", "u1", "i8", "u1", "i4", "u1", "u1", "i1", "i8", "f8", "i8", "i4")
 WIRE_ARRAYS = ("grp_nmates", "mate_naln", "mate_seq_len", "seq_exc_idx", "seq_exc_val", "aln_len", "aln_code", "bins_dict",
                "bins_exc_idx", "bins_exc_val", "aln_node0", "aln_al_first", "aln_al_last", "walk_step", "exc_idx", "exc_cov",
                "wide_idx", "wide_node")
@@ -79,6 +80,7 @@ ABI_VERSION = 8
 EXPORTS = ("sfb_abi_version", "sfb_version", "sfb_last_error", "sfb_expand_reads", "sfb_match", "sfb_classify", "sfb_pass1_scatter",
            "sfb_pass2", "sfb_pass2_resolve", "sfb_pass2_scatter", "sfb_accum_collapse", "sfb_path_reduce", "sfb_cluster_strain_counts", "sfb_strain_aggregate",
            "sfb_decode_json", "sfb_decoded_error", "sfb_decoded_size", "sfb_decoded_copy", "sfb_decoded_free",
+           "sfb_wire_pack", "sfb_packed_status", "sfb_packed_size", "sfb_packed_copy", "sfb_packed_free",
            "sfb_load_gfa", "sfb_gfa_error", "sfb_gfa_size", "sfb_gfa_copy", "sfb_gfa_free")
 
 
@@ -126,6 +128,16 @@ def load(build_if_missing=True):
     lib.sfb_strain_aggregate.argtypes = [i64, i64, vp, vp, vp, vp, vp, vp, f64, vp, vp, vp, vp, vp]
     for name in EXPORTS[3:14]:
         getattr(lib, name).restype = C.c_int
+    lib.sfb_wire_pack.argtypes = [R, C.c_int]
+    lib.sfb_wire_pack.restype = C.c_void_p
+    lib.sfb_packed_status.argtypes = [vp, C.POINTER(C.c_char_p)]
+    lib.sfb_packed_status.restype = C.c_int
+    lib.sfb_packed_size.argtypes = [vp, C.c_int]
+    lib.sfb_packed_size.restype = C.c_int64
+    lib.sfb_packed_copy.argtypes = [vp, C.c_int, vp]
+    lib.sfb_packed_copy.restype = C.c_int
+    lib.sfb_packed_free.argtypes = [vp]
+    lib.sfb_packed_free.restype = None
     lib.sfb_decode_json.argtypes = [C.c_char_p, vp, vp, i64, f64, C.c_int, i64]
     lib.sfb_decode_json.restype = C.c_void_p
     lib.sfb_decoded_error.argtypes = [vp, C.POINTER(C.c_char_p)]

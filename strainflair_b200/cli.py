@@ -24,22 +24,34 @@ def run_json2csv(graph_file, mapping_file, pickle_file, prefix, thr=0.95, device
     t["decode_s"] = time.perf_counter() - t0
     t0 = time.perf_counter()
     eng = engine.AbundanceEngine(graph, device, deterministic=True)     # files out: bit-reproducible from run to run
+    t["abundance_engine_s"] = time.perf_counter() - t0
     print("Parsing Alignment: second pass")
     res = eng.run(reads, keep_codes=True, keep_slots=False)
     t["abundance_s"] = time.perf_counter() - t0
-    t0 = time.perf_counter()
+    t0 = t1 = time.perf_counter()
+
+    def lap(key):
+        nonlocal t1
+        t[key] = time.perf_counter() - t1
+        t1 = time.perf_counter()
+
     clusters = report.cluster_records(graph, reads, res)
+    lap("report_cluster_records_s")
     gene_csv = prefix + "_gene_table.csv"
     print(f"Print gene-level results to file {gene_csv}")
     report.write_gene_table(gene_csv, graph, res)
+    lap("report_gene_table_s")
     for k, name in enumerate(report.HIST_FILES):
         print(f"Print {name} distribution results to file {prefix + '_' + name + '.csv'}")
         report.write_histogram(prefix + "_" + name + ".csv", graph, res, k)
     print(f"Print cluster-level unassigned reads distribution results to file {prefix + '_unassigned.csv'}")
+    lap("report_histograms_s")
     report.write_unassigned(prefix + "_unassigned.csv", graph, clusters, engine.cluster_strain_counts(graph, device))
+    lap("report_unassigned_s")
     report.write_clusters_pickle("allclusters.pickle", clusters)        # current directory, as json2csv.py:1344 (Q11)
     for line in report.summary_lines(res.C, thr, prefix):
         print(line)
+    lap("report_pickle_s")
     t["report_s"] = time.perf_counter() - t0
     if timings is not None:
         timings.update(t)

@@ -100,93 +100,60 @@ WIRE_FIELDS = ("grp_nmates", "mate_naln", "mate_seq_len", "aln_len", "aln_bins",
                "exc_cov")
 
 
-def _bins_dictionary(bins):
-    """(dict u8[255, 5], code u8[A], listed alignments, their bins): the 255 most frequent 5-tuples of a sample."""
-    A = len(bins)
-    key = np.zeros(A, np.int64)
-    for k in range(5):
-        key |= bins[:, k].astype(np.int64) << (8 * k)
-    sample = key[:: max(1, A // 2_000_000)]
-    uniq, cnt = np.unique(sample, return_counts=True)
-    top = np.sort(uniq[np.argsort(-cnt, kind="stable")[:255]])
-    table = np.zeros((255, 5), np.uint8)
-    for k in range(5):
-        table[:len(top), k] = (top >> (8 * k)) & 0xFF
-    pos = np.searchsorted(top, key)
-    pos[pos >= len(top)] = 0
-    hit = top[pos] == key if len(top) else np.zeros(A, bool)
-    code = np.where(hit, pos, 255).astype(np.uint8)
-    listed = np.flatnonzero(~hit)
-    return table, code, listed, bins[listed]
+class _Packed:
+    """Handle on the native packer's result (csrc/wire.cpp): sizes first, then copies straight into the arena."""
+
+    def __init__(self, reads: Reads, threads=None):
+        import os
+        self.lib = _lib.load()
+        keep = {k: np.ascontiguousarray(getattr(reads, k), dt).reshape(-1) for k, dt in (
+            ("grp_nmates", np.uint8), ("grp_aln_off", np.int64), ("mate_seq_len", np.int32), ("aln_walk_off", np.int64),
+            ("aln_bins", np.uint8), ("walk_node", np.int32), ("walk_alen", np.int32), ("exc_cov", np.float64))}
+        view = _lib.SfbReads(n_groups=reads.n_groups, n_alns=reads.n_alns, n_records=reads.n_records,
+                             n_exc=len(keep["exc_cov"]), **{k: v.ctypes.data for k, v in keep.items()})
+        self.h = self.lib.sfb_wire_pack(C.byref(view), int(threads or len(os.sched_getaffinity(0))))
+        msg = C.c_char_p()
+        self.status = self.lib.sfb_packed_status(self.h, C.byref(msg))
+        if self.status > 1:
+            text = (msg.value or b"").decode()
+            self.close()
+            raise MemoryError(text)
+        self.nbytes = [int(self.lib.sfb_packed_size(self.h, k)) for k in range(len(_lib.WIRE_ARRAYS))] if self.status == 0 else None
+        self.seq_len_common = int(self.lib.sfb_packed_size(self.h, 100))
+
+    def copy_to(self, which, ptr):
+        self.lib.sfb_packed_copy(self.h, which, C.c_void_p(ptr))
+
+    def close(self):
+        if self.h:
+            self.lib.sfb_packed_free(self.h)
+            self.h = None
 
 
-def wire_arrays(reads: Reads):
-    """Compact transfer layout (include/sfb200.h, sfb_wire) of a read shard: (arrays, seq_len_common), or None when
-    it does not apply (a mate with > 255 alignments, a walk of > 255 nodes, a read of > 65535 bases, or so many
-    records needing an explicit coverage / a wide node step that the plain layout is smaller)."""
-    naln = np.diff(reads.grp_aln_off)
-    alen = np.diff(reads.aln_walk_off)
-    if (naln.size and naln.max() > 255) or (alen.size and alen.max() > 255) or \
-            (reads.mate_seq_len.size and reads.mate_seq_len.max() > 0xFFFF):
-        return None
-    G, A, R = reads.n_groups, reads.n_alns, reads.n_records
-    some = alen > 0
-    first = reads.aln_walk_off[:-1][some]
-    last = reads.aln_walk_off[1:][some] - 1
-    # aligned bases: a byte for the first and the last record of a walk, the node length in between; everything
-    # else is shipped as an explicit fp64 coverage (the same ratio, computed here as the device would)
-    v = reads.walk_alen
-    low, nl = v & 0xFFFF, v >> 16
-    edge = np.zeros(R, bool)
-    edge[first] = True
-    edge[last] = True
-    listed = (v < 0) | np.where(edge, low >= 255, low != nl)
-    exc_idx = np.flatnonzero(listed)
-    ve = v[exc_idx]
-    exc_cov = np.where(ve < 0, reads.exc_cov[np.where(ve < 0, -ve.astype(np.int64) - 1, 0)] if len(reads.exc_cov) else 0.0,
-                       (ve & 0xFFFF) / np.maximum(ve >> 16, 1))
-    al = np.where(listed, 255, low).astype(np.uint8)
-    al_first, al_last = np.zeros(A, np.uint8), np.zeros(A, np.uint8)
-    al_first[some] = al[first]
-    al_last[some] = np.where(last > first, al[last], 0)
-    # node ids as steps along the walk
-    node = reads.walk_node
-    step = np.zeros(R, np.int64)
-    if R:
-        step[1:] = node[1:].astype(np.int64) - node[:-1]
-        step[first] = 0
-    wide_idx = np.flatnonzero((step < -127) | (step > 127))
-    step[wide_idx] = -128
-    if 16 * len(exc_idx) + 12 * len(wide_idx) > 2 * R:
-        return None
-    node0 = np.zeros(A, np.int32)
-    node0[some] = node[first]
-    # read lengths: the most frequent one + the mates that differ, when that is smaller than 16 bits per mate
-    present = (np.arange(2 * G) & 1) < np.repeat(reads.grp_nmates, 2)
-    lens = reads.mate_seq_len[present]
-    common = int(np.bincount(lens).argmax()) if len(lens) else 0
-    seq_exc = np.flatnonzero(np.where(present, reads.mate_seq_len != common, reads.mate_seq_len != 0))
-    seq16 = np.zeros(0, np.uint16)
-    if 12 * len(seq_exc) > 4 * G:
-        seq16, seq_exc = reads.mate_seq_len.astype(np.uint16), seq_exc[:0]
-    table, code, bins_listed, bins_val = _bins_dictionary(reads.aln_bins.reshape(-1, 5))
-    arrays = dict(grp_nmates=reads.grp_nmates, mate_naln=naln.astype(np.uint8), mate_seq_len=seq16,
-                  seq_exc_idx=seq_exc.astype(np.int64), seq_exc_val=reads.mate_seq_len[seq_exc].astype(np.int32),
-                  aln_len=alen.astype(np.uint8), aln_code=code, bins_dict=table.reshape(-1),
-                  bins_exc_idx=bins_listed.astype(np.int64), bins_exc_val=np.ascontiguousarray(bins_val).reshape(-1),
-                  aln_node0=node0, aln_al_first=al_first, aln_al_last=al_last, walk_step=step.astype(np.int8),
-                  exc_idx=exc_idx.astype(np.int64), exc_cov=exc_cov.astype(np.float64),
-                  wide_idx=wide_idx.astype(np.int64), wide_node=node[wide_idx].astype(np.int32))
-    assert tuple(arrays) == _lib.WIRE_ARRAYS
-    return arrays, common
+def wire_arrays(reads: Reads, threads=None):
+    """Compact transfer layout (include/sfb200.h, sfb_wire) of a read shard as numpy arrays: (arrays, seq_len_common),
+    or None when it does not apply (a mate with > 255 alignments, a walk of > 255 nodes, a read of > 65535 bases, or
+    so many records needing an explicit coverage / a wide node step that the plain layout is smaller)."""
+    p = _Packed(reads, threads)
+    try:
+        if p.status:
+            return None
+        arrays = {}
+        for k, (name, dt) in enumerate(zip(_lib.WIRE_ARRAYS, _lib.WIRE_DTYPES)):
+            arrays[name] = np.empty(p.nbytes[k] // np.dtype(dt).itemsize, dt)
+            if p.nbytes[k]:
+                p.copy_to(k, arrays[name].ctypes.data)
+        return arrays, p.seq_len_common
+    finally:
+        p.close()
 
 
-def _layout(arrays):
-    """Offsets of the arrays inside one arena (256-byte aligned), and the arena size."""
+def _layout(sizes):
+    """Offsets of the arrays (name -> bytes) inside one arena (256-byte aligned), and the arena size."""
     offs, pos = {}, 0
-    for k, a in arrays.items():
-        offs[k] = (pos, a.nbytes)
-        pos += (a.nbytes + 255) & ~255
+    for k, n in sizes.items():
+        offs[k] = (pos, int(n))
+        pos += (int(n) + 255) & ~255
     return offs, max(pos, 256)
 
 
@@ -197,23 +164,33 @@ class HostReads:
 
     def __init__(self, reads: Reads, pin=True, wire=True):
         self.reads = reads
-        packed = wire_arrays(reads) if wire else None
-        self.wire = packed is not None
-        arrays, self.seq_len_common = packed if packed else (None, 0)
-        if arrays is None:
-            arrays = {k: np.ascontiguousarray(getattr(reads, k)).reshape(-1) for k in READS_DEVICE_FIELDS}
-        self.offs, self.size = _layout(arrays)
-        self.arena = torch.empty(self.size, dtype=torch.uint8)
-        if pin:
-            self.arena = self.arena.pin_memory()
-        view = self.arena.numpy()
-        for k, (o, n) in self.offs.items():
-            if n:
-                view[o:o + n] = np.ascontiguousarray(arrays[k]).reshape(-1).view(np.uint8)
+        packed = _Packed(reads) if wire else None
+        try:
+            self.wire = packed is not None and packed.status == 0
+            if self.wire:
+                sizes = dict(zip(_lib.WIRE_ARRAYS, packed.nbytes))
+                self.seq_len_common = packed.seq_len_common
+                self.n_exc, self.n_wide, self.n_seq_exc, self.n_bins_exc = \
+                    (sizes[k] // 8 for k in ("exc_cov", "wide_idx", "seq_exc_idx", "bins_exc_idx"))
+            else:
+                arrays = {k: np.ascontiguousarray(getattr(reads, k)).reshape(-1) for k in READS_DEVICE_FIELDS}
+                sizes = {k: a.nbytes for k, a in arrays.items()}
+                self.seq_len_common = 0
+                self.n_exc, self.n_wide, self.n_seq_exc, self.n_bins_exc = len(reads.exc_cov), 0, 0, 0
+            self.offs, self.size = _layout(sizes)
+            self.arena = torch.empty(self.size, dtype=torch.uint8, pin_memory=bool(pin))
+            view = self.arena.numpy()
+            for k, (name, (o, n)) in enumerate(self.offs.items()):
+                if not n:
+                    continue
+                if self.wire:
+                    packed.copy_to(k, view.ctypes.data + o)
+                else:
+                    view[o:o + n] = arrays[name].view(np.uint8)
+        finally:
+            if packed is not None:
+                packed.close()
         self.n_groups, self.n_alns, self.n_records = reads.n_groups, reads.n_alns, reads.n_records
-        self.n_exc = len(arrays["exc_cov"])
-        self.n_wide, self.n_seq_exc, self.n_bins_exc = \
-            (len(arrays[k]) if self.wire else 0 for k in ("wide_idx", "seq_exc_idx", "bins_exc_idx"))
 
     def nbytes(self):
         return sum(n for _, n in self.offs.values())

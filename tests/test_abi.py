@@ -14,7 +14,7 @@ HEADER = open(os.path.join(ROOT, "include", "sfb200.h")).read()
 
 
 def declared_functions():
-    return sorted(set(re.findall(r"^\s*(?:int|const char\*|sfb_decoded\*|sfb_gfa\*|int64_t|void)\s+(sfb_[a-z0-9_]+)\s*\(", HEADER, re.M)))
+    return sorted(set(re.findall(r"^\s*(?:int|const char\*|sfb_decoded\*|sfb_gfa\*|sfb_packed\*|int64_t|void)\s+(sfb_[a-z0-9_]+)\s*\(", HEADER, re.M)))
 
 
 def test_header_declares_expected_entry_points():
