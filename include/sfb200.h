@@ -303,6 +303,15 @@ int64_t      sfb_packed_size(const sfb_packed* p, int which);
 int          sfb_packed_copy(const sfb_packed* p, int which, void* dst);
 void         sfb_packed_free(sfb_packed* p);
 
+/* ---- host-side analysis of the unassigned reads (no GPU involved) ---------------------------
+ * Cluster.min_strains_inference (json2csv.py:149-201, with canonical_tiny :63-71, check_incomp_comp :83-97, sublist
+ * :99-100) for every cluster: the walks of cluster c are walks clu_off[c] .. clu_off[c+1]-1, walk w is
+ * nodes[walk_off[w] .. walk_off[w+1]-1] (node ids as in the GFA).  Per cluster: size of the largest set of mutually
+ * incompatible walks, number of walks kept by the support filter, the same size among the kept walks, mean number of
+ * kept walks per node (NaN when none is kept); zeros for a cluster without walks.  Multi-threaded over clusters. */
+int sfb_min_strains(int64_t n_clusters, const int64_t* clu_off, const int64_t* walk_off, const int64_t* nodes,
+                    int n_threads, int64_t* before, int64_t* kept, int64_t* after, double* support);
+
 /* ---- host-side GFA loader (no GPU involved) ------------------------------------------------
  * Pangenome.build_pangenome + canonical + get_accession_number (json2csv.py:46-81, 223-298) over a memory-mapped
  * GFA.  sfb_gfa_size(which): 0 nodes, 1 paths, 2 path nodes, 3 (path, strain) entries, 4 strains, 5 bytes of strain

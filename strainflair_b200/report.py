@@ -8,7 +8,6 @@ reference is a ``set`` iteration order: here it is first-seen ord
 """
 import math
 import pickle
-import warnings
 
 import numpy as np
 
@@ -110,75 +109,27 @@ def cluster_records(graph, reads, res):
     return clusters
 
 
-def _oriented(walk):
-    if len(walk) == 1:
-        return walk
-    rising = sum(1 for a, b in zip(walk, walk[1:]) if b - a > 0)
-    return walk if rising / (len(walk) - 1) > 0.5 else walk[::-1]          # json2csv.py:63-71
-
-
-def _relation(a, b):
-    """1 if the two walks agree around a shared node, -1 if they share a node but disagree, 0 if disjoint
-    (json2csv.py:83-97; the pivot is the first element of the set intersection, as there)."""
-    shared = list(set(a) & set(b))
-    if not shared:
-        return 0
-    pivot = shared[0]
-    pos_b = [j for j, v in enumerate(b) if v == pivot]
-    for i in (i for i, v in enumerate(a) if v == pivot):
-        for j in pos_b:
-            left, right = min(i, j), min(len(a) - i, len(b) - j)
-            if a[i - left:i + right] == b[j - left:j + right]:
-                return 1
-    return -1
-
-
-def min_strains(walks):
-    """Lower bounds on the number of strains explaining a cluster's unassigned reads (json2csv.py:149-201):
-    (max clique of the incompatibility graph, reads kept by the support filter, max clique among them,
-    mean per-node support of the kept reads)."""
-    import networkx as nx
-    import scipy.signal
-    walks = [_oriented(w) for w in walks]
-    n = len(walks)
-    conflict = nx.Graph()
-    conflict.add_nodes_from(range(n))
-    friends = [[] for _ in range(n)]
-    for i in range(n):
-        for j in range(i + 1, n):
-            rel = _relation(walks[i], walks[j])
-            if rel < 0:
-                conflict.add_edge(i, j)
-            elif rel > 0:
-                friends[i].append(j)
-                friends[j].append(i)
-    biggest = lambda gr: max((len(c) for c in nx.clique.find_cliques(gr)), default=0)   # noqa: E731
-    before = biggest(conflict)
-    kept = []
-    for i in range(n):
-        mine = set(walks[i])
-        proper = [r for r in friends[i] if not (mine <= set(walks[r]) or set(walks[r]) <= mine)]
-        keep = False
-        if len(proper) >= 2:
-            support = [1] * len(walks[i])
-            for r in friends[i]:
-                for node in walks[r]:
-                    if node in mine:
-                        support[walks[i].index(node)] += 1
-            keep = len(scipy.signal.find_peaks(-np.asarray(support))[0]) == 0
-        if keep:
-            kept.append(walks[i])
-        else:
-            conflict.remove_node(i)
-    after = biggest(conflict)
-    tally = {}
-    for w in kept:
-        for node in w:
-            tally[node] = tally.get(node, 0) + 1
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        support = np.mean(list(tally.values()))
-    return before, len(kept), after, support
+def min_strains(cluster_walks, threads=None):
+    """Lower bounds on the number of strains explaining each cluster's unassigned reads (json2csv.py:149-201), native
+    (csrc/unassigned.cpp).  ``cluster_walks``: per cluster, the list of walks (lists of node ids).  Returns four
+    arrays over the clusters: largest clique of the incompatibility graph, reads kept by the support filter, largest
+    clique among them, mean per-node support of the kept reads (NaN when none)."""
+    import ctypes as C
+    import os
+    n = len(cluster_walks)
+    counts = np.fromiter((len(w) for w in cluster_walks), np.int64, n)
+    clu_off = np.concatenate([[0], np.cumsum(counts, dtype=np.int64)]).astype(np.int64)
+    lens = np.fromiter((len(w) for ws in cluster_walks for w in ws), np.int64, int(clu_off[-1]))
+    walk_off = np.concatenate([[0], np.cumsum(lens, dtype=np.int64)]).astype(np.int64)
+    nodes = np.fromiter((v for ws in cluster_walks for w in ws for v in w), np.int64, int(walk_off[-1]))
+    before, kept, after = (np.zeros(n, np.int64) for _ in range(3))
+    support = np.zeros(n, np.float64)
+    rc = _lib.load().sfb_min_strains(n, clu_off.ctypes.data, walk_off.ctypes.data, nodes.ctypes.data,
+                                     int(threads or len(os.sched_getaffinity(0))), before.ctypes.data, kept.ctypes.data,
+                                     after.ctypes.data, support.ctypes.data)
+    if rc:
+        raise _lib.SfbError(f"sfb_min_strains failed ({rc})")
+    return before, kept, after, support
 
 
 def write_unassigned(path, graph, clusters, strain_counts):
@@ -187,12 +138,11 @@ def write_unassigned(path, graph, clusters, strain_counts):
     with open(path, "w") as fh:
         fh.write("Clusters;" + "".join(f"{graph.strain_names[s]};" for s in keys)
                  + "nb_reads_unfilt;min_strains_unfilt;nb_reads_afterfilt;min_strains;mean_abund\n")
+        before, kept, after, support = min_strains([rec["unassigned_paths"] for rec in clusters])
         for cid, rec in enumerate(clusters):
-            before = kept = after = support = 0
-            if rec["count"] != 0:
-                before, kept, after, support = min_strains(rec["unassigned_paths"])
+            tail = f"{before[cid]};{kept[cid]};{after[cid]};{float(support[cid])}" if rec["count"] != 0 else "0;0;0;0"
             fh.write(f"Cluster_{cid};" + "".join(f"{int(strain_counts[cid, s])};" for s in keys)
-                     + f"{len(rec['unassigned_paths'])};{before};{kept};{after};{support}\n")
+                     + f"{len(rec['unassigned_paths'])};{tail}\n")
 
 
 def write_clusters_pickle(path, clusters):

@@ -249,3 +249,91 @@ def test_transfer_layout_round_trip_on_host(variant):
         # a shard whose exceptions would outweigh the saving falls back to the plain layout
         reads.walk_node[:] = rng.integers(0, graph.n_nodes, reads.n_records)
         assert engine.wire_arrays(reads) is None
+
+
+def _random_walk_sets(rng, n_clusters):
+    """Per cluster a handful of walks over a small node alphabet: sub-walks of a few 'haplotypes' (so that many agree),
+    mutated, reversed, with repeated nodes and cyclic shifts (so that the choice of the anchor node matters), node ids
+    from ranges that collide in CPython's set table (multiples of 8, huge ids, mixed)."""
+    out = []
+    for c in range(n_clusters):
+        style = c % 6
+        base = [1, 1000, 8, 2 ** 20, 2 ** 40, 7][style]
+        stride = [1, 1, 8, 64, 2 ** 31, 3][style]
+        alphabet = [base + stride * k for k in range(int(rng.integers(4, 40)))]
+        haps = []
+        for _ in range(int(rng.integers(1, 4))):
+            h = list(alphabet)
+            for _ in range(int(rng.integers(0, 4))):
+                h[int(rng.integers(len(h)))] = int(rng.choice(alphabet))           # repeated nodes
+            if rng.random() < 0.3:
+                k = int(rng.integers(1, len(h)))
+                h = h[k:] + h[:k]                                                  # cyclic shift
+            haps.append(h)
+        walks = []
+        for _ in range(int(rng.integers(0, 14))):
+            h = haps[int(rng.integers(len(haps)))]
+            i = int(rng.integers(len(h)))
+            w = h[i:i + int(rng.integers(1, 12))]
+            if rng.random() < 0.25:
+                w[int(rng.integers(len(w)))] = int(rng.choice(alphabet))
+            if rng.random() < 0.4:
+                w = w[::-1]
+            walks.append([int(v) for v in w])
+        out.append(walks)
+    return out
+
+
+def test_native_min_strains_matches_the_python_restatement():
+    """csrc/unassigned.cpp (CPython set order replayed, find_peaks and clique sizes restated) == oracle/report.py,
+    which runs the real set / scipy / networkx code of the reference's Cluster.min_strains_inference."""
+    from oracle import report as orp
+    from strainflair_b200 import report
+    rng = np.random.default_rng(77)
+    sets = _random_walk_sets(rng, 1500)
+    sets.append([])                                     # a cluster without unassigned reads
+    sets.append([[5]])                                  # one single-node walk
+    sets.append([[3, 2, 1], [1, 2, 3], [2, 3, 4], [9, 3, 4, 1]])
+    got = report.min_strains(sets, threads=3)
+    n_filtered = 0
+    for k, walks in enumerate(sets):
+        if not walks:
+            assert (got[0][k], got[1][k], got[2][k], got[3][k]) == (0, 0, 0, 0.0)
+            continue
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = orp.min_strains([list(w) for w in walks])
+        assert (int(got[0][k]), int(got[1][k]), int(got[2][k])) == tuple(int(v) for v in want[:3]), (k, walks)
+        assert (np.isnan(got[3][k]) and np.isnan(want[3])) or got[3][k] == want[3], (k, walks)
+        n_filtered += want[1] > 0
+    assert n_filtered > 50                               # the support filter keeps something often enough to be tested
+    one = report.min_strains(sets, threads=1)
+    assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(got, one))
+
+
+def test_relation_pivot_follows_cpython_set_order():
+    """Pairs of walks whose verdict depends on which shared node anchors the comparison: the native code must pick
+    CPython's (first element of the set intersection in hash-table order)."""
+    from oracle import report as orp
+    from strainflair_b200 import report
+    rng = np.random.default_rng(3)
+    n_dep = 0
+    for _ in range(3000):
+        k = int(rng.integers(3, 30))
+        ids = rng.choice(np.arange(1, 400) * int(rng.choice([1, 8, 16, 1024])), k, replace=False).tolist()
+        a = ids[:int(rng.integers(2, k + 1))]
+        b = list(a)
+        rng.shuffle(b)
+        b = b[:int(rng.integers(1, len(b) + 1))] + [int(v) + 100000 for v in ids[:int(rng.integers(0, 3))]]
+        verdicts = set()
+        shared = set(a) & set(b)
+        for pivot in shared:                             # what each possible anchor would say
+            i, j = a.index(pivot), b.index(pivot)
+            left, right = min(i, j), min(len(a) - i, len(b) - j)
+            verdicts.add(a[i - left:i + right] == b[j - left:j + right])
+        n_dep += len(verdicts) > 1
+        want = orp.compat(orp.orient_small(a), orp.orient_small(b))
+        before = int(report.min_strains([[a, b]], threads=1)[0][0])
+        assert before == (2 if want == -1 else 1), (a, b)
+    assert n_dep > 100
