@@ -6,7 +6,6 @@ gene table (json2csv.py:399-474), five error-distribution tables (:515-526), per
 stdout summary (:1346-1356).  The only free choice is the order of the strain columns, which in the
 reference is a ``set`` iteration order: here it is first-seen order.
 """
-import math
 import pickle
 
 import numpy as np
@@ -22,8 +21,7 @@ HIST_FILES = ("mappingscore_freq", "identityscore_freq", "subst_freq", "indel_fr
 
 def _f(x):
     """str() of a Python/numpy float as the reference's f-strings print it."""
-    x = float(x)
-    return "nan" if math.isnan(x) else repr(x)
+    return repr(float(x))              # repr(nan) == "nan"
 
 
 def gene_table_lines(graph, res):
@@ -34,7 +32,27 @@ def gene_table_lines(graph, res):
     yield "".join(f"{names[s]};" for s in keys) + ";".join(GENE_COLS) + "\n"
     t = res.table
     po, pid, pcnt = graph.pstr_off, graph.pstr_id, graph.pstr_cnt
-    for p in range(graph.n_paths):
+    P = graph.n_paths
+    col = np.full(max(len(graph.strain_names), 1), -1, np.int64)
+    col[np.asarray(keys, np.int64)] = np.arange(len(keys))
+    if P and len(keys) and (len(pid) == 0 or (col[pid].min() >= 0 and pcnt.max() < 10 and pcnt.min() >= 0)):
+        # the usual case (every strain in the header, single-digit copy counts): strain cells of all rows at once
+        cells = np.full((P, 2 * len(keys)), ord(";"), np.uint8)
+        cells[:, 0::2] = ord("0")
+        row = np.repeat(np.arange(P), np.diff(po))
+        cells[row, 2 * col[pid]] = ord("0") + pcnt.astype(np.uint8)
+        strain_cells = cells.tobytes().decode("ascii")
+        width = 2 * len(keys)
+        uniq_all, multi_all = res.uniq_reads.astype(np.int64).tolist(), (np.asarray(res.mult_hits) > 0).tolist()
+        cluster_all, seq_all, rows = graph.path_cluster.tolist(), graph.path_seq_len.tolist(), t.tolist()
+        for p in range(P):
+            uniq, multi_touched, c, v = uniq_all[p], multi_all[p], cluster_all[p], rows[p]
+            yield (strain_cells[p * width:(p + 1) * width]
+                   + f"{'None' if c < 0 else c};{seq_all[p]};{uniq};{_f(v[0]) if uniq else '0'};"
+                     f"{_f(v[1]) if multi_touched else uniq};{_f(v[2]) if (uniq or multi_touched) else '0'};"
+                     f"{_f(v[3])};{_f(v[4])};{_f(v[5])};{_f(v[6])};{_f(v[7])}\n")
+        return
+    for p in range(P):
         cnt = dict.fromkeys(keys, 0)
         for e in range(int(po[p]), int(po[p + 1])):
             s = int(pid[e])

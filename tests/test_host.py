@@ -337,3 +337,30 @@ def test_relation_pivot_follows_cpython_set_order():
         before = int(report.min_strains([[a, b]], threads=1)[0][0])
         assert before == (2 if want == -1 else 1), (a, b)
     assert n_dep > 100
+
+
+@pytest.mark.parametrize("d", CASES[:4], ids=os.path.basename)
+def test_gene_table_writer_matches_oracle_text(d):
+    """report.gene_table_lines (vectorised strain cells, and the row-by-row path for ragged rows / large copy counts)
+    prints what the oracle prints, given the oracle's numbers."""
+    import types
+    from oracle import abundance as oa
+    from oracle import report as orp
+    from strainflair_b200 import report
+    files = [os.path.join(d, f) for f in ("graph.gfa", "reads.json", "dict_clusters.pickle")]
+    g = gfa.load_graph(files[0], files[2])
+    go = og.load_graph(files[0], files[2])
+    orc = oa.AbundanceOracle(go, od.decode_json(files[1], go, 0.95))
+    orc.run()
+    rows = orp.gene_rows(orc)
+    cols = ("nb_uniq_mapped_normalized", "nb_multimapped", "nb_multimapped_normalized", "mean_abund_uniq",
+            "mean_abund_uniq_nz", "mean_abund_multiple", "mean_abund_multiple_nz", "ratio_covered_nodes")
+    table = np.array([[float(r[k]) for k in cols] for r in rows], np.float64).reshape(len(rows), 8)
+    touched = np.array([not isinstance(m, int) for m in orc.mult_reads], np.uint8)      # the reference's int 0 until touched
+    res = types.SimpleNamespace(table=table, uniq_reads=np.array([int(u) for u in orc.uniq_reads], np.int64), mult_hits=touched)
+    assert "".join(report.gene_table_lines(g, res)) == orp.gene_table_text(orc)
+    # the same rows through the row-by-row writer (a copy count of 12 switches the vectorised cells off)
+    big = int(g.pstr_cnt[0])
+    g.pstr_cnt[0] = go["pstr_cnt"][0] = 12
+    assert "".join(report.gene_table_lines(g, res)) == orp.gene_table_text(orc)
+    g.pstr_cnt[0] = go["pstr_cnt"][0] = big
