@@ -10,47 +10,14 @@
 
 namespace sfb {
 
-constexpr int kKeep = 8;   // matches kept in registers; longer lists are produced by a second sweep
+#ifndef SFB_MATCH_KEEP
+#define SFB_MATCH_KEEP 10     /* measured: 9-10 best on C3 (no list of its 2-9 haplotypes falls to phase C); more shared memory costs L1 */
+#endif
+constexpr int kKeep = SFB_MATCH_KEEP;   // matches staged per alignment; longer lists are produced by a second sweep
 
 struct MatchStats {
     int cand, cmp;
 };
-
-// One orientation: candidates are the occurrences of `anchor` (= the first node of the oriented walk); `second` is the
-// oriented walk's second node and step = +1 (walk as is) or -1 (reversed walk, read from its last record backwards).
-template <bool kEmit>
-__device__ __forceinline__ int sweep_one(const sfb_graph& g, const sfb_reads& r, i64 w_first, int step, int L, int anchor,
-                                         int second, uint32_t flag, int n, uint2* keep, uint2* out, MatchStats& st) {
-    const int2* occ = reinterpret_cast<const int2*>(g.occ_pair);
-    for (int o = g.occ_off[anchor], oe = g.occ_off[anchor + 1]; o < oe; ++o) {
-        const int2 e = occ[o];
-        st.cand += 1;
-        if (L > 1) {
-            st.cmp += 1;
-            if (e.y != second) continue;                  // successor differs (or path end, -1): rejected from the index
-            int i = 2;
-            for (; i < L; ++i)
-                if (g.slot_node[e.x + i] != r.walk_node[w_first + (i64)step * i]) break;   // sentinel stops overruns
-            st.cmp += min(i, L - 1) - 1;
-            if (i < L) continue;
-        }
-        const uint2 t = make_uint2((uint32_t)e.x | flag, (uint32_t)path_of_slot(g, e.x));
-        if (kEmit) out[n] = t; else if (n < kKeep) keep[n] = t;
-        ++n;
-    }
-    return n;
-}
-
-template <bool kEmit>
-__device__ __forceinline__ int match_sweep(const sfb_graph& g, const sfb_reads& r, i64 w0, int L, uint2* keep,
-                                           uint2* out, MatchStats& st) {
-    const int first = r.walk_node[w0];
-    if (L == 1) return sweep_one<kEmit>(g, r, w0, 1, 1, first, 0, 0u, 0, keep, out, st);
-    const int last = r.walk_node[w0 + L - 1];
-    int n = sweep_one<kEmit>(g, r, w0, 1, L, first, r.walk_node[w0 + 1], 0u, 0, keep, out, st);
-    // reversed walk (json2csv.py:861-866): starts at walk[L-1], continues with walk[L-2] ...
-    return sweep_one<kEmit>(g, r, w0 + L - 1, -1, L, last, r.walk_node[w0 + L - 2], SFB_MATCH_REV, n, keep, out, st);
-}
 
 // Candidate-parallel kernel, two phases per warp pass (the kernel is bound by memory latency, so the structure
 // minimises dependent round trips and keeps lanes dense):
@@ -62,7 +29,9 @@ __device__ __forceinline__ int match_sweep(const sfb_graph& g, const sfb_reads& 
 //   B  The list is drained 32 survivors at a time, all lanes busy: the remaining walk positions are fetched
 //      together and compared, matches get their path id and their rank inside their alignment (ballot +
 //      __match_any over the owner lane; candidate order = the reference's match order) and are staged in shared
-//      memory, kKeep per alignment; longer lists are redone serially by the owner lane.
+//      memory, kKeep per alignment.
+//   C  Alignments with more than kKeep matches are redone by the whole warp, one at a time, one lane per candidate,
+//      and written straight to their place in match_buf.
 #ifndef SFB_MATCH_KU
 #define SFB_MATCH_KU 4
 #endif
@@ -216,22 +185,69 @@ __global__ void __launch_bounds__(256, SFB_MATCH_MINBLK) k_match(sfb_graph g, sf
         tuples += n;
         const unsigned need = n > 1 ? (unsigned)n : 0u;
         const u64 pos = warp_claim(w.cursor, need);
+        const bool fits = pos + need <= (u64)w.match_cap;
         if (live) {
             if (n == 0) {
                 aln_match[a] = make_uint2(SFB_MATCH_NONE, 0u);
             } else if (n == 1) {
                 aln_match[a] = s_stage[wi][lane][0];
-            } else if (pos + need <= (u64)w.match_cap) {
-                if (n <= kKeep) {
+            } else if (fits) {
+                if (n <= kKeep)
                     for (int q = 0; q < n; ++q) match_buf[pos + q] = s_stage[wi][lane][q];
-                } else {
-                    MatchStats scratch{0, 0};
-                    match_sweep<true>(g, r, w0, L, nullptr, match_buf + pos, scratch);
-                }
                 aln_match[a] = make_uint2(SFB_MATCH_MULTI | (uint32_t)pos, (uint32_t)n);
             } else {
                 aln_match[a] = make_uint2(SFB_MATCH_NONE, 0u);
                 SFB_COUNT(sc, SFB_C_MATCH_OVERFLOW, (int)need);
+            }
+        }
+        // ---- phase C: lists longer than kKeep are produced again by the whole warp, one alignment at a time, one
+        //      lane per candidate, straight into match_buf (a lane doing it alone would chain every load) ----
+        unsigned big = __ballot_sync(0xffffffffu, live && n > kKeep && fits);
+        while (big) {
+            const int j = __ffs(big) - 1;
+            big &= big - 1;
+            // the alignment's data again from (cached) global memory: keeping it in registers until here would spill
+            const u64 o_pos = __shfl_sync(0xffffffffu, pos, j);
+            const i64 o_w0 = r.aln_walk_off[base + j];
+            const int o_L = (int)(r.aln_walk_off[base + j + 1] - o_w0);
+            const int o_first = r.walk_node[o_w0], o_last = r.walk_node[o_w0 + o_L - 1];
+            const int o_second = o_L > 1 ? r.walk_node[o_w0 + 1] : 0, o_penult = o_L > 1 ? r.walk_node[o_w0 + o_L - 2] : 0;
+            const int o_fo = g.occ_off[o_first], o_fcnt = g.occ_off[o_first + 1] - o_fo;
+            const int o_ro = g.occ_off[o_last], o_rcnt = o_L > 1 ? g.occ_off[o_last + 1] - o_ro : 0;
+            int written = 0;
+            for (int c0 = 0; c0 < o_fcnt + o_rcnt; c0 += 32) {          // forward candidates first, then reverse
+                const int c = c0 + lane;
+                const bool in = c < o_fcnt + o_rcnt;
+                const bool rev = c >= o_fcnt;
+                bool ok = false;
+                int slot = 0;
+                if (in) {
+                    const int2 e = occ[rev ? o_ro + (c - o_fcnt) : o_fo + c];
+                    slot = e.x;
+                    ok = o_L == 1 || e.y == (rev ? o_penult : o_second);
+                    if (ok && o_L > 2) {
+                        const i64 wf = rev ? o_w0 + o_L - 1 : o_w0;
+                        const int step = rev ? -1 : 1;
+                        int pn[kU], wn[kU];
+#pragma unroll
+                        for (int u = 0; u < kU; ++u) {
+                            pn[u] = wn[u] = 0;
+                            if (u + 2 < o_L) {
+                                pn[u] = g.slot_node[min(slot + u + 2, last_slot)];
+                                wn[u] = r.walk_node[wf + (i64)step * (u + 2)];
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < kU; ++u) ok = ok && pn[u] == wn[u];
+                        for (int i = kU + 2; i < o_L && ok; ++i)
+                            ok = g.slot_node[min(slot + i, last_slot)] == r.walk_node[wf + (i64)step * i];
+                    }
+                }
+                const unsigned ball = __ballot_sync(0xffffffffu, ok);
+                if (ok)
+                    match_buf[o_pos + written + __popc(ball & below)] =
+                        make_uint2((uint32_t)slot | (rev ? SFB_MATCH_REV : 0u), (uint32_t)path_of_slot(g, slot));
+                written += __popc(ball);
             }
         }
         __syncwarp();

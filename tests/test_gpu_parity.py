@@ -133,6 +133,73 @@ def test_match_lists_equal_oracle():
         assert flags == sorted(flags)
 
 
+def _repetitive_case(seed, n_paths=40, alphabet=4, n_walks=4000):
+    """Paths over a tiny node alphabet (repeated nodes, palindromes, many occurrences per node) and walks cut from
+    them in both orientations, some run past either path end or altered: every corner of get_matching_path
+    (json2csv.py:341-363) and of its reversed-walk twin (:861-866) -- several positions in one path, more than
+    eight matches, overruns at slot 0 and at the last slot."""
+    rng = np.random.default_rng(seed)
+    paths, seen = [], set()
+    while len(paths) < n_paths:
+        n = int(rng.integers(1, 14))
+        pth = tuple(int(x) for x in rng.integers(0, alphabet, n))
+        if pth not in seen:                    # identical contents are one Path in the reference (:260)
+            seen.add(pth)
+            paths.append(list(pth))
+    node_len = rng.integers(1, 40, alphabet).astype(np.int32)
+    plen = np.array([len(x) for x in paths])
+    path_off = np.concatenate(([0], np.cumsum(plen))).astype(np.int64)
+    path_nodes = np.concatenate(paths).astype(np.int32)
+    P = len(paths)
+    graph = Graph(
+        node_ids=np.arange(1, alphabet + 1), node_len=node_len, path_off=path_off, path_nodes=path_nodes,
+        path_seq_len=np.array([int(node_len[x].sum()) for x in paths]), pstr_off=np.arange(P + 1),
+        pstr_id=(np.arange(P) % 3).astype(np.int32), pstr_cnt=np.ones(P, np.int32),
+        path_cluster=np.zeros(P, np.int32), clu_off=np.array([0, P]), clu_paths=np.arange(P, dtype=np.int32),
+        strain_names=["NC_1.1", "NC_2.1", "NC_3.1"], header_strains=[0, 1, 2], path_names=None)
+    walks = []
+    for _ in range(n_walks):
+        pth = paths[int(rng.integers(0, P))]
+        i = int(rng.integers(0, len(pth)))
+        j = int(rng.integers(i + 1, len(pth) + 1))
+        wk = list(pth[i:j])
+        kind = rng.random()
+        if kind < 0.4:
+            wk = wk[::-1]
+        elif kind < 0.55:
+            wk = wk + [int(rng.integers(0, alphabet))]                    # past the path end (or onto another path)
+        elif kind < 0.7:
+            wk = [int(rng.integers(0, alphabet))] + wk
+        elif kind < 0.8:
+            wk[int(rng.integers(0, len(wk)))] = int(rng.integers(0, alphabet))
+        walks.append(wk)
+    A = len(walks)
+    wl = np.array([len(x) for x in walks])
+    walk_node = np.concatenate(walks).astype(np.int32)
+    reads = Reads(
+        grp_nmates=np.ones(A, np.uint8), grp_aln_off=np.minimum(np.arange(2 * A + 1) + 1, 2 * A + 1) // 2,
+        mate_seq_len=np.full(2 * A, 100, np.int32), aln_walk_off=np.concatenate(([0], np.cumsum(wl))),
+        aln_read_len=np.full(A, 100, np.int32), aln_bins=np.zeros((A, 5), np.uint8), walk_node=walk_node,
+        walk_alen=(1 | (node_len[walk_node].astype(np.int32) << 16)), exc_cov=np.zeros(0), mate_names=None)
+    return graph, reads
+
+
+@pytest.mark.parametrize("seed,alphabet", [(1, 2), (2, 3), (3, 9), (4, 20), (5, 40)])
+def test_match_corner_cases_equal_oracle(seed, alphabet):
+    need_gpu()
+    graph, reads = _repetitive_case(seed, alphabet=alphabet)
+    res = engine.abundance_pass(graph, reads)
+    orc = oa.AbundanceOracle(graph.as_dict(), reads.as_dict())
+    most = 0
+    for a in range(reads.n_alns):
+        mine = engine.decode_matches(res, a)
+        assert [(p, pos) for p, pos, _ in mine] == orc.match(a), (a, reads.walk_node[reads.aln_walk_off[a]:reads.aln_walk_off[a + 1]])
+        most = max(most, len(mine))
+    if alphabet <= 3:
+        assert most > 8                           # the serial path for long match lists was taken
+    check_against_oracle(graph, reads, res, orc.run())
+
+
 def test_match_buffer_regrows():
     need_gpu()
     graph, reads = synth.make_config("tiny")

@@ -7,11 +7,14 @@ import torch
 from strainflair_b200 import engine, synth
 
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 0.2
-gkw, rkw = synth.CONFIGS["c3"]
-graph = synth.make_graph(synth.SEED0 + 2, **gkw)
-reads = synth.make_reads(graph, synth.SEED0 + 1002, n_pairs=int(rkw["n_pairs"] * scale), read_len=150)
+cfg = sys.argv[2] if len(sys.argv) > 2 else "c3"
+gkw, rkw = synth.CONFIGS[cfg]
+idx = list(synth.CONFIGS).index(cfg)
+graph = synth.make_graph(synth.SEED0 + idx, **gkw)
+reads = synth.make_reads(graph, synth.SEED0 + 1000 + idx, n_pairs=int(rkw["n_pairs"] * scale), read_len=150)
 eng = engine.AbundanceEngine(graph, "cuda:0")
 dr = eng.upload(engine.HostReads(reads))
+eng.match_cap_hint = int(os.environ.get("SFB_CAP_MULT", "2")) * reads.n_alns
 work = eng._work_for(dr)
 stages = ("match", "classify", "pass1_scatter", "pass2_resolve", "pass2_scatter")
 tot = {k: 0.0 for k in stages}
@@ -30,4 +33,7 @@ for it in range(8):
     if it >= 3:
         for k, st in enumerate(stages):
             tot[st] += evs[k].elapsed_time(evs[k + 1]) / 5
-print(os.path.basename(os.environ.get("SFB200_LIB", "default")), {k: round(v, 4) for k, v in tot.items()}, "alns", reads.n_alns, flush=True)
+from strainflair_b200 import _lib
+cn = dict(zip(_lib.COUNTER_NAMES, eng.acc.counters.cpu().tolist()))
+chk = (cn["MATCH_OVERFLOW"], cn["ST_TUPLES"], cn["ST_CAND"], cn["ASSIGNED_U"], int(eng.acc.uniq_reads.sum().item()), int(work.t["aln_match"][:reads.n_alns].sum().item()) & 0xffffffff)
+print(os.path.basename(os.environ.get("SFB200_LIB", "default")), os.environ.get("SFB_ENTRY8", ""), {k: round(v, 4) for k, v in tot.items()}, cfg, "alns", reads.n_alns, "check", chk, flush=True)
