@@ -26,7 +26,7 @@ UNIT = "reads/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", default="c3", help="synthetic workload (strainflair_b200/synth.py CONFIGS)")
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the config's read pairs per rank")
@@ -34,7 +34,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-pairs", type=int, default=160_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-shards", type=int, default=8)
+    ap.add_argument("--e2e-shards", type=int, default=4)
     ap.add_argument("--no-det", action="store_true", help="skip the order-independent-mode measurement")
     return ap.parse_args()
 
@@ -195,15 +195,58 @@ def run_reference(args):
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
+    """SM clock, power and throttle reasons of one GPU, sampled DURING the timed region: NVML in-process every 2 ms
+    (a timed region of a few steps is tens of milliseconds), `nvidia-smi` every 100 ms when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _nvml_row(self):
+        n, h = self.nvml, self.handle
+        sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+        try:
+            power = n.nvmlDeviceGetPowerUsage(h) / 1000.0
+        except Exception:
+            power = 0.0
+        try:
+            bits = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            bits = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        flag = lambda name, old: bool(bits & getattr(n, name, getattr(n, old, 0)))   # noqa: E731
+        act = lambda v: "Active" if v else "Not Active"                              # noqa: E731
+        return [str(sm), str(self.max_sm), str(power),
+                act(flag("nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown")),
+                act(flag("nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown")),
+                act(flag("nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown")),
+                act(flag("nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap"))]
 
     def run(self):
         while not self.stop_flag:
+            if self.nvml is not None:
+                try:
+                    self.rows.append(self._nvml_row())
+                except Exception:
+                    self.nvml = None
+                    continue
+                time.sleep(0.002)
+                continue
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
@@ -227,7 +270,7 @@ class ClockSampler(threading.Thread):
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -362,22 +405,46 @@ def run_ours(args):
         shards = [engine.HostReads(reads.slice_groups(a, b), pin=True) for a, b in cuts]
         h2d = sum(s_.nbytes() for s_ in shards)
         del host
+        from collections import deque
         eng.run_stream(shards)
         eng.run_stream(shards)
         barrier()
         torch.cuda.synchronize()
+        # one step alone: upload, kernels, read-back, nothing else in flight (latency of a single data set)
+        t0 = time.perf_counter()
+        for _ in range(min(args.steps, 5)):
+            res = eng.run_stream(shards)
+        torch.cuda.synchronize()
+        t_single = torch.tensor([(time.perf_counter() - t0) / min(args.steps, 5)], dtype=torch.float64, device=device)
+        # steady state, two steps in flight (submit / collect): the uploads of step k+1 run under pass 2 of step k,
+        # every step on its own accumulators and device buffers; every step's inputs are copied from pinned host
+        # memory and its results read back inside the timed region
+        pending = deque()
+        for _ in range(2):
+            pending.append(eng.submit(shards, depth=2))
+        while pending:
+            eng.collect(pending.popleft())
+        barrier()
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            res = eng.run_stream(shards)     # returns what the reports need: table, per-path counters, histograms
+            pending.append(eng.submit(shards, depth=2))
+            if len(pending) == 2:
+                res = eng.collect(pending.popleft())   # what the reports need: table, per-path counters, histograms
+        while pending:
+            res = eng.collect(pending.popleft())
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t_single, op=dist.ReduceOp.MAX)
         dt = float(t.item())
+        assert res.C["NB_READS"] == stats.C["NB_READS"]
         d2h = eng.d2h_bytes(keep_slots=False) * world
         e2e = {"value": total_reads * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "shards": args.e2e_shards,
-               "d2h_bytes_per_step": d2h, "ms_per_step": dt / args.steps * 1e3}
+               "d2h_bytes_per_step": d2h, "ms_per_step": dt / args.steps * 1e3, "steps_in_flight": 2,
+               "single_step_ms": float(t_single.item()) * 1e3}
 
     if rank == 0:
         Cr = dict(stats.C)

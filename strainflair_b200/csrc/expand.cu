@@ -105,35 +105,79 @@ __global__ void k_apply_bins_exceptions(sfb_wire w, uint8_t* out) {
         for (int q = 0; q < SFB_N_HIST; ++q) out[w.bins_exc_idx[k] * SFB_N_HIST + q] = w.bins_exc_val[k * SFB_N_HIST + q];
 }
 // Node ids and packed coverage words (aligned bases | node length << 16, see record_cov) of every record.
-// One thread per walk: a walk is a handful of records, the threads of a warp cover one contiguous stretch.
-__global__ void __launch_bounds__(256) k_expand_walks(sfb_wire w, const i64* __restrict__ walk_off,
-                                                      const int32_t* __restrict__ node_len, int32_t* __restrict__ walk_node,
-                                                      int32_t* __restrict__ walk_alen) {
-    for (i64 a = (i64)blockIdx.x * blockDim.x + threadIdx.x; a < w.n_alns; a += (i64)gridDim.x * blockDim.x) {
-        const i64 lo = walk_off[a], hi = walk_off[a + 1];
-        int32_t node = w.aln_node0[a];
-        for (i64 r = lo; r < hi; ++r) {
-            if (r > lo) {
-                const int step = w.walk_step[r];
-                if (step != -128) {
-                    node += step;
-                } else {                         // wide step: binary search of the record in the (short) list
-                    i64 x = 0, y = w.n_wide;
-                    while (x < y) {
-                        const i64 mid = (x + y) >> 1;
-                        if (w.wide_idx[mid] < r) x = mid + 1;
-                        else y = mid;
+// A block takes 256 consecutive walks = one contiguous stretch of records.  One thread per walk sums the steps along
+// its walk (a handful of records) and gathers the node lengths, writing into a shared-memory image of the stretch;
+// the block then stores the image with coalesced 4-byte rows (a thread writing its own 6 records straight to global
+// memory touches 32 sectors per store instruction).  Stretches that do not fit the image are written directly.
+constexpr int kWalkTile = 256;          // walks per block pass
+constexpr int kWalkImage = 2560;        // records of the shared-memory image (mean walk: 5-7 records)
+
+__device__ __forceinline__ int32_t wide_node_of(const sfb_wire& w, i64 r) {
+    i64 x = 0, y = w.n_wide;            // wide step: binary search of the record in the (short) list
+    while (x < y) {
+        const i64 mid = (x + y) >> 1;
+        if (w.wide_idx[mid] < r) x = mid + 1;
+        else y = mid;
+    }
+    return w.wide_node[x];
+}
+
+__global__ void __launch_bounds__(kWalkTile) k_expand_walks(sfb_wire w, const i64* __restrict__ walk_off,
+                                                            const int32_t* __restrict__ node_len,
+                                                            int32_t* __restrict__ walk_node, int32_t* __restrict__ walk_alen) {
+    __shared__ int32_t s_node[kWalkImage];
+    __shared__ int32_t s_alen[kWalkImage];
+    const i64 n_tiles = (w.n_alns + kWalkTile - 1) / kWalkTile;
+    for (i64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const i64 a0 = tile * kWalkTile;
+        const i64 a1 = a0 + kWalkTile < (i64)w.n_alns ? a0 + kWalkTile : (i64)w.n_alns;
+        const i64 r0 = walk_off[a0], r1 = walk_off[a1];
+        const bool staged = r1 - r0 <= kWalkImage;
+        const i64 a = a0 + threadIdx.x;
+        if (a < a1) {
+            const i64 lo = walk_off[a], hi = walk_off[a + 1];
+            int32_t node = w.aln_node0[a];
+            const int32_t al_first = w.aln_al_first[a], al_last = w.aln_al_last[a];
+            // eight records at a time: their steps, then their node lengths, are loaded together (a record-by-record
+            // loop would chain two dependent loads per record)
+            for (i64 c = lo; c < hi; c += 8) {
+                int st[8];
+                int32_t nd[8], nl[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) st[k] = (c + k < hi && c + k > lo) ? (int)w.walk_step[c + k] : 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (c + k < hi && c + k > lo) node = st[k] != -128 ? node + st[k] : wide_node_of(w, c + k);
+                    nd[k] = node;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) nl[k] = c + k < hi ? node_len[nd[k]] : 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const i64 r = c + k;
+                    if (r >= hi) break;
+                    // first / last record: the shipped byte; in between the node is covered completely.  Records with
+                    // an explicit coverage (byte 255, or listed) are overwritten by k_apply_exceptions.
+                    const int32_t al = r == lo ? al_first : (r == hi - 1 ? al_last : (nl[k] & 0xFFFF));
+                    if (staged) {
+                        s_node[r - r0] = nd[k];
+                        s_alen[r - r0] = al | (nl[k] << 16);
+                    } else {
+                        walk_node[r] = nd[k];
+                        walk_alen[r] = al | (nl[k] << 16);
                     }
-                    node = w.wide_node[x];
                 }
             }
-            const int32_t nl = node_len[node];
-            // first / last record: the shipped byte; in between the node is covered completely.  Records with an
-            // explicit coverage (byte 255, or listed) are overwritten by k_apply_exceptions.
-            const int32_t al = r == lo ? (int32_t)w.aln_al_first[a] : (r == hi - 1 ? (int32_t)w.aln_al_last[a] : (nl & 0xFFFF));
-            walk_node[r] = node;
-            walk_alen[r] = al | (nl << 16);
         }
+        __syncthreads();
+        if (staged) {
+            const int n = (int)(r1 - r0);
+            for (int i = threadIdx.x; i < n; i += kWalkTile) {
+                walk_node[r0 + i] = s_node[i];
+                walk_alen[r0 + i] = s_alen[i];
+            }
+        }
+        __syncthreads();
     }
 }
 __global__ void k_apply_exceptions(const i64* exc_idx, i64 n_exc, int32_t* walk_alen) {
@@ -166,7 +210,7 @@ int launch_expand(const sfb_wire* w, const int32_t* node_len, const sfb_reads* d
     if (w->n_seq_exc) k_apply_seq_exceptions<<<blocks_for(w->n_seq_exc, 256), 256, 0, st>>>(*w, mate_seq_len);
     if (w->n_alns) k_expand_bins<<<kSMs * 8, 256, 0, st>>>(*w, aln_bins);
     if (w->n_bins_exc) k_apply_bins_exceptions<<<blocks_for(w->n_bins_exc, 256), 256, 0, st>>>(*w, aln_bins);
-    if (w->n_records) k_expand_walks<<<kSMs * 8, 256, 0, st>>>(*w, aln_walk_off, node_len, walk_node, walk_alen);
+    if (w->n_records) k_expand_walks<<<kSMs * 8, kWalkTile, 0, st>>>(*w, aln_walk_off, node_len, walk_node, walk_alen);
     if (w->n_exc) k_apply_exceptions<<<blocks_for(w->n_exc, 256), 256, 0, st>>>((const i64*)w->exc_idx, w->n_exc, walk_alen);
     return check_launch("expand_reads");
 }

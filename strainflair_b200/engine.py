@@ -481,58 +481,115 @@ class AbundanceEngine:
         self._arena, self._wide = dr.arena, dr.wide
         return dr
 
-    def run_stream(self, shards):
-        """End-to-end pass over a data set staged as several HostReads shards (read groups split contiguously):
-        the H2D copy of shard k+1 overlaps with match / classify / pass-1 scatter of shard k; pass 2 runs once
-        every shard has contributed to ``uniq_reads``.  Device buffers are kept across calls.  Returns the
-        per-path results (no per-group codes)."""
-        import torch.distributed as dist
+    # ---- end-to-end pass over staged shards ------------------------------------------------
+    class _Job:
+        """One run of the pass in flight (``submit`` ... ``collect``): its own accumulators, per-shard device buffers,
+        result table and pinned read-back buffers, so that two jobs can overlap."""
+
+        def __init__(self, eng):
+            self.acc = Accum(eng.dg, eng.deterministic)
+            self.table = torch.empty_like(eng.table)
+            self.slots, self.stage, self.done, self.shards, self.live = {}, None, None, None, None
+
+    def _job_context(self, depth):
         if getattr(self, "_copy", None) is None:
             self._copy = torch.cuda.Stream(device=self.device)
-            self._slots = {}
+            self._jobs, self._next_job = [], 0
+        while len(self._jobs) < depth:
+            job = AbundanceEngine._Job(self)
+            if not self._jobs:                          # the first context is the engine's own set of buffers
+                job.acc, job.table = self.acc, self.table
+            self._jobs.append(job)
+        job = self._jobs[self._next_job % depth]
+        self._next_job += 1
+        return job
+
+    def submit(self, shards, depth=2, _reuse=None):
+        """Enqueue one whole pass over a data set staged as several HostReads shards (read groups split contiguously)
+        and the read-back of its results; returns a job for ``collect``.  Nothing here waits for the GPU: the H2D copy
+        of shard k+1 overlaps with match / classify / pass-1 scatter of shard k, pass 2 runs once every shard has
+        contributed to ``uniq_reads``, and -- with ``depth`` jobs in flight, each on its own buffers -- the uploads
+        of the next job overlap with pass 2 of this one."""
+        import torch.distributed as dist
+        job = _reuse if _reuse is not None else self._job_context(depth)
+        if job.done is not None:
+            job.done.synchronize()                  # the job that used these buffers before must have finished
         main = torch.cuda.current_stream()
+        self.acc, self.table = job.acc, job.table
+        self.acc.zero()
+        if job.done is not None:
+            self._copy.wait_event(job.done)         # its buffers are free again
+        live = []
+        for k, host in enumerate(shards):
+            slot = job.slots.setdefault(k, {})
+            with torch.cuda.stream(self._copy):
+                dr = DeviceReads(host, self.device, slot.get("arena"), slot.get("wide"), self.node_len, expand=False)
+                arrived = torch.cuda.Event()
+                arrived.record(self._copy)
+            slot["arena"] = dr.arena
+            main.wait_event(arrived)
+            dr.expand()
+            slot["wide"] = dr.wide
+            cap = max(slot.get("cap", 0), 2 * dr.n_alns + 1024)
+            work = slot.get("work")
+            if work is None or work.n_groups < dr.n_groups or work.n_alns < dr.n_alns or work.match_cap < cap:
+                work = slot["work"] = Work(dr.n_groups, dr.n_alns, cap, self.device)
+            work.reset()
+            self.match(dr, work)
+            self.classify(dr, work)
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side):
+                self.pass1_scatter(dr, work)
+            live.append((dr, work))
+        uniq_global = None
+        if self.comm is not None:
+            uniq_global = self.acc.uniq_reads.clone()
+            dist.all_reduce(uniq_global, group=self.comm)
+        for dr, work in live:
+            self.pass2_resolve(dr, work, uniq_global)
+        main.wait_stream(self.side)
+        for dr, work in live:
+            self.pass2_scatter(dr, work)
+        self._finish_pass()
+        # read-back (small, pinned, asynchronous): per-path state, table, every shard's cursors
+        P, acc = self.acc.P, self.acc
+        if job.stage is None or job.stage["c"].shape[0] < len(live):
+            job.stage = dict(
+                f=torch.empty(3 * P, dtype=torch.float64).pin_memory(),
+                i=torch.empty(acc.i64.numel(), dtype=torch.int64).pin_memory(),
+                t=torch.empty((max(1, P), _lib.TABLE_COLS), dtype=torch.float64).pin_memory(),
+                c=torch.empty((len(live), 8), dtype=torch.int64).pin_memory())
+        st = job.stage
+        st["f"].copy_(acc.f64[:3 * P], non_blocking=True)
+        st["i"].copy_(acc.i64, non_blocking=True)
+        st["t"].copy_(self.table, non_blocking=True)
+        for k, (_, work) in enumerate(live):
+            st["c"][k].copy_(work.t["cursor"], non_blocking=True)
+        job.done = torch.cuda.Event()
+        job.done.record(main)
+        job.shards, job.live = shards, live
+        return job
+
+    def collect(self, job):
+        """Wait for a submitted job and return its per-path results (no per-group codes).  A shard whose match buffer
+        was too small (first use of a workload) is regrown to its exact need and the job is run again."""
         for attempt in range(3):
-            self.acc.zero()
-            self._copy.wait_stream(main)            # buffers of the previous call are free again
-            live = []
-            for k, host in enumerate(shards):
-                slot = self._slots.setdefault(k, {})
-                with torch.cuda.stream(self._copy):
-                    dr = DeviceReads(host, self.device, slot.get("arena"), slot.get("wide"), self.node_len, expand=False)
-                    arrived = torch.cuda.Event()
-                    arrived.record(self._copy)
-                slot["arena"] = dr.arena
-                main.wait_event(arrived)
-                dr.expand()
-                slot["wide"] = dr.wide
-                cap = max(slot.get("cap", 0), 2 * dr.n_alns + 1024)
-                work = slot.get("work")
-                if work is None or work.n_groups < dr.n_groups or work.n_alns < dr.n_alns or work.match_cap < cap:
-                    work = slot["work"] = Work(dr.n_groups, dr.n_alns, cap, self.device)
-                work.reset()
-                self.match(dr, work)
-                self.classify(dr, work)
-                self.side.wait_stream(main)
-                with torch.cuda.stream(self.side):
-                    self.pass1_scatter(dr, work)
-                live.append((dr, work))
-            uniq_global = None
-            if self.comm is not None:
-                uniq_global = self.acc.uniq_reads.clone()
-                dist.all_reduce(uniq_global, group=self.comm)
-            for dr, work in live:
-                self.pass2_resolve(dr, work, uniq_global)
-            main.wait_stream(self.side)
-            for dr, work in live:
-                self.pass2_scatter(dr, work)
-            self._finish_pass()
-            res = self.fetch(live[-1][1], live[-1][0], keep_codes=False, keep_slots=False)
+            job.done.synchronize()
+            res = self._result_from(job.acc, job.stage["f"].numpy(), job.stage["i"].numpy(), job.stage["t"].numpy())
+            cur = job.stage["c"].numpy()
             if res.C["MATCH_OVERFLOW"] == 0:
-                res.n_deferred = sum(int(w.t["cursor"][1].item()) for _, w in live)
+                res.n_deferred = int(cur[:len(job.live), 1].sum())
+                res.match_fill = int(cur[len(job.live) - 1, 0])
+                check_errors(res.C)
                 return res
-            for k, (dr, work) in enumerate(live):   # grow every shard's match buffer to its exact need, rerun
-                self._slots[k]["cap"] = int(work.t["cursor"][0].item()) + 1024
+            for k in range(len(job.live)):            # grow every shard's match buffer to its exact need, rerun
+                job.slots[k]["cap"] = int(cur[k, 0]) + 1024
+            job = self.submit(job.shards, _reuse=job)     # same buffers again
         raise MatchOverflow("match buffer still too small after regrowing")
+
+    def run_stream(self, shards):
+        """End-to-end pass over a data set staged as several HostReads shards: ``collect(submit(shards))``."""
+        return self.collect(self.submit(shards, depth=max(1, len(getattr(self, "_jobs", [])))))
 
     def run(self, reads, keep_codes=True, keep_slots=True):
         """Public entry: host arrays in, host results out (H2D and D2H included).  The reports need the
@@ -548,6 +605,21 @@ class AbundanceEngine:
                 return res
             self.match_cap_hint = res.match_fill + 1024                    # exact need, rerun
         raise MatchOverflow("match buffer still too small after regrowing")
+
+    def _result_from(self, acc, f64, i64, table):
+        """Host copies of the read-back buffers as a Result."""
+        P = acc.P
+        counters_raw = i64[P + acc.n_hist:P + acc.n_hist + _lib.N_COUNTERS].copy()
+        return Result(
+            g=self.graph.as_dict(),
+            uniq_reads=i64[0:P].copy(),
+            hist=i64[P:P + acc.n_hist].reshape(_lib.N_HIST, acc.S, _lib.N_BINS).copy(),
+            counters_raw=counters_raw,
+            C={k: int(v) for k, v in zip(_lib.COUNTER_NAMES, counters_raw)},
+            mult_hits=i64[P + acc.n_hist + _lib.N_COUNTERS:].view(np.int32)[:P].copy(),
+            uniq_norm=f64[0:P].copy(), mult_reads=f64[P:2 * P].copy(), mult_norm=f64[2 * P:3 * P].copy(),
+            table=table[:P].copy() if P else np.zeros((0, _lib.TABLE_COLS)),
+        )
 
     def fetch(self, work, dr, keep_codes=True, keep_slots=True):
         acc, dg = self.acc, self.dg
@@ -578,19 +650,8 @@ class AbundanceEngine:
                 self._plain_idx = torch.from_numpy(dg.slot_of_plain).to(self.device)
             slots = (acc.uniq_abund[self._plain_idx].cpu(), acc.mult_abund[self._plain_idx].cpu())   # sentinels dropped on device
         torch.cuda.current_stream().synchronize()
-        f64, i64 = st["f"].numpy(), st["i"].numpy()
-        counters_raw = i64[P + acc.n_hist:P + acc.n_hist + _lib.N_COUNTERS].copy()
-        res = Result(
-            g=self.graph.as_dict(),
-            uniq_reads=i64[0:P].copy(),
-            hist=i64[P:P + acc.n_hist].reshape(_lib.N_HIST, acc.S, _lib.N_BINS).copy(),
-            counters_raw=counters_raw,
-            C={k: int(v) for k, v in zip(_lib.COUNTER_NAMES, counters_raw)},
-            mult_hits=i64[P + acc.n_hist + _lib.N_COUNTERS:].view(np.int32)[:P].copy(),
-            uniq_norm=f64[0:P].copy(), mult_reads=f64[P:2 * P].copy(), mult_norm=f64[2 * P:3 * P].copy(),
-            table=st["t"].numpy()[:P].copy() if P else np.zeros((0, _lib.TABLE_COLS)),
-            n_deferred=int(st["c"][1]), match_fill=int(st["c"][0]),
-        )
+        res = self._result_from(acc, st["f"].numpy(), st["i"].numpy(), st["t"].numpy())
+        res.n_deferred, res.match_fill = int(st["c"][1]), int(st["c"][0])
         if slots is not None:
             res.uniq_abund, res.mult_abund = slots[0].numpy(), slots[1].numpy()
         if keep_codes:

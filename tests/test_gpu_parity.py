@@ -327,6 +327,29 @@ def test_transfer_layout_expands_to_the_same_arrays(variant):
     assert np.allclose(a.mult_abund, b.mult_abund, rtol=1e-12, atol=0)
 
 
+def test_transfer_layout_long_walks_take_the_direct_path():
+    """Walks of ~35 nodes: 256 of them do not fit the shared-memory image of k_expand_walks, the block writes them
+    straight to global memory; mixed with a stretch of short walks that is staged."""
+    need_gpu()
+    graph = synth.make_graph(11, n_clusters=60, chain_len=150, hap_lo=1, hap_hi=4, n_strains=8, bubble_p=0.3, flip_p=0.2,
+                             max_node_len=7)
+    long_reads = synth.make_reads(graph, 12, n_pairs=4000, read_len=150)
+    short_reads = synth.make_reads(graph, 13, n_pairs=4000, read_len=12)
+    assert long_reads.n_records > 20 * long_reads.n_alns and short_reads.n_records < 8 * short_reads.n_alns
+    eng = engine.AbundanceEngine(graph)
+    for reads in (long_reads, short_reads):
+        host = engine.HostReads(reads, wire=True)
+        assert host.wire
+        a = eng.run(host)
+        b = eng.run(engine.HostReads(reads, wire=False))
+        assert a.C == b.C and np.array_equal(a.uniq_reads, b.uniq_reads) and np.array_equal(a.grp_code, b.grp_code)
+        assert np.array_equal(a.aln_assign, b.aln_assign)
+        assert np.allclose(a.uniq_abund, b.uniq_abund, rtol=1e-12, atol=0)
+        assert np.allclose(a.mult_abund, b.mult_abund, rtol=1e-12, atol=0)
+        orc = oa.AbundanceOracle(graph.as_dict(), reads.as_dict()).run()
+        check_against_oracle(graph, reads, a, orc)
+
+
 def test_streamed_shards_equal_single_pass():
     """run_stream (uploads overlapped with kernels, shards accumulated into the same arrays) == run."""
     need_gpu()
@@ -345,6 +368,45 @@ def test_streamed_shards_equal_single_pass():
             ok = np.abs(many.table - one.table) <= 1e-9 * np.maximum(np.abs(many.table), np.abs(one.table))
             assert (ok | (np.isnan(many.table) & np.isnan(one.table))).all()
             assert np.allclose(many.mult_reads, one.mult_reads, rtol=1e-9, atol=0)
+
+
+def test_pipelined_jobs_equal_single_passes():
+    """submit/collect with two jobs in flight (uploads of job k+1 under pass 2 of job k, each job on its own
+    accumulators and device buffers): every job returns what a plain run of its reads returns, in any interleaving,
+    including the first jobs whose match buffers are still too small and are run again."""
+    need_gpu()
+    from collections import deque
+    from strainflair_b200 import dist as sfdist
+    graph, reads_a = synth.make_config("small", scale=0.5)
+    reads_b = synth.make_reads(graph, 4242, n_pairs=9000, read_len=150, p_same_path=0.7)
+    eng = engine.AbundanceEngine(graph, deterministic=True)
+    ref = {"a": eng.run(reads_a, keep_codes=False), "b": eng.run(reads_b, keep_codes=False)}
+    sets = {}
+    for name, rd, k in (("a", reads_a, 4), ("b", reads_b, 3)):
+        sets[name] = [engine.HostReads(rd.slice_groups(*sfdist.shard_bounds(rd.n_groups, k, i))) for i in range(k)]
+    order = ["a", "b", "b", "a", "a", "b", "a"]
+    pending, got = deque(), []
+    for name in order:
+        pending.append((name, eng.submit(sets[name], depth=2)))
+        if len(pending) == 2:
+            nm, job = pending.popleft()
+            got.append((nm, eng.collect(job)))
+    while pending:
+        nm, job = pending.popleft()
+        got.append((nm, eng.collect(job)))
+    assert [nm for nm, _ in got] == order
+    for nm, res in got:
+        one = ref[nm]
+        for name in oa.COUNTERS:
+            assert res.C[name] == one.C[name], (nm, name)
+        assert np.array_equal(res.uniq_reads, one.uniq_reads) and np.array_equal(res.hist, one.hist)
+        assert res.n_deferred == one.n_deferred
+        # order-independent accumulation: bit-identical whatever the sharding and the interleaving
+        assert np.array_equal(res.table, one.table, equal_nan=True)
+        assert np.array_equal(res.mult_reads, one.mult_reads) and np.array_equal(res.uniq_norm, one.uniq_norm)
+    # the plain entry still works on the engine afterwards
+    again = eng.run(reads_b, keep_codes=False)
+    assert np.array_equal(again.table, ref["b"].table, equal_nan=True)
 
 
 def test_order_independent_mode_is_bit_reproducible():
