@@ -45,6 +45,17 @@ def main():
         for name in ("uniq_norm", "mult_reads", "mult_norm", "uniq_abund", "mult_abund", "table"):
             assert np.array_equal(getattr(res_d, name), getattr(single_d, name), equal_nan=True), name
         print("MGPU_DET_OK")
+    # two pipelined jobs per rank (submit / collect), each rank's shard staged as two host shards: same bits again
+    mine = reads.slice_groups(g0, g1)
+    staged = [engine.HostReads(mine.slice_groups(*sfdist.shard_bounds(mine.n_groups, 2, i))) for i in range(2)]
+    jobs = [eng_d.submit(staged, depth=2) for _ in range(3)]
+    outs = [eng_d.collect(j) for j in jobs]
+    for out in outs:
+        assert out.C["NB_READS"] == res_d.C["NB_READS"]
+        for name in ("uniq_norm", "mult_reads", "mult_norm", "table"):
+            assert np.array_equal(getattr(out, name), getattr(res_d, name), equal_nan=True), name
+    if rank == 0:
+        print("MGPU_PIPE_OK")
     dist.barrier()
     dist.destroy_process_group()
 
