@@ -44,7 +44,10 @@ struct MatchStats {
 constexpr int kWarpsPerBlock = 8;
 constexpr int kU = SFB_MATCH_KU;    // compare positions fetched together (walks of up to kU + 2 nodes need no loop)
 constexpr int kWin = SFB_MATCH_WIN; // windows of 32 candidates per phase-A trip
-constexpr int kSurv = 32 * kWin + 96;   // survivor list entries per warp
+#ifndef SFB_MATCH_SURV_EXTRA
+#define SFB_MATCH_SURV_EXTRA 96
+#endif
+constexpr int kSurv = 32 * kWin + SFB_MATCH_SURV_EXTRA;   // survivor list entries per warp
 
 __global__ void __launch_bounds__(256, SFB_MATCH_MINBLK) k_match(sfb_graph g, sfb_reads r, sfb_work w, long long* counters) {
     __shared__ BlockCounters sc;

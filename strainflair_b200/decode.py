@@ -17,6 +17,12 @@ _ERRORS = {1: ValueError, 2: KeyError, 3: ZeroDivisionError, 4: IndexError, 5: O
 def decode_json(json_path, graph: Graph, thr=0.95, threads=None, block_bytes=0, want_cov=False) -> Reads:
     """Decode a whole alignment file.  Raises the exception class the reference would raise on bad input
     (unknown node id -> KeyError, zero-length read -> ZeroDivisionError, malformed line -> ValueError)."""
+    from . import cache
+    t0 = time.perf_counter()
+    hit = cache.load_reads_entry(json_path, graph, thr, want_cov)     # only when SFB200_CACHE_DIR is set
+    if hit is not None:
+        hit.decode_seconds, hit.from_cache = time.perf_counter() - t0, True
+        return hit
     lib = _lib.load()
     threads = threads or len(os.sched_getaffinity(0))
     ids = np.ascontiguousarray(graph.node_ids, np.int64)
@@ -53,7 +59,8 @@ def decode_json(json_path, graph: Graph, thr=0.95, threads=None, block_bytes=0, 
         reads.aln_stats = take(6, 5 * A, np.float64).reshape(A, 5)
         if want_cov:
             reads.walk_cov = take(9, R, np.float64)
-        reads.decode_seconds = time.perf_counter() - t0
+        reads.decode_seconds, reads.from_cache = time.perf_counter() - t0, False
+        cache.save_reads_entry(json_path, graph, thr, reads)
         return reads
     finally:
         lib.sfb_decoded_free(h)

@@ -25,6 +25,17 @@ _ERRORS = {2: KeyError, 4: IndexError, 5: OSError, 6: ValueError}
 
 
 def load_graph(gfa_path, pickle_path=None) -> Graph:
+    from . import cache
+    g = cache.load_graph_entry(gfa_path)                  # only when SFB200_CACHE_DIR is set
+    if g is None:
+        g = _parse_gfa(gfa_path)
+        cache.save_graph_entry(gfa_path, g)
+    if pickle_path is not None:
+        attach_clusters(g, pickle_path)
+    return g
+
+
+def _parse_gfa(gfa_path) -> Graph:
     lib = _lib.load()
     h = lib.sfb_load_gfa(os.fsencode(gfa_path))
     try:
@@ -60,8 +71,6 @@ def load_graph(gfa_path, pickle_path=None) -> Graph:
         path_cluster=np.full(P, -1, np.int32), clu_off=np.zeros(1, np.int64), clu_paths=np.zeros(0, np.int32),
         strain_names=strain_names, header_strains=header, path_names=path_names, node_index=None,
     )
-    if pickle_path is not None:
-        attach_clusters(g, pickle_path)
     return g
 
 

@@ -364,3 +364,55 @@ def test_gene_table_writer_matches_oracle_text(d):
     g.pstr_cnt[0] = go["pstr_cnt"][0] = 12
     assert "".join(report.gene_table_lines(g, res)) == orp.gene_table_text(orc)
     g.pstr_cnt[0] = go["pstr_cnt"][0] = big
+
+
+def test_on_disk_caches_hit_miss_and_invalidate(tmp_path, monkeypatch):
+    """SFB200_CACHE_DIR: the parsed graph and the decoded reads come back array for array from their cache entries;
+    a changed input, threshold or graph misses; without the variable nothing is written."""
+    import shutil
+    from strainflair_b200 import cache
+    from strainflair_b200.schema import GRAPH_ARRAYS, READS_ARRAYS
+    src = os.path.join(HERE, "golden", "case_011")
+    work = tmp_path / "in"
+    shutil.copytree(src, work)
+    gf, js, pk = (str(work / n) for n in ("graph.gfa", "reads.json", "dict_clusters.pickle"))
+
+    monkeypatch.delenv("SFB200_CACHE_DIR", raising=False)
+    g0 = gfa.load_graph(gf, pk)
+    r0 = decode.decode_json(js, g0, 0.95, want_cov=True)
+    assert not r0.from_cache and sorted(os.listdir(work)) == ["dict_clusters.pickle", "expected.json", "graph.gfa", "reads.json"]
+
+    cdir = tmp_path / "cache"
+    monkeypatch.setenv("SFB200_CACHE_DIR", str(cdir))
+    g1 = gfa.load_graph(gf, pk)                       # miss: parsed and stored
+    r1 = decode.decode_json(js, g1, 0.95, want_cov=True)
+    assert not r1.from_cache and len(os.listdir(cdir)) == 2
+    g2 = gfa.load_graph(gf, pk)                       # hit
+    r2 = decode.decode_json(js, g2, 0.95, want_cov=True)
+    assert r2.from_cache
+    for k in GRAPH_ARRAYS:
+        assert np.array_equal(getattr(g0, k), getattr(g2, k)), k
+    assert g2.strain_names == g0.strain_names and g2.header_strains == g0.header_strains and g2.path_names == g0.path_names
+    for k in READS_ARRAYS:
+        assert np.array_equal(getattr(r0, k), getattr(r2, k)), k
+    assert np.array_equal(r0.aln_stats, r2.aln_stats) and np.array_equal(r0.walk_cov, r2.walk_cov)
+    assert np.array_equal(r0.name_off, r2.name_off) and r0.name_blob == r2.name_blob
+    assert decode.mate_name(r2, 0, 0) == decode.mate_name(r0, 0, 0)
+
+    assert not decode.decode_json(js, g2, 0.5).from_cache          # another threshold: its own entry
+    assert decode.decode_json(js, g2, 0.5).from_cache
+    st = os.stat(js)
+    os.utime(js, ns=(st.st_atime_ns, st.st_mtime_ns + 10**9))      # touched input: miss
+    assert not decode.decode_json(js, g2, 0.95).from_cache
+    g3 = gfa.load_graph(gf, pk)
+    g3.node_len = g3.node_len + 1                                  # another graph: miss (the decoder reads node lengths)
+    assert not decode.decode_json(js, g3, 0.95).from_cache
+    # an unreadable entry is ignored, not fatal
+    entry = cache._entry(gf, "graph")
+    with open(entry, "wb") as fh:
+        fh.write(b"not an npz")
+    g4 = gfa.load_graph(gf, pk)
+    assert np.array_equal(g4.path_nodes, g0.path_nodes)
+    monkeypatch.setenv("SFB200_CACHE_DIR", ".")                    # "." = next to the input
+    gfa.load_graph(gf, pk)
+    assert any(n.endswith(".sfb200.npz") for n in os.listdir(work))
