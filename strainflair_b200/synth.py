@@ -108,7 +108,10 @@ def _python_round_bins(values):
 
 def make_reads(graph, seed, n_pairs, read_len=150, p_same_path=0.95, p_low_score=0.03, p_tie=0.10,
                p_recomb=0.01, p_single=0.02, p_exc=0.0, chunk=1_000_000, threads=8):
-    """Returns Reads for ``n_pairs`` read groups (a ``p_single`` share of them single-end)."""
+    """Returns Reads for ``n_pairs`` read groups (a ``p_single`` share of them single-end).  Keep ``read_len`` at or
+    below the shortest path's sequence length: a "tied" second alignment placed on a shorter sibling path would be
+    clipped to another length, hence another normalised score, and would not be a tie for the reference
+    (json2csv.py:729-737) -- the arrays would then describe an input no JSON file decodes to."""
     rng = np.random.default_rng(seed)
     K = graph.chain_len
     P = graph.n_paths
