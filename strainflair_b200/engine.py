@@ -490,6 +490,7 @@ class AbundanceEngine:
             self.acc = Accum(eng.dg, eng.deterministic)
             self.table = torch.empty_like(eng.table)
             self.slots, self.stage, self.done, self.shards, self.live = {}, None, None, None, None
+            self.pending = False                        # submitted, not collected yet
 
     def _job_context(self, depth):
         if getattr(self, "_copy", None) is None:
@@ -512,6 +513,10 @@ class AbundanceEngine:
         of the next job overlap with pass 2 of this one."""
         import torch.distributed as dist
         job = _reuse if _reuse is not None else self._job_context(depth)
+        if job.pending and _reuse is None:
+            self._next_job -= 1
+            raise RuntimeError(f"submit: {depth} jobs are in flight already; collect the oldest one first "
+                               "(its buffers would be reused)")
         if job.done is not None:
             job.done.synchronize()                  # the job that used these buffers before must have finished
         main = torch.cuda.current_stream()
@@ -567,7 +572,7 @@ class AbundanceEngine:
             st["c"][k].copy_(work.t["cursor"], non_blocking=True)
         job.done = torch.cuda.Event()
         job.done.record(main)
-        job.shards, job.live = shards, live
+        job.shards, job.live, job.pending = shards, live, True
         return job
 
     def collect(self, job):
@@ -578,6 +583,7 @@ class AbundanceEngine:
             res = self._result_from(job.acc, job.stage["f"].numpy(), job.stage["i"].numpy(), job.stage["t"].numpy())
             cur = job.stage["c"].numpy()
             if res.C["MATCH_OVERFLOW"] == 0:
+                job.pending = False
                 res.n_deferred = int(cur[:len(job.live), 1].sum())
                 res.match_fill = int(cur[len(job.live) - 1, 0])
                 check_errors(res.C)
@@ -585,6 +591,7 @@ class AbundanceEngine:
             for k in range(len(job.live)):            # grow every shard's match buffer to its exact need, rerun
                 job.slots[k]["cap"] = int(cur[k, 0]) + 1024
             job = self.submit(job.shards, _reuse=job)     # same buffers again
+        job.pending = False
         raise MatchOverflow("match buffer still too small after regrowing")
 
     def run_stream(self, shards):

@@ -48,8 +48,10 @@ def main():
     # two pipelined jobs per rank (submit / collect), each rank's shard staged as two host shards: same bits again
     mine = reads.slice_groups(g0, g1)
     staged = [engine.HostReads(mine.slice_groups(*sfdist.shard_bounds(mine.n_groups, 2, i))) for i in range(2)]
-    jobs = [eng_d.submit(staged, depth=2) for _ in range(3)]
-    outs = [eng_d.collect(j) for j in jobs]
+    j1, j2 = eng_d.submit(staged, depth=2), eng_d.submit(staged, depth=2)
+    outs = [eng_d.collect(j1)]
+    j3 = eng_d.submit(staged, depth=2)
+    outs += [eng_d.collect(j2), eng_d.collect(j3)]
     for out in outs:
         assert out.C["NB_READS"] == res_d.C["NB_READS"]
         for name in ("uniq_norm", "mult_reads", "mult_norm", "table"):

@@ -404,6 +404,14 @@ def test_pipelined_jobs_equal_single_passes():
         # order-independent accumulation: bit-identical whatever the sharding and the interleaving
         assert np.array_equal(res.table, one.table, equal_nan=True)
         assert np.array_equal(res.mult_reads, one.mult_reads) and np.array_equal(res.uniq_norm, one.uniq_norm)
+    # a third job without collecting the oldest would reuse its buffers: refused
+    j1, j2 = eng.submit(sets["a"], depth=2), eng.submit(sets["b"], depth=2)
+    with pytest.raises(RuntimeError):
+        eng.submit(sets["a"], depth=2)
+    assert np.array_equal(eng.collect(j1).table, ref["a"].table, equal_nan=True)
+    j3 = eng.submit(sets["a"], depth=2)
+    assert np.array_equal(eng.collect(j2).table, ref["b"].table, equal_nan=True)
+    assert np.array_equal(eng.collect(j3).table, ref["a"].table, equal_nan=True)
     # the plain entry still works on the engine afterwards
     again = eng.run(reads_b, keep_codes=False)
     assert np.array_equal(again.table, ref["b"].table, equal_nan=True)
