@@ -91,6 +91,42 @@ class Reads(_Bag):
     def n_mates(self):
         return int(self.grp_nmates.sum())
 
+    def permute_groups(self, order):
+        """The same read groups in another order (``order[k]`` = old index of new group k); mates, alignments and
+        records follow their group.  Every sum of the abundance pass is independent of the group order."""
+        order = np.asarray(order, np.int64)
+        ms = (2 * order[:, None] + np.arange(2)).reshape(-1)                      # mate slots in the new order
+        n_aln = np.diff(self.grp_aln_off)[ms]
+        grp_aln_off = np.concatenate(([0], np.cumsum(n_aln))).astype(np.int64)
+        A = int(grp_aln_off[-1])
+        aln = np.repeat(self.grp_aln_off[:-1][ms], n_aln) + (np.arange(A, dtype=np.int64) - np.repeat(grp_aln_off[:-1], n_aln))
+        L = np.diff(self.aln_walk_off)[aln]
+        aln_walk_off = np.concatenate(([0], np.cumsum(L))).astype(np.int64)
+        R = int(aln_walk_off[-1])
+        rec = np.repeat(self.aln_walk_off[:-1][aln], L) + (np.arange(R, dtype=np.int64) - np.repeat(aln_walk_off[:-1], L))
+        names = None
+        if self.mate_names is not None:
+            names = [self.mate_names[int(k)] for k in ms]
+        return Reads(
+            grp_nmates=self.grp_nmates[order], grp_aln_off=grp_aln_off, mate_seq_len=self.mate_seq_len[ms],
+            aln_walk_off=aln_walk_off, aln_read_len=self.aln_read_len[aln], aln_bins=self.aln_bins[aln],
+            walk_node=self.walk_node[rec], walk_alen=self.walk_alen[rec], exc_cov=self.exc_cov, mate_names=names,
+        )
+
+    def locality_order(self):
+        """Stable order of the read groups by the first node of their first retained alignment (groups without one
+        last): neighbours in that order start in the same region of the graph -- node ids of a pangenome built
+        cluster by cluster are contiguous per cluster -- so the gathers of the pass hit the same index entries, paths
+        and accumulator slots."""
+        first_aln = self.grp_aln_off[0:-1:2]
+        has = self.grp_aln_off[2::2] > first_aln
+        key = np.full(self.n_groups, np.iinfo(np.int64).max, np.int64)
+        if self.n_alns:
+            a = np.minimum(first_aln, self.n_alns - 1)
+            w = np.minimum(self.aln_walk_off[:-1][a], max(self.n_records - 1, 0))
+            key[has] = self.walk_node[w][has] if self.n_records else 0
+        return np.argsort(key, kind="stable")
+
     def slice_groups(self, g0, g1):
         """Contiguous shard [g0, g1) of read groups, re-based (pairs are never split)."""
         a0, a1 = int(self.grp_aln_off[2 * g0]), int(self.grp_aln_off[2 * g1])

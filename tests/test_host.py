@@ -416,3 +416,30 @@ def test_on_disk_caches_hit_miss_and_invalidate(tmp_path, monkeypatch):
     monkeypatch.setenv("SFB200_CACHE_DIR", ".")                    # "." = next to the input
     gfa.load_graph(gf, pk)
     assert any(n.endswith(".sfb200.npz") for n in os.listdir(work))
+
+
+def test_group_permutation_keeps_every_result():
+    """Reads.permute_groups / locality_order: the same groups in another order give the same counters, integer
+    arrays and histograms, the same leaf code per group and the same fp64 sums (to rounding) in the oracle."""
+    from oracle import abundance as oa
+    from strainflair_b200 import synth
+    graph, reads = synth.make_config("tiny")
+    base = oa.AbundanceOracle(graph.as_dict(), reads.as_dict()).run()
+    ident = reads.permute_groups(np.arange(reads.n_groups))
+    for k in ("grp_nmates", "grp_aln_off", "mate_seq_len", "aln_walk_off", "aln_read_len", "aln_bins", "walk_node", "walk_alen"):
+        assert np.array_equal(getattr(ident, k), getattr(reads, k)), k
+    local = reads.locality_order()
+    firsts = []
+    for g in local:
+        a0, a1 = int(reads.grp_aln_off[2 * g]), int(reads.grp_aln_off[2 * g + 2])
+        firsts.append(int(reads.walk_node[reads.aln_walk_off[a0]]) if a1 > a0 else 1 << 62)
+    assert firsts == sorted(firsts) and sorted(local.tolist()) == list(range(reads.n_groups))
+    for order in (local, np.random.default_rng(3).permutation(reads.n_groups)):
+        moved = reads.permute_groups(order)
+        assert (moved.n_groups, moved.n_alns, moved.n_records) == (reads.n_groups, reads.n_alns, reads.n_records)
+        got = oa.AbundanceOracle(graph.as_dict(), moved.as_dict()).run()
+        assert got.C == base.C and got.uniq_reads == base.uniq_reads and np.array_equal(got.hist, base.hist)
+        assert np.array_equal(base.grp_code[order], got.grp_code) and np.array_equal(base.grp_code2[order], got.grp_code2)
+        for name in ("uniq_norm", "mult_reads", "mult_norm", "uniq_abund", "mult_abund"):
+            a, b = np.asarray(getattr(base, name), np.float64), np.asarray(getattr(got, name), np.float64)
+            assert np.allclose(a, b, rtol=1e-12, atol=0) and np.array_equal(a > 0, b > 0), name

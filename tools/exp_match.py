@@ -12,6 +12,8 @@ gkw, rkw = synth.CONFIGS[cfg]
 idx = list(synth.CONFIGS).index(cfg)
 graph = synth.make_graph(synth.SEED0 + idx, **gkw)
 reads = synth.make_reads(graph, synth.SEED0 + 1000 + idx, n_pairs=int(rkw["n_pairs"] * scale), read_len=150)
+if os.environ.get("SFB_SORT"):      # read groups in locality order (schema.Reads.locality_order)
+    reads = reads.permute_groups(reads.locality_order())
 eng = engine.AbundanceEngine(graph, "cuda:0")
 dr = eng.upload(engine.HostReads(reads))
 eng.match_cap_hint = int(os.environ.get("SFB_CAP_MULT", "2")) * reads.n_alns
@@ -36,4 +38,4 @@ for it in range(8):
 from strainflair_b200 import _lib
 cn = dict(zip(_lib.COUNTER_NAMES, eng.acc.counters.cpu().tolist()))
 chk = (cn["MATCH_OVERFLOW"], cn["ST_TUPLES"], cn["ST_CAND"], cn["ASSIGNED_U"], int(eng.acc.uniq_reads.sum().item()), int(work.t["aln_match"][:reads.n_alns].sum().item()) & 0xffffffff)
-print(os.path.basename(os.environ.get("SFB200_LIB", "default")), os.environ.get("SFB_ENTRY8", ""), {k: round(v, 4) for k, v in tot.items()}, cfg, "alns", reads.n_alns, "check", chk, flush=True)
+print(os.path.basename(os.environ.get("SFB200_LIB", "default")), "sorted" if os.environ.get("SFB_SORT") else "file-order", {k: round(v, 4) for k, v in tot.items()}, cfg, "alns", reads.n_alns, "check", chk, flush=True)
