@@ -162,7 +162,14 @@ class HostReads:
     (the end-to-end path copies from here every step).  ``wire``: use the compact transfer layout when the shard
     allows it (offsets as 1-byte counts, 16-bit lengths; expanded on the device by sfb_expand_reads)."""
 
-    def __init__(self, reads: Reads, pin=True, wire=True):
+    def __init__(self, reads: Reads, pin=True, wire=True, locality=False):
+        # ``locality`` (opt-in; measured -10 % over the kernels of the pass, profiles/README.md; not validated on a
+        # GPU through this entry yet): stage the groups in locality order (schema.Reads.locality_order).  The per-path
+        # results do not depend on the order; per-group / per-alignment outputs are put back in file order by fetch.
+        self.order = self.aln_index = None
+        if locality and reads.n_groups > 1:
+            self.order = reads.locality_order()
+            reads, self.aln_index = reads.permute_groups(self.order, return_index=True)
         self.reads = reads
         packed = _Packed(reads) if wire else None
         try:
@@ -319,6 +326,24 @@ class Result:
 
 class MatchOverflow(RuntimeError):
     pass
+
+
+def restore_file_order(res, order, aln_index):
+    """Per-group and per-alignment outputs of a pass over permuted read groups (``order[k]`` / ``aln_index[k]`` = old
+    index of new group / alignment k), back in the order of the input file."""
+    for name in ("grp_code", "grp_code2"):
+        v = getattr(res, name, None)
+        if v is not None:
+            out = np.empty_like(v)
+            out[order] = v
+            setattr(res, name, out)
+    for name in ("aln_assign", "aln_match"):
+        v = getattr(res, name, None)
+        if v is not None:
+            out = np.empty_like(v)
+            out[aln_index] = v
+            setattr(res, name, out)
+    return res
 
 
 class AbundanceEngine:
@@ -668,6 +693,9 @@ class AbundanceEngine:
             res.aln_match = work.t["aln_match"][:dr.n_alns].cpu().numpy().view(np.uint32).reshape(-1, 2)
             res.match_buf = work.t["match_buf"][:min(work.match_cap, max(0, res.match_fill))].cpu().numpy() \
                 .view(np.uint32).reshape(-1, 2)
+            host = getattr(dr, "host", None)
+            if host is not None and getattr(host, "order", None) is not None:
+                restore_file_order(res, host.order, host.aln_index)
         check_errors(res.C)
         return res
 

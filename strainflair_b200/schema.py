@@ -91,9 +91,10 @@ class Reads(_Bag):
     def n_mates(self):
         return int(self.grp_nmates.sum())
 
-    def permute_groups(self, order):
+    def permute_groups(self, order, return_index=False):
         """The same read groups in another order (``order[k]`` = old index of new group k); mates, alignments and
-        records follow their group.  Every sum of the abundance pass is independent of the group order."""
+        records follow their group.  Every sum of the abundance pass is independent of the group order.
+        ``return_index``: also return the old index of every new alignment."""
         order = np.asarray(order, np.int64)
         ms = (2 * order[:, None] + np.arange(2)).reshape(-1)                      # mate slots in the new order
         n_aln = np.diff(self.grp_aln_off)[ms]
@@ -107,11 +108,12 @@ class Reads(_Bag):
         names = None
         if self.mate_names is not None:
             names = [self.mate_names[int(k)] for k in ms]
-        return Reads(
+        moved = Reads(
             grp_nmates=self.grp_nmates[order], grp_aln_off=grp_aln_off, mate_seq_len=self.mate_seq_len[ms],
             aln_walk_off=aln_walk_off, aln_read_len=self.aln_read_len[aln], aln_bins=self.aln_bins[aln],
             walk_node=self.walk_node[rec], walk_alen=self.walk_alen[rec], exc_cov=self.exc_cov, mate_names=names,
         )
+        return (moved, aln) if return_index else moved
 
     def locality_order(self):
         """Stable order of the read groups by the first node of their first retained alignment (groups without one

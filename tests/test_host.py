@@ -443,3 +443,27 @@ def test_group_permutation_keeps_every_result():
         for name in ("uniq_norm", "mult_reads", "mult_norm", "uniq_abund", "mult_abund"):
             a, b = np.asarray(getattr(base, name), np.float64), np.asarray(getattr(got, name), np.float64)
             assert np.allclose(a, b, rtol=1e-12, atol=0) and np.array_equal(a > 0, b > 0), name
+
+
+def test_locality_staging_and_file_order_restoration():
+    """HostReads(locality=True) stages the permuted groups (packed natively as any other shard) and
+    engine.restore_file_order puts per-group / per-alignment outputs back in file order (the oracle stands in for the
+    kernels here; the opt-in entry itself still has to be validated on a GPU)."""
+    from oracle import abundance as oa
+    from strainflair_b200 import engine, synth
+    graph, reads = synth.make_config("tiny")
+    host = engine.HostReads(reads, pin=False, wire=True, locality=True)
+    plain = engine.HostReads(reads, pin=False, wire=True)
+    assert plain.order is None and host.order is not None and host.wire
+    assert sorted(host.order.tolist()) == list(range(reads.n_groups))
+    moved, aln_index = reads.permute_groups(host.order, return_index=True)
+    assert np.array_equal(host.reads.walk_node, moved.walk_node) and np.array_equal(host.aln_index, aln_index)
+    assert sorted(aln_index.tolist()) == list(range(reads.n_alns))
+    base = oa.AbundanceOracle(graph.as_dict(), reads.as_dict()).run()
+    got = oa.AbundanceOracle(graph.as_dict(), moved.as_dict()).run()
+    res = engine.Result(grp_code=np.asarray(got.grp_code).copy(), grp_code2=np.asarray(got.grp_code2).copy(),
+                        aln_assign=np.asarray(got.aln_assign).copy())
+    assert not np.array_equal(res.grp_code, base.grp_code)
+    engine.restore_file_order(res, host.order, host.aln_index)
+    assert np.array_equal(res.grp_code, base.grp_code) and np.array_equal(res.grp_code2, base.grp_code2)
+    assert np.array_equal(res.aln_assign, base.aln_assign)
