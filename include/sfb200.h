@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SFB_ABI_VERSION 8
+#define SFB_ABI_VERSION 9
 
 /* ---- status codes ---------------------------------------------------- */
 #define SFB_OK            0
@@ -302,6 +302,15 @@ int          sfb_packed_status(const sfb_packed* p, const char** msg);
 int64_t      sfb_packed_size(const sfb_packed* p, int which);
 int          sfb_packed_copy(const sfb_packed* p, int which, void* dst);
 void         sfb_packed_free(sfb_packed* p);
+
+/* ---- host-side locality order of the read groups (no GPU involved) ------------------------
+ * The sums of the abundance pass do not depend on the order of the read groups; staged stable by the first node of their
+ * first retained alignment (groups without one last), neighbouring groups gather the same index entries, paths and
+ * accumulator slots.  `src` and `dst` hold HOST pointers; dst's grp_nmates[G], grp_aln_off[2G+1], mate_seq_len[2G],
+ * aln_walk_off[A+1], aln_bins[5A], walk_node[R], walk_alen[R] are caller-allocated and filled with the permuted CSR
+ * (exc_cov is shared: explicit-coverage records keep their index).  order[G]: old index of new group k; aln_index[A]: old
+ * index of new alignment k (per-alignment side arrays and outputs follow it).  The result does not depend on n_threads. */
+int sfb_locality_permute(const sfb_reads* src, int n_threads, int64_t* order, int64_t* aln_index, const sfb_reads* dst);
 
 /* ---- host-side analysis of the unassigned reads (no GPU involved) ---------------------------
  * Cluster.min_strains_inference (json2csv.py:149-201, with canonical_tiny :63-71, check_incomp_comp :83-97, sublist

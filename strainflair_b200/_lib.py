@@ -75,13 +75,13 @@ SLOT_MASK, MATCH_REV, MATCH_MULTI, MATCH_NONE = 0x3FFFFFFF, 0x40000000, 0x800000
 MAX_SLOTS = 0x3FFFFFFF
 (ABSENT, FILTERED, UNASSIGNED, UNASSIGNED_BOOK, DEFER, ASSIGN_SAME, ASSIGN_DIFF, MULTI_ALIGN, INCONSIST,
  SE_COUNTED) = range(10)
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 EXPORTS = ("sfb_abi_version", "sfb_version", "sfb_last_error", "sfb_expand_reads", "sfb_match", "sfb_classify", "sfb_pass1_scatter",
            "sfb_pass2", "sfb_pass2_resolve", "sfb_pass2_scatter", "sfb_accum_collapse", "sfb_path_reduce", "sfb_cluster_strain_counts", "sfb_strain_aggregate",
            "sfb_decode_json", "sfb_decoded_error", "sfb_decoded_size", "sfb_decoded_copy", "sfb_decoded_free",
            "sfb_min_strains", "sfb_wire_pack", "sfb_packed_status", "sfb_packed_size", "sfb_packed_copy", "sfb_packed_free",
-           "sfb_load_gfa", "sfb_gfa_error", "sfb_gfa_size", "sfb_gfa_copy", "sfb_gfa_free")
+           "sfb_load_gfa", "sfb_gfa_error", "sfb_gfa_size", "sfb_gfa_copy", "sfb_gfa_free", "sfb_locality_permute")
 
 
 class SfbError(RuntimeError):
@@ -130,6 +130,8 @@ def load(build_if_missing=True):
         getattr(lib, name).restype = C.c_int
     lib.sfb_min_strains.argtypes = [i64, vp, vp, vp, C.c_int, vp, vp, vp, vp]
     lib.sfb_min_strains.restype = C.c_int
+    lib.sfb_locality_permute.argtypes = [R, C.c_int, vp, vp, R]
+    lib.sfb_locality_permute.restype = C.c_int
     lib.sfb_wire_pack.argtypes = [R, C.c_int]
     lib.sfb_wire_pack.restype = C.c_void_p
     lib.sfb_packed_status.argtypes = [vp, C.POINTER(C.c_char_p)]

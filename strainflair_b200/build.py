@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SOURCES = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "match.cu", "group.cu", "scatter.cu", "reduce.cu", "expand.cu", "decode.cpp", "gfa.cpp", "wire.cpp", "unassigned.cpp")]
+SOURCES = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "match.cu", "group.cu", "scatter.cu", "reduce.cu", "expand.cu", "decode.cpp", "gfa.cpp", "wire.cpp", "unassigned.cpp", "locality.cpp")]
 HEADERS = [os.path.join(HERE, "csrc", "common.cuh"), os.path.join(ROOT, "include", "sfb200.h")]
 LIB = os.path.join(HERE, "libsfb200.so")
 

@@ -1,0 +1,140 @@
+// Host-side locality order of the read groups and the permuted Reads CSR (no GPU involved).
+//
+// The abundance pass is a chain of gathers into the graph index, the paths and the per-path / per-slot accumulators.
+// Its sums do not depend on the order of the read groups, so the host may stage them in the order in which
+// neighbouring groups touch the same part of the graph: stable by the first node of the group's first retained
+// alignment (node ids of a pangenome built cluster by cluster are contiguous per cluster), groups without an
+// alignment last.  Same result as schema.Reads.locality_order() + permute_groups() in numpy, multi-threaded:
+// keys -> stable LSD radix sort of the group indices (16-bit digits, per-thread histograms) -> prefix sums ->
+// parallel copy of the mates, alignments and records of every group.
+#include <algorithm>
+#include <atomic>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "sfb200.h"
+
+namespace {
+
+template <class F>
+void for_chunks(int T, size_t n_items, F&& body) {      // chunk c of exactly T contiguous chunks (some may be empty)
+    std::vector<std::thread> pool;
+    auto work = [&](int c) {
+        const size_t lo = n_items * (size_t)c / (size_t)T, hi = n_items * (size_t)(c + 1) / (size_t)T;
+        body(c, lo, hi);
+    };
+    for (int c = 1; c < T; ++c) pool.emplace_back(work, c);
+    work(0);
+    for (auto& th : pool) th.join();
+}
+
+}  // namespace
+
+extern "C" int sfb_locality_permute(const sfb_reads* r, int n_threads, int64_t* order, int64_t* aln_index,
+                                    const sfb_reads* dst) {
+    if (!r || !dst || !order || (r->n_alns && !aln_index)) return SFB_E_ARG;
+    const int64_t G = r->n_groups, A = r->n_alns, R = r->n_records;
+    if (G < 0 || A < 0 || R < 0) return SFB_E_ARG;
+    const int T = std::max(1, std::min(n_threads, 64));
+    uint8_t* d_nmates = const_cast<uint8_t*>(dst->grp_nmates);
+    int64_t* d_grp_off = const_cast<int64_t*>(dst->grp_aln_off);
+    int32_t* d_seq_len = const_cast<int32_t*>(dst->mate_seq_len);
+    int64_t* d_walk_off = const_cast<int64_t*>(dst->aln_walk_off);
+    uint8_t* d_bins = const_cast<uint8_t*>(dst->aln_bins);
+    int32_t* d_node = const_cast<int32_t*>(dst->walk_node);
+    int32_t* d_alen = const_cast<int32_t*>(dst->walk_alen);
+    try {
+        // ---- keys: first node of the first retained alignment; none -> after every node ----
+        std::vector<uint32_t> key((size_t)G);
+        std::vector<uint32_t> max_part((size_t)T, 0);
+        for_chunks(T, (size_t)G, [&](int c, size_t lo, size_t hi) {
+            uint32_t mx = 0;
+            for (size_t g = lo; g < hi; ++g) {
+                const int64_t a0 = r->grp_aln_off[2 * g], a1 = r->grp_aln_off[2 * g + 2];
+                uint32_t k = 0xffffffffu;
+                if (a1 > a0 && R > 0) {
+                    const int64_t w = std::min<int64_t>(r->aln_walk_off[a0], R - 1);
+                    k = (uint32_t)r->walk_node[w];
+                    mx = std::max(mx, k);
+                }
+                key[g] = k;
+            }
+            max_part[c] = mx;
+        });
+        uint32_t top = 0;
+        for (uint32_t v : max_part) top = std::max(top, v);
+        const uint32_t none = top + 1;                     // groups without an alignment sort last
+        for_chunks(T, (size_t)G, [&](int, size_t lo, size_t hi) {
+            for (size_t g = lo; g < hi; ++g)
+                if (key[g] == 0xffffffffu) key[g] = none;
+        });
+        // ---- stable LSD radix sort of the group indices by key, 16 bits per pass ----
+        std::vector<int64_t> idx_a((size_t)G), idx_b((size_t)G);
+        for_chunks(T, (size_t)G, [&](int, size_t lo, size_t hi) {
+            for (size_t g = lo; g < hi; ++g) idx_a[g] = (int64_t)g;
+        });
+        int64_t* src = idx_a.data();
+        int64_t* out = idx_b.data();
+        const int passes = none >> 16 ? 2 : 1;
+        std::vector<std::vector<size_t>> hist((size_t)T, std::vector<size_t>(65536));
+        for (int pass = 0; pass < passes; ++pass) {
+            const int shift = 16 * pass;
+            for_chunks(T, (size_t)G, [&](int c, size_t lo, size_t hi) {
+                auto& h = hist[c];
+                std::fill(h.begin(), h.end(), 0);
+                for (size_t i = lo; i < hi; ++i) h[(key[src[i]] >> shift) & 0xffff] += 1;
+            });
+            size_t pos = 0;                                  // digit-major, chunk-minor: stable
+            for (size_t dgt = 0; dgt < 65536; ++dgt)
+                for (int c = 0; c < T; ++c) {
+                    const size_t n = hist[c][dgt];
+                    hist[c][dgt] = pos;
+                    pos += n;
+                }
+            for_chunks(T, (size_t)G, [&](int c, size_t lo, size_t hi) {
+                auto& h = hist[c];
+                for (size_t i = lo; i < hi; ++i) out[h[(key[src[i]] >> shift) & 0xffff]++] = src[i];
+            });
+            std::swap(src, out);
+        }
+        memcpy(order, src, (size_t)G * sizeof(int64_t));
+        // ---- offsets of the permuted arrays (serial prefix sums: one pass over the groups, one over the alignments) ----
+        d_grp_off[0] = 0;
+        for (int64_t k = 0; k < G; ++k) {
+            const int64_t g = order[k];
+            d_grp_off[2 * k + 1] = d_grp_off[2 * k] + (r->grp_aln_off[2 * g + 1] - r->grp_aln_off[2 * g]);
+            d_grp_off[2 * k + 2] = d_grp_off[2 * k + 1] + (r->grp_aln_off[2 * g + 2] - r->grp_aln_off[2 * g + 1]);
+        }
+        for_chunks(T, (size_t)G, [&](int, size_t lo, size_t hi) {
+            for (size_t k = lo; k < hi; ++k) {
+                const int64_t g = order[k];
+                d_nmates[k] = r->grp_nmates[g];
+                d_seq_len[2 * k] = r->mate_seq_len[2 * g];
+                d_seq_len[2 * k + 1] = r->mate_seq_len[2 * g + 1];
+                const int64_t n = r->grp_aln_off[2 * g + 2] - r->grp_aln_off[2 * g];
+                for (int64_t j = 0; j < n; ++j) aln_index[d_grp_off[2 * k] + j] = r->grp_aln_off[2 * g] + j;
+            }
+        });
+        if (A > 0 || d_walk_off) d_walk_off[0] = 0;
+        for (int64_t a = 0; a < A; ++a) {
+            const int64_t old = aln_index[a];
+            d_walk_off[a + 1] = d_walk_off[a] + (r->aln_walk_off[old + 1] - r->aln_walk_off[old]);
+        }
+        for_chunks(T, (size_t)A, [&](int, size_t lo, size_t hi) {
+            for (size_t a = lo; a < hi; ++a) {
+                const int64_t old = aln_index[a];
+                memcpy(d_bins + 5 * a, r->aln_bins + 5 * old, 5);
+                const int64_t w = r->aln_walk_off[old], n = r->aln_walk_off[old + 1] - w;
+                if (n > 0) {
+                    memcpy(d_node + d_walk_off[a], r->walk_node + w, (size_t)n * sizeof(int32_t));
+                    memcpy(d_alen + d_walk_off[a], r->walk_alen + w, (size_t)n * sizeof(int32_t));
+                }
+            }
+        });
+    } catch (const std::exception&) {
+        return SFB_E_ARG;                                    // out of memory
+    }
+    return SFB_OK;
+}

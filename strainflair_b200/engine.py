@@ -168,8 +168,7 @@ class HostReads:
         # results do not depend on the order; per-group / per-alignment outputs are put back in file order by fetch.
         self.order = self.aln_index = None
         if locality and reads.n_groups > 1:
-            self.order = reads.locality_order()
-            reads, self.aln_index = reads.permute_groups(self.order, return_index=True)
+            reads, self.order, self.aln_index = locality_permute(reads)
         self.reads = reads
         packed = _Packed(reads) if wire else None
         try:
@@ -326,6 +325,34 @@ class Result:
 
 class MatchOverflow(RuntimeError):
     pass
+
+
+def locality_permute(reads: Reads, threads=None):
+    """(reads in locality order, order, aln_index): schema.Reads.locality_order + permute_groups, done by the native
+    multi-threaded sfb_locality_permute (csrc/locality.cpp)."""
+    import os
+    G, A, R = reads.n_groups, reads.n_alns, reads.n_records
+    src = {k: np.ascontiguousarray(getattr(reads, k), dt).reshape(-1) for k, dt in (
+        ("grp_nmates", np.uint8), ("grp_aln_off", np.int64), ("mate_seq_len", np.int32), ("aln_walk_off", np.int64),
+        ("aln_bins", np.uint8), ("walk_node", np.int32), ("walk_alen", np.int32), ("exc_cov", np.float64))}
+    dst = dict(grp_nmates=np.empty(G, np.uint8), grp_aln_off=np.empty(2 * G + 1, np.int64),
+               mate_seq_len=np.empty(2 * G, np.int32), aln_walk_off=np.empty(A + 1, np.int64),
+               aln_bins=np.empty(5 * A, np.uint8), walk_node=np.empty(R, np.int32), walk_alen=np.empty(R, np.int32),
+               exc_cov=src["exc_cov"])
+    order, aln_index = np.empty(G, np.int64), np.empty(A, np.int64)
+    view = lambda d: _lib.SfbReads(n_groups=G, n_alns=A, n_records=R, n_exc=len(src["exc_cov"]),       # noqa: E731
+                                   **{k: v.ctypes.data for k, v in d.items()})
+    vs, vd = view(src), view(dst)
+    _lib.check(_lib.load().sfb_locality_permute(C.byref(vs), int(threads or len(os.sched_getaffinity(0))),
+                                                C.c_void_p(order.ctypes.data), C.c_void_p(aln_index.ctypes.data), C.byref(vd)))
+    names = None
+    if reads.mate_names is not None:
+        names = [reads.mate_names[2 * int(g) + m] for g in order for m in (0, 1)]
+    moved = Reads(grp_nmates=dst["grp_nmates"], grp_aln_off=dst["grp_aln_off"], mate_seq_len=dst["mate_seq_len"],
+                  aln_walk_off=dst["aln_walk_off"], aln_read_len=reads.aln_read_len[aln_index],
+                  aln_bins=dst["aln_bins"].reshape(A, 5), walk_node=dst["walk_node"], walk_alen=dst["walk_alen"],
+                  exc_cov=reads.exc_cov, mate_names=names)
+    return moved, order, aln_index
 
 
 def restore_file_order(res, order, aln_index):

@@ -467,3 +467,22 @@ def test_locality_staging_and_file_order_restoration():
     engine.restore_file_order(res, host.order, host.aln_index)
     assert np.array_equal(res.grp_code, base.grp_code) and np.array_equal(res.grp_code2, base.grp_code2)
     assert np.array_equal(res.aln_assign, base.aln_assign)
+
+
+@pytest.mark.parametrize("threads", [1, 3, 8])
+def test_native_locality_permutation_equals_numpy(threads):
+    """csrc/locality.cpp (stable radix sort of the groups + parallel copy) == Reads.locality_order + permute_groups,
+    whatever the number of threads; groups without alignments, empty and one-group inputs included."""
+    from strainflair_b200 import engine, synth
+    graph, reads = synth.make_config("small", scale=0.3)
+    cases = [reads, reads.slice_groups(0, 0), reads.slice_groups(7, 8), reads.slice_groups(100, 1500),
+             synth.make_reads(graph, 5, n_pairs=3000, read_len=150, p_low_score=0.6, p_single=0.5, p_exc=0.05)]
+    fields = ("grp_nmates", "grp_aln_off", "mate_seq_len", "aln_walk_off", "aln_read_len", "aln_bins", "walk_node",
+              "walk_alen", "exc_cov")
+    for rd in cases:
+        moved, order, aln_index = engine.locality_permute(rd, threads=threads)
+        want_order = rd.locality_order()
+        want, want_index = rd.permute_groups(want_order, return_index=True)
+        assert np.array_equal(order, want_order) and np.array_equal(aln_index, want_index)
+        for k in fields:
+            assert np.array_equal(getattr(moved, k), getattr(want, k)), k
