@@ -36,6 +36,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-shards", type=int, default=4)
     ap.add_argument("--no-det", action="store_true", help="skip the order-independent-mode measurement")
+    ap.add_argument("--locality", action="store_true",
+                    help="experimental: stage the read groups in locality order (host-side sort by first node, "
+                         "sfb_locality_permute) before they go to the device; reported in config.group_order")
     return ap.parse_args()
 
 
@@ -317,6 +320,11 @@ def run_ours(args):
 
     t_gen = time.perf_counter()
     reads = synth.make_reads(graph, synth.SEED0 + idx + 1000 + 7919 * rank, n_pairs=pairs, read_len=rkw["read_len"])
+    group_order = "file order"
+    if args.locality:
+        t_sort = time.perf_counter()
+        reads, _, _ = engine.locality_permute(reads)
+        group_order = f"locality order (host-side stable sort by first node, {time.perf_counter() - t_sort:.2f} s, outside the timed region)"
     t_gen = time.perf_counter() - t_gen
     eng = engine.AbundanceEngine(graph, device, comm=comm)
     host = engine.HostReads(reads, pin=True)
@@ -479,7 +487,7 @@ def run_ours(args):
                        "parallelism": f"read groups sharded over {world} GPU(s), graph replicated",
                        "groups_per_gpu": reads.n_groups, "alignments_per_gpu": reads.n_alns,
                        "records_per_gpu": reads.n_records, "paths": graph.n_paths, "nodes": graph.n_nodes,
-                       "slots": eng.dg.n_slots, "deferred_groups": stats.n_deferred,
+                       "slots": eng.dg.n_slots, "deferred_groups": stats.n_deferred, "group_order": group_order,
                        "mean_candidates_per_alignment": Cr["ST_CAND"] / max(1, reads.n_alns),
                        "mean_matches_per_alignment": Cr["ST_TUPLES"] / max(1, reads.n_alns)},
             "records_per_s": total_records * args.steps / (ms * 1e-3),
