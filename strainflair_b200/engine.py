@@ -399,6 +399,8 @@ class AbundanceEngine:
         self.work = None
         self.side = torch.cuda.Stream(device=self.device)     # pass-1 scatter runs beside the uniq exchange + pass-2 resolve
         self.overlap = True
+        import os
+        self.locality = bool(os.environ.get("SFB200_LOCALITY"))   # experimental, off by default: HostReads(locality=True)
         self.match_cap_hint = 0
         self.launches = 0
 
@@ -654,7 +656,7 @@ class AbundanceEngine:
         """Public entry: host arrays in, host results out (H2D and D2H included).  The reports need the
         per-path table, counters and histograms; ``keep_slots`` also brings the two per-node accumulator
         arrays back, ``keep_codes`` the per-group leaf codes, assignments and match lists."""
-        host = reads if isinstance(reads, HostReads) else HostReads(reads)
+        host = reads if isinstance(reads, HostReads) else HostReads(reads, locality=self.locality)
         for _ in range(3):
             dr = self.upload(host)
             work = self.run_device(dr)
