@@ -617,7 +617,7 @@ class AbundanceEngine:
                 f=torch.empty(3 * P, dtype=torch.float64).pin_memory(),
                 i=torch.empty(acc.i64.numel(), dtype=torch.int64).pin_memory(),
                 t=torch.empty((max(1, P), _lib.TABLE_COLS), dtype=torch.float64).pin_memory(),
-                c=torch.empty((len(live), 8), dtype=torch.int64).pin_memory())
+                c=torch.empty((max(1, len(live)), 8), dtype=torch.int64).pin_memory())
         st = job.stage
         st["f"].copy_(acc.f64[:3 * P], non_blocking=True)
         st["i"].copy_(acc.i64, non_blocking=True)
@@ -639,7 +639,7 @@ class AbundanceEngine:
             if res.C["MATCH_OVERFLOW"] == 0:
                 job.pending = False
                 res.n_deferred = int(cur[:len(job.live), 1].sum())
-                res.match_fill = int(cur[len(job.live) - 1, 0])
+                res.match_fill = int(cur[len(job.live) - 1, 0]) if job.live else 0
                 check_errors(res.C)
                 return res
             for k in range(len(job.live)):            # grow every shard's match buffer to its exact need, rerun
