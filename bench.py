@@ -35,10 +35,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-shards", type=int, default=4)
-    ap.add_argument("--no-det", action="store_true", help="skip the order-independent-mode measurement")
-    ap.add_argument("--locality", action="store_true",
-                    help="experimental: stage the read groups in locality order (host-side sort by first node, "
-                         "sfb_locality_permute) before they go to the device; reported in config.group_order")
+    ap.add_argument("--no-det", action="store_true", help="skip the measurements of the other modes (plain fp64 atomics, global-memory kernels)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C4 / C5 sub-measurements")
     return ap.parse_args()
 
 
@@ -55,7 +53,7 @@ def workload_name(args):
 # ------------------------------------------------------------------------------------------------
 def cpu_port_rate(graph_d, reads_d, cores, repeats=1):
     """Times the oracle's abundance pass (decode excluded, like the GPU arm) on ``cores`` processes.
-    Returns (reads/s, records/s, seconds per pass)."""
+    Returns (reads/s, records/s, seconds per pass, result of the last pass as a dict of arrays)."""
     from oracle import abundance as oa
     from oracle import parallel as op
     n_reads = int(reads_d["grp_nmates"].sum())
@@ -65,20 +63,24 @@ def cpu_port_rate(graph_d, reads_d, cores, repeats=1):
         idx = oa.AbundanceOracle.build_index(graph_d)
         for _ in range(repeats):
             t0 = time.perf_counter()
-            oa.AbundanceOracle(graph_d, reads_d, index=idx).run()
+            orc = oa.AbundanceOracle(graph_d, reads_d, index=idx).run()
             dt = time.perf_counter() - t0
             best = dt if best is None else min(best, dt)
+        import numpy as np
+        out = dict(C=orc.C, uniq_reads=np.asarray(orc.uniq_reads, np.int64), hist=orc.hist, n_deferred=len(orc.deferred),
+                   mult_hits=np.array([not isinstance(v, int) for v in orc.mult_reads]),
+                   **{k: np.asarray(getattr(orc, k), np.float64) for k in ("uniq_norm", "mult_reads", "mult_norm", "uniq_abund", "mult_abund")})
     else:
         po = op.ParallelOracle(graph_d, reads_d, cores=cores)
         try:
             for _ in range(repeats):
                 t0 = time.perf_counter()
-                po.run()
+                out = po.run()
                 dt = time.perf_counter() - t0
                 best = dt if best is None else min(best, dt)
         finally:
             po.close()
-    return n_reads / best, n_rec / best, best
+    return n_reads / best, n_rec / best, best, out
 
 
 def decode_rates(graph, synth, idx, rkw, n_pairs):
@@ -186,7 +188,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32/f64", "data": "synthetic",
-        "config": {"workload": workload_name(args)},
+        "config": config_dict(args, args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "records_per_s": len(rd["walk_node"]) * args.steps / dt,
@@ -279,6 +281,151 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+KERNEL_STAGES = ("tile_pass1", "match", "classify", "tile_pass2", "pass2_resolve", "pass2_scatter", "path_reduce")
+
+
+def check_parity(res, ref, what):
+    """GPU result against the CPU port's on the same read sample: integers exact, fp64 within 1e-9 relative with the
+    same zero pattern (north_star).  Raises on a difference."""
+    import numpy as np
+    for k, v in ref["C"].items():
+        assert int(res.C[k]) == int(v), (what, k, res.C[k], v)
+    assert np.array_equal(res.uniq_reads, ref["uniq_reads"]), what
+    assert np.array_equal(res.hist, ref["hist"]), what
+    assert res.n_deferred == ref["n_deferred"], (what, res.n_deferred, ref["n_deferred"])
+    assert np.array_equal(res.mult_hits > 0, ref["mult_hits"]), what
+    for name in ("uniq_norm", "mult_reads", "mult_norm", "uniq_abund", "mult_abund"):
+        a, b = np.asarray(getattr(res, name), np.float64), np.asarray(ref[name], np.float64)
+        assert a.shape == b.shape, (what, name)
+        bad = np.flatnonzero(np.abs(a - b) > 1e-9 * np.maximum(np.abs(a), np.abs(b)))
+        assert bad.size == 0, (what, name, bad[:5], a[bad[:5]], b[bad[:5]])
+        assert np.array_equal(a > 0, b > 0), (what, name, "zero pattern")
+    return {"status": "ok", "against": what,
+            "checked": "20 counters, uniq_reads, histograms, deferred groups: exact; 5 fp64 accumulators: <= 1e-9 relative, "
+                       "identical zero pattern"}
+
+
+def device_pass(eng, reads, steps, warmup, world, dist, device, want_marks=True):
+    """Stages ``reads`` for ``eng``, uploads them once and times ``steps`` passes with the inputs resident in HBM.
+    Returns (ms for all steps [max over ranks], per-stage ms, stats of one pass, launches per step, host staging)."""
+    import torch
+    from strainflair_b200 import _lib
+    t0 = time.perf_counter()
+    host = eng.stage(reads, pin=True)
+    stage_s = time.perf_counter() - t0
+    dr = eng.upload(host)
+    torch.cuda.synchronize()
+    done = 0
+    while done < max(warmup, 1):          # warm-up (also settles the match-buffer capacity)
+        work = eng.run_device(dr)
+        torch.cuda.synchronize()
+        over = int(eng.acc.counters[_lib.COUNTER_NAMES.index("MATCH_OVERFLOW")].item())
+        if over:                          # grow the match buffer to the exact need; not a warm-up step
+            eng.match_cap_hint = int(work.t["cursor"][0].item()) + 1024
+            continue
+        done += 1
+    stats = eng.fetch(work, dr, keep_codes=False, keep_slots=False)
+    assert stats.C["MATCH_OVERFLOW"] == 0
+    launches0 = eng.launches
+    marks_all = []
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        marks = [] if want_marks else None
+        eng.run_device(dr, marks)
+        if want_marks:
+            marks_all.append(marks)
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    stage_ms = {}
+    for marks in marks_all:
+        for (_, e_prev), (name, e) in zip(marks[:-1], marks[1:]):
+            stage_ms[name] = stage_ms.get(name, 0.0) + e_prev.elapsed_time(e) / steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms, stage_ms, stats, (eng.launches - launches0) // max(1, steps), host, stage_s, dr
+
+
+def roofline_block(args, graph, eng, reads, host, stats, stage_ms, world):
+    from strainflair_b200 import roofline
+    Cr = dict(stats.C)
+    if world > 1:                 # the counters were summed over ranks; the roofline line is per GPU
+        Cr = {k: v // world for k, v in Cr.items()}
+    by = roofline.kernel_bytes(reads.n_groups, reads.n_alns, reads.n_records, graph.n_paths, eng.dg.n_slots,
+                               Cr, stats.match_fill, stats.n_deferred, graph.n_strains,
+                               tile_groups=host.grp_begin, tile_alns=host.aln_begin)
+    kernels = {k: v for k, v in stage_ms.items() if k in KERNEL_STAGES and by.get(k, 0) > 0}
+    top = max(kernels, key=kernels.get)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = by[top] / (kernels[top] * 1e-3) / 1e9
+    traffic = traffic_src = None
+    try:                      # DRAM bytes per launch of that kernel from the committed ncu capture of this workload
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            tj = json.load(fh)
+        traffic = tj.get(f"{args.config}@{args.scale}", {}).get(top)
+        traffic_src = tj.get("source")
+    except Exception:
+        pass
+    t_all = sum(kernels.values()) * 1e-3
+    whole, survey, stream = by["total"] / t_all / 1e9, by["survey_total"] / t_all / 1e9, by["stream_total"] / t_all / 1e9
+    return {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": traffic,
+            "traffic_source": ("profile constant: " + traffic_src) if traffic_src else None,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
+            "algorithmic_bytes": by[top], "kernel_ms": kernels[top],
+            "whole_pass": {"achieved": whole, "frac": whole / peak, "algorithmic_bytes": by["total"]},
+            "whole_pass_survey_formula": {"achieved": survey, "frac": survey / peak,
+                                          "algorithmic_bytes": by["survey_total"],
+                                          "bytes_per_record": by["survey_total"] / max(1, reads.n_records)},
+            "whole_pass_streamed_bytes": {"what": "bytes the tile design must move through HBM: every input array once in "
+                                                  "pass 1, the deferred groups again in pass 2, outputs, accumulator flushes",
+                                          "achieved": stream, "frac": stream / peak, "bytes": by["stream_total"]},
+            "per_kernel": {k: {"ms": round(kernels[k], 4), "GBps": by[k] / (kernels[k] * 1e-3) / 1e9,
+                               "frac": by[k] / (kernels[k] * 1e-3) / 1e9 / peak} for k in kernels}}
+
+
+def extra_config(name, scale, steps, device, comm, world, rank, dist, strong=False):
+    """Device-resident pass on another BASELINE.json configuration (C4: ~8+ candidate paths per read; C5: the 20 M-node
+    graph), a few steps, reported beside the headline workload.  ``strong``: the configuration's reads are split over
+    the ranks (strong scaling) instead of one ``scale`` share per rank."""
+    import torch
+    from strainflair_b200 import engine, synth
+    gkw, rkw = synth.CONFIGS[name]
+    idx = list(synth.CONFIGS).index(name)
+    graph = synth.make_graph(synth.SEED0 + idx, **gkw)
+    pairs = max(1, int(rkw["n_pairs"] * scale / (world if strong else 1)))
+    reads = synth.make_reads(graph, synth.SEED0 + idx + 1000 + 7919 * rank, n_pairs=pairs, read_len=rkw["read_len"])
+    eng = engine.AbundanceEngine(graph, device, comm=comm)
+    ms, stage_ms, stats, launches, host, stage_s, dr = device_pass(eng, reads, steps, 2, world, dist, device)
+    tot = torch.tensor([float(reads.n_mates), float(reads.n_records)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tot)
+    out = {"workload": f"{name}: {pairs} read pairs/GPU, {graph.n_nodes} nodes, {graph.n_paths} paths, {eng.dg.n_slots} slots",
+           "scaling": "strong" if strong else "weak", "ms_per_step": ms / steps, "steps": steps,
+           "reads_per_s": float(tot[0].item()) * steps / (ms * 1e-3), "records_per_s": float(tot[1].item()) * steps / (ms * 1e-3),
+           "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
+           "groups_in_tiles": host.grp_begin / max(1, reads.n_groups), "deferred_groups": stats.n_deferred,
+           "mean_matches_per_alignment": (stats.C["ST_TUPLES"] / max(1, world)) / max(1, reads.n_alns),
+           "host_staging_s": round(stage_s, 2)}
+    del eng, dr, host, reads, graph
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -289,27 +436,30 @@ def run_ours(args):
     graph = synth.make_graph(synth.SEED0 + idx, **gkw)
     pairs = max(1, int(rkw["n_pairs"] * args.scale))
 
-    # CPU baseline first (forks workers; do it before CUDA is initialised)
-    cpu = None
+    # CPU baseline first (forks workers; do it before CUDA is initialised); its result is kept for the parity check
+    cpu = cpu_out = cpu_sample = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = len(os.sched_getaffinity(0))
-        # one run of ~13 s on 16 cores (the reference arm repeats a 2.5x smaller sample --steps times)
         sp = min(int(2.5 * args.cpu_sample_pairs), pairs)
-        sample = synth.make_reads(graph, synth.SEED0 + idx + 1000, n_pairs=sp, read_len=rkw["read_len"])
-        rate, rec_rate, secs = cpu_port_rate(graph.as_dict(), sample.as_dict(), cores)
+        cpu_sample = synth.make_reads(graph, synth.SEED0 + idx + 1000, n_pairs=sp, read_len=rkw["read_len"])
+        rate, rec_rate, secs, cpu_out = cpu_port_rate(graph.as_dict(), cpu_sample.as_dict(), cores)
+        one = min(sp, 40_000)
+        rate1, _, secs1, _ = cpu_port_rate(graph.as_dict(), cpu_sample.slice_groups(0, one).as_dict(), 1)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "records_per_s": rec_rate,
+               "single_process": {"value": rate1, "unit": UNIT, "sample_pairs": one, "seconds": round(secs1, 1)},
+               "speedup_over_single_process": rate / rate1,
                "sample": f"first {sp} read pairs of the workload, oracle port (Python) sharded over {cores} processes, "
                          f"decode excluded, {secs:.1f} s"}
-        del sample
 
     # decode, reported separately (north_star): native streaming decoder on all cores vs the oracle's Python decoder
     dec = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         dec = decode_rates(graph, synth, idx, rkw, min(40_000, pairs))
 
+    import numpy as np
     import torch
     import torch.distributed as dist
-    from strainflair_b200 import _lib, engine, roofline
+    from strainflair_b200 import engine
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     comm = None
@@ -320,104 +470,73 @@ def run_ours(args):
 
     t_gen = time.perf_counter()
     reads = synth.make_reads(graph, synth.SEED0 + idx + 1000 + 7919 * rank, n_pairs=pairs, read_len=rkw["read_len"])
-    group_order = "file order"
-    if args.locality:
-        t_sort = time.perf_counter()
-        reads, _, _ = engine.locality_permute(reads)
-        group_order = f"locality order (host-side stable sort by first node, {time.perf_counter() - t_sort:.2f} s, outside the timed region)"
     t_gen = time.perf_counter() - t_gen
+    # headline: the default engine -- tile kernels, order-independent (deterministic) accumulation
     eng = engine.AbundanceEngine(graph, device, comm=comm)
-    host = engine.HostReads(reads, pin=True)
-    dr = eng.upload(host)
-    torch.cuda.synchronize()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-
-    # warm-up (also settles the match-buffer capacity)
-    done = 0
-    while done < max(args.warmup, 1):
-        work = eng.run_device(dr)
-        torch.cuda.synchronize()
-        over = int(eng.acc.counters[_lib.COUNTER_NAMES.index("MATCH_OVERFLOW")].item())
-        if over:                              # grow the match buffer to the exact need; not a warm-up step
-            eng.match_cap_hint = int(work.t["cursor"][0].item()) + 1024
-            continue
-        done += 1
-    stats = eng.fetch(work, dr, keep_codes=False)
-    assert stats.C["MATCH_OVERFLOW"] == 0
-
     sampler = ClockSampler(local)
     sampler.start()
-    launches0 = eng.launches
-    marks_all = []
-    barrier()
-    torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        marks = []
-        eng.run_device(dr, marks)
-        marks_all.append(marks)
-    ev1.record()
-    torch.cuda.synchronize()
-    barrier()
+    ms, stage_ms, stats, launches, host, stage_s, dr = device_pass(eng, reads, args.steps, args.warmup, world, dist, device)
     sampler.stop_flag = True
-    ms = ev0.elapsed_time(ev1)
-    launches = eng.launches - launches0
-    # per-stage device time (CUDA events on the launching stream)
-    stage_ms = {}
-    for marks in marks_all:
-        for (_, e_prev), (name, e) in zip(marks[:-1], marks[1:]):
-            stage_ms[name] = stage_ms.get(name, 0.0) + e_prev.elapsed_time(e) / args.steps
 
-    n_reads = stats.C["NB_READS"] if world == 1 else None
     local_reads = int(reads.grp_nmates.sum())
-    tot = torch.tensor([ms, float(local_reads), float(reads.n_records), float(reads.n_alns)], dtype=torch.float64, device=device)
+    tot = torch.tensor([float(local_reads), float(reads.n_records), float(reads.n_alns)], dtype=torch.float64, device=device)
     if world > 1:
-        mx = tot.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        ms = float(mx[0].item())
-    total_reads, total_records, total_alns = float(tot[1].item()), float(tot[2].item()), float(tot[3].item())
+    total_reads, total_records, total_alns = float(tot[0].item()), float(tot[1].item()), float(tot[2].item())
     value = total_reads * args.steps / (ms * 1e-3)
 
-    # the same pass with order-independent fp64 accumulation (three exact partial sums per accumulator)
-    det = None
+    # parity: the same engine on the CPU arm's sample, against the CPU port's result of that run
+    parity = None
+    if cpu_out is not None:
+        parity = check_parity(eng.run(cpu_sample), cpu_out, f"oracle port on the first {cpu_sample.n_groups} read pairs of the workload")
+        parity["global_kernels"] = check_parity(engine.AbundanceEngine(graph, device, tiles=False).run(cpu_sample), cpu_out,
+                                                "same sample, global-memory kernels")["status"]
+    elif world > 1:
+        # rank-count independence: a fixed sample split over the ranks against the same sample on one rank
+        sample = synth.make_reads(graph, synth.SEED0 + idx + 555, n_pairs=min(200_000, pairs), read_len=rkw["read_len"])
+        from strainflair_b200 import dist as sfdist
+        a, b = sfdist.shard_bounds(sample.n_groups, world, rank)
+        many = eng.run(sample.slice_groups(a, b), keep_codes=False, keep_slots=False)
+        if rank == 0:
+            one = engine.AbundanceEngine(graph, device).run(sample, keep_codes=False, keep_slots=False)
+            for k in one.C:
+                if not k.startswith("ST_") and k != "MATCH_OVERFLOW":
+                    assert one.C[k] == many.C[k], (k, one.C[k], many.C[k])
+            assert np.array_equal(one.uniq_reads, many.uniq_reads) and np.array_equal(one.hist, many.hist)
+            for name in ("uniq_norm", "mult_reads", "mult_norm", "table"):
+                assert np.array_equal(getattr(one, name), getattr(many, name), equal_nan=True), name
+            parity = {"status": "ok", "against": f"one rank on the same {sample.n_groups} read pairs",
+                      "checked": f"counters, uniq_reads, histograms exact; per-path fp64 sums and the gene table bit-identical "
+                                 f"between 1 and {world} ranks (order-independent accumulation)"}
+
+    # the plain accumulation mode (fp64 REDs, not reproducible) and the global-memory kernels, for comparison
+    alt = {}
     if not args.no_det:
-        eng_d = engine.AbundanceEngine(graph, device, comm=comm, deterministic=True)
-        eng_d.match_cap_hint = eng.match_cap_hint
-        for _ in range(2):
-            eng_d.run_device(dr)
-        barrier()
-        torch.cuda.synchronize()
-        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        d0.record()
-        for _ in range(args.steps):
-            eng_d.run_device(dr)
-        d1.record()
-        torch.cuda.synchronize()
-        td = torch.tensor([d0.elapsed_time(d1)], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(td, op=dist.ReduceOp.MAX)
-        det = {"ms_per_step": float(td.item()) / args.steps, "value": total_reads * args.steps / (float(td.item()) * 1e-3),
-               "unit": UNIT, "note": "bit-identical results across runs, shard counts and GPU counts"}
-        del eng_d
+        for key, kw in (("plain_fp64_atomics", dict(deterministic=False)), ("global_memory_kernels", dict(tiles=False))):
+            e2 = engine.AbundanceEngine(graph, device, comm=comm, **kw)
+            e2.match_cap_hint = eng.match_cap_hint
+            ms2, st2, _, _, _, _, dr2 = device_pass(e2, reads, max(3, args.steps // 4), 2, world, dist, device)
+            n2 = max(3, args.steps // 4)
+            alt[key] = {"ms_per_step": ms2 / n2, "value": total_reads * n2 / (ms2 * 1e-3), "unit": UNIT,
+                        "stage_ms": {k: round(v, 4) for k, v in st2.items()}}
+            del e2, dr2
+            torch.cuda.empty_cache()
 
     # end to end: pinned host buffers -> device -> kernels -> results on the host, every step
     e2e = None
     if not args.no_e2e:
-        # the data set staged as 8 pinned shards: uploads overlap with match / classify of the previous shard
         from strainflair_b200 import dist as sfdist
+        del dr
         cuts = [sfdist.shard_bounds(reads.n_groups, args.e2e_shards, k) for k in range(args.e2e_shards)]
-        shards = [engine.HostReads(reads.slice_groups(a, b), pin=True) for a, b in cuts]
+        t0 = time.perf_counter()
+        shards = [eng.stage(reads.slice_groups(a, b), pin=True) for a, b in cuts]
+        pack_s = time.perf_counter() - t0
         h2d = sum(s_.nbytes() for s_ in shards)
-        del host
         from collections import deque
         eng.run_stream(shards)
         eng.run_stream(shards)
-        barrier()
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize()
         # one step alone: upload, kernels, read-back, nothing else in flight (latency of a single data set)
         t0 = time.perf_counter()
@@ -433,7 +552,8 @@ def run_ours(args):
             pending.append(eng.submit(shards, depth=2))
         while pending:
             eng.collect(pending.popleft())
-        barrier()
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(args.steps):
@@ -453,67 +573,72 @@ def run_ours(args):
         d2h = eng.d2h_bytes(keep_slots=False) * world
         e2e = {"value": total_reads * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "shards": args.e2e_shards,
                "d2h_bytes_per_step": d2h, "ms_per_step": dt / args.steps * 1e3, "steps_in_flight": 2,
-               "single_step_ms": float(t_single.item()) * 1e3}
+               "single_step_ms": float(t_single.item()) * 1e3,
+               "pack_ms": pack_s * 1e3,
+               "pack_note": "host staging of one step's decoded reads (tile order + transfer layout + copy into pinned "
+                            "arenas, native, all host threads), done once outside the timed region: in a job it belongs to "
+                            "the decode stage, which is reported separately"}
+        del shards
+
+    extras = {}
+    if not args.no_extras and args.config == "c3" and args.scale == 1.0:
+        del reads
+        torch.cuda.empty_cache()
+        if world == 1:
+            extras["c4"] = extra_config("c4", 1.0, 5, device, comm, world, rank, dist)
+            extras["c5q"] = extra_config("c5", 0.25, 5, device, comm, world, rank, dist)
+        else:
+            extras["c5"] = extra_config("c5", 1.0, 5, device, comm, world, rank, dist, strong=True)
 
     if rank == 0:
-        Cr = dict(stats.C)
-        if world > 1:            # the counters were summed over ranks; the roofline line is per GPU
-            Cr = {k: v // world for k, v in Cr.items()}
-        by = roofline.kernel_bytes(reads.n_groups, reads.n_alns, reads.n_records, graph.n_paths, eng.dg.n_slots,
-                                   Cr, stats.match_fill, stats.n_deferred, graph.n_strains)
-        kernels = {k: v for k, v in stage_ms.items() if k in by and k not in ("total", "survey_total", "pass2")}
-        top = max(kernels, key=kernels.get)
-        peaks = {}
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
-                peaks = json.load(fh)
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = by[top] / (kernels[top] * 1e-3) / 1e9
-        traffic = None
-        try:                      # DRAM bytes per launch of that kernel from the committed ncu capture of this workload
-            with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-                traffic = json.load(fh).get(f"{args.config}@{args.scale}", {}).get(top)
-        except Exception:
-            pass
-        whole = by["total"] / (sum(kernels.values()) * 1e-3) / 1e9
-        survey = by["survey_total"] / (sum(kernels.values()) * 1e-3) / 1e9
+        reads_n = {"groups": host.n_groups, "alns": host.n_alns, "records": host.n_records}
+
+        class _R:            # sizes of this rank's shard for the roofline arithmetic
+            n_groups, n_alns, n_records = reads_n["groups"], reads_n["alns"], reads_n["records"]
+        Cr = {k: v // world for k, v in stats.C.items()} if world > 1 else dict(stats.C)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32/f64", "data": "synthetic",
-            "config": {"workload": workload_name(args), "l2": "inputs (GBs of walk arrays) exceed the 126 MB L2",
-                       "parallelism": f"read groups sharded over {world} GPU(s), graph replicated",
-                       "groups_per_gpu": reads.n_groups, "alignments_per_gpu": reads.n_alns,
-                       "records_per_gpu": reads.n_records, "paths": graph.n_paths, "nodes": graph.n_nodes,
-                       "slots": eng.dg.n_slots, "deferred_groups": stats.n_deferred, "group_order": group_order,
-                       "mean_candidates_per_alignment": Cr["ST_CAND"] / max(1, reads.n_alns),
-                       "mean_matches_per_alignment": Cr["ST_TUPLES"] / max(1, reads.n_alns)},
+            "config": config_dict(args, world),
+            "workload_stats": workload_stats(args, world, _R, graph, eng, stats, Cr, host),
+            "accumulation": "order-independent (96-bit fixed point): results bit-identical across runs, shard counts and GPU counts",
+            "parity": parity,
             "records_per_s": total_records * args.steps / (ms * 1e-3),
             "alignments_per_s": total_alns * args.steps / (ms * 1e-3),
-            "gpu_launches": launches,
+            "gpu_launches": launches * args.steps,
             "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
-            "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
-                         "algorithmic_bytes": by[top], "kernel_ms": kernels[top],
-                         "whole_pass": {"achieved": whole, "frac": whole / peak, "algorithmic_bytes": by["total"]},
-                         "whole_pass_survey_formula": {"achieved": survey, "frac": survey / peak,
-                                                       "algorithmic_bytes": by["survey_total"],
-                                                       "bytes_per_record": by["survey_total"] / max(1, reads.n_records)},
-                         "per_kernel": {k: {"ms": round(kernels[k], 4), "GBps": by[k] / (kernels[k] * 1e-3) / 1e9,
-                                            "frac": by[k] / (kernels[k] * 1e-3) / 1e9 / peak} for k in kernels}},
+            "roofline": roofline_block(args, graph, eng, _R, host, stats, stage_ms, world),
             "clocks": sampler.summary(),
             "e2e": e2e,
             "cpu_baseline": cpu,
             "decode": dec,
-            "order_independent_mode": det,
+            "other_modes": alt,
+            "extra": extras,
+            "host_staging_s": round(stage_s, 2),
             "gen_seconds": round(t_gen, 1),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def config_dict(args, world):
+    """The same dictionary from both arms (the driver compares them)."""
+    return {"workload": workload_name(args), "l2": "inputs (GBs of walk arrays) exceed the 126 MB L2",
+            "parallelism": f"read groups sharded over {world} GPU(s), graph replicated"}
+
+
+def workload_stats(args, world, R, graph, eng, stats, Cr, host):
+    return {"groups_per_gpu": R.n_groups, "alignments_per_gpu": R.n_alns,
+            "records_per_gpu": R.n_records, "paths": graph.n_paths, "nodes": graph.n_nodes,
+            "slots": eng.dg.n_slots, "deferred_groups": stats.n_deferred,
+            "group_order": "tile order (host staging: read groups sorted by the graph tile that holds them, the rest last)",
+            "tiles": 0 if eng.tiling is None else eng.tiling.n_tiles,
+            "groups_in_tiles": host.grp_begin / max(1, R.n_groups),
+            "tile_tuple_cap": None if eng.tiling is None else eng.tiling.tuple_cap,
+            "mean_candidates_per_alignment": Cr["ST_CAND"] / max(1, R.n_alns),
+            "mean_matches_per_alignment": Cr["ST_TUPLES"] / max(1, R.n_alns)}
 
 
 def main():

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SFB_ABI_VERSION 9
+#define SFB_ABI_VERSION 10
 
 /* ---- status codes ---------------------------------------------------- */
 #define SFB_OK            0
@@ -173,8 +173,9 @@ typedef struct sfb_work {
     int32_t*  match_buf;          /* [2*match_cap] (code, path id) pairs (8-byte aligned)     */
     int64_t   match_cap;          /* pairs; < 2^31                                            */
     unsigned long long* cursor;   /* [8]   [0] match_buf fill (pairs), [1] deferred groups, [2] app_buf fill,
-                                           [3]/[4] groups handed to the generic kernels of classify / pass 2;
-                                           zero before sfb_match                              */
+                                           [3]/[4] groups handed to the generic kernels of classify / pass 2,
+                                           [5]/[6] work items taken by sfb_tile_pass1 / sfb_tile_pass2, [7] groups
+                                           deferred inside tiles; zero before the first call of a pass          */
     uint8_t*  grp_code;           /* [G]                                                      */
     uint8_t*  grp_code2;          /* [G]   zero before sfb_pass2                              */
     int32_t*  aln_assign;         /* [A]   >= 0: match code of the unique assignment (:945,:958,:996);
@@ -186,6 +187,9 @@ typedef struct sfb_work {
                                            share}: scratch between the two kernels of sfb_pass2; the number
                                            of matches of a shard (<= A + match_cap) always suffices     */
     int64_t   app_cap;
+    int64_t   grp_begin, aln_begin; /* first read group / alignment owned by the global-memory kernels (sfb_match,
+                                           sfb_classify, sfb_pass1_scatter); the groups before it are in tile order and
+                                           belong to sfb_tile_pass1 / sfb_tile_pass2.  0, 0 without tiles             */
 } sfb_work;
 
 /* ---- accumulators (Path counters, json2csv.py:113-118, and histograms) ---- */
@@ -200,13 +204,34 @@ typedef struct sfb_accum {
     unsigned long long* hist;     /* [5*n_strains*101]                                        */
     long long* counters;          /* [SFB_N_COUNTERS]                                         */
     int64_t    det_stride;        /* 0: fp64 RED.ADD straight into the five fp64 arrays (order of the additions, hence
-                                     the last bits, vary from run to run).  > 0: order-independent accumulation --
-                                     every array has three planes, plane k of x at x + k*det_stride doubles; a term
-                                     is split into multiples of 2^-16, 2^-40 and 2^-64, each plane's sums are exact
-                                     in fp64 (up to 2^29 terms), so the result does not depend on thread order,
-                                     sharding or GPU count; sfb_accum_collapse folds the planes before
-                                     sfb_path_reduce                                                         */
+                                     the last bits, vary from run to run).  > 0: order-independent accumulation in
+                                     96-bit fixed point -- a term v is the integer floor(v * 2^64); every array has two
+                                     64-bit INTEGER planes, plane 0 at x (units of 2^-32), plane 1 at x + det_stride
+                                     (units of 2^-64); integer sums are exact, so the result does not depend on thread
+                                     order, sharding or GPU count (sum the planes over ranks as int64);
+                                     sfb_accum_collapse turns the planes into fp64 before sfb_path_reduce.  Terms and
+                                     per-accumulator totals must stay below 2^31                              */
 } sfb_accum;
+
+/* ---- tiles: parts of the graph that fit in shared memory ------------------------------------
+ * A tile is a set of colored paths with consecutive ids [p0, p1) whose nodes have consecutive dense indices inside
+ * [n0, n1), such that no path outside the tile crosses a node of [n0, n1) (a cluster of the pangenome, or a few
+ * small neighbouring clusters: StrainFLAIR builds one variation graph per gene cluster and concatenates their id
+ * spaces, graphs_construction.py:88, concat_graphs.py).  Every alignment whose first and last node lie in the tile
+ * can only match paths of the tile, so a thread block that holds the tile's path nodes, occurrence index and slot
+ * accumulators in shared memory runs get_matching_path, the decision tree and the node loops of such read groups
+ * without touching the graph or the accumulators in HBM.  Limits per tile: 32767 slots, 255 paths, 65520 nodes.
+ * Read groups are staged in tile order (sfb_tile_permute); the others (mates in different tiles, nodes outside
+ * every tile, no alignment at all) follow and go through the global-memory kernels. */
+typedef struct sfb_tiles {
+    int64_t n_tiles, n_items;
+    int64_t max_slots, max_nodes, max_paths;  /* of the largest tile: sizes the shared memory of the tile kernels  */
+    int64_t tuple_cap;             /* match tuples per mate kept in shared memory (8, 16 or 32); aligned pairs with
+                                      more are handed to the global-memory kernels through w->slow              */
+    const int32_t* tile_desc;      /* [4*n_tiles] (p0, p1, n0, n1) per tile                                     */
+    const int32_t* items;          /* [4*n_items] (tile, first group, end group, 0): work items of this read shard,
+                                      a tile with many groups is cut into several                               */
+} sfb_tiles;
 
 /* ---- entry points ------------------------------------------------------- */
 int         sfb_abi_version(void);
@@ -244,7 +269,22 @@ int sfb_pass2_resolve(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_a
                       const long long* uniq_reads_global, void* stream);
 int sfb_pass2_scatter(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_accum* acc, void* stream);
 
-/* Order-independent mode only (acc->det_stride > 0): x[i] = (plane0 + plane1) + plane2 for the n doubles at x. */
+/* Tile kernels: match + pass-1 decision tree + per-read and node-level parts of fill_abund_dist in one kernel
+ * (json2csv.py:341-363, :828-1053, :321-339) for the read groups of t->items; then, once uniq_reads is complete over
+ * all read shards, pass 2 for their deferred groups (json2csv.py:1085-1274; matches are recomputed from shared memory
+ * as the reference recomputes them from the file).  Outputs as the global-memory kernels': grp_code, grp_code2,
+ * aln_assign, the accumulators (shared-memory bins in 96-bit fixed point, flushed once per work item), counters,
+ * histograms.  Aligned pairs with more than t->tuple_cap match tuples in a mate get their match lists written to
+ * aln_match / match_buf and are appended to w->slow: call sfb_classify afterwards (it classifies them, adds their
+ * node loops itself and leaves their deferred ones to sfb_pass2). */
+int sfb_tile_pass1(const sfb_graph* g, const sfb_tiles* t, const sfb_reads* r, sfb_work* w, sfb_accum* acc, void* stream);
+int sfb_tile_pass2(const sfb_graph* g, const sfb_tiles* t, const sfb_reads* r, sfb_work* w, sfb_accum* acc,
+                   const long long* uniq_reads_global, void* stream);
+/* Dynamic shared memory (bytes) the tile kernels need for these tiles; SFB_E_ARG when a tile exceeds the limits. */
+int64_t sfb_tile_smem_bytes(const sfb_tiles* t);
+
+/* Order-independent mode only (acc->det_stride > 0): x[i] = plane0[i] * 2^-32 + plane1[i] * 2^-64 (fp64) for the n
+ * accumulators at x. */
 int sfb_accum_collapse(double* x, int64_t n, int64_t det_stride, void* stream);
 
 /* Pangenome.print_gene_table's per-path reductions (json2csv.py:440-469) for paths
@@ -311,6 +351,13 @@ void         sfb_packed_free(sfb_packed* p);
  * (exc_cov is shared: explicit-coverage records keep their index).  order[G]: old index of new group k; aln_index[A]: old
  * index of new alignment k (per-alignment side arrays and outputs follow it).  The result does not depend on n_threads. */
 int sfb_locality_permute(const sfb_reads* src, int n_threads, int64_t* order, int64_t* aln_index, const sfb_reads* dst);
+
+/* Tile order (see sfb_tiles): as sfb_locality_permute, but the key of a group is the tile that holds the first and
+ * the last node of every one of its alignments (node_tile[n] = tile of dense node n, -1 = none); groups without such
+ * a tile -- and groups without any alignment -- go last, in file order.  tile_grp_off[n_tiles + 2]: the groups of tile
+ * t are [off[t], off[t+1]) of the permuted order, the others [off[n_tiles], off[n_tiles+1] = G). */
+int sfb_tile_permute(const sfb_reads* src, const int32_t* node_tile, int64_t n_tiles, int n_threads, int64_t* order,
+                     int64_t* aln_index, const sfb_reads* dst, int64_t* tile_grp_off);
 
 /* ---- host-side analysis of the unassigned reads (no GPU involved) ---------------------------
  * Cluster.min_strains_inference (json2csv.py:149-201, with canonical_tiny :63-71, check_incomp_comp :83-97, sublist

@@ -36,12 +36,21 @@ def _pass1(args):
     return np.asarray(orc.uniq_reads, np.int64)
 
 
+def _sparse(a):
+    idx = np.flatnonzero(a)
+    return idx, a[idx]
+
+
 def _pass2(uniq):
+    """The slot arrays go back as (index, value) lists: a shard touches a small part of the graph, and pickling the
+    dense arrays of every worker through a pipe used to cost more than the pass itself."""
     orc = _G.pop("orc")
     orc.run_pass2(uniq_reads=[int(v) for v in uniq])
     return dict(uniq_reads=np.asarray(orc.uniq_reads, np.int64), uniq_norm=np.asarray(orc.uniq_norm, np.float64),
                 mult_reads=np.asarray(orc.mult_reads, np.float64), mult_norm=np.asarray(orc.mult_norm, np.float64),
-                uniq_abund=orc.uniq_abund, mult_abund=orc.mult_abund, hist=orc.hist, C=orc.C)
+                mult_hits=np.array([not isinstance(v, int) for v in orc.mult_reads]),
+                uniq_abund=_sparse(orc.uniq_abund), mult_abund=_sparse(orc.mult_abund), hist=orc.hist, C=orc.C,
+                n_slots=len(orc.uniq_abund), n_deferred=len(orc.deferred))
 
 
 class ParallelOracle:
@@ -62,8 +71,16 @@ class ParallelOracle:
         uniq = np.sum([x.get() for x in parts], axis=0)
         parts = [p.apply_async(_pass2, (uniq,)) for p in self.pools]
         res = [x.get() for x in parts]
-        out = {k: np.sum([r[k] for r in res], axis=0) for k in res[0] if k != "C"}
+        out = {k: np.sum([r[k] for r in res], axis=0) for k in ("uniq_reads", "uniq_norm", "mult_reads", "mult_norm", "hist")}
+        out["mult_hits"] = np.any([r["mult_hits"] for r in res], axis=0)
+        for k in ("uniq_abund", "mult_abund"):
+            dense = np.zeros(res[0]["n_slots"], np.float64)
+            for r in res:
+                idx, val = r[k]
+                dense[idx] += val            # the indices of one shard are distinct
+            out[k] = dense
         out["C"] = {k: sum(r["C"][k] for r in res) for k in res[0]["C"]}
+        out["n_deferred"] = sum(r["n_deferred"] for r in res)
         return out
 
     def close(self):

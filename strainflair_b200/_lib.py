@@ -51,6 +51,14 @@ class SfbWork(C.Structure):
         ("aln_match", C.c_void_p), ("match_buf", C.c_void_p), ("match_cap", C.c_int64), ("cursor", C.c_void_p),
         ("grp_code", C.c_void_p), ("grp_code2", C.c_void_p), ("aln_assign", C.c_void_p), ("deferred", C.c_void_p),
         ("slow", C.c_void_p), ("app_buf", C.c_void_p), ("app_cap", C.c_int64),
+        ("grp_begin", C.c_int64), ("aln_begin", C.c_int64),
+    ]
+
+
+class SfbTiles(C.Structure):
+    _fields_ = [
+        ("n_tiles", C.c_int64), ("n_items", C.c_int64), ("max_slots", C.c_int64), ("max_nodes", C.c_int64),
+        ("max_paths", C.c_int64), ("tuple_cap", C.c_int64), ("tile_desc", C.c_void_p), ("items", C.c_void_p),
     ]
 
 
@@ -75,10 +83,11 @@ SLOT_MASK, MATCH_REV, MATCH_MULTI, MATCH_NONE = 0x3FFFFFFF, 0x40000000, 0x800000
 MAX_SLOTS = 0x3FFFFFFF
 (ABSENT, FILTERED, UNASSIGNED, UNASSIGNED_BOOK, DEFER, ASSIGN_SAME, ASSIGN_DIFF, MULTI_ALIGN, INCONSIST,
  SE_COUNTED) = range(10)
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 EXPORTS = ("sfb_abi_version", "sfb_version", "sfb_last_error", "sfb_expand_reads", "sfb_match", "sfb_classify", "sfb_pass1_scatter",
            "sfb_pass2", "sfb_pass2_resolve", "sfb_pass2_scatter", "sfb_accum_collapse", "sfb_path_reduce", "sfb_cluster_strain_counts", "sfb_strain_aggregate",
+           "sfb_tile_pass1", "sfb_tile_pass2", "sfb_tile_smem_bytes", "sfb_tile_permute",
            "sfb_decode_json", "sfb_decoded_error", "sfb_decoded_size", "sfb_decoded_copy", "sfb_decoded_free",
            "sfb_min_strains", "sfb_wire_pack", "sfb_packed_status", "sfb_packed_size", "sfb_packed_copy", "sfb_packed_free",
            "sfb_load_gfa", "sfb_gfa_error", "sfb_gfa_size", "sfb_gfa_copy", "sfb_gfa_free", "sfb_locality_permute")
@@ -128,6 +137,15 @@ def load(build_if_missing=True):
     lib.sfb_strain_aggregate.argtypes = [i64, i64, vp, vp, vp, vp, vp, vp, f64, vp, vp, vp, vp, vp]
     for name in EXPORTS[3:14]:
         getattr(lib, name).restype = C.c_int
+    TL = C.POINTER(SfbTiles)
+    lib.sfb_tile_pass1.argtypes = [G, TL, R, W, A, vp]
+    lib.sfb_tile_pass1.restype = C.c_int
+    lib.sfb_tile_pass2.argtypes = [G, TL, R, W, A, vp, vp]
+    lib.sfb_tile_pass2.restype = C.c_int
+    lib.sfb_tile_smem_bytes.argtypes = [TL]
+    lib.sfb_tile_smem_bytes.restype = C.c_int64
+    lib.sfb_tile_permute.argtypes = [R, vp, i64, C.c_int, vp, vp, R, vp]
+    lib.sfb_tile_permute.restype = C.c_int
     lib.sfb_min_strains.argtypes = [i64, vp, vp, vp, C.c_int, vp, vp, vp, vp]
     lib.sfb_min_strains.restype = C.c_int
     lib.sfb_locality_permute.argtypes = [R, C.c_int, vp, vp, R]

@@ -5,8 +5,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SOURCES = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "match.cu", "group.cu", "scatter.cu", "reduce.cu", "expand.cu", "decode.cpp", "gfa.cpp", "wire.cpp", "unassigned.cpp", "locality.cpp")]
-HEADERS = [os.path.join(HERE, "csrc", "common.cuh"), os.path.join(ROOT, "include", "sfb200.h")]
+SOURCES = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "match.cu", "group.cu", "scatter.cu", "tile.cu", "reduce.cu", "expand.cu", "decode.cpp", "gfa.cpp", "wire.cpp", "unassigned.cpp", "locality.cpp")]
+import glob
+HEADERS = sorted(glob.glob(os.path.join(HERE, "csrc", "*.cuh"))) + sorted(glob.glob(os.path.join(ROOT, "include", "*.h")))
 LIB = os.path.join(HERE, "libsfb200.so")
 
 NVCC_FLAGS = [

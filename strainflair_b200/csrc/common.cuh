@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "sfb200.h"
 
 namespace sfb {
@@ -29,17 +31,25 @@ constexpr int kSMs = 148;   // B200: persistent grids are sized in multiples of 
 static inline unsigned blocks_for(i64 n, int per) { return (unsigned)((n + per - 1) / per); }
 
 // Grid of a persistent kernel: every SM filled with as many CTAs as are resident at once (one wave), never
-// more CTAs than there is work.  The occupancy is queried once per kernel.
+// more CTAs than there is work.  The occupancy is queried once per kernel AND device: the cache is a table of
+// atomics indexed by the device ordinal (a constant of the hardware, so racing writers store the same value).
+struct OccCache {
+    std::atomic<int> per_device[64];
+    OccCache() { for (auto& v : per_device) v.store(0, std::memory_order_relaxed); }
+};
 template <class K>
-static inline unsigned persistent_grid(K kernel, int block, i64 work_blocks, int* cache) {
-    if (*cache == 0) {
-        int per_sm = 0, dev = 0, sms = kSMs;
-        cudaGetDevice(&dev);
+static inline unsigned persistent_grid(K kernel, int block, i64 work_blocks, OccCache& cache) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int slots = dev >= 0 && dev < 64 ? cache.per_device[dev].load(std::memory_order_relaxed) : 0;
+    if (slots == 0) {
+        int per_sm = 0, sms = kSMs;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
-        *cache = per_sm * sms;
+        slots = per_sm * sms;
+        if (dev >= 0 && dev < 64) cache.per_device[dev].store(slots, std::memory_order_relaxed);
     }
-    const i64 g = work_blocks < (i64)*cache ? work_blocks : (i64)*cache;
+    const i64 g = work_blocks < (i64)slots ? work_blocks : (i64)slots;
     return (unsigned)(g < 1 ? 1 : g);
 }
 
@@ -120,19 +130,38 @@ __device__ __forceinline__ double record_cov(const sfb_reads& r, i64 rec) {
     return (double)(v & 0xffff) / (double)(v >> 16);        // aligned bases / node length, IEEE division
 }
 
-// fp64 accumulation: plain RED, or (det_stride > 0) three exact partial sums, see sfb_accum in sfb200.h.  v >= 0.
+// ---- order-independent accumulation: 96-bit fixed point ------------------------------------------------------
+// A term v >= 0 (v < 2^32) is the integer floor(v * 2^64), split into three 32-bit limbs x2:x1:x0 (x2 = integer
+// part, x1 = multiples of 2^-32, x0 = multiples of 2^-64).  Integer sums are exact, so the result does not depend
+// on the order of the additions, on the sharding of the reads or on the number of GPUs.  In global memory an
+// accumulator is two 64-bit integer planes: plane 0 (at x) holds x2:x1 in units of 2^-32, plane 1 (at x +
+// det_stride) holds the x0 limbs in units of 2^-64; sfb_accum_collapse turns the pair into the fp64 value.
+struct Fx {
+    uint32_t x0, x1, x2;
+};
+__device__ __forceinline__ Fx fx_split(double v) {
+    const double t = v * 4294967296.0;                 // exact (power of two)
+    const double hi = floor(t);
+    const u64 H = __double2ull_rz(hi);
+    Fx f;
+    f.x0 = __double2uint_rz((t - hi) * 4294967296.0);  // t - hi is exact and in [0, 1)
+    f.x1 = (uint32_t)H;
+    f.x2 = (uint32_t)(H >> 32);
+    return f;
+}
+__device__ __forceinline__ void fx_red(double* p, i64 det_stride, Fx f) {
+    const u64 H = ((u64)f.x2 << 32) | f.x1;
+    if (H) atomicAdd(reinterpret_cast<u64*>(p), H);
+    if (f.x0) atomicAdd(reinterpret_cast<u64*>(p + det_stride), (u64)f.x0);
+}
+// fp64 accumulation: plain RED (det_stride == 0: the order of the additions, hence the last bits, vary from run to
+// run), or the two exact integer planes above.  v >= 0.
 __device__ __forceinline__ void acc_add(double* p, i64 det_stride, double v) {
     if (det_stride == 0) {
         atomicAdd(p, v);
         return;
     }
-    const double c0 = floor(v * 0x1p16) * 0x1p-16;      // every step below is exact in fp64
-    const double r0 = v - c0;
-    const double c1 = floor(r0 * 0x1p40) * 0x1p-40;
-    const double c2 = rint((r0 - c1) * 0x1p64) * 0x1p-64;
-    if (c0 != 0.0) atomicAdd(p, c0);
-    if (c1 != 0.0) atomicAdd(p + det_stride, c1);
-    if (c2 != 0.0) atomicAdd(p + 2 * det_stride, c2);
+    fx_red(p, det_stride, fx_split(v));
 }
 
 // slot -> path id from the 64-slot block table: one 8-byte load; path_off is only walked for blocks in which several

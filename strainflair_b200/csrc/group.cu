@@ -7,6 +7,7 @@
 // more than kCap tuples per mate take the same code through GlobalView.
 #include "common.cuh"
 #include "group_fast.cuh"
+#include "group_logic.cuh"
 
 namespace sfb {
 
@@ -29,6 +30,15 @@ __device__ __forceinline__ void assign_unique(const Dev& d, BlockCounters& sc, i
     atomicAdd((u64*)&d.acc.uniq_reads[pid], 1ull);
     acc_add(&d.acc.uniq_norm[pid], d.acc.det_stride, (double)seq_len / (double)d.g.path_seq_len[pid]);
     hist_add(d, sc, pid, a);
+    if (a < d.w.aln_begin) {
+        // a read group of the tile range that sfb_tile_pass1 handed over (more match tuples than its buffers hold):
+        // k_pass1_scatter does not visit it, the node loop (json2csv.py:329-330) runs here
+        const i64 w0 = d.r.aln_walk_off[a];
+        const int L = (int)(d.r.aln_walk_off[a + 1] - w0);
+        double* dst = d.acc.uniq_abund + (code & SFB_SLOT_MASK);
+        for (int i = 0; i < L; ++i) acc_add(dst + i, d.acc.det_stride, record_cov(d.r, w0 + i));
+        SFB_COUNT(sc, SFB_C_ST_P1_RECORDS, L);
+    }
 }
 
 // cluster of the first path through the walk's first node (json2csv.py:875,901,1036); -1 = None, -2 = no path
@@ -43,107 +53,40 @@ __device__ __forceinline__ void book(const Dev& d, BlockCounters& sc, const Mate
     d.w.aln_assign[mt.a0] = -(cluster + 2);
 }
 
-// Strain reduction (json2csv.py:964-986): size of each mate's reduced list (a tuple counts once per
-// common strain its path carries) and whether any common strain exists.
-struct StrainCut {
-    bool any;
-    int n_new[2];
-    u64 common0;   // the common-strain word when mask_words == 1
-};
-template <class V>
-__device__ __forceinline__ StrainCut strain_cut(const sfb_graph& g, const V& v) {
-    StrainCut c;
-    c.any = false;
-    c.n_new[0] = c.n_new[1] = 0;
-    c.common0 = 0;
-    for (int word = 0; word < (int)g.mask_words; ++word) {
-        const u64 common = common_strains(g, v, word);
-        if (word == 0) c.common0 = common;
-        if (!common) continue;
-        c.any = true;
-        for (int k = 0; k < 2; ++k)
-            for (int i = 0; i < v.nt(k); ++i)
-                c.n_new[k] += __popcll(g.path_smask[(size_t)v.pid(k, i) * g.mask_words + word] & common);
+// json2csv.py:1155-1156 (and :1207-1208, :1265-1266) + the work item for the node loop (:1157-1158)
+__device__ __forceinline__ void emit_app(const Dev& d, App* out, i64 a, uint32_t code, int pid, int seq_len,
+                                      double ratio, int times) {
+    acc_add(&d.acc.mult_reads[pid], d.acc.det_stride, ratio * (double)times);
+    acc_add(&d.acc.mult_norm[pid], d.acc.det_stride,
+            (ratio * (double)seq_len / (double)d.g.path_seq_len[pid]) * (double)times);
+    d.acc.mult_hits[pid] = 1u;           // "touched" flag: same value from every writer, no atomic needed
+    App app;
+    app.aln = (int32_t)a;
+    app.code = code;
+    app.weight = ratio * (double)times;
+    *out = app;
+}
+
+// Effects of the decision logic (group_logic.cuh) for the global-memory kernels: atomics on the accumulators in HBM,
+// pass-2 work items into app_buf (the node loops run in k_pass1_scatter / k_pass2_scatter).
+struct GlobalOps {
+    const long long* U;
+    App* out;
+    __device__ __forceinline__ void assign_unique(const Dev& d, BlockCounters& sc, i64 a, uint32_t code, int pid, int seq_len) {
+        sfb::assign_unique(d, sc, a, code, pid, seq_len);
     }
-    return c;
-}
-template <class V>
-__device__ __forceinline__ int times_of(const sfb_graph& g, const V& v, const StrainCut& c, int p) {
-    if (g.mask_words == 1) return __popcll(g.path_smask[p] & c.common0);
-    return strain_times(g, v, p);
-}
+    __device__ __forceinline__ void hist(const Dev& d, BlockCounters& sc, int pid, i64 a) { hist_add(d, sc, pid, a); }
+    __device__ __forceinline__ int first_cluster(const Dev& d, i64 a) { return sfb::first_cluster(d, a); }
+    __device__ __forceinline__ void book(const Dev& d, BlockCounters& sc, const Mate& mt, int cluster) { sfb::book(d, sc, mt, cluster); }
+    __device__ __forceinline__ long long uniq(int pid) const { return U[pid]; }
+    __device__ __forceinline__ void apply(const Dev& d, i64 a, uint32_t code, int pid, int seq_len, double ratio, int times) {
+        emit_app(d, out++, a, code, pid, seq_len, ratio, times);
+    }
+};
 
 // =============================================================================================
 // classify
 // =============================================================================================
-// both mates have colored paths (json2csv.py:918-1000)
-template <class V>
-__device__ __forceinline__ void classify_pair(const Dev& d, BlockCounters& sc, const V& v, const Mate* mt, int* code,
-                                              bool& defer) {
-    int n_inter = 0, p_inter = -1;
-    for (int i = 0; i < v.nt(0); ++i)
-        if (first_of_pid(v, 0, i) && count_pid(v, 1, v.pid(0, i)) > 0) {
-            if (n_inter++ == 0) p_inter = v.pid(0, i);
-        }
-    if (n_inter > 1) {
-        SFB_COUNT(sc, SFB_C_SECOND_PASS, 2);
-        defer = true;
-        code[0] = code[1] = SFB_DEFER;
-        return;
-    }
-    if (n_inter == 1) {
-        for (int k = 0; k < 2; ++k) {
-            if (count_pid(v, k, p_inter) > 1) {
-                SFB_COUNT(sc, SFB_C_MULTI_ALIGN, 1);
-                code[k] = SFB_MULTI_ALIGN;
-                continue;
-            }
-            for (int i = 0; i < v.nt(k); ++i)
-                if (v.pid(k, i) == p_inter) {
-                    assign_unique(d, sc, mt[k].a0 + v.aloc(k, i), v.code(k, i), p_inter, mt[k].seq_len);
-                    break;
-                }
-            SFB_COUNT(sc, SFB_C_ASSIGNED_U, 1);
-            SFB_COUNT(sc, SFB_C_SAME_CP, 1);
-            if (v.nt(k) > 1) SFB_COUNT(sc, SFB_C_AMBIG_CP_RESOLVED, 1);
-            code[k] = SFB_ASSIGN_SAME;
-        }
-        return;
-    }
-    // no common path: intersect strains (json2csv.py:961-1000)
-    const StrainCut cut = strain_cut(d.g, v);
-    if (!cut.any) {
-        SFB_COUNT(sc, SFB_C_INCONSIST, 2);
-        code[0] = code[1] = SFB_INCONSIST;
-        return;
-    }
-    for (int k = 0; k < 2; ++k) {
-        const int nn = cut.n_new[k];
-        if (nn < v.nt(k)) SFB_COUNT(sc, nn == 1 ? SFB_C_AMBIG_RESOLVED : SFB_C_AMBIG_REDUCED, 1);
-        if (nn > 1) {
-            SFB_COUNT(sc, SFB_C_SECOND_PASS, 1);
-            defer = true;
-            code[k] = SFB_DEFER;
-            continue;
-        }
-        for (int i = 0; i < v.nt(k); ++i) {      // exactly one tuple survives, once
-            const int p = v.pid(k, i);
-            if (times_of(d.g, v, cut, p) == 0) continue;
-            if (count_pid(v, k, p) == 1) {
-                assign_unique(d, sc, mt[k].a0 + v.aloc(k, i), v.code(k, i), p, mt[k].seq_len);
-                SFB_COUNT(sc, SFB_C_ASSIGNED_U, 1);
-                SFB_COUNT(sc, SFB_C_DIFF_CP, 1);
-                code[k] = SFB_ASSIGN_DIFF;
-            } else {
-                SFB_COUNT(sc, SFB_C_MULTI_ALIGN, 1);
-                code[k] = SFB_MULTI_ALIGN;
-            }
-            break;
-        }
-    }
-}
-
-
 // ---- register fast path of classify_pair (see group_fast.cuh) ---------------------------------
 __device__ __forceinline__ void strain_mate_fast(const Dev& d, BlockCounters& sc, const Mate& mt, const RegMate& R,
                                                  const u64* sw, u64 common, unsigned dup, int& code, bool& defer) {
@@ -241,36 +184,6 @@ __device__ __forceinline__ int classify_single(const Dev& d, BlockCounters& sc, 
     return SFB_SE_COUNTED;
 }
 
-// both mates aligned, neither has a colored path (json2csv.py:868-891)
-__device__ __forceinline__ void classify_both_unassigned(const Dev& d, BlockCounters& sc, const Mate* mt, int* code) {
-    SFB_COUNT(sc, SFB_C_UNASSIGNED, 2);
-    int n_common = 0, common = 0;
-    bool bad = false;
-    for (int i = 0; i < mt[0].na; ++i) {
-        const int ci = first_cluster(d, mt[0].a0 + i);
-        bad |= ci == -2;
-        bool seen = false;
-        for (int j = 0; j < i; ++j) seen |= first_cluster(d, mt[0].a0 + j) == ci;
-        if (seen) continue;
-        bool other = false;
-        for (int j = 0; j < mt[1].na; ++j) other |= first_cluster(d, mt[1].a0 + j) == ci;
-        if (other) { ++n_common; common = ci; }
-    }
-    for (int j = 0; j < mt[1].na; ++j) bad |= first_cluster(d, mt[1].a0 + j) == -2;
-    code[0] = code[1] = SFB_UNASSIGNED;
-    if (bad) { SFB_COUNT(sc, SFB_C_NO_PATH, 1); return; }
-    if (n_common > 1) return;
-    for (int k = 0; k < 2; ++k) {
-        int len = mt[k].na, cl = first_cluster(d, mt[k].a0);
-        if (n_common == 1) {
-            len = 0;
-            for (int j = 0; j < mt[k].na; ++j) len += first_cluster(d, mt[k].a0 + j) == common;
-            cl = common;
-        }
-        if (len == 1) { book(d, sc, mt[k], cl); code[k] = SFB_UNASSIGNED_BOOK; }
-    }
-}
-
 // Generic handling of a pair whose mates both have alignments (json2csv.py:847-1000); `single` is set
 // when one mate has no colored path and the other continues single-end style.
 __device__ __forceinline__ void classify_aligned_pair_generic(const Dev& d, BlockCounters& sc, const Mate* mt, int* code,
@@ -281,7 +194,8 @@ __device__ __forceinline__ void classify_aligned_pair_generic(const Dev& d, Bloc
     if (!fits) gv.init(d.w, mt);
     const int nt0 = fits ? lv.nt(0) : gv.nt(0), nt1 = fits ? lv.nt(1) : gv.nt(1);
     if (nt0 == 0 && nt1 == 0) {
-        classify_both_unassigned(d, sc, mt, code);
+        GlobalOps ops{nullptr, nullptr};
+        classify_both_unassigned(d, ops, sc, mt, code);
     } else if (nt0 == 0 || nt1 == 0) {
         // one mate without colored path (json2csv.py:895-916)
         SFB_COUNT(sc, SFB_C_UNASSIGNED, 1);
@@ -298,9 +212,11 @@ __device__ __forceinline__ void classify_aligned_pair_generic(const Dev& d, Bloc
         }
         single = 1 - gone;
     } else if (fits) {
-        classify_pair(d, sc, lv, mt, code, defer);
+        GlobalOps ops{nullptr, nullptr};
+        classify_pair(d, ops, sc, lv, mt, code, defer);
     } else {
-        classify_pair(d, sc, gv, mt, code, defer);
+        GlobalOps ops{nullptr, nullptr};
+        classify_pair(d, ops, sc, gv, mt, code, defer);
     }
 }
 
@@ -315,8 +231,8 @@ __global__ void __launch_bounds__(128, SFB_CLS_MINBLK) k_classify(Dev d) {
     __shared__ BlockCounters sc;
     block_counters_zero(sc);
     __syncthreads();
-    const i64 n_round = (d.r.n_groups + 127) & ~(i64)127;
-    for (i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x; g < n_round; g += (i64)gridDim.x * blockDim.x) {
+    const i64 n_round = d.w.grp_begin + ((d.r.n_groups - d.w.grp_begin + 127) & ~(i64)127);
+    for (i64 g = d.w.grp_begin + (i64)blockIdx.x * blockDim.x + threadIdx.x; g < n_round; g += (i64)gridDim.x * blockDim.x) {
         bool defer = false, slow = false;
         if (g < d.r.n_groups) {
             const int nm = d.r.grp_nmates[g];
@@ -394,139 +310,6 @@ __global__ void __launch_bounds__(128) k_classify_slow(Dev d) {
 // =============================================================================================
 // pass 2, resolve: which (alignment, path position) pairs receive which share
 // =============================================================================================
-enum { kNone = 0, kInter = 1, kStrain = 2, kSingle = 3 };
-
-struct Plan {
-    int mode[2];
-    int napp[2];
-    int n_inter;
-    long long total_inter;
-    long long total_strain[2];
-    int nn[2];
-    StrainCut cut;
-};
-
-__device__ __forceinline__ double ratio_of(long long u, long long total, int n) {
-    return total == 0 ? 1.0 / (double)n : (double)u / (double)total;        // json2csv.py:1151-1154
-}
-
-// json2csv.py:1123-1217: decide per mate; counters and grp_code2 here, the additions in p2_emit
-template <class V>
-__device__ __forceinline__ void p2_decide_pair(const Dev& d, BlockCounters& sc, const V& v, const long long* U,
-                                               Plan& pl, int* code) {
-    pl.n_inter = 0;
-    pl.total_inter = 0;
-    for (int i = 0; i < v.nt(0); ++i)
-        if (first_of_pid(v, 0, i) && count_pid(v, 1, v.pid(0, i)) > 0) {
-            ++pl.n_inter;
-            pl.total_inter += U[v.pid(0, i)];
-        }
-    if (pl.n_inter >= 1) {
-        for (int k = 0; k < 2; ++k) {
-            bool simple = true;      // every common path has exactly one tuple in this mate
-            for (int i = 0; i < v.nt(k) && simple; ++i) {
-                const int p = v.pid(k, i);
-                if (count_pid(v, 1 - k, p) > 0 && count_pid(v, k, p) != 1) simple = false;
-            }
-            if (!simple) {
-                SFB_COUNT(sc, SFB_C_MULTI_ALIGN, 1);
-                code[k] = SFB_P2_MULTI_ALIGN;
-                continue;
-            }
-            SFB_COUNT(sc, SFB_C_ASSIGNED_M, 1);
-            code[k] = SFB_P2_ASSIGNED;
-            pl.mode[k] = kInter;
-            pl.napp[k] = pl.n_inter;
-        }
-        return;
-    }
-    pl.cut = strain_cut(d.g, v);
-    if (!pl.cut.any) {
-        SFB_COUNT(sc, SFB_C_INCONSIST_M, (v.nt(0) == 1 || v.nt(1) == 1) ? 1 : 2);
-        code[0] = code[1] = SFB_P2_INCONSIST;
-        return;
-    }
-    for (int k = 0; k < 2; ++k) {
-        pl.nn[k] = pl.cut.n_new[k];
-        if (pl.nn[k] <= 1) continue;          // handled in pass 1 (json2csv.py:1185)
-        bool simple = true;
-        long long tot = 0;
-        int napp = 0;
-        for (int i = 0; i < v.nt(k); ++i) {
-            const int p = v.pid(k, i);
-            const int times = times_of(d.g, v, pl.cut, p);
-            if (times == 0) continue;
-            if (count_pid(v, k, p) != 1) { simple = false; break; }
-            tot += U[p] * times;
-            ++napp;
-        }
-        if (!simple) {
-            SFB_COUNT(sc, SFB_C_MULTI_ALIGN, 1);
-            code[k] = SFB_P2_MULTI_ALIGN;
-            continue;
-        }
-        SFB_COUNT(sc, SFB_C_ASSIGNED_M, 1);
-        code[k] = SFB_P2_ASSIGNED;
-        pl.mode[k] = kStrain;
-        pl.napp[k] = napp;
-        pl.total_strain[k] = tot;
-    }
-}
-
-// json2csv.py:1155-1156 (and :1207-1208, :1265-1266) + the work item for the node loop (:1157-1158)
-__device__ __forceinline__ void emit_app(const Dev& d, App* out, i64 a, uint32_t code, int pid, int seq_len,
-                                      double ratio, int times) {
-    acc_add(&d.acc.mult_reads[pid], d.acc.det_stride, ratio * (double)times);
-    acc_add(&d.acc.mult_norm[pid], d.acc.det_stride,
-            (ratio * (double)seq_len / (double)d.g.path_seq_len[pid]) * (double)times);
-    d.acc.mult_hits[pid] = 1u;           // "touched" flag: same value from every writer, no atomic needed
-    App app;
-    app.aln = (int32_t)a;
-    app.code = code;
-    app.weight = ratio * (double)times;
-    *out = app;
-}
-
-template <class V>
-__device__ __forceinline__ void p2_emit(const Dev& d, BlockCounters& sc, const V& v, const Mate* mt,
-                                        const long long* U, const Plan& pl, App* out) {
-    for (int k = 0; k < 2; ++k) {
-        if (pl.mode[k] == kInter) {
-            for (int i = 0; i < v.nt(k); ++i) {
-                const int p = v.pid(k, i);
-                if (count_pid(v, 1 - k, p) > 0)
-                    emit_app(d, out++, mt[k].a0 + v.aloc(k, i), v.code(k, i), p, mt[k].seq_len,
-                             ratio_of(U[p], pl.total_inter, pl.n_inter), 1);
-            }
-        } else if (pl.mode[k] == kStrain) {
-            for (int i = 0; i < v.nt(k); ++i) {
-                const int p = v.pid(k, i);
-                const int times = times_of(d.g, v, pl.cut, p);
-                if (times)
-                    emit_app(d, out++, mt[k].a0 + v.aloc(k, i), v.code(k, i), p, mt[k].seq_len,
-                             ratio_of(U[p], pl.total_strain[k], pl.nn[k]), times);
-            }
-        } else if (pl.mode[k] == kSingle) {
-            // every alignment separately (json2csv.py:1230-1268)
-            int i = 0;
-            while (i < v.nt(k)) {
-                const int j = v.aloc(k, i);
-                int e = i;
-                long long total = 0;
-                for (; e < v.nt(k) && v.aloc(k, e) == j; ++e) {
-                    total += U[v.pid(k, e)];
-                    hist_add(d, sc, v.pid(k, e), mt[k].a0 + j);
-                }
-                for (int t = i; t < e; ++t)
-                    emit_app(d, out++, mt[k].a0 + j, v.code(k, t), v.pid(k, t), mt[k].seq_len,
-                             ratio_of(U[v.pid(k, t)], total, e - i), 1);
-                i = e;
-            }
-        }
-    }
-}
-
-
 // ---- register fast path of pass 2 (see group_fast.cuh) -----------------------------------------
 struct FastPlan {
     int mode[2];
@@ -639,17 +422,6 @@ __device__ __forceinline__ App* p2_fast_emit(const Dev& d, BlockCounters& sc, co
     return out;
 }
 
-// single-end bookkeeping shared by both resolve kernels (json2csv.py:1270-1274)
-__device__ __forceinline__ int p2_single_outcome(BlockCounters& sc, int n_tuples) {
-    if (n_tuples > 0) {
-        SFB_COUNT(sc, SFB_C_ASSIGNED_M, 1);
-        SFB_COUNT(sc, SFB_C_SE_M, 1);
-        return SFB_P2_SE_ASSIGNED;
-    }
-    SFB_COUNT(sc, SFB_C_UNASSIGNED, 1);
-    return SFB_P2_UNASSIGNED;
-}
-
 // Fast kernel over the deferred groups; groups that do not fit the register path go to w.slow (cursor[4]).
 __global__ void __launch_bounds__(128, SFB_P2_MINBLK) k_pass2_resolve(Dev d, const long long* __restrict__ U) {
     __shared__ BlockCounters sc;
@@ -716,21 +488,23 @@ __global__ void __launch_bounds__(128, SFB_P2_MINBLK) k_pass2_resolve(Dev d, con
 
 int launch_classify(const Dev& d, cudaStream_t st) {
     if (d.r.n_groups == 0) return SFB_OK;
-    static int c_fast = 0, c_slow = 0;
-    const unsigned grid = persistent_grid(k_classify, 128, blocks_for(d.r.n_groups, 128), &c_fast);
-    k_classify<<<grid, 128, 0, st>>>(d);
-    SFB_TRY(check_launch("k_classify"));
-    const unsigned grid2 = persistent_grid(k_classify_slow, 128, blocks_for(d.r.n_groups, 128), &c_slow);
+    static OccCache c_fast, c_slow;
+    if (d.r.n_groups > d.w.grp_begin) {
+        const unsigned grid = persistent_grid(k_classify, 128, blocks_for(d.r.n_groups - d.w.grp_begin, 128), c_fast);
+        k_classify<<<grid, 128, 0, st>>>(d);
+        SFB_TRY(check_launch("k_classify"));
+    }
+    const unsigned grid2 = persistent_grid(k_classify_slow, 128, blocks_for(d.r.n_groups, 128), c_slow);
     k_classify_slow<<<grid2, 128, 0, st>>>(d);             // usually a few percent of the groups
     return check_launch("k_classify_slow");
 }
 int launch_pass2_resolve(const Dev& d, const long long* U, cudaStream_t st) {
     if (d.r.n_groups == 0) return SFB_OK;
-    static int c_fast = 0, c_slow = 0;
-    const unsigned grid = persistent_grid(k_pass2_resolve, 128, blocks_for(d.r.n_groups, 128), &c_fast);
+    static OccCache c_fast, c_slow;
+    const unsigned grid = persistent_grid(k_pass2_resolve, 128, blocks_for(d.r.n_groups, 128), c_fast);
     k_pass2_resolve<<<grid, 128, 0, st>>>(d, U);
     SFB_TRY(check_launch("k_pass2_resolve"));
-    const unsigned grid2 = persistent_grid(k_pass2_resolve_slow, 128, blocks_for(d.r.n_groups, 128), &c_slow);
+    const unsigned grid2 = persistent_grid(k_pass2_resolve_slow, 128, blocks_for(d.r.n_groups, 128), c_slow);
     k_pass2_resolve_slow<<<grid2, 128, 0, st>>>(d, U);
     return check_launch("k_pass2_resolve_slow");
 }

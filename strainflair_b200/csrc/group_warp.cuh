@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(128) k_pass2_resolve_slow(Dev d, const long lo
             if (lane == 0) {
                 GlobalView gv;
                 gv.init(d.w, mt);
+                GlobalOps ops{U, nullptr};
                 Plan pl;
                 pl.mode[0] = pl.mode[1] = kNone;
                 pl.napp[0] = pl.napp[1] = 0;
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(128) k_pass2_resolve_slow(Dev d, const long lo
                 if (nm == 2) {
                     if (mt[0].na == 0 || mt[1].na == 0) single = mt[0].na == 0 ? 1 : 0;
                     else if (gv.nt(0) == 0 || gv.nt(1) == 0) single = gv.nt(0) == 0 ? 1 : 0;
-                    else p2_decide_pair(d, sc, gv, U, pl, code);
+                    else p2_decide_pair(d, ops, sc, gv, pl, code);
                 }
                 if (single >= 0) {
                     pl.mode[single] = kSingle;
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(128) k_pass2_resolve_slow(Dev d, const long lo
                 if (need) {
                     const u64 pos = atomicAdd(d.w.cursor + 2, (u64)need);
                     SFB_COUNT(sc, SFB_C_ST_P2_APPLIED, (int)need);
-                    if (pos + need <= (u64)d.w.app_cap) p2_emit(d, sc, gv, mt, U, pl, apps + pos);
+                    if (pos + need <= (u64)d.w.app_cap) { ops.out = apps + pos; p2_emit(d, ops, sc, gv, mt, pl); }
                     else SFB_COUNT(sc, SFB_C_MATCH_OVERFLOW, (int)need);
                 }
                 d.w.grp_code2[g] = (uint8_t)(code[0] | (code[1] << 4));

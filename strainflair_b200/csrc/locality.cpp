@@ -30,14 +30,11 @@ void for_chunks(int T, size_t n_items, F&& body) {      // chunk c of exactly T 
     for (auto& th : pool) th.join();
 }
 
-}  // namespace
 
-extern "C" int sfb_locality_permute(const sfb_reads* r, int n_threads, int64_t* order, int64_t* aln_index,
-                                    const sfb_reads* dst) {
-    if (!r || !dst || !order || (r->n_alns && !aln_index)) return SFB_E_ARG;
-    const int64_t G = r->n_groups, A = r->n_alns, R = r->n_records;
-    if (G < 0 || A < 0 || R < 0) return SFB_E_ARG;
-    const int T = std::max(1, std::min(n_threads, 64));
+// Stable order of the groups by key (keys in [0, none]) and the permuted CSR; shared by the two entry points.
+int permute_by_key(const sfb_reads* r, int T, const std::vector<uint32_t>& key, uint32_t none, int64_t* order,
+                   int64_t* aln_index, const sfb_reads* dst) {
+    const int64_t G = r->n_groups, A = r->n_alns;
     uint8_t* d_nmates = const_cast<uint8_t*>(dst->grp_nmates);
     int64_t* d_grp_off = const_cast<int64_t*>(dst->grp_aln_off);
     int32_t* d_seq_len = const_cast<int32_t*>(dst->mate_seq_len);
@@ -45,31 +42,7 @@ extern "C" int sfb_locality_permute(const sfb_reads* r, int n_threads, int64_t* 
     uint8_t* d_bins = const_cast<uint8_t*>(dst->aln_bins);
     int32_t* d_node = const_cast<int32_t*>(dst->walk_node);
     int32_t* d_alen = const_cast<int32_t*>(dst->walk_alen);
-    try {
-        // ---- keys: first node of the first retained alignment; none -> after every node ----
-        std::vector<uint32_t> key((size_t)G);
-        std::vector<uint32_t> max_part((size_t)T, 0);
-        for_chunks(T, (size_t)G, [&](int c, size_t lo, size_t hi) {
-            uint32_t mx = 0;
-            for (size_t g = lo; g < hi; ++g) {
-                const int64_t a0 = r->grp_aln_off[2 * g], a1 = r->grp_aln_off[2 * g + 2];
-                uint32_t k = 0xffffffffu;
-                if (a1 > a0 && R > 0) {
-                    const int64_t w = std::min<int64_t>(r->aln_walk_off[a0], R - 1);
-                    k = (uint32_t)r->walk_node[w];
-                    mx = std::max(mx, k);
-                }
-                key[g] = k;
-            }
-            max_part[c] = mx;
-        });
-        uint32_t top = 0;
-        for (uint32_t v : max_part) top = std::max(top, v);
-        const uint32_t none = top + 1;                     // groups without an alignment sort last
-        for_chunks(T, (size_t)G, [&](int, size_t lo, size_t hi) {
-            for (size_t g = lo; g < hi; ++g)
-                if (key[g] == 0xffffffffu) key[g] = none;
-        });
+    {
         // ---- stable LSD radix sort of the group indices by key, 16 bits per pass ----
         std::vector<int64_t> idx_a((size_t)G), idx_b((size_t)G);
         for_chunks(T, (size_t)G, [&](int, size_t lo, size_t hi) {
@@ -133,8 +106,88 @@ extern "C" int sfb_locality_permute(const sfb_reads* r, int n_threads, int64_t* 
                 }
             }
         });
+    }
+    return SFB_OK;
+}
+
+}  // namespace
+
+extern "C" int sfb_locality_permute(const sfb_reads* r, int n_threads, int64_t* order, int64_t* aln_index,
+                                    const sfb_reads* dst) {
+    if (!r || !dst || !order || (r->n_alns && !aln_index)) return SFB_E_ARG;
+    const int64_t G = r->n_groups, A = r->n_alns, R = r->n_records;
+    if (G < 0 || A < 0 || R < 0) return SFB_E_ARG;
+    const int T = std::max(1, std::min(n_threads, 64));
+    try {
+        // ---- keys: first node of the first retained alignment; none -> after every node ----
+        std::vector<uint32_t> key((size_t)G);
+        std::vector<uint32_t> max_part((size_t)T, 0);
+        for_chunks(T, (size_t)G, [&](int c, size_t lo, size_t hi) {
+            uint32_t mx = 0;
+            for (size_t g = lo; g < hi; ++g) {
+                const int64_t a0 = r->grp_aln_off[2 * g], a1 = r->grp_aln_off[2 * g + 2];
+                uint32_t k = 0xffffffffu;
+                if (a1 > a0 && R > 0) {
+                    const int64_t w = std::min<int64_t>(r->aln_walk_off[a0], R - 1);
+                    k = (uint32_t)r->walk_node[w];
+                    mx = std::max(mx, k);
+                }
+                key[g] = k;
+            }
+            max_part[c] = mx;
+        });
+        uint32_t top = 0;
+        for (uint32_t v : max_part) top = std::max(top, v);
+        const uint32_t none = top + 1;                     // groups without an alignment sort last
+        for_chunks(T, (size_t)G, [&](int, size_t lo, size_t hi) {
+            for (size_t g = lo; g < hi; ++g)
+                if (key[g] == 0xffffffffu) key[g] = none;
+        });
+        return permute_by_key(r, T, key, none, order, aln_index, dst);
     } catch (const std::exception&) {
         return SFB_E_ARG;                                    // out of memory
     }
-    return SFB_OK;
+}
+
+// Tile order (sfb_tiles in sfb200.h): key = the tile that holds the first and the last node of every alignment of the
+// group; groups without such a tile (mates in different tiles, a node outside every tile, no alignment) go last.
+extern "C" int sfb_tile_permute(const sfb_reads* r, const int32_t* node_tile, int64_t n_tiles, int n_threads,
+                                int64_t* order, int64_t* aln_index, const sfb_reads* dst, int64_t* tile_grp_off) {
+    if (!r || !dst || !order || !tile_grp_off || (r->n_alns && (!aln_index || !node_tile))) return SFB_E_ARG;
+    const int64_t G = r->n_groups, A = r->n_alns, R = r->n_records;
+    if (G < 0 || A < 0 || R < 0 || n_tiles < 0 || n_tiles >= 0x7fffffffLL) return SFB_E_ARG;
+    const int T = std::max(1, std::min(n_threads, 64));
+    try {
+        const uint32_t none = (uint32_t)n_tiles;
+        std::vector<uint32_t> key((size_t)G);
+        std::vector<std::vector<int64_t>> count((size_t)T);
+        for_chunks(T, (size_t)G, [&](int c, size_t lo, size_t hi) {
+            auto& cnt = count[c];
+            cnt.assign((size_t)n_tiles + 1, 0);
+            for (size_t g = lo; g < hi; ++g) {
+                const int64_t a0 = r->grp_aln_off[2 * g], a1 = r->grp_aln_off[2 * g + 2];
+                int64_t tile = -1;
+                bool ok = a1 > a0;
+                for (int64_t a = a0; a < a1 && ok; ++a) {
+                    const int64_t w0 = r->aln_walk_off[a], w1 = r->aln_walk_off[a + 1];
+                    if (w1 <= w0) continue;                               // an empty walk matches nothing anywhere
+                    const int32_t t0 = node_tile[r->walk_node[w0]], t1 = node_tile[r->walk_node[w1 - 1]];
+                    if (t0 < 0 || t0 != t1 || (tile >= 0 && t0 != tile)) ok = false;
+                    tile = t0;
+                }
+                const uint32_t k = ok && tile >= 0 ? (uint32_t)tile : none;
+                key[g] = k;
+                cnt[k] += 1;
+            }
+        });
+        tile_grp_off[0] = 0;
+        for (int64_t t = 0; t <= n_tiles; ++t) {
+            int64_t n = 0;
+            for (int c = 0; c < T; ++c) n += count[c][(size_t)t];
+            tile_grp_off[t + 1] = tile_grp_off[t] + n;
+        }
+        return permute_by_key(r, T, key, none, order, aln_index, dst);
+    } catch (const std::exception&) {
+        return SFB_E_ARG;                                    // out of memory
+    }
 }

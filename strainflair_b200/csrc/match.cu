@@ -64,10 +64,11 @@ __global__ void __launch_bounds__(256, SFB_MATCH_MINBLK) k_match(sfb_graph g, sf
     const int wi = threadIdx.x >> 5, lane = lane_id();
     const unsigned below = (1u << lane) - 1u;
     const int last_slot = (int)g.n_slots - 1;
-    const i64 n_round = (r.n_alns + 31) & ~(i64)31;
+    const i64 a_lo = w.aln_begin;                       // the alignments before it belong to the tile kernels
+    const i64 n_round = (r.n_alns - a_lo + 31) & ~(i64)31;
     for (i64 base = ((i64)blockIdx.x * kWarpsPerBlock + wi) * 32; base < n_round;
          base += (i64)gridDim.x * kWarpsPerBlock * 32) {
-        const i64 a = base + lane;
+        const i64 a = a_lo + base + lane;
         const bool live = a < r.n_alns;
         i64 w0 = 0;
         int L = 0, second = 0, penult = 0, fo = 0, fcnt = 0, ro = 0, rcnt = 0;
@@ -211,8 +212,8 @@ __global__ void __launch_bounds__(256, SFB_MATCH_MINBLK) k_match(sfb_graph g, sf
             big &= big - 1;
             // the alignment's data again from (cached) global memory: keeping it in registers until here would spill
             const u64 o_pos = __shfl_sync(0xffffffffu, pos, j);
-            const i64 o_w0 = r.aln_walk_off[base + j];
-            const int o_L = (int)(r.aln_walk_off[base + j + 1] - o_w0);
+            const i64 o_w0 = r.aln_walk_off[a_lo + base + j];
+            const int o_L = (int)(r.aln_walk_off[a_lo + base + j + 1] - o_w0);
             const int o_first = r.walk_node[o_w0], o_last = r.walk_node[o_w0 + o_L - 1];
             const int o_second = o_L > 1 ? r.walk_node[o_w0 + 1] : 0, o_penult = o_L > 1 ? r.walk_node[o_w0 + o_L - 2] : 0;
             const int o_fo = g.occ_off[o_first], o_fcnt = g.occ_off[o_first + 1] - o_fo;
@@ -266,9 +267,9 @@ __global__ void __launch_bounds__(256, SFB_MATCH_MINBLK) k_match(sfb_graph g, sf
 }
 
 int launch_match(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_accum* acc, cudaStream_t st) {
-    if (r->n_alns == 0) return SFB_OK;
-    static int cache = 0;
-    const unsigned grid = persistent_grid(k_match, 256, blocks_for(r->n_alns, 256), &cache);   // a warp per 32 alignments
+    if (r->n_alns - w->aln_begin <= 0) return SFB_OK;
+    static OccCache cache;
+    const unsigned grid = persistent_grid(k_match, 256, blocks_for(r->n_alns - w->aln_begin, 256), cache);   // a warp per 32 alignments
     k_match<<<grid, 256, 0, st>>>(*g, *r, *w, acc->counters);
     return check_launch("k_match");
 }

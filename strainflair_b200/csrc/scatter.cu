@@ -13,7 +13,7 @@ namespace sfb {
 __global__ void __launch_bounds__(256) k_pass1_scatter(sfb_reads r, sfb_work w, double* uniq_abund, i64 det_stride,
                                                        long long* counters) {
     int done = 0;
-    for (i64 a = (i64)blockIdx.x * blockDim.x + threadIdx.x; a < r.n_alns; a += (i64)gridDim.x * blockDim.x) {
+    for (i64 a = w.aln_begin + (i64)blockIdx.x * blockDim.x + threadIdx.x; a < r.n_alns; a += (i64)gridDim.x * blockDim.x) {
         const int32_t code = w.aln_assign[a];
         if (code < 0) continue;
         const i64 w0 = r.aln_walk_off[a];
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) k_pass2_scatter(sfb_reads r, sfb_work w, 
 
 __global__ void k_collapse(double* x, i64 n, i64 stride) {
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
-        x[i] = (x[i] + x[i + stride]) + x[i + 2 * stride];
+        x[i] = (double)reinterpret_cast<const u64*>(x)[i] * 0x1p-32 + (double)reinterpret_cast<const u64*>(x)[i + stride] * 0x1p-64;
 }
 int launch_collapse(double* x, i64 n, i64 stride, cudaStream_t st) {
     if (n == 0) return SFB_OK;
@@ -53,16 +53,16 @@ int launch_collapse(double* x, i64 n, i64 stride, cudaStream_t st) {
 }
 
 int launch_pass1_scatter(const sfb_graph* g, const sfb_reads* r, const sfb_work* w, sfb_accum* acc, cudaStream_t st) {
-    if (r->n_alns == 0) return SFB_OK;
-    static int cache = 0;
-    const unsigned grid = persistent_grid(k_pass1_scatter, 256, blocks_for(r->n_alns, 256), &cache);
+    if (r->n_alns - w->aln_begin <= 0) return SFB_OK;
+    static OccCache cache;
+    const unsigned grid = persistent_grid(k_pass1_scatter, 256, blocks_for(r->n_alns - w->aln_begin, 256), cache);
     k_pass1_scatter<<<grid, 256, 0, st>>>(*r, *w, acc->uniq_abund, acc->det_stride, acc->counters);
     return check_launch("k_pass1_scatter");
 }
 int launch_pass2_scatter(const sfb_graph* g, const sfb_reads* r, const sfb_work* w, sfb_accum* acc, cudaStream_t st) {
     if (r->n_alns == 0 || w->app_cap == 0) return SFB_OK;
-    static int cache = 0;
-    const unsigned grid = persistent_grid(k_pass2_scatter, 256, blocks_for(w->app_cap, 256), &cache);
+    static OccCache cache;
+    const unsigned grid = persistent_grid(k_pass2_scatter, 256, blocks_for(w->app_cap, 256), cache);
     k_pass2_scatter<<<grid, 256, 0, st>>>(*r, *w, acc->mult_abund, acc->det_stride, acc->counters);
     return check_launch("k_pass2_scatter");
 }

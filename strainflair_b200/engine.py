@@ -32,7 +32,7 @@ class DeviceGraph:
     plus the node -> slot occurrence index that replaces Node.traversed_path and the position scan
     (json2csv.py:352-357)."""
 
-    def __init__(self, graph: Graph, device):
+    def __init__(self, graph: Graph, device, tiles=True):
         self.graph = graph
         self.device = torch.device(device)
         P = graph.n_paths
@@ -79,6 +79,20 @@ class DeviceGraph:
         self.n_slots, self.n_paths, self.n_strains, self.mask_words = n_slots, P, S, words
         self.path_off_host = path_off
         d = self.device
+        # tiles of the graph for the shared-memory kernels (tiles.py); none when the graph has no closed parts that fit
+        from .tiles import Tiling
+        import os
+        self.tiling = Tiling(graph, slot_cap=int(os.environ.get("SFB200_TILE_SLOTS", "4096"))) if tiles else None
+        if self.tiling is not None and self.tiling.n_tiles == 0:
+            self.tiling = None
+        if self.tiling is not None:
+            tl = self.tiling
+            self.tile_desc = _to_dev(tl.tile_desc.reshape(-1), d)
+            probe = _lib.SfbTiles(n_tiles=tl.n_tiles, n_items=0, max_slots=tl.max_slots, max_nodes=tl.max_nodes,
+                                  max_paths=tl.max_paths, tuple_cap=tl.tuple_cap, tile_desc=0, items=0)
+            need = int(_lib.load().sfb_tile_smem_bytes(C.byref(probe)))
+            if need < 0 or need > 227 * 1024:
+                self.tiling = None
         self.t = dict(
             slot_node=_to_dev(slot_node, d), path_off=_to_dev(path_off, d), occ_off=_to_dev(occ_off.astype(np.int32), d), occ_pair=_to_dev(occ_pair.reshape(-1), d), blk_path=_to_dev(blk_path.reshape(-1), d),
             path_seq_len=_to_dev(graph.path_seq_len, d), path_nstrain=_to_dev(nstrain, d),
@@ -162,13 +176,18 @@ class HostReads:
     (the end-to-end path copies from here every step).  ``wire``: use the compact transfer layout when the shard
     allows it (offsets as 1-byte counts, 16-bit lengths; expanded on the device by sfb_expand_reads)."""
 
-    def __init__(self, reads: Reads, pin=True, wire=True, locality=False):
-        # ``locality`` (opt-in; measured -10 % over the kernels of the pass, profiles/README.md; not validated on a
-        # GPU through this entry yet): stage the groups in locality order (schema.Reads.locality_order).  The per-path
-        # results do not depend on the order; per-group / per-alignment outputs are put back in file order by fetch.
+    def __init__(self, reads: Reads, pin=True, wire=True, tiling=None):
+        # ``tiling`` (tiles.Tiling of the graph; AbundanceEngine.stage passes its own): the groups are staged in tile
+        # order -- those whose alignments all start and end inside one tile first, tile by tile, the rest after them in
+        # file order -- with the work items of the tile kernels.  The per-path results do not depend on the order;
+        # per-group / per-alignment outputs are put back in file order by fetch.
         self.order = self.aln_index = None
-        if locality and reads.n_groups > 1:
-            reads, self.order, self.aln_index = locality_permute(reads)
+        self.tiling, self.items, self.grp_begin, self.aln_begin = tiling, None, 0, 0
+        if tiling is not None and reads.n_groups > 0:
+            reads, self.order, self.aln_index, tile_grp_off = tile_permute(reads, tiling)
+            self.items = tiling.items(tile_grp_off)
+            self.grp_begin = int(tile_grp_off[tiling.n_tiles])
+            self.aln_begin = int(reads.grp_aln_off[2 * self.grp_begin])
         self.reads = reads
         packed = _Packed(reads) if wire else None
         try:
@@ -183,13 +202,17 @@ class HostReads:
                 sizes = {k: a.nbytes for k, a in arrays.items()}
                 self.seq_len_common = 0
                 self.n_exc, self.n_wide, self.n_seq_exc, self.n_bins_exc = len(reads.exc_cov), 0, 0, 0
+            if self.items is not None:
+                sizes["tile_items"] = self.items.nbytes
             self.offs, self.size = _layout(sizes)
             self.arena = torch.empty(self.size, dtype=torch.uint8, pin_memory=bool(pin))
             view = self.arena.numpy()
             for k, (name, (o, n)) in enumerate(self.offs.items()):
                 if not n:
                     continue
-                if self.wire:
+                if name == "tile_items":
+                    view[o:o + n] = self.items.reshape(-1).view(np.uint8)
+                elif self.wire:
                     packed.copy_to(k, view.ctypes.data + o)
                 else:
                     view[o:o + n] = arrays[name].view(np.uint8)
@@ -206,8 +229,9 @@ class DeviceReads:
     """Device copy of a HostReads arena (one DMA), expanded on the device when it is in the transfer layout.
     ``arena`` / ``wide``: existing device buffers to reuse."""
 
-    def __init__(self, host: HostReads, device, arena=None, wide=None, node_len=None, expand=True):
+    def __init__(self, host: HostReads, device, arena=None, wide=None, node_len=None, expand=True, tile_desc=None):
         self.host = host
+        self.tile_desc = tile_desc
         if arena is None or arena.numel() < host.size:
             arena = torch.empty(host.size, dtype=torch.uint8, device=device)
         self.arena = arena
@@ -225,6 +249,14 @@ class DeviceReads:
         G, A, R, E = host.n_groups, host.n_alns, host.n_records, host.n_exc
         self.n_groups, self.n_alns, self.n_records, self.n_exc = G, A, R, E
         ptr = {k: (base + o if n else 0) for k, (o, n) in host.offs.items()}
+        items_ptr = ptr.pop("tile_items", 0)
+        self.tiles_c = None
+        if host.items is not None and len(host.items) and self.tile_desc is not None:
+            tl = host.tiling
+            self.tiles_c = _lib.SfbTiles(n_tiles=tl.n_tiles, n_items=len(host.items), max_slots=tl.max_slots,
+                                         max_nodes=tl.max_nodes, max_paths=tl.max_paths, tuple_cap=tl.tuple_cap,
+                                         tile_desc=self.tile_desc.data_ptr(), items=items_ptr)
+        self.grp_begin, self.aln_begin = (host.grp_begin, host.aln_begin) if self.tiles_c is not None else (0, 0)
         self.wide = wide
         if not host.wire:
             self.c = _lib.SfbReads(n_groups=G, n_alns=A, n_records=R, n_exc=E, **ptr)
@@ -285,10 +317,11 @@ class Accum:
         P, S, n_slots = dg.n_paths, dg.n_strains, dg.n_slots
         dev = dg.device
         self.P, self.S, self.n_slots = P, S, n_slots
-        # fp64 block: uniq_norm | mult_reads | mult_norm | uniq_abund | mult_abund; in the order-independent mode
-        # three such planes (exact partial sums of multiples of 2^-16 / 2^-40 / 2^-64, see sfb200.h)
+        # fp64 block: uniq_norm | mult_reads | mult_norm | uniq_abund | mult_abund; in the order-independent mode two
+        # such planes of 64-bit INTEGERS (96-bit fixed point: units of 2^-32 and of 2^-64, see sfb200.h), collapsed
+        # into the fp64 values of plane 0 before the path reduction
         self.F = 3 * P + 2 * n_slots
-        self.planes = 3 if deterministic else 1
+        self.planes = 2 if deterministic else 1
         self.f64_all = torch.zeros(self.planes * self.F, dtype=torch.float64, device=dev)
         self.f64 = self.f64_all[:self.F]
         # int64 block: uniq_reads | hist | counters | mult_hits (uint32 pairs packed in the tail)
@@ -313,7 +346,9 @@ class Accum:
         self.i64.zero_()
 
     def plane(self, k):
-        return self.f64_all[k * self.F:(k + 1) * self.F]
+        """Plane k as the tensor to sum over ranks: int64 in the order-independent mode (exact), else fp64."""
+        pl = self.f64_all[k * self.F:(k + 1) * self.F]
+        return pl.view(torch.int64) if self.planes > 1 else pl
 
 
 class Result:
@@ -355,6 +390,37 @@ def locality_permute(reads: Reads, threads=None):
     return moved, order, aln_index
 
 
+def tile_permute(reads: Reads, tiling, threads=None):
+    """(reads in tile order, order, aln_index, tile_grp_off): the native sfb_tile_permute (csrc/locality.cpp)."""
+    import os
+    G, A, R = reads.n_groups, reads.n_alns, reads.n_records
+    src = {k: np.ascontiguousarray(getattr(reads, k), dt).reshape(-1) for k, dt in (
+        ("grp_nmates", np.uint8), ("grp_aln_off", np.int64), ("mate_seq_len", np.int32), ("aln_walk_off", np.int64),
+        ("aln_bins", np.uint8), ("walk_node", np.int32), ("walk_alen", np.int32), ("exc_cov", np.float64))}
+    dst = dict(grp_nmates=np.empty(G, np.uint8), grp_aln_off=np.empty(2 * G + 1, np.int64),
+               mate_seq_len=np.empty(2 * G, np.int32), aln_walk_off=np.empty(A + 1, np.int64),
+               aln_bins=np.empty(5 * A, np.uint8), walk_node=np.empty(R, np.int32), walk_alen=np.empty(R, np.int32),
+               exc_cov=src["exc_cov"])
+    order, aln_index = np.empty(G, np.int64), np.empty(A, np.int64)
+    tile_grp_off = np.zeros(tiling.n_tiles + 2, np.int64)
+    view = lambda d: _lib.SfbReads(n_groups=G, n_alns=A, n_records=R, n_exc=len(src["exc_cov"]),       # noqa: E731
+                                   **{k: v.ctypes.data for k, v in d.items()})
+    vs, vd = view(src), view(dst)
+    node_tile = np.ascontiguousarray(tiling.node_tile, np.int32)
+    _lib.check(_lib.load().sfb_tile_permute(C.byref(vs), C.c_void_p(node_tile.ctypes.data), tiling.n_tiles,
+                                            int(threads or len(os.sched_getaffinity(0))), C.c_void_p(order.ctypes.data),
+                                            C.c_void_p(aln_index.ctypes.data), C.byref(vd),
+                                            C.c_void_p(tile_grp_off.ctypes.data)))
+    names = None
+    if reads.mate_names is not None:
+        names = [reads.mate_names[2 * int(g) + m] for g in order for m in (0, 1)]
+    moved = Reads(grp_nmates=dst["grp_nmates"], grp_aln_off=dst["grp_aln_off"], mate_seq_len=dst["mate_seq_len"],
+                  aln_walk_off=dst["aln_walk_off"], aln_read_len=reads.aln_read_len[aln_index],
+                  aln_bins=dst["aln_bins"].reshape(A, 5), walk_node=dst["walk_node"], walk_alen=dst["walk_alen"],
+                  exc_cov=reads.exc_cov, mate_names=names)
+    return moved, order, aln_index, tile_grp_off
+
+
 def restore_file_order(res, order, aln_index):
     """Per-group and per-alignment outputs of a pass over permuted read groups (``order[k]`` / ``aln_index[k]`` = old
     index of new group / alignment k), back in the order of the input file."""
@@ -377,17 +443,23 @@ class AbundanceEngine:
     """One engine per process/GPU.  ``comm`` is an optional torch.distributed process group: when
     given, ``run`` treats ``reads`` as this rank's shard of the read groups."""
 
-    def __init__(self, graph: Graph, device="cuda:0", comm=None, deterministic=False):
+    def __init__(self, graph: Graph, device="cuda:0", comm=None, deterministic=True, tiles=True):
         if not torch.cuda.is_available():
             raise _lib.SfbError("no CUDA device: the abundance engine has no CPU fallback")
         self.lib = _lib.load()
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
         self.graph = graph
-        self.dg = DeviceGraph(graph, self.device)
+        import os
+        if os.environ.get("SFB200_TILES", "1").strip().lower() in ("0", "false", "no", "off"):
+            tiles = False
+        self.dg = DeviceGraph(graph, self.device, tiles=tiles)
+        self.tiling = self.dg.tiling             # None: every read group goes through the global-memory kernels
         self.node_len = _to_dev(graph.node_len, self.device)
         self.comm = comm
-        self.deterministic = deterministic      # order-independent fp64 sums: bit-identical across runs / shards / GPUs
+        # order-independent sums (96-bit fixed point, the default): bit-identical across runs, shard counts and GPU
+        # counts; False = plain fp64 REDs, whose order (hence the last bits) varies from run to run
+        self.deterministic = deterministic
         self.acc = Accum(self.dg, deterministic)
         self.table = torch.empty((max(1, graph.n_paths), _lib.TABLE_COLS), dtype=torch.float64, device=self.device)
         self.world = 1 if comm is None else torch.distributed.get_world_size(comm)
@@ -399,8 +471,6 @@ class AbundanceEngine:
         self.work = None
         self.side = torch.cuda.Stream(device=self.device)     # pass-1 scatter runs beside the uniq exchange + pass-2 resolve
         self.overlap = True
-        import os
-        self.locality = bool(os.environ.get("SFB200_LOCALITY"))   # experimental, off by default: HostReads(locality=True)
         self.match_cap_hint = 0
         self.launches = 0
 
@@ -412,6 +482,29 @@ class AbundanceEngine:
             self.work = None
             self.work = Work(dr.n_groups, dr.n_alns, cap, self.device)
         return self.work
+
+    def stage(self, reads: Reads, pin=True, wire=True):
+        """Host staging of a read shard for this engine's graph: tile order + work items, transfer layout, one pinned arena."""
+        return HostReads(reads, pin=pin, wire=wire, tiling=self.tiling)
+
+    def _bind(self, dr, work):
+        """The global-memory kernels own the groups / alignments after the tile range of this shard."""
+        work.c.grp_begin, work.c.aln_begin = dr.grp_begin, dr.aln_begin
+
+    def tile_pass1(self, dr, work):
+        if dr.tiles_c is None:
+            return
+        _lib.check(self.lib.sfb_tile_pass1(C.byref(self.dg.c), C.byref(dr.tiles_c), C.byref(dr.c), C.byref(work.c),
+                                           C.byref(self.acc.c), _stream()))
+        self.launches += 1
+
+    def tile_pass2(self, dr, work, uniq_global=None):
+        if dr.tiles_c is None:
+            return
+        u = self.acc.uniq_reads if uniq_global is None else uniq_global
+        _lib.check(self.lib.sfb_tile_pass2(C.byref(self.dg.c), C.byref(dr.tiles_c), C.byref(dr.c), C.byref(work.c),
+                                           C.byref(self.acc.c), C.c_void_p(u.data_ptr()), _stream()))
+        self.launches += 1
 
     def match(self, dr, work):
         _lib.check(self.lib.sfb_match(C.byref(self.dg.c), C.byref(dr.c), C.byref(work.c), C.byref(self.acc.c), _stream()))
@@ -472,6 +565,9 @@ class AbundanceEngine:
         work.reset()
         self.acc.zero()
         mark("zero")
+        self._bind(dr, work)
+        self.tile_pass1(dr, work)
+        mark("tile_pass1")
         self.match(dr, work)
         mark("match")
         self.classify(dr, work)
@@ -491,6 +587,8 @@ class AbundanceEngine:
             uniq_global = self.acc.uniq_reads.clone()
             dist.all_reduce(uniq_global, group=self.comm)          # exact integer sum over shards
             mark("allreduce_uniq")
+        self.tile_pass2(dr, work, uniq_global)
+        mark("tile_pass2")
         self.pass2_resolve(dr, work, uniq_global)
         mark("pass2_resolve")
         if self.overlap:
@@ -531,7 +629,8 @@ class AbundanceEngine:
 
     def upload(self, host: HostReads):
         """H2D of a staged shard (+ device-side expansion of the transfer layout), reusing the device buffers."""
-        dr = DeviceReads(host, self.device, getattr(self, "_arena", None), getattr(self, "_wide", None), self.node_len)
+        dr = DeviceReads(host, self.device, getattr(self, "_arena", None), getattr(self, "_wide", None), self.node_len,
+                         tile_desc=getattr(self.dg, "tile_desc", None) if self.tiling is not None else None)
         self._arena, self._wide = dr.arena, dr.wide
         return dr
 
@@ -582,7 +681,8 @@ class AbundanceEngine:
         for k, host in enumerate(shards):
             slot = job.slots.setdefault(k, {})
             with torch.cuda.stream(self._copy):
-                dr = DeviceReads(host, self.device, slot.get("arena"), slot.get("wide"), self.node_len, expand=False)
+                dr = DeviceReads(host, self.device, slot.get("arena"), slot.get("wide"), self.node_len, expand=False,
+                                 tile_desc=getattr(self.dg, "tile_desc", None) if self.tiling is not None else None)
                 arrived = torch.cuda.Event()
                 arrived.record(self._copy)
             slot["arena"] = dr.arena
@@ -594,6 +694,8 @@ class AbundanceEngine:
             if work is None or work.n_groups < dr.n_groups or work.n_alns < dr.n_alns or work.match_cap < cap:
                 work = slot["work"] = Work(dr.n_groups, dr.n_alns, cap, self.device)
             work.reset()
+            self._bind(dr, work)
+            self.tile_pass1(dr, work)
             self.match(dr, work)
             self.classify(dr, work)
             self.side.wait_stream(main)
@@ -605,9 +707,12 @@ class AbundanceEngine:
             uniq_global = self.acc.uniq_reads.clone()
             dist.all_reduce(uniq_global, group=self.comm)
         for dr, work in live:
+            self._bind(dr, work)
+            self.tile_pass2(dr, work, uniq_global)
             self.pass2_resolve(dr, work, uniq_global)
         main.wait_stream(self.side)
         for dr, work in live:
+            self._bind(dr, work)
             self.pass2_scatter(dr, work)
         self._finish_pass()
         # read-back (small, pinned, asynchronous): per-path state, table, every shard's cursors
@@ -638,7 +743,7 @@ class AbundanceEngine:
             cur = job.stage["c"].numpy()
             if res.C["MATCH_OVERFLOW"] == 0:
                 job.pending = False
-                res.n_deferred = int(cur[:len(job.live), 1].sum())
+                res.n_deferred = int(cur[:len(job.live), 1].sum() + cur[:len(job.live), 7].sum())
                 res.match_fill = int(cur[len(job.live) - 1, 0]) if job.live else 0
                 check_errors(res.C)
                 return res
@@ -656,7 +761,7 @@ class AbundanceEngine:
         """Public entry: host arrays in, host results out (H2D and D2H included).  The reports need the
         per-path table, counters and histograms; ``keep_slots`` also brings the two per-node accumulator
         arrays back, ``keep_codes`` the per-group leaf codes, assignments and match lists."""
-        host = reads if isinstance(reads, HostReads) else HostReads(reads, locality=self.locality)
+        host = reads if isinstance(reads, HostReads) else self.stage(reads)
         for _ in range(3):
             dr = self.upload(host)
             work = self.run_device(dr)
@@ -712,16 +817,17 @@ class AbundanceEngine:
             slots = (acc.uniq_abund[self._plain_idx].cpu(), acc.mult_abund[self._plain_idx].cpu())   # sentinels dropped on device
         torch.cuda.current_stream().synchronize()
         res = self._result_from(acc, st["f"].numpy(), st["i"].numpy(), st["t"].numpy())
-        res.n_deferred, res.match_fill = int(st["c"][1]), int(st["c"][0])
+        res.n_deferred, res.match_fill = int(st["c"][1]) + int(st["c"][7]), int(st["c"][0])
         if slots is not None:
             res.uniq_abund, res.mult_abund = slots[0].numpy(), slots[1].numpy()
         if keep_codes:
             res.grp_code = work.t["grp_code"][:dr.n_groups].cpu().numpy()
             res.grp_code2 = work.t["grp_code2"][:dr.n_groups].cpu().numpy()
             res.aln_assign = work.t["aln_assign"][:dr.n_alns].cpu().numpy()
-            res.aln_match = work.t["aln_match"][:dr.n_alns].cpu().numpy().view(np.uint32).reshape(-1, 2)
-            res.match_buf = work.t["match_buf"][:min(work.match_cap, max(0, res.match_fill))].cpu().numpy() \
-                .view(np.uint32).reshape(-1, 2)
+            if getattr(dr, "tiles_c", None) is None:      # the tile kernels keep the match lists in shared memory
+                res.aln_match = work.t["aln_match"][:dr.n_alns].cpu().numpy().view(np.uint32).reshape(-1, 2)
+                res.match_buf = work.t["match_buf"][:min(work.match_cap, max(0, res.match_fill))].cpu().numpy() \
+                    .view(np.uint32).reshape(-1, 2)
             host = getattr(dr, "host", None)
             if host is not None and getattr(host, "order", None) is not None:
                 restore_file_order(res, host.order, host.aln_index)
@@ -758,9 +864,9 @@ def decode_matches(res, a):
     return [(pid, int((c & _lib.SLOT_MASK) - starts[pid]), bool(c & _lib.MATCH_REV)) for c, pid in pairs]
 
 
-def abundance_pass(graph: Graph, reads: Reads, device="cuda:0", deterministic=False) -> Result:
+def abundance_pass(graph: Graph, reads: Reads, device="cuda:0", deterministic=True, tiles=True) -> Result:
     """One-call public API: decoded alignments + graph in, per-path abundances and counters out."""
-    return AbundanceEngine(graph, device, deterministic=deterministic).run(reads)
+    return AbundanceEngine(graph, device, deterministic=deterministic, tiles=tiles).run(reads)
 
 
 def cluster_strain_counts(graph: Graph, device="cuda:0"):

@@ -18,7 +18,8 @@ The per-launch work statistics come from the ST_* counters the kernels maintain.
 """
 
 
-def kernel_bytes(n_groups, n_alns, n_records, n_paths, n_slots, C, match_fill, n_deferred, n_strains):
+def kernel_bytes(n_groups, n_alns, n_records, n_paths, n_slots, C, match_fill, n_deferred, n_strains, tile_groups=0,
+                 tile_alns=0):
     G, A, R = n_groups, n_alns, n_records
     cand, cmp_, tuples = C["ST_CAND"], C["ST_COMPARES"], C["ST_TUPLES"]
     r1, app, r2, hist = C["ST_P1_RECORDS"], C["ST_P2_APPLIED"], C["ST_P2_RECORDS"], C["ST_HIST"]
@@ -43,7 +44,22 @@ def kernel_bytes(n_groups, n_alns, n_records, n_paths, n_slots, C, match_fill, n
     out["pass2"] = out["pass2_resolve"] + out["pass2_scatter"]
     # path reduce: two fp64 slot arrays in, 8 fp64 + 3 counters per path
     out["path_reduce"] = 16 * n_slots + (8 * 8 + 4 * 8 + 8) * n_paths
+    # Tile kernels: the same algorithmic work (the per-unit figures above are those of the algorithm, not of one
+    # implementation), attributed by the share of alignments / groups that sit in tiles: tile_pass1 = match + classify +
+    # pass-1 scatter of those reads, tile_pass2 = pass-2 resolve + scatter; the global-memory kernels keep the rest.
+    ft = tile_alns / A if A else 0.0
+    out["tile_pass1"] = ft * (out["match"] + out["classify"] + out["pass1_scatter"])
+    out["tile_pass2"] = ft * out["pass2"]
+    for k in ("match", "classify", "pass1_scatter", "pass2_resolve", "pass2_scatter", "pass2"):
+        out[k] = (1.0 - ft) * out[k]
     out["total"] = sum(v for k, v in out.items() if k != "pass2")
+    # What the tile design has to move through HBM at the least (no index gathers, no per-record accumulator RMWs):
+    # every input array once in pass 1 (group header 25 B, alignment 8 + 5 B, record 8 B), grp_code 1 B + aln_assign 4 B
+    # out, the deferred groups' inputs once more in pass 2 + grp_code 1 B in / grp_code2 1 B out, the tile images
+    # (12 B per slot per work item ~ per tile) and the flushes (16 B per touched slot and pass), the path reduction.
+    fd = n_deferred / G if G else 0.0
+    inputs = 25 * G + 13 * A + 8 * R
+    out["stream_total"] = inputs + G + 4 * A + fd * inputs + G + fd * G + 2 * (12 + 16) * n_slots + out["path_reduce"]
     # SURVEY.md section 8d's closed form, with the realised c (compares/record), m (slot RMWs/record) and
     # candidates+matches per alignment: R(8 + 4c + 16m) + A(24 + 8(cand+matches)/A) + 16G + 20T + 8(S+11)P
     out["survey_total"] = (8 * R + 4 * cmp_ + 16 * (r1 + r2)) + (24 * A + 8 * (cand + tuples)) + 16 * G \

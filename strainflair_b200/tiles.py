@@ -1,0 +1,122 @@
+"""Tiles of the graph for the shared-memory kernels (include/sfb200.h, ``sfb_tiles``).
+
+A tile is a set of colored paths with consecutive ids whose nodes have consecutive dense indices, closed in the sense
+that no path outside the tile crosses one of its nodes.  StrainFLAIR builds one variation graph per gene cluster and
+concatenates their id spaces (graphs_construction.py:88, concat_graphs.py), so a cluster -- or a few small neighbouring
+clusters -- is a tile; a graph whose clusters interleave their node ids simply has fewer (or no) tiles and its reads go
+through the global-memory kernels.  Nothing here depends on ``dict_clusters.pickle``: the tiles come from the paths.
+"""
+import os
+
+import numpy as np
+
+SLOT_LIMIT, PATH_LIMIT, NODE_LIMIT = 32767, 255, 65520       # what the 15/8/16-bit local ids of the kernels can hold
+ITEM_GROUPS = 4096                                            # read groups per work item
+
+
+class Tiling:
+    """node_tile int32[N] (-1 = none), tile_desc int32[NT, 4] = (p0, p1, n0, n1), sizes of the largest tile."""
+
+    def __init__(self, graph, slot_cap=4096, node_cap=4096, path_cap=PATH_LIMIT, merge_target=640, tuple_cap=None):
+        P, N = graph.n_paths, graph.n_nodes
+        slot_cap, node_cap, path_cap = min(slot_cap, SLOT_LIMIT), min(node_cap, NODE_LIMIT), min(path_cap, PATH_LIMIT)
+        self.node_tile = np.full(N, -1, np.int32)
+        self.tile_desc = np.zeros((0, 4), np.int32)
+        self.max_slots = self.max_nodes = self.max_paths = 0
+        if P and N:
+            self._build(graph, slot_cap, node_cap, path_cap, merge_target)
+        k = os.environ.get("SFB200_TILE_K")
+        if tuple_cap is None and k:
+            tuple_cap = int(k)
+        if tuple_cap is None:          # match tuples per mate kept in shared memory: a mate has about one per path of its tile
+            tuple_cap = 8 if self.max_paths <= 4 else 16 if self.max_paths <= 10 else 32
+        self.tuple_cap = int(tuple_cap)
+
+    @property
+    def n_tiles(self):
+        return len(self.tile_desc)
+
+    def _build(self, graph, slot_cap, node_cap, path_cap, merge_target):
+        P, N = graph.n_paths, graph.n_nodes
+        off = graph.path_off.astype(np.int64)
+        plen = np.diff(off)
+        nodes = graph.path_nodes.astype(np.int64)
+        has = plen > 0
+        lo, hi = np.zeros(P, np.int64), np.zeros(P, np.int64)
+        if has.any():
+            starts = off[:-1][has]
+            lo[has] = np.minimum.reduceat(nodes, starts)
+            hi[has] = np.maximum.reduceat(nodes, starts)
+            # a path without nodes joins the tile of the previous path with nodes (the next one for leading ones)
+            idx = np.where(has, np.arange(P), -1)
+            np.maximum.accumulate(idx, out=idx)
+            first = int(np.argmax(has))
+            idx[idx < 0] = first
+            lo, hi = lo[idx], hi[idx]
+        else:
+            return
+        # node ranges of the paths merge into segments of the node id space: a segment starts at a covered node that no
+        # range reaches from the left, and ends at a covered node that no range leaves to the right
+        starts_at = np.bincount(lo, minlength=N + 1)[:N]
+        ends_at = np.bincount(hi, minlength=N + 1)[:N]
+        inside = np.cumsum(starts_at - np.concatenate(([0], ends_at[:-1])))      # ranges containing node n
+        covered = inside > 0
+        start = covered & (inside - starts_at == 0)
+        end = covered & (inside - ends_at == 0)
+        seg_of_node = np.cumsum(start) - 1
+        n_seg = int(start.sum())
+        seg_lo = np.flatnonzero(start)
+        seg_hi = np.flatnonzero(end) + 1                                  # exclusive
+        seg_of_path = seg_of_node[lo]
+        pmin = np.full(n_seg, P, np.int64)
+        pmax = np.full(n_seg, -1, np.int64)
+        ids = np.arange(P, dtype=np.int64)
+        np.minimum.at(pmin, seg_of_path, ids)
+        np.maximum.at(pmax, seg_of_path, ids)
+        count = np.bincount(seg_of_path, minlength=n_seg)
+        slots = np.bincount(seg_of_path, weights=plen + 1, minlength=n_seg).astype(np.int64)
+        ok = (count == pmax - pmin + 1) & (slots <= slot_cap) & (seg_hi - seg_lo <= node_cap) & (count <= path_cap)
+        # neighbouring small segments (in node order AND path order) merge up to merge_target slots
+        desc = []
+        cur = None
+        for s in range(n_seg):
+            if not ok[s]:
+                if cur is not None:
+                    desc.append(cur)
+                    cur = None
+                continue
+            item = [int(pmin[s]), int(pmax[s]) + 1, int(seg_lo[s]), int(seg_hi[s]), int(slots[s])]
+            if cur is not None and cur[1] == item[0] and cur[4] + item[4] <= merge_target \
+                    and item[3] - cur[2] <= node_cap and item[1] - cur[0] <= path_cap:
+                cur = [cur[0], item[1], cur[2], item[3], cur[4] + item[4]]
+            else:
+                if cur is not None:
+                    desc.append(cur)
+                cur = item
+        if cur is not None:
+            desc.append(cur)
+        if not desc:
+            return
+        desc = np.asarray(desc, np.int64)
+        self.tile_desc = np.ascontiguousarray(desc[:, :4], np.int32)
+        self.max_slots = int(desc[:, 4].max())
+        self.max_nodes = int((desc[:, 3] - desc[:, 2]).max())
+        self.max_paths = int((desc[:, 1] - desc[:, 0]).max())
+        span = desc[:, 3] - desc[:, 2]
+        self.node_tile[np.repeat(desc[:, 2], span) + (np.arange(int(span.sum())) - np.repeat(np.cumsum(span) - span, span))] = \
+            np.repeat(np.arange(len(desc), dtype=np.int32), span)
+
+    def items(self, tile_grp_off):
+        """Work items int32[n, 4] = (tile, first group, end group, 0) of a read shard in tile order."""
+        cnt = np.diff(tile_grp_off[:self.n_tiles + 1])
+        n_chunk = (cnt + ITEM_GROUPS - 1) // ITEM_GROUPS
+        total = int(n_chunk.sum())
+        out = np.zeros((total, 4), np.int32)
+        if total:
+            tile = np.repeat(np.arange(self.n_tiles, dtype=np.int64), n_chunk)
+            k = np.arange(total, dtype=np.int64) - np.repeat(np.cumsum(n_chunk) - n_chunk, n_chunk)
+            g0 = tile_grp_off[tile] + k * ITEM_GROUPS
+            out[:, 0] = tile
+            out[:, 1] = g0
+            out[:, 2] = np.minimum(g0 + ITEM_GROUPS, tile_grp_off[tile + 1])
+        return out

@@ -66,12 +66,13 @@ def test_leaf_codes_match_oracle():
 
 
 def test_struct_sizes_are_pointer_and_int64_multiples():
-    for st in (_lib.SfbGraph, _lib.SfbReads, _lib.SfbWork, _lib.SfbAccum):
+    for st in (_lib.SfbGraph, _lib.SfbReads, _lib.SfbWork, _lib.SfbAccum, _lib.SfbTiles):
         assert ctypes.sizeof(st) % 8 == 0
     assert ctypes.sizeof(_lib.SfbGraph) == 8 * 15
     assert ctypes.sizeof(_lib.SfbReads) == 8 * 12
     assert ctypes.sizeof(_lib.SfbWire) == 8 * 26
-    assert ctypes.sizeof(_lib.SfbWork) == 8 * 11
+    assert ctypes.sizeof(_lib.SfbWork) == 8 * 13
+    assert ctypes.sizeof(_lib.SfbTiles) == 8 * 8
     assert ctypes.sizeof(_lib.SfbAccum) == 8 * 10
 
 
@@ -90,6 +91,13 @@ def test_argument_validation_needs_no_gpu():
     assert rc == -1 and b"null" in lib.sfb_last_error()
     with pytest.raises(_lib.SfbError):
         _lib.check(rc)
+    # tiles: limits of the local ids, tuple capacity, shared-memory size
+    t = _lib.SfbTiles(n_tiles=1, n_items=0, max_slots=1359, max_nodes=472, max_paths=9, tuple_cap=16)
+    assert 40_000 < lib.sfb_tile_smem_bytes(ctypes.byref(t)) < 100_000
+    t.tuple_cap = 12
+    assert lib.sfb_tile_smem_bytes(ctypes.byref(t)) == -1 and b"tuple_cap" in lib.sfb_last_error()
+    t.tuple_cap, t.max_slots = 16, 40_000
+    assert lib.sfb_tile_smem_bytes(ctypes.byref(t)) == -1 and b"limits" in lib.sfb_last_error()
 
 
 def test_engine_refuses_without_gpu():

@@ -20,6 +20,13 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+# every combination of the two kernel families (shared-memory tiles / global memory) and the two accumulation modes
+MODES = [dict(tiles=True, deterministic=True), dict(tiles=True, deterministic=False),
+         dict(tiles=False, deterministic=True), dict(tiles=False, deterministic=False)]
+MODE_IDS = ["tiles-det", "tiles-plain", "global-det", "global-plain"]
+all_modes = pytest.mark.parametrize("mode", MODES, ids=MODE_IDS)
+
+
 def need_gpu():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
@@ -76,23 +83,25 @@ def check_against_oracle(graph, reads, res, orc, rel=compare.REL):
             assert compare.close(res.table[p, k], row[c], rel), (p, c, res.table[p, k], row[c])
 
 
+@all_modes
 @pytest.mark.parametrize("name,scale", [("tiny", 1.0), ("small", 0.2)])
-def test_synthetic_matches_oracle(name, scale):
+def test_synthetic_matches_oracle(name, scale, mode):
     need_gpu()
     graph, reads = synth.make_config(name, scale=scale)
-    res = engine.abundance_pass(graph, reads)
+    res = engine.abundance_pass(graph, reads, **mode)
     orc = oa.AbundanceOracle(graph.as_dict(), reads.as_dict()).run()
     check_against_oracle(graph, reads, res, orc)
 
 
+@all_modes
 @pytest.mark.parametrize("n_hap", [16, 48])
-def test_many_candidate_paths_take_the_generic_kernels(n_hap):
+def test_many_candidate_paths_take_the_generic_kernels(n_hap, mode):
     """~10 tuples per alignment (LocalView: > 8 per mate) and ~24, up to 60 with ties (GlobalView: > 32)."""
     need_gpu()
     graph = synth.make_graph(11, n_clusters=6, chain_len=80, hap_lo=n_hap, hap_hi=n_hap, n_strains=9, bubble_p=0.4,
                              flip_p=0.03)
     reads = synth.make_reads(graph, 12, n_pairs=1200, read_len=100, p_tie=0.3)
-    res = engine.abundance_pass(graph, reads)
+    res = engine.abundance_pass(graph, reads, **mode)
     orc = oa.AbundanceOracle(graph.as_dict(), reads.as_dict()).run()
     per_aln = res.C["ST_TUPLES"] / max(1, reads.n_alns)
     assert per_aln > (9 if n_hap == 16 else 20), per_aln
@@ -100,22 +109,24 @@ def test_many_candidate_paths_take_the_generic_kernels(n_hap):
     check_against_oracle(graph, reads, res, orc)
 
 
-def test_more_than_64_strains_uses_multiword_masks():
+@all_modes
+def test_more_than_64_strains_uses_multiword_masks(mode):
     need_gpu()
     graph = synth.make_graph(21, n_clusters=30, chain_len=14, hap_lo=1, hap_hi=6, n_strains=150, bubble_p=0.4, flip_p=0.3)
     reads = synth.make_reads(graph, 22, n_pairs=2500, read_len=80, p_same_path=0.6)
-    res = engine.abundance_pass(graph, reads)
+    res = engine.abundance_pass(graph, reads, **mode)
     orc = oa.AbundanceOracle(graph.as_dict(), reads.as_dict()).run()
     assert orc.C["DIFF_CP"] > 0 and orc.C["INCONSIST"] > 0
     check_against_oracle(graph, reads, res, orc)
 
 
-def test_explicit_coverage_records():
+@all_modes
+def test_explicit_coverage_records(mode):
     need_gpu()
     gkw, rkw = synth.CONFIGS["tiny"]
     graph = synth.make_graph(7, **gkw)
     reads = synth.make_reads(graph, 8, n_pairs=3000, read_len=60, p_exc=0.05)
-    res = engine.abundance_pass(graph, reads)
+    res = engine.abundance_pass(graph, reads, **mode)
     orc = oa.AbundanceOracle(graph.as_dict(), reads.as_dict()).run()
     check_against_oracle(graph, reads, res, orc)
 
@@ -123,7 +134,7 @@ def test_explicit_coverage_records():
 def test_match_lists_equal_oracle():
     need_gpu()
     graph, reads = synth.make_config("tiny")
-    res = engine.abundance_pass(graph, reads)
+    res = engine.abundance_pass(graph, reads, tiles=False)      # the tile kernels keep their match lists in shared memory
     orc = oa.AbundanceOracle(graph.as_dict(), reads.as_dict())
     for a in range(reads.n_alns):
         mine = engine.decode_matches(res, a)
@@ -188,7 +199,7 @@ def _repetitive_case(seed, n_paths=40, alphabet=4, n_walks=4000):
 def test_match_corner_cases_equal_oracle(seed, alphabet):
     need_gpu()
     graph, reads = _repetitive_case(seed, alphabet=alphabet)
-    res = engine.abundance_pass(graph, reads)
+    res = engine.abundance_pass(graph, reads, tiles=False)
     orc = oa.AbundanceOracle(graph.as_dict(), reads.as_dict())
     most = 0
     for a in range(reads.n_alns):
@@ -197,7 +208,12 @@ def test_match_corner_cases_equal_oracle(seed, alphabet):
         most = max(most, len(mine))
     if alphabet <= 3:
         assert most > 8                           # the serial path for long match lists was taken
-    check_against_oracle(graph, reads, res, orc.run())
+    orc.run()
+    check_against_oracle(graph, reads, res, orc)
+    # the same corners against the shared-memory index: all 40 paths share the alphabet, so they are one tile
+    eng = engine.AbundanceEngine(graph)
+    assert eng.tiling is not None and eng.tiling.n_tiles == 1
+    check_against_oracle(graph, reads, eng.run(reads), orc)
 
 
 def test_match_buffer_regrows():
@@ -217,8 +233,9 @@ def _small_work(eng, dr):
     return eng.work
 
 
+@all_modes
 @pytest.mark.parametrize("d", sorted(glob.glob(os.path.join(HERE, "golden", "case_*"))), ids=os.path.basename)
-def test_golden_cases_through_cuda(d):
+def test_golden_cases_through_cuda(d, mode):
     """The reference's own outputs (tests/golden) reproduced by the CUDA path: ints exact, fp64 <= 1e-9."""
     need_gpu()
     with open(os.path.join(d, "expected.json")) as fh:
@@ -226,18 +243,19 @@ def test_golden_cases_through_cuda(d):
     g = og.load_graph(os.path.join(d, "graph.gfa"), os.path.join(d, "dict_clusters.pickle"))
     r = od.decode_json(os.path.join(d, "reads.json"), g, exp["params"]["thr"])
     graph, reads = Graph.from_dict(g), Reads.from_dict(r)
-    res = engine.abundance_pass(graph, reads)
+    res = engine.abundance_pass(graph, reads, **mode)
     compare.check_state_vs_reference(res, exp, exact=False)
 
 
-def test_empty_and_degenerate_inputs():
+@all_modes
+def test_empty_and_degenerate_inputs(mode):
     need_gpu()
     graph, reads = synth.make_config("tiny")
     empty = reads.slice_groups(0, 0)
-    res = engine.abundance_pass(graph, empty)
+    res = engine.abundance_pass(graph, empty, **mode)
     assert res.C["NB_READS"] == 0 and not res.uniq_abund.any()
     one = reads.slice_groups(5, 6)
-    res = engine.abundance_pass(graph, one)
+    res = engine.abundance_pass(graph, one, **mode)
     orc = oa.AbundanceOracle(graph.as_dict(), one.as_dict()).run()
     check_against_oracle(graph, one, res, orc)
 

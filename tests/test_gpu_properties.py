@@ -54,8 +54,17 @@ def test_conservation_laws(name, scale):
     assert abs(float(res.uniq_abund.sum()) - want) <= 1e-9 * want
     L = np.diff(reads.aln_walk_off)
     assert C["ST_P1_RECORDS"] == int(L[res.aln_assign >= 0].sum())
+    # the two kernel families (shared-memory tiles above, global memory here) agree: integers exactly, and -- the sums
+    # being exact integer sums of the same terms in the default order-independent mode -- the fp64 arrays bit for bit
+    assert eng.tiling is not None and eng.tiling.n_tiles > 1000
+    glob = engine.AbundanceEngine(graph, tiles=False).run(reads)
+    assert glob.C == {**res.C, **{k: glob.C[k] for k in ("ST_CAND", "ST_COMPARES")}}
+    for name in ("grp_code", "grp_code2", "aln_assign", "uniq_reads", "hist", "mult_hits"):
+        assert np.array_equal(getattr(glob, name), getattr(res, name)), name
+    for name in ("uniq_norm", "mult_reads", "mult_norm", "uniq_abund", "mult_abund", "table"):
+        assert np.array_equal(getattr(glob, name), getattr(res, name), equal_nan=True), name
     # pass 2 hands out exactly one read per (mate, alignment) unit: the shares of a unit sum to 1
-    x, y = res.aln_match[:, 0], res.aln_match[:, 1]
+    x, y = glob.aln_match[:, 0], glob.aln_match[:, 1]
     has_tuples = x != _lib.MATCH_NONE
     units = n2(1)
     for m, codes in ((0, lo2), (1, hi2)):

@@ -1,0 +1,32 @@
+"""GPU parity at the shapes of BASELINE.json's configurations: the CUDA path against the oracle on samples of the C3,
+C4 and C5 workloads (the full graphs, as many read pairs as the Python oracle finishes in well under a minute)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import abundance as oa
+from strainflair_b200 import engine, synth
+from test_gpu_parity import check_against_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name,pairs", [("c3", 60_000), ("c4", 12_000), ("c5", 30_000)])
+def test_config_shapes_match_oracle(name, pairs):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    gkw, rkw = synth.CONFIGS[name]
+    idx = list(synth.CONFIGS).index(name)
+    graph = synth.make_graph(synth.SEED0 + idx, **gkw)
+    reads = synth.make_reads(graph, synth.SEED0 + idx + 1000, n_pairs=pairs, read_len=rkw["read_len"])
+    orc = oa.AbundanceOracle(graph.as_dict(), reads.as_dict()).run()
+    eng = engine.AbundanceEngine(graph)
+    assert eng.tiling is not None and eng.tiling.n_tiles >= 3000          # every cluster is a tile (or shares one)
+    host = eng.stage(reads)
+    assert host.grp_begin > 0.9 * reads.n_groups                          # ... and holds most read groups
+    res = eng.run(host)
+    check_against_oracle(graph, reads, res, orc)
+    if name == "c4":
+        assert res.C["ST_TUPLES"] / reads.n_alns > 8 and res.n_deferred > 0.7 * reads.n_groups
+    # the global-memory kernels on the same sample
+    check_against_oracle(graph, reads, engine.AbundanceEngine(graph, tiles=False).run(reads), orc)

@@ -445,20 +445,86 @@ def test_group_permutation_keeps_every_result():
             assert np.allclose(a, b, rtol=1e-12, atol=0) and np.array_equal(a > 0, b > 0), name
 
 
-def test_locality_staging_and_file_order_restoration():
-    """HostReads(locality=True) stages the permuted groups (packed natively as any other shard) and
-    engine.restore_file_order puts per-group / per-alignment outputs back in file order (the oracle stands in for the
-    kernels here; the opt-in entry itself still has to be validated on a GPU)."""
+def _tile_keys(reads, tiling):
+    """numpy statement of sfb_tile_permute's key: the tile holding the first and last node of every alignment."""
+    keys = np.full(reads.n_groups, tiling.n_tiles, np.int64)
+    for g in range(reads.n_groups):
+        a0, a1 = int(reads.grp_aln_off[2 * g]), int(reads.grp_aln_off[2 * g + 2])
+        tiles = set()
+        for a in range(a0, a1):
+            w0, w1 = int(reads.aln_walk_off[a]), int(reads.aln_walk_off[a + 1])
+            if w1 > w0:
+                tiles.add(int(tiling.node_tile[reads.walk_node[w0]]))
+                tiles.add(int(tiling.node_tile[reads.walk_node[w1 - 1]]))
+        if len(tiles) == 1 and -1 not in tiles:
+            keys[g] = tiles.pop()
+    return keys
+
+
+def test_tiling_of_the_synthetic_graph():
+    """tiles.Tiling: every tile is a closed part of the graph (consecutive paths, consecutive nodes, no path outside
+    crosses one of its nodes) within the limits of the kernels; the bubble-chain generator gives one tile per cluster
+    or per few small clusters."""
+    from strainflair_b200 import synth
+    from strainflair_b200.tiles import Tiling
+    for name in ("tiny", "small"):
+        graph, _ = synth.make_config(name, scale=0.01)
+        tl = Tiling(graph)
+        assert tl.n_tiles > 0 and tl.tuple_cap in (8, 16, 32)
+        path_of_node = [set() for _ in range(graph.n_nodes)]
+        for p in range(graph.n_paths):
+            for n in graph.path_nodes[graph.path_off[p]:graph.path_off[p + 1]]:
+                path_of_node[int(n)].add(p)
+        seen_paths = 0
+        for t, (p0, p1, n0, n1) in enumerate(tl.tile_desc):
+            assert p0 < p1 and n0 < n1
+            slots = int(graph.path_off[p1] - graph.path_off[p0]) + (p1 - p0)
+            assert slots <= tl.max_slots <= 32767 and p1 - p0 <= tl.max_paths <= 255 and n1 - n0 <= tl.max_nodes
+            for p in range(p0, p1):
+                nodes = graph.path_nodes[graph.path_off[p]:graph.path_off[p + 1]]
+                assert nodes.min() >= n0 and nodes.max() < n1
+            for n in range(n0, n1):
+                assert all(p0 <= p < p1 for p in path_of_node[n]) and tl.node_tile[n] == t
+            seen_paths += p1 - p0
+        assert seen_paths == graph.n_paths                      # the generator's clusters are all tileable
+    # a graph whose two paths interleave their node ids is one closed part; with a small cap it has no tile at all
+    from strainflair_b200.schema import Graph
+    g = Graph(node_ids=np.arange(1, 9), node_len=np.full(8, 5, np.int32), path_off=np.array([0, 4, 8]),
+              path_nodes=np.array([0, 2, 4, 6, 1, 3, 5, 7], np.int32), path_seq_len=np.array([20, 20]),
+              pstr_off=np.array([0, 1, 2]), pstr_id=np.array([0, 1], np.int32), pstr_cnt=np.array([1, 1], np.int32),
+              path_cluster=np.array([0, 1], np.int32), clu_off=np.array([0, 1, 2]), clu_paths=np.array([0, 1], np.int32),
+              strain_names=["a", "b"], header_strains=[0, 1])
+    one = Tiling(g)
+    assert one.n_tiles == 1 and tuple(one.tile_desc[0]) == (0, 2, 0, 8)
+    assert Tiling(g, slot_cap=6).n_tiles == 0 and (Tiling(g, slot_cap=6).node_tile == -1).all()
+
+
+def test_tile_staging_and_file_order_restoration():
+    """HostReads(tiling=...) stages the groups in tile order (native sfb_tile_permute == the numpy statement of its key
+    + a stable sort), with the work items of the tile kernels, and engine.restore_file_order puts per-group /
+    per-alignment outputs back in file order (the oracle stands in for the kernels here)."""
     from oracle import abundance as oa
     from strainflair_b200 import engine, synth
+    from strainflair_b200.tiles import ITEM_GROUPS, Tiling
     graph, reads = synth.make_config("tiny")
-    host = engine.HostReads(reads, pin=False, wire=True, locality=True)
+    tl = Tiling(graph)
+    host = engine.HostReads(reads, pin=False, wire=True, tiling=tl)
     plain = engine.HostReads(reads, pin=False, wire=True)
-    assert plain.order is None and host.order is not None and host.wire
-    assert sorted(host.order.tolist()) == list(range(reads.n_groups))
+    assert plain.order is None and plain.items is None and host.order is not None and host.wire
+    keys = _tile_keys(reads, tl)
+    want = np.argsort(keys, kind="stable")
+    assert np.array_equal(host.order, want)
     moved, aln_index = reads.permute_groups(host.order, return_index=True)
     assert np.array_equal(host.reads.walk_node, moved.walk_node) and np.array_equal(host.aln_index, aln_index)
-    assert sorted(aln_index.tolist()) == list(range(reads.n_alns))
+    assert host.grp_begin == int((keys < tl.n_tiles).sum()) and 0 < host.grp_begin < reads.n_groups
+    assert host.aln_begin == int(moved.grp_aln_off[2 * host.grp_begin])
+    # the work items cover the tile range exactly once, tile by tile, in pieces of at most ITEM_GROUPS groups
+    covered = np.zeros(reads.n_groups, np.int32)
+    for tile, g0, g1, _ in host.items:
+        assert 0 < g1 - g0 <= ITEM_GROUPS and (keys[host.order[g0:g1]] == tile).all()
+        covered[g0:g1] += 1
+    assert (covered[:host.grp_begin] == 1).all() and (covered[host.grp_begin:] == 0).all()
+    assert "tile_items" in host.offs
     base = oa.AbundanceOracle(graph.as_dict(), reads.as_dict()).run()
     got = oa.AbundanceOracle(graph.as_dict(), moved.as_dict()).run()
     res = engine.Result(grp_code=np.asarray(got.grp_code).copy(), grp_code2=np.asarray(got.grp_code2).copy(),
@@ -467,6 +533,9 @@ def test_locality_staging_and_file_order_restoration():
     engine.restore_file_order(res, host.order, host.aln_index)
     assert np.array_equal(res.grp_code, base.grp_code) and np.array_equal(res.grp_code2, base.grp_code2)
     assert np.array_equal(res.aln_assign, base.aln_assign)
+    # empty and tile-free shards
+    empty = engine.HostReads(reads.slice_groups(0, 0), pin=False, tiling=tl)
+    assert empty.items is None and empty.grp_begin == 0
 
 
 @pytest.mark.parametrize("threads", [1, 3, 8])
