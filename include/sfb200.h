@@ -220,17 +220,29 @@ typedef struct sfb_accum {
  * spaces, graphs_construction.py:88, concat_graphs.py).  Every alignment whose first and last node lie in the tile
  * can only match paths of the tile, so a thread block that holds the tile's path nodes, occurrence index and slot
  * accumulators in shared memory runs get_matching_path, the decision tree and the node loops of such read groups
- * without touching the graph or the accumulators in HBM.  Limits per tile: 32767 slots, 255 paths, 65520 nodes.
+ * without touching the graph or the accumulators in HBM.  Limits per tile: 32767 slots, 255 paths, 65520 nodes,
+ * 65535 distinct steps.
  * Read groups are staged in tile order (sfb_tile_permute); the others (mates in different tiles, nodes outside
  * every tile, no alignment at all) follow and go through the global-memory kernels. */
 typedef struct sfb_tiles {
     int64_t n_tiles, n_items;
-    int64_t max_slots, max_nodes, max_paths;  /* of the largest tile: sizes the shared memory of the tile kernels  */
-    int64_t tuple_cap;             /* match tuples per mate kept in shared memory (8, 16 or 32); aligned pairs with
-                                      more are handed to the global-memory kernels through w->slow              */
-    const int32_t* tile_desc;      /* [4*n_tiles] (p0, p1, n0, n1) per tile                                     */
+    int64_t max_slots, max_nodes, max_paths, max_edges;  /* of the largest tile: size the shared memory of the kernels */
+    int64_t tuple_cap;             /* match tuples per ALIGNMENT kept in shared memory (8, 16 or 32) in tiles that are not
+                                      "simple"; aligned pairs with an alignment that has more are handed to the
+                                      global-memory kernels through w->slow                                      */
+    const int32_t* tile_desc;      /* [8*n_tiles] (p0, p1, n0, n1, flags, 0, 0, 0) per tile; flags bit 0 = "simple":
+                                      at most 64 paths and no node twice in one path -- a walk then matches a path
+                                      iff the path takes every step of the walk, and get_matching_path is an AND of
+                                      the 64-bit path sets of the steps (32-byte aligned)                       */
     const int32_t* items;          /* [4*n_items] (tile, first group, end group, 0): work items of this read shard,
                                       a tile with many groups is cut into several                               */
+    /* step index of the simple tiles (zeros elsewhere): the distinct successors of node n on the tile's paths are
+       edge_succ[edge_off[n] .. edge_off[n+1]), ascending, edge_mask[e] = the paths that take that step (bit = path id
+       - p0); node_mask[n] = the paths through n */
+    const int32_t*  edge_off;      /* [n_nodes+1] */
+    const int32_t*  edge_succ;     /* [edge_off[n_nodes]] */
+    const uint64_t* edge_mask;     /* [edge_off[n_nodes]] */
+    const uint64_t* node_mask;     /* [n_nodes] */
 } sfb_tiles;
 
 /* ---- entry points ------------------------------------------------------- */
@@ -354,7 +366,7 @@ int sfb_locality_permute(const sfb_reads* src, int n_threads, int64_t* order, in
 
 /* Tile order (see sfb_tiles): as sfb_locality_permute, but the key of a group is the tile that holds the first and
  * the last node of every one of its alignments (node_tile[n] = tile of dense node n, -1 = none); groups without such
- * a tile -- and groups without any alignment -- go last, in file order.  tile_grp_off[n_tiles + 2]: the groups of tile
+ * a tile -- and groups without any alignment, or with more than 255 alignments in a mate -- go last, in file order.  tile_grp_off[n_tiles + 2]: the groups of tile
  * t are [off[t], off[t+1]) of the permuted order, the others [off[n_tiles], off[n_tiles+1] = G). */
 int sfb_tile_permute(const sfb_reads* src, const int32_t* node_tile, int64_t n_tiles, int n_threads, int64_t* order,
                      int64_t* aln_index, const sfb_reads* dst, int64_t* tile_grp_off);

@@ -58,7 +58,9 @@ class SfbWork(C.Structure):
 class SfbTiles(C.Structure):
     _fields_ = [
         ("n_tiles", C.c_int64), ("n_items", C.c_int64), ("max_slots", C.c_int64), ("max_nodes", C.c_int64),
-        ("max_paths", C.c_int64), ("tuple_cap", C.c_int64), ("tile_desc", C.c_void_p), ("items", C.c_void_p),
+        ("max_paths", C.c_int64), ("max_edges", C.c_int64), ("tuple_cap", C.c_int64), ("tile_desc", C.c_void_p),
+        ("items", C.c_void_p), ("edge_off", C.c_void_p), ("edge_succ", C.c_void_p), ("edge_mask", C.c_void_p),
+        ("node_mask", C.c_void_p),
     ]
 
 

@@ -167,7 +167,8 @@ extern "C" int sfb_tile_permute(const sfb_reads* r, const int32_t* node_tile, in
             for (size_t g = lo; g < hi; ++g) {
                 const int64_t a0 = r->grp_aln_off[2 * g], a1 = r->grp_aln_off[2 * g + 2];
                 int64_t tile = -1;
-                bool ok = a1 > a0;
+                const int64_t am = r->grp_aln_off[2 * g + 1];
+                bool ok = a1 > a0 && am - a0 <= 255 && a1 - am <= 255;      // the kernels' chunks hold 2 * 255 alignments
                 for (int64_t a = a0; a < a1 && ok; ++a) {
                     const int64_t w0 = r->aln_walk_off[a], w1 = r->aln_walk_off[a + 1];
                     if (w1 <= w0) continue;                               // an empty walk matches nothing anywhere

@@ -2,11 +2,17 @@
 //
 // A thread block takes a work item (tile, range of read groups in tile order), stages the tile in shared memory --
 // path nodes, node -> occurrence index, slot -> path, per-path constants -- together with zeroed accumulator bins,
-// and then runs, one thread per read group, everything the reference does for the group:
-//   k_tile_pass1   get_matching_path (json2csv.py:341-363) on both orientations of every alignment, the pass-1
-//                  decision tree (:828-1053), fill_abund_dist (:321-339) including its node loop
-//   k_tile_pass2   for the deferred groups: the matches again (as the reference recomputes them, :1103-1114), the
-//                  pass-2 candidate selection and ratios (:1123-1274), the node loops (:1157-1158)
+// and works through the item in chunks of 256 read groups.  Every chunk runs as a sequence of phases, each over a
+// dense list so that the lanes of a warp stay busy (one thread per group for everything ran at 4-8 active lanes):
+//   k_tile_pass1   M  thread = alignment: get_matching_path (json2csv.py:341-363) on both orientations against the
+//                     shared-memory index, match tuples into a per-alignment store
+//                  C  thread = read group: the pass-1 decision tree (:828-1053) and the per-read part of
+//                     fill_abund_dist (:321-339); unique assignments go to a list
+//                  S  thread = assigned alignment: its node loop (:329-330) into the bins
+//   k_tile_pass2   D  thread = read group: deferred?  its alignments go to a list
+//                  M  thread = listed alignment: the matches again (as the reference recomputes them, :1103-1114)
+//                  C  thread = deferred group: candidate selection and ratios (:1123-1274), per-path sums, work items
+//                  S  thread = work item: the node loop (:1157-1158)
 // Compares run against shared memory instead of index gathers, the fp64 additions go to shared-memory bins in 96-bit
 // fixed point (three 32-bit limbs per accumulator, native ATOMS.ADD with exact carries: integer sums do not depend
 // on the order of the additions) and are flushed once per work item with 64-bit integer REDs; histogram updates are
@@ -19,24 +25,35 @@
 
 namespace sfb {
 
-constexpr int kTT = 256;              // threads per block
+constexpr int kTT = 256;              // threads per block = read groups per chunk
+constexpr int kAC = 3 * kTT;          // alignments per chunk (a chunk shrinks until its alignments fit)
 constexpr int kHash = 256;            // entries of the histogram aggregation table
 constexpr u64 kHashEmpty = ~0ull;
 constexpr unsigned kNoNode = 0xFFFEu; // local id of a walk node outside the tile (never equal to a path node)
 constexpr unsigned kSentinel = 0xFFFFu;
+constexpr int kOver = 255;            // tuple count of an alignment with more than KA matches
+
+__host__ __device__ inline int tile_app_cap(int KA) { return 192 * KA; }     // pass-2 work items per chunk
 
 // ---- shared-memory layout, sized by the largest tile (same arithmetic on host and device) -----------------------
 struct TileLayout {
-    unsigned hkey, pseq, pU, tup, bins, plimb, pclu, pstr0, pnstr, hcnt, sc, misc, poff, node, occ, occ_off, spath, total;
+    unsigned hkey, pseq, pU, appw, emask, nmask, store, bins, plimb, pclu, pstr0, pnstr, hcnt, sc, misc, lst, appk, poff, node,
+        occ, occ_off, eoff, esucc, alist, glist, spath, cnt, total;
 };
-__host__ __device__ inline TileLayout tile_layout(int ms, int mn, int mp, int K) {
+__host__ __device__ inline TileLayout tile_layout(int pass, int ms, int mn, int mp, int me, int KA) {
     TileLayout L;
     unsigned o = 0;
     auto take = [&](unsigned bytes) { const unsigned at = o; o += (bytes + 15u) & ~15u; return at; };
+    const unsigned napp = pass == 2 ? tile_app_cap(KA) : 0;
+    const unsigned store_tup = 2u * kAC * KA, store_mask = 16u * kAC;
     L.hkey = take(8u * kHash);
     L.pseq = take(8u * mp);
-    L.pU = take(8u * mp);
-    L.tup = take(4u * 2 * K * kTT);
+    L.pU = take(pass == 2 ? 8u * mp : 0);
+    L.appw = take(8u * napp);                   // pass 2: weight of a work item
+    L.emask = take(8u * me);                    // step index of a simple tile: path set of every step ...
+    L.nmask = take(8u * mn);                    // ... and of every node
+    L.store = take(store_tup > store_mask ? store_tup : store_mask);   // per alignment: match tuples (rev << 15 | slot),
+                                                                       // or the forward / reverse path sets (simple tile)
     L.bins = take(12u * ms);
     L.plimb = take(28u * mp);
     L.pclu = take(4u * mp);
@@ -44,12 +61,19 @@ __host__ __device__ inline TileLayout tile_layout(int ms, int mn, int mp, int K)
     L.pnstr = take(4u * mp);
     L.hcnt = take(4u * kHash);
     L.sc = take(sizeof(BlockCounters));
-    L.misc = take(16);
+    L.misc = take(32);
+    L.lst = take(pass == 1 ? 4u * kAC : 0);     // pass 1: unique assignments (alignment << 16 | slot)
+    L.appk = take(4u * napp);                   // pass 2: work item (alignment << 16 | slot)
     L.poff = take(2u * (mp + 1));
     L.node = take(2u * (ms + 2));
     L.occ = take(2u * ms);
     L.occ_off = take(2u * (mn + 1));
+    L.eoff = take(2u * (mn + 1));
+    L.esucc = take(2u * me);
+    L.alist = take(pass == 2 ? 2u * kAC : 0);   // pass 2: alignments of the deferred groups
+    L.glist = take(pass == 2 ? 2u * kTT : 0);   // pass 2: deferred groups
     L.spath = take(ms);
+    L.cnt = take(kAC);                          // tuples per alignment, kOver = more than KA
     L.total = o;
     return L;
 }
@@ -58,7 +82,10 @@ struct TileS {
     u64* hkey;
     long long* pseq;
     long long* pU;
-    uint32_t* tup;       // [2][K][kTT], this thread's column
+    double* appw;
+    u64* emask;
+    u64* nmask;
+    u64* amask;          // [kAC][2] forward / reverse path set of an alignment (simple tile; shares `tup`'s memory)
     uint32_t* bins;      // [ns][3] limbs x0, x1, x2
     uint32_t* plimb;     // [np][7]: count / flag, three limbs A, three limbs B
     int* pclu;
@@ -66,21 +93,35 @@ struct TileS {
     int* pnstr;
     uint32_t* hcnt;
     BlockCounters* sc;
-    int* misc;
+    int* misc;           // [0] work item, [1] list fill (assignments / work items), [2] alignment list, [3] group list
+    uint32_t* lst;
+    uint32_t* appk;
     uint16_t* poff;
     uint16_t* node;
     uint16_t* occ;
     uint16_t* occ_off;
+    uint16_t* eoff;
+    uint16_t* esucc;
+    uint16_t* tup;
+    uint16_t* alist;
+    uint16_t* glist;
     uint8_t* spath;
+    uint8_t* cnt;
     int p0, np, n0, nn, s0, ns;
+    bool simple;
+    i64 a0c;             // first alignment of the chunk
 };
-__device__ __forceinline__ TileS tile_carve(unsigned char* smem, const sfb_tiles& t) {
-    const TileLayout L = tile_layout((int)t.max_slots, (int)t.max_nodes, (int)t.max_paths, (int)t.tuple_cap);
+__device__ __forceinline__ TileS tile_carve(int pass, unsigned char* smem, const sfb_tiles& t) {
+    const TileLayout L = tile_layout(pass, (int)t.max_slots, (int)t.max_nodes, (int)t.max_paths, (int)t.max_edges, (int)t.tuple_cap);
     TileS T;
     T.hkey = reinterpret_cast<u64*>(smem + L.hkey);
     T.pseq = reinterpret_cast<long long*>(smem + L.pseq);
     T.pU = reinterpret_cast<long long*>(smem + L.pU);
-    T.tup = reinterpret_cast<uint32_t*>(smem + L.tup) + threadIdx.x;
+    T.appw = reinterpret_cast<double*>(smem + L.appw);
+    T.emask = reinterpret_cast<u64*>(smem + L.emask);
+    T.nmask = reinterpret_cast<u64*>(smem + L.nmask);
+    T.amask = reinterpret_cast<u64*>(smem + L.store);
+    T.tup = reinterpret_cast<uint16_t*>(smem + L.store);
     T.bins = reinterpret_cast<uint32_t*>(smem + L.bins);
     T.plimb = reinterpret_cast<uint32_t*>(smem + L.plimb);
     T.pclu = reinterpret_cast<int*>(smem + L.pclu);
@@ -89,12 +130,21 @@ __device__ __forceinline__ TileS tile_carve(unsigned char* smem, const sfb_tiles
     T.hcnt = reinterpret_cast<uint32_t*>(smem + L.hcnt);
     T.sc = reinterpret_cast<BlockCounters*>(smem + L.sc);
     T.misc = reinterpret_cast<int*>(smem + L.misc);
+    T.lst = reinterpret_cast<uint32_t*>(smem + L.lst);
+    T.appk = reinterpret_cast<uint32_t*>(smem + L.appk);
     T.poff = reinterpret_cast<uint16_t*>(smem + L.poff);
     T.node = reinterpret_cast<uint16_t*>(smem + L.node);
     T.occ = reinterpret_cast<uint16_t*>(smem + L.occ);
     T.occ_off = reinterpret_cast<uint16_t*>(smem + L.occ_off);
+    T.eoff = reinterpret_cast<uint16_t*>(smem + L.eoff);
+    T.esucc = reinterpret_cast<uint16_t*>(smem + L.esucc);
+    T.alist = reinterpret_cast<uint16_t*>(smem + L.alist);
+    T.glist = reinterpret_cast<uint16_t*>(smem + L.glist);
     T.spath = smem + L.spath;
+    T.cnt = smem + L.cnt;
     T.p0 = T.np = T.n0 = T.nn = T.s0 = T.ns = 0;
+    T.simple = false;
+    T.a0c = 0;
     return T;
 }
 
@@ -152,7 +202,8 @@ __device__ __forceinline__ void tile_add_records(const TileS& T, const sfb_reads
 // ---- staging / flushing of a tile -------------------------------------------------------------------------------
 template <int PASS>
 __device__ __forceinline__ void tile_stage(TileS& T, const Dev& d, const sfb_tiles& t, int tile, const long long* U) {
-    const int4 desc = reinterpret_cast<const int4*>(t.tile_desc)[tile];
+    const int4 desc = reinterpret_cast<const int4*>(t.tile_desc)[2 * tile];
+    T.simple = (reinterpret_cast<const int4*>(t.tile_desc)[2 * tile + 1].x & 1) != 0;
     T.p0 = desc.x;
     T.np = desc.y - desc.x;
     T.n0 = desc.z;
@@ -171,6 +222,16 @@ __device__ __forceinline__ void tile_stage(TileS& T, const Dev& d, const sfb_til
     const int2* occ = reinterpret_cast<const int2*>(d.g.occ_pair);
     for (int i = tid; i < nocc; i += kTT) T.occ[i] = (uint16_t)(occ[obase + i].x - T.s0);
     for (int p = tid; p <= T.np; p += kTT) T.poff[p] = (uint16_t)(d.g.path_off[T.p0 + p] - T.s0);
+    if (T.simple) {
+        const int ebase = t.edge_off[T.n0];
+        for (int i = tid; i <= T.nn; i += kTT) T.eoff[i] = (uint16_t)(t.edge_off[T.n0 + i] - ebase);
+        const int ne = t.edge_off[T.n0 + T.nn] - ebase;
+        for (int i = tid; i < ne; i += kTT) {
+            T.esucc[i] = (uint16_t)(t.edge_succ[ebase + i] - T.n0);
+            T.emask[i] = t.edge_mask[ebase + i];
+        }
+        for (int i = tid; i < T.nn; i += kTT) T.nmask[i] = t.node_mask[T.n0 + i];
+    }
     for (int p = tid; p < T.np; p += kTT) {
         T.pseq[p] = d.g.path_seq_len[T.p0 + p];
         T.pclu[p] = d.g.path_cluster[T.p0 + p];
@@ -277,56 +338,78 @@ __device__ __forceinline__ void tile_enum(const TileS& T, const sfb_reads& r, i6
         }
 }
 
-// match tuple in shared memory: rev (1) | local slot (15) | local path (8) | alignment inside the mate (8)
-__device__ __forceinline__ uint32_t tup_pack(int slot, int pidx, int aloc, bool rev) {
-    return ((uint32_t)rev << 31) | ((uint32_t)slot << 16) | ((uint32_t)pidx << 8) | (uint32_t)aloc;
-}
+// match tuple in shared memory: rev (1) | local slot (15); the path is spath[slot], the alignment is the row
 __device__ __forceinline__ uint32_t tile_code(const TileS& T, int slot, bool rev) {
     return (uint32_t)(T.s0 + slot) | (rev ? SFB_MATCH_REV : 0u);
 }
 
-template <int K>
+// phase M: the matches of chunk alignment `i` into its row of the tuple store
+template <int KA>
+__device__ __forceinline__ void tile_match_aln(const TileS& T, const sfb_reads& r, int i, TileStats& st) {
+    const i64 a = T.a0c + i;
+    const i64 w0 = r.aln_walk_off[a];
+    const int L = (int)(r.aln_walk_off[a + 1] - w0);
+    uint16_t* row = T.tup + i * KA;
+    int n = 0;
+    tile_enum(T, r, w0, L, st, [&](int s, bool rev) {
+        if (n < KA) row[n] = (uint16_t)(s | ((int)rev << 15));
+        ++n;
+    });
+    T.cnt[i] = (uint8_t)(n > KA ? kOver : n);
+    st.tuples += n;
+}
+
+// The match tuples of a read group ("colored_match", json2csv.py:851-866) as stored by phase M: tuple i of mate k is
+// found by walking the mate's alignments (one or two almost always).
+template <int KA>
 struct TileView {
     const TileS* T;
+    int row[2];      // first alignment of the mate, chunk-relative
+    int na[2];
     int n[2];
-    __device__ __forceinline__ uint32_t word(int k, int i) const { return T->tup[(k * K + i) * kTT]; }
-    __device__ __forceinline__ int nt(int k) const { return n[k]; }
-    __device__ __forceinline__ int pid(int k, int i) const { return T->p0 + (int)((word(k, i) >> 8) & 0xffu); }
-    __device__ __forceinline__ uint32_t code(int k, int i) const {
-        const uint32_t w = word(k, i);
-        return tile_code(*T, (int)((w >> 16) & 0x7fffu), (w >> 31) != 0);
-    }
-    __device__ __forceinline__ int aloc(int k, int i) const { return (int)(word(k, i) & 0xffu); }
-};
-
-// tuples of both mates of an aligned pair into shared memory; false when a mate has more than K (or more than 255
-// alignments): the pair goes to the global-memory kernels
-template <int K>
-__device__ __forceinline__ bool tile_match_pair(const TileS& T, const sfb_reads& r, const Mate* mt, TileView<K>& v,
-                                                TileStats& st) {
-    bool fits = true;
-    for (int k = 0; k < 2; ++k) {
-        int n = 0;
-        if (mt[k].na > 255) fits = false;
-        for (int j = 0; j < mt[k].na && fits; ++j) {
-            const i64 w0 = r.aln_walk_off[mt[k].a0 + j];
-            const int L = (int)(r.aln_walk_off[mt[k].a0 + j + 1] - w0);
-            tile_enum(T, r, w0, L, st, [&](int s, bool rev) {
-                if (n < K) T.tup[(k * K + n) * kTT] = tup_pack(s, T.spath[s], j, rev);
-                ++n;
-            });
-            if (n > K) fits = false;
+    int c0[2];       // tuples of the mate's first alignment
+    // false when an alignment overflowed its row
+    __device__ __forceinline__ bool load(const TileS& T_, const Mate* mt) {
+        T = &T_;
+        bool fits = true;
+        for (int k = 0; k < 2; ++k) {
+            row[k] = (int)(mt[k].a0 - T_.a0c);
+            na[k] = mt[k].na;
+            int tot = 0;
+            for (int j = 0; j < na[k]; ++j) {
+                const int c = T_.cnt[row[k] + j];
+                fits &= c != kOver;
+                tot += c;
+            }
+            n[k] = tot;
+            c0[k] = na[k] ? T_.cnt[row[k]] : 0;
         }
-        v.n[k] = n;
-        st.tuples += n;
+        return fits;
     }
-    return fits;
-}
+    __device__ __forceinline__ uint32_t word(int k, int i, int& j) const {
+        j = 0;
+        if (i >= c0[k]) {
+            i -= c0[k];
+            j = 1;
+            for (int c; i >= (c = T->cnt[row[k] + j]); ++j) i -= c;
+        }
+        return T->tup[(row[k] + j) * KA + i];
+    }
+    __device__ __forceinline__ int nt(int k) const { return n[k]; }
+    __device__ __forceinline__ int pid(int k, int i) const { int j; return T->p0 + T->spath[word(k, i, j) & 0x7fffu]; }
+    __device__ __forceinline__ uint32_t code(int k, int i) const {
+        int j;
+        const uint32_t w = word(k, i, j);
+        return tile_code(*T, (int)(w & 0x7fffu), (w >> 15) != 0);
+    }
+    __device__ __forceinline__ int aloc(int k, int i) const { int j; word(k, i, j); return j; }
+};
 
 // ---- effects (the Ops of group_logic.cuh) on the resident tile ---------------------------------------------------
 struct TileOps {
     TileS* T;
     TileStats* st;
+    int app_cap;
     __device__ __forceinline__ void hist(const Dev& d, BlockCounters& sc, int pid, i64 a) {
         const int p = pid - T->p0;
         if (T->pnstr[p] != 1) return;                        // json2csv.py:333 / :1246
@@ -343,17 +426,15 @@ struct TileOps {
         }
         hist_out(d, sc, key, 1u);                            // table full: straight to the global histograms
     }
-    // fill_abund_dist (json2csv.py:321-339), node loop included
+    // fill_abund_dist (json2csv.py:321-339); the node loop (:329-330) goes to the list of phase S
     __device__ __forceinline__ void assign_unique(const Dev& d, BlockCounters& sc, i64 a, uint32_t code, int pid, int seq_len) {
         d.w.aln_assign[a] = (int32_t)code;
         const int p = pid - T->p0;
         atomicAdd(&T->plimb[7 * p], 1u);
         fx_smem_add(&T->plimb[7 * p + 1], fx_split((double)seq_len / (double)T->pseq[p]));
         hist(d, sc, pid, a);
-        const i64 w0 = d.r.aln_walk_off[a];
-        const int L = (int)(d.r.aln_walk_off[a + 1] - w0);
-        tile_add_records(*T, d.r, w0, L, (int)(code & SFB_SLOT_MASK) - T->s0, true, 1.0);
-        st->rec += L;
+        const int q = atomicAdd(&T->misc[1], 1);             // an alignment is assigned at most once: q < kAC
+        T->lst[q] = ((uint32_t)(a - T->a0c) << 16) | (uint32_t)((int)(code & SFB_SLOT_MASK) - T->s0);
     }
     // cluster of the first path through the walk's first node (json2csv.py:875,901,1036); -1 = None, -2 = no path
     __device__ __forceinline__ int first_cluster(const Dev& d, i64 a) {
@@ -373,13 +454,285 @@ struct TileOps {
         T->plimb[7 * p] = 1u;                                // "touched" flag
         fx_smem_add(&T->plimb[7 * p + 1], fx_split(weight));
         fx_smem_add(&T->plimb[7 * p + 4], fx_split((ratio * (double)seq_len / (double)T->pseq[p]) * (double)times));
-        const i64 w0 = d.r.aln_walk_off[a];
-        const int L = (int)(d.r.aln_walk_off[a + 1] - w0);
-        tile_add_records(*T, d.r, w0, L, (int)(code & SFB_SLOT_MASK) - T->s0, false, weight);
-        st->rec += L;
         st->app += 1;
+        const int slot = (int)(code & SFB_SLOT_MASK) - T->s0;
+        const int q = atomicAdd(&T->misc[1], 1);
+        if (q < app_cap) {                                   // the node loop goes to the list of phase S
+            T->appk[q] = ((uint32_t)(a - T->a0c) << 16) | (uint32_t)slot;
+            T->appw[q] = weight;
+            return;
+        }
+        const i64 w0 = d.r.aln_walk_off[a];                  // list full (many candidate paths per read): here and now
+        const int L = (int)(d.r.aln_walk_off[a + 1] - w0);
+        tile_add_records(*T, d.r, w0, L, slot, false, weight);
+        st->rec += L;
     }
 };
+
+// =================================================================================================================
+// Simple tiles (at most 64 paths, no node twice in a path): path sets as 64-bit masks
+// =================================================================================================================
+// A walk matches path p (at the position of its first node) iff p takes every step of the walk; the reversed walk
+// matches iff p takes every step backwards.  So the matches of an alignment are two path sets, the AND over the
+// walk's steps of the step index, and the set logic of the decision tree becomes AND / OR / popcount on them.  The
+// tuple order of the reference (json2csv.py:851-866: alignment by alignment, forward matches by ascending path, then
+// reverse) only matters for picking "the first" tuple; sums are exact integers here, so their order is free.
+__device__ __forceinline__ u64 tile_step(const TileS& T, unsigned n, unsigned succ) {
+    for (int e = T.eoff[n]; e < (int)T.eoff[n + 1]; ++e)
+        if (T.esucc[e] == succ) return T.emask[e];
+    return 0ull;
+}
+// phase M: forward / reverse path sets of chunk alignment `i`
+__device__ __forceinline__ void mask_match_aln(const TileS& T, const sfb_reads& r, int i, TileStats& st) {
+    const i64 a = T.a0c + i;
+    const i64 w0 = r.aln_walk_off[a];
+    const int L = (int)(r.aln_walk_off[a + 1] - w0);
+    u64 f = 0, rv = 0;
+    if (L > 0) {
+        unsigned prev = tile_local(T, r.walk_node[w0]);
+        if (L == 1) {
+            if (prev != kNoNode) f = T.nmask[prev];
+        } else if (prev != kNoNode) {
+            f = rv = ~0ull;
+            for (int k = 1; k < L; ++k) {
+                const unsigned n = tile_local(T, r.walk_node[w0 + k]);
+                if (n == kNoNode) { f = rv = 0; break; }
+                if (f) f &= tile_step(T, prev, n);
+                if (rv) rv &= tile_step(T, n, prev);
+                st.cmp += 1;
+                if (!(f | rv)) break;
+                prev = n;
+            }
+        }
+    }
+    T.amask[2 * i] = f;
+    T.amask[2 * i + 1] = rv;
+    const int n = __popcll(f) + __popcll(rv);
+    st.cand += n;
+    st.tuples += n;
+}
+// slot of node `n` (local) on path `p` (local) of a simple tile
+__device__ __forceinline__ int tile_slot_of(const TileS& T, unsigned n, int p) {
+    for (int c = T.occ_off[n]; c < (int)T.occ_off[n + 1]; ++c)
+        if (T.spath[T.occ[c]] == p) return T.occ[c];
+    return 0;
+}
+// match code of the tuple (alignment a, path p, orientation): the walk's first node for a forward match, its last node
+// for a reverse one (json2csv.py:862 matches the reversed walk)
+__device__ __forceinline__ uint32_t mask_code(const TileS& T, const sfb_reads& r, i64 a, int p, bool rev) {
+    const i64 w = rev ? r.aln_walk_off[a + 1] - 1 : r.aln_walk_off[a];
+    return tile_code(T, tile_slot_of(T, tile_local(T, r.walk_node[w]), p), rev);
+}
+
+struct MaskMate {
+    int row, na, nt;     // first alignment (chunk-relative), alignments, tuples
+    u64 S, dup;          // paths matched, paths matched more than once
+    __device__ __forceinline__ void load(const TileS& T, const Mate& m) {
+        row = (int)(m.a0 - T.a0c);
+        na = m.na;
+        S = dup = 0;
+        nt = 0;
+        for (int j = 0; j < 2 * na; ++j) {
+            const u64 x = T.amask[2 * row + j];
+            dup |= S & x;
+            S |= x;
+            nt += __popcll(x);
+        }
+    }
+    __device__ __forceinline__ int count(const TileS& T, int p) const {      // list_path_id.count(pid)
+        int c = 0;
+        for (int j = 0; j < 2 * na; ++j) c += (int)((T.amask[2 * row + j] >> p) & 1ull);
+        return c;
+    }
+    // the first tuple carrying path p: alignment j inside the mate, orientation
+    __device__ __forceinline__ void find(const TileS& T, int p, int& j, bool& rev) const {
+        for (int q = 0; q < 2 * na; ++q)
+            if ((T.amask[2 * row + q] >> p) & 1ull) { j = q >> 1; rev = q & 1; return; }
+        j = 0;
+        rev = false;
+    }
+};
+
+// strains common to both mates' candidate paths, one word (json2csv.py:964-972)
+__device__ __forceinline__ u64 mask_common(const sfb_graph& g, const TileS& T, const MaskMate* mm, int word) {
+    u64 u[2] = {0, 0};
+    for (int k = 0; k < 2; ++k)
+        for (u64 rest = mm[k].S; rest; rest &= rest - 1)
+            u[k] |= g.path_smask[(size_t)(T.p0 + __ffsll((long long)rest) - 1) * g.mask_words + word];
+    return u[0] & u[1];
+}
+// in how many common strains path p occurs (Q4: a tuple counts once per common strain its path carries)
+__device__ __forceinline__ int mask_times(const sfb_graph& g, const TileS& T, const MaskMate* mm, u64 common0, int p) {
+    if (g.mask_words == 1) return __popcll(g.path_smask[T.p0 + p] & common0);
+    int t = 0;
+    for (int word = 0; word < (int)g.mask_words; ++word)
+        t += __popcll(g.path_smask[(size_t)(T.p0 + p) * g.mask_words + word] & mask_common(g, T, mm, word));
+    return t;
+}
+struct MaskCut {
+    bool any;
+    int nn[2];
+    u64 common0;
+};
+__device__ __forceinline__ MaskCut mask_cut(const sfb_graph& g, const TileS& T, const MaskMate* mm) {
+    MaskCut c;
+    c.any = false;
+    c.nn[0] = c.nn[1] = 0;
+    c.common0 = 0;
+    for (int word = 0; word < (int)g.mask_words; ++word) {
+        const u64 common = mask_common(g, T, mm, word);
+        if (word == 0) c.common0 = common;
+        if (!common) continue;
+        c.any = true;
+        for (int k = 0; k < 2; ++k)
+            for (u64 rest = mm[k].S; rest; rest &= rest - 1) {
+                const int p = __ffsll((long long)rest) - 1;
+                c.nn[k] += mm[k].count(T, p) * __popcll(g.path_smask[(size_t)(T.p0 + p) * g.mask_words + word] & common);
+            }
+    }
+    return c;
+}
+
+// both mates have colored paths (json2csv.py:918-1000); same decisions as classify_pair (group_logic.cuh)
+__device__ __forceinline__ void mask_classify_pair(TileS& T, const Dev& d, TileOps& ops, BlockCounters& sc, const Mate* mt,
+                                                   const MaskMate* mm, int* code, bool& defer) {
+    const u64 inter = mm[0].S & mm[1].S;
+    const int n_inter = __popcll(inter);
+    if (n_inter > 1) {
+        SFB_COUNT(sc, SFB_C_SECOND_PASS, 2);
+        defer = true;
+        code[0] = code[1] = SFB_DEFER;
+        return;
+    }
+    if (n_inter == 1) {
+        const int p = __ffsll((long long)inter) - 1;
+        for (int k = 0; k < 2; ++k) {
+            if ((mm[k].dup >> p) & 1ull) {
+                SFB_COUNT(sc, SFB_C_MULTI_ALIGN, 1);
+                code[k] = SFB_MULTI_ALIGN;
+                continue;
+            }
+            int j;
+            bool rev;
+            mm[k].find(T, p, j, rev);
+            const i64 a = mt[k].a0 + j;
+            ops.assign_unique(d, sc, a, mask_code(T, d.r, a, p, rev), T.p0 + p, mt[k].seq_len);
+            SFB_COUNT(sc, SFB_C_ASSIGNED_U, 1);
+            SFB_COUNT(sc, SFB_C_SAME_CP, 1);
+            if (mm[k].nt > 1) SFB_COUNT(sc, SFB_C_AMBIG_CP_RESOLVED, 1);
+            code[k] = SFB_ASSIGN_SAME;
+        }
+        return;
+    }
+    // no common path: intersect strains (json2csv.py:961-1000)
+    const MaskCut cut = mask_cut(d.g, T, mm);
+    if (!cut.any) {
+        SFB_COUNT(sc, SFB_C_INCONSIST, 2);
+        code[0] = code[1] = SFB_INCONSIST;
+        return;
+    }
+    for (int k = 0; k < 2; ++k) {
+        const int nn = cut.nn[k];
+        if (nn < mm[k].nt) SFB_COUNT(sc, nn == 1 ? SFB_C_AMBIG_RESOLVED : SFB_C_AMBIG_REDUCED, 1);
+        if (nn > 1) {
+            SFB_COUNT(sc, SFB_C_SECOND_PASS, 1);
+            defer = true;
+            code[k] = SFB_DEFER;
+            continue;
+        }
+        for (u64 rest = mm[k].S; rest; rest &= rest - 1) {       // exactly one tuple survives, once
+            const int p = __ffsll((long long)rest) - 1;
+            if (mask_times(d.g, T, mm, cut.common0, p) == 0) continue;
+            if (mm[k].count(T, p) == 1) {
+                int j;
+                bool rev;
+                mm[k].find(T, p, j, rev);
+                const i64 a = mt[k].a0 + j;
+                ops.assign_unique(d, sc, a, mask_code(T, d.r, a, p, rev), T.p0 + p, mt[k].seq_len);
+                SFB_COUNT(sc, SFB_C_ASSIGNED_U, 1);
+                SFB_COUNT(sc, SFB_C_DIFF_CP, 1);
+                code[k] = SFB_ASSIGN_DIFF;
+            } else {
+                SFB_COUNT(sc, SFB_C_MULTI_ALIGN, 1);
+                code[k] = SFB_MULTI_ALIGN;
+            }
+            break;
+        }
+    }
+}
+
+// every tuple of mate k whose path is in `sel`: apply(share(p), times(p))
+template <class W>
+__device__ __forceinline__ void mask_apply(TileS& T, const Dev& d, TileOps& ops, const Mate& m, const MaskMate& mk, u64 sel,
+                                           W&& weight) {
+    for (int q = 0; q < 2 * mk.na; ++q)
+        for (u64 rest = T.amask[2 * mk.row + q] & sel; rest; rest &= rest - 1) {
+            const int p = __ffsll((long long)rest) - 1;
+            const i64 a = m.a0 + (q >> 1);
+            double ratio;
+            int times;
+            weight(p, ratio, times);
+            ops.apply(d, a, mask_code(T, d.r, a, p, (q & 1) != 0), T.p0 + p, m.seq_len, ratio, times);
+        }
+}
+
+// pass 2 for an aligned pair whose mates both have colored paths (json2csv.py:1123-1217); same decisions as
+// p2_decide_pair + p2_emit (group_logic.cuh)
+__device__ __forceinline__ void mask_pass2_pair(TileS& T, const Dev& d, TileOps& ops, BlockCounters& sc, const Mate* mt,
+                                                const MaskMate* mm, int* code) {
+    const u64 inter = mm[0].S & mm[1].S;
+    const int n_inter = __popcll(inter);
+    if (n_inter >= 1) {
+        long long total = 0;
+        for (u64 rest = inter; rest; rest &= rest - 1) total += T.pU[__ffsll((long long)rest) - 1];
+        for (int k = 0; k < 2; ++k) {
+            if (mm[k].dup & inter) {             // a common path with several tuples in this mate
+                SFB_COUNT(sc, SFB_C_MULTI_ALIGN, 1);
+                code[k] = SFB_P2_MULTI_ALIGN;
+                continue;
+            }
+            SFB_COUNT(sc, SFB_C_ASSIGNED_M, 1);
+            code[k] = SFB_P2_ASSIGNED;
+            mask_apply(T, d, ops, mt[k], mm[k], inter, [&](int p, double& ratio, int& times) {
+                ratio = ratio_of(T.pU[p], total, n_inter);
+                times = 1;
+            });
+        }
+        return;
+    }
+    const MaskCut cut = mask_cut(d.g, T, mm);
+    if (!cut.any) {
+        SFB_COUNT(sc, SFB_C_INCONSIST_M, (mm[0].nt == 1 || mm[1].nt == 1) ? 1 : 2);
+        code[0] = code[1] = SFB_P2_INCONSIST;
+        return;
+    }
+    for (int k = 0; k < 2; ++k) {
+        const int nn = cut.nn[k];
+        if (nn <= 1) continue;                   // handled in pass 1 (json2csv.py:1185)
+        bool simple = true;
+        long long tot = 0;
+        u64 sel = 0;
+        for (u64 rest = mm[k].S; rest && simple; rest &= rest - 1) {
+            const int p = __ffsll((long long)rest) - 1;
+            const int times = mask_times(d.g, T, mm, cut.common0, p);
+            if (times == 0) continue;
+            if (mm[k].count(T, p) != 1) { simple = false; break; }
+            tot += T.pU[p] * times;
+            sel |= 1ull << p;
+        }
+        if (!simple) {
+            SFB_COUNT(sc, SFB_C_MULTI_ALIGN, 1);
+            code[k] = SFB_P2_MULTI_ALIGN;
+            continue;
+        }
+        SFB_COUNT(sc, SFB_C_ASSIGNED_M, 1);
+        code[k] = SFB_P2_ASSIGNED;
+        mask_apply(T, d, ops, mt[k], mm[k], sel, [&](int p, double& ratio, int& times) {
+            ratio = ratio_of(T.pU[p], tot, nn);
+            times = mask_times(d.g, T, mm, cut.common0, p);
+        });
+    }
+}
 
 // An aligned pair that does not fit the tuple buffers: its match lists in the format of sfb_match, the group on the
 // list of the generic classify kernel (which also takes care of its node loops and of its deferral).
@@ -416,8 +769,8 @@ __device__ __noinline__ void tile_export(const TileS& T, const Dev& d, BlockCoun
     d.w.slow[atomicAdd(d.w.cursor + 3, 1ull)] = (int32_t)g;
 }
 
-// ---- pass 1, one read group (json2csv.py:828-1053) --------------------------------------------------------------
-template <int K>
+// ---- phase C of pass 1, one read group (json2csv.py:828-1053) ----------------------------------------------------
+template <int KA>
 __device__ __forceinline__ void tile_group1(TileS& T, const Dev& d, BlockCounters& sc, i64 g, TileStats& st) {
     const int nm = d.r.grp_nmates[g];
     Mate mt[2];
@@ -429,8 +782,7 @@ __device__ __forceinline__ void tile_group1(TileS& T, const Dev& d, BlockCounter
     bool defer = false;
     SFB_COUNT(sc, SFB_C_NB_READS, nm);
     int single = nm == 1 ? 0 : -1;           // mate handled single-end style, -1 = none
-    int known = -1;                          // its number of matches when already counted
-    TileOps ops{&T, &st};
+    TileOps ops{&T, &st, 0};
     if (nm == 2) {
         SFB_COUNT(sc, SFB_C_PAIRS, 1);
         if (mt[0].na == 0 && mt[1].na == 0) {
@@ -443,19 +795,29 @@ __device__ __forceinline__ void tile_group1(TileS& T, const Dev& d, BlockCounter
             code[gone] = SFB_FILTERED;
             single = 1 - gone;
         } else {
-            TileView<K> v;
-            v.T = &T;
-            if (!tile_match_pair<K>(T, d.r, mt, v, st)) {
-                tile_export(T, d, sc, g, mt, st);
-                return;
+            TileView<KA> v;
+            MaskMate mm[2];
+            int nt[2];
+            if (T.simple) {
+                mm[0].load(T, mt[0]);
+                mm[1].load(T, mt[1]);
+                nt[0] = mm[0].nt;
+                nt[1] = mm[1].nt;
+            } else {
+                if (!v.load(T, mt) || mt[0].na > 255 || mt[1].na > 255) {
+                    tile_export(T, d, sc, g, mt, st);
+                    return;
+                }
+                nt[0] = v.n[0];
+                nt[1] = v.n[1];
             }
-            if (v.n[0] == 0 && v.n[1] == 0) {
+            if (nt[0] == 0 && nt[1] == 0) {
                 classify_both_unassigned(d, ops, sc, mt, code);
-            } else if (v.n[0] == 0 || v.n[1] == 0) {
+            } else if (nt[0] == 0 || nt[1] == 0) {
                 // one mate without colored path (json2csv.py:895-916)
                 SFB_COUNT(sc, SFB_C_UNASSIGNED, 1);
                 SFB_COUNT(sc, SFB_C_ONE_NOCP, 1);
-                const int gone = v.n[0] == 0 ? 0 : 1;
+                const int gone = nt[0] == 0 ? 0 : 1;
                 code[gone] = SFB_UNASSIGNED;
                 bool bad = false;
                 for (int j = 0; j < mt[gone].na; ++j) bad |= ops.first_cluster(d, mt[gone].a0 + j) == -2;
@@ -466,7 +828,8 @@ __device__ __forceinline__ void tile_group1(TileS& T, const Dev& d, BlockCounter
                     code[gone] = SFB_UNASSIGNED_BOOK;
                 }
                 single = 1 - gone;
-                known = v.n[single];
+            } else if (T.simple) {
+                mask_classify_pair(T, d, ops, sc, mt, mm, code, defer);
             } else {
                 classify_pair(d, ops, sc, v, mt, code, defer);
             }
@@ -484,13 +847,9 @@ __device__ __forceinline__ void tile_group1(TileS& T, const Dev& d, BlockCounter
             defer = true;
             code[single] = SFB_DEFER;
         } else {
-            int n = known;
-            if (n < 0) {
-                n = 0;
-                const i64 w0 = d.r.aln_walk_off[m.a0];
-                tile_enum(T, d.r, w0, (int)(d.r.aln_walk_off[m.a0 + 1] - w0), st, [&](int, bool) { ++n; });
-                st.tuples += n;
-            }
+            const int row = (int)(m.a0 - T.a0c);
+            const int n = T.simple ? __popcll(T.amask[2 * row]) + __popcll(T.amask[2 * row + 1])
+                                   : T.cnt[row];                 // kOver: more than KA, in any case more than one
             if (n > 1) {
                 SFB_COUNT(sc, SFB_C_SECOND_PASS, 1);
                 defer = true;
@@ -511,30 +870,37 @@ __device__ __forceinline__ void tile_group1(TileS& T, const Dev& d, BlockCounter
     st.deferred += defer;
 }
 
-// ---- pass 2, one deferred read group (json2csv.py:1085-1274) ----------------------------------------------------
-template <int K>
+// ---- phase C of pass 2, one deferred read group (json2csv.py:1085-1274) -----------------------------------------
+template <int KA>
 __device__ __forceinline__ void tile_group2(TileS& T, const Dev& d, BlockCounters& sc, i64 g, TileStats& st) {
-    const int c1 = d.w.grp_code[g];
-    if ((c1 & 0xf) != SFB_DEFER && (c1 >> 4) != SFB_DEFER) return;
     const int nm = d.r.grp_nmates[g];
     Mate mt[2];
     mate_load(d.r, g, 0, mt[0]);
     mate_load(d.r, g, 1, mt[1]);
     int code[2] = {SFB_P2_NONE, SFB_P2_NONE};
     int single = nm == 1 ? 0 : -1;
-    TileOps ops{&T, &st};
+    TileOps ops{&T, &st, tile_app_cap(KA)};
     if (nm == 2) {
         if (mt[0].na == 0 || mt[1].na == 0) {
             single = mt[0].na == 0 ? 1 : 0;                                  // json2csv.py:1088-1093
         } else {
-            TileView<K> v;
-            v.T = &T;
-            const int seen = st.tuples;
-            const bool fits = tile_match_pair<K>(T, d.r, mt, v, st);
-            st.tuples = seen;                                                // counted in pass 1
-            if (!fits) return;                                               // exported in pass 1: sfb_pass2 has it
-            if (v.n[0] == 0 || v.n[1] == 0) {
-                single = v.n[0] == 0 ? 1 : 0;                                // :1117-1122
+            TileView<KA> v;
+            MaskMate mm[2];
+            int nt[2];
+            if (T.simple) {
+                mm[0].load(T, mt[0]);
+                mm[1].load(T, mt[1]);
+                nt[0] = mm[0].nt;
+                nt[1] = mm[1].nt;
+            } else {
+                if (!v.load(T, mt) || mt[0].na > 255 || mt[1].na > 255) return;  // handed over in pass 1: sfb_pass2 has it
+                nt[0] = v.n[0];
+                nt[1] = v.n[1];
+            }
+            if (nt[0] == 0 || nt[1] == 0) {
+                single = nt[0] == 0 ? 1 : 0;                                 // :1117-1122
+            } else if (T.simple) {
+                mask_pass2_pair(T, d, ops, sc, mt, mm, code);
             } else {
                 Plan pl;
                 pl.mode[0] = pl.mode[1] = kNone;
@@ -545,56 +911,156 @@ __device__ __forceinline__ void tile_group2(TileS& T, const Dev& d, BlockCounter
         }
     }
     if (single >= 0) {
-        // every alignment separately (json2csv.py:1230-1268): the matches are enumerated twice instead of stored
+        // every alignment separately (json2csv.py:1230-1268)
         const Mate& m = mt[single];
         int n_all = 0;
         for (int j = 0; j < m.na; ++j) {
             const i64 a = m.a0 + j;
-            const i64 w0 = d.r.aln_walk_off[a];
-            const int L = (int)(d.r.aln_walk_off[a + 1] - w0);
-            long long total = 0;
-            int cnt = 0;
-            tile_enum(T, d.r, w0, L, st, [&](int s, bool) {
-                const int p = T.spath[s];
-                total += T.pU[p];
-                ++cnt;
-                ops.hist(d, sc, T.p0 + p, a);                                // :1246-1252
-            });
+            const int row = (int)(a - T.a0c);
+            if (T.simple) {
+                const u64 f = T.amask[2 * row], rv = T.amask[2 * row + 1];
+                const int cnt = __popcll(f) + __popcll(rv);
+                if (cnt == 0) continue;
+                long long total = 0;
+                for (int q = 0; q < 2; ++q)
+                    for (u64 rest = q ? rv : f; rest; rest &= rest - 1) {
+                        const int p = __ffsll((long long)rest) - 1;
+                        total += T.pU[p];
+                        ops.hist(d, sc, T.p0 + p, a);                        // :1246-1252
+                    }
+                for (int q = 0; q < 2; ++q)
+                    for (u64 rest = q ? rv : f; rest; rest &= rest - 1) {
+                        const int p = __ffsll((long long)rest) - 1;
+                        ops.apply(d, a, mask_code(T, d.r, a, p, q != 0), T.p0 + p, m.seq_len, ratio_of(T.pU[p], total, cnt), 1);
+                    }
+                n_all += cnt;
+                continue;
+            }
+            const int cnt = T.cnt[row];
+            if (cnt == kOver) {
+                // more matches than a row holds: enumerated twice from the index instead of stored
+                const i64 w0 = d.r.aln_walk_off[a];
+                const int L = (int)(d.r.aln_walk_off[a + 1] - w0);
+                long long total = 0;
+                int c2 = 0;
+                tile_enum(T, d.r, w0, L, st, [&](int s, bool) {
+                    const int p = T.spath[s];
+                    total += T.pU[p];
+                    ++c2;
+                    ops.hist(d, sc, T.p0 + p, a);                            // :1246-1252
+                });
+                tile_enum(T, d.r, w0, L, st, [&](int s, bool rev) {
+                    const int p = T.spath[s];
+                    ops.apply(d, a, tile_code(T, s, rev), T.p0 + p, m.seq_len, ratio_of(T.pU[p], total, c2), 1);
+                });
+                n_all += c2;
+                continue;
+            }
             if (cnt == 0) continue;
+            const uint16_t* tp = T.tup + row * KA;
+            long long total = 0;
+            for (int i = 0; i < cnt; ++i) {
+                const int p = T.spath[tp[i] & 0x7fffu];
+                total += T.pU[p];
+                ops.hist(d, sc, T.p0 + p, a);                                // :1246-1252
+            }
+            for (int i = 0; i < cnt; ++i) {
+                const int s = tp[i] & 0x7fffu, p = T.spath[s];
+                ops.apply(d, a, tile_code(T, s, (tp[i] >> 15) != 0), T.p0 + p, m.seq_len, ratio_of(T.pU[p], total, cnt), 1);
+            }
             n_all += cnt;
-            tile_enum(T, d.r, w0, L, st, [&](int s, bool rev) {
-                const int p = T.spath[s];
-                ops.apply(d, a, tile_code(T, s, rev), T.p0 + p, m.seq_len, ratio_of(T.pU[p], total, cnt), 1);
-            });
         }
-        if (m.na > 1) st.tuples += n_all;                     // pass 1 deferred this mate without matching it
         code[single] = p2_single_outcome(sc, n_all);
     }
     d.w.grp_code2[g] = (uint8_t)(code[0] | (code[1] << 4));
 }
 
 // ---- kernels ----------------------------------------------------------------------------------------------------
-template <int PASS, int K>
-__global__ void __launch_bounds__(kTT) k_tile_pass(Dev d, sfb_tiles t, const long long* __restrict__ U) {
+#ifndef SFB_TILE_MINBLK
+#define SFB_TILE_MINBLK 3
+#endif
+template <int PASS, int KA>
+__global__ void __launch_bounds__(kTT, SFB_TILE_MINBLK) k_tile_pass(const __grid_constant__ Dev d, const __grid_constant__ sfb_tiles t,
+                                                                        const long long* __restrict__ U) {
     extern __shared__ __align__(16) unsigned char smem[];
-    TileS T = tile_carve(smem, t);
+    TileS T = tile_carve(PASS, smem, t);
     BlockCounters& sc = *T.sc;
     block_counters_zero(sc);
     TileStats st{0, 0, 0, 0, 0, 0};
     const int4* items = reinterpret_cast<const int4*>(t.items);
+    const int tid = threadIdx.x;
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) T.misc[0] = (int)atomicAdd(d.w.cursor + (PASS == 1 ? 5 : 6), 1ull);
+        if (tid == 0) T.misc[0] = (int)atomicAdd(d.w.cursor + (PASS == 1 ? 5 : 6), 1ull);
         __syncthreads();
         const int item = T.misc[0];
         if (item >= (int)t.n_items) break;
         const int4 it = items[item];
         tile_stage<PASS>(T, d, t, it.x, U);
-        for (i64 g = (i64)it.y + threadIdx.x; g < (i64)it.z; g += kTT) {
-            if (PASS == 1) tile_group1<K>(T, d, sc, g, st);
-            else tile_group2<K>(T, d, sc, g, st);
+        for (i64 g0 = it.y; g0 < (i64)it.z;) {
+            // a chunk: up to kTT read groups whose alignments fit the tuple store (block-uniform arithmetic)
+            i64 g1 = min(g0 + kTT, (i64)it.z);
+            T.a0c = d.r.grp_aln_off[2 * g0];
+            while (g1 - g0 > 1 && d.r.grp_aln_off[2 * g1] - T.a0c > kAC) g1 = g0 + (g1 - g0) / 2;
+            const int nA = (int)(d.r.grp_aln_off[2 * g1] - T.a0c);
+            if (nA > kAC) {            // one group with more alignments than a chunk holds: not in tile order as staged
+                if (tid == 0) SFB_COUNT(sc, SFB_C_MATCH_OVERFLOW, 1);      // (sfb_tile_permute keeps such groups out)
+                g0 = g1;
+                continue;
+            }
+            if (tid < 3) T.misc[1 + tid] = 0;
+            __syncthreads();
+            if (PASS == 1) {
+                if (T.simple) for (int i = tid; i < nA; i += kTT) mask_match_aln(T, d.r, i, st);
+                else for (int i = tid; i < nA; i += kTT) tile_match_aln<KA>(T, d.r, i, st);
+                __syncthreads();
+                if (g0 + tid < g1) tile_group1<KA>(T, d, sc, g0 + tid, st);
+                __syncthreads();
+                const int n_asg = T.misc[1];
+                for (int q = tid; q < n_asg; q += kTT) {
+                    const uint32_t e = T.lst[q];
+                    const i64 a = T.a0c + (e >> 16);
+                    const i64 w0 = d.r.aln_walk_off[a];
+                    const int L = (int)(d.r.aln_walk_off[a + 1] - w0);
+                    tile_add_records(T, d.r, w0, L, (int)(e & 0xffffu), true, 1.0);
+                    st.rec += L;
+                }
+            } else {
+                // D: the deferred groups of the chunk and their alignments
+                if (g0 + tid < g1) {
+                    const i64 g = g0 + tid;
+                    const int c1 = d.w.grp_code[g];
+                    if ((c1 & 0xf) == SFB_DEFER || (c1 >> 4) == SFB_DEFER) {
+                        T.glist[atomicAdd(&T.misc[3], 1)] = (uint16_t)tid;
+                        const int r0 = (int)(d.r.grp_aln_off[2 * g] - T.a0c), r1 = (int)(d.r.grp_aln_off[2 * g + 2] - T.a0c);
+                        const int q = atomicAdd(&T.misc[2], r1 - r0);
+                        for (int j = r0; j < r1; ++j) T.alist[q + j - r0] = (uint16_t)j;
+                    }
+                }
+                __syncthreads();
+                const int n_aln = T.misc[2], n_grp = T.misc[3];
+                {
+                    const int seen = st.tuples;                       // counted in pass 1
+                    if (T.simple) for (int q = tid; q < n_aln; q += kTT) mask_match_aln(T, d.r, T.alist[q], st);
+                    else for (int q = tid; q < n_aln; q += kTT) tile_match_aln<KA>(T, d.r, T.alist[q], st);
+                    st.tuples = seen;
+                }
+                __syncthreads();
+                if (tid < n_grp) tile_group2<KA>(T, d, sc, g0 + T.glist[tid], st);
+                __syncthreads();
+                const int n_app = min(T.misc[1], tile_app_cap(KA));
+                for (int q = tid; q < n_app; q += kTT) {
+                    const uint32_t e = T.appk[q];
+                    const i64 a = T.a0c + (e >> 16);
+                    const i64 w0 = d.r.aln_walk_off[a];
+                    const int L = (int)(d.r.aln_walk_off[a + 1] - w0);
+                    tile_add_records(T, d.r, w0, L, (int)(e & 0xffffu), false, T.appw[q]);
+                    st.rec += L;
+                }
+            }
+            __syncthreads();
+            g0 = g1;
         }
-        __syncthreads();
         tile_flush<PASS>(T, d, sc);
     }
     const int c0 = warp_sum(st.cand), c1 = warp_sum(st.cmp), c2 = warp_sum(st.tuples), c3 = warp_sum(st.rec),
@@ -609,7 +1075,6 @@ __global__ void __launch_bounds__(kTT) k_tile_pass(Dev d, sfb_tiles t, const lon
         } else {
             SFB_COUNT(sc, SFB_C_ST_P2_RECORDS, c3);
             SFB_COUNT(sc, SFB_C_ST_P2_APPLIED, c4);
-            SFB_COUNT(sc, SFB_C_ST_TUPLES, c2);
         }
     }
     __syncthreads();
@@ -621,20 +1086,25 @@ static int tile_check(const sfb_tiles* t) {
     SFB_REQUIRE(t->n_tiles >= 0 && t->n_items >= 0 && t->n_items < 0x7fffffffLL, "bad tile / item count");
     SFB_REQUIRE(t->tuple_cap == 8 || t->tuple_cap == 16 || t->tuple_cap == 32, "tuple_cap must be 8, 16 or 32");
     SFB_REQUIRE(t->max_slots >= 0 && t->max_slots <= 32767 && t->max_paths >= 0 && t->max_paths <= 255 &&
-                    t->max_nodes >= 0 && t->max_nodes <= 65520, "tile exceeds the limits (32767 slots, 255 paths, 65520 nodes)");
+                    t->max_nodes >= 0 && t->max_nodes <= 65520 && t->max_edges >= 0 && t->max_edges <= 65535,
+                "tile exceeds the limits (32767 slots, 255 paths, 65520 nodes, 65535 steps)");
     SFB_REQUIRE(t->n_items == 0 || (t->tile_desc && t->items && t->n_tiles > 0), "null tile array");
+    SFB_REQUIRE(t->n_items == 0 || t->max_edges == 0 || (t->edge_off && t->edge_succ && t->edge_mask && t->node_mask),
+                "null step index");
     return SFB_OK;
 }
 
 i64 tile_smem_bytes(const sfb_tiles* t) {
     if (tile_check(t) != SFB_OK) return SFB_E_ARG;
-    return (i64)tile_layout((int)t->max_slots, (int)t->max_nodes, (int)t->max_paths, (int)t->tuple_cap).total;
+    const i64 a = tile_layout(1, (int)t->max_slots, (int)t->max_nodes, (int)t->max_paths, (int)t->max_edges, (int)t->tuple_cap).total;
+    const i64 b = tile_layout(2, (int)t->max_slots, (int)t->max_nodes, (int)t->max_paths, (int)t->max_edges, (int)t->tuple_cap).total;
+    return a > b ? a : b;
 }
 
-template <int PASS, int K>
+template <int PASS, int KA>
 static int launch_tile_k(const Dev& d, const sfb_tiles* t, const long long* U, cudaStream_t st) {
-    const size_t smem = tile_layout((int)t->max_slots, (int)t->max_nodes, (int)t->max_paths, K).total;
-    auto kern = k_tile_pass<PASS, K>;
+    const size_t smem = tile_layout(PASS, (int)t->max_slots, (int)t->max_nodes, (int)t->max_paths, (int)t->max_edges, KA).total;
+    auto kern = k_tile_pass<PASS, KA>;
     if (smem > 227 * 1024) return fail(SFB_E_ARG, "tile kernels: %zu bytes of shared memory needed, 232448 available", smem);
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return check_launch("k_tile_pass (shared memory size)");

@@ -88,8 +88,11 @@ class DeviceGraph:
         if self.tiling is not None:
             tl = self.tiling
             self.tile_desc = _to_dev(tl.tile_desc.reshape(-1), d)
+            self.tile_edges = dict(edge_off=_to_dev(tl.edge_off, d), edge_succ=_to_dev(tl.edge_succ, d),
+                                   edge_mask=_to_dev(tl.edge_mask.view(np.int64), d),
+                                   node_mask=_to_dev(tl.node_mask.view(np.int64), d))
             probe = _lib.SfbTiles(n_tiles=tl.n_tiles, n_items=0, max_slots=tl.max_slots, max_nodes=tl.max_nodes,
-                                  max_paths=tl.max_paths, tuple_cap=tl.tuple_cap, tile_desc=0, items=0)
+                                  max_paths=tl.max_paths, max_edges=tl.max_edges, tuple_cap=tl.tuple_cap)
             need = int(_lib.load().sfb_tile_smem_bytes(C.byref(probe)))
             if need < 0 or need > 227 * 1024:
                 self.tiling = None
@@ -229,9 +232,10 @@ class DeviceReads:
     """Device copy of a HostReads arena (one DMA), expanded on the device when it is in the transfer layout.
     ``arena`` / ``wide``: existing device buffers to reuse."""
 
-    def __init__(self, host: HostReads, device, arena=None, wide=None, node_len=None, expand=True, tile_desc=None):
+    def __init__(self, host: HostReads, device, arena=None, wide=None, node_len=None, expand=True, tile_desc=None,
+                 tile_edges=None):
         self.host = host
-        self.tile_desc = tile_desc
+        self.tile_desc, self.tile_edges = tile_desc, tile_edges
         if arena is None or arena.numel() < host.size:
             arena = torch.empty(host.size, dtype=torch.uint8, device=device)
         self.arena = arena
@@ -254,8 +258,9 @@ class DeviceReads:
         if host.items is not None and len(host.items) and self.tile_desc is not None:
             tl = host.tiling
             self.tiles_c = _lib.SfbTiles(n_tiles=tl.n_tiles, n_items=len(host.items), max_slots=tl.max_slots,
-                                         max_nodes=tl.max_nodes, max_paths=tl.max_paths, tuple_cap=tl.tuple_cap,
-                                         tile_desc=self.tile_desc.data_ptr(), items=items_ptr)
+                                         max_nodes=tl.max_nodes, max_paths=tl.max_paths, max_edges=tl.max_edges,
+                                         tuple_cap=tl.tuple_cap, tile_desc=self.tile_desc.data_ptr(), items=items_ptr,
+                                         **{k: v.data_ptr() for k, v in self.tile_edges.items()})
         self.grp_begin, self.aln_begin = (host.grp_begin, host.aln_begin) if self.tiles_c is not None else (0, 0)
         self.wide = wide
         if not host.wire:
@@ -630,7 +635,8 @@ class AbundanceEngine:
     def upload(self, host: HostReads):
         """H2D of a staged shard (+ device-side expansion of the transfer layout), reusing the device buffers."""
         dr = DeviceReads(host, self.device, getattr(self, "_arena", None), getattr(self, "_wide", None), self.node_len,
-                         tile_desc=getattr(self.dg, "tile_desc", None) if self.tiling is not None else None)
+                         tile_desc=getattr(self.dg, "tile_desc", None) if self.tiling is not None else None,
+                         tile_edges=getattr(self.dg, "tile_edges", None))
         self._arena, self._wide = dr.arena, dr.wide
         return dr
 
@@ -682,7 +688,8 @@ class AbundanceEngine:
             slot = job.slots.setdefault(k, {})
             with torch.cuda.stream(self._copy):
                 dr = DeviceReads(host, self.device, slot.get("arena"), slot.get("wide"), self.node_len, expand=False,
-                                 tile_desc=getattr(self.dg, "tile_desc", None) if self.tiling is not None else None)
+                                 tile_desc=getattr(self.dg, "tile_desc", None) if self.tiling is not None else None,
+                         tile_edges=getattr(self.dg, "tile_edges", None))
                 arrived = torch.cuda.Event()
                 arrived.record(self._copy)
             slot["arena"] = dr.arena

@@ -15,21 +15,31 @@ ITEM_GROUPS = 4096                                            # read groups per 
 
 
 class Tiling:
-    """node_tile int32[N] (-1 = none), tile_desc int32[NT, 4] = (p0, p1, n0, n1), sizes of the largest tile."""
+    """node_tile int32[N] (-1 = none), tile_desc int32[NT, 8] = (p0, p1, n0, n1, flags, 0, 0, 0), sizes of the largest
+    tile, and the edge index of the "simple" tiles (flags bit 0: at most 64 paths and no node twice in a path): for
+    every node its distinct successors on the tile's paths with the set of paths taking that step as a 64-bit mask
+    (bit = path id - p0), and the set of paths through the node.  A walk matches a path iff the path takes every
+    step of the walk, so get_matching_path (json2csv.py:341-363) becomes an AND over the steps."""
 
     def __init__(self, graph, slot_cap=4096, node_cap=4096, path_cap=PATH_LIMIT, merge_target=640, tuple_cap=None):
+        # (slot_cap / node_cap keep the shared-memory image of the largest tile, which sizes every launch, moderate)
         P, N = graph.n_paths, graph.n_nodes
         slot_cap, node_cap, path_cap = min(slot_cap, SLOT_LIMIT), min(node_cap, NODE_LIMIT), min(path_cap, PATH_LIMIT)
         self.node_tile = np.full(N, -1, np.int32)
-        self.tile_desc = np.zeros((0, 4), np.int32)
+        self.tile_desc = np.zeros((0, 8), np.int32)
+        self.edge_off = np.zeros(N + 1, np.int32)
+        self.edge_succ = np.zeros(0, np.int32)
+        self.edge_mask = np.zeros(0, np.uint64)
+        self.node_mask = np.zeros(N, np.uint64)
+        self.max_edges = 0
         self.max_slots = self.max_nodes = self.max_paths = 0
         if P and N:
             self._build(graph, slot_cap, node_cap, path_cap, merge_target)
         k = os.environ.get("SFB200_TILE_K")
         if tuple_cap is None and k:
             tuple_cap = int(k)
-        if tuple_cap is None:          # match tuples per mate kept in shared memory: a mate has about one per path of its tile
-            tuple_cap = 8 if self.max_paths <= 4 else 16 if self.max_paths <= 10 else 32
+        if tuple_cap is None:          # match tuples per alignment kept in shared memory: about one per path of the tile
+            tuple_cap = 8 if self.max_paths <= 9 else 16 if self.max_paths <= 20 else 32
         self.tuple_cap = int(tuple_cap)
 
     @property
@@ -98,13 +108,63 @@ class Tiling:
         if not desc:
             return
         desc = np.asarray(desc, np.int64)
-        self.tile_desc = np.ascontiguousarray(desc[:, :4], np.int32)
+        self.tile_desc = np.zeros((len(desc), 8), np.int32)
+        self.tile_desc[:, :4] = desc[:, :4]
         self.max_slots = int(desc[:, 4].max())
         self.max_nodes = int((desc[:, 3] - desc[:, 2]).max())
         self.max_paths = int((desc[:, 1] - desc[:, 0]).max())
         span = desc[:, 3] - desc[:, 2]
         self.node_tile[np.repeat(desc[:, 2], span) + (np.arange(int(span.sum())) - np.repeat(np.cumsum(span) - span, span))] = \
             np.repeat(np.arange(len(desc), dtype=np.int32), span)
+        self._edges(graph, desc)
+
+    def _edges(self, graph, desc):
+        """Edge index of the simple tiles (see the class docstring)."""
+        P, N = graph.n_paths, graph.n_nodes
+        off = graph.path_off.astype(np.int64)
+        plen = np.diff(off)
+        nodes = graph.path_nodes.astype(np.int64)
+        path_of = np.repeat(np.arange(P, dtype=np.int64), plen)
+        tile_of_path = np.full(P, -1, np.int64)
+        np_t = desc[:, 1] - desc[:, 0]
+        tile_of_path[np.repeat(desc[:, 0], np_t) + (np.arange(int(np_t.sum())) - np.repeat(np.cumsum(np_t) - np_t, np_t))] = \
+            np.repeat(np.arange(len(desc)), np_t)
+        # a node twice in one path?  (path, node) pairs must be distinct
+        key = path_of * N + nodes
+        srt = np.sort(key)
+        dup_path = np.zeros(P, bool)
+        if len(srt) > 1:
+            dup_path[(srt[1:][srt[1:] == srt[:-1]] // N)] = True
+        bad_tile = np.zeros(len(desc), bool)
+        tp = tile_of_path[dup_path]
+        bad_tile[tp[tp >= 0]] = True
+        simple = (np_t <= 64) & ~bad_tile
+        self.tile_desc[:, 4] = simple.astype(np.int32)
+        # occurrences on paths of simple tiles
+        t_occ = tile_of_path[path_of]
+        use = t_occ >= 0
+        use[use] = simple[t_occ[use]]
+        bit = np.left_shift(np.uint64(1), (path_of - desc[np.maximum(t_occ, 0), 0]).clip(0, 63).astype(np.uint64))
+        nm = np.zeros(N, np.uint64)
+        np.bitwise_or.at(nm, nodes[use], bit[use])
+        self.node_mask = nm
+        # steps: occurrence -> next occurrence of the same path
+        last = np.zeros(len(nodes), bool)
+        last[off[1:][plen > 0] - 1] = True
+        step = use & ~last
+        a, b, m = nodes[step], nodes[np.flatnonzero(step) + 1], bit[step]
+        ekey = a * N + b
+        order = np.argsort(ekey, kind="stable")
+        ekey, m = ekey[order], m[order]
+        first = np.ones(len(ekey), bool)
+        first[1:] = ekey[1:] != ekey[:-1]
+        starts = np.flatnonzero(first)
+        self.edge_mask = np.bitwise_or.reduceat(m, starts) if len(starts) else np.zeros(0, np.uint64)
+        ua = ekey[starts] // N
+        self.edge_succ = (ekey[starts] % N).astype(np.int32)
+        self.edge_off = np.concatenate(([0], np.cumsum(np.bincount(ua, minlength=N)))).astype(np.int32)
+        per_tile = self.edge_off[desc[:, 3]] - self.edge_off[desc[:, 2]]
+        self.max_edges = int(per_tile.max()) if len(per_tile) else 0
 
     def items(self, tile_grp_off):
         """Work items int32[n, 4] = (tile, first group, end group, 0) of a read shard in tile order."""

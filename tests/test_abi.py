@@ -72,7 +72,7 @@ def test_struct_sizes_are_pointer_and_int64_multiples():
     assert ctypes.sizeof(_lib.SfbReads) == 8 * 12
     assert ctypes.sizeof(_lib.SfbWire) == 8 * 26
     assert ctypes.sizeof(_lib.SfbWork) == 8 * 13
-    assert ctypes.sizeof(_lib.SfbTiles) == 8 * 8
+    assert ctypes.sizeof(_lib.SfbTiles) == 8 * 13
     assert ctypes.sizeof(_lib.SfbAccum) == 8 * 10
 
 
@@ -92,11 +92,11 @@ def test_argument_validation_needs_no_gpu():
     with pytest.raises(_lib.SfbError):
         _lib.check(rc)
     # tiles: limits of the local ids, tuple capacity, shared-memory size
-    t = _lib.SfbTiles(n_tiles=1, n_items=0, max_slots=1359, max_nodes=472, max_paths=9, tuple_cap=16)
+    t = _lib.SfbTiles(n_tiles=1, n_items=0, max_slots=1359, max_nodes=472, max_paths=9, max_edges=451, tuple_cap=8)
     assert 40_000 < lib.sfb_tile_smem_bytes(ctypes.byref(t)) < 100_000
     t.tuple_cap = 12
     assert lib.sfb_tile_smem_bytes(ctypes.byref(t)) == -1 and b"tuple_cap" in lib.sfb_last_error()
-    t.tuple_cap, t.max_slots = 16, 40_000
+    t.tuple_cap, t.max_slots = 8, 40_000
     assert lib.sfb_tile_smem_bytes(ctypes.byref(t)) == -1 and b"limits" in lib.sfb_last_error()
 
 

@@ -476,7 +476,7 @@ def test_tiling_of_the_synthetic_graph():
             for n in graph.path_nodes[graph.path_off[p]:graph.path_off[p + 1]]:
                 path_of_node[int(n)].add(p)
         seen_paths = 0
-        for t, (p0, p1, n0, n1) in enumerate(tl.tile_desc):
+        for t, (p0, p1, n0, n1) in enumerate(tl.tile_desc[:, :4]):
             assert p0 < p1 and n0 < n1
             slots = int(graph.path_off[p1] - graph.path_off[p0]) + (p1 - p0)
             assert slots <= tl.max_slots <= 32767 and p1 - p0 <= tl.max_paths <= 255 and n1 - n0 <= tl.max_nodes
@@ -495,7 +495,7 @@ def test_tiling_of_the_synthetic_graph():
               path_cluster=np.array([0, 1], np.int32), clu_off=np.array([0, 1, 2]), clu_paths=np.array([0, 1], np.int32),
               strain_names=["a", "b"], header_strains=[0, 1])
     one = Tiling(g)
-    assert one.n_tiles == 1 and tuple(one.tile_desc[0]) == (0, 2, 0, 8)
+    assert one.n_tiles == 1 and tuple(one.tile_desc[0]) == (0, 2, 0, 8, 1, 0, 0, 0)
     assert Tiling(g, slot_cap=6).n_tiles == 0 and (Tiling(g, slot_cap=6).node_tile == -1).all()
 
 

@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-ncu --set full --clock-control none --import-source on -k regex:k_tile_pass -c 2 -o gpurun_out/c_tile python bench.py --scale 0.1 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-det --no-extras > gpurun_out/c_ncu.log 2>&1
-tail -5 gpurun_out/c_ncu.log
-ls -la gpurun_out/
+ncu --set full --clock-control none --import-source on -k regex:k_tile_pass -c 2 -o gpurun_out/e_tile python bench.py --scale 0.4 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-det --no-extras > gpurun_out/e_ncu.log 2>&1
+tail -2 gpurun_out/e_ncu.log | cut -c1-600
