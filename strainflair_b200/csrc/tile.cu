@@ -1,79 +1,89 @@
 // Tile kernels: the abundance pass for read groups that live inside one tile of the graph (sfb_tiles in sfb200.h).
 //
 // A thread block takes a work item (tile, range of read groups in tile order), stages the tile in shared memory --
-// path nodes, node -> occurrence index, slot -> path, per-path constants -- together with zeroed accumulator bins,
-// and works through the item in chunks of 256 read groups.  Every chunk runs as a sequence of phases, each over a
-// dense list so that the lanes of a warp stay busy (one thread per group for everything ran at 4-8 active lanes):
-//   k_tile_pass1   M  thread = alignment: get_matching_path (json2csv.py:341-363) on both orientations against the
-//                     shared-memory index, match tuples into a per-alignment store
-//                  C  thread = read group: the pass-1 decision tree (:828-1053) and the per-read part of
-//                     fill_abund_dist (:321-339); unique assignments go to a list
-//                  S  thread = assigned alignment: its node loop (:329-330) into the bins
-//   k_tile_pass2   D  thread = read group: deferred?  its alignments go to a list
+// path nodes, node -> occurrence index, slot -> path, step index, per-path constants -- together with zeroed
+// accumulator bins, and works through the item in rounds.  A round is a sequence of phases, each over a dense list so
+// that the lanes of a warp stay busy (one thread per read group for everything ran at 4-8 active lanes of 32):
+//   k_tile_pass1   M  thread = alignment of a window of 256 groups: get_matching_path (json2csv.py:341-363) on both
+//                     orientations against the shared-memory index
+//                  C  thread = read group: the pass-1 decision tree (:828-1053); unique assignments go to a list
+//                  S  thread = unique assignment: fill_abund_dist (:321-339) -- per-path counters, histogram, node loop
+//   k_tile_pass2   D  thread = read group, window after window until ~256 deferred groups are listed
 //                  M  thread = listed alignment: the matches again (as the reference recomputes them, :1103-1114)
-//                  C  thread = deferred group: candidate selection and ratios (:1123-1274), per-path sums, work items
-//                  S  thread = work item: the node loop (:1157-1158)
-// Compares run against shared memory instead of index gathers, the fp64 additions go to shared-memory bins in 96-bit
-// fixed point (three 32-bit limbs per accumulator, native ATOMS.ADD with exact carries: integer sums do not depend
-// on the order of the additions) and are flushed once per work item with 64-bit integer REDs; histogram updates are
-// aggregated per block in a small hash table keyed by (strain, five bins).  The decision logic is group_logic.cuh,
-// shared with the global-memory kernels.
-#include <atomic>
-
+//                  C  thread = deferred group: candidate selection and ratios (:1123-1274); work items go to a list
+//                  S  thread = work item: per-path sums (:1155-1156) and the node loop (:1157-1158)
+// Matches: in a "simple" tile (at most 64 paths, no node twice in a path) an alignment's matches are two 64-bit path
+// sets, the AND over the walk's steps of the step index, and the set logic of the decision tree is AND / OR / popcount;
+// other tiles keep per-alignment tuple lists and run the generic logic of group_logic.cuh.
+// Sums: shared-memory bins in 96-bit fixed point (three 32-bit limbs per accumulator, native ATOMS.ADD with exact
+// carries: integer sums do not depend on the order of the additions), flushed once per work item with 64-bit integer
+// REDs; histogram updates are aggregated per block in a small hash table keyed by (strain, five bins).
 #include "common.cuh"
 #include "group_logic.cuh"
 
 namespace sfb {
 
-constexpr int kTT = 256;              // threads per block = read groups per chunk
-constexpr int kAC = 3 * kTT;          // alignments per chunk (a chunk shrinks until its alignments fit)
+constexpr int kTT = 256;              // threads per block = read groups per window
+constexpr int kRows1 = 3 * kTT;       // pass 1: alignments per window (a window shrinks until its alignments fit)
+constexpr int kWin2 = 2 * kTT;        // pass 2: alignments per window ...
+constexpr int kRows2 = 4 * kTT;       // ... listed alignments per round
+constexpr int kGrp2 = 2 * kTT;        // ... listed groups per round
 constexpr int kHash = 256;            // entries of the histogram aggregation table
 constexpr u64 kHashEmpty = ~0ull;
 constexpr unsigned kNoNode = 0xFFFEu; // local id of a walk node outside the tile (never equal to a path node)
 constexpr unsigned kSentinel = 0xFFFFu;
 constexpr int kOver = 255;            // tuple count of an alignment with more than KA matches
+constexpr uint32_t kHasSlot = 0x80000000u;   // list entry carries its slot (tuple tiles); else phase S looks it up
 
-__host__ __device__ inline int tile_app_cap(int KA) { return 192 * KA; }     // pass-2 work items per chunk
+__host__ __device__ inline int tile_rows(int pass) { return pass == 1 ? kRows1 : kRows2; }
+__host__ __device__ inline int tile_list_cap(int pass) { return pass == 1 ? kRows1 : 6 * kTT; }   // entries of phase S's list
+constexpr int kRec2 = 2 * kTT;        // pass 2: share records per round (total and count of a candidate set)
+__host__ __device__ inline int tile_reps(int mp) { return mp <= 32 ? 8 : mp <= 64 ? 4 : 1; }       // copies of the per-path sums
 
 // ---- shared-memory layout, sized by the largest tile (same arithmetic on host and device) -----------------------
 struct TileLayout {
-    unsigned hkey, pseq, pU, appw, emask, nmask, store, bins, plimb, pclu, pstr0, pnstr, hcnt, sc, misc, lst, appk, poff, node,
-        occ, occ_off, eoff, esucc, alist, glist, spath, cnt, total;
+    unsigned hkey, pseq, pU, rec, emask, nmask, store, bins, plimb, la, lx, lseq, alist, glist, pclu, pstr0, pnstr, hcnt, sc, misc,
+        lt, lm, grow, poff, node, occ, occ_off, eoff, esucc, spath, cnt, total;
 };
 __host__ __device__ inline TileLayout tile_layout(int pass, int ms, int mn, int mp, int me, int KA) {
     TileLayout L;
     unsigned o = 0;
     auto take = [&](unsigned bytes) { const unsigned at = o; o += (bytes + 15u) & ~15u; return at; };
-    const unsigned napp = pass == 2 ? tile_app_cap(KA) : 0;
-    const unsigned store_tup = 2u * kAC * KA, store_mask = 16u * kAC;
+    const unsigned rows = tile_rows(pass), cap = tile_list_cap(pass);
+    const unsigned store_tup = 2u * rows * KA, store_mask = 16u * rows;
     L.hkey = take(8u * kHash);
     L.pseq = take(8u * mp);
     L.pU = take(pass == 2 ? 8u * mp : 0);
-    L.appw = take(8u * napp);                   // pass 2: weight of a work item
+    L.rec = take(pass == 2 ? 16u * kRec2 : 0);  // pass 2: share records (long long total | ratio bits, int n, int len(sequence))
     L.emask = take(8u * me);                    // step index of a simple tile: path set of every step ...
     L.nmask = take(8u * mn);                    // ... and of every node
     L.store = take(store_tup > store_mask ? store_tup : store_mask);   // per alignment: match tuples (rev << 15 | slot),
                                                                        // or the forward / reverse path sets (simple tile)
     L.bins = take(12u * ms);
-    L.plimb = take(28u * mp);
+    L.plimb = take(28u * mp * tile_reps(mp));
+    L.la = take(4u * cap);                      // list of phase S: alignment (offset inside the work item) ...
+    L.lx = take(4u * cap);                      // ... path << 16 | reverse (the slot is looked up in phase S), or
+                                                //     kHasSlot | path << 16 | slot ...
+    L.lseq = take(pass == 1 ? 4u * cap : 0);    // ... len(sequence) of the mate (pass 1)
+    L.alist = take(pass == 2 ? 4u * kRows2 : 0);   // pass 2: listed alignments (offset inside the work item)
+    L.glist = take(pass == 2 ? 4u * kGrp2 : 0);    // pass 2: listed groups (offset inside the work item)
     L.pclu = take(4u * mp);
     L.pstr0 = take(4u * mp);
     L.pnstr = take(4u * mp);
     L.hcnt = take(4u * kHash);
     L.sc = take(sizeof(BlockCounters));
     L.misc = take(32);
-    L.lst = take(pass == 1 ? 4u * kAC : 0);     // pass 1: unique assignments (alignment << 16 | slot)
-    L.appk = take(4u * napp);                   // pass 2: work item (alignment << 16 | slot)
+    L.lt = take(pass == 2 ? 2u * cap : 0);      // list of phase S: times (pass 2) ...
+    L.lm = take(pass == 2 ? 2u * cap : 0);      // ... and share record
+    L.grow = take(pass == 2 ? 2u * kGrp2 : 0);  // pass 2: first row of a listed group
     L.poff = take(2u * (mp + 1));
     L.node = take(2u * (ms + 2));
     L.occ = take(2u * ms);
     L.occ_off = take(2u * (mn + 1));
     L.eoff = take(2u * (mn + 1));
     L.esucc = take(2u * me);
-    L.alist = take(pass == 2 ? 2u * kAC : 0);   // pass 2: alignments of the deferred groups
-    L.glist = take(pass == 2 ? 2u * kTT : 0);   // pass 2: deferred groups
     L.spath = take(ms);
-    L.cnt = take(kAC);                          // tuples per alignment, kOver = more than KA
+    L.cnt = take(rows);                         // tuples per alignment, kOver = more than KA
     L.total = o;
     return L;
 }
@@ -82,20 +92,26 @@ struct TileS {
     u64* hkey;
     long long* pseq;
     long long* pU;
-    double* appw;
+    longlong2* rec;      // .x = total of unique counts over the candidate set | bits of an explicit share, .y = n | len << 32
     u64* emask;
     u64* nmask;
-    u64* amask;          // [kAC][2] forward / reverse path set of an alignment (simple tile; shares `tup`'s memory)
+    u64* amask;          // [rows][2] forward / reverse path set of an alignment (simple tile; shares `tup`'s memory)
     uint32_t* bins;      // [ns][3] limbs x0, x1, x2
-    uint32_t* plimb;     // [np][7]: count / flag, three limbs A, three limbs B
+    uint32_t* plimb;     // [reps][np][7]: count / flag, three limbs A, three limbs B
+    uint32_t* la;
+    uint32_t* lx;
+    int* lseq;
+    uint32_t* alist;
+    uint32_t* glist;
     int* pclu;
     int* pstr0;
     int* pnstr;
     uint32_t* hcnt;
     BlockCounters* sc;
-    int* misc;           // [0] work item, [1] list fill (assignments / work items), [2] alignment list, [3] group list
-    uint32_t* lst;
-    uint32_t* appk;
+    int* misc;           // [0] work item, [1] fill of phase S's list, [2] listed alignments, [3] listed groups, [4] records
+    uint16_t* lt;
+    uint16_t* lm;
+    uint16_t* grow;
     uint16_t* poff;
     uint16_t* node;
     uint16_t* occ;
@@ -103,13 +119,12 @@ struct TileS {
     uint16_t* eoff;
     uint16_t* esucc;
     uint16_t* tup;
-    uint16_t* alist;
-    uint16_t* glist;
     uint8_t* spath;
     uint8_t* cnt;
-    int p0, np, n0, nn, s0, ns;
+    int p0, np, n0, nn, s0, ns, mp, reps;
     bool simple;
-    i64 a0c;             // first alignment of the chunk
+    i64 a_item;          // first alignment of the work item
+    i64 a_row0;          // pass 1: alignment of row 0 of the window
 };
 __device__ __forceinline__ TileS tile_carve(int pass, unsigned char* smem, const sfb_tiles& t) {
     const TileLayout L = tile_layout(pass, (int)t.max_slots, (int)t.max_nodes, (int)t.max_paths, (int)t.max_edges, (int)t.tuple_cap);
@@ -117,34 +132,40 @@ __device__ __forceinline__ TileS tile_carve(int pass, unsigned char* smem, const
     T.hkey = reinterpret_cast<u64*>(smem + L.hkey);
     T.pseq = reinterpret_cast<long long*>(smem + L.pseq);
     T.pU = reinterpret_cast<long long*>(smem + L.pU);
-    T.appw = reinterpret_cast<double*>(smem + L.appw);
+    T.rec = reinterpret_cast<longlong2*>(smem + L.rec);
     T.emask = reinterpret_cast<u64*>(smem + L.emask);
     T.nmask = reinterpret_cast<u64*>(smem + L.nmask);
     T.amask = reinterpret_cast<u64*>(smem + L.store);
     T.tup = reinterpret_cast<uint16_t*>(smem + L.store);
     T.bins = reinterpret_cast<uint32_t*>(smem + L.bins);
     T.plimb = reinterpret_cast<uint32_t*>(smem + L.plimb);
+    T.la = reinterpret_cast<uint32_t*>(smem + L.la);
+    T.lx = reinterpret_cast<uint32_t*>(smem + L.lx);
+    T.lseq = reinterpret_cast<int*>(smem + L.lseq);
+    T.alist = reinterpret_cast<uint32_t*>(smem + L.alist);
+    T.glist = reinterpret_cast<uint32_t*>(smem + L.glist);
     T.pclu = reinterpret_cast<int*>(smem + L.pclu);
     T.pstr0 = reinterpret_cast<int*>(smem + L.pstr0);
     T.pnstr = reinterpret_cast<int*>(smem + L.pnstr);
     T.hcnt = reinterpret_cast<uint32_t*>(smem + L.hcnt);
     T.sc = reinterpret_cast<BlockCounters*>(smem + L.sc);
     T.misc = reinterpret_cast<int*>(smem + L.misc);
-    T.lst = reinterpret_cast<uint32_t*>(smem + L.lst);
-    T.appk = reinterpret_cast<uint32_t*>(smem + L.appk);
+    T.lt = reinterpret_cast<uint16_t*>(smem + L.lt);
+    T.lm = reinterpret_cast<uint16_t*>(smem + L.lm);
+    T.grow = reinterpret_cast<uint16_t*>(smem + L.grow);
     T.poff = reinterpret_cast<uint16_t*>(smem + L.poff);
     T.node = reinterpret_cast<uint16_t*>(smem + L.node);
     T.occ = reinterpret_cast<uint16_t*>(smem + L.occ);
     T.occ_off = reinterpret_cast<uint16_t*>(smem + L.occ_off);
     T.eoff = reinterpret_cast<uint16_t*>(smem + L.eoff);
     T.esucc = reinterpret_cast<uint16_t*>(smem + L.esucc);
-    T.alist = reinterpret_cast<uint16_t*>(smem + L.alist);
-    T.glist = reinterpret_cast<uint16_t*>(smem + L.glist);
     T.spath = smem + L.spath;
     T.cnt = smem + L.cnt;
     T.p0 = T.np = T.n0 = T.nn = T.s0 = T.ns = 0;
+    T.mp = (int)t.max_paths;
+    T.reps = tile_reps(T.mp);
     T.simple = false;
-    T.a0c = 0;
+    T.a_item = T.a_row0 = 0;
     return T;
 }
 
@@ -183,15 +204,19 @@ __device__ __forceinline__ void fx_flush(double* p, i64 det_stride, const uint32
         atomicAdd(p, (double)x2 + (double)x1 * 0x1p-32 + (double)x0 * 0x1p-64);
     }
 }
-// cov[i] * weight into the bins of slot (local); full-coverage records (aligned == node length) with weight 1 are
-// the integer 1
+// The node loop: cov[i] * weight into the bins of slot + i.  Records that cover their node (aligned == node length)
+// add the weight itself, split once; with weight 1 that is the integer 1.
 __device__ __forceinline__ void tile_add_records(const TileS& T, const sfb_reads& r, i64 w0, int L, int slot, bool unit,
                                                  double weight) {
     uint32_t* b = T.bins + 3 * slot;
+    Fx whole;
+    whole.x0 = whole.x1 = 0u;
+    whole.x2 = 1u;
+    if (!unit) whole = fx_split(weight);
     for (int i = 0; i < L; ++i, b += 3) {
         const int v = r.walk_alen[w0 + i];
-        if (unit && v >= 0 && (v & 0xffff) == (v >> 16)) {
-            atomicAdd(b + 2, 1u);
+        if (v >= 0 && (v & 0xffff) == (v >> 16)) {
+            if (unit) atomicAdd(b + 2, 1u); else fx_smem_add(b, whole);
             continue;
         }
         const double cov = v < 0 ? r.exc_cov[-(i64)v - 1] : (double)(v & 0xffff) / (double)(v >> 16);
@@ -240,7 +265,7 @@ __device__ __forceinline__ void tile_stage(TileS& T, const Dev& d, const sfb_til
         if (PASS == 2) T.pU[p] = U[T.p0 + p];
     }
     for (int i = tid; i < 3 * T.ns; i += kTT) T.bins[i] = 0u;
-    for (int i = tid; i < 7 * T.np; i += kTT) T.plimb[i] = 0u;
+    for (int i = tid; i < 7 * T.mp * T.reps; i += kTT) T.plimb[i] = 0u;
     for (int i = tid; i < kHash; i += kTT) {
         T.hkey[i] = kHashEmpty;
         T.hcnt[i] = 0u;
@@ -267,14 +292,31 @@ __device__ __forceinline__ void hist_out(const Dev& d, BlockCounters& sc, u64 ke
         atomicAdd(&d.acc.hist[((size_t)k * d.g.n_strains + s) * SFB_N_BINS + b], (u64)cnt);
     }
 }
+// histogram update of a read on path `p` (local), aggregated in the block's table (json2csv.py:333-339 / :1246-1252)
+__device__ __forceinline__ void tile_hist(const TileS& T, const Dev& d, BlockCounters& sc, int p, i64 a) {
+    if (T.pnstr[p] != 1) return;
+    const uint8_t* b = d.r.aln_bins + a * SFB_N_HIST;
+    const u64 key = ((u64)(uint32_t)T.pstr0[p] << 40) | (u64)b[0] | ((u64)b[1] << 8) | ((u64)b[2] << 16) |
+                    ((u64)b[3] << 24) | ((u64)b[4] << 32);
+    unsigned h = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 56) & (kHash - 1);
+    for (int probe = 0; probe < kHash; ++probe, h = (h + 1) & (kHash - 1)) {
+        const u64 old = atomicCAS(&T.hkey[h], kHashEmpty, key);
+        if (old == kHashEmpty || old == key) {
+            atomicAdd(&T.hcnt[h], 1u);
+            return;
+        }
+    }
+    hist_out(d, sc, key, 1u);                            // table full: straight to the global histograms
+}
 
 template <int PASS>
 __device__ __forceinline__ void tile_flush(const TileS& T, const Dev& d, BlockCounters& sc) {
     const int tid = threadIdx.x;
     double* slots = PASS == 1 ? d.acc.uniq_abund : d.acc.mult_abund;
     for (int i = tid; i < T.ns; i += kTT) fx_flush(slots + T.s0 + i, d.acc.det_stride, T.bins + 3 * i);
-    for (int p = tid; p < T.np; p += kTT) {
-        const uint32_t* l = T.plimb + 7 * p;
+    for (int q = tid; q < T.np * T.reps; q += kTT) {
+        const int p = q % T.np, rep = q / T.np;
+        const uint32_t* l = T.plimb + 7 * (rep * T.mp + p);
         const int pid = T.p0 + p;
         if (PASS == 1) {
             if (l[0]) atomicAdd((u64*)&d.acc.uniq_reads[pid], (u64)l[0]);
@@ -288,14 +330,20 @@ __device__ __forceinline__ void tile_flush(const TileS& T, const Dev& d, BlockCo
     for (int i = tid; i < kHash; i += kTT)
         if (T.hkey[i] != kHashEmpty) hist_out(d, sc, T.hkey[i], T.hcnt[i]);
 }
+__device__ __forceinline__ uint32_t* tile_plimb(const TileS& T, int p) {      // this warp's copy of path p's sums
+    return T.plimb + 7 * (((threadIdx.x >> 5) % T.reps) * T.mp + p);
+}
 
 // ---- matching against the resident tile -------------------------------------------------------------------------
 __device__ __forceinline__ unsigned tile_local(const TileS& T, int node) {
     const unsigned x = (unsigned)(node - T.n0);
     return x < (unsigned)T.nn ? x : kNoNode;
 }
+__device__ __forceinline__ uint32_t tile_code(const TileS& T, int slot, bool rev) {
+    return (uint32_t)(T.s0 + slot) | (rev ? SFB_MATCH_REV : 0u);
+}
 // get_matching_path (json2csv.py:341-363) for the walk and, if longer than one node, the reversed walk: f(slot, rev)
-// for every match, in the reference's order (forward by ascending slot, then reverse)
+// for every match, in the reference's order (forward by ascending slot, then reverse).  Any tile.
 template <class F>
 __device__ __forceinline__ void tile_enum(const TileS& T, const sfb_reads& r, i64 w0, int L, TileStats& st, F&& f) {
     if (L <= 0) return;
@@ -338,24 +386,18 @@ __device__ __forceinline__ void tile_enum(const TileS& T, const sfb_reads& r, i6
         }
 }
 
-// match tuple in shared memory: rev (1) | local slot (15); the path is spath[slot], the alignment is the row
-__device__ __forceinline__ uint32_t tile_code(const TileS& T, int slot, bool rev) {
-    return (uint32_t)(T.s0 + slot) | (rev ? SFB_MATCH_REV : 0u);
-}
-
-// phase M: the matches of chunk alignment `i` into its row of the tuple store
+// phase M, any tile: the matches of alignment `a` into row `row` of the tuple store (rev << 15 | slot)
 template <int KA>
-__device__ __forceinline__ void tile_match_aln(const TileS& T, const sfb_reads& r, int i, TileStats& st) {
-    const i64 a = T.a0c + i;
+__device__ __forceinline__ void tile_match_aln(const TileS& T, const sfb_reads& r, int row, i64 a, TileStats& st) {
     const i64 w0 = r.aln_walk_off[a];
     const int L = (int)(r.aln_walk_off[a + 1] - w0);
-    uint16_t* row = T.tup + i * KA;
+    uint16_t* out = T.tup + row * KA;
     int n = 0;
     tile_enum(T, r, w0, L, st, [&](int s, bool rev) {
-        if (n < KA) row[n] = (uint16_t)(s | ((int)rev << 15));
+        if (n < KA) out[n] = (uint16_t)(s | ((int)rev << 15));
         ++n;
     });
-    T.cnt[i] = (uint8_t)(n > KA ? kOver : n);
+    T.cnt[row] = (uint8_t)(n > KA ? kOver : n);
     st.tuples += n;
 }
 
@@ -364,16 +406,17 @@ __device__ __forceinline__ void tile_match_aln(const TileS& T, const sfb_reads& 
 template <int KA>
 struct TileView {
     const TileS* T;
-    int row[2];      // first alignment of the mate, chunk-relative
+    int row[2];      // row of the mate's first alignment
     int na[2];
     int n[2];
     int c0[2];       // tuples of the mate's first alignment
     // false when an alignment overflowed its row
-    __device__ __forceinline__ bool load(const TileS& T_, const Mate* mt) {
+    __device__ __forceinline__ bool load(const TileS& T_, const Mate* mt, int row0) {
         T = &T_;
         bool fits = true;
+        row[0] = row0;
+        row[1] = row0 + mt[0].na;
         for (int k = 0; k < 2; ++k) {
-            row[k] = (int)(mt[k].a0 - T_.a0c);
             na[k] = mt[k].na;
             int tot = 0;
             for (int j = 0; j < na[k]; ++j) {
@@ -405,36 +448,26 @@ struct TileView {
     __device__ __forceinline__ int aloc(int k, int i) const { int j; word(k, i, j); return j; }
 };
 
-// ---- effects (the Ops of group_logic.cuh) on the resident tile ---------------------------------------------------
+// ---- effects of the decisions (the Ops of group_logic.cuh) ---------------------------------------------------------
+// Phase C only decides; what a decision adds to the accumulators is listed for phase S, where every lane has one entry.
+// An entry names the alignment, the path and either the slot (tuple tiles) or the orientation (simple tiles: the slot
+// is looked up in phase S); in pass 2 also the share record (total and count of the candidate set) and the
+// multiplicity of the path (Q4).
 struct TileOps {
     TileS* T;
     TileStats* st;
-    int app_cap;
-    __device__ __forceinline__ void hist(const Dev& d, BlockCounters& sc, int pid, i64 a) {
-        const int p = pid - T->p0;
-        if (T->pnstr[p] != 1) return;                        // json2csv.py:333 / :1246
-        const uint8_t* b = d.r.aln_bins + a * SFB_N_HIST;
-        const u64 key = ((u64)(uint32_t)T->pstr0[p] << 40) | (u64)b[0] | ((u64)b[1] << 8) | ((u64)b[2] << 16) |
-                        ((u64)b[3] << 24) | ((u64)b[4] << 32);
-        unsigned h = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 56) & (kHash - 1);
-        for (int probe = 0; probe < kHash; ++probe, h = (h + 1) & (kHash - 1)) {
-            const u64 old = atomicCAS(&T->hkey[h], kHashEmpty, key);
-            if (old == kHashEmpty || old == key) {
-                atomicAdd(&T->hcnt[h], 1u);
-                return;
-            }
-        }
-        hist_out(d, sc, key, 1u);                            // table full: straight to the global histograms
+    int cap;
+    __device__ __forceinline__ void hist(const Dev& d, BlockCounters& sc, int pid, i64 a) { tile_hist(*T, d, sc, pid - T->p0, a); }
+    // fill_abund_dist (json2csv.py:321-339): listed with (tuple tiles) or without (simple tiles) the slot
+    __device__ __forceinline__ void list_unique(i64 a, uint32_t x, int seq_len) {
+        const int q = atomicAdd(&T->misc[1], 1);             // an alignment is assigned at most once: q < kRows1
+        T->la[q] = (uint32_t)(a - T->a_item);
+        T->lx[q] = x;
+        T->lseq[q] = seq_len;
     }
-    // fill_abund_dist (json2csv.py:321-339); the node loop (:329-330) goes to the list of phase S
     __device__ __forceinline__ void assign_unique(const Dev& d, BlockCounters& sc, i64 a, uint32_t code, int pid, int seq_len) {
         d.w.aln_assign[a] = (int32_t)code;
-        const int p = pid - T->p0;
-        atomicAdd(&T->plimb[7 * p], 1u);
-        fx_smem_add(&T->plimb[7 * p + 1], fx_split((double)seq_len / (double)T->pseq[p]));
-        hist(d, sc, pid, a);
-        const int q = atomicAdd(&T->misc[1], 1);             // an alignment is assigned at most once: q < kAC
-        T->lst[q] = ((uint32_t)(a - T->a0c) << 16) | (uint32_t)((int)(code & SFB_SLOT_MASK) - T->s0);
+        list_unique(a, kHasSlot | ((uint32_t)(pid - T->p0) << 16) | (uint32_t)((int)(code & SFB_SLOT_MASK) - T->s0), seq_len);
     }
     // cluster of the first path through the walk's first node (json2csv.py:875,901,1036); -1 = None, -2 = no path
     __device__ __forceinline__ int first_cluster(const Dev& d, i64 a) {
@@ -447,27 +480,97 @@ struct TileOps {
         d.w.aln_assign[mt.a0] = -(cluster + 2);
     }
     __device__ __forceinline__ long long uniq(int pid) const { return T->pU[pid - T->p0]; }
-    // json2csv.py:1155-1158 (and :1207-1210, :1265-1268)
-    __device__ __forceinline__ void apply(const Dev& d, i64 a, uint32_t code, int pid, int seq_len, double ratio, int times) {
-        const int p = pid - T->p0;
-        const double weight = ratio * (double)times;
-        T->plimb[7 * p] = 1u;                                // "touched" flag
-        fx_smem_add(&T->plimb[7 * p + 1], fx_split(weight));
-        fx_smem_add(&T->plimb[7 * p + 4], fx_split((ratio * (double)seq_len / (double)T->pseq[p]) * (double)times));
+    // a share record: the shares of a candidate set are uniq[p] / total, or 1 / n when total is 0 (json2csv.py:1151-1154);
+    // n < 0: `total` holds the bits of an explicit share.  -1 when the table is full.
+    __device__ __forceinline__ int record(long long total, int n, int seq_len) {
+        const int k = atomicAdd(&T->misc[4], 1);
+        if (k >= kRec2) return -1;
+        T->rec[k] = make_longlong2(total, (long long)(uint32_t)n | ((long long)seq_len << 32));
+        return k;
+    }
+    // one work item of pass 2 (json2csv.py:1155-1158 and twins); false when a list is full
+    __device__ __forceinline__ bool list_share(i64 a, uint32_t x, int times, int rec) {
         st->app += 1;
-        const int slot = (int)(code & SFB_SLOT_MASK) - T->s0;
+        if (rec < 0 || times > 0xffff) return false;
         const int q = atomicAdd(&T->misc[1], 1);
-        if (q < app_cap) {                                   // the node loop goes to the list of phase S
-            T->appk[q] = ((uint32_t)(a - T->a0c) << 16) | (uint32_t)slot;
-            T->appw[q] = weight;
+        if (q >= cap) return false;
+        T->la[q] = (uint32_t)(a - T->a_item);
+        T->lx[q] = x;
+        T->lt[q] = (uint16_t)times;
+        T->lm[q] = (uint16_t)rec;
+        return true;
+    }
+    // generic logic (tuple tiles): the share comes computed
+    __device__ __forceinline__ void apply(const Dev& d, i64 a, uint32_t code, int pid, int seq_len, double ratio, int times) {
+        const int slot = (int)(code & SFB_SLOT_MASK) - T->s0, p = pid - T->p0;
+        if (list_share(a, kHasSlot | ((uint32_t)p << 16) | (uint32_t)slot, times, record(__double_as_longlong(ratio), -1, seq_len)))
             return;
-        }
-        const i64 w0 = d.r.aln_walk_off[a];                  // list full (many candidate paths per read): here and now
+        st->app -= 1;
+        apply_now(d, a, slot, p, seq_len, ratio, times);
+    }
+    // a list is full (many candidate paths per read): here and now
+    __device__ __forceinline__ void apply_now(const Dev& d, i64 a, int slot, int p, int seq_len, double ratio, int times) {
+        st->app += 1;
+        const double weight = ratio * (double)times;
+        uint32_t* l = tile_plimb(*T, p);
+        l[0] = 1u;                                           // "touched" flag
+        fx_smem_add(l + 1, fx_split(weight));
+        fx_smem_add(l + 4, fx_split((ratio * (double)seq_len / (double)T->pseq[p]) * (double)times));
+        const i64 w0 = d.r.aln_walk_off[a];
         const int L = (int)(d.r.aln_walk_off[a + 1] - w0);
         tile_add_records(*T, d.r, w0, L, slot, false, weight);
         st->rec += L;
     }
 };
+// slot of node `n` (local) on path `p` (local) of a simple tile
+__device__ __forceinline__ int tile_slot_of(const TileS& T, unsigned n, int p) {
+    for (int c = T.occ_off[n]; c < (int)T.occ_off[n + 1]; ++c)
+        if (T.spath[T.occ[c]] == p) return T.occ[c];
+    return 0;
+}
+// slot of a list entry: carried, or (simple tile) where path p has the walk's first node -- its last node for a match of
+// the reversed walk (json2csv.py:862)
+__device__ __forceinline__ int tile_entry_slot(const TileS& T, const sfb_reads& r, uint32_t x, i64 w0, int L) {
+    if (x & kHasSlot) return (int)(x & 0x7fffu);
+    const i64 w = (x & 1u) ? w0 + L - 1 : w0;
+    return tile_slot_of(T, tile_local(T, r.walk_node[w]), (int)((x >> 16) & 0xffu));
+}
+// phase S of pass 1: one unique assignment (fill_abund_dist, json2csv.py:321-339)
+__device__ __forceinline__ void tile_scatter1(TileS& T, const Dev& d, BlockCounters& sc, int q, TileStats& st) {
+    const i64 a = T.a_item + T.la[q];
+    const uint32_t x = T.lx[q];
+    const int p = (int)((x >> 16) & 0xffu);
+    const i64 w0 = d.r.aln_walk_off[a];
+    const int L = (int)(d.r.aln_walk_off[a + 1] - w0);
+    const int slot = tile_entry_slot(T, d.r, x, w0, L);
+    if (!(x & kHasSlot)) d.w.aln_assign[a] = (int32_t)tile_code(T, slot, (x & 1u) != 0);
+    uint32_t* l = tile_plimb(T, p);
+    atomicAdd(l, 1u);
+    fx_smem_add(l + 1, fx_split((double)T.lseq[q] / (double)T.pseq[p]));
+    tile_hist(T, d, sc, p, a);
+    tile_add_records(T, d.r, w0, L, slot, true, 1.0);
+    st.rec += L;
+}
+// phase S of pass 2: one work item (json2csv.py:1155-1158)
+__device__ __forceinline__ void tile_scatter2(TileS& T, const Dev& d, int q, TileStats& st) {
+    const i64 a = T.a_item + T.la[q];
+    const uint32_t x = T.lx[q];
+    const int p = (int)((x >> 16) & 0xffu);
+    const longlong2 rc = T.rec[T.lm[q]];
+    const int n = (int)(uint32_t)rc.y, seq_len = (int)(rc.y >> 32);
+    const double ratio = n < 0 ? __longlong_as_double(rc.x) : ratio_of(T.pU[p], rc.x, n);
+    const double times = (double)T.lt[q];
+    const double weight = ratio * times;
+    const i64 w0 = d.r.aln_walk_off[a];
+    const int L = (int)(d.r.aln_walk_off[a + 1] - w0);
+    const int slot = tile_entry_slot(T, d.r, x, w0, L);
+    uint32_t* l = tile_plimb(T, p);
+    l[0] = 1u;                                               // "touched" flag
+    fx_smem_add(l + 1, fx_split(weight));
+    fx_smem_add(l + 4, fx_split((ratio * (double)seq_len / (double)T.pseq[p]) * times));
+    tile_add_records(T, d.r, w0, L, slot, false, weight);
+    st.rec += L;
+}
 
 // =================================================================================================================
 // Simple tiles (at most 64 paths, no node twice in a path): path sets as 64-bit masks
@@ -482,9 +585,8 @@ __device__ __forceinline__ u64 tile_step(const TileS& T, unsigned n, unsigned su
         if (T.esucc[e] == succ) return T.emask[e];
     return 0ull;
 }
-// phase M: forward / reverse path sets of chunk alignment `i`
-__device__ __forceinline__ void mask_match_aln(const TileS& T, const sfb_reads& r, int i, TileStats& st) {
-    const i64 a = T.a0c + i;
+// phase M: forward / reverse path sets of alignment `a` into row `row`
+__device__ __forceinline__ void mask_match_aln(const TileS& T, const sfb_reads& r, int row, i64 a, TileStats& st) {
     const i64 w0 = r.aln_walk_off[a];
     const int L = (int)(r.aln_walk_off[a + 1] - w0);
     u64 f = 0, rv = 0;
@@ -505,31 +607,24 @@ __device__ __forceinline__ void mask_match_aln(const TileS& T, const sfb_reads& 
             }
         }
     }
-    T.amask[2 * i] = f;
-    T.amask[2 * i + 1] = rv;
+    T.amask[2 * row] = f;
+    T.amask[2 * row + 1] = rv;
     const int n = __popcll(f) + __popcll(rv);
     st.cand += n;
     st.tuples += n;
 }
-// slot of node `n` (local) on path `p` (local) of a simple tile
-__device__ __forceinline__ int tile_slot_of(const TileS& T, unsigned n, int p) {
-    for (int c = T.occ_off[n]; c < (int)T.occ_off[n + 1]; ++c)
-        if (T.spath[T.occ[c]] == p) return T.occ[c];
-    return 0;
-}
-// match code of the tuple (alignment a, path p, orientation): the walk's first node for a forward match, its last node
-// for a reverse one (json2csv.py:862 matches the reversed walk)
+// match code of the tuple (alignment a, path p, orientation), for the rare paths that need it at once
 __device__ __forceinline__ uint32_t mask_code(const TileS& T, const sfb_reads& r, i64 a, int p, bool rev) {
     const i64 w = rev ? r.aln_walk_off[a + 1] - 1 : r.aln_walk_off[a];
     return tile_code(T, tile_slot_of(T, tile_local(T, r.walk_node[w]), p), rev);
 }
 
 struct MaskMate {
-    int row, na, nt;     // first alignment (chunk-relative), alignments, tuples
+    int row, na, nt;     // row of the first alignment, alignments, tuples
     u64 S, dup;          // paths matched, paths matched more than once
-    __device__ __forceinline__ void load(const TileS& T, const Mate& m) {
-        row = (int)(m.a0 - T.a0c);
-        na = m.na;
+    __device__ __forceinline__ void load(const TileS& T, int row_, int na_) {
+        row = row_;
+        na = na_;
         S = dup = 0;
         nt = 0;
         for (int j = 0; j < 2 * na; ++j) {
@@ -615,8 +710,7 @@ __device__ __forceinline__ void mask_classify_pair(TileS& T, const Dev& d, TileO
             int j;
             bool rev;
             mm[k].find(T, p, j, rev);
-            const i64 a = mt[k].a0 + j;
-            ops.assign_unique(d, sc, a, mask_code(T, d.r, a, p, rev), T.p0 + p, mt[k].seq_len);
+            ops.list_unique(mt[k].a0 + j, ((uint32_t)p << 16) | (uint32_t)rev, mt[k].seq_len);
             SFB_COUNT(sc, SFB_C_ASSIGNED_U, 1);
             SFB_COUNT(sc, SFB_C_SAME_CP, 1);
             if (mm[k].nt > 1) SFB_COUNT(sc, SFB_C_AMBIG_CP_RESOLVED, 1);
@@ -647,8 +741,7 @@ __device__ __forceinline__ void mask_classify_pair(TileS& T, const Dev& d, TileO
                 int j;
                 bool rev;
                 mm[k].find(T, p, j, rev);
-                const i64 a = mt[k].a0 + j;
-                ops.assign_unique(d, sc, a, mask_code(T, d.r, a, p, rev), T.p0 + p, mt[k].seq_len);
+                ops.list_unique(mt[k].a0 + j, ((uint32_t)p << 16) | (uint32_t)rev, mt[k].seq_len);
                 SFB_COUNT(sc, SFB_C_ASSIGNED_U, 1);
                 SFB_COUNT(sc, SFB_C_DIFF_CP, 1);
                 code[k] = SFB_ASSIGN_DIFF;
@@ -661,18 +754,20 @@ __device__ __forceinline__ void mask_classify_pair(TileS& T, const Dev& d, TileO
     }
 }
 
-// every tuple of mate k whose path is in `sel`: apply(share(p), times(p))
+// every tuple of mate k whose path is in `sel` becomes a work item of share record `rec`, times(p) times
 template <class W>
-__device__ __forceinline__ void mask_apply(TileS& T, const Dev& d, TileOps& ops, const Mate& m, const MaskMate& mk, u64 sel,
-                                           W&& weight) {
-    for (int q = 0; q < 2 * mk.na; ++q)
-        for (u64 rest = T.amask[2 * mk.row + q] & sel; rest; rest &= rest - 1) {
+__device__ __forceinline__ void mask_list(TileS& T, const Dev& d, TileOps& ops, const Mate& m, int row, int n_masks, u64 sel,
+                                          long long total, int n, W&& times_of_path) {
+    const int rec = ops.record(total, n, m.seq_len);
+    for (int q = 0; q < n_masks; ++q)
+        for (u64 rest = T.amask[2 * row + q] & sel; rest; rest &= rest - 1) {
             const int p = __ffsll((long long)rest) - 1;
             const i64 a = m.a0 + (q >> 1);
-            double ratio;
-            int times;
-            weight(p, ratio, times);
-            ops.apply(d, a, mask_code(T, d.r, a, p, (q & 1) != 0), T.p0 + p, m.seq_len, ratio, times);
+            const int times = times_of_path(p);
+            if (ops.list_share(a, ((uint32_t)p << 16) | (uint32_t)(q & 1), times, rec)) continue;
+            ops.st->app -= 1;                // a list is full: the share here and now
+            ops.apply_now(d, a, (int)(mask_code(T, d.r, a, p, (q & 1) != 0) & SFB_SLOT_MASK) - T.s0, p, m.seq_len,
+                          ratio_of(T.pU[p], total, n), times);
         }
 }
 
@@ -693,10 +788,7 @@ __device__ __forceinline__ void mask_pass2_pair(TileS& T, const Dev& d, TileOps&
             }
             SFB_COUNT(sc, SFB_C_ASSIGNED_M, 1);
             code[k] = SFB_P2_ASSIGNED;
-            mask_apply(T, d, ops, mt[k], mm[k], inter, [&](int p, double& ratio, int& times) {
-                ratio = ratio_of(T.pU[p], total, n_inter);
-                times = 1;
-            });
+            mask_list(T, d, ops, mt[k], mm[k].row, 2 * mm[k].na, inter, total, n_inter, [](int) { return 1; });
         }
         return;
     }
@@ -727,10 +819,8 @@ __device__ __forceinline__ void mask_pass2_pair(TileS& T, const Dev& d, TileOps&
         }
         SFB_COUNT(sc, SFB_C_ASSIGNED_M, 1);
         code[k] = SFB_P2_ASSIGNED;
-        mask_apply(T, d, ops, mt[k], mm[k], sel, [&](int p, double& ratio, int& times) {
-            ratio = ratio_of(T.pU[p], tot, nn);
-            times = mask_times(d.g, T, mm, cut.common0, p);
-        });
+        mask_list(T, d, ops, mt[k], mm[k].row, 2 * mm[k].na, sel, tot, nn,
+                  [&](int p) { return mask_times(d.g, T, mm, cut.common0, p); });
     }
 }
 
@@ -769,9 +859,9 @@ __device__ __noinline__ void tile_export(const TileS& T, const Dev& d, BlockCoun
     d.w.slow[atomicAdd(d.w.cursor + 3, 1ull)] = (int32_t)g;
 }
 
-// ---- phase C of pass 1, one read group (json2csv.py:828-1053) ----------------------------------------------------
+// ---- phase C of pass 1, one read group (json2csv.py:828-1053); row0 = row of its first alignment ------------------
 template <int KA>
-__device__ __forceinline__ void tile_group1(TileS& T, const Dev& d, BlockCounters& sc, i64 g, TileStats& st) {
+__device__ __forceinline__ void tile_group1(TileS& T, const Dev& d, BlockCounters& sc, i64 g, int row0, TileStats& st) {
     const int nm = d.r.grp_nmates[g];
     Mate mt[2];
     mate_load(d.r, g, 0, mt[0]);
@@ -799,12 +889,12 @@ __device__ __forceinline__ void tile_group1(TileS& T, const Dev& d, BlockCounter
             MaskMate mm[2];
             int nt[2];
             if (T.simple) {
-                mm[0].load(T, mt[0]);
-                mm[1].load(T, mt[1]);
+                mm[0].load(T, row0, mt[0].na);
+                mm[1].load(T, row0 + mt[0].na, mt[1].na);
                 nt[0] = mm[0].nt;
                 nt[1] = mm[1].nt;
             } else {
-                if (!v.load(T, mt) || mt[0].na > 255 || mt[1].na > 255) {
+                if (!v.load(T, mt, row0) || mt[0].na > 255 || mt[1].na > 255) {
                     tile_export(T, d, sc, g, mt, st);
                     return;
                 }
@@ -847,7 +937,7 @@ __device__ __forceinline__ void tile_group1(TileS& T, const Dev& d, BlockCounter
             defer = true;
             code[single] = SFB_DEFER;
         } else {
-            const int row = (int)(m.a0 - T.a0c);
+            const int row = row0 + (single ? mt[0].na : 0);
             const int n = T.simple ? __popcll(T.amask[2 * row]) + __popcll(T.amask[2 * row + 1])
                                    : T.cnt[row];                 // kOver: more than KA, in any case more than one
             if (n > 1) {
@@ -872,14 +962,14 @@ __device__ __forceinline__ void tile_group1(TileS& T, const Dev& d, BlockCounter
 
 // ---- phase C of pass 2, one deferred read group (json2csv.py:1085-1274) -----------------------------------------
 template <int KA>
-__device__ __forceinline__ void tile_group2(TileS& T, const Dev& d, BlockCounters& sc, i64 g, TileStats& st) {
+__device__ __forceinline__ void tile_group2(TileS& T, const Dev& d, BlockCounters& sc, i64 g, int row0, TileStats& st) {
     const int nm = d.r.grp_nmates[g];
     Mate mt[2];
     mate_load(d.r, g, 0, mt[0]);
     mate_load(d.r, g, 1, mt[1]);
     int code[2] = {SFB_P2_NONE, SFB_P2_NONE};
     int single = nm == 1 ? 0 : -1;
-    TileOps ops{&T, &st, tile_app_cap(KA)};
+    TileOps ops{&T, &st, tile_list_cap(2)};
     if (nm == 2) {
         if (mt[0].na == 0 || mt[1].na == 0) {
             single = mt[0].na == 0 ? 1 : 0;                                  // json2csv.py:1088-1093
@@ -888,12 +978,12 @@ __device__ __forceinline__ void tile_group2(TileS& T, const Dev& d, BlockCounter
             MaskMate mm[2];
             int nt[2];
             if (T.simple) {
-                mm[0].load(T, mt[0]);
-                mm[1].load(T, mt[1]);
+                mm[0].load(T, row0, mt[0].na);
+                mm[1].load(T, row0 + mt[0].na, mt[1].na);
                 nt[0] = mm[0].nt;
                 nt[1] = mm[1].nt;
             } else {
-                if (!v.load(T, mt) || mt[0].na > 255 || mt[1].na > 255) return;  // handed over in pass 1: sfb_pass2 has it
+                if (!v.load(T, mt, row0) || mt[0].na > 255 || mt[1].na > 255) return;  // handed over in pass 1: sfb_pass2 has it
                 nt[0] = v.n[0];
                 nt[1] = v.n[1];
             }
@@ -916,7 +1006,7 @@ __device__ __forceinline__ void tile_group2(TileS& T, const Dev& d, BlockCounter
         int n_all = 0;
         for (int j = 0; j < m.na; ++j) {
             const i64 a = m.a0 + j;
-            const int row = (int)(a - T.a0c);
+            const int row = row0 + (single ? mt[0].na : 0) + j;
             if (T.simple) {
                 const u64 f = T.amask[2 * row], rv = T.amask[2 * row + 1];
                 const int cnt = __popcll(f) + __popcll(rv);
@@ -926,13 +1016,11 @@ __device__ __forceinline__ void tile_group2(TileS& T, const Dev& d, BlockCounter
                     for (u64 rest = q ? rv : f; rest; rest &= rest - 1) {
                         const int p = __ffsll((long long)rest) - 1;
                         total += T.pU[p];
-                        ops.hist(d, sc, T.p0 + p, a);                        // :1246-1252
+                        tile_hist(T, d, sc, p, a);                           // :1246-1252
                     }
-                for (int q = 0; q < 2; ++q)
-                    for (u64 rest = q ? rv : f; rest; rest &= rest - 1) {
-                        const int p = __ffsll((long long)rest) - 1;
-                        ops.apply(d, a, mask_code(T, d.r, a, p, q != 0), T.p0 + p, m.seq_len, ratio_of(T.pU[p], total, cnt), 1);
-                    }
+                Mate one = m;                                                // this alignment alone
+                one.a0 = a;
+                mask_list(T, d, ops, one, row, 2, ~0ull, total, cnt, [](int) { return 1; });
                 n_all += cnt;
                 continue;
             }
@@ -947,7 +1035,7 @@ __device__ __forceinline__ void tile_group2(TileS& T, const Dev& d, BlockCounter
                     const int p = T.spath[s];
                     total += T.pU[p];
                     ++c2;
-                    ops.hist(d, sc, T.p0 + p, a);                            // :1246-1252
+                    tile_hist(T, d, sc, p, a);
                 });
                 tile_enum(T, d.r, w0, L, st, [&](int s, bool rev) {
                     const int p = T.spath[s];
@@ -962,7 +1050,7 @@ __device__ __forceinline__ void tile_group2(TileS& T, const Dev& d, BlockCounter
             for (int i = 0; i < cnt; ++i) {
                 const int p = T.spath[tp[i] & 0x7fffu];
                 total += T.pU[p];
-                ops.hist(d, sc, T.p0 + p, a);                                // :1246-1252
+                tile_hist(T, d, sc, p, a);
             }
             for (int i = 0; i < cnt; ++i) {
                 const int s = tp[i] & 0x7fffu, p = T.spath[s];
@@ -976,6 +1064,14 @@ __device__ __forceinline__ void tile_group2(TileS& T, const Dev& d, BlockCounter
 }
 
 // ---- kernels ----------------------------------------------------------------------------------------------------
+// end of the window of read groups that starts at g0: at most kTT groups and at most `cap` alignments (block-uniform)
+__device__ __forceinline__ i64 tile_window(const sfb_reads& r, i64 g0, i64 g_end, int cap, int groups = kTT) {
+    i64 g1 = min(g0 + groups, g_end);
+    const i64 a0 = r.grp_aln_off[2 * g0];
+    while (g1 - g0 > 1 && r.grp_aln_off[2 * g1] - a0 > cap) g1 = g0 + (g1 - g0) / 2;
+    return g1;
+}
+
 #ifndef SFB_TILE_MINBLK
 #define SFB_TILE_MINBLK 3
 #endif
@@ -987,6 +1083,7 @@ __global__ void __launch_bounds__(kTT, SFB_TILE_MINBLK) k_tile_pass(const __grid
     BlockCounters& sc = *T.sc;
     block_counters_zero(sc);
     TileStats st{0, 0, 0, 0, 0, 0};
+    float apg = 5.0f, dfrac = 0.3f;      // pass 2: running averages that size a round (block-uniform)
     const int4* items = reinterpret_cast<const int4*>(t.items);
     const int tid = threadIdx.x;
     for (;;) {
@@ -997,69 +1094,78 @@ __global__ void __launch_bounds__(kTT, SFB_TILE_MINBLK) k_tile_pass(const __grid
         if (item >= (int)t.n_items) break;
         const int4 it = items[item];
         tile_stage<PASS>(T, d, t, it.x, U);
+        T.a_item = d.r.grp_aln_off[2 * (i64)it.y];
         for (i64 g0 = it.y; g0 < (i64)it.z;) {
-            // a chunk: up to kTT read groups whose alignments fit the tuple store (block-uniform arithmetic)
-            i64 g1 = min(g0 + kTT, (i64)it.z);
-            T.a0c = d.r.grp_aln_off[2 * g0];
-            while (g1 - g0 > 1 && d.r.grp_aln_off[2 * g1] - T.a0c > kAC) g1 = g0 + (g1 - g0) / 2;
-            const int nA = (int)(d.r.grp_aln_off[2 * g1] - T.a0c);
-            if (nA > kAC) {            // one group with more alignments than a chunk holds: not in tile order as staged
-                if (tid == 0) SFB_COUNT(sc, SFB_C_MATCH_OVERFLOW, 1);      // (sfb_tile_permute keeps such groups out)
-                g0 = g1;
-                continue;
-            }
-            if (tid < 3) T.misc[1 + tid] = 0;
+            if (tid < 4) T.misc[1 + tid] = 0;
             __syncthreads();
             if (PASS == 1) {
-                if (T.simple) for (int i = tid; i < nA; i += kTT) mask_match_aln(T, d.r, i, st);
-                else for (int i = tid; i < nA; i += kTT) tile_match_aln<KA>(T, d.r, i, st);
+                const i64 g1 = tile_window(d.r, g0, it.z, kRows1);
+                T.a_row0 = d.r.grp_aln_off[2 * g0];
+                const int nA = (int)(d.r.grp_aln_off[2 * g1] - T.a_row0);
+                if (nA > kRows1) {         // one group with more alignments than a window holds: not in tile order as staged
+                    if (tid == 0) SFB_COUNT(sc, SFB_C_MATCH_OVERFLOW, 1);      // (sfb_tile_permute keeps such groups out)
+                    g0 = g1;
+                    continue;
+                }
+                // M
+                if (T.simple) for (int i = tid; i < nA; i += kTT) mask_match_aln(T, d.r, i, T.a_row0 + i, st);
+                else for (int i = tid; i < nA; i += kTT) tile_match_aln<KA>(T, d.r, i, T.a_row0 + i, st);
                 __syncthreads();
-                if (g0 + tid < g1) tile_group1<KA>(T, d, sc, g0 + tid, st);
+                // C
+                if (g0 + tid < g1) tile_group1<KA>(T, d, sc, g0 + tid, (int)(d.r.grp_aln_off[2 * (g0 + tid)] - T.a_row0), st);
                 __syncthreads();
+                // S
                 const int n_asg = T.misc[1];
-                for (int q = tid; q < n_asg; q += kTT) {
-                    const uint32_t e = T.lst[q];
-                    const i64 a = T.a0c + (e >> 16);
-                    const i64 w0 = d.r.aln_walk_off[a];
-                    const int L = (int)(d.r.aln_walk_off[a + 1] - w0);
-                    tile_add_records(T, d.r, w0, L, (int)(e & 0xffffu), true, 1.0);
-                    st.rec += L;
-                }
+                for (int q = tid; q < n_asg; q += kTT) tile_scatter1(T, d, sc, q, st);
+                g0 = g1;
             } else {
-                // D: the deferred groups of the chunk and their alignments
-                if (g0 + tid < g1) {
-                    const i64 g = g0 + tid;
-                    const int c1 = d.w.grp_code[g];
-                    if ((c1 & 0xf) == SFB_DEFER || (c1 >> 4) == SFB_DEFER) {
-                        T.glist[atomicAdd(&T.misc[3], 1)] = (uint16_t)tid;
-                        const int r0 = (int)(d.r.grp_aln_off[2 * g] - T.a0c), r1 = (int)(d.r.grp_aln_off[2 * g + 2] - T.a0c);
-                        const int q = atomicAdd(&T.misc[2], r1 - r0);
-                        for (int j = r0; j < r1; ++j) T.alist[q + j - r0] = (uint16_t)j;
+                // D: windows of read groups until the deferred groups listed should fill phase S's list (apg = work
+                //    items per deferred group, dfrac = share of deferred groups, running averages of this block)
+                const int target = max(8, min(kTT, (int)(0.7f * (float)tile_list_cap(2) / apg)));
+                for (;;) {
+                    const int want = max(16, min(kTT, (int)((float)(target - T.misc[3]) / fmaxf(dfrac, 0.03f))));
+                    const i64 g1 = tile_window(d.r, g0, it.z, kWin2, want);
+                    const i64 a0 = d.r.grp_aln_off[2 * g0];
+                    const int before = T.misc[3];
+                    __syncthreads();       // everyone has read the fill
+                    if (d.r.grp_aln_off[2 * g1] - a0 > kWin2) {                // see above
+                        if (tid == 0) SFB_COUNT(sc, SFB_C_MATCH_OVERFLOW, 1);
+                    } else if (g0 + tid < g1) {
+                        const i64 g = g0 + tid;
+                        const int c1 = d.w.grp_code[g];
+                        if ((c1 & 0xf) == SFB_DEFER || (c1 >> 4) == SFB_DEFER) {
+                            const i64 ga = d.r.grp_aln_off[2 * g];
+                            const int na = (int)(d.r.grp_aln_off[2 * g + 2] - ga);
+                            const int slot = atomicAdd(&T.misc[3], 1), row = atomicAdd(&T.misc[2], na);
+                            T.glist[slot] = (uint32_t)(g - it.y);
+                            T.grow[slot] = (uint16_t)row;
+                            for (int j = 0; j < na; ++j) T.alist[row + j] = (uint32_t)(ga + j - T.a_item);
+                        }
                     }
+                    __syncthreads();
+                    dfrac = 0.5f * dfrac + 0.5f * (float)(T.misc[3] - before) / (float)(g1 - g0);
+                    g0 = g1;
+                    if (g0 >= (i64)it.z || T.misc[3] >= target - target / 8 || T.misc[3] + kTT > kGrp2 || T.misc[2] + kWin2 > kRows2)
+                        break;
                 }
-                __syncthreads();
                 const int n_aln = T.misc[2], n_grp = T.misc[3];
+                // M
                 {
                     const int seen = st.tuples;                       // counted in pass 1
-                    if (T.simple) for (int q = tid; q < n_aln; q += kTT) mask_match_aln(T, d.r, T.alist[q], st);
-                    else for (int q = tid; q < n_aln; q += kTT) tile_match_aln<KA>(T, d.r, T.alist[q], st);
+                    if (T.simple) for (int q = tid; q < n_aln; q += kTT) mask_match_aln(T, d.r, q, T.a_item + T.alist[q], st);
+                    else for (int q = tid; q < n_aln; q += kTT) tile_match_aln<KA>(T, d.r, q, T.a_item + T.alist[q], st);
                     st.tuples = seen;
                 }
                 __syncthreads();
-                if (tid < n_grp) tile_group2<KA>(T, d, sc, g0 + T.glist[tid], st);
+                // C
+                for (int q = tid; q < n_grp; q += kTT) tile_group2<KA>(T, d, sc, (i64)it.y + T.glist[q], T.grow[q], st);
                 __syncthreads();
-                const int n_app = min(T.misc[1], tile_app_cap(KA));
-                for (int q = tid; q < n_app; q += kTT) {
-                    const uint32_t e = T.appk[q];
-                    const i64 a = T.a0c + (e >> 16);
-                    const i64 w0 = d.r.aln_walk_off[a];
-                    const int L = (int)(d.r.aln_walk_off[a + 1] - w0);
-                    tile_add_records(T, d.r, w0, L, (int)(e & 0xffffu), false, T.appw[q]);
-                    st.rec += L;
-                }
+                // S: per-path sums (json2csv.py:1155-1156) and node loop (:1157-1158) of every work item
+                const int n_app = min(T.misc[1], tile_list_cap(2));
+                if (n_grp) apg = 0.5f * apg + 0.5f * (float)T.misc[1] / (float)n_grp;
+                for (int q = tid; q < n_app; q += kTT) tile_scatter2(T, d, q, st);
             }
             __syncthreads();
-            g0 = g1;
         }
         tile_flush<PASS>(T, d, sc);
     }

@@ -18,7 +18,8 @@ for r in rows:
         continue
     g = lambda name: r[hdr.index(name)]                         # noqa: E731
     try:
-        out.append((int(g("# Samples")), int(g("Instructions Executed")), float(g("Avg. Threads Executed") or 0), cur, r[0], r[1].strip()[:110]))
+        ie = int(g("Instructions Executed"))
+        out.append((int(g("# Samples")), ie, int(g("Thread Instructions Executed")) / max(1, ie), cur, r[0], r[1].strip()[:110]))
     except ValueError:
         pass
 tot_s, tot_i = sum(o[0] for o in out), sum(o[1] for o in out)
