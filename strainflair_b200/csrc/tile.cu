@@ -36,14 +36,15 @@ constexpr int kOver = 255;            // tuple count of an alignment with more t
 constexpr uint32_t kHasSlot = 0x80000000u;   // list entry carries its slot (tuple tiles); else phase S looks it up
 
 __host__ __device__ inline int tile_rows(int pass) { return pass == 1 ? kRows1 : kRows2; }
-__host__ __device__ inline int tile_list_cap(int pass) { return pass == 1 ? kRows1 : 6 * kTT; }   // entries of phase S's list
+__host__ __device__ inline int tile_list_cap(int pass) { return pass == 1 ? kRows1 + kTT : 6 * kTT; }   // entries of phase S's list
+constexpr int kStageRec = 16 * kTT;   // pass 1: walk records of a window staged in shared memory (local node ids)
 constexpr int kRec2 = 2 * kTT;        // pass 2: share records per round (total and count of a candidate set)
 __host__ __device__ inline int tile_reps(int mp) { return mp <= 32 ? 8 : mp <= 64 ? 4 : 1; }       // copies of the per-path sums
 
 // ---- shared-memory layout, sized by the largest tile (same arithmetic on host and device) -----------------------
 struct TileLayout {
     unsigned hkey, pseq, pU, rec, emask, nmask, store, bins, plimb, la, lx, lseq, alist, glist, pclu, pstr0, pnstr, hcnt, sc, misc,
-        lt, lm, grow, poff, node, occ, occ_off, eoff, esucc, spath, cnt, total;
+        lt, lm, grow, woff, wnode, goff, poff, node, occ, occ_off, eoff, esucc, spath, cnt, total;
 };
 __host__ __device__ inline TileLayout tile_layout(int pass, int ms, int mn, int mp, int me, int KA) {
     TileLayout L;
@@ -76,6 +77,9 @@ __host__ __device__ inline TileLayout tile_layout(int pass, int ms, int mn, int 
     L.lt = take(pass == 2 ? 2u * cap : 0);      // list of phase S: times (pass 2) ...
     L.lm = take(pass == 2 ? 2u * cap : 0);      // ... and share record
     L.grow = take(pass == 2 ? 2u * kGrp2 : 0);  // pass 2: first row of a listed group
+    L.woff = take(pass == 1 ? 4u * (kRows1 + 1) : 0);   // pass 1: walk offsets of the window's alignments (from its first record)
+    L.wnode = take(pass == 1 ? 2u * kStageRec : 0);     // pass 1: local node ids of the window's first kStageRec records
+    L.goff = take(4u * (kTT + 1));                      // alignment offsets of the next kTT groups (from the first one)
     L.poff = take(2u * (mp + 1));
     L.node = take(2u * (ms + 2));
     L.occ = take(2u * ms);
@@ -112,6 +116,9 @@ struct TileS {
     uint16_t* lt;
     uint16_t* lm;
     uint16_t* grow;
+    uint32_t* woff;
+    uint16_t* wnode;
+    uint32_t* goff;
     uint16_t* poff;
     uint16_t* node;
     uint16_t* occ;
@@ -125,6 +132,7 @@ struct TileS {
     bool simple;
     i64 a_item;          // first alignment of the work item
     i64 a_row0;          // pass 1: alignment of row 0 of the window
+    i64 w_row0;          // pass 1: first walk record of the window
 };
 __device__ __forceinline__ TileS tile_carve(int pass, unsigned char* smem, const sfb_tiles& t) {
     const TileLayout L = tile_layout(pass, (int)t.max_slots, (int)t.max_nodes, (int)t.max_paths, (int)t.max_edges, (int)t.tuple_cap);
@@ -152,6 +160,9 @@ __device__ __forceinline__ TileS tile_carve(int pass, unsigned char* smem, const
     T.misc = reinterpret_cast<int*>(smem + L.misc);
     T.lt = reinterpret_cast<uint16_t*>(smem + L.lt);
     T.lm = reinterpret_cast<uint16_t*>(smem + L.lm);
+    T.woff = reinterpret_cast<uint32_t*>(smem + L.woff);
+    T.wnode = reinterpret_cast<uint16_t*>(smem + L.wnode);
+    T.goff = reinterpret_cast<uint32_t*>(smem + L.goff);
     T.grow = reinterpret_cast<uint16_t*>(smem + L.grow);
     T.poff = reinterpret_cast<uint16_t*>(smem + L.poff);
     T.node = reinterpret_cast<uint16_t*>(smem + L.node);
@@ -165,7 +176,7 @@ __device__ __forceinline__ TileS tile_carve(int pass, unsigned char* smem, const
     T.mp = (int)t.max_paths;
     T.reps = tile_reps(T.mp);
     T.simple = false;
-    T.a_item = T.a_row0 = 0;
+    T.a_item = T.a_row0 = T.w_row0 = 0;
     return T;
 }
 
@@ -553,6 +564,7 @@ __device__ __forceinline__ void tile_scatter1(TileS& T, const Dev& d, BlockCount
 }
 // phase S of pass 2: one work item (json2csv.py:1155-1158)
 __device__ __forceinline__ void tile_scatter2(TileS& T, const Dev& d, int q, TileStats& st) {
+    if (T.lt[q] == 0) return;                                // reserved, then applied at once (a table was full)
     const i64 a = T.a_item + T.la[q];
     const uint32_t x = T.lx[q];
     const int p = (int)((x >> 16) & 0xffu);
@@ -581,23 +593,42 @@ __device__ __forceinline__ void tile_scatter2(TileS& T, const Dev& d, int q, Til
 // tuple order of the reference (json2csv.py:851-866: alignment by alignment, forward matches by ascending path, then
 // reverse) only matters for picking "the first" tuple; sums are exact integers here, so their order is free.
 __device__ __forceinline__ u64 tile_step(const TileS& T, unsigned n, unsigned succ) {
-    for (int e = T.eoff[n]; e < (int)T.eoff[n + 1]; ++e)
-        if (T.esucc[e] == succ) return T.emask[e];
-    return 0ull;
+    const int e0 = T.eoff[n], e1 = T.eoff[n + 1];
+    // almost every node has one or two successors: two predicated probes, no loop
+    u64 m = 0;
+    if (e0 < e1 && T.esucc[e0] == succ) m = T.emask[e0];
+    if (e0 + 1 < e1 && T.esucc[e0 + 1] == succ) m = T.emask[e0 + 1];
+    for (int e = e0 + 2; e < e1; ++e)
+        if (T.esucc[e] == succ) m = T.emask[e];
+    return m;
 }
-// phase M: forward / reverse path sets of alignment `a` into row `row`
+// phase M: forward / reverse path sets of alignment `a` into row `row`.  STAGED (pass 1): the walk offsets and the first
+// kStageRec records of the window are in shared memory.
+template <bool STAGED>
 __device__ __forceinline__ void mask_match_aln(const TileS& T, const sfb_reads& r, int row, i64 a, TileStats& st) {
-    const i64 w0 = r.aln_walk_off[a];
-    const int L = (int)(r.aln_walk_off[a + 1] - w0);
+    i64 w0;
+    int L;
+    if (STAGED) {
+        w0 = T.w_row0 + T.woff[row];
+        L = (int)(T.woff[row + 1] - T.woff[row]);
+    } else {
+        w0 = r.aln_walk_off[a];
+        L = (int)(r.aln_walk_off[a + 1] - w0);
+    }
+    const unsigned rel = STAGED ? T.woff[row] : 0u;
+    auto node_at = [&](int k) -> unsigned {
+        if (STAGED && rel + (unsigned)k < (unsigned)kStageRec) return T.wnode[rel + k];
+        return tile_local(T, r.walk_node[w0 + k]);
+    };
     u64 f = 0, rv = 0;
     if (L > 0) {
-        unsigned prev = tile_local(T, r.walk_node[w0]);
+        unsigned prev = node_at(0);
         if (L == 1) {
             if (prev != kNoNode) f = T.nmask[prev];
         } else if (prev != kNoNode) {
             f = rv = ~0ull;
             for (int k = 1; k < L; ++k) {
-                const unsigned n = tile_local(T, r.walk_node[w0 + k]);
+                const unsigned n = node_at(k);
                 if (n == kNoNode) { f = rv = 0; break; }
                 if (f) f &= tile_step(T, prev, n);
                 if (rv) rv &= tile_step(T, n, prev);
@@ -758,14 +789,26 @@ __device__ __forceinline__ void mask_classify_pair(TileS& T, const Dev& d, TileO
 template <class W>
 __device__ __forceinline__ void mask_list(TileS& T, const Dev& d, TileOps& ops, const Mate& m, int row, int n_masks, u64 sel,
                                           long long total, int n, W&& times_of_path) {
+    int cnt = 0;
+    for (int q = 0; q < n_masks; ++q) cnt += __popcll(T.amask[2 * row + q] & sel);
+    if (cnt == 0) return;
     const int rec = ops.record(total, n, m.seq_len);
+    int at = atomicAdd(&T.misc[1], cnt);             // one reservation per candidate set, not one per work item
+    ops.st->app += cnt;
     for (int q = 0; q < n_masks; ++q)
-        for (u64 rest = T.amask[2 * row + q] & sel; rest; rest &= rest - 1) {
+        for (u64 rest = T.amask[2 * row + q] & sel; rest; rest &= rest - 1, ++at) {
             const int p = __ffsll((long long)rest) - 1;
             const i64 a = m.a0 + (q >> 1);
             const int times = times_of_path(p);
-            if (ops.list_share(a, ((uint32_t)p << 16) | (uint32_t)(q & 1), times, rec)) continue;
+            if (rec >= 0 && at < ops.cap && times <= 0xffff) {
+                T.la[at] = (uint32_t)(a - T.a_item);
+                T.lx[at] = ((uint32_t)p << 16) | (uint32_t)(q & 1);
+                T.lt[at] = (uint16_t)times;
+                T.lm[at] = (uint16_t)rec;
+                continue;
+            }
             ops.st->app -= 1;                // a list is full: the share here and now
+            if (at < ops.cap) T.lt[at] = 0;  // (a reserved entry that stays empty)
             ops.apply_now(d, a, (int)(mask_code(T, d.r, a, p, (q & 1) != 0) & SFB_SLOT_MASK) - T.s0, p, m.seq_len,
                           ratio_of(T.pU[p], total, n), times);
         }
@@ -866,8 +909,6 @@ __device__ __forceinline__ void tile_group1(TileS& T, const Dev& d, BlockCounter
     Mate mt[2];
     mate_load(d.r, g, 0, mt[0]);
     mate_load(d.r, g, 1, mt[1]);
-    for (int k = 0; k < 2; ++k)
-        for (int j = 0; j < mt[k].na; ++j) d.w.aln_assign[mt[k].a0 + j] = -1;
     int code[2] = {SFB_ABSENT, SFB_ABSENT};
     bool defer = false;
     SFB_COUNT(sc, SFB_C_NB_READS, nm);
@@ -1064,12 +1105,58 @@ __device__ __forceinline__ void tile_group2(TileS& T, const Dev& d, BlockCounter
 }
 
 // ---- kernels ----------------------------------------------------------------------------------------------------
-// end of the window of read groups that starts at g0: at most kTT groups and at most `cap` alignments (block-uniform)
-__device__ __forceinline__ i64 tile_window(const sfb_reads& r, i64 g0, i64 g_end, int cap, int groups = kTT) {
-    i64 g1 = min(g0 + groups, g_end);
+// End of the window of read groups that starts at g0: at most `groups` groups and at most `cap` alignments, trimmed to
+// at most `want` alignments when want > 0 (whole iterations of phase M).  The offsets of the candidate groups are staged
+// in shared memory with one coalesced load, the searches then run there.  Block-uniform; ends with a barrier.
+__device__ __forceinline__ i64 tile_window(TileS& T, const sfb_reads& r, i64 g0, i64 g_end, int cap, int groups = kTT, int want = 0) {
+    const int n = (int)min((i64)groups, g_end - g0);
     const i64 a0 = r.grp_aln_off[2 * g0];
-    while (g1 - g0 > 1 && r.grp_aln_off[2 * g1] - a0 > cap) g1 = g0 + (g1 - g0) / 2;
-    return g1;
+    for (int i = threadIdx.x; i <= n; i += kTT) {
+        const i64 v = r.grp_aln_off[2 * (g0 + i)] - a0;
+        T.goff[i] = (uint32_t)min(v, (i64)0x7fffffff);
+    }
+    __syncthreads();
+    int lim = cap;
+    if (want > 0 && want < cap && (int)T.goff[1] <= want) lim = want;        // (a first group above `want` keeps `cap`)
+    int lo = 1, hi = n;                      // largest k in [1, n] with goff[k] <= lim (k = 1 whatever the first group has)
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if ((int)T.goff[mid] <= lim) lo = mid; else hi = mid - 1;
+    }
+    return g0 + lo;
+}
+// the arrays of read groups [g0, g1) on their way to the L2 (they stream from HBM, every byte is used once)
+__device__ __forceinline__ void tile_prefetch(const sfb_reads& r, i64 g0, i64 g1, i64 g_end) {
+    g1 = min(g1, g_end);
+    if (g0 >= g1) return;
+    auto lines = [&](const void* base, size_t lo, size_t hi) {       // bytes [lo, hi) of an array, one line per thread
+        const char* p = (const char*)base;
+        for (size_t b = (lo & ~(size_t)127) + 128 * (size_t)threadIdx.x; b < hi; b += 128 * (size_t)kTT)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p + b));
+    };
+    lines(r.grp_aln_off, 16 * (size_t)g0, 16 * (size_t)g1 + 8);
+    lines(r.grp_nmates, (size_t)g0, (size_t)g1);
+    lines(r.mate_seq_len, 8 * (size_t)g0, 8 * (size_t)g1);
+}
+__device__ __forceinline__ void tile_prefetch_alns(const sfb_reads& r, i64 a0, i64 a1) {
+    if (a0 >= a1) return;
+    auto lines = [&](const void* base, size_t lo, size_t hi) {
+        const char* p = (const char*)base;
+        for (size_t b = (lo & ~(size_t)127) + 128 * (size_t)threadIdx.x; b < hi; b += 128 * (size_t)kTT)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p + b));
+    };
+    lines(r.aln_walk_off, 8 * (size_t)a0, 8 * (size_t)a1 + 8);
+    lines(r.aln_bins, 5 * (size_t)a0, 5 * (size_t)a1);
+}
+__device__ __forceinline__ void tile_prefetch_recs(const sfb_reads& r, i64 w0, i64 w1) {
+    if (w0 >= w1) return;
+    auto lines = [&](const void* base, size_t lo, size_t hi) {
+        const char* p = (const char*)base;
+        for (size_t b = (lo & ~(size_t)127) + 128 * (size_t)threadIdx.x; b < hi; b += 128 * (size_t)kTT)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p + b));
+    };
+    lines(r.walk_node, 4 * (size_t)w0, 4 * (size_t)w1);
+    lines(r.walk_alen, 4 * (size_t)w0, 4 * (size_t)w1);
 }
 
 #ifndef SFB_TILE_MINBLK
@@ -1095,11 +1182,12 @@ __global__ void __launch_bounds__(kTT, SFB_TILE_MINBLK) k_tile_pass(const __grid
         const int4 it = items[item];
         tile_stage<PASS>(T, d, t, it.x, U);
         T.a_item = d.r.grp_aln_off[2 * (i64)it.y];
+        if (tid == 0) T.misc[1] = 0;
         for (i64 g0 = it.y; g0 < (i64)it.z;) {
-            if (tid < 4) T.misc[1 + tid] = 0;
+            if (tid < 4 && (PASS == 2 || tid > 0)) T.misc[1 + tid] = 0;
             __syncthreads();
             if (PASS == 1) {
-                const i64 g1 = tile_window(d.r, g0, it.z, kRows1);
+                const i64 g1 = tile_window(T, d.r, g0, it.z, kRows1, kTT, 2 * kTT);
                 T.a_row0 = d.r.grp_aln_off[2 * g0];
                 const int nA = (int)(d.r.grp_aln_off[2 * g1] - T.a_row0);
                 if (nA > kRows1) {         // one group with more alignments than a window holds: not in tile order as staged
@@ -1107,24 +1195,48 @@ __global__ void __launch_bounds__(kTT, SFB_TILE_MINBLK) k_tile_pass(const __grid
                     g0 = g1;
                     continue;
                 }
+                // the window's walk offsets and records into shared memory (coalesced), aln_assign = "none"
+                T.w_row0 = d.r.aln_walk_off[T.a_row0];
+                for (int i = tid; i <= nA; i += kTT) T.woff[i] = (uint32_t)(d.r.aln_walk_off[T.a_row0 + i] - T.w_row0);
+                for (int i = tid; i < nA; i += kTT) d.w.aln_assign[T.a_row0 + i] = -1;
+                {
+                    const int nR = (int)min((i64)kStageRec, d.r.aln_walk_off[T.a_row0 + nA] - T.w_row0);
+                    for (int i = tid; i < nR; i += kTT) T.wnode[i] = (uint16_t)tile_local(T, d.r.walk_node[T.w_row0 + i]);
+                }
+                {   // the next window (about as large as this one) on its way to the L2 while this one is worked on
+                    const i64 g2 = min(g1 + (g1 - g0), (i64)it.z);
+                    const i64 a1 = T.a_row0 + nA, w1 = d.r.aln_walk_off[a1];
+                    tile_prefetch(d.r, g1, g2, it.z);
+                    tile_prefetch_alns(d.r, a1, min(a1 + nA, d.r.n_alns));
+                    tile_prefetch_recs(d.r, w1, min(w1 + (w1 - T.w_row0), d.r.n_records));
+                }
+                __syncthreads();
                 // M
-                if (T.simple) for (int i = tid; i < nA; i += kTT) mask_match_aln(T, d.r, i, T.a_row0 + i, st);
+                if (T.simple) for (int i = tid; i < nA; i += kTT) mask_match_aln<true>(T, d.r, i, T.a_row0 + i, st);
                 else for (int i = tid; i < nA; i += kTT) tile_match_aln<KA>(T, d.r, i, T.a_row0 + i, st);
                 __syncthreads();
                 // C
                 if (g0 + tid < g1) tile_group1<KA>(T, d, sc, g0 + tid, (int)(d.r.grp_aln_off[2 * (g0 + tid)] - T.a_row0), st);
                 __syncthreads();
-                // S
-                const int n_asg = T.misc[1];
-                for (int q = tid; q < n_asg; q += kTT) tile_scatter1(T, d, sc, q, st);
+                // S: whole iterations only; the rest of the list stays for the next window (the last one takes all)
                 g0 = g1;
+                const int n_asg = T.misc[1];
+                const int full = g0 >= (i64)it.z ? n_asg : (n_asg / kTT) * kTT;
+                for (int q = tid; q < full; q += kTT) tile_scatter1(T, d, sc, q, st);
+                uint32_t ka = 0, kx = 0;
+                int ks = 0;
+                const bool keep = full + tid < n_asg;
+                if (keep) { ka = T.la[full + tid]; kx = T.lx[full + tid]; ks = T.lseq[full + tid]; }
+                __syncthreads();
+                if (keep) { T.la[tid] = ka; T.lx[tid] = kx; T.lseq[tid] = ks; }
+                if (tid == 0) T.misc[1] = n_asg - full;
             } else {
                 // D: windows of read groups until the deferred groups listed should fill phase S's list (apg = work
                 //    items per deferred group, dfrac = share of deferred groups, running averages of this block)
                 const int target = max(8, min(kTT, (int)(0.7f * (float)tile_list_cap(2) / apg)));
                 for (;;) {
                     const int want = max(16, min(kTT, (int)((float)(target - T.misc[3]) / fmaxf(dfrac, 0.03f))));
-                    const i64 g1 = tile_window(d.r, g0, it.z, kWin2, want);
+                    const i64 g1 = tile_window(T, d.r, g0, it.z, kWin2, want);
                     const i64 a0 = d.r.grp_aln_off[2 * g0];
                     const int before = T.misc[3];
                     __syncthreads();       // everyone has read the fill
@@ -1152,7 +1264,7 @@ __global__ void __launch_bounds__(kTT, SFB_TILE_MINBLK) k_tile_pass(const __grid
                 // M
                 {
                     const int seen = st.tuples;                       // counted in pass 1
-                    if (T.simple) for (int q = tid; q < n_aln; q += kTT) mask_match_aln(T, d.r, q, T.a_item + T.alist[q], st);
+                    if (T.simple) for (int q = tid; q < n_aln; q += kTT) mask_match_aln<false>(T, d.r, q, T.a_item + T.alist[q], st);
                     else for (int q = tid; q < n_aln; q += kTT) tile_match_aln<KA>(T, d.r, q, T.a_item + T.alist[q], st);
                     st.tuples = seen;
                 }
