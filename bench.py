@@ -284,6 +284,17 @@ class ClockSampler(threading.Thread):
 KERNEL_STAGES = ("tile_pass1", "match", "classify", "tile_pass2", "pass2_resolve", "pass2_scatter", "path_reduce")
 
 
+def log_mem(tag):
+    """Host memory of this process to stderr (a rank killed for memory leaves no other trace)."""
+    try:
+        import psutil
+        rss = psutil.Process().memory_info().rss / 2 ** 30
+        avail = psutil.virtual_memory().available / 2 ** 30
+        print(f"[bench rank {os.environ.get('RANK', '0')}] {tag}: rss {rss:.1f} GiB, available {avail:.1f} GiB", file=sys.stderr, flush=True)
+    except Exception:
+        pass
+
+
 def check_parity(res, ref, what):
     """GPU result against the CPU port's on the same read sample: integers exact, fp64 within 1e-9 relative with the
     same zero pattern (north_star).  Raises on a difference."""
@@ -313,6 +324,7 @@ def device_pass(eng, reads, steps, warmup, world, dist, device, want_marks=True)
     t0 = time.perf_counter()
     host = eng.stage(reads, pin=True)
     stage_s = time.perf_counter() - t0
+    host.reads = None                     # the staged arena is all the passes need
     dr = eng.upload(host)
     torch.cuda.synchronize()
     done = 0
@@ -361,7 +373,8 @@ def roofline_block(args, graph, eng, reads, host, stats, stage_ms, world):
         Cr = {k: v // world for k, v in Cr.items()}
     by = roofline.kernel_bytes(reads.n_groups, reads.n_alns, reads.n_records, graph.n_paths, eng.dg.n_slots,
                                Cr, stats.match_fill, stats.n_deferred, graph.n_strains,
-                               tile_groups=host.grp_begin, tile_alns=host.aln_begin)
+                               tile_groups=host.grp_begin if eng.tile_kernels else 0,
+                               tile_alns=host.aln_begin if eng.tile_kernels else 0)
     kernels = {k: v for k, v in stage_ms.items() if k in KERNEL_STAGES and by.get(k, 0) > 0}
     top = max(kernels, key=kernels.get)
     peaks = {}
@@ -471,7 +484,8 @@ def run_ours(args):
     t_gen = time.perf_counter()
     reads = synth.make_reads(graph, synth.SEED0 + idx + 1000 + 7919 * rank, n_pairs=pairs, read_len=rkw["read_len"])
     t_gen = time.perf_counter() - t_gen
-    # headline: the default engine -- tile kernels, order-independent (deterministic) accumulation
+    log_mem("reads generated")
+    # headline: the default engine -- read groups in tile order, order-independent (deterministic) accumulation
     eng = engine.AbundanceEngine(graph, device, comm=comm)
     sampler = ClockSampler(local)
     sampler.start()
@@ -489,8 +503,8 @@ def run_ours(args):
     parity = None
     if cpu_out is not None:
         parity = check_parity(eng.run(cpu_sample), cpu_out, f"oracle port on the first {cpu_sample.n_groups} read pairs of the workload")
-        parity["global_kernels"] = check_parity(engine.AbundanceEngine(graph, device, tiles=False).run(cpu_sample), cpu_out,
-                                                "same sample, global-memory kernels")["status"]
+        parity["tile_kernels"] = check_parity(engine.AbundanceEngine(graph, device, tile_kernels=True).run(cpu_sample), cpu_out,
+                                              "same sample, shared-memory tile kernels")["status"]
     elif world > 1:
         # rank-count independence: a fixed sample split over the ranks against the same sample on one rank
         sample = synth.make_reads(graph, synth.SEED0 + idx + 555, n_pairs=min(200_000, pairs), read_len=rkw["read_len"])
@@ -509,10 +523,11 @@ def run_ours(args):
                       "checked": f"counters, uniq_reads, histograms exact; per-path fp64 sums and the gene table bit-identical "
                                  f"between 1 and {world} ranks (order-independent accumulation)"}
 
-    # the plain accumulation mode (fp64 REDs, not reproducible) and the global-memory kernels, for comparison
+    # for comparison: the plain accumulation mode (fp64 REDs, not reproducible), reads in file order, the tile kernels
     alt = {}
     if not args.no_det:
-        for key, kw in (("plain_fp64_atomics", dict(deterministic=False)), ("global_memory_kernels", dict(tiles=False))):
+        for key, kw in (("plain_fp64_atomics", dict(deterministic=False)), ("file_order", dict(tiles=False)),
+                        ("shared_memory_tile_kernels", dict(tile_kernels=True))):
             e2 = engine.AbundanceEngine(graph, device, comm=comm, **kw)
             e2.match_cap_hint = eng.match_cap_hint
             ms2, st2, _, _, _, _, dr2 = device_pass(e2, reads, max(3, args.steps // 4), 2, world, dist, device)
@@ -529,8 +544,12 @@ def run_ours(args):
         del dr
         cuts = [sfdist.shard_bounds(reads.n_groups, args.e2e_shards, k) for k in range(args.e2e_shards)]
         t0 = time.perf_counter()
-        shards = [eng.stage(reads.slice_groups(a, b), pin=True) for a, b in cuts]
+        shards = []
+        for a, b in cuts:
+            shards.append(eng.stage(reads.slice_groups(a, b), pin=True))
+            shards[-1].reads = None
         pack_s = time.perf_counter() - t0
+        log_mem("e2e shards staged")
         h2d = sum(s_.nbytes() for s_ in shards)
         from collections import deque
         eng.run_stream(shards)

@@ -49,6 +49,40 @@ def reduce_scatter_ranges(t, bounds, group):
     return t
 
 
+class RangeReduceScatter:
+    """Sum over ranks of several arrays that share one partition into contiguous ranges (``bounds``): rank k ends up
+    with the sums of range k of every array -- ONE reduce_scatter_tensor per call instead of one reduce per destination
+    and array.  The ranges are unequal (they end at path boundaries), the collective wants equal chunks: a gather
+    index, built once, lays range k of array j at ``[k][j][0:len_k]`` of a staging buffer padded to the longest range
+    (padding reads the LAST element of the source, which the caller keeps at zero).  ``arrays``: 1-D tensors of equal
+    length and dtype, views of ONE flat tensor ``flat`` (the index addresses ``flat``); results are written back in place."""
+
+    def __init__(self, flat, arrays, bounds, group):
+        self.group, self.flat, self.arrays = group, flat, arrays
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        b = [int(x) for x in bounds]
+        self.lo, self.hi = b[self.rank], b[self.rank + 1]
+        self.chunk = max(1, max(b[k + 1] - b[k] for k in range(self.world)))
+        base = [(a.data_ptr() - flat.data_ptr()) // flat.element_size() for a in arrays]
+        zero = flat.numel() - 1                               # the spare element that stays zero
+        idx = np.full((self.world, len(arrays), self.chunk), zero, np.int64)
+        for k in range(self.world):
+            n = b[k + 1] - b[k]
+            for j, off in enumerate(base):
+                idx[k, j, :n] = off + b[k] + np.arange(n, dtype=np.int64)
+        self.idx = torch.from_numpy(idx.reshape(-1)).to(flat.device)
+        self.send = torch.empty(self.idx.numel(), dtype=flat.dtype, device=flat.device)
+        self.recv = torch.empty(len(arrays) * self.chunk, dtype=flat.dtype, device=flat.device)
+
+    def __call__(self):
+        torch.index_select(self.flat, 0, self.idx, out=self.send)
+        dist.reduce_scatter_tensor(self.recv, self.send, op=dist.ReduceOp.SUM, group=self.group)
+        n = self.hi - self.lo
+        for j, a in enumerate(self.arrays):
+            a[self.lo:self.hi].copy_(self.recv[j * self.chunk:j * self.chunk + n])
+
+
 def all_gather_rows(local_rows, row_bounds, group):
     """local_rows: [n_k, C] on each rank (n_k = row_bounds[k+1]-row_bounds[k]); returns the full [N, C] on every rank."""
     world = dist.get_world_size(group)

@@ -327,7 +327,7 @@ class Accum:
         # into the fp64 values of plane 0 before the path reduction
         self.F = 3 * P + 2 * n_slots
         self.planes = 2 if deterministic else 1
-        self.f64_all = torch.zeros(self.planes * self.F, dtype=torch.float64, device=dev)
+        self.f64_all = torch.zeros(self.planes * self.F + 1, dtype=torch.float64, device=dev)   # + one element that stays 0
         self.f64 = self.f64_all[:self.F]
         # int64 block: uniq_reads | hist | counters | mult_hits (uint32 pairs packed in the tail)
         self.n_hist = _lib.N_HIST * S * _lib.N_BINS
@@ -350,10 +350,23 @@ class Accum:
         self.f64_all.zero_()
         self.i64.zero_()
 
+    def flat(self):
+        """The whole fp64 block as the tensor to sum over ranks: int64 in the order-independent mode (exact), else fp64."""
+        return self.f64_all.view(torch.int64) if self.planes > 1 else self.f64_all
+
     def plane(self, k):
-        """Plane k as the tensor to sum over ranks: int64 in the order-independent mode (exact), else fp64."""
-        pl = self.f64_all[k * self.F:(k + 1) * self.F]
-        return pl.view(torch.int64) if self.planes > 1 else pl
+        return self.flat()[k * self.F:(k + 1) * self.F]
+
+    def exchange(self, which, bounds, comm):
+        """The reduce-scatter of one slot array (0 uniq_abund, 1 mult_abund; every plane) onto the path-partitioned layout,
+        built once per accumulator set."""
+        from . import dist as sfdist
+        key = "_rs%d" % which
+        if getattr(self, key, None) is None:
+            flat, P, n = self.flat(), self.P, self.n_slots
+            arrays = [self.plane(k)[3 * P + which * n:3 * P + (which + 1) * n] for k in range(self.planes)]
+            setattr(self, key, sfdist.RangeReduceScatter(flat, arrays, bounds, comm))
+        return getattr(self, key)
 
 
 class Result:
@@ -448,7 +461,7 @@ class AbundanceEngine:
     """One engine per process/GPU.  ``comm`` is an optional torch.distributed process group: when
     given, ``run`` treats ``reads`` as this rank's shard of the read groups."""
 
-    def __init__(self, graph: Graph, device="cuda:0", comm=None, deterministic=True, tiles=True):
+    def __init__(self, graph: Graph, device="cuda:0", comm=None, deterministic=True, tiles=True, tile_kernels=None):
         if not torch.cuda.is_available():
             raise _lib.SfbError("no CUDA device: the abundance engine has no CPU fallback")
         self.lib = _lib.load()
@@ -459,7 +472,14 @@ class AbundanceEngine:
         if os.environ.get("SFB200_TILES", "1").strip().lower() in ("0", "false", "no", "off"):
             tiles = False
         self.dg = DeviceGraph(graph, self.device, tiles=tiles)
-        self.tiling = self.dg.tiling             # None: every read group goes through the global-memory kernels
+        self.tiling = self.dg.tiling             # None: no tile order, every read group through the global-memory kernels
+        # tile order is a layout decision of the staging (neighbouring groups touch the same part of the graph); which
+        # kernels then run is a second one: the shared-memory tile kernels, or the global-memory kernels on everything
+        # (measured on C3, profiles/README.md r02: the global-memory kernels on tile-ordered reads are the faster ones,
+        # so they are the default; SFB200_TILE_KERNELS=1 / tile_kernels=True switches the tile kernels on)
+        if tile_kernels is None:
+            tile_kernels = os.environ.get("SFB200_TILE_KERNELS", "0").strip().lower() in ("1", "true", "yes", "on")
+        self.tile_kernels = bool(tile_kernels) and self.tiling is not None
         self.node_len = _to_dev(graph.node_len, self.device)
         self.comm = comm
         # order-independent sums (96-bit fixed point, the default): bit-identical across runs, shard counts and GPU
@@ -592,6 +612,7 @@ class AbundanceEngine:
             uniq_global = self.acc.uniq_reads.clone()
             dist.all_reduce(uniq_global, group=self.comm)          # exact integer sum over shards
             mark("allreduce_uniq")
+            self._exchange_uniq(main)
         self.tile_pass2(dr, work, uniq_global)
         mark("tile_pass2")
         self.pass2_resolve(dr, work, uniq_global)
@@ -602,6 +623,12 @@ class AbundanceEngine:
         mark("pass2_scatter")
         self._finish_pass(mark)
         return work
+
+    def _exchange_uniq(self, main):
+        """uniq_abund is final once the pass-1 node loops are done: its reduce-scatter onto the path-partitioned layout is
+        issued behind them on the side stream and runs under pass 2."""
+        with torch.cuda.stream(self.side if self.overlap else main):
+            self.acc.exchange(0, self.slot_bounds, self.comm)()
 
     def _finish_pass(self, mark=lambda name: None):
         """Exchange 2 (multi-GPU) and the per-path reduction."""
@@ -619,10 +646,8 @@ class AbundanceEngine:
         P, n_slots = acc.P, acc.n_slots
         dist.all_reduce(acc.i64, group=self.comm)
         for k in range(acc.planes):
-            pl = acc.plane(k)
-            dist.all_reduce(pl[:3 * P], group=self.comm)
-            sfdist.reduce_scatter_ranges(pl[3 * P:3 * P + n_slots], self.slot_bounds, self.comm)
-            sfdist.reduce_scatter_ranges(pl[3 * P + n_slots:], self.slot_bounds, self.comm)
+            dist.all_reduce(acc.plane(k)[:3 * P], group=self.comm)
+        acc.exchange(1, self.slot_bounds, self.comm)()             # mult_abund (uniq_abund went under pass 2)
         if acc.planes > 1:
             self.collapse()
         mark("reduce_accum")
@@ -635,7 +660,7 @@ class AbundanceEngine:
     def upload(self, host: HostReads):
         """H2D of a staged shard (+ device-side expansion of the transfer layout), reusing the device buffers."""
         dr = DeviceReads(host, self.device, getattr(self, "_arena", None), getattr(self, "_wide", None), self.node_len,
-                         tile_desc=getattr(self.dg, "tile_desc", None) if self.tiling is not None else None,
+                         tile_desc=getattr(self.dg, "tile_desc", None) if self.tile_kernels else None,
                          tile_edges=getattr(self.dg, "tile_edges", None))
         self._arena, self._wide = dr.arena, dr.wide
         return dr
@@ -688,7 +713,7 @@ class AbundanceEngine:
             slot = job.slots.setdefault(k, {})
             with torch.cuda.stream(self._copy):
                 dr = DeviceReads(host, self.device, slot.get("arena"), slot.get("wide"), self.node_len, expand=False,
-                                 tile_desc=getattr(self.dg, "tile_desc", None) if self.tiling is not None else None,
+                                 tile_desc=getattr(self.dg, "tile_desc", None) if self.tile_kernels else None,
                          tile_edges=getattr(self.dg, "tile_edges", None))
                 arrived = torch.cuda.Event()
                 arrived.record(self._copy)
@@ -713,6 +738,7 @@ class AbundanceEngine:
         if self.comm is not None:
             uniq_global = self.acc.uniq_reads.clone()
             dist.all_reduce(uniq_global, group=self.comm)
+            self._exchange_uniq(main)
         for dr, work in live:
             self._bind(dr, work)
             self.tile_pass2(dr, work, uniq_global)
@@ -871,9 +897,9 @@ def decode_matches(res, a):
     return [(pid, int((c & _lib.SLOT_MASK) - starts[pid]), bool(c & _lib.MATCH_REV)) for c, pid in pairs]
 
 
-def abundance_pass(graph: Graph, reads: Reads, device="cuda:0", deterministic=True, tiles=True) -> Result:
+def abundance_pass(graph: Graph, reads: Reads, device="cuda:0", deterministic=True, tiles=True, tile_kernels=None) -> Result:
     """One-call public API: decoded alignments + graph in, per-path abundances and counters out."""
-    return AbundanceEngine(graph, device, deterministic=deterministic, tiles=tiles).run(reads)
+    return AbundanceEngine(graph, device, deterministic=deterministic, tiles=tiles, tile_kernels=tile_kernels).run(reads)
 
 
 def cluster_strain_counts(graph: Graph, device="cuda:0"):

@@ -38,8 +38,10 @@ class Tiling:
         k = os.environ.get("SFB200_TILE_K")
         if tuple_cap is None and k:
             tuple_cap = int(k)
-        if tuple_cap is None:          # match tuples per alignment kept in shared memory: about one per path of the tile
-            tuple_cap = 8 if self.max_paths <= 9 else 16 if self.max_paths <= 20 else 32
+        if tuple_cap is None:          # match tuples per alignment kept in shared memory: about one per path of the tile;
+            # simple tiles keep path sets instead, so a graph of simple tiles takes the smallest store
+            all_simple = self.n_tiles > 0 and bool(self.tile_desc[:, 4].all())
+            tuple_cap = 8 if all_simple or self.max_paths <= 9 else 16 if self.max_paths <= 20 else 32
         self.tuple_cap = int(tuple_cap)
 
     @property

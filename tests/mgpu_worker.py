@@ -20,10 +20,10 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     graph, reads = synth.make_config("small", scale=0.4)
     g0, g1 = sfdist.shard_bounds(reads.n_groups, world, rank)
-    eng = engine.AbundanceEngine(graph, dev, comm=dist.group.WORLD)
+    eng = engine.AbundanceEngine(graph, dev, comm=dist.group.WORLD, deterministic=False)
     res = eng.run(reads.slice_groups(g0, g1))
     if rank == 0:
-        single = engine.AbundanceEngine(graph, dev).run(reads)
+        single = engine.AbundanceEngine(graph, dev, deterministic=False).run(reads)
         for k in ("NB_READS", "PAIRS", "SINGLES", "FILTERED", "UNASSIGNED", "ASSIGNED_U", "ASSIGNED_M", "INCONSIST",
                   "MULTI_ALIGN", "SE", "SAME_CP", "DIFF_CP", "SE_M", "SECOND_PASS", "AMBIG_CP_RESOLVED"):
             assert res.C[k] == single.C[k], (k, res.C[k], single.C[k])
@@ -45,6 +45,12 @@ def main():
         for name in ("uniq_norm", "mult_reads", "mult_norm", "uniq_abund", "mult_abund", "table"):
             assert np.array_equal(getattr(res_d, name), getattr(single_d, name), equal_nan=True), name
         print("MGPU_DET_OK")
+    # ... and whatever the kernels: the shared-memory tile kernels on the shards against the default on one GPU
+    res_t = engine.AbundanceEngine(graph, dev, comm=dist.group.WORLD, tile_kernels=True).run(reads.slice_groups(g0, g1))
+    if rank == 0:
+        for name in ("uniq_reads", "hist", "uniq_norm", "mult_reads", "mult_norm", "uniq_abund", "mult_abund", "table"):
+            assert np.array_equal(getattr(res_t, name), getattr(single_d, name), equal_nan=True), name
+        print("MGPU_TILE_OK")
     # two pipelined jobs per rank (submit / collect), each rank's shard staged as two host shards: same bits again
     mine = reads.slice_groups(g0, g1)
     staged = [engine.HostReads(mine.slice_groups(*sfdist.shard_bounds(mine.n_groups, 2, i))) for i in range(2)]

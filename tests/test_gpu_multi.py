@@ -22,4 +22,4 @@ def test_two_gpus_match_one():
                         "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(HERE, "mgpu_worker.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
-    assert "MGPU_OK" in r.stdout and "MGPU_DET_OK" in r.stdout and "MGPU_PIPE_OK" in r.stdout
+    assert all(tag in r.stdout for tag in ("MGPU_OK", "MGPU_DET_OK", "MGPU_TILE_OK", "MGPU_PIPE_OK"))

@@ -20,10 +20,11 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-# every combination of the two kernel families (shared-memory tiles / global memory) and the two accumulation modes
-MODES = [dict(tiles=True, deterministic=True), dict(tiles=True, deterministic=False),
-         dict(tiles=False, deterministic=True), dict(tiles=False, deterministic=False)]
-MODE_IDS = ["tiles-det", "tiles-plain", "global-det", "global-plain"]
+# the kernel families (global-memory kernels on tile-ordered reads = the default, shared-memory tile kernels,
+# global-memory kernels on reads in file order) and the two accumulation modes
+MODES = [dict(), dict(deterministic=False), dict(tile_kernels=True), dict(tile_kernels=True, deterministic=False),
+         dict(tiles=False), dict(tiles=False, deterministic=False)]
+MODE_IDS = ["default", "default-plain", "tilekernels-det", "tilekernels-plain", "fileorder-det", "fileorder-plain"]
 all_modes = pytest.mark.parametrize("mode", MODES, ids=MODE_IDS)
 
 
@@ -211,8 +212,8 @@ def test_match_corner_cases_equal_oracle(seed, alphabet):
     orc.run()
     check_against_oracle(graph, reads, res, orc)
     # the same corners against the shared-memory index: all 40 paths share the alphabet, so they are one tile
-    eng = engine.AbundanceEngine(graph)
-    assert eng.tiling is not None and eng.tiling.n_tiles == 1
+    eng = engine.AbundanceEngine(graph, tile_kernels=True)
+    assert eng.tiling is not None and eng.tiling.n_tiles == 1 and eng.tile_kernels
     check_against_oracle(graph, reads, eng.run(reads), orc)
 
 

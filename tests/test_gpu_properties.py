@@ -27,7 +27,7 @@ def cov_of(reads):
 def test_conservation_laws(name, scale):
     need_gpu()
     graph, reads = synth.make_config(name, scale=scale)
-    eng = engine.AbundanceEngine(graph)
+    eng = engine.AbundanceEngine(graph, tile_kernels=True)
     res = eng.run(reads)
     C = res.C
     lo, hi = res.grp_code & 15, res.grp_code >> 4
@@ -57,7 +57,11 @@ def test_conservation_laws(name, scale):
     # the two kernel families (shared-memory tiles above, global memory here) agree: integers exactly, and -- the sums
     # being exact integer sums of the same terms in the default order-independent mode -- the fp64 arrays bit for bit
     assert eng.tiling is not None and eng.tiling.n_tiles > 1000
-    glob = engine.AbundanceEngine(graph, tiles=False).run(reads)
+    dflt = engine.AbundanceEngine(graph).run(reads)                       # global-memory kernels on tile-ordered reads
+    glob = engine.AbundanceEngine(graph, tiles=False).run(reads)          # ... and on reads in file order
+    for name in ("grp_code", "grp_code2", "aln_assign", "uniq_reads", "hist", "mult_hits", "uniq_norm", "mult_reads",
+                 "mult_norm", "uniq_abund", "mult_abund", "table"):
+        assert np.array_equal(getattr(glob, name), getattr(dflt, name), equal_nan=True), name
     assert glob.C == {**res.C, **{k: glob.C[k] for k in ("ST_CAND", "ST_COMPARES")}}
     for name in ("grp_code", "grp_code2", "aln_assign", "uniq_reads", "hist", "mult_hits"):
         assert np.array_equal(getattr(glob, name), getattr(res, name)), name
