@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SFB_ABI_VERSION 10
+#define SFB_ABI_VERSION 11
 
 /* ---- status codes ---------------------------------------------------- */
 #define SFB_OK            0
@@ -249,6 +249,23 @@ typedef struct sfb_tiles {
 int         sfb_abi_version(void);
 const char* sfb_version(void);
 const char* sfb_last_error(void);
+
+/* Sizes of the caller-allocated buffers, so that a binding does not restate the formulas:
+ *   SFB_WS_EXPANDED      bytes of ONE device allocation that holds, each aligned to 256 bytes and in this order, what
+ *                        sfb_expand_reads fills: grp_aln_off[2G+1], aln_walk_off[A+1], its scratch, mate_seq_len[2G],
+ *                        aln_bins[5A], walk_node[R], walk_alen[R]
+ *   SFB_WS_MATCH_PAIRS   default capacity of match_buf in (code, path id) pairs (the exact need is cursor[0] after a pass)
+ *   SFB_WS_APP_ITEMS     capacity of app_buf in 16-byte items that always suffices for that match_buf
+ *   SFB_WS_ACCUM_F64     doubles of the fp64 accumulator block: every plane (1, or 2 in the order-independent mode) =
+ *                        uniq_norm[P] | mult_reads[P] | mult_norm[P] | uniq_abund[n_slots] | mult_abund[n_slots], plus one
+ *                        spare element; det_stride = 3P + 2 n_slots
+ *   SFB_WS_ACCUM_I64     64-bit words of the integer block: uniq_reads[P] | hist[5*S*101] | counters[32] | mult_hits (uint32[P])
+ * Unused dimensions may be 0.  Returns SFB_E_ARG for an unknown `what` or a negative dimension. */
+enum { SFB_WS_EXPANDED = 0, SFB_WS_MATCH_PAIRS = 1, SFB_WS_APP_ITEMS = 2, SFB_WS_ACCUM_F64 = 3, SFB_WS_ACCUM_I64 = 4 };
+typedef struct sfb_dims {
+    int64_t n_groups, n_alns, n_records, n_paths, n_slots, n_strains, deterministic;
+} sfb_dims;
+int64_t sfb_workspace_bytes(int what, const sfb_dims* dims);
 
 /* Device-side expansion of the transfer layout.  `dst` is the view the kernels will use: its grp_aln_off[2G+1],
  * mate_seq_len[2G], aln_walk_off[A+1], aln_bins[5A], walk_node[R] and walk_alen[R] point at caller-allocated device

@@ -55,6 +55,22 @@ class SfbWork(C.Structure):
     ]
 
 
+class SfbDims(C.Structure):
+    _fields_ = [(k, C.c_int64) for k in ("n_groups", "n_alns", "n_records", "n_paths", "n_slots", "n_strains", "deterministic")]
+
+
+WS_EXPANDED, WS_MATCH_PAIRS, WS_APP_ITEMS, WS_ACCUM_F64, WS_ACCUM_I64 = range(5)
+
+
+def workspace(what, **dims):
+    """sfb_workspace_bytes: the buffer sizes come from the library, not from formulas restated here."""
+    d = SfbDims(**{k: int(v) for k, v in dims.items()})
+    n = int(load().sfb_workspace_bytes(int(what), C.byref(d)))
+    if n < 0:
+        raise SfbError(f"sfb_workspace_bytes({what}): {load().sfb_last_error().decode()}")
+    return n
+
+
 class SfbTiles(C.Structure):
     _fields_ = [
         ("n_tiles", C.c_int64), ("n_items", C.c_int64), ("max_slots", C.c_int64), ("max_nodes", C.c_int64),
@@ -85,11 +101,11 @@ SLOT_MASK, MATCH_REV, MATCH_MULTI, MATCH_NONE = 0x3FFFFFFF, 0x40000000, 0x800000
 MAX_SLOTS = 0x3FFFFFFF
 (ABSENT, FILTERED, UNASSIGNED, UNASSIGNED_BOOK, DEFER, ASSIGN_SAME, ASSIGN_DIFF, MULTI_ALIGN, INCONSIST,
  SE_COUNTED) = range(10)
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 EXPORTS = ("sfb_abi_version", "sfb_version", "sfb_last_error", "sfb_expand_reads", "sfb_match", "sfb_classify", "sfb_pass1_scatter",
            "sfb_pass2", "sfb_pass2_resolve", "sfb_pass2_scatter", "sfb_accum_collapse", "sfb_path_reduce", "sfb_cluster_strain_counts", "sfb_strain_aggregate",
-           "sfb_tile_pass1", "sfb_tile_pass2", "sfb_tile_smem_bytes", "sfb_tile_permute",
+           "sfb_tile_pass1", "sfb_tile_pass2", "sfb_tile_smem_bytes", "sfb_tile_permute", "sfb_workspace_bytes",
            "sfb_decode_json", "sfb_decoded_error", "sfb_decoded_size", "sfb_decoded_copy", "sfb_decoded_free",
            "sfb_min_strains", "sfb_wire_pack", "sfb_packed_status", "sfb_packed_size", "sfb_packed_copy", "sfb_packed_free",
            "sfb_load_gfa", "sfb_gfa_error", "sfb_gfa_size", "sfb_gfa_copy", "sfb_gfa_free", "sfb_locality_permute")
@@ -115,9 +131,10 @@ def load(build_if_missing=True):
     if build_if_missing and "SFB200_LIB" not in os.environ:
         try:
             _build.build()
-        except Exception as e:          # no nvcc on this machine: use the prebuilt .so if there is one
+        except (FileNotFoundError, PermissionError) as e:     # no nvcc on this machine: use the prebuilt .so if there is one
             if not os.path.exists(path):
                 raise SfbError(f"libsfb200.so is missing and could not be built: {e}") from e
+        # (a compile error is not caught: a stale library must never stand in for sources that do not build)
     if not os.path.exists(path):
         raise SfbError(f"{path} not found; run `python -m strainflair_b200.build` (there is no CPU fallback)")
     lib = C.CDLL(path)
@@ -148,6 +165,8 @@ def load(build_if_missing=True):
     lib.sfb_tile_smem_bytes.restype = C.c_int64
     lib.sfb_tile_permute.argtypes = [R, vp, i64, C.c_int, vp, vp, R, vp]
     lib.sfb_tile_permute.restype = C.c_int
+    lib.sfb_workspace_bytes.argtypes = [C.c_int, C.POINTER(SfbDims)]
+    lib.sfb_workspace_bytes.restype = C.c_int64
     lib.sfb_min_strains.argtypes = [i64, vp, vp, vp, C.c_int, vp, vp, vp, vp]
     lib.sfb_min_strains.restype = C.c_int
     lib.sfb_locality_permute.argtypes = [R, C.c_int, vp, vp, R]

@@ -20,7 +20,7 @@ def _nvcc():
     for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
         if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
             return cand
-    raise RuntimeError("nvcc not found")
+    raise FileNotFoundError("nvcc not found")
 
 
 def needs_build():

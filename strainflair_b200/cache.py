@@ -9,7 +9,7 @@ format version, so a changed input or parameter simply misses.  Entries are writ
 """
 import hashlib
 import os
-import pickle
+import json
 
 import numpy as np
 
@@ -51,7 +51,7 @@ def _save(entry, arrays):
 
 
 def _blob(obj):
-    return np.frombuffer(pickle.dumps(obj, protocol=4), np.uint8)
+    return np.frombuffer(json.dumps(obj).encode("utf-8"), np.uint8)
 
 
 def graph_fingerprint(graph: Graph):
@@ -70,9 +70,13 @@ def load_graph_entry(gfa_path):
     try:
         with np.load(entry, allow_pickle=False) as z:
             kw = {k: z[k] for k in GRAPH_ARRAYS}
-            extras = pickle.loads(z["extras"].tobytes())
-    except (OSError, KeyError, ValueError, pickle.UnpicklingError):
-        return None                          # unreadable entry: parse again
+            extras = json.loads(z["extras"].tobytes().decode("utf-8"))     # plain JSON: a cache entry is never executed
+            extras["strain_names"] = [None if v is None else str(v) for v in extras["strain_names"]]
+            extras["header_strains"] = [int(v) for v in extras["header_strains"]]
+            if extras.get("path_names") is not None:
+                extras["path_names"] = {str(k): int(v) for k, v in extras["path_names"].items()}
+    except Exception:
+        return None                          # unreadable or foreign entry: parse again
     P = len(kw["path_off"]) - 1
     kw["path_cluster"] = np.full(P, -1, np.int32)
     kw["clu_off"], kw["clu_paths"] = np.zeros(1, np.int64), np.zeros(0, np.int32)
@@ -84,8 +88,10 @@ def save_graph_entry(gfa_path, graph: Graph):
     if entry is None:
         return
     arrays = {k: getattr(graph, k) for k in GRAPH_ARRAYS}
-    arrays["extras"] = _blob(dict(strain_names=graph.strain_names, header_strains=graph.header_strains,
-                                  path_names=graph.path_names))
+    arrays["extras"] = _blob(dict(strain_names=[None if v is None else str(v) for v in graph.strain_names],
+                                  header_strains=[int(v) for v in graph.header_strains],
+                                  path_names=None if graph.path_names is None else
+                                  {str(k): int(v) for k, v in graph.path_names.items()}))
     _save(entry, arrays)
 
 
@@ -107,8 +113,8 @@ def load_reads_entry(json_path, graph: Graph, thr, want_cov):
             reads.name_blob = z["name_blob"].tobytes()
             if want_cov:
                 reads.walk_cov = z["walk_cov"]
-    except (OSError, KeyError, ValueError):
-        return None
+    except Exception:
+        return None                          # unreadable entry: decode again
     return reads
 
 

@@ -10,23 +10,42 @@ def _usage_json2csv():
           f"(pickle) -t alignment_score_threshold -o prefix_output_files_name -f")
 
 
+def update_progress(progress):
+    """The reference's console progress bar on stderr (json2csv.py:16-35), same text: its callers tick it through the
+    GFA (:245,298), the two passes over the alignments (:819,1055 / :1074,1275) and the gene table (:411,474)."""
+    bar, status = 50, ""
+    if progress < 0:
+        progress, status = 0, "Halt...\r\n"
+    if progress >= 1:
+        progress, status = 1, "Done...\r\n"
+    block = int(round(bar * progress))
+    sys.stderr.write("\rPercent: [{0}] {1}% {2}".format("#" * block + "-" * (bar - block), round(progress * 100, 2), status))
+    sys.stderr.flush()
+
+
 def run_json2csv(graph_file, mapping_file, pickle_file, prefix, thr=0.95, device="cuda:0", timings=None):
     """The whole json2csv job; returns (graph, reads, result)."""
     from . import decode, engine, gfa, report
     t = {}
     t0 = time.perf_counter()
     print("Load the pangenome graph")
+    update_progress(0)
     graph = gfa.load_graph(graph_file, pickle_file)
+    update_progress(1)
     t["graph_s"] = time.perf_counter() - t0
     t0 = time.perf_counter()
     print("Parsing Alignment: first pass")
+    update_progress(0)
     reads = decode.decode_json(mapping_file, graph, thr)
     t["decode_s"] = time.perf_counter() - t0
     t0 = time.perf_counter()
     eng = engine.AbundanceEngine(graph, device, deterministic=True)     # files out: bit-reproducible from run to run
     t["abundance_engine_s"] = time.perf_counter() - t0
+    update_progress(1)                                                  # (the first pass is the decode + the kernels' pass 1)
     print("Parsing Alignment: second pass")
+    update_progress(0)
     res = eng.run(reads, keep_codes=True, keep_slots=False)
+    update_progress(1)
     t["abundance_s"] = time.perf_counter() - t0
     t0 = t1 = time.perf_counter()
 
@@ -39,7 +58,9 @@ def run_json2csv(graph_file, mapping_file, pickle_file, prefix, thr=0.95, device
     lap("report_cluster_records_s")
     gene_csv = prefix + "_gene_table.csv"
     print(f"Print gene-level results to file {gene_csv}")
+    update_progress(0)
     report.write_gene_table(gene_csv, graph, res)
+    update_progress(1)
     lap("report_gene_table_s")
     for k, name in enumerate(report.HIST_FILES):
         print(f"Print {name} distribution results to file {prefix + '_' + name + '.csv'}")

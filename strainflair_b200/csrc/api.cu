@@ -93,6 +93,23 @@ int sfb_abi_version(void) { return SFB_ABI_VERSION; }
 const char* sfb_version(void) { return "sfb200 0.2 (sm_100a)"; }
 const char* sfb_last_error(void) { return g_err; }
 
+int64_t sfb_workspace_bytes(int what, const sfb_dims* d) {
+    if (!d || d->n_groups < 0 || d->n_alns < 0 || d->n_records < 0 || d->n_paths < 0 || d->n_slots < 0 || d->n_strains < 0)
+        return fail(SFB_E_ARG, "sfb_workspace_bytes: null or negative dimensions");
+    const int64_t G = d->n_groups, A = d->n_alns, R = d->n_records, P = d->n_paths, T = d->n_slots, S = d->n_strains;
+    auto al = [](int64_t n) { return (n + 255) & ~(int64_t)255; };
+    switch (what) {
+    case SFB_WS_EXPANDED:
+        return al(8 * (2 * G + 1)) + al(8 * (A + 1)) + al(8 * ((2 * G > A ? 2 * G : A) / 4096 + 2)) + al(8 * G) + al(5 * A) +
+               al(4 * R) + al(4 * R);
+    case SFB_WS_MATCH_PAIRS: return 2 * A + 1024;
+    case SFB_WS_APP_ITEMS: return A + (2 * A + 1024);
+    case SFB_WS_ACCUM_F64: return (d->deterministic ? 2 : 1) * (3 * P + 2 * T) + 1;
+    case SFB_WS_ACCUM_I64: return P + (int64_t)SFB_N_HIST * S * SFB_N_BINS + SFB_N_COUNTERS + (P + 1) / 2;
+    default: return fail(SFB_E_ARG, "sfb_workspace_bytes: unknown size %d", what);
+    }
+}
+
 int sfb_expand_reads(const sfb_wire* w, const int32_t* node_len, const sfb_reads* dst, int64_t* scratch, void* stream) {
     SFB_REQUIRE(w && dst, "wire or destination is null");
     SFB_REQUIRE(w->n_groups >= 0 && w->n_alns >= 0 && w->n_records >= 0 && w->n_exc >= 0 && w->n_wide >= 0 &&

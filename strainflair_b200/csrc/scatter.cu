@@ -28,7 +28,9 @@ __global__ void __launch_bounds__(256) k_pass1_scatter(sfb_reads r, sfb_work w, 
 __global__ void __launch_bounds__(256) k_pass2_scatter(sfb_reads r, sfb_work w, double* mult_abund, i64 det_stride,
                                                        long long* counters) {
     const App* apps = reinterpret_cast<const App*>(w.app_buf);
-    const i64 n_app = min((i64)w.cursor[2], (i64)w.app_cap);
+    // more work items claimed than app_buf holds: the resolve kernels counted MATCH_OVERFLOW and left claims unwritten;
+    // nothing is added (the caller regrows the buffer and reruns the pass)
+    const i64 n_app = (i64)w.cursor[2] > (i64)w.app_cap ? 0 : (i64)w.cursor[2];
     int done = 0;
     for (i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x; q < n_app; q += (i64)gridDim.x * blockDim.x) {
         const App app = apps[q];

@@ -1207,8 +1207,8 @@ __global__ void __launch_bounds__(kTT, SFB_TILE_MINBLK) k_tile_pass(const __grid
                     const i64 g2 = min(g1 + (g1 - g0), (i64)it.z);
                     const i64 a1 = T.a_row0 + nA, w1 = d.r.aln_walk_off[a1];
                     tile_prefetch(d.r, g1, g2, it.z);
-                    tile_prefetch_alns(d.r, a1, min(a1 + nA, d.r.n_alns));
-                    tile_prefetch_recs(d.r, w1, min(w1 + (w1 - T.w_row0), d.r.n_records));
+                    tile_prefetch_alns(d.r, a1, min(a1 + nA, (i64)d.r.n_alns));
+                    tile_prefetch_recs(d.r, w1, min(w1 + (w1 - T.w_row0), (i64)d.r.n_records));
                 }
                 __syncthreads();
                 // M

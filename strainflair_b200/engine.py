@@ -267,7 +267,7 @@ class DeviceReads:
             self.c = _lib.SfbReads(n_groups=G, n_alns=A, n_records=R, n_exc=E, **ptr)
             return
         # expanded arrays (one device allocation, reused across steps)
-        need = 8 * (2 * G + 1) + 4 * 2 * G + 8 * (A + 1) + 5 * A + 8 * R + 8 * (max(2 * G, A) // 4096 + 2) + 7 * 256
+        need = _lib.workspace(_lib.WS_EXPANDED, n_groups=G, n_alns=A, n_records=R)
         if wide is None or wide.numel() < need:
             wide = torch.empty(need, dtype=torch.uint8, device=device)
         self.wide = wide
@@ -294,7 +294,8 @@ class Work:
         i32, u8 = torch.int32, torch.uint8
         self.n_groups, self.n_alns = n_groups, n_alns
         self.match_cap = int(max(2, match_cap))
-        self.app_cap = int(n_alns + self.match_cap)     # >= number of matches of the shard
+        self.app_cap = max(int(n_alns + self.match_cap),        # >= number of matches of the shard
+                           _lib.workspace(_lib.WS_APP_ITEMS, n_alns=n_alns))
         self.t = dict(
             aln_match=torch.empty(max(1, n_alns), dtype=torch.int64, device=device),      # (x, y) pairs
             match_buf=torch.empty(self.match_cap, dtype=torch.int64, device=device),       # (code, pid) pairs
@@ -327,11 +328,13 @@ class Accum:
         # into the fp64 values of plane 0 before the path reduction
         self.F = 3 * P + 2 * n_slots
         self.planes = 2 if deterministic else 1
+        dims = dict(n_paths=P, n_slots=n_slots, n_strains=S, deterministic=int(deterministic))
+        assert _lib.workspace(_lib.WS_ACCUM_F64, **dims) == self.planes * self.F + 1
         self.f64_all = torch.zeros(self.planes * self.F + 1, dtype=torch.float64, device=dev)   # + one element that stays 0
         self.f64 = self.f64_all[:self.F]
         # int64 block: uniq_reads | hist | counters | mult_hits (uint32 pairs packed in the tail)
         self.n_hist = _lib.N_HIST * S * _lib.N_BINS
-        self.i64 = torch.zeros(P + self.n_hist + _lib.N_COUNTERS + (P + 1) // 2, dtype=torch.int64, device=dev)
+        self.i64 = torch.zeros(_lib.workspace(_lib.WS_ACCUM_I64, **dims), dtype=torch.int64, device=dev)
         f, i = self.f64, self.i64
         self.uniq_norm, self.mult_reads, self.mult_norm = f[0:P], f[P:2 * P], f[2 * P:3 * P]
         self.uniq_abund, self.mult_abund = f[3 * P:3 * P + n_slots], f[3 * P + n_slots:]
@@ -501,7 +504,7 @@ class AbundanceEngine:
 
     # ---- stages (each is one kernel launch through the C ABI) -----------------------------
     def _work_for(self, dr):
-        cap = max(self.match_cap_hint, 2 * dr.n_alns + 1024)      # (code, path id) pairs for multi-matched alignments
+        cap = max(self.match_cap_hint, _lib.workspace(_lib.WS_MATCH_PAIRS, n_alns=dr.n_alns))   # (code, path id) pairs
         if self.work is None or self.work.n_groups < dr.n_groups or self.work.n_alns < dr.n_alns \
                 or self.work.match_cap < cap:
             self.work = None
@@ -721,7 +724,7 @@ class AbundanceEngine:
             main.wait_event(arrived)
             dr.expand()
             slot["wide"] = dr.wide
-            cap = max(slot.get("cap", 0), 2 * dr.n_alns + 1024)
+            cap = max(slot.get("cap", 0), _lib.workspace(_lib.WS_MATCH_PAIRS, n_alns=dr.n_alns))
             work = slot.get("work")
             if work is None or work.n_groups < dr.n_groups or work.n_alns < dr.n_alns or work.match_cap < cap:
                 work = slot["work"] = Work(dr.n_groups, dr.n_alns, cap, self.device)
