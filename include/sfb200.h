@@ -354,6 +354,12 @@ int sfb_strain_aggregate(int64_t n_rows, int64_t n_strains, const int32_t* row_o
 typedef struct sfb_decoded sfb_decoded;
 sfb_decoded* sfb_decode_json(const char* path, const int64_t* node_ids, const int32_t* node_len, int64_t n_nodes,
                              double thr, int n_threads, int64_t block_bytes);
+/* The same from the GAMP file `vg mpmap` writes (StrainFLAIR.sh:582), without the `vg view -j -K` conversion to JSON
+ * (:592-602): vg's stream framing (groups of length-prefixed messages, optional "MGAM" type tag, optional BGZF / gzip
+ * compression) around MultipathAlignment protobuf messages.  Restated from the published format -- no vg binary or GAMP
+ * file is at hand to pin it; block_records: messages decoded per block (<= 0: default). */
+sfb_decoded* sfb_decode_gamp(const char* path, const int64_t* node_ids, const int32_t* node_len, int64_t n_nodes,
+                             double thr, int n_threads, int64_t block_records);
 int          sfb_decoded_error(const sfb_decoded* d, const char** msg);
 int64_t      sfb_decoded_size(const sfb_decoded* d, int which);
 int          sfb_decoded_copy(const sfb_decoded* d, int which, void* dst);

@@ -106,7 +106,7 @@ ABI_VERSION = 11
 EXPORTS = ("sfb_abi_version", "sfb_version", "sfb_last_error", "sfb_expand_reads", "sfb_match", "sfb_classify", "sfb_pass1_scatter",
            "sfb_pass2", "sfb_pass2_resolve", "sfb_pass2_scatter", "sfb_accum_collapse", "sfb_path_reduce", "sfb_cluster_strain_counts", "sfb_strain_aggregate",
            "sfb_tile_pass1", "sfb_tile_pass2", "sfb_tile_smem_bytes", "sfb_tile_permute", "sfb_workspace_bytes",
-           "sfb_decode_json", "sfb_decoded_error", "sfb_decoded_size", "sfb_decoded_copy", "sfb_decoded_free",
+           "sfb_decode_json", "sfb_decode_gamp", "sfb_decoded_error", "sfb_decoded_size", "sfb_decoded_copy", "sfb_decoded_free",
            "sfb_min_strains", "sfb_wire_pack", "sfb_packed_status", "sfb_packed_size", "sfb_packed_copy", "sfb_packed_free",
            "sfb_load_gfa", "sfb_gfa_error", "sfb_gfa_size", "sfb_gfa_copy", "sfb_gfa_free", "sfb_locality_permute")
 
@@ -183,6 +183,8 @@ def load(build_if_missing=True):
     lib.sfb_packed_free.restype = None
     lib.sfb_decode_json.argtypes = [C.c_char_p, vp, vp, i64, f64, C.c_int, i64]
     lib.sfb_decode_json.restype = C.c_void_p
+    lib.sfb_decode_gamp.argtypes = [C.c_char_p, vp, vp, i64, f64, C.c_int, i64]
+    lib.sfb_decode_gamp.restype = C.c_void_p
     lib.sfb_decoded_error.argtypes = [vp, C.POINTER(C.c_char_p)]
     lib.sfb_decoded_error.restype = C.c_int
     lib.sfb_decoded_size.argtypes = [vp, C.c_int]

@@ -36,7 +36,7 @@ def run_json2csv(graph_file, mapping_file, pickle_file, prefix, thr=0.95, device
     t0 = time.perf_counter()
     print("Parsing Alignment: first pass")
     update_progress(0)
-    reads = decode.decode_json(mapping_file, graph, thr)
+    reads = decode.decode_alignments(mapping_file, graph, thr)      # `vg view -j -K` JSON, or the GAMP file itself
     t["decode_s"] = time.perf_counter() - t0
     t0 = time.perf_counter()
     eng = engine.AbundanceEngine(graph, device, deterministic=True)     # files out: bit-reproducible from run to run

@@ -17,6 +17,7 @@
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <zlib.h>
 #include <unistd.h>
 #include <atomic>
 #include <cmath>
@@ -313,6 +314,142 @@ void parse_line(const char* b, const char* e, Parsed& ln) {
     if (!has_name) throw Fail{E_KEY, "'name'"};
 }
 
+
+// ---- one GAMP record: vg's MultipathAlignment message (protobuf wire format) ----------------------------------
+// Field numbers of vg.proto as published with vg 1.2x (the schema is not vendored in the reference; what it reads of
+// the JSON rendering is listed in SURVEY.md section 8c): MultipathAlignment { sequence = 1, name = 3, subpath = 6,
+// start = 8, paired_read_name = 9 }, Subpath { path = 1, next = 2, score = 3 }, Path { mapping = 2 },
+// Mapping { position = 1, edit = 2 }, Position { node_id = 1 }, Edit { from_length = 1, to_length = 2, sequence = 3 }.
+// The same Parsed as a JSON line, with the same presence semantics (`vg view -j` omits fields at their default).
+struct Pb {
+    const uint8_t* p;
+    const uint8_t* e;
+    bool more() const { return p < e; }
+    uint64_t varint() {
+        uint64_t v = 0;
+        for (int shift = 0; shift < 70; shift += 7) {
+            if (p >= e) throw Fail{E_JSON, "truncated GAMP record"};
+            const uint8_t b = *p++;
+            v |= (uint64_t)(b & 0x7f) << (shift & 63);
+            if (!(b & 0x80)) return v;
+        }
+        throw Fail{E_JSON, "bad varint in GAMP record"};
+    }
+    Pb sub() {                                   // a length-delimited field
+        const uint64_t n = varint();
+        if (n > (uint64_t)(e - p)) throw Fail{E_JSON, "truncated GAMP record"};
+        Pb s{p, p + n};
+        p += n;
+        return s;
+    }
+    void skip(int wire) {
+        switch (wire) {
+            case 0: varint(); break;
+            case 1: if (e - p < 8) throw Fail{E_JSON, "truncated GAMP record"}; p += 8; break;
+            case 2: sub(); break;
+            case 5: if (e - p < 4) throw Fail{E_JSON, "truncated GAMP record"}; p += 4; break;
+            default: throw Fail{E_JSON, "unsupported wire type in GAMP record"};
+        }
+    }
+};
+template <class F>
+inline void pb_ints(Pb& c, int wire, F f) {       // a repeated integer field: packed or one by one
+    if (wire == 2) { Pb s = c.sub(); while (s.more()) f((long long)s.varint()); }
+    else if (wire == 0) f((long long)c.varint());
+    else c.skip(wire);
+}
+void parse_pb(const char* b, const char* e, Parsed& ln) {
+    Pb c{(const uint8_t*)b, (const uint8_t*)e};
+    ln.reset();
+    while (c.more()) {
+        const uint64_t key = c.varint();
+        const int field = (int)(key >> 3), wire = (int)(key & 7);
+        if (wire == 2 && (field == 1 || field == 3 || field == 9)) {
+            Pb v = c.sub();
+            const char* q = (const char*)v.p;
+            const size_t n = (size_t)(v.e - v.p);
+            if (field == 1) { ln.seq = q; ln.seq_n = n; ln.has_seq = n > 0; }
+            else if (field == 3) { ln.name = q; ln.name_n = n; }
+            else { ln.pair = n ? q : nullptr; ln.pair_n = n; }
+        } else if (field == 8) {
+            ln.has_start = true;
+            pb_ints(c, wire, [&](long long v) { ln.start.push_back((int)v); });
+        } else if (field == 6 && wire == 2) {
+            ln.has_subpath = true;
+            Pb sc = c.sub();
+            Sub sp;
+            sp.m0 = sp.m1 = (uint32_t)ln.maps.size();
+            sp.n0 = sp.n1 = (uint32_t)ln.nexts.size();
+            sp.score = 0.0;
+            sp.has_next = false;
+            bool has_path = false, has_mapping = false;
+            while (sc.more()) {
+                const uint64_t k2 = sc.varint();
+                const int f2 = (int)(k2 >> 3), w2 = (int)(k2 & 7);
+                if (f2 == 3 && w2 == 0) {
+                    sp.score = (double)(int32_t)sc.varint();              // int32: negative values are sign-extended varints
+                } else if (f2 == 2) {
+                    pb_ints(sc, w2, [&](long long v) { ln.nexts.push_back((int)v); sp.has_next = true; });
+                    sp.n1 = (uint32_t)ln.nexts.size();
+                } else if (f2 == 1 && w2 == 2) {
+                    has_path = true;
+                    Pb pc = sc.sub();
+                    while (pc.more()) {
+                        const uint64_t k3 = pc.varint();
+                        if ((k3 >> 3) != 2 || (k3 & 7) != 2) { pc.skip((int)(k3 & 7)); continue; }
+                        has_mapping = true;
+                        Pb mc = pc.sub();
+                        Mapping mp;
+                        mp.node = -1;
+                        mp.has_edit = false;
+                        mp.e0 = mp.e1 = (uint32_t)ln.edits.size();
+                        bool has_pos = false, has_node = false;
+                        while (mc.more()) {
+                            const uint64_t k4 = mc.varint();
+                            const int f4 = (int)(k4 >> 3), w4 = (int)(k4 & 7);
+                            if (f4 == 1 && w4 == 2) {
+                                has_pos = true;
+                                Pb qc = mc.sub();
+                                while (qc.more()) {
+                                    const uint64_t k5 = qc.varint();
+                                    if ((k5 >> 3) == 1 && (k5 & 7) == 0) { mp.node = (long long)qc.varint(); has_node = true; }
+                                    else qc.skip((int)(k5 & 7));
+                                }
+                            } else if (f4 == 2 && w4 == 2) {
+                                mp.has_edit = true;
+                                Pb ec = mc.sub();
+                                Edit ed{0, 0, false};
+                                while (ec.more()) {
+                                    const uint64_t k5 = ec.varint();
+                                    const int f5 = (int)(k5 >> 3), w5 = (int)(k5 & 7);
+                                    if (f5 == 1 && w5 == 0) ed.from = (int)ec.varint();
+                                    else if (f5 == 2 && w5 == 0) ed.to = (int)ec.varint();
+                                    else if (f5 == 3 && w5 == 2) { Pb t = ec.sub(); ed.has_seq = t.e > t.p; }
+                                    else ec.skip(w5);
+                                }
+                                ln.edits.push_back(ed);
+                                mp.e1 = (uint32_t)ln.edits.size();
+                            } else {
+                                mc.skip(w4);
+                            }
+                        }
+                        if (!has_pos || !has_node) mp.node = -2;          // KeyError 'position' / 'node_id' when used
+                        ln.maps.push_back(mp);
+                    }
+                } else {
+                    sc.skip(w2);
+                }
+            }
+            sp.m1 = (uint32_t)ln.maps.size();
+            if (!has_path || !has_mapping) sp.m0 = sp.m1 = UINT32_MAX;        // KeyError when used
+            ln.subs.push_back(sp);
+        } else {
+            c.skip(wire);
+        }
+    }
+    if (!ln.name) throw Fail{E_KEY, "'name'"};           // `vg view -j` prints no "name" key for an empty name
+}
+
 struct NodeTable {
     const int64_t* ids;
     const int32_t* len;
@@ -562,7 +699,7 @@ void route_to_aln(const Parsed& ln, const Router& rt, const Route& route, const 
     ar.alns.push_back(a);
 }
 
-void decode_line(const char* b, const char* e, Worker& w, int tid, const NodeTable& nt, LineOut& out) {
+void decode_line(const char* b, const char* e, Worker& w, int tid, const NodeTable& nt, LineOut& out, bool pb = false) {
     Arena& ar = w.arena;
     out.line = b;
     out.fail = -1;
@@ -571,7 +708,7 @@ void decode_line(const char* b, const char* e, Worker& w, int tid, const NodeTab
     out.naln = 0;
     const size_t rec_mark = ar.node.size();
     try {
-        parse_line(b, e, w.parsed);
+        if (pb) parse_pb(b, e, w.parsed); else parse_line(b, e, w.parsed);
         if (w.parsed.has_subpath) {
             w.router.run(w.parsed);
             for (uint32_t r : w.router.best) route_to_aln(w.parsed, w.router, w.router.routes[r], nt, ar);
@@ -591,12 +728,22 @@ void decode_line(const char* b, const char* e, Worker& w, int tid, const NodeTab
     out.seq = p.seq;
     out.seq_n = (uint32_t)p.seq_n;
     out.has_name = p.name != nullptr;
-    out.name_off = (uint32_t)ar.text.size();
-    out.name_n = (uint32_t)p.name_n;
-    if (p.name_n) ar.text.insert(ar.text.end(), p.name, p.name + p.name_n);
-    out.pair_off = (uint32_t)ar.text.size();
-    out.pair_n = (uint32_t)p.pair_n;
-    if (p.pair_n) ar.text.insert(ar.text.end(), p.pair, p.pair + p.pair_n);
+    // names are kept as JSON text (escapes are undone when they are written out); raw protobuf names are brought to
+    // that form by doubling their backslashes
+    auto put = [&](const char* q, size_t n, uint32_t& off, uint32_t& len) {
+        off = (uint32_t)ar.text.size();
+        if (!pb || !n || !memchr(q, '\\', n)) {
+            if (n) ar.text.insert(ar.text.end(), q, q + n);
+        } else {
+            for (size_t i = 0; i < n; ++i) {
+                if (q[i] == '\\') ar.text.push_back('\\');
+                ar.text.push_back(q[i]);
+            }
+        }
+        len = (uint32_t)(ar.text.size() - off);
+    };
+    put(p.name, p.name_n, out.name_off, out.name_n);
+    put(p.pair, p.pair_n, out.pair_off, out.pair_n);
     out.has_seq = p.has_seq;
     out.has_subpath = p.has_subpath;
 }
@@ -845,6 +992,76 @@ void run_parallel(int T, size_t n_items, size_t grain, F&& body) {
     for (auto& th : pool) th.join();
 }
 
+// Phases B-E for the decoded records of one block (JSON lines or GAMP messages): read-group boundaries, what every mate
+// keeps, offsets, fill.  Returns the number of records consumed; 0 (with eof false): one read group larger than the block.
+struct BlockTimes { double b, c, e; };
+size_t finish_block(sfb_decoded* D, std::vector<LineOut>& lines, std::vector<Group>& groups, std::vector<Worker>& workers,
+                    std::vector<std::vector<Exc>>& exc, int T, double thr, const int32_t* node_len, bool eof, BlockTimes& bt) {
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t0;
+    double &t_b = bt.b, &t_c = bt.c, &t_e = bt.e;
+    // B: groups
+    t0 = now();
+    groups.clear();
+    const size_t used = find_groups(lines, workers, eof, groups);
+    t_b += now() - t0;
+    if (used == 0 && !eof) return 0;       // one read group larger than the block: the caller widens the block
+    // C: what every mate keeps
+    t0 = now();
+    run_parallel(T, groups.size(), 512, [&](size_t lo, size_t hi, int tid) {
+        for (size_t g = lo; g < hi; ++g) select_group(groups[g], lines, workers, tid, thr);
+    });
+    // D: offsets
+    OutBlock ob;
+    ob.G = (int64_t)groups.size();
+    int64_t aln = D->n_alns, rec = D->n_recs, nb = D->n_name_bytes;
+    for (Group& g : groups) {
+        g.aln_base = aln;
+        g.rec_base = rec;
+        g.name_base = nb;
+        aln += g.n_aln[0] + g.n_aln[1];
+        rec += g.n_rec;
+        nb += g.name_bytes[0] + g.name_bytes[1];
+    }
+    ob.A = aln - D->n_alns;
+    ob.R = rec - D->n_recs;
+    ob.NB = nb - D->n_name_bytes;
+    t_c += now() - t0;
+    // E: fill
+    t0 = now();
+    ob.grp_nmates.alloc((size_t)ob.G);
+    ob.grp_aln_off.alloc((size_t)ob.G * 2);
+    ob.name_off.alloc((size_t)ob.G * 2);
+    ob.mate_seq_len.alloc((size_t)ob.G * 2);
+    ob.aln_walk_off.alloc((size_t)ob.A);
+    ob.aln_read_len.alloc((size_t)ob.A);
+    ob.aln_bins.alloc((size_t)ob.A * 5);
+    ob.aln_stats.alloc((size_t)ob.A * 5);
+    ob.walk_node.alloc((size_t)ob.R);
+    ob.walk_alen.alloc((size_t)ob.R);
+    ob.names.alloc((size_t)ob.NB);
+    const int64_t a0 = D->n_alns, r0 = D->n_recs, n0 = D->n_name_bytes;
+    run_parallel(T, groups.size(), 512, [&](size_t lo, size_t hi, int tid) {
+        for (size_t g = lo; g < hi; ++g)
+            fill_group(groups[g], g, ob, a0, r0, n0, lines, workers, tid, node_len, exc[(size_t)tid]);
+    });
+    // explicit coverages in record order (deterministic whatever the thread count)
+    std::vector<Exc> all;
+    for (auto& v : exc) { all.insert(all.end(), v.begin(), v.end()); v.clear(); }
+    std::sort(all.begin(), all.end(), [](const Exc& x, const Exc& y) { return x.rec < y.rec; });
+    for (const Exc& e : all) {
+        D->exc_cov.push_back(e.cov);
+        ob.walk_alen.p[(size_t)(e.rec - r0)] = -(int32_t)D->exc_cov.size();
+    }
+    D->n_groups += ob.G;
+    D->n_alns = aln;
+    D->n_recs = rec;
+    D->n_name_bytes = nb;
+    D->blocks.push_back(std::move(ob));
+    t_e += now() - t0;
+    return used;
+}
+
 }  // namespace
 
 extern "C" {
@@ -935,68 +1152,13 @@ sfb_decoded* sfb_decode_json(const char* path, const int64_t* node_ids, const in
                 }
             });
             t_a += now() - t0;
-            // B: groups
-            t0 = now();
-            groups.clear();
-            const size_t used = find_groups(lines, workers, eof, groups);
-            t_b += now() - t0;
+            BlockTimes bt{0, 0, 0};
+            const size_t used = finish_block(D, lines, groups, workers, exc, T, thr, node_len, eof, bt);
+            t_b += bt.b; t_c += bt.c; t_e += bt.e;
             if (used == 0 && !eof) {               // one read group larger than the block: widen the block
                 block_bytes *= 2;
                 continue;
             }
-            // C: what every mate keeps
-            t0 = now();
-            run_parallel(T, groups.size(), 512, [&](size_t lo, size_t hi, int tid) {
-                for (size_t g = lo; g < hi; ++g) select_group(groups[g], lines, workers, tid, thr);
-            });
-            // D: offsets
-            OutBlock ob;
-            ob.G = (int64_t)groups.size();
-            int64_t aln = D->n_alns, rec = D->n_recs, nb = D->n_name_bytes;
-            for (Group& g : groups) {
-                g.aln_base = aln;
-                g.rec_base = rec;
-                g.name_base = nb;
-                aln += g.n_aln[0] + g.n_aln[1];
-                rec += g.n_rec;
-                nb += g.name_bytes[0] + g.name_bytes[1];
-            }
-            ob.A = aln - D->n_alns;
-            ob.R = rec - D->n_recs;
-            ob.NB = nb - D->n_name_bytes;
-            t_c += now() - t0;
-            // E: fill
-            t0 = now();
-            ob.grp_nmates.alloc((size_t)ob.G);
-            ob.grp_aln_off.alloc((size_t)ob.G * 2);
-            ob.name_off.alloc((size_t)ob.G * 2);
-            ob.mate_seq_len.alloc((size_t)ob.G * 2);
-            ob.aln_walk_off.alloc((size_t)ob.A);
-            ob.aln_read_len.alloc((size_t)ob.A);
-            ob.aln_bins.alloc((size_t)ob.A * 5);
-            ob.aln_stats.alloc((size_t)ob.A * 5);
-            ob.walk_node.alloc((size_t)ob.R);
-            ob.walk_alen.alloc((size_t)ob.R);
-            ob.names.alloc((size_t)ob.NB);
-            const int64_t a0 = D->n_alns, r0 = D->n_recs, n0 = D->n_name_bytes;
-            run_parallel(T, groups.size(), 512, [&](size_t lo, size_t hi, int tid) {
-                for (size_t g = lo; g < hi; ++g)
-                    fill_group(groups[g], g, ob, a0, r0, n0, lines, workers, tid, node_len, exc[(size_t)tid]);
-            });
-            // explicit coverages in record order (deterministic whatever the thread count)
-            std::vector<Exc> all;
-            for (auto& v : exc) { all.insert(all.end(), v.begin(), v.end()); v.clear(); }
-            std::sort(all.begin(), all.end(), [](const Exc& x, const Exc& y) { return x.rec < y.rec; });
-            for (const Exc& e : all) {
-                D->exc_cov.push_back(e.cov);
-                ob.walk_alen.p[(size_t)(e.rec - r0)] = -(int32_t)D->exc_cov.size();
-            }
-            D->n_groups += ob.G;
-            D->n_alns = aln;
-            D->n_recs = rec;
-            D->n_name_bytes = nb;
-            D->blocks.push_back(std::move(ob));
-            t_e += now() - t0;
             pos = used < n_lines ? (size_t)(lines[used].line - data) : end;
         }
         if (trace)
@@ -1010,6 +1172,134 @@ sfb_decoded* sfb_decode_json(const char* path, const int64_t* node_ids, const in
         D->err_msg = ex.what();
     }
     if (data) munmap((void*)data, size);
+    if (fd >= 0) close(fd);
+    return D;
+}
+
+
+// ---- GAMP: the file `vg mpmap` writes (StrainFLAIR.sh:582), without the `vg view -j -K` hop (:592-602) ---------------
+// Container (vg's stream framing, libvgio): optionally BGZF / gzip compressed; a sequence of groups, each a varint
+// message count followed by that many (varint length, bytes) messages; in the type-tagged flavour the first message
+// of every group is the tag "MGAM".  Restated from the published format: no vg binary, schema or GAMP file is
+// available in the reference checkout or in this image -- parity unpinned (the tests write GAMP files with the
+// protobuf library from the golden JSON cases and require decode(GAMP) == decode(JSON)).
+sfb_decoded* sfb_decode_gamp(const char* path, const int64_t* node_ids, const int32_t* node_len, int64_t n_nodes,
+                             double thr, int n_threads, int64_t block_records) {
+    sfb_decoded* D = new sfb_decoded();
+    int fd = -1;
+    const char* map = nullptr;
+    size_t map_size = 0;
+    std::vector<char> plain;                      // the decompressed stream (the records point into it)
+    try {
+        fd = open(path, O_RDONLY);
+        if (fd < 0) throw Fail{E_IO, std::string("cannot open ") + path};
+        struct stat sb;
+        if (fstat(fd, &sb) != 0) throw Fail{E_IO, "fstat failed"};
+        map_size = (size_t)sb.st_size;
+        if (map_size) {
+            void* m = mmap(nullptr, map_size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m == MAP_FAILED) throw Fail{E_IO, "mmap failed"};
+            map = (const char*)m;
+        }
+        const char* data = map;
+        size_t size = map_size;
+        if (size >= 2 && (uint8_t)map[0] == 0x1f && (uint8_t)map[1] == 0x8b) {
+            // gzip members one after the other (BGZF is that, with 64 KiB blocks)
+            z_stream zs;
+            memset(&zs, 0, sizeof zs);
+            if (inflateInit2(&zs, 16 + MAX_WBITS) != Z_OK) throw Fail{E_IO, "zlib: inflateInit2 failed"};
+            plain.resize(std::max<size_t>(1 << 20, map_size * 4));
+            size_t in_pos = 0, out_pos = 0;
+            zs.avail_in = 0;
+            for (;;) {
+                if (zs.avail_in == 0) {
+                    if (in_pos >= map_size) break;
+                    const size_t chunk = std::min<size_t>(map_size - in_pos, 1u << 30);
+                    zs.next_in = (Bytef*)(map + in_pos);
+                    zs.avail_in = (uInt)chunk;
+                    in_pos += chunk;
+                }
+                if (out_pos == plain.size()) plain.resize(plain.size() * 2);
+                const size_t room = std::min<size_t>(plain.size() - out_pos, 1u << 30);
+                zs.next_out = (Bytef*)(plain.data() + out_pos);
+                zs.avail_out = (uInt)room;
+                const int rc = inflate(&zs, Z_NO_FLUSH);
+                out_pos += room - zs.avail_out;
+                if (rc == Z_STREAM_END) {                  // end of a member: the next one starts right behind it
+                    if (zs.avail_in == 0 && in_pos >= map_size) break;
+                    if (inflateReset(&zs) != Z_OK) { inflateEnd(&zs); throw Fail{E_IO, "zlib: inflateReset failed"}; }
+                    continue;
+                }
+                if (rc != Z_OK && rc != Z_BUF_ERROR) { inflateEnd(&zs); throw Fail{E_IO, "zlib: corrupt compressed GAMP"}; }
+                if (rc == Z_BUF_ERROR && zs.avail_in == 0 && in_pos >= map_size) {
+                    inflateEnd(&zs);
+                    throw Fail{E_IO, "zlib: truncated compressed GAMP"};
+                }
+            }
+            inflateEnd(&zs);
+            plain.resize(out_pos);
+            data = plain.data();
+            size = plain.size();
+        }
+        // the records of the stream
+        std::vector<std::pair<size_t, size_t>> recs;
+        {
+            Pb c{(const uint8_t*)data, (const uint8_t*)data + size};
+            auto is_tag = [](const uint8_t* b, size_t n) {
+                if (n == 0 || n > 24) return false;
+                for (size_t i = 0; i < n; ++i)
+                    if (!((b[i] >= 'A' && b[i] <= 'Z') || (b[i] >= '0' && b[i] <= '9') || b[i] == '_')) return false;
+                return true;
+            };
+            while (c.more()) {
+                const uint64_t count = c.varint();
+                for (uint64_t k = 0; k < count; ++k) {
+                    Pb m = c.sub();
+                    const size_t n = (size_t)(m.e - m.p);
+                    if (k == 0 && is_tag(m.p, n)) {      // type tag of the group (a MultipathAlignment never looks like one)
+                        if (!(n == 4 && memcmp(m.p, "MGAM", 4) == 0))
+                            throw Fail{E_JSON, "not a GAMP stream: type tag '" + std::string((const char*)m.p, n) + "'"};
+                        continue;
+                    }
+                    recs.emplace_back((size_t)((const char*)m.p - data), (size_t)((const char*)m.e - data));
+                }
+            }
+        }
+        if (block_records <= 0) block_records = 1 << 20;
+        NodeTable nt{node_ids, node_len, n_nodes, {}, {}};
+        nt.build();
+        const int T = std::max(1, std::min(n_threads, 4096));
+        std::vector<Worker> workers((size_t)T);
+        std::vector<std::vector<Exc>> exc((size_t)T);
+        std::vector<LineOut> lines;
+        std::vector<Group> groups;
+        size_t pos = 0;
+        while (pos < recs.size()) {
+            const size_t end = std::min(recs.size(), pos + (size_t)block_records);
+            const bool eof = end >= recs.size();
+            for (Worker& w : workers) { w.arena.clear(); w.sel.clear(); }
+            lines.resize(end - pos);
+            run_parallel(T, end - pos, 256, [&](size_t lo, size_t hi, int tid) {
+                for (size_t i = lo; i < hi; ++i)
+                    decode_line(data + recs[pos + i].first, data + recs[pos + i].second, workers[(size_t)tid], tid, nt, lines[i], true);
+            });
+            groups.clear();
+            BlockTimes bt{0, 0, 0};
+            const size_t used = finish_block(D, lines, groups, workers, exc, T, thr, node_len, eof, bt);
+            if (used == 0 && !eof) {               // one read group larger than the block: widen the block
+                block_records *= 2;
+                continue;
+            }
+            pos += used < lines.size() ? used : end - pos;
+        }
+    } catch (const Fail& f) {
+        D->err_kind = f.kind;
+        D->err_msg = f.msg;
+    } catch (const std::exception& ex) {
+        D->err_kind = E_IO;
+        D->err_msg = ex.what();
+    }
+    if (map) munmap((void*)map, map_size);
     if (fd >= 0) close(fd);
     return D;
 }

@@ -14,7 +14,26 @@ from .schema import Graph, Reads
 _ERRORS = {1: ValueError, 2: KeyError, 3: ZeroDivisionError, 4: IndexError, 5: OSError, 6: ValueError}
 
 
-def decode_json(json_path, graph: Graph, thr=0.95, threads=None, block_bytes=0, want_cov=False) -> Reads:
+def is_gamp(path):
+    """GAMP (what `vg mpmap` writes, StrainFLAIR.sh:582) or its `vg view -j -K` JSON rendering (:592-602)?  JSON lines
+    start with '{'; a GAMP stream starts with a gzip / BGZF header or with a small binary varint."""
+    with open(path, "rb") as fh:
+        head = fh.read(64).lstrip()
+    return bool(head) and not head.startswith(b"{")
+
+
+def decode_alignments(path, graph: Graph, thr=0.95, **kw) -> Reads:
+    """The alignment file of a query, whichever of the two forms it is in."""
+    return decode_gamp(path, graph, thr, **kw) if is_gamp(path) else decode_json(path, graph, thr, **kw)
+
+
+def decode_gamp(gamp_path, graph: Graph, thr=0.95, threads=None, block_records=0, want_cov=False) -> Reads:
+    """Decode the GAMP file of `vg mpmap` directly (no JSON hop): same Reads as ``decode_json`` of its JSON rendering.
+    The container and message layout are restated from vg's published format (parity unpinned: no vg at hand)."""
+    return decode_json(gamp_path, graph, thr, threads, block_records, want_cov, _gamp=True)
+
+
+def decode_json(json_path, graph: Graph, thr=0.95, threads=None, block_bytes=0, want_cov=False, _gamp=False) -> Reads:
     """Decode a whole alignment file.  Raises the exception class the reference would raise on bad input
     (unknown node id -> KeyError, zero-length read -> ZeroDivisionError, malformed line -> ValueError)."""
     from . import cache
@@ -28,8 +47,8 @@ def decode_json(json_path, graph: Graph, thr=0.95, threads=None, block_bytes=0, 
     ids = np.ascontiguousarray(graph.node_ids, np.int64)
     lens = np.ascontiguousarray(graph.node_len, np.int32)
     t0 = time.perf_counter()
-    h = lib.sfb_decode_json(os.fsencode(json_path), ids.ctypes.data, lens.ctypes.data, len(ids), float(thr),
-                            int(threads), int(block_bytes))
+    entry = lib.sfb_decode_gamp if _gamp else lib.sfb_decode_json
+    h = entry(os.fsencode(json_path), ids.ctypes.data, lens.ctypes.data, len(ids), float(thr), int(threads), int(block_bytes))
     try:
         msg = C.c_char_p()
         kind = lib.sfb_decoded_error(h, C.byref(msg))
