@@ -92,86 +92,58 @@ __host__ __device__ inline TileLayout tile_layout(int pass, int ms, int mn, int 
     return L;
 }
 
+// The block's shared memory.  Everything in it is addressed as (this array + an offset of the layout): the layout is a
+// __grid_constant__ kernel parameter, so the offsets are constant-bank operands and every access is an LDS / STS / ATOMS
+// on a known shared address (pointers kept in a struct ended up in local memory and turned every access into a generic
+// load behind a local one).
+extern __shared__ __align__(16) unsigned char sfb_smem[];
+
 struct TileS {
-    u64* hkey;
-    long long* pseq;
-    long long* pU;
-    longlong2* rec;      // .x = total of unique counts over the candidate set | bits of an explicit share, .y = n | len << 32
-    u64* emask;
-    u64* nmask;
-    u64* amask;          // [rows][2] forward / reverse path set of an alignment (simple tile; shares `tup`'s memory)
-    uint32_t* bins;      // [ns][3] limbs x0, x1, x2
-    uint32_t* plimb;     // [reps][np][7]: count / flag, three limbs A, three limbs B
-    uint32_t* la;
-    uint32_t* lx;
-    int* lseq;
-    uint32_t* alist;
-    uint32_t* glist;
-    int* pclu;
-    int* pstr0;
-    int* pnstr;
-    uint32_t* hcnt;
-    BlockCounters* sc;
-    int* misc;           // [0] work item, [1] fill of phase S's list, [2] listed alignments, [3] listed groups, [4] records
-    uint16_t* lt;
-    uint16_t* lm;
-    uint16_t* grow;
-    uint32_t* woff;
-    uint16_t* wnode;
-    uint32_t* goff;
-    uint16_t* poff;
-    uint16_t* node;
-    uint16_t* occ;
-    uint16_t* occ_off;
-    uint16_t* eoff;
-    uint16_t* esucc;
-    uint16_t* tup;
-    uint8_t* spath;
-    uint8_t* cnt;
+    TileLayout L;        // by value: its fields are kernel constants (constant-bank operands), not loads through a pointer
+    __device__ __forceinline__ u64* hkey() const { return reinterpret_cast<u64*>(sfb_smem + L.hkey); }
+    __device__ __forceinline__ long long* pseq() const { return reinterpret_cast<long long*>(sfb_smem + L.pseq); }
+    __device__ __forceinline__ long long* pU() const { return reinterpret_cast<long long*>(sfb_smem + L.pU); }
+    __device__ __forceinline__ longlong2* rec() const { return reinterpret_cast<longlong2*>(sfb_smem + L.rec); }
+    __device__ __forceinline__ u64* emask() const { return reinterpret_cast<u64*>(sfb_smem + L.emask); }
+    __device__ __forceinline__ u64* nmask() const { return reinterpret_cast<u64*>(sfb_smem + L.nmask); }
+    __device__ __forceinline__ u64* amask() const { return reinterpret_cast<u64*>(sfb_smem + L.store); }
+    __device__ __forceinline__ uint16_t* tup() const { return reinterpret_cast<uint16_t*>(sfb_smem + L.store); }
+    __device__ __forceinline__ uint32_t* bins() const { return reinterpret_cast<uint32_t*>(sfb_smem + L.bins); }
+    __device__ __forceinline__ uint32_t* plimb() const { return reinterpret_cast<uint32_t*>(sfb_smem + L.plimb); }
+    __device__ __forceinline__ uint32_t* la() const { return reinterpret_cast<uint32_t*>(sfb_smem + L.la); }
+    __device__ __forceinline__ uint32_t* lx() const { return reinterpret_cast<uint32_t*>(sfb_smem + L.lx); }
+    __device__ __forceinline__ int* lseq() const { return reinterpret_cast<int*>(sfb_smem + L.lseq); }
+    __device__ __forceinline__ uint32_t* alist() const { return reinterpret_cast<uint32_t*>(sfb_smem + L.alist); }
+    __device__ __forceinline__ uint32_t* glist() const { return reinterpret_cast<uint32_t*>(sfb_smem + L.glist); }
+    __device__ __forceinline__ int* pclu() const { return reinterpret_cast<int*>(sfb_smem + L.pclu); }
+    __device__ __forceinline__ int* pstr0() const { return reinterpret_cast<int*>(sfb_smem + L.pstr0); }
+    __device__ __forceinline__ int* pnstr() const { return reinterpret_cast<int*>(sfb_smem + L.pnstr); }
+    __device__ __forceinline__ uint32_t* hcnt() const { return reinterpret_cast<uint32_t*>(sfb_smem + L.hcnt); }
+    __device__ __forceinline__ int* misc() const { return reinterpret_cast<int*>(sfb_smem + L.misc); }
+    __device__ __forceinline__ uint16_t* lt() const { return reinterpret_cast<uint16_t*>(sfb_smem + L.lt); }
+    __device__ __forceinline__ uint16_t* lm() const { return reinterpret_cast<uint16_t*>(sfb_smem + L.lm); }
+    __device__ __forceinline__ uint16_t* grow() const { return reinterpret_cast<uint16_t*>(sfb_smem + L.grow); }
+    __device__ __forceinline__ uint32_t* woff() const { return reinterpret_cast<uint32_t*>(sfb_smem + L.woff); }
+    __device__ __forceinline__ uint16_t* wnode() const { return reinterpret_cast<uint16_t*>(sfb_smem + L.wnode); }
+    __device__ __forceinline__ uint32_t* goff() const { return reinterpret_cast<uint32_t*>(sfb_smem + L.goff); }
+    __device__ __forceinline__ uint16_t* poff() const { return reinterpret_cast<uint16_t*>(sfb_smem + L.poff); }
+    __device__ __forceinline__ uint16_t* node() const { return reinterpret_cast<uint16_t*>(sfb_smem + L.node); }
+    __device__ __forceinline__ uint16_t* occ() const { return reinterpret_cast<uint16_t*>(sfb_smem + L.occ); }
+    __device__ __forceinline__ uint16_t* occ_off() const { return reinterpret_cast<uint16_t*>(sfb_smem + L.occ_off); }
+    __device__ __forceinline__ uint16_t* eoff() const { return reinterpret_cast<uint16_t*>(sfb_smem + L.eoff); }
+    __device__ __forceinline__ uint16_t* esucc() const { return reinterpret_cast<uint16_t*>(sfb_smem + L.esucc); }
+    __device__ __forceinline__ uint8_t* spath() const { return reinterpret_cast<uint8_t*>(sfb_smem + L.spath); }
+    __device__ __forceinline__ uint8_t* cnt() const { return reinterpret_cast<uint8_t*>(sfb_smem + L.cnt); }
+    __device__ __forceinline__ BlockCounters* sc() const { return reinterpret_cast<BlockCounters*>(sfb_smem + L.sc); }
     int p0, np, n0, nn, s0, ns, mp, reps;
     bool simple;
     i64 a_item;          // first alignment of the work item
     i64 a_row0;          // pass 1: alignment of row 0 of the window
     i64 w_row0;          // pass 1: first walk record of the window
 };
-__device__ __forceinline__ TileS tile_carve(int pass, unsigned char* smem, const sfb_tiles& t) {
-    const TileLayout L = tile_layout(pass, (int)t.max_slots, (int)t.max_nodes, (int)t.max_paths, (int)t.max_edges, (int)t.tuple_cap);
+__device__ __forceinline__ TileS tile_carve(const TileLayout& L, const sfb_tiles& t) {
     TileS T;
-    T.hkey = reinterpret_cast<u64*>(smem + L.hkey);
-    T.pseq = reinterpret_cast<long long*>(smem + L.pseq);
-    T.pU = reinterpret_cast<long long*>(smem + L.pU);
-    T.rec = reinterpret_cast<longlong2*>(smem + L.rec);
-    T.emask = reinterpret_cast<u64*>(smem + L.emask);
-    T.nmask = reinterpret_cast<u64*>(smem + L.nmask);
-    T.amask = reinterpret_cast<u64*>(smem + L.store);
-    T.tup = reinterpret_cast<uint16_t*>(smem + L.store);
-    T.bins = reinterpret_cast<uint32_t*>(smem + L.bins);
-    T.plimb = reinterpret_cast<uint32_t*>(smem + L.plimb);
-    T.la = reinterpret_cast<uint32_t*>(smem + L.la);
-    T.lx = reinterpret_cast<uint32_t*>(smem + L.lx);
-    T.lseq = reinterpret_cast<int*>(smem + L.lseq);
-    T.alist = reinterpret_cast<uint32_t*>(smem + L.alist);
-    T.glist = reinterpret_cast<uint32_t*>(smem + L.glist);
-    T.pclu = reinterpret_cast<int*>(smem + L.pclu);
-    T.pstr0 = reinterpret_cast<int*>(smem + L.pstr0);
-    T.pnstr = reinterpret_cast<int*>(smem + L.pnstr);
-    T.hcnt = reinterpret_cast<uint32_t*>(smem + L.hcnt);
-    T.sc = reinterpret_cast<BlockCounters*>(smem + L.sc);
-    T.misc = reinterpret_cast<int*>(smem + L.misc);
-    T.lt = reinterpret_cast<uint16_t*>(smem + L.lt);
-    T.lm = reinterpret_cast<uint16_t*>(smem + L.lm);
-    T.woff = reinterpret_cast<uint32_t*>(smem + L.woff);
-    T.wnode = reinterpret_cast<uint16_t*>(smem + L.wnode);
-    T.goff = reinterpret_cast<uint32_t*>(smem + L.goff);
-    T.grow = reinterpret_cast<uint16_t*>(smem + L.grow);
-    T.poff = reinterpret_cast<uint16_t*>(smem + L.poff);
-    T.node = reinterpret_cast<uint16_t*>(smem + L.node);
-    T.occ = reinterpret_cast<uint16_t*>(smem + L.occ);
-    T.occ_off = reinterpret_cast<uint16_t*>(smem + L.occ_off);
-    T.eoff = reinterpret_cast<uint16_t*>(smem + L.eoff);
-    T.esucc = reinterpret_cast<uint16_t*>(smem + L.esucc);
-    T.spath = smem + L.spath;
-    T.cnt = smem + L.cnt;
+    T.L = L;
     T.p0 = T.np = T.n0 = T.nn = T.s0 = T.ns = 0;
     T.mp = (int)t.max_paths;
     T.reps = tile_reps(T.mp);
@@ -219,7 +191,7 @@ __device__ __forceinline__ void fx_flush(double* p, i64 det_stride, const uint32
 // add the weight itself, split once; with weight 1 that is the integer 1.
 __device__ __forceinline__ void tile_add_records(const TileS& T, const sfb_reads& r, i64 w0, int L, int slot, bool unit,
                                                  double weight) {
-    uint32_t* b = T.bins + 3 * slot;
+    uint32_t* b = T.bins() + 3 * slot;
     Fx whole;
     whole.x0 = whole.x1 = 0u;
     whole.x2 = 1u;
@@ -249,37 +221,37 @@ __device__ __forceinline__ void tile_stage(TileS& T, const Dev& d, const sfb_til
     const int tid = threadIdx.x;
     for (int i = tid; i < T.ns; i += kTT) {
         const int v = d.g.slot_node[T.s0 + i];
-        T.node[i] = v < 0 ? (uint16_t)kSentinel : (uint16_t)(v - T.n0);
+        T.node()[i] = v < 0 ? (uint16_t)kSentinel : (uint16_t)(v - T.n0);
     }
-    if (tid < 2) T.node[T.ns + tid] = (uint16_t)kSentinel;
+    if (tid < 2) T.node()[T.ns + tid] = (uint16_t)kSentinel;
     const int obase = d.g.occ_off[T.n0];
-    for (int i = tid; i <= T.nn; i += kTT) T.occ_off[i] = (uint16_t)(d.g.occ_off[T.n0 + i] - obase);
+    for (int i = tid; i <= T.nn; i += kTT) T.occ_off()[i] = (uint16_t)(d.g.occ_off[T.n0 + i] - obase);
     const int nocc = d.g.occ_off[T.n0 + T.nn] - obase;
     const int2* occ = reinterpret_cast<const int2*>(d.g.occ_pair);
-    for (int i = tid; i < nocc; i += kTT) T.occ[i] = (uint16_t)(occ[obase + i].x - T.s0);
-    for (int p = tid; p <= T.np; p += kTT) T.poff[p] = (uint16_t)(d.g.path_off[T.p0 + p] - T.s0);
+    for (int i = tid; i < nocc; i += kTT) T.occ()[i] = (uint16_t)(occ[obase + i].x - T.s0);
+    for (int p = tid; p <= T.np; p += kTT) T.poff()[p] = (uint16_t)(d.g.path_off[T.p0 + p] - T.s0);
     if (T.simple) {
         const int ebase = t.edge_off[T.n0];
-        for (int i = tid; i <= T.nn; i += kTT) T.eoff[i] = (uint16_t)(t.edge_off[T.n0 + i] - ebase);
+        for (int i = tid; i <= T.nn; i += kTT) T.eoff()[i] = (uint16_t)(t.edge_off[T.n0 + i] - ebase);
         const int ne = t.edge_off[T.n0 + T.nn] - ebase;
         for (int i = tid; i < ne; i += kTT) {
-            T.esucc[i] = (uint16_t)(t.edge_succ[ebase + i] - T.n0);
-            T.emask[i] = t.edge_mask[ebase + i];
+            T.esucc()[i] = (uint16_t)(t.edge_succ[ebase + i] - T.n0);
+            T.emask()[i] = t.edge_mask[ebase + i];
         }
-        for (int i = tid; i < T.nn; i += kTT) T.nmask[i] = t.node_mask[T.n0 + i];
+        for (int i = tid; i < T.nn; i += kTT) T.nmask()[i] = t.node_mask[T.n0 + i];
     }
     for (int p = tid; p < T.np; p += kTT) {
-        T.pseq[p] = d.g.path_seq_len[T.p0 + p];
-        T.pclu[p] = d.g.path_cluster[T.p0 + p];
-        T.pstr0[p] = d.g.path_strain0[T.p0 + p];
-        T.pnstr[p] = d.g.path_nstrain[T.p0 + p];
-        if (PASS == 2) T.pU[p] = U[T.p0 + p];
+        T.pseq()[p] = d.g.path_seq_len[T.p0 + p];
+        T.pclu()[p] = d.g.path_cluster[T.p0 + p];
+        T.pstr0()[p] = d.g.path_strain0[T.p0 + p];
+        T.pnstr()[p] = d.g.path_nstrain[T.p0 + p];
+        if (PASS == 2) T.pU()[p] = U[T.p0 + p];
     }
-    for (int i = tid; i < 3 * T.ns; i += kTT) T.bins[i] = 0u;
-    for (int i = tid; i < 7 * T.mp * T.reps; i += kTT) T.plimb[i] = 0u;
+    for (int i = tid; i < 3 * T.ns; i += kTT) T.bins()[i] = 0u;
+    for (int i = tid; i < 7 * T.mp * T.reps; i += kTT) T.plimb()[i] = 0u;
     for (int i = tid; i < kHash; i += kTT) {
-        T.hkey[i] = kHashEmpty;
-        T.hcnt[i] = 0u;
+        T.hkey()[i] = kHashEmpty;
+        T.hcnt()[i] = 0u;
     }
     __syncthreads();
     // slot -> local path: binary search over the staged path offsets
@@ -287,9 +259,9 @@ __device__ __forceinline__ void tile_stage(TileS& T, const Dev& d, const sfb_til
         int lo = 0, hi = T.np;               // largest p with poff[p] <= i
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
-            if ((int)T.poff[mid] <= i) lo = mid; else hi = mid;
+            if ((int)T.poff()[mid] <= i) lo = mid; else hi = mid;
         }
-        T.spath[i] = (uint8_t)lo;
+        T.spath()[i] = (uint8_t)lo;
     }
     __syncthreads();
 }
@@ -305,15 +277,15 @@ __device__ __forceinline__ void hist_out(const Dev& d, BlockCounters& sc, u64 ke
 }
 // histogram update of a read on path `p` (local), aggregated in the block's table (json2csv.py:333-339 / :1246-1252)
 __device__ __forceinline__ void tile_hist(const TileS& T, const Dev& d, BlockCounters& sc, int p, i64 a) {
-    if (T.pnstr[p] != 1) return;
+    if (T.pnstr()[p] != 1) return;
     const uint8_t* b = d.r.aln_bins + a * SFB_N_HIST;
-    const u64 key = ((u64)(uint32_t)T.pstr0[p] << 40) | (u64)b[0] | ((u64)b[1] << 8) | ((u64)b[2] << 16) |
+    const u64 key = ((u64)(uint32_t)T.pstr0()[p] << 40) | (u64)b[0] | ((u64)b[1] << 8) | ((u64)b[2] << 16) |
                     ((u64)b[3] << 24) | ((u64)b[4] << 32);
     unsigned h = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 56) & (kHash - 1);
     for (int probe = 0; probe < kHash; ++probe, h = (h + 1) & (kHash - 1)) {
-        const u64 old = atomicCAS(&T.hkey[h], kHashEmpty, key);
+        const u64 old = atomicCAS(&T.hkey()[h], kHashEmpty, key);
         if (old == kHashEmpty || old == key) {
-            atomicAdd(&T.hcnt[h], 1u);
+            atomicAdd(&T.hcnt()[h], 1u);
             return;
         }
     }
@@ -324,10 +296,10 @@ template <int PASS>
 __device__ __forceinline__ void tile_flush(const TileS& T, const Dev& d, BlockCounters& sc) {
     const int tid = threadIdx.x;
     double* slots = PASS == 1 ? d.acc.uniq_abund : d.acc.mult_abund;
-    for (int i = tid; i < T.ns; i += kTT) fx_flush(slots + T.s0 + i, d.acc.det_stride, T.bins + 3 * i);
+    for (int i = tid; i < T.ns; i += kTT) fx_flush(slots + T.s0 + i, d.acc.det_stride, T.bins() + 3 * i);
     for (int q = tid; q < T.np * T.reps; q += kTT) {
         const int p = q % T.np, rep = q / T.np;
-        const uint32_t* l = T.plimb + 7 * (rep * T.mp + p);
+        const uint32_t* l = T.plimb() + 7 * (rep * T.mp + p);
         const int pid = T.p0 + p;
         if (PASS == 1) {
             if (l[0]) atomicAdd((u64*)&d.acc.uniq_reads[pid], (u64)l[0]);
@@ -339,10 +311,10 @@ __device__ __forceinline__ void tile_flush(const TileS& T, const Dev& d, BlockCo
         }
     }
     for (int i = tid; i < kHash; i += kTT)
-        if (T.hkey[i] != kHashEmpty) hist_out(d, sc, T.hkey[i], T.hcnt[i]);
+        if (T.hkey()[i] != kHashEmpty) hist_out(d, sc, T.hkey()[i], T.hcnt()[i]);
 }
 __device__ __forceinline__ uint32_t* tile_plimb(const TileS& T, int p) {      // this warp's copy of path p's sums
-    return T.plimb + 7 * (((threadIdx.x >> 5) % T.reps) * T.mp + p);
+    return T.plimb() + 7 * (((threadIdx.x >> 5) % T.reps) * T.mp + p);
 }
 
 // ---- matching against the resident tile -------------------------------------------------------------------------
@@ -361,37 +333,37 @@ __device__ __forceinline__ void tile_enum(const TileS& T, const sfb_reads& r, i6
     const unsigned first = tile_local(T, r.walk_node[w0]);
     if (L == 1) {
         if (first == kNoNode) return;
-        for (int c = T.occ_off[first]; c < (int)T.occ_off[first + 1]; ++c) {
+        for (int c = T.occ_off()[first]; c < (int)T.occ_off()[first + 1]; ++c) {
             st.cand += 1;
-            f((int)T.occ[c], false);
+            f((int)T.occ()[c], false);
         }
         return;
     }
     const unsigned last = tile_local(T, r.walk_node[w0 + L - 1]);
     const unsigned second = tile_local(T, r.walk_node[w0 + 1]), penult = tile_local(T, r.walk_node[w0 + L - 2]);
     if (first != kNoNode)
-        for (int c = T.occ_off[first]; c < (int)T.occ_off[first + 1]; ++c) {
-            const int s = T.occ[c];
+        for (int c = T.occ_off()[first]; c < (int)T.occ_off()[first + 1]; ++c) {
+            const int s = T.occ()[c];
             st.cand += 1;
             st.cmp += 1;
-            if (T.node[s + 1] != second) continue;
+            if (T.node()[s + 1] != second) continue;
             bool ok = true;
             for (int i = 2; i < L && ok; ++i) {
                 st.cmp += 1;
-                ok = T.node[s + i] == tile_local(T, r.walk_node[w0 + i]);     // a sentinel ends the compare
+                ok = T.node()[s + i] == tile_local(T, r.walk_node[w0 + i]);     // a sentinel ends the compare
             }
             if (ok) f(s, false);
         }
     if (last != kNoNode)
-        for (int c = T.occ_off[last]; c < (int)T.occ_off[last + 1]; ++c) {
-            const int s = T.occ[c];
+        for (int c = T.occ_off()[last]; c < (int)T.occ_off()[last + 1]; ++c) {
+            const int s = T.occ()[c];
             st.cand += 1;
             st.cmp += 1;
-            if (T.node[s + 1] != penult) continue;
+            if (T.node()[s + 1] != penult) continue;
             bool ok = true;
             for (int i = 2; i < L && ok; ++i) {
                 st.cmp += 1;
-                ok = T.node[s + i] == tile_local(T, r.walk_node[w0 + L - 1 - i]);
+                ok = T.node()[s + i] == tile_local(T, r.walk_node[w0 + L - 1 - i]);
             }
             if (ok) f(s, true);
         }
@@ -402,13 +374,13 @@ template <int KA>
 __device__ __forceinline__ void tile_match_aln(const TileS& T, const sfb_reads& r, int row, i64 a, TileStats& st) {
     const i64 w0 = r.aln_walk_off[a];
     const int L = (int)(r.aln_walk_off[a + 1] - w0);
-    uint16_t* out = T.tup + row * KA;
+    uint16_t* out = T.tup() + row * KA;
     int n = 0;
     tile_enum(T, r, w0, L, st, [&](int s, bool rev) {
         if (n < KA) out[n] = (uint16_t)(s | ((int)rev << 15));
         ++n;
     });
-    T.cnt[row] = (uint8_t)(n > KA ? kOver : n);
+    T.cnt()[row] = (uint8_t)(n > KA ? kOver : n);
     st.tuples += n;
 }
 
@@ -431,12 +403,12 @@ struct TileView {
             na[k] = mt[k].na;
             int tot = 0;
             for (int j = 0; j < na[k]; ++j) {
-                const int c = T_.cnt[row[k] + j];
+                const int c = T_.cnt()[row[k] + j];
                 fits &= c != kOver;
                 tot += c;
             }
             n[k] = tot;
-            c0[k] = na[k] ? T_.cnt[row[k]] : 0;
+            c0[k] = na[k] ? T_.cnt()[row[k]] : 0;
         }
         return fits;
     }
@@ -445,12 +417,12 @@ struct TileView {
         if (i >= c0[k]) {
             i -= c0[k];
             j = 1;
-            for (int c; i >= (c = T->cnt[row[k] + j]); ++j) i -= c;
+            for (int c; i >= (c = T->cnt()[row[k] + j]); ++j) i -= c;
         }
-        return T->tup[(row[k] + j) * KA + i];
+        return T->tup()[(row[k] + j) * KA + i];
     }
     __device__ __forceinline__ int nt(int k) const { return n[k]; }
-    __device__ __forceinline__ int pid(int k, int i) const { int j; return T->p0 + T->spath[word(k, i, j) & 0x7fffu]; }
+    __device__ __forceinline__ int pid(int k, int i) const { int j; return T->p0 + T->spath()[word(k, i, j) & 0x7fffu]; }
     __device__ __forceinline__ uint32_t code(int k, int i) const {
         int j;
         const uint32_t w = word(k, i, j);
@@ -471,10 +443,10 @@ struct TileOps {
     __device__ __forceinline__ void hist(const Dev& d, BlockCounters& sc, int pid, i64 a) { tile_hist(*T, d, sc, pid - T->p0, a); }
     // fill_abund_dist (json2csv.py:321-339): listed with (tuple tiles) or without (simple tiles) the slot
     __device__ __forceinline__ void list_unique(i64 a, uint32_t x, int seq_len) {
-        const int q = atomicAdd(&T->misc[1], 1);             // an alignment is assigned at most once: q < kRows1
-        T->la[q] = (uint32_t)(a - T->a_item);
-        T->lx[q] = x;
-        T->lseq[q] = seq_len;
+        const int q = atomicAdd(&T->misc()[1], 1);             // an alignment is assigned at most once: q < kRows1
+        T->la()[q] = (uint32_t)(a - T->a_item);
+        T->lx()[q] = x;
+        T->lseq()[q] = seq_len;
     }
     __device__ __forceinline__ void assign_unique(const Dev& d, BlockCounters& sc, i64 a, uint32_t code, int pid, int seq_len) {
         d.w.aln_assign[a] = (int32_t)code;
@@ -483,32 +455,32 @@ struct TileOps {
     // cluster of the first path through the walk's first node (json2csv.py:875,901,1036); -1 = None, -2 = no path
     __device__ __forceinline__ int first_cluster(const Dev& d, i64 a) {
         const unsigned n = tile_local(*T, d.r.walk_node[d.r.aln_walk_off[a]]);
-        if (n == kNoNode || T->occ_off[n] == T->occ_off[n + 1]) return -2;
-        return T->pclu[T->spath[T->occ[T->occ_off[n]]]];
+        if (n == kNoNode || T->occ_off()[n] == T->occ_off()[n + 1]) return -2;
+        return T->pclu()[T->spath()[T->occ()[T->occ_off()[n]]]];
     }
     __device__ __forceinline__ void book(const Dev& d, BlockCounters& sc, const Mate& mt, int cluster) {
         if (cluster < 0) { SFB_COUNT(sc, SFB_C_NO_CLUSTER, 1); return; }
         d.w.aln_assign[mt.a0] = -(cluster + 2);
     }
-    __device__ __forceinline__ long long uniq(int pid) const { return T->pU[pid - T->p0]; }
+    __device__ __forceinline__ long long uniq(int pid) const { return T->pU()[pid - T->p0]; }
     // a share record: the shares of a candidate set are uniq[p] / total, or 1 / n when total is 0 (json2csv.py:1151-1154);
     // n < 0: `total` holds the bits of an explicit share.  -1 when the table is full.
     __device__ __forceinline__ int record(long long total, int n, int seq_len) {
-        const int k = atomicAdd(&T->misc[4], 1);
+        const int k = atomicAdd(&T->misc()[4], 1);
         if (k >= kRec2) return -1;
-        T->rec[k] = make_longlong2(total, (long long)(uint32_t)n | ((long long)seq_len << 32));
+        T->rec()[k] = make_longlong2(total, (long long)(uint32_t)n | ((long long)seq_len << 32));
         return k;
     }
     // one work item of pass 2 (json2csv.py:1155-1158 and twins); false when a list is full
     __device__ __forceinline__ bool list_share(i64 a, uint32_t x, int times, int rec) {
         st->app += 1;
         if (rec < 0 || times > 0xffff) return false;
-        const int q = atomicAdd(&T->misc[1], 1);
+        const int q = atomicAdd(&T->misc()[1], 1);
         if (q >= cap) return false;
-        T->la[q] = (uint32_t)(a - T->a_item);
-        T->lx[q] = x;
-        T->lt[q] = (uint16_t)times;
-        T->lm[q] = (uint16_t)rec;
+        T->la()[q] = (uint32_t)(a - T->a_item);
+        T->lx()[q] = x;
+        T->lt()[q] = (uint16_t)times;
+        T->lm()[q] = (uint16_t)rec;
         return true;
     }
     // generic logic (tuple tiles): the share comes computed
@@ -526,7 +498,7 @@ struct TileOps {
         uint32_t* l = tile_plimb(*T, p);
         l[0] = 1u;                                           // "touched" flag
         fx_smem_add(l + 1, fx_split(weight));
-        fx_smem_add(l + 4, fx_split((ratio * (double)seq_len / (double)T->pseq[p]) * (double)times));
+        fx_smem_add(l + 4, fx_split((ratio * (double)seq_len / (double)T->pseq()[p]) * (double)times));
         const i64 w0 = d.r.aln_walk_off[a];
         const int L = (int)(d.r.aln_walk_off[a + 1] - w0);
         tile_add_records(*T, d.r, w0, L, slot, false, weight);
@@ -535,8 +507,8 @@ struct TileOps {
 };
 // slot of node `n` (local) on path `p` (local) of a simple tile
 __device__ __forceinline__ int tile_slot_of(const TileS& T, unsigned n, int p) {
-    for (int c = T.occ_off[n]; c < (int)T.occ_off[n + 1]; ++c)
-        if (T.spath[T.occ[c]] == p) return T.occ[c];
+    for (int c = T.occ_off()[n]; c < (int)T.occ_off()[n + 1]; ++c)
+        if (T.spath()[T.occ()[c]] == p) return T.occ()[c];
     return 0;
 }
 // slot of a list entry: carried, or (simple tile) where path p has the walk's first node -- its last node for a match of
@@ -548,8 +520,8 @@ __device__ __forceinline__ int tile_entry_slot(const TileS& T, const sfb_reads& 
 }
 // phase S of pass 1: one unique assignment (fill_abund_dist, json2csv.py:321-339)
 __device__ __forceinline__ void tile_scatter1(TileS& T, const Dev& d, BlockCounters& sc, int q, TileStats& st) {
-    const i64 a = T.a_item + T.la[q];
-    const uint32_t x = T.lx[q];
+    const i64 a = T.a_item + T.la()[q];
+    const uint32_t x = T.lx()[q];
     const int p = (int)((x >> 16) & 0xffu);
     const i64 w0 = d.r.aln_walk_off[a];
     const int L = (int)(d.r.aln_walk_off[a + 1] - w0);
@@ -557,21 +529,21 @@ __device__ __forceinline__ void tile_scatter1(TileS& T, const Dev& d, BlockCount
     if (!(x & kHasSlot)) d.w.aln_assign[a] = (int32_t)tile_code(T, slot, (x & 1u) != 0);
     uint32_t* l = tile_plimb(T, p);
     atomicAdd(l, 1u);
-    fx_smem_add(l + 1, fx_split((double)T.lseq[q] / (double)T.pseq[p]));
+    fx_smem_add(l + 1, fx_split((double)T.lseq()[q] / (double)T.pseq()[p]));
     tile_hist(T, d, sc, p, a);
     tile_add_records(T, d.r, w0, L, slot, true, 1.0);
     st.rec += L;
 }
 // phase S of pass 2: one work item (json2csv.py:1155-1158)
 __device__ __forceinline__ void tile_scatter2(TileS& T, const Dev& d, int q, TileStats& st) {
-    if (T.lt[q] == 0) return;                                // reserved, then applied at once (a table was full)
-    const i64 a = T.a_item + T.la[q];
-    const uint32_t x = T.lx[q];
+    if (T.lt()[q] == 0) return;                                // reserved, then applied at once (a table was full)
+    const i64 a = T.a_item + T.la()[q];
+    const uint32_t x = T.lx()[q];
     const int p = (int)((x >> 16) & 0xffu);
-    const longlong2 rc = T.rec[T.lm[q]];
+    const longlong2 rc = T.rec()[T.lm()[q]];
     const int n = (int)(uint32_t)rc.y, seq_len = (int)(rc.y >> 32);
-    const double ratio = n < 0 ? __longlong_as_double(rc.x) : ratio_of(T.pU[p], rc.x, n);
-    const double times = (double)T.lt[q];
+    const double ratio = n < 0 ? __longlong_as_double(rc.x) : ratio_of(T.pU()[p], rc.x, n);
+    const double times = (double)T.lt()[q];
     const double weight = ratio * times;
     const i64 w0 = d.r.aln_walk_off[a];
     const int L = (int)(d.r.aln_walk_off[a + 1] - w0);
@@ -579,7 +551,7 @@ __device__ __forceinline__ void tile_scatter2(TileS& T, const Dev& d, int q, Til
     uint32_t* l = tile_plimb(T, p);
     l[0] = 1u;                                               // "touched" flag
     fx_smem_add(l + 1, fx_split(weight));
-    fx_smem_add(l + 4, fx_split((ratio * (double)seq_len / (double)T.pseq[p]) * times));
+    fx_smem_add(l + 4, fx_split((ratio * (double)seq_len / (double)T.pseq()[p]) * times));
     tile_add_records(T, d.r, w0, L, slot, false, weight);
     st.rec += L;
 }
@@ -593,13 +565,13 @@ __device__ __forceinline__ void tile_scatter2(TileS& T, const Dev& d, int q, Til
 // tuple order of the reference (json2csv.py:851-866: alignment by alignment, forward matches by ascending path, then
 // reverse) only matters for picking "the first" tuple; sums are exact integers here, so their order is free.
 __device__ __forceinline__ u64 tile_step(const TileS& T, unsigned n, unsigned succ) {
-    const int e0 = T.eoff[n], e1 = T.eoff[n + 1];
+    const int e0 = T.eoff()[n], e1 = T.eoff()[n + 1];
     // almost every node has one or two successors: two predicated probes, no loop
     u64 m = 0;
-    if (e0 < e1 && T.esucc[e0] == succ) m = T.emask[e0];
-    if (e0 + 1 < e1 && T.esucc[e0 + 1] == succ) m = T.emask[e0 + 1];
+    if (e0 < e1 && T.esucc()[e0] == succ) m = T.emask()[e0];
+    if (e0 + 1 < e1 && T.esucc()[e0 + 1] == succ) m = T.emask()[e0 + 1];
     for (int e = e0 + 2; e < e1; ++e)
-        if (T.esucc[e] == succ) m = T.emask[e];
+        if (T.esucc()[e] == succ) m = T.emask()[e];
     return m;
 }
 // phase M: forward / reverse path sets of alignment `a` into row `row`.  STAGED (pass 1): the walk offsets and the first
@@ -609,22 +581,22 @@ __device__ __forceinline__ void mask_match_aln(const TileS& T, const sfb_reads& 
     i64 w0;
     int L;
     if (STAGED) {
-        w0 = T.w_row0 + T.woff[row];
-        L = (int)(T.woff[row + 1] - T.woff[row]);
+        w0 = T.w_row0 + T.woff()[row];
+        L = (int)(T.woff()[row + 1] - T.woff()[row]);
     } else {
         w0 = r.aln_walk_off[a];
         L = (int)(r.aln_walk_off[a + 1] - w0);
     }
-    const unsigned rel = STAGED ? T.woff[row] : 0u;
+    const unsigned rel = STAGED ? T.woff()[row] : 0u;
     auto node_at = [&](int k) -> unsigned {
-        if (STAGED && rel + (unsigned)k < (unsigned)kStageRec) return T.wnode[rel + k];
+        if (STAGED && rel + (unsigned)k < (unsigned)kStageRec) return T.wnode()[rel + k];
         return tile_local(T, r.walk_node[w0 + k]);
     };
     u64 f = 0, rv = 0;
     if (L > 0) {
         unsigned prev = node_at(0);
         if (L == 1) {
-            if (prev != kNoNode) f = T.nmask[prev];
+            if (prev != kNoNode) f = T.nmask()[prev];
         } else if (prev != kNoNode) {
             f = rv = ~0ull;
             for (int k = 1; k < L; ++k) {
@@ -638,8 +610,8 @@ __device__ __forceinline__ void mask_match_aln(const TileS& T, const sfb_reads& 
             }
         }
     }
-    T.amask[2 * row] = f;
-    T.amask[2 * row + 1] = rv;
+    T.amask()[2 * row] = f;
+    T.amask()[2 * row + 1] = rv;
     const int n = __popcll(f) + __popcll(rv);
     st.cand += n;
     st.tuples += n;
@@ -659,7 +631,7 @@ struct MaskMate {
         S = dup = 0;
         nt = 0;
         for (int j = 0; j < 2 * na; ++j) {
-            const u64 x = T.amask[2 * row + j];
+            const u64 x = T.amask()[2 * row + j];
             dup |= S & x;
             S |= x;
             nt += __popcll(x);
@@ -667,13 +639,13 @@ struct MaskMate {
     }
     __device__ __forceinline__ int count(const TileS& T, int p) const {      // list_path_id.count(pid)
         int c = 0;
-        for (int j = 0; j < 2 * na; ++j) c += (int)((T.amask[2 * row + j] >> p) & 1ull);
+        for (int j = 0; j < 2 * na; ++j) c += (int)((T.amask()[2 * row + j] >> p) & 1ull);
         return c;
     }
     // the first tuple carrying path p: alignment j inside the mate, orientation
     __device__ __forceinline__ void find(const TileS& T, int p, int& j, bool& rev) const {
         for (int q = 0; q < 2 * na; ++q)
-            if ((T.amask[2 * row + q] >> p) & 1ull) { j = q >> 1; rev = q & 1; return; }
+            if ((T.amask()[2 * row + q] >> p) & 1ull) { j = q >> 1; rev = q & 1; return; }
         j = 0;
         rev = false;
     }
@@ -790,27 +762,27 @@ template <class W>
 __device__ __forceinline__ void mask_list(TileS& T, const Dev& d, TileOps& ops, const Mate& m, int row, int n_masks, u64 sel,
                                           long long total, int n, W&& times_of_path) {
     int cnt = 0;
-    for (int q = 0; q < n_masks; ++q) cnt += __popcll(T.amask[2 * row + q] & sel);
+    for (int q = 0; q < n_masks; ++q) cnt += __popcll(T.amask()[2 * row + q] & sel);
     if (cnt == 0) return;
     const int rec = ops.record(total, n, m.seq_len);
-    int at = atomicAdd(&T.misc[1], cnt);             // one reservation per candidate set, not one per work item
+    int at = atomicAdd(&T.misc()[1], cnt);             // one reservation per candidate set, not one per work item
     ops.st->app += cnt;
     for (int q = 0; q < n_masks; ++q)
-        for (u64 rest = T.amask[2 * row + q] & sel; rest; rest &= rest - 1, ++at) {
+        for (u64 rest = T.amask()[2 * row + q] & sel; rest; rest &= rest - 1, ++at) {
             const int p = __ffsll((long long)rest) - 1;
             const i64 a = m.a0 + (q >> 1);
             const int times = times_of_path(p);
             if (rec >= 0 && at < ops.cap && times <= 0xffff) {
-                T.la[at] = (uint32_t)(a - T.a_item);
-                T.lx[at] = ((uint32_t)p << 16) | (uint32_t)(q & 1);
-                T.lt[at] = (uint16_t)times;
-                T.lm[at] = (uint16_t)rec;
+                T.la()[at] = (uint32_t)(a - T.a_item);
+                T.lx()[at] = ((uint32_t)p << 16) | (uint32_t)(q & 1);
+                T.lt()[at] = (uint16_t)times;
+                T.lm()[at] = (uint16_t)rec;
                 continue;
             }
             ops.st->app -= 1;                // a list is full: the share here and now
-            if (at < ops.cap) T.lt[at] = 0;  // (a reserved entry that stays empty)
+            if (at < ops.cap) T.lt()[at] = 0;  // (a reserved entry that stays empty)
             ops.apply_now(d, a, (int)(mask_code(T, d.r, a, p, (q & 1) != 0) & SFB_SLOT_MASK) - T.s0, p, m.seq_len,
-                          ratio_of(T.pU[p], total, n), times);
+                          ratio_of(T.pU()[p], total, n), times);
         }
 }
 
@@ -822,7 +794,7 @@ __device__ __forceinline__ void mask_pass2_pair(TileS& T, const Dev& d, TileOps&
     const int n_inter = __popcll(inter);
     if (n_inter >= 1) {
         long long total = 0;
-        for (u64 rest = inter; rest; rest &= rest - 1) total += T.pU[__ffsll((long long)rest) - 1];
+        for (u64 rest = inter; rest; rest &= rest - 1) total += T.pU()[__ffsll((long long)rest) - 1];
         for (int k = 0; k < 2; ++k) {
             if (mm[k].dup & inter) {             // a common path with several tuples in this mate
                 SFB_COUNT(sc, SFB_C_MULTI_ALIGN, 1);
@@ -852,7 +824,7 @@ __device__ __forceinline__ void mask_pass2_pair(TileS& T, const Dev& d, TileOps&
             const int times = mask_times(d.g, T, mm, cut.common0, p);
             if (times == 0) continue;
             if (mm[k].count(T, p) != 1) { simple = false; break; }
-            tot += T.pU[p] * times;
+            tot += T.pU()[p] * times;
             sel |= 1ull << p;
         }
         if (!simple) {
@@ -869,7 +841,7 @@ __device__ __forceinline__ void mask_pass2_pair(TileS& T, const Dev& d, TileOps&
 
 // An aligned pair that does not fit the tuple buffers: its match lists in the format of sfb_match, the group on the
 // list of the generic classify kernel (which also takes care of its node loops and of its deferral).
-__device__ __noinline__ void tile_export(const TileS& T, const Dev& d, BlockCounters& sc, i64 g, const Mate* mt,
+__device__ __forceinline__ void tile_export(const TileS& T, const Dev& d, BlockCounters& sc, i64 g, const Mate* mt,
                                          TileStats& st) {
     uint2* aln_match = reinterpret_cast<uint2*>(d.w.aln_match);
     uint2* match_buf = reinterpret_cast<uint2*>(d.w.match_buf);
@@ -881,7 +853,7 @@ __device__ __noinline__ void tile_export(const TileS& T, const Dev& d, BlockCoun
             int n = 0;
             uint2 only = make_uint2(SFB_MATCH_NONE, 0u);
             tile_enum(T, d.r, w0, L, st, [&](int s, bool rev) {
-                if (n++ == 0) only = make_uint2(tile_code(T, s, rev), (uint32_t)(T.p0 + T.spath[s]));
+                if (n++ == 0) only = make_uint2(tile_code(T, s, rev), (uint32_t)(T.p0 + T.spath()[s]));
             });
             if (n <= 1) {
                 aln_match[a] = only;
@@ -895,7 +867,7 @@ __device__ __noinline__ void tile_export(const TileS& T, const Dev& d, BlockCoun
             }
             int q = 0;
             tile_enum(T, d.r, w0, L, st, [&](int s, bool rev) {
-                match_buf[pos + q++] = make_uint2(tile_code(T, s, rev), (uint32_t)(T.p0 + T.spath[s]));
+                match_buf[pos + q++] = make_uint2(tile_code(T, s, rev), (uint32_t)(T.p0 + T.spath()[s]));
             });
             aln_match[a] = make_uint2(SFB_MATCH_MULTI | (uint32_t)pos, (uint32_t)n);
         }
@@ -979,8 +951,8 @@ __device__ __forceinline__ void tile_group1(TileS& T, const Dev& d, BlockCounter
             code[single] = SFB_DEFER;
         } else {
             const int row = row0 + (single ? mt[0].na : 0);
-            const int n = T.simple ? __popcll(T.amask[2 * row]) + __popcll(T.amask[2 * row + 1])
-                                   : T.cnt[row];                 // kOver: more than KA, in any case more than one
+            const int n = T.simple ? __popcll(T.amask()[2 * row]) + __popcll(T.amask()[2 * row + 1])
+                                   : T.cnt()[row];                 // kOver: more than KA, in any case more than one
             if (n > 1) {
                 SFB_COUNT(sc, SFB_C_SECOND_PASS, 1);
                 defer = true;
@@ -1049,14 +1021,14 @@ __device__ __forceinline__ void tile_group2(TileS& T, const Dev& d, BlockCounter
             const i64 a = m.a0 + j;
             const int row = row0 + (single ? mt[0].na : 0) + j;
             if (T.simple) {
-                const u64 f = T.amask[2 * row], rv = T.amask[2 * row + 1];
+                const u64 f = T.amask()[2 * row], rv = T.amask()[2 * row + 1];
                 const int cnt = __popcll(f) + __popcll(rv);
                 if (cnt == 0) continue;
                 long long total = 0;
                 for (int q = 0; q < 2; ++q)
                     for (u64 rest = q ? rv : f; rest; rest &= rest - 1) {
                         const int p = __ffsll((long long)rest) - 1;
-                        total += T.pU[p];
+                        total += T.pU()[p];
                         tile_hist(T, d, sc, p, a);                           // :1246-1252
                     }
                 Mate one = m;                                                // this alignment alone
@@ -1065,7 +1037,7 @@ __device__ __forceinline__ void tile_group2(TileS& T, const Dev& d, BlockCounter
                 n_all += cnt;
                 continue;
             }
-            const int cnt = T.cnt[row];
+            const int cnt = T.cnt()[row];
             if (cnt == kOver) {
                 // more matches than a row holds: enumerated twice from the index instead of stored
                 const i64 w0 = d.r.aln_walk_off[a];
@@ -1073,29 +1045,29 @@ __device__ __forceinline__ void tile_group2(TileS& T, const Dev& d, BlockCounter
                 long long total = 0;
                 int c2 = 0;
                 tile_enum(T, d.r, w0, L, st, [&](int s, bool) {
-                    const int p = T.spath[s];
-                    total += T.pU[p];
+                    const int p = T.spath()[s];
+                    total += T.pU()[p];
                     ++c2;
                     tile_hist(T, d, sc, p, a);
                 });
                 tile_enum(T, d.r, w0, L, st, [&](int s, bool rev) {
-                    const int p = T.spath[s];
-                    ops.apply(d, a, tile_code(T, s, rev), T.p0 + p, m.seq_len, ratio_of(T.pU[p], total, c2), 1);
+                    const int p = T.spath()[s];
+                    ops.apply(d, a, tile_code(T, s, rev), T.p0 + p, m.seq_len, ratio_of(T.pU()[p], total, c2), 1);
                 });
                 n_all += c2;
                 continue;
             }
             if (cnt == 0) continue;
-            const uint16_t* tp = T.tup + row * KA;
+            const uint16_t* tp = T.tup() + row * KA;
             long long total = 0;
             for (int i = 0; i < cnt; ++i) {
-                const int p = T.spath[tp[i] & 0x7fffu];
-                total += T.pU[p];
+                const int p = T.spath()[tp[i] & 0x7fffu];
+                total += T.pU()[p];
                 tile_hist(T, d, sc, p, a);
             }
             for (int i = 0; i < cnt; ++i) {
-                const int s = tp[i] & 0x7fffu, p = T.spath[s];
-                ops.apply(d, a, tile_code(T, s, (tp[i] >> 15) != 0), T.p0 + p, m.seq_len, ratio_of(T.pU[p], total, cnt), 1);
+                const int s = tp[i] & 0x7fffu, p = T.spath()[s];
+                ops.apply(d, a, tile_code(T, s, (tp[i] >> 15) != 0), T.p0 + p, m.seq_len, ratio_of(T.pU()[p], total, cnt), 1);
             }
             n_all += cnt;
         }
@@ -1113,15 +1085,15 @@ __device__ __forceinline__ i64 tile_window(TileS& T, const sfb_reads& r, i64 g0,
     const i64 a0 = r.grp_aln_off[2 * g0];
     for (int i = threadIdx.x; i <= n; i += kTT) {
         const i64 v = r.grp_aln_off[2 * (g0 + i)] - a0;
-        T.goff[i] = (uint32_t)min(v, (i64)0x7fffffff);
+        T.goff()[i] = (uint32_t)min(v, (i64)0x7fffffff);
     }
     __syncthreads();
     int lim = cap;
-    if (want > 0 && want < cap && (int)T.goff[1] <= want) lim = want;        // (a first group above `want` keeps `cap`)
+    if (want > 0 && want < cap && (int)T.goff()[1] <= want) lim = want;        // (a first group above `want` keeps `cap`)
     int lo = 1, hi = n;                      // largest k in [1, n] with goff[k] <= lim (k = 1 whatever the first group has)
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
-        if ((int)T.goff[mid] <= lim) lo = mid; else hi = mid - 1;
+        if ((int)T.goff()[mid] <= lim) lo = mid; else hi = mid - 1;
     }
     return g0 + lo;
 }
@@ -1164,10 +1136,25 @@ __device__ __forceinline__ void tile_prefetch_recs(const sfb_reads& r, i64 w0, i
 #endif
 template <int PASS, int KA>
 __global__ void __launch_bounds__(kTT, SFB_TILE_MINBLK) k_tile_pass(const __grid_constant__ Dev d, const __grid_constant__ sfb_tiles t,
+                                                                        const __grid_constant__ TileLayout lay,
                                                                         const long long* __restrict__ U) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    TileS T = tile_carve(PASS, smem, t);
-    BlockCounters& sc = *T.sc;
+    // every array of the call lives in global memory: say so, or each access is a generic load
+#define SFB_GLOBAL(p) __builtin_assume(__isGlobal(p))
+    SFB_GLOBAL(d.r.grp_nmates); SFB_GLOBAL(d.r.grp_aln_off); SFB_GLOBAL(d.r.mate_seq_len); SFB_GLOBAL(d.r.aln_walk_off);
+    SFB_GLOBAL(d.r.aln_bins); SFB_GLOBAL(d.r.walk_node); SFB_GLOBAL(d.r.walk_alen); SFB_GLOBAL(d.r.exc_cov);
+    SFB_GLOBAL(d.w.aln_match); SFB_GLOBAL(d.w.match_buf); SFB_GLOBAL(d.w.cursor); SFB_GLOBAL(d.w.grp_code);
+    SFB_GLOBAL(d.w.grp_code2); SFB_GLOBAL(d.w.aln_assign); SFB_GLOBAL(d.w.slow);
+    SFB_GLOBAL(d.g.slot_node); SFB_GLOBAL(d.g.path_off); SFB_GLOBAL(d.g.occ_off); SFB_GLOBAL(d.g.occ_pair);
+    SFB_GLOBAL(d.g.path_seq_len); SFB_GLOBAL(d.g.path_nstrain); SFB_GLOBAL(d.g.path_strain0); SFB_GLOBAL(d.g.path_smask);
+    SFB_GLOBAL(d.g.path_cluster);
+    SFB_GLOBAL(d.acc.uniq_reads); SFB_GLOBAL(d.acc.uniq_norm); SFB_GLOBAL(d.acc.mult_reads); SFB_GLOBAL(d.acc.mult_norm);
+    SFB_GLOBAL(d.acc.mult_hits); SFB_GLOBAL(d.acc.uniq_abund); SFB_GLOBAL(d.acc.mult_abund); SFB_GLOBAL(d.acc.hist);
+    SFB_GLOBAL(d.acc.counters);
+    SFB_GLOBAL(t.tile_desc); SFB_GLOBAL(t.items); SFB_GLOBAL(t.edge_off); SFB_GLOBAL(t.edge_succ); SFB_GLOBAL(t.edge_mask);
+    SFB_GLOBAL(t.node_mask); SFB_GLOBAL(U);
+#undef SFB_GLOBAL
+    TileS T = tile_carve(lay, t);
+    BlockCounters& sc = *T.sc();
     block_counters_zero(sc);
     TileStats st{0, 0, 0, 0, 0, 0};
     float apg = 5.0f, dfrac = 0.3f;      // pass 2: running averages that size a round (block-uniform)
@@ -1175,16 +1162,16 @@ __global__ void __launch_bounds__(kTT, SFB_TILE_MINBLK) k_tile_pass(const __grid
     const int tid = threadIdx.x;
     for (;;) {
         __syncthreads();
-        if (tid == 0) T.misc[0] = (int)atomicAdd(d.w.cursor + (PASS == 1 ? 5 : 6), 1ull);
+        if (tid == 0) T.misc()[0] = (int)atomicAdd(d.w.cursor + (PASS == 1 ? 5 : 6), 1ull);
         __syncthreads();
-        const int item = T.misc[0];
+        const int item = T.misc()[0];
         if (item >= (int)t.n_items) break;
         const int4 it = items[item];
         tile_stage<PASS>(T, d, t, it.x, U);
         T.a_item = d.r.grp_aln_off[2 * (i64)it.y];
-        if (tid == 0) T.misc[1] = 0;
+        if (tid == 0) T.misc()[1] = 0;
         for (i64 g0 = it.y; g0 < (i64)it.z;) {
-            if (tid < 4 && (PASS == 2 || tid > 0)) T.misc[1 + tid] = 0;
+            if (tid < 4 && (PASS == 2 || tid > 0)) T.misc()[1 + tid] = 0;
             __syncthreads();
             if (PASS == 1) {
                 const i64 g1 = tile_window(T, d.r, g0, it.z, kRows1, kTT, 2 * kTT);
@@ -1197,11 +1184,11 @@ __global__ void __launch_bounds__(kTT, SFB_TILE_MINBLK) k_tile_pass(const __grid
                 }
                 // the window's walk offsets and records into shared memory (coalesced), aln_assign = "none"
                 T.w_row0 = d.r.aln_walk_off[T.a_row0];
-                for (int i = tid; i <= nA; i += kTT) T.woff[i] = (uint32_t)(d.r.aln_walk_off[T.a_row0 + i] - T.w_row0);
+                for (int i = tid; i <= nA; i += kTT) T.woff()[i] = (uint32_t)(d.r.aln_walk_off[T.a_row0 + i] - T.w_row0);
                 for (int i = tid; i < nA; i += kTT) d.w.aln_assign[T.a_row0 + i] = -1;
                 {
                     const int nR = (int)min((i64)kStageRec, d.r.aln_walk_off[T.a_row0 + nA] - T.w_row0);
-                    for (int i = tid; i < nR; i += kTT) T.wnode[i] = (uint16_t)tile_local(T, d.r.walk_node[T.w_row0 + i]);
+                    for (int i = tid; i < nR; i += kTT) T.wnode()[i] = (uint16_t)tile_local(T, d.r.walk_node[T.w_row0 + i]);
                 }
                 {   // the next window (about as large as this one) on its way to the L2 while this one is worked on
                     const i64 g2 = min(g1 + (g1 - g0), (i64)it.z);
@@ -1220,25 +1207,25 @@ __global__ void __launch_bounds__(kTT, SFB_TILE_MINBLK) k_tile_pass(const __grid
                 __syncthreads();
                 // S: whole iterations only; the rest of the list stays for the next window (the last one takes all)
                 g0 = g1;
-                const int n_asg = T.misc[1];
+                const int n_asg = T.misc()[1];
                 const int full = g0 >= (i64)it.z ? n_asg : (n_asg / kTT) * kTT;
                 for (int q = tid; q < full; q += kTT) tile_scatter1(T, d, sc, q, st);
                 uint32_t ka = 0, kx = 0;
                 int ks = 0;
                 const bool keep = full + tid < n_asg;
-                if (keep) { ka = T.la[full + tid]; kx = T.lx[full + tid]; ks = T.lseq[full + tid]; }
+                if (keep) { ka = T.la()[full + tid]; kx = T.lx()[full + tid]; ks = T.lseq()[full + tid]; }
                 __syncthreads();
-                if (keep) { T.la[tid] = ka; T.lx[tid] = kx; T.lseq[tid] = ks; }
-                if (tid == 0) T.misc[1] = n_asg - full;
+                if (keep) { T.la()[tid] = ka; T.lx()[tid] = kx; T.lseq()[tid] = ks; }
+                if (tid == 0) T.misc()[1] = n_asg - full;
             } else {
                 // D: windows of read groups until the deferred groups listed should fill phase S's list (apg = work
                 //    items per deferred group, dfrac = share of deferred groups, running averages of this block)
                 const int target = max(8, min(kTT, (int)(0.7f * (float)tile_list_cap(2) / apg)));
                 for (;;) {
-                    const int want = max(16, min(kTT, (int)((float)(target - T.misc[3]) / fmaxf(dfrac, 0.03f))));
+                    const int want = max(16, min(kTT, (int)((float)(target - T.misc()[3]) / fmaxf(dfrac, 0.03f))));
                     const i64 g1 = tile_window(T, d.r, g0, it.z, kWin2, want);
                     const i64 a0 = d.r.grp_aln_off[2 * g0];
-                    const int before = T.misc[3];
+                    const int before = T.misc()[3];
                     __syncthreads();       // everyone has read the fill
                     if (d.r.grp_aln_off[2 * g1] - a0 > kWin2) {                // see above
                         if (tid == 0) SFB_COUNT(sc, SFB_C_MATCH_OVERFLOW, 1);
@@ -1248,33 +1235,33 @@ __global__ void __launch_bounds__(kTT, SFB_TILE_MINBLK) k_tile_pass(const __grid
                         if ((c1 & 0xf) == SFB_DEFER || (c1 >> 4) == SFB_DEFER) {
                             const i64 ga = d.r.grp_aln_off[2 * g];
                             const int na = (int)(d.r.grp_aln_off[2 * g + 2] - ga);
-                            const int slot = atomicAdd(&T.misc[3], 1), row = atomicAdd(&T.misc[2], na);
-                            T.glist[slot] = (uint32_t)(g - it.y);
-                            T.grow[slot] = (uint16_t)row;
-                            for (int j = 0; j < na; ++j) T.alist[row + j] = (uint32_t)(ga + j - T.a_item);
+                            const int slot = atomicAdd(&T.misc()[3], 1), row = atomicAdd(&T.misc()[2], na);
+                            T.glist()[slot] = (uint32_t)(g - it.y);
+                            T.grow()[slot] = (uint16_t)row;
+                            for (int j = 0; j < na; ++j) T.alist()[row + j] = (uint32_t)(ga + j - T.a_item);
                         }
                     }
                     __syncthreads();
-                    dfrac = 0.5f * dfrac + 0.5f * (float)(T.misc[3] - before) / (float)(g1 - g0);
+                    dfrac = 0.5f * dfrac + 0.5f * (float)(T.misc()[3] - before) / (float)(g1 - g0);
                     g0 = g1;
-                    if (g0 >= (i64)it.z || T.misc[3] >= target - target / 8 || T.misc[3] + kTT > kGrp2 || T.misc[2] + kWin2 > kRows2)
+                    if (g0 >= (i64)it.z || T.misc()[3] >= target - target / 8 || T.misc()[3] + kTT > kGrp2 || T.misc()[2] + kWin2 > kRows2)
                         break;
                 }
-                const int n_aln = T.misc[2], n_grp = T.misc[3];
+                const int n_aln = T.misc()[2], n_grp = T.misc()[3];
                 // M
                 {
                     const int seen = st.tuples;                       // counted in pass 1
-                    if (T.simple) for (int q = tid; q < n_aln; q += kTT) mask_match_aln<false>(T, d.r, q, T.a_item + T.alist[q], st);
-                    else for (int q = tid; q < n_aln; q += kTT) tile_match_aln<KA>(T, d.r, q, T.a_item + T.alist[q], st);
+                    if (T.simple) for (int q = tid; q < n_aln; q += kTT) mask_match_aln<false>(T, d.r, q, T.a_item + T.alist()[q], st);
+                    else for (int q = tid; q < n_aln; q += kTT) tile_match_aln<KA>(T, d.r, q, T.a_item + T.alist()[q], st);
                     st.tuples = seen;
                 }
                 __syncthreads();
                 // C
-                for (int q = tid; q < n_grp; q += kTT) tile_group2<KA>(T, d, sc, (i64)it.y + T.glist[q], T.grow[q], st);
+                for (int q = tid; q < n_grp; q += kTT) tile_group2<KA>(T, d, sc, (i64)it.y + T.glist()[q], T.grow()[q], st);
                 __syncthreads();
                 // S: per-path sums (json2csv.py:1155-1156) and node loop (:1157-1158) of every work item
-                const int n_app = min(T.misc[1], tile_list_cap(2));
-                if (n_grp) apg = 0.5f * apg + 0.5f * (float)T.misc[1] / (float)n_grp;
+                const int n_app = min(T.misc()[1], tile_list_cap(2));
+                if (n_grp) apg = 0.5f * apg + 0.5f * (float)T.misc()[1] / (float)n_grp;
                 for (int q = tid; q < n_app; q += kTT) tile_scatter2(T, d, q, st);
             }
             __syncthreads();
@@ -1321,7 +1308,8 @@ i64 tile_smem_bytes(const sfb_tiles* t) {
 
 template <int PASS, int KA>
 static int launch_tile_k(const Dev& d, const sfb_tiles* t, const long long* U, cudaStream_t st) {
-    const size_t smem = tile_layout(PASS, (int)t->max_slots, (int)t->max_nodes, (int)t->max_paths, (int)t->max_edges, KA).total;
+    const TileLayout lay = tile_layout(PASS, (int)t->max_slots, (int)t->max_nodes, (int)t->max_paths, (int)t->max_edges, KA);
+    const size_t smem = lay.total;
     auto kern = k_tile_pass<PASS, KA>;
     if (smem > 227 * 1024) return fail(SFB_E_ARG, "tile kernels: %zu bytes of shared memory needed, 232448 available", smem);
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -1331,7 +1319,7 @@ static int launch_tile_k(const Dev& d, const sfb_tiles* t, const long long* U, c
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTT, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     const i64 grid = t->n_items < (i64)per_sm * sms ? t->n_items : (i64)per_sm * sms;
-    kern<<<(unsigned)grid, kTT, smem, st>>>(d, *t, U);
+    kern<<<(unsigned)grid, kTT, smem, st>>>(d, *t, lay, U);
     return check_launch(PASS == 1 ? "k_tile_pass1" : "k_tile_pass2");
 }
 
