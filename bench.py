@@ -327,13 +327,16 @@ def device_pass(eng, reads, steps, warmup, world, dist, device, want_marks=True)
     host.reads = None                     # the staged arena is all the passes need
     dr = eng.upload(host)
     torch.cuda.synchronize()
-    done = 0
-    while done < max(warmup, 1):          # warm-up (also settles the match-buffer capacity)
+    done = tries = 0
+    while done < max(warmup, 1):          # warm-up (also settles the capacity of the match / work-item buffers)
         work = eng.run_device(dr)
         torch.cuda.synchronize()
         over = int(eng.acc.counters[_lib.COUNTER_NAMES.index("MATCH_OVERFLOW")].item())
-        if over:                          # grow the match buffer to the exact need; not a warm-up step
+        if over:                          # grow the buffers to the exact need; not a warm-up step
+            tries += 1
+            assert tries <= 4, "match / work-item buffers still too small after regrowing"
             eng.match_cap_hint = int(work.t["cursor"][0].item()) + 1024
+            eng.app_cap_hint = int(work.t["cursor"][2].item()) + 1024
             continue
         done += 1
     stats = eng.fetch(work, dr, keep_codes=False, keep_slots=False)
@@ -529,7 +532,7 @@ def run_ours(args):
         for key, kw in (("plain_fp64_atomics", dict(deterministic=False)), ("file_order", dict(tiles=False)),
                         ("shared_memory_tile_kernels", dict(tile_kernels=True))):
             e2 = engine.AbundanceEngine(graph, device, comm=comm, **kw)
-            e2.match_cap_hint = eng.match_cap_hint
+            e2.match_cap_hint, e2.app_cap_hint = eng.match_cap_hint, eng.app_cap_hint
             ms2, st2, _, _, _, _, dr2 = device_pass(e2, reads, max(3, args.steps // 4), 2, world, dist, device)
             n2 = max(3, args.steps // 4)
             alt[key] = {"ms_per_step": ms2 / n2, "value": total_reads * n2 / (ms2 * 1e-3), "unit": UNIT,

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SFB_ABI_VERSION 11
+#define SFB_ABI_VERSION 12
 
 /* ---- status codes ---------------------------------------------------- */
 #define SFB_OK            0
@@ -44,11 +44,17 @@ extern "C" {
  *   x bit 31 clear                exactly one match: x = code, y = path id
  *   x bit 31 set                  y matches, stored as consecutive (code, path id) pairs of match_buf
  *                                 starting at pair index (x & 0x7fffffff), in the reference's order
- *                                 (forward matches by ascending path id / position, then reverse) */
+ *                                 (forward matches by ascending path id / position, then reverse)
+ *   x == SFB_MATCH_SETS           (sfb_match_steps) the matches are two sets of paths of one simple tile, y = first
+ *                                 path id p0 of that tile: bit b of aln_sets[2a] = the walk matches path p0 + b, bit b
+ *                                 of aln_sets[2a+1] = the reversed walk does; at least one bit is set.  The tuple of a
+ *                                 set bit: the occurrence of the walk's first (reversed: last) node on that path, which
+ *                                 is occurrence number popcount(node_mask[node] & (bit - 1)) of the node */
 #define SFB_SLOT_MASK    0x3fffffffu
 #define SFB_MATCH_REV    0x40000000u
 #define SFB_MATCH_MULTI  0x80000000u
 #define SFB_MATCH_NONE   0xffffffffu
+#define SFB_MATCH_SETS   0xfffffffeu
 #define SFB_MAX_SLOTS    0x3fffffff          /* n_slots limit (2^30-1)           */
 
 /* Per-mate pass-1 outcome, one nibble per mate in grp_code[g] (mate 0 = low
@@ -114,6 +120,24 @@ typedef struct sfb_graph {
     const int32_t*  path_strain0;  /* [n_paths] first strain id of the path (histogram row, :334) */
     const uint64_t* path_smask;    /* [n_paths*mask_words] bit s set iff strain s in path.strain_ids */
     const int32_t*  path_cluster;  /* [n_paths] Path.cluster_id, -1 for None                 */
+    /* Optional step index (all NULL / 0 without it): get_matching_path as an AND of path sets.  In a "simple" tile
+     * (see sfb_tiles: at most 64 paths, no node twice in one path) a walk matches path p at the position of its first
+     * node iff p takes every step of the walk, and the reversed walk matches iff p takes every step backwards, so the
+     * matches of an alignment are two 64-bit path sets (bit = path id - p0): the AND, over the walk's steps, of the set
+     * of paths taking that step.  node_step holds one 32-byte record per dense node:
+     *     int32 succ0, succ1     the first two distinct successors of the node on the tile's paths (-1: none)
+     *     uint64 mask0, mask1    the paths taking those steps
+     *     int32 p0               first path id of the node's tile; -1: the node lies outside the simple tiles (walks
+     *                            that start there go through the occurrence-index kernel)
+     *     int32 n_succ           distinct successors; those after the first two are step_succ / step_mask[step_off[n]+2 ..)
+     * node_mask[n] = the paths through n.  The occurrences of a node are ordered by slot, hence by path: occurrence
+     * number k of n belongs to the path of the k-th set bit of node_mask[n]. */
+    const void*     node_step;     /* [n_nodes] 32-byte records, 32-byte aligned             */
+    const uint64_t* node_mask;     /* [n_nodes]                                              */
+    const int32_t*  step_off;      /* [n_nodes+1] distinct successors of node n: step_succ[step_off[n] .. step_off[n+1]) */
+    const int32_t*  step_succ;
+    const uint64_t* step_mask;
+    int64_t         steps_partial; /* != 0: some node with occurrences has p0 = -1           */
 } sfb_graph;
 
 /* ---- reads: decoded alignments (json2csv.py:551-739) as CSR -------------- */
@@ -170,12 +194,15 @@ typedef struct sfb_wire {
 /* ---- per-shard work arrays (outputs of match / classify) ----------------- */
 typedef struct sfb_work {
     uint32_t* aln_match;          /* [2A]  one (x, y) pair per alignment, see encodings (8-byte aligned) */
+    uint64_t* aln_sets;           /* [2A]  path sets of the SFB_MATCH_SETS alignments (sfb_match_steps); may be NULL
+                                           when that entry point is not used                   */
     int32_t*  match_buf;          /* [2*match_cap] (code, path id) pairs (8-byte aligned)     */
     int64_t   match_cap;          /* pairs; < 2^31                                            */
-    unsigned long long* cursor;   /* [8]   [0] match_buf fill (pairs), [1] deferred groups, [2] app_buf fill,
+    unsigned long long* cursor;   /* [16]  [0] match_buf fill (pairs), [1] deferred groups, [2] app_buf fill,
                                            [3]/[4] groups handed to the generic kernels of classify / pass 2,
                                            [5]/[6] work items taken by sfb_tile_pass1 / sfb_tile_pass2, [7] groups
-                                           deferred inside tiles; zero before the first call of a pass          */
+                                           deferred inside tiles, [8] alignments sfb_match_steps left to the
+                                           occurrence-index kernel; zero before the first call of a pass        */
     uint8_t*  grp_code;           /* [G]                                                      */
     uint8_t*  grp_code2;          /* [G]   zero before sfb_pass2                              */
     int32_t*  aln_assign;         /* [A]   >= 0: match code of the unique assignment (:945,:958,:996);
@@ -277,6 +304,13 @@ int sfb_expand_reads(const sfb_wire* w, const int32_t* node_len, const sfb_reads
 /* Pangenome.get_matching_path on the walk and, if longer than one node, on the reversed
  * walk (json2csv.py:341-363 with callers :855-866, :1024-1026, :1103-1114, :1231-1233). */
 int sfb_match(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_accum* acc, void* stream);
+/* The same matches through the step index of `g` (node_step ...), left as path sets: one thread per alignment ANDs the
+ * path sets of its walk's steps, both orientations at once, into w->aln_sets and marks the alignment SFB_MATCH_SETS
+ * (SFB_MATCH_NONE when both sets are empty).  sfb_classify / sfb_pass2 work on the sets directly (intersections, counts
+ * and strain algebra are AND / OR / popcount) and look the slot of a path up only when they assign or share a read.
+ * Alignments whose first node lies outside the simple tiles are listed (cursor[8]; the list lives in w->aln_assign,
+ * which sfb_classify only writes afterwards) and matched by the occurrence-index kernel of sfb_match, tuples as usual. */
+int sfb_match_steps(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_accum* acc, void* stream);
 
 /* Pass-1 decision tree per read group (json2csv.py:828-1053) including the per-read part
  * of fill_abund_dist (:326-327, :333-339): counters, grp_code, aln_assign, deferred list,
@@ -390,7 +424,9 @@ int sfb_locality_permute(const sfb_reads* src, int n_threads, int64_t* order, in
 /* Tile order (see sfb_tiles): as sfb_locality_permute, but the key of a group is the tile that holds the first and
  * the last node of every one of its alignments (node_tile[n] = tile of dense node n, -1 = none); groups without such
  * a tile -- and groups without any alignment, or with more than 255 alignments in a mate -- go last, in file order.  tile_grp_off[n_tiles + 2]: the groups of tile
- * t are [off[t], off[t+1]) of the permuted order, the others [off[n_tiles], off[n_tiles+1] = G). */
+ * t are [off[t], off[t+1]) of the permuted order -- inside a tile stable by the first node of the group's first alignment,
+ * so that neighbouring groups touch neighbouring positions of the tile's paths (the tiles must be numbered in node order:
+ * every node of tile t before every node of tile t+1) -- the others [off[n_tiles], off[n_tiles+1] = G). */
 int sfb_tile_permute(const sfb_reads* src, const int32_t* node_tile, int64_t n_tiles, int n_threads, int64_t* order,
                      int64_t* aln_index, const sfb_reads* dst, int64_t* tile_grp_off);
 

@@ -28,6 +28,8 @@ class SfbGraph(C.Structure):
         ("occ_off", C.c_void_p), ("occ_pair", C.c_void_p), ("blk_path", C.c_void_p), ("path_seq_len", C.c_void_p),
         ("path_nstrain", C.c_void_p), ("path_strain0", C.c_void_p), ("path_smask", C.c_void_p),
         ("path_cluster", C.c_void_p),
+        ("node_step", C.c_void_p), ("node_mask", C.c_void_p), ("step_off", C.c_void_p), ("step_succ", C.c_void_p),
+        ("step_mask", C.c_void_p), ("steps_partial", C.c_int64),
     ]
 
 
@@ -48,7 +50,7 @@ class SfbWire(C.Structure):
 
 class SfbWork(C.Structure):
     _fields_ = [
-        ("aln_match", C.c_void_p), ("match_buf", C.c_void_p), ("match_cap", C.c_int64), ("cursor", C.c_void_p),
+        ("aln_match", C.c_void_p), ("aln_sets", C.c_void_p), ("match_buf", C.c_void_p), ("match_cap", C.c_int64), ("cursor", C.c_void_p),
         ("grp_code", C.c_void_p), ("grp_code2", C.c_void_p), ("aln_assign", C.c_void_p), ("deferred", C.c_void_p),
         ("slow", C.c_void_p), ("app_buf", C.c_void_p), ("app_cap", C.c_int64),
         ("grp_begin", C.c_int64), ("aln_begin", C.c_int64),
@@ -80,6 +82,9 @@ class SfbTiles(C.Structure):
     ]
 
 
+CURSOR_N = 16          # entries of sfb_work.cursor
+
+
 class SfbAccum(C.Structure):
     _fields_ = [
         ("uniq_reads", C.c_void_p), ("uniq_norm", C.c_void_p), ("mult_reads", C.c_void_p), ("mult_norm", C.c_void_p),
@@ -97,13 +102,13 @@ COUNTER_NAMES = (
 )
 N_COUNTERS = 32
 N_HIST, N_BINS, TABLE_COLS = 5, 101, 8
-SLOT_MASK, MATCH_REV, MATCH_MULTI, MATCH_NONE = 0x3FFFFFFF, 0x40000000, 0x80000000, 0xFFFFFFFF
+SLOT_MASK, MATCH_REV, MATCH_MULTI, MATCH_NONE, MATCH_SETS = 0x3FFFFFFF, 0x40000000, 0x80000000, 0xFFFFFFFF, 0xFFFFFFFE
 MAX_SLOTS = 0x3FFFFFFF
 (ABSENT, FILTERED, UNASSIGNED, UNASSIGNED_BOOK, DEFER, ASSIGN_SAME, ASSIGN_DIFF, MULTI_ALIGN, INCONSIST,
  SE_COUNTED) = range(10)
-ABI_VERSION = 11
+ABI_VERSION = 12
 
-EXPORTS = ("sfb_abi_version", "sfb_version", "sfb_last_error", "sfb_expand_reads", "sfb_match", "sfb_classify", "sfb_pass1_scatter",
+EXPORTS = ("sfb_abi_version", "sfb_version", "sfb_last_error", "sfb_expand_reads", "sfb_match", "sfb_match_steps", "sfb_classify", "sfb_pass1_scatter",
            "sfb_pass2", "sfb_pass2_resolve", "sfb_pass2_scatter", "sfb_accum_collapse", "sfb_path_reduce", "sfb_cluster_strain_counts", "sfb_strain_aggregate",
            "sfb_tile_pass1", "sfb_tile_pass2", "sfb_tile_smem_bytes", "sfb_tile_permute", "sfb_workspace_bytes",
            "sfb_decode_json", "sfb_decode_gamp", "sfb_decoded_error", "sfb_decoded_size", "sfb_decoded_copy", "sfb_decoded_free",
@@ -145,6 +150,7 @@ def load(build_if_missing=True):
     vp, i64, f64 = C.c_void_p, C.c_int64, C.c_double
     lib.sfb_expand_reads.argtypes = [C.POINTER(SfbWire), vp, R, vp, vp]
     lib.sfb_match.argtypes = [G, R, W, A, vp]
+    lib.sfb_match_steps.argtypes = [G, R, W, A, vp]
     lib.sfb_classify.argtypes = [G, R, W, A, vp]
     lib.sfb_pass1_scatter.argtypes = [G, R, W, A, vp]
     lib.sfb_pass2.argtypes = [G, R, W, A, vp, vp]
@@ -154,7 +160,7 @@ def load(build_if_missing=True):
     lib.sfb_path_reduce.argtypes = [G, A, i64, i64, vp, vp]
     lib.sfb_cluster_strain_counts.argtypes = [i64, i64, vp, vp, vp, vp, vp, vp, vp]
     lib.sfb_strain_aggregate.argtypes = [i64, i64, vp, vp, vp, vp, vp, vp, f64, vp, vp, vp, vp, vp]
-    for name in EXPORTS[3:14]:
+    for name in EXPORTS[3:15]:
         getattr(lib, name).restype = C.c_int
     TL = C.POINTER(SfbTiles)
     lib.sfb_tile_pass1.argtypes = [G, TL, R, W, A, vp]

@@ -23,6 +23,7 @@ int check_launch(const char* what) {
 }
 
 int launch_match(const sfb_graph*, const sfb_reads*, sfb_work*, sfb_accum*, cudaStream_t);
+int launch_match_steps(const sfb_graph*, const sfb_reads*, sfb_work*, sfb_accum*, cudaStream_t);
 int launch_classify(const Dev&, cudaStream_t);
 int launch_pass2_resolve(const Dev&, const long long*, cudaStream_t);
 int launch_pass1_scatter(const sfb_graph*, const sfb_reads*, const sfb_work*, sfb_accum*, cudaStream_t);
@@ -129,6 +130,14 @@ int sfb_expand_reads(const sfb_wire* w, const int32_t* node_len, const sfb_reads
 int sfb_match(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_accum* acc, void* stream) {
     SFB_TRY(check_all(g, r, w, acc));
     return launch_match(g, r, w, acc, (cudaStream_t)stream);
+}
+
+int sfb_match_steps(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_accum* acc, void* stream) {
+    SFB_TRY(check_all(g, r, w, acc));
+    SFB_REQUIRE(g->n_nodes == 0 || (g->node_step && g->node_mask && g->step_off), "the graph has no step index");
+    SFB_REQUIRE(((uintptr_t)g->node_step & 31) == 0, "node_step must be 32-byte aligned");
+    SFB_REQUIRE(w->aln_sets && ((uintptr_t)w->aln_sets & 15) == 0, "aln_sets is null or not 16-byte aligned");
+    return launch_match_steps(g, r, w, acc, (cudaStream_t)stream);
 }
 
 int sfb_classify(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_accum* acc, void* stream) {

@@ -111,9 +111,15 @@ __device__ __forceinline__ void block_counters_flush(BlockCounters& sc, long lon
 __device__ __forceinline__ uint2 match_word(const sfb_work& w, i64 a) {
     return reinterpret_cast<const uint2*>(w.aln_match)[a];
 }
-__device__ __forceinline__ int match_count(uint2 m) {
+__device__ __forceinline__ int match_count(uint2 m) {          // (tuple form; path sets: match_count_at)
     if (m.x == SFB_MATCH_NONE) return 0;
     return (m.x & SFB_MATCH_MULTI) ? (int)m.y : 1;
+}
+// number of matches of alignment a, path sets included
+__device__ __forceinline__ int match_count_at(const sfb_work& w, i64 a) {
+    const uint2 m = match_word(w, a);
+    if (m.x == SFB_MATCH_SETS) return __popcll(w.aln_sets[2 * a]) + __popcll(w.aln_sets[2 * a + 1]);
+    return match_count(m);
 }
 // k-th match of an alignment as (code, path id)
 __device__ __forceinline__ uint2 match_get(const sfb_work& w, uint2 m, int k) {
@@ -174,6 +180,16 @@ __device__ __forceinline__ int path_of_block(const sfb_graph& g, int2 e, int s) 
 }
 __device__ __forceinline__ int path_of_slot(const sfb_graph& g, int s) {
     return path_of_block(g, reinterpret_cast<const int2*>(g.blk_path)[s >> 6], s);
+}
+
+// Path sets (SFB_MATCH_SETS, sfb200.h): the tuple of the lowest set bit of `rest`, a subset of the forward (reverse) set of
+// an alignment whose walk starts (ends) on `node`.  Occurrences are ordered by slot, hence by path: the rank of the bit
+// inside node_mask is the rank of the occurrence.
+__device__ __forceinline__ uint2 sets_tuple(const sfb_graph& g, int node, int p0, u64 rest, bool rev) {
+    const u64 bit = rest & (~rest + 1);
+    const int k = __popcll(g.node_mask[node] & (bit - 1));
+    const int slot = reinterpret_cast<const int2*>(g.occ_pair)[g.occ_off[node] + k].x;
+    return make_uint2((uint32_t)slot | (rev ? SFB_MATCH_REV : 0u), (uint32_t)(p0 + __ffsll((long long)bit) - 1));
 }
 
 // A mate of a read group: its retained alignments [a0, a0+na) (json2csv.py:686-739).

@@ -84,6 +84,10 @@ struct GlobalOps {
     }
 };
 
+}  // namespace sfb
+#include "group_sets.cuh"
+namespace sfb {
+
 // =============================================================================================
 // classify
 // =============================================================================================
@@ -171,7 +175,7 @@ __device__ __forceinline__ int classify_single(const Dev& d, BlockCounters& sc, 
     SFB_COUNT(sc, SFB_C_SINGLES, 1);
     if (mt.na == 0) { SFB_COUNT(sc, SFB_C_FILTERED, 1); return SFB_FILTERED; }
     if (mt.na > 1) { SFB_COUNT(sc, SFB_C_SECOND_PASS, 1); defer = true; return SFB_DEFER; }
-    const int n = match_count(match_word(d.w, mt.a0));
+    const int n = match_count_at(d.w, mt.a0);
     if (n > 1) { SFB_COUNT(sc, SFB_C_SECOND_PASS, 1); defer = true; return SFB_DEFER; }
     if (n == 0) {
         SFB_COUNT(sc, SFB_C_UNASSIGNED, 1);
@@ -182,6 +186,22 @@ __device__ __forceinline__ int classify_single(const Dev& d, BlockCounters& sc, 
     SFB_COUNT(sc, SFB_C_ASSIGNED_U, 1);      // counted, never accumulated (json2csv.py:1047-1053, Q1)
     SFB_COUNT(sc, SFB_C_SE, 1);
     return SFB_SE_COUNTED;
+}
+
+// one mate without colored path (json2csv.py:895-916); returns the mate that continues single-end style
+__device__ __forceinline__ int classify_one_without_path(const Dev& d, BlockCounters& sc, const Mate* mt, int gone, int* code) {
+    SFB_COUNT(sc, SFB_C_UNASSIGNED, 1);
+    SFB_COUNT(sc, SFB_C_ONE_NOCP, 1);
+    code[gone] = SFB_UNASSIGNED;
+    bool bad = false;
+    for (int j = 0; j < mt[gone].na; ++j) bad |= first_cluster(d, mt[gone].a0 + j) == -2;
+    if (bad) {
+        SFB_COUNT(sc, SFB_C_NO_PATH, 1);
+    } else if (mt[gone].na == 1) {
+        book(d, sc, mt[gone], first_cluster(d, mt[gone].a0));
+        code[gone] = SFB_UNASSIGNED_BOOK;
+    }
+    return 1 - gone;
 }
 
 // Generic handling of a pair whose mates both have alignments (json2csv.py:847-1000); `single` is set
@@ -197,20 +217,7 @@ __device__ __forceinline__ void classify_aligned_pair_generic(const Dev& d, Bloc
         GlobalOps ops{nullptr, nullptr};
         classify_both_unassigned(d, ops, sc, mt, code);
     } else if (nt0 == 0 || nt1 == 0) {
-        // one mate without colored path (json2csv.py:895-916)
-        SFB_COUNT(sc, SFB_C_UNASSIGNED, 1);
-        SFB_COUNT(sc, SFB_C_ONE_NOCP, 1);
-        const int gone = nt0 == 0 ? 0 : 1;
-        code[gone] = SFB_UNASSIGNED;
-        bool bad = false;
-        for (int j = 0; j < mt[gone].na; ++j) bad |= first_cluster(d, mt[gone].a0 + j) == -2;
-        if (bad) {
-            SFB_COUNT(sc, SFB_C_NO_PATH, 1);
-        } else if (mt[gone].na == 1) {
-            book(d, sc, mt[gone], first_cluster(d, mt[gone].a0));
-            code[gone] = SFB_UNASSIGNED_BOOK;
-        }
-        single = 1 - gone;
+        single = classify_one_without_path(d, sc, mt, nt0 == 0 ? 0 : 1, code);
     } else if (fits) {
         GlobalOps ops{nullptr, nullptr};
         classify_pair(d, ops, sc, lv, mt, code, defer);
@@ -226,7 +233,10 @@ __device__ __forceinline__ void classify_aligned_pair_generic(const Dev& d, Bloc
 #ifndef SFB_P2_MINBLK
 #define SFB_P2_MINBLK 6       /* 64 registers */
 #endif
-// Fast kernel: everything except aligned pairs that do not fit the register path, which go to w.slow.
+// Fast kernel: everything except aligned pairs that do not fit the register path, which go to w.slow.  SETS: the matches
+// are the path sets of sfb_match_steps (group_sets.cuh), else tuples (group_fast.cuh); one kernel per form, so that
+// neither carries the other's registers.
+template <bool SETS>
 __global__ void __launch_bounds__(128, SFB_CLS_MINBLK) k_classify(Dev d) {
     __shared__ BlockCounters sc;
     block_counters_zero(sc);
@@ -255,6 +265,23 @@ __global__ void __launch_bounds__(128, SFB_CLS_MINBLK) k_classify(Dev d) {
                     const int gone = mt[0].na == 0 ? 0 : 1;
                     code[gone] = SFB_FILTERED;
                     single = 1 - gone;
+                } else if (SETS) {
+                    // path sets of the step index: any number of candidate paths in registers
+                    SetMate sm[2];
+                    if (d.g.mask_words == 1 && sets_load(d.w, mt[0], sm[0]) && sets_load(d.w, mt[1], sm[1])) {
+                        if (sm[0].nt == 0 && sm[1].nt == 0) {
+                            GlobalOps ops{nullptr, nullptr};
+                            classify_both_unassigned(d, ops, sc, mt, code);
+                        } else if (sm[0].nt == 0) {
+                            single = classify_one_without_path(d, sc, mt, 0, code);
+                        } else if (sm[1].nt == 0) {
+                            single = classify_one_without_path(d, sc, mt, 1, code);
+                        } else {
+                            sets_classify_pair(d, sc, mt, sm, code, defer);
+                        }
+                    } else {
+                        slow = true;
+                    }
                 } else {
                     RegMate A, B;
                     const bool quick = d.g.mask_words == 1 && reg_load(d.w, mt[0], -2, A) && reg_load(d.w, mt[1], -32, B) &&
@@ -423,6 +450,7 @@ __device__ __forceinline__ App* p2_fast_emit(const Dev& d, BlockCounters& sc, co
 }
 
 // Fast kernel over the deferred groups; groups that do not fit the register path go to w.slow (cursor[4]).
+template <bool SETS>
 __global__ void __launch_bounds__(128, SFB_P2_MINBLK) k_pass2_resolve(Dev d, const long long* __restrict__ U) {
     __shared__ BlockCounters sc;
     block_counters_zero(sc);
@@ -436,8 +464,11 @@ __global__ void __launch_bounds__(128, SFB_P2_MINBLK) k_pass2_resolve(Dev d, con
         FastPlan fp;
         fp.mode[0] = fp.mode[1] = kNone;
         fp.sel[0] = fp.sel[1] = 0;
+        SetMate sm[2];
+        SetPlan sp;
+        sp.mode[0] = sp.mode[1] = kNone;
         Mate mt[2];
-        bool slow = false;
+        bool slow = false, sets = false;
         i64 g = 0;
         unsigned need = 0;
         if (live) {
@@ -445,8 +476,26 @@ __global__ void __launch_bounds__(128, SFB_P2_MINBLK) k_pass2_resolve(Dev d, con
             const int nm = d.r.grp_nmates[g];
             mate_load(d.r, g, 0, mt[0]);
             mate_load(d.r, g, 1, mt[1]);
-            const bool quick = d.g.mask_words == 1 && reg_load(d.w, mt[0], -2, A) && reg_load(d.w, mt[1], -32, B);
-            if (!quick) {
+            sets = SETS && d.g.mask_words == 1 && sets_load(d.w, mt[0], sm[0]) && sets_load(d.w, mt[1], sm[1]);
+            const bool quick = !SETS && d.g.mask_words == 1 && reg_load(d.w, mt[0], -2, A) && reg_load(d.w, mt[1], -32, B);
+            if (sets) {
+                int code[2] = {SFB_P2_NONE, SFB_P2_NONE};
+                int single = nm == 1 ? 0 : -1;
+                if (nm == 2) {
+                    if (mt[0].na == 0 || mt[1].na == 0) single = mt[0].na == 0 ? 1 : 0;          // json2csv.py:1088-1093
+                    else if (sm[0].nt == 0 || sm[1].nt == 0) single = sm[0].nt == 0 ? 1 : 0;    // :1117-1122
+                    else sets_p2_decide_pair(d, sc, sm, U, sp, code);
+                }
+                if (single == 0) {                    // (no run-time index into the register structs)
+                    sp.mode[0] = kSingle;
+                    code[0] = p2_single_outcome(sc, sm[0].nt);
+                } else if (single == 1) {
+                    sp.mode[1] = kSingle;
+                    code[1] = p2_single_outcome(sc, sm[1].nt);
+                }
+                d.w.grp_code2[g] = (uint8_t)(code[0] | (code[1] << 4));
+                need = (unsigned)(sets_p2_need(sm[0], sp.mode[0], sp.sel[0]) + sets_p2_need(sm[1], sp.mode[1], sp.sel[1]));
+            } else if (!quick) {
                 slow = true;
             } else {
                 int code[2] = {SFB_P2_NONE, SFB_P2_NONE};
@@ -471,8 +520,13 @@ __global__ void __launch_bounds__(128, SFB_P2_MINBLK) k_pass2_resolve(Dev d, con
         if (live && need) {
             SFB_COUNT(sc, SFB_C_ST_P2_APPLIED, (int)need);
             if (pos + need <= (u64)d.w.app_cap) {
-                App* out = p2_fast_emit(d, sc, mt[0], A, fp.mode[0], fp.sel[0], fp, 0, U, apps + pos);
-                p2_fast_emit(d, sc, mt[1], B, fp.mode[1], fp.sel[1], fp, 1, U, out);
+                if (SETS) {
+                    App* out = sets_p2_emit(d, sc, mt[0], sm[0], sp, 0, U, apps + pos);
+                    sets_p2_emit(d, sc, mt[1], sm[1], sp, 1, U, out);
+                } else {
+                    App* out = p2_fast_emit(d, sc, mt[0], A, fp.mode[0], fp.sel[0], fp, 0, U, apps + pos);
+                    p2_fast_emit(d, sc, mt[1], B, fp.mode[1], fp.sel[1], fp, 1, U, out);
+                }
             } else {
                 SFB_COUNT(sc, SFB_C_MATCH_OVERFLOW, (int)need);
             }
@@ -486,24 +540,42 @@ __global__ void __launch_bounds__(128, SFB_P2_MINBLK) k_pass2_resolve(Dev d, con
 
 #include "group_warp.cuh"
 
+int launch_expand_sets(const sfb_graph*, const sfb_reads*, const sfb_work*, sfb_accum*, int, cudaStream_t);
+
 int launch_classify(const Dev& d, cudaStream_t st) {
     if (d.r.n_groups == 0) return SFB_OK;
-    static OccCache c_fast, c_slow;
+    static OccCache c_fast, c_sets, c_slow;
+    const bool sets = d.g.node_step && d.w.aln_sets;          // the matches came from sfb_match_steps
     if (d.r.n_groups > d.w.grp_begin) {
-        const unsigned grid = persistent_grid(k_classify, 128, blocks_for(d.r.n_groups - d.w.grp_begin, 128), c_fast);
-        k_classify<<<grid, 128, 0, st>>>(d);
+        if (sets) {
+            const unsigned grid = persistent_grid(k_classify<true>, 128, blocks_for(d.r.n_groups - d.w.grp_begin, 128), c_sets);
+            k_classify<true><<<grid, 128, 0, st>>>(d);
+        } else {
+            const unsigned grid = persistent_grid(k_classify<false>, 128, blocks_for(d.r.n_groups - d.w.grp_begin, 128), c_fast);
+            k_classify<false><<<grid, 128, 0, st>>>(d);
+        }
         SFB_TRY(check_launch("k_classify"));
     }
+    if (sets) SFB_TRY(launch_expand_sets(&d.g, &d.r, &d.w, const_cast<sfb_accum*>(&d.acc), 3, st));   // tuple lists for the generic kernel
     const unsigned grid2 = persistent_grid(k_classify_slow, 128, blocks_for(d.r.n_groups, 128), c_slow);
     k_classify_slow<<<grid2, 128, 0, st>>>(d);             // usually a few percent of the groups
     return check_launch("k_classify_slow");
 }
 int launch_pass2_resolve(const Dev& d, const long long* U, cudaStream_t st) {
     if (d.r.n_groups == 0) return SFB_OK;
-    static OccCache c_fast, c_slow;
-    const unsigned grid = persistent_grid(k_pass2_resolve, 128, blocks_for(d.r.n_groups, 128), c_fast);
-    k_pass2_resolve<<<grid, 128, 0, st>>>(d, U);
+    static OccCache c_fast, c_sets, c_slow;
+    const bool sets = d.g.node_step && d.w.aln_sets;
+    if (sets) {
+        const unsigned grid = persistent_grid(k_pass2_resolve<true>, 128, blocks_for(d.r.n_groups, 128), c_sets);
+        k_pass2_resolve<true><<<grid, 128, 0, st>>>(d, U);
+    } else {
+        const unsigned grid = persistent_grid(k_pass2_resolve<false>, 128, blocks_for(d.r.n_groups, 128), c_fast);
+        k_pass2_resolve<false><<<grid, 128, 0, st>>>(d, U);
+    }
     SFB_TRY(check_launch("k_pass2_resolve"));
+    // (a deferred group that never went through the generic classify kernel -- a single mate with several alignments --
+    // may still hold path sets when it takes the generic kernel here)
+    if (sets) SFB_TRY(launch_expand_sets(&d.g, &d.r, &d.w, const_cast<sfb_accum*>(&d.acc), 4, st));
     const unsigned grid2 = persistent_grid(k_pass2_resolve_slow, 128, blocks_for(d.r.n_groups, 128), c_slow);
     k_pass2_resolve_slow<<<grid2, 128, 0, st>>>(d, U);
     return check_launch("k_pass2_resolve_slow");

@@ -29,6 +29,7 @@ __device__ __forceinline__ bool reg_load(const sfb_work& w, const Mate& mt, int 
     uint2 ma = make_uint2(SFB_MATCH_NONE, 0u), mb = ma;
     if (mt.na >= 1) ma = match_word(w, mt.a0);
     if (mt.na == 2) mb = match_word(w, mt.a0 + 1);
+    if (ma.x == SFB_MATCH_SETS || mb.x == SFB_MATCH_SETS) return false;      // path sets: group_sets.cuh, or expanded first
     const int c0 = match_count(ma), c1 = match_count(mb);
     if (c0 + c1 > kR) return false;
     r.n = c0 + c1;

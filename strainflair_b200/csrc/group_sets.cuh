@@ -1,0 +1,279 @@
+// The per-group logic on path sets (SFB_MATCH_SETS, sfb_match_steps): the fast path of k_classify / k_pass2_resolve for
+// read groups whose alignments all lie in simple tiles.
+//
+// A mate with at most two retained alignments is four 64-bit sets in registers -- forward and reverse matches of each
+// alignment, bit = path id - p0 of the tile -- whatever the number of candidate paths (the tuple fast path of
+// group_fast.cuh holds eight tuples per mate).  "colored_match" (json2csv.py:851-866) lists the tuples alignment by
+// alignment, forward matches by ascending path, then reverse: tuple order only matters for picking "the first tuple on
+// path p", which is the first of the four sets that holds p.  Set algebra of json2csv.py:922-1000 / :1123-1217:
+//     paths of a mate            S = OR of its sets          paths with several tuples   dup
+//     common paths               S0 & S1 (same tile)         list.count(p)               number of sets holding p
+//     strains of a mate          OR of path_smask over S     strain-reduced list         count(p) * popcount(smask[p] & common)
+// Included by group.cu after its effect helpers (assign_unique, hist_add, first_cluster, book, emit_app).
+#pragma once
+#include "common.cuh"
+#include "group_logic.cuh"
+
+namespace sfb {
+
+struct SetMate {
+    int na, p0, nt;      // alignments, first path id of the tile (-1: no match at all), tuples
+    u64 m[4];            // forward / reverse set of the first alignment, of the second
+    u64 S, dup;
+};
+// false: the mate does not fit (more than two alignments, tuple lists, alignments in different tiles)
+__device__ __forceinline__ bool sets_load(const sfb_work& w, const Mate& mt, SetMate& s) {
+    s.na = mt.na;
+    s.p0 = -1;
+    s.m[0] = s.m[1] = s.m[2] = s.m[3] = 0;
+    if (mt.na > 2) return false;
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+        if (j < mt.na) {
+            const uint2 x = match_word(w, mt.a0 + j);
+            if (x.x == SFB_MATCH_SETS) {
+                ok &= s.p0 < 0 || s.p0 == (int)x.y;
+                s.p0 = (int)x.y;
+                const ulonglong2 v = reinterpret_cast<const ulonglong2*>(w.aln_sets)[mt.a0 + j];
+                s.m[2 * j] = v.x;
+                s.m[2 * j + 1] = v.y;
+            } else {
+                ok &= x.x == SFB_MATCH_NONE;
+            }
+        }
+    s.S = s.m[0] | s.m[1] | s.m[2] | s.m[3];
+    s.dup = (s.m[0] & s.m[1]) | ((s.m[0] | s.m[1]) & s.m[2]) | ((s.m[0] | s.m[1] | s.m[2]) & s.m[3]);
+    s.nt = __popcll(s.m[0]) + __popcll(s.m[1]) + __popcll(s.m[2]) + __popcll(s.m[3]);
+    return ok;
+}
+__device__ __forceinline__ int sets_count(const SetMate& s, int p) {          // list_path_id.count(pid)
+    return (int)((s.m[0] >> p) & 1ull) + (int)((s.m[1] >> p) & 1ull) + (int)((s.m[2] >> p) & 1ull) + (int)((s.m[3] >> p) & 1ull);
+}
+// the node that carries the tuples of set q of the mate: the walk's first node (forward sets), its last (reverse sets)
+__device__ __forceinline__ int sets_node(const sfb_reads& r, const Mate& mt, int q) {
+    const i64 a = mt.a0 + (q >> 1);
+    return (q & 1) ? r.walk_node[r.aln_walk_off[a + 1] - 1] : r.walk_node[r.aln_walk_off[a]];
+}
+// fill_abund_dist for the first tuple of the mate on path bit p
+__device__ __forceinline__ void sets_assign(const Dev& d, BlockCounters& sc, const Mate& mt, const SetMate& s, int p) {
+    int q = 3;
+#pragma unroll
+    for (int k = 2; k >= 0; --k)
+        if ((s.m[k] >> p) & 1ull) q = k;
+    const uint2 t = sets_tuple(d.g, sets_node(d.r, mt, q), s.p0, 1ull << p, (q & 1) != 0);
+    assign_unique(d, sc, mt.a0 + (q >> 1), t.x, (int)t.y, mt.seq_len);
+}
+// strains of the mate's candidate paths (mask_words == 1)
+__device__ __forceinline__ u64 sets_strains(const sfb_graph& g, const SetMate& s) {
+    u64 u = 0;
+    for (u64 rest = s.S; rest; rest &= rest - 1) u |= g.path_smask[s.p0 + __ffsll((long long)rest) - 1];
+    return u;
+}
+// size of the strain-reduced list: a tuple counts once per common strain its path carries (json2csv.py:964-986, Q4)
+__device__ __forceinline__ int sets_reduced(const sfb_graph& g, const SetMate& s, u64 common) {
+    int nn = 0;
+    for (u64 rest = s.S; rest; rest &= rest - 1) {
+        const int p = __ffsll((long long)rest) - 1;
+        nn += sets_count(s, p) * __popcll(g.path_smask[s.p0 + p] & common);
+    }
+    return nn;
+}
+
+// both mates have colored paths (json2csv.py:918-1000); same decisions as classify_pair (group_logic.cuh)
+__device__ __forceinline__ void sets_classify_pair(const Dev& d, BlockCounters& sc, const Mate* mt, const SetMate* sm, int* code,
+                                                   bool& defer) {
+    const u64 inter = sm[0].p0 == sm[1].p0 ? sm[0].S & sm[1].S : 0ull;
+    const int n_inter = __popcll(inter);
+    if (n_inter > 1) {
+        SFB_COUNT(sc, SFB_C_SECOND_PASS, 2);
+        defer = true;
+        code[0] = code[1] = SFB_DEFER;
+        return;
+    }
+    if (n_inter == 1) {
+        const int p = __ffsll((long long)inter) - 1;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if ((sm[k].dup >> p) & 1ull) {
+                SFB_COUNT(sc, SFB_C_MULTI_ALIGN, 1);
+                code[k] = SFB_MULTI_ALIGN;
+                continue;
+            }
+            sets_assign(d, sc, mt[k], sm[k], p);
+            SFB_COUNT(sc, SFB_C_ASSIGNED_U, 1);
+            SFB_COUNT(sc, SFB_C_SAME_CP, 1);
+            if (sm[k].nt > 1) SFB_COUNT(sc, SFB_C_AMBIG_CP_RESOLVED, 1);
+            code[k] = SFB_ASSIGN_SAME;
+        }
+        return;
+    }
+    // no common path: intersect strains (json2csv.py:961-1000)
+    const u64 common = sets_strains(d.g, sm[0]) & sets_strains(d.g, sm[1]);
+    if (!common) {
+        SFB_COUNT(sc, SFB_C_INCONSIST, 2);
+        code[0] = code[1] = SFB_INCONSIST;
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int nn = sets_reduced(d.g, sm[k], common);
+        if (nn < sm[k].nt) SFB_COUNT(sc, nn == 1 ? SFB_C_AMBIG_RESOLVED : SFB_C_AMBIG_REDUCED, 1);
+        if (nn > 1) {
+            SFB_COUNT(sc, SFB_C_SECOND_PASS, 1);
+            defer = true;
+            code[k] = SFB_DEFER;
+            continue;
+        }
+        for (u64 rest = sm[k].S; rest; rest &= rest - 1) {       // exactly one tuple survives, once
+            const int p = __ffsll((long long)rest) - 1;
+            if ((d.g.path_smask[sm[k].p0 + p] & common) == 0) continue;
+            if (sets_count(sm[k], p) == 1) {
+                sets_assign(d, sc, mt[k], sm[k], p);
+                SFB_COUNT(sc, SFB_C_ASSIGNED_U, 1);
+                SFB_COUNT(sc, SFB_C_DIFF_CP, 1);
+                code[k] = SFB_ASSIGN_DIFF;
+            } else {
+                SFB_COUNT(sc, SFB_C_MULTI_ALIGN, 1);
+                code[k] = SFB_MULTI_ALIGN;
+            }
+            break;
+        }
+    }
+}
+
+// single-end style (json2csv.py:1003-1050); same decisions as classify_single (group.cu)
+__device__ __forceinline__ int sets_classify_single(const Dev& d, BlockCounters& sc, const Mate& mt, const SetMate& s, bool& defer) {
+    SFB_COUNT(sc, SFB_C_SINGLES, 1);
+    if (mt.na == 0) { SFB_COUNT(sc, SFB_C_FILTERED, 1); return SFB_FILTERED; }
+    if (mt.na > 1 || s.nt > 1) { SFB_COUNT(sc, SFB_C_SECOND_PASS, 1); defer = true; return SFB_DEFER; }
+    if (s.nt == 0) {
+        SFB_COUNT(sc, SFB_C_UNASSIGNED, 1);
+        const int c = first_cluster(d, mt.a0);
+        if (c == -2) SFB_COUNT(sc, SFB_C_NO_PATH, 1); else book(d, sc, mt, c);
+        return SFB_UNASSIGNED_BOOK;
+    }
+    SFB_COUNT(sc, SFB_C_ASSIGNED_U, 1);      // counted, never accumulated (json2csv.py:1047-1053, Q1)
+    SFB_COUNT(sc, SFB_C_SE, 1);
+    return SFB_SE_COUNTED;
+}
+
+// ---- pass 2 (json2csv.py:1085-1274) -------------------------------------------------------------------------------
+struct SetPlan {
+    int mode[2];           // kNone / kInter / kStrain / kSingle
+    u64 sel[2];            // paths that receive a share
+    long long total[2];    // kInter / kStrain: sum of the unique counts over the candidate list
+    int n[2];              // ... and its length
+    u64 common;
+};
+// json2csv.py:1123-1217; same decisions as p2_decide_pair (group_logic.cuh)
+__device__ __forceinline__ void sets_p2_decide_pair(const Dev& d, BlockCounters& sc, const SetMate* sm, const long long* U,
+                                                    SetPlan& pl, int* code) {
+    const u64 inter = sm[0].p0 == sm[1].p0 ? sm[0].S & sm[1].S : 0ull;
+    const int n_inter = __popcll(inter);
+    if (n_inter >= 1) {
+        long long total = 0;
+        for (u64 rest = inter; rest; rest &= rest - 1) total += U[sm[0].p0 + __ffsll((long long)rest) - 1];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (sm[k].dup & inter) {             // a common path with several tuples in this mate
+                SFB_COUNT(sc, SFB_C_MULTI_ALIGN, 1);
+                code[k] = SFB_P2_MULTI_ALIGN;
+                continue;
+            }
+            SFB_COUNT(sc, SFB_C_ASSIGNED_M, 1);
+            code[k] = SFB_P2_ASSIGNED;
+            pl.mode[k] = kInter;
+            pl.sel[k] = inter;
+            pl.total[k] = total;
+            pl.n[k] = n_inter;
+        }
+        return;
+    }
+    pl.common = sets_strains(d.g, sm[0]) & sets_strains(d.g, sm[1]);
+    if (!pl.common) {
+        SFB_COUNT(sc, SFB_C_INCONSIST_M, (sm[0].nt == 1 || sm[1].nt == 1) ? 1 : 2);
+        code[0] = code[1] = SFB_P2_INCONSIST;
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int nn = sets_reduced(d.g, sm[k], pl.common);
+        if (nn <= 1) continue;                   // handled in pass 1 (json2csv.py:1185)
+        bool simple = true;
+        long long tot = 0;
+        u64 sel = 0;
+        for (u64 rest = sm[k].S; rest; rest &= rest - 1) {
+            const int p = __ffsll((long long)rest) - 1;
+            const int times = __popcll(d.g.path_smask[sm[k].p0 + p] & pl.common);
+            if (times == 0) continue;
+            if (sets_count(sm[k], p) != 1) { simple = false; break; }
+            tot += U[sm[k].p0 + p] * times;
+            sel |= 1ull << p;
+        }
+        if (!simple) {
+            SFB_COUNT(sc, SFB_C_MULTI_ALIGN, 1);
+            code[k] = SFB_P2_MULTI_ALIGN;
+            continue;
+        }
+        SFB_COUNT(sc, SFB_C_ASSIGNED_M, 1);
+        code[k] = SFB_P2_ASSIGNED;
+        pl.mode[k] = kStrain;
+        pl.sel[k] = sel;
+        pl.total[k] = tot;
+        pl.n[k] = nn;
+    }
+}
+__device__ __forceinline__ int sets_p2_need(const SetMate& s, int mode, u64 sel) {
+    if (mode == kNone) return 0;
+    if (mode == kSingle) return s.nt;
+    return __popcll(s.m[0] & sel) + __popcll(s.m[1] & sel) + __popcll(s.m[2] & sel) + __popcll(s.m[3] & sel);
+}
+// The work items of one mate (json2csv.py:1155-1158, :1207-1210, :1246-1268).  An item names its path, not its slot
+// (kAppPath): k_pass2_scatter, one thread per item with every lane busy, looks the slot up next to the walk it reads
+// anyway; here a tuple costs its share and the per-path sums, no gather into the index.  One loop over the tuples of the
+// mate's four sets, so that lanes whose tuples sit in different sets (forward for one read, reverse for the next) run
+// together.
+constexpr uint32_t kAppPath = 0x80000000u;      // App.code = kAppPath | SFB_MATCH_REV? | path id
+__device__ __forceinline__ App* sets_p2_emit(const Dev& d, BlockCounters& sc, const Mate& mt, const SetMate& s, const SetPlan& pl,
+                                             int k, const long long* U, App* out) {
+    const int mode = pl.mode[k];
+    if (mode == kNone) return out;
+    const u64 sel = mode == kSingle ? ~0ull : pl.sel[k];
+    long long tot0 = 0, tot1 = 0;
+    if (mode == kSingle) {                       // every alignment separately: its own total and count
+        for (u64 rest = s.m[0]; rest; rest &= rest - 1) tot0 += U[s.p0 + __ffsll((long long)rest) - 1];
+        for (u64 rest = s.m[1]; rest; rest &= rest - 1) tot0 += U[s.p0 + __ffsll((long long)rest) - 1];
+        for (u64 rest = s.m[2]; rest; rest &= rest - 1) tot1 += U[s.p0 + __ffsll((long long)rest) - 1];
+        for (u64 rest = s.m[3]; rest; rest &= rest - 1) tot1 += U[s.p0 + __ffsll((long long)rest) - 1];
+    }
+    const int cnt0 = __popcll(s.m[0]) + __popcll(s.m[1]), cnt1 = __popcll(s.m[2]) + __popcll(s.m[3]);
+    int q = 0;
+    u64 cur = s.m[0] & sel;
+    for (;;) {
+        while (!cur && q < 3) {
+            ++q;
+            cur = (q == 1 ? s.m[1] : q == 2 ? s.m[2] : s.m[3]) & sel;
+        }
+        if (!cur) break;
+        const int pid = s.p0 + __ffsll((long long)cur) - 1;
+        cur &= cur - 1;
+        const i64 a = mt.a0 + (q >> 1);
+        const long long u = U[pid];
+        double wgt;
+        int times = 1;
+        if (mode == kInter) {
+            wgt = ratio_of(u, pl.total[k], pl.n[k]);
+        } else if (mode == kStrain) {
+            times = __popcll(d.g.path_smask[pid] & pl.common);
+            wgt = ratio_of(u, pl.total[k], pl.n[k]);
+        } else {
+            hist_add(d, sc, pid, a);                                                   // json2csv.py:1246-1252
+            wgt = (q >> 1) ? ratio_of(u, tot1, cnt1) : ratio_of(u, tot0, cnt0);
+        }
+        emit_app(d, out++, a, kAppPath | ((q & 1) ? SFB_MATCH_REV : 0u) | (uint32_t)pid, pid, mt.seq_len, wgt, times);
+    }
+    return out;
+}
+
+}  // namespace sfb

@@ -149,8 +149,9 @@ extern "C" int sfb_locality_permute(const sfb_reads* r, int n_threads, int64_t* 
     }
 }
 
-// Tile order (sfb_tiles in sfb200.h): key = the tile that holds the first and the last node of every alignment of the
-// group; groups without such a tile (mates in different tiles, a node outside every tile, no alignment) go last.
+// Tile order (sfb_tiles in sfb200.h): the groups of a tile -- the tile that holds the first and the last node of every
+// alignment of the group -- together, tiles in order, inside a tile by the first node of the group's first alignment;
+// groups without such a tile (mates in different tiles, a node outside every tile, no alignment) go last.
 extern "C" int sfb_tile_permute(const sfb_reads* r, const int32_t* node_tile, int64_t n_tiles, int n_threads,
                                 int64_t* order, int64_t* aln_index, const sfb_reads* dst, int64_t* tile_grp_off) {
     if (!r || !dst || !order || !tile_grp_off || (r->n_alns && (!aln_index || !node_tile))) return SFB_E_ARG;
@@ -158,15 +159,21 @@ extern "C" int sfb_tile_permute(const sfb_reads* r, const int32_t* node_tile, in
     if (G < 0 || A < 0 || R < 0 || n_tiles < 0 || n_tiles >= 0x7fffffffLL) return SFB_E_ARG;
     const int T = std::max(1, std::min(n_threads, 64));
     try {
-        const uint32_t none = (uint32_t)n_tiles;
+        // Inside a tile the groups are ordered by the first node of their first alignment: tiles are built in node order
+        // (tile t's nodes lie before tile t+1's), so ONE key -- that node, or "none" -- orders the groups by tile and,
+        // within a tile, by position: neighbouring alignments then gather the same index records, path constants and
+        // accumulator lines.
         std::vector<uint32_t> key((size_t)G);
         std::vector<std::vector<int64_t>> count((size_t)T);
+        std::vector<uint32_t> max_part((size_t)T, 0);
         for_chunks(T, (size_t)G, [&](int c, size_t lo, size_t hi) {
             auto& cnt = count[c];
             cnt.assign((size_t)n_tiles + 1, 0);
+            uint32_t mx = 0;
             for (size_t g = lo; g < hi; ++g) {
                 const int64_t a0 = r->grp_aln_off[2 * g], a1 = r->grp_aln_off[2 * g + 2];
                 int64_t tile = -1;
+                uint32_t node = 0xffffffffu;
                 const int64_t am = r->grp_aln_off[2 * g + 1];
                 bool ok = a1 > a0 && am - a0 <= 255 && a1 - am <= 255;      // the kernels' chunks hold 2 * 255 alignments
                 for (int64_t a = a0; a < a1 && ok; ++a) {
@@ -174,12 +181,22 @@ extern "C" int sfb_tile_permute(const sfb_reads* r, const int32_t* node_tile, in
                     if (w1 <= w0) continue;                               // an empty walk matches nothing anywhere
                     const int32_t t0 = node_tile[r->walk_node[w0]], t1 = node_tile[r->walk_node[w1 - 1]];
                     if (t0 < 0 || t0 != t1 || (tile >= 0 && t0 != tile)) ok = false;
+                    if (tile < 0) node = (uint32_t)r->walk_node[w0];
                     tile = t0;
                 }
-                const uint32_t k = ok && tile >= 0 ? (uint32_t)tile : none;
-                key[g] = k;
-                cnt[k] += 1;
+                const bool in = ok && tile >= 0;
+                key[g] = in ? node : 0xffffffffu;
+                if (in) mx = std::max(mx, node);
+                cnt[in ? (size_t)tile : (size_t)n_tiles] += 1;
             }
+            max_part[c] = mx;
+        });
+        uint32_t top = 0;
+        for (uint32_t v : max_part) top = std::max(top, v);
+        const uint32_t none = top + 1;                     // the groups outside the tiles sort last, in file order
+        for_chunks(T, (size_t)G, [&](int, size_t lo, size_t hi) {
+            for (size_t g = lo; g < hi; ++g)
+                if (key[g] == 0xffffffffu) key[g] = none;
         });
         tile_grp_off[0] = 0;
         for (int64_t t = 0; t <= n_tiles; ++t) {

@@ -49,7 +49,10 @@ constexpr int kWin = SFB_MATCH_WIN; // windows of 32 candidates per phase-A trip
 #endif
 constexpr int kSurv = 32 * kWin + SFB_MATCH_SURV_EXTRA;   // survivor list entries per warp
 
-__global__ void __launch_bounds__(256, SFB_MATCH_MINBLK) k_match(sfb_graph g, sfb_reads r, sfb_work w, long long* counters) {
+// `list` (optional): the alignments to match, *n_list of them (left over by k_match_steps); else all from w.aln_begin on.
+__global__ void __launch_bounds__(256, SFB_MATCH_MINBLK) k_match(sfb_graph g, sfb_reads r, sfb_work w, long long* counters,
+                                                                 const int32_t* __restrict__ list,
+                                                                 const unsigned long long* __restrict__ n_list) {
     __shared__ BlockCounters sc;
     __shared__ uint2 s_stage[kWarpsPerBlock][32][kKeep];
     __shared__ uint2 s_surv[kWarpsPerBlock][kSurv];
@@ -65,11 +68,12 @@ __global__ void __launch_bounds__(256, SFB_MATCH_MINBLK) k_match(sfb_graph g, sf
     const unsigned below = (1u << lane) - 1u;
     const int last_slot = (int)g.n_slots - 1;
     const i64 a_lo = w.aln_begin;                       // the alignments before it belong to the tile kernels
-    const i64 n_round = (r.n_alns - a_lo + 31) & ~(i64)31;
+    const i64 n_todo = list ? (i64)*n_list : r.n_alns - a_lo;
+    const i64 n_round = (n_todo + 31) & ~(i64)31;
     for (i64 base = ((i64)blockIdx.x * kWarpsPerBlock + wi) * 32; base < n_round;
          base += (i64)gridDim.x * kWarpsPerBlock * 32) {
-        const i64 a = a_lo + base + lane;
-        const bool live = a < r.n_alns;
+        const bool live = base + lane < n_todo;
+        const i64 a = !live ? 0 : list ? (i64)list[base + lane] : a_lo + base + lane;
         i64 w0 = 0;
         int L = 0, second = 0, penult = 0, fo = 0, fcnt = 0, ro = 0, rcnt = 0;
         if (live) {
@@ -212,8 +216,9 @@ __global__ void __launch_bounds__(256, SFB_MATCH_MINBLK) k_match(sfb_graph g, sf
             big &= big - 1;
             // the alignment's data again from (cached) global memory: keeping it in registers until here would spill
             const u64 o_pos = __shfl_sync(0xffffffffu, pos, j);
-            const i64 o_w0 = r.aln_walk_off[a_lo + base + j];
-            const int o_L = (int)(r.aln_walk_off[a_lo + base + j + 1] - o_w0);
+            const i64 o_a = __shfl_sync(0xffffffffu, a, j);
+            const i64 o_w0 = r.aln_walk_off[o_a];
+            const int o_L = (int)(r.aln_walk_off[o_a + 1] - o_w0);
             const int o_first = r.walk_node[o_w0], o_last = r.walk_node[o_w0 + o_L - 1];
             const int o_second = o_L > 1 ? r.walk_node[o_w0 + 1] : 0, o_penult = o_L > 1 ? r.walk_node[o_w0 + o_L - 2] : 0;
             const int o_fo = g.occ_off[o_first], o_fcnt = g.occ_off[o_first + 1] - o_fo;
@@ -266,12 +271,20 @@ __global__ void __launch_bounds__(256, SFB_MATCH_MINBLK) k_match(sfb_graph g, sf
     block_counters_flush(sc, counters);
 }
 
+static OccCache g_match_cache;
 int launch_match(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_accum* acc, cudaStream_t st) {
     if (r->n_alns - w->aln_begin <= 0) return SFB_OK;
-    static OccCache cache;
-    const unsigned grid = persistent_grid(k_match, 256, blocks_for(r->n_alns - w->aln_begin, 256), cache);   // a warp per 32 alignments
-    k_match<<<grid, 256, 0, st>>>(*g, *r, *w, acc->counters);
+    const unsigned grid = persistent_grid(k_match, 256, blocks_for(r->n_alns - w->aln_begin, 256), g_match_cache);   // a warp per 32 alignments
+    k_match<<<grid, 256, 0, st>>>(*g, *r, *w, acc->counters, nullptr, nullptr);
     return check_launch("k_match");
+}
+// the alignments of a device-side list (its length is only known on the device: the grid is the persistent one)
+int launch_match_list(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_accum* acc, const int32_t* list,
+                      const unsigned long long* n_list, cudaStream_t st) {
+    if (r->n_alns - w->aln_begin <= 0) return SFB_OK;
+    const unsigned grid = persistent_grid(k_match, 256, blocks_for(r->n_alns - w->aln_begin, 256), g_match_cache);
+    k_match<<<grid, 256, 0, st>>>(*g, *r, *w, acc->counters, list, n_list);
+    return check_launch("k_match (list)");
 }
 
 }  // namespace sfb

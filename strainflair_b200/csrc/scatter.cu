@@ -25,7 +25,10 @@ __global__ void __launch_bounds__(256) k_pass1_scatter(sfb_reads r, sfb_work w, 
     done = warp_sum(done);
     if (lane_id() == 0 && done) atomicAdd((u64*)&counters[SFB_C_ST_P1_RECORDS], (u64)done);
 }
-__global__ void __launch_bounds__(256) k_pass2_scatter(sfb_reads r, sfb_work w, double* mult_abund, i64 det_stride,
+// A work item of the path-set kernels names its path (bit 31 of the code; group_sets.cuh): the slot is where that path
+// has the walk's first node -- its last node for a match of the reversed walk -- i.e. occurrence number
+// popcount(node_mask & (bit - 1)) of the node (sfb200.h, SFB_MATCH_SETS).
+__global__ void __launch_bounds__(256) k_pass2_scatter(sfb_graph g, sfb_reads r, sfb_work w, double* mult_abund, i64 det_stride,
                                                        long long* counters) {
     const App* apps = reinterpret_cast<const App*>(w.app_buf);
     // more work items claimed than app_buf holds: the resolve kernels counted MATCH_OVERFLOW and left claims unwritten;
@@ -36,7 +39,13 @@ __global__ void __launch_bounds__(256) k_pass2_scatter(sfb_reads r, sfb_work w, 
         const App app = apps[q];
         const i64 w0 = r.aln_walk_off[app.aln];
         const int L = (int)(r.aln_walk_off[app.aln + 1] - w0);
-        double* dst = mult_abund + (app.code & SFB_SLOT_MASK);
+        uint32_t slot = app.code & SFB_SLOT_MASK;
+        if (app.code & 0x80000000u) {
+            const int node = r.walk_node[(app.code & SFB_MATCH_REV) ? w0 + L - 1 : w0];
+            const u64 bit = 1ull << ((int)slot - (int)reinterpret_cast<const uint2*>(w.aln_match)[app.aln].y);
+            slot = (uint32_t)reinterpret_cast<const int2*>(g.occ_pair)[g.occ_off[node] + __popcll(g.node_mask[node] & (bit - 1))].x;
+        }
+        double* dst = mult_abund + slot;
         for (int i = 0; i < L; ++i) acc_add(dst + i, det_stride, record_cov(r, w0 + i) * app.weight);
         done += L;
     }
@@ -65,7 +74,7 @@ int launch_pass2_scatter(const sfb_graph* g, const sfb_reads* r, const sfb_work*
     if (r->n_alns == 0 || w->app_cap == 0) return SFB_OK;
     static OccCache cache;
     const unsigned grid = persistent_grid(k_pass2_scatter, 256, blocks_for(w->app_cap, 256), cache);
-    k_pass2_scatter<<<grid, 256, 0, st>>>(*r, *w, acc->mult_abund, acc->det_stride, acc->counters);
+    k_pass2_scatter<<<grid, 256, 0, st>>>(*g, *r, *w, acc->mult_abund, acc->det_stride, acc->counters);
     return check_launch("k_pass2_scatter");
 }
 

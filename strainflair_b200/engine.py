@@ -83,6 +83,7 @@ class DeviceGraph:
         from .tiles import Tiling
         import os
         self.tiling = Tiling(graph, slot_cap=int(os.environ.get("SFB200_TILE_SLOTS", "4096"))) if tiles else None
+        self.steps = None                        # pointers of the step index inside sfb_graph, when the graph has simple tiles
         if self.tiling is not None and self.tiling.n_tiles == 0:
             self.tiling = None
         if self.tiling is not None:
@@ -94,6 +95,13 @@ class DeviceGraph:
             probe = _lib.SfbTiles(n_tiles=tl.n_tiles, n_items=0, max_slots=tl.max_slots, max_nodes=tl.max_nodes,
                                   max_paths=tl.max_paths, max_edges=tl.max_edges, tuple_cap=tl.tuple_cap)
             need = int(_lib.load().sfb_tile_smem_bytes(C.byref(probe)))
+            # step index of the simple tiles for sfb_match_steps (needs no shared memory: kept whatever the tile kernels say)
+            if tl.tile_desc[:, 4].any():
+                rec, partial = tl.step_records(graph)
+                self.node_step = _to_dev(rec.view(np.int64), d)
+                self.steps = dict(node_step=self.node_step.data_ptr(), node_mask=self.tile_edges["node_mask"].data_ptr(),
+                                  step_off=self.tile_edges["edge_off"].data_ptr(), step_succ=self.tile_edges["edge_succ"].data_ptr(),
+                                  step_mask=self.tile_edges["edge_mask"].data_ptr(), steps_partial=int(partial))
             if need < 0 or need > 227 * 1024:
                 self.tiling = None
         self.t = dict(
@@ -104,6 +112,10 @@ class DeviceGraph:
         )
         self.c = _lib.SfbGraph(n_nodes=graph.n_nodes, n_paths=P, n_slots=n_slots, n_strains=S, mask_words=words,
                                **{k: v.data_ptr() for k, v in self.t.items()})
+        # the same graph with its step index: sfb_match_steps and the group kernels on path sets
+        self.c_steps = None if self.steps is None else _lib.SfbGraph(
+            n_nodes=graph.n_nodes, n_paths=P, n_slots=n_slots, n_strains=S, mask_words=words,
+            **{k: v.data_ptr() for k, v in self.t.items()}, **self.steps)
 
     def nbytes(self):
         return sum(v.numel() * v.element_size() for v in self.t.values())
@@ -290,17 +302,20 @@ class DeviceReads:
 class Work:
     """Per-shard work arrays (sfb_work)."""
 
-    def __init__(self, n_groups, n_alns, match_cap, device):
+    def __init__(self, n_groups, n_alns, match_cap, device, app_cap=0):
         i32, u8 = torch.int32, torch.uint8
         self.n_groups, self.n_alns = n_groups, n_alns
         self.match_cap = int(max(2, match_cap))
-        self.app_cap = max(int(n_alns + self.match_cap),        # >= number of matches of the shard
-                           _lib.workspace(_lib.WS_APP_ITEMS, n_alns=n_alns))
+        # pass-2 work items: one per match that receives a share.  With tuple lists that is at most n_alns + match_cap;
+        # with path sets (sfb_match_steps) the matches are not in match_buf, so the default is a guess and a pass that
+        # needs more reports its exact need (cursor[2]) for the rerun
+        self.app_cap = max(int(n_alns + self.match_cap), int(app_cap), _lib.workspace(_lib.WS_APP_ITEMS, n_alns=n_alns))
         self.t = dict(
             aln_match=torch.empty(max(1, n_alns), dtype=torch.int64, device=device),      # (x, y) pairs
+            aln_sets=torch.empty(2 * max(1, n_alns), dtype=torch.int64, device=device),   # forward / reverse path sets
             match_buf=torch.empty(self.match_cap, dtype=torch.int64, device=device),       # (code, pid) pairs
             app_buf=torch.empty(2 * self.app_cap, dtype=torch.int64, device=device),       # 16-byte items
-            cursor=torch.zeros(8, dtype=torch.int64, device=device),
+            cursor=torch.zeros(_lib.CURSOR_N, dtype=torch.int64, device=device),
             slow=torch.empty(max(1, n_groups), dtype=i32, device=device),
             grp_code=torch.zeros(max(1, n_groups), dtype=u8, device=device),
             grp_code2=torch.zeros(max(1, n_groups), dtype=u8, device=device),
@@ -464,7 +479,8 @@ class AbundanceEngine:
     """One engine per process/GPU.  ``comm`` is an optional torch.distributed process group: when
     given, ``run`` treats ``reads`` as this rank's shard of the read groups."""
 
-    def __init__(self, graph: Graph, device="cuda:0", comm=None, deterministic=True, tiles=True, tile_kernels=None):
+    def __init__(self, graph: Graph, device="cuda:0", comm=None, deterministic=True, tiles=True, tile_kernels=None,
+                 step_index=None):
         if not torch.cuda.is_available():
             raise _lib.SfbError("no CUDA device: the abundance engine has no CPU fallback")
         self.lib = _lib.load()
@@ -483,6 +499,12 @@ class AbundanceEngine:
         if tile_kernels is None:
             tile_kernels = os.environ.get("SFB200_TILE_KERNELS", "0").strip().lower() in ("1", "true", "yes", "on")
         self.tile_kernels = bool(tile_kernels) and self.tiling is not None
+        # matching through the step index of the simple tiles (sfb_match_steps) wherever the graph has such tiles;
+        # step_index=False / SFB200_STEP_INDEX=0: the occurrence-index kernel (sfb_match) for every alignment
+        if step_index is None:
+            step_index = os.environ.get("SFB200_STEP_INDEX", "1").strip().lower() not in ("0", "false", "no", "off")
+        self.step_index = bool(step_index) and self.dg.steps is not None
+        self.gc = self.dg.c_steps if self.step_index else self.dg.c          # the sfb_graph every call of this engine gets
         self.node_len = _to_dev(graph.node_len, self.device)
         self.comm = comm
         # order-independent sums (96-bit fixed point, the default): bit-identical across runs, shard counts and GPU
@@ -500,15 +522,16 @@ class AbundanceEngine:
         self.side = torch.cuda.Stream(device=self.device)     # pass-1 scatter runs beside the uniq exchange + pass-2 resolve
         self.overlap = True
         self.match_cap_hint = 0
+        self.app_cap_hint = 0
         self.launches = 0
 
     # ---- stages (each is one kernel launch through the C ABI) -----------------------------
     def _work_for(self, dr):
         cap = max(self.match_cap_hint, _lib.workspace(_lib.WS_MATCH_PAIRS, n_alns=dr.n_alns))   # (code, path id) pairs
         if self.work is None or self.work.n_groups < dr.n_groups or self.work.n_alns < dr.n_alns \
-                or self.work.match_cap < cap:
+                or self.work.match_cap < cap or self.work.app_cap < self.app_cap_hint:
             self.work = None
-            self.work = Work(dr.n_groups, dr.n_alns, cap, self.device)
+            self.work = Work(dr.n_groups, dr.n_alns, cap, self.device, self.app_cap_hint)
         return self.work
 
     def stage(self, reads: Reads, pin=True, wire=True):
@@ -522,7 +545,7 @@ class AbundanceEngine:
     def tile_pass1(self, dr, work):
         if dr.tiles_c is None:
             return
-        _lib.check(self.lib.sfb_tile_pass1(C.byref(self.dg.c), C.byref(dr.tiles_c), C.byref(dr.c), C.byref(work.c),
+        _lib.check(self.lib.sfb_tile_pass1(C.byref(self.gc), C.byref(dr.tiles_c), C.byref(dr.c), C.byref(work.c),
                                            C.byref(self.acc.c), _stream()))
         self.launches += 1
 
@@ -530,36 +553,40 @@ class AbundanceEngine:
         if dr.tiles_c is None:
             return
         u = self.acc.uniq_reads if uniq_global is None else uniq_global
-        _lib.check(self.lib.sfb_tile_pass2(C.byref(self.dg.c), C.byref(dr.tiles_c), C.byref(dr.c), C.byref(work.c),
+        _lib.check(self.lib.sfb_tile_pass2(C.byref(self.gc), C.byref(dr.tiles_c), C.byref(dr.c), C.byref(work.c),
                                            C.byref(self.acc.c), C.c_void_p(u.data_ptr()), _stream()))
         self.launches += 1
 
     def match(self, dr, work):
-        _lib.check(self.lib.sfb_match(C.byref(self.dg.c), C.byref(dr.c), C.byref(work.c), C.byref(self.acc.c), _stream()))
+        if self.step_index:
+            _lib.check(self.lib.sfb_match_steps(C.byref(self.gc), C.byref(dr.c), C.byref(work.c), C.byref(self.acc.c), _stream()))
+            self.launches += 2 if self.dg.steps["steps_partial"] else 1
+            return
+        _lib.check(self.lib.sfb_match(C.byref(self.gc), C.byref(dr.c), C.byref(work.c), C.byref(self.acc.c), _stream()))
         self.launches += 1
 
     def classify(self, dr, work):
-        _lib.check(self.lib.sfb_classify(C.byref(self.dg.c), C.byref(dr.c), C.byref(work.c), C.byref(self.acc.c), _stream()))
-        self.launches += 2       # register-path kernel + generic kernel
+        _lib.check(self.lib.sfb_classify(C.byref(self.gc), C.byref(dr.c), C.byref(work.c), C.byref(self.acc.c), _stream()))
+        self.launches += 3       # register-path kernel, tuple lists for the generic kernel, generic kernel
 
     def pass1_scatter(self, dr, work):
-        _lib.check(self.lib.sfb_pass1_scatter(C.byref(self.dg.c), C.byref(dr.c), C.byref(work.c), C.byref(self.acc.c), _stream()))
+        _lib.check(self.lib.sfb_pass1_scatter(C.byref(self.gc), C.byref(dr.c), C.byref(work.c), C.byref(self.acc.c), _stream()))
         self.launches += 1
 
     def pass2(self, dr, work, uniq_global=None):
         u = self.acc.uniq_reads if uniq_global is None else uniq_global
-        _lib.check(self.lib.sfb_pass2(C.byref(self.dg.c), C.byref(dr.c), C.byref(work.c), C.byref(self.acc.c),
+        _lib.check(self.lib.sfb_pass2(C.byref(self.gc), C.byref(dr.c), C.byref(work.c), C.byref(self.acc.c),
                                       C.c_void_p(u.data_ptr()), _stream()))
-        self.launches += 3
+        self.launches += 4
 
     def pass2_resolve(self, dr, work, uniq_global=None):
         u = self.acc.uniq_reads if uniq_global is None else uniq_global
-        _lib.check(self.lib.sfb_pass2_resolve(C.byref(self.dg.c), C.byref(dr.c), C.byref(work.c), C.byref(self.acc.c),
+        _lib.check(self.lib.sfb_pass2_resolve(C.byref(self.gc), C.byref(dr.c), C.byref(work.c), C.byref(self.acc.c),
                                               C.c_void_p(u.data_ptr()), _stream()))
-        self.launches += 2
+        self.launches += 3
 
     def pass2_scatter(self, dr, work):
-        _lib.check(self.lib.sfb_pass2_scatter(C.byref(self.dg.c), C.byref(dr.c), C.byref(work.c), C.byref(self.acc.c), _stream()))
+        _lib.check(self.lib.sfb_pass2_scatter(C.byref(self.gc), C.byref(dr.c), C.byref(work.c), C.byref(self.acc.c), _stream()))
         self.launches += 1
 
     def collapse(self):
@@ -570,7 +597,7 @@ class AbundanceEngine:
     def path_reduce(self, p_begin=0, p_end=None):
         p_end = self.graph.n_paths if p_end is None else p_end
         out = self.table[p_begin:p_end]
-        _lib.check(self.lib.sfb_path_reduce(C.byref(self.dg.c), C.byref(self.acc.c), p_begin, p_end,
+        _lib.check(self.lib.sfb_path_reduce(C.byref(self.gc), C.byref(self.acc.c), p_begin, p_end,
                                             C.c_void_p(out.data_ptr()), _stream()))
         self.launches += 1
         return out
@@ -726,8 +753,9 @@ class AbundanceEngine:
             slot["wide"] = dr.wide
             cap = max(slot.get("cap", 0), _lib.workspace(_lib.WS_MATCH_PAIRS, n_alns=dr.n_alns))
             work = slot.get("work")
-            if work is None or work.n_groups < dr.n_groups or work.n_alns < dr.n_alns or work.match_cap < cap:
-                work = slot["work"] = Work(dr.n_groups, dr.n_alns, cap, self.device)
+            if work is None or work.n_groups < dr.n_groups or work.n_alns < dr.n_alns or work.match_cap < cap \
+                    or work.app_cap < slot.get("app", 0):
+                work = slot["work"] = Work(dr.n_groups, dr.n_alns, cap, self.device, slot.get("app", 0))
             work.reset()
             self._bind(dr, work)
             self.tile_pass1(dr, work)
@@ -758,7 +786,7 @@ class AbundanceEngine:
                 f=torch.empty(3 * P, dtype=torch.float64).pin_memory(),
                 i=torch.empty(acc.i64.numel(), dtype=torch.int64).pin_memory(),
                 t=torch.empty((max(1, P), _lib.TABLE_COLS), dtype=torch.float64).pin_memory(),
-                c=torch.empty((max(1, len(live)), 8), dtype=torch.int64).pin_memory())
+                c=torch.empty((max(1, len(live)), _lib.CURSOR_N), dtype=torch.int64).pin_memory())
         st = job.stage
         st["f"].copy_(acc.f64[:3 * P], non_blocking=True)
         st["i"].copy_(acc.i64, non_blocking=True)
@@ -781,10 +809,12 @@ class AbundanceEngine:
                 job.pending = False
                 res.n_deferred = int(cur[:len(job.live), 1].sum() + cur[:len(job.live), 7].sum())
                 res.match_fill = int(cur[len(job.live) - 1, 0]) if job.live else 0
+                res.app_fill = int(cur[:len(job.live), 2].max()) if job.live else 0
                 check_errors(res.C)
                 return res
-            for k in range(len(job.live)):            # grow every shard's match buffer to its exact need, rerun
+            for k in range(len(job.live)):            # grow every shard's buffers to their exact need, rerun
                 job.slots[k]["cap"] = int(cur[k, 0]) + 1024
+                job.slots[k]["app"] = int(cur[k, 2]) + 1024
             job = self.submit(job.shards, _reuse=job)     # same buffers again
         job.pending = False
         raise MatchOverflow("match buffer still too small after regrowing")
@@ -806,7 +836,41 @@ class AbundanceEngine:
             if over == 0:
                 return res
             self.match_cap_hint = res.match_fill + 1024                    # exact need, rerun
+            self.app_cap_hint = res.app_fill + 1024
         raise MatchOverflow("match buffer still too small after regrowing")
+
+    def _sets_to_tuples(self, res, sets, reads):
+        """Diagnostics (``keep_codes``): the path sets sfb_match_steps left in ``aln_sets`` written out as the tuple lists
+        sfb_match would have produced -- forward matches by ascending path, then reverse; the slot of a tuple is where its
+        path has the walk's first (reversed: last) node."""
+        if reads is None:
+            raise ValueError("the staged reads were dropped: the path sets cannot be turned into match lists")
+        g = self.graph
+        starts = g.path_off[:-1].astype(np.int64) + np.arange(g.n_paths)                   # sentinel layout
+        aln_match, extra = res.aln_match.copy(), []
+        base = len(res.match_buf)
+        for a in np.flatnonzero(aln_match[:, 0] == _lib.MATCH_SETS):
+            p0 = int(aln_match[a, 1])
+            w0, w1 = int(reads.aln_walk_off[a]), int(reads.aln_walk_off[a + 1])
+            tuples = []
+            for word, node, flag in ((int(sets[a, 0]), int(reads.walk_node[w0]), 0),
+                                     (int(sets[a, 1]), int(reads.walk_node[w1 - 1]), _lib.MATCH_REV)):
+                b = 0
+                while word >> b:
+                    if (word >> b) & 1:
+                        pid = p0 + b
+                        nodes = g.path_nodes[g.path_off[pid]:g.path_off[pid + 1]]
+                        pos = int(np.flatnonzero(nodes == node)[0])
+                        tuples.append((int(starts[pid]) + pos | flag, pid))
+                    b += 1
+            if len(tuples) == 1:
+                aln_match[a] = tuples[0]
+            else:
+                aln_match[a] = (_lib.MATCH_MULTI | (base + len(extra)), len(tuples))
+                extra.extend(tuples)
+        res.aln_match = aln_match
+        if extra:
+            res.match_buf = np.concatenate([res.match_buf, np.asarray(extra, np.uint32).reshape(-1, 2)])
 
     def _result_from(self, acc, f64, i64, table):
         """Host copies of the read-back buffers as a Result."""
@@ -840,7 +904,7 @@ class AbundanceEngine:
                 f=torch.empty(3 * P, dtype=torch.float64).pin_memory(),
                 i=torch.empty(acc.i64.numel(), dtype=torch.int64).pin_memory(),
                 t=torch.empty((max(1, P), _lib.TABLE_COLS), dtype=torch.float64).pin_memory(),
-                c=torch.empty(8, dtype=torch.int64).pin_memory())
+                c=torch.empty(_lib.CURSOR_N, dtype=torch.int64).pin_memory())
         st = self._stage
         st["f"].copy_(acc.f64[:3 * P], non_blocking=True)
         st["i"].copy_(acc.i64, non_blocking=True)
@@ -853,7 +917,7 @@ class AbundanceEngine:
             slots = (acc.uniq_abund[self._plain_idx].cpu(), acc.mult_abund[self._plain_idx].cpu())   # sentinels dropped on device
         torch.cuda.current_stream().synchronize()
         res = self._result_from(acc, st["f"].numpy(), st["i"].numpy(), st["t"].numpy())
-        res.n_deferred, res.match_fill = int(st["c"][1]) + int(st["c"][7]), int(st["c"][0])
+        res.n_deferred, res.match_fill, res.app_fill = int(st["c"][1]) + int(st["c"][7]), int(st["c"][0]), int(st["c"][2])
         if slots is not None:
             res.uniq_abund, res.mult_abund = slots[0].numpy(), slots[1].numpy()
         if keep_codes:
@@ -864,6 +928,9 @@ class AbundanceEngine:
                 res.aln_match = work.t["aln_match"][:dr.n_alns].cpu().numpy().view(np.uint32).reshape(-1, 2)
                 res.match_buf = work.t["match_buf"][:min(work.match_cap, max(0, res.match_fill))].cpu().numpy() \
                     .view(np.uint32).reshape(-1, 2)
+                if (res.aln_match[:, 0] == _lib.MATCH_SETS).any():
+                    sets = work.t["aln_sets"][:2 * dr.n_alns].cpu().numpy().view(np.uint64).reshape(-1, 2)
+                    self._sets_to_tuples(res, sets, getattr(getattr(dr, "host", None), "reads", None))
             host = getattr(dr, "host", None)
             if host is not None and getattr(host, "order", None) is not None:
                 restore_file_order(res, host.order, host.aln_index)
@@ -900,9 +967,11 @@ def decode_matches(res, a):
     return [(pid, int((c & _lib.SLOT_MASK) - starts[pid]), bool(c & _lib.MATCH_REV)) for c, pid in pairs]
 
 
-def abundance_pass(graph: Graph, reads: Reads, device="cuda:0", deterministic=True, tiles=True, tile_kernels=None) -> Result:
+def abundance_pass(graph: Graph, reads: Reads, device="cuda:0", deterministic=True, tiles=True, tile_kernels=None,
+                   step_index=None) -> Result:
     """One-call public API: decoded alignments + graph in, per-path abundances and counters out."""
-    return AbundanceEngine(graph, device, deterministic=deterministic, tiles=tiles, tile_kernels=tile_kernels).run(reads)
+    return AbundanceEngine(graph, device, deterministic=deterministic, tiles=tiles, tile_kernels=tile_kernels,
+                           step_index=step_index).run(reads)
 
 
 def cluster_strain_counts(graph: Graph, device="cuda:0"):

@@ -88,7 +88,12 @@ class Tiling:
         count = np.bincount(seg_of_path, minlength=n_seg)
         slots = np.bincount(seg_of_path, weights=plen + 1, minlength=n_seg).astype(np.int64)
         ok = (count == pmax - pmin + 1) & (slots <= slot_cap) & (seg_hi - seg_lo <= node_cap) & (count <= path_cap)
-        # neighbouring small segments (in node order AND path order) merge up to merge_target slots
+        # a segment is "simple" when it has at most 64 paths and none of them visits a node twice
+        seg_dup = np.zeros(n_seg, bool)
+        seg_dup[seg_of_path[self._dup_paths(graph)]] = True
+        seg_simple = (count <= 64) & ~seg_dup
+        # neighbouring small segments (in node order AND path order) merge up to merge_target slots; a simple segment only
+        # merges with simple ones, and only while the merged tile stays simple
         desc = []
         cur = None
         for s in range(n_seg):
@@ -97,10 +102,11 @@ class Tiling:
                     desc.append(cur)
                     cur = None
                 continue
-            item = [int(pmin[s]), int(pmax[s]) + 1, int(seg_lo[s]), int(seg_hi[s]), int(slots[s])]
+            item = [int(pmin[s]), int(pmax[s]) + 1, int(seg_lo[s]), int(seg_hi[s]), int(slots[s]), bool(seg_simple[s])]
             if cur is not None and cur[1] == item[0] and cur[4] + item[4] <= merge_target \
-                    and item[3] - cur[2] <= node_cap and item[1] - cur[0] <= path_cap:
-                cur = [cur[0], item[1], cur[2], item[3], cur[4] + item[4]]
+                    and item[3] - cur[2] <= node_cap and item[1] - cur[0] <= path_cap \
+                    and cur[5] == item[5] and (not item[5] or item[1] - cur[0] <= 64):
+                cur = [cur[0], item[1], cur[2], item[3], cur[4] + item[4], cur[5]]
             else:
                 if cur is not None:
                     desc.append(cur)
@@ -109,7 +115,7 @@ class Tiling:
             desc.append(cur)
         if not desc:
             return
-        desc = np.asarray(desc, np.int64)
+        desc = np.asarray([d[:5] for d in desc], np.int64)
         self.tile_desc = np.zeros((len(desc), 8), np.int32)
         self.tile_desc[:, :4] = desc[:, :4]
         self.max_slots = int(desc[:, 4].max())
@@ -119,6 +125,16 @@ class Tiling:
         self.node_tile[np.repeat(desc[:, 2], span) + (np.arange(int(span.sum())) - np.repeat(np.cumsum(span) - span, span))] = \
             np.repeat(np.arange(len(desc), dtype=np.int32), span)
         self._edges(graph, desc)
+
+    @staticmethod
+    def _dup_paths(graph):
+        """Ids of the paths that visit a node more than once."""
+        P, N = graph.n_paths, graph.n_nodes
+        path_of = np.repeat(np.arange(P, dtype=np.int64), np.diff(graph.path_off.astype(np.int64)))
+        srt = np.sort(path_of * N + graph.path_nodes.astype(np.int64))
+        if len(srt) < 2:
+            return np.zeros(0, np.int64)
+        return np.unique(srt[1:][srt[1:] == srt[:-1]] // N)
 
     def _edges(self, graph, desc):
         """Edge index of the simple tiles (see the class docstring)."""
@@ -132,11 +148,8 @@ class Tiling:
         tile_of_path[np.repeat(desc[:, 0], np_t) + (np.arange(int(np_t.sum())) - np.repeat(np.cumsum(np_t) - np_t, np_t))] = \
             np.repeat(np.arange(len(desc)), np_t)
         # a node twice in one path?  (path, node) pairs must be distinct
-        key = path_of * N + nodes
-        srt = np.sort(key)
         dup_path = np.zeros(P, bool)
-        if len(srt) > 1:
-            dup_path[(srt[1:][srt[1:] == srt[:-1]] // N)] = True
+        dup_path[self._dup_paths(graph)] = True
         bad_tile = np.zeros(len(desc), bool)
         tp = tile_of_path[dup_path]
         bad_tile[tp[tp >= 0]] = True
@@ -167,6 +180,32 @@ class Tiling:
         self.edge_off = np.concatenate(([0], np.cumsum(np.bincount(ua, minlength=N)))).astype(np.int32)
         per_tile = self.edge_off[desc[:, 3]] - self.edge_off[desc[:, 2]]
         self.max_edges = int(per_tile.max()) if len(per_tile) else 0
+
+    STEP_DTYPE = np.dtype([("succ0", "<i4"), ("succ1", "<i4"), ("mask0", "<u8"), ("mask1", "<u8"), ("p0", "<i4"), ("n_succ", "<i4")])
+
+    def step_records(self, graph):
+        """The per-node records of ``sfb_steps`` (include/sfb200.h) and whether any node with occurrences lies outside
+        the simple tiles (its walks then need the occurrence-index kernel)."""
+        N = graph.n_nodes
+        rec = np.zeros(N, self.STEP_DTYPE)
+        rec["succ0"] = rec["succ1"] = -1
+        rec["p0"] = -1
+        t = self.node_tile
+        simple = np.zeros(N, bool)
+        if self.n_tiles:
+            inside = t >= 0
+            simple[inside] = self.tile_desc[t[inside], 4] != 0
+            rec["p0"][simple] = self.tile_desc[t[simple], 0]
+        crossed = np.bincount(graph.path_nodes, minlength=N) > 0
+        rec["p0"][~crossed] = 0                     # no path through the node: no match, whatever the rest of the walk
+        n_succ = np.diff(self.edge_off).astype(np.int32)
+        rec["n_succ"] = n_succ
+        e0 = self.edge_off[:-1].astype(np.int64)
+        for k, (sk, mk) in enumerate((("succ0", "mask0"), ("succ1", "mask1"))):
+            has = n_succ > k
+            rec[sk][has] = self.edge_succ[e0[has] + k]
+            rec[mk][has] = self.edge_mask[e0[has] + k]
+        return rec, bool((crossed & ~simple).any())
 
     def items(self, tile_grp_off):
         """Work items int32[n, 4] = (tile, first group, end group, 0) of a read shard in tile order."""

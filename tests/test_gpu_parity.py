@@ -23,8 +23,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # the kernel families (global-memory kernels on tile-ordered reads = the default, shared-memory tile kernels,
 # global-memory kernels on reads in file order) and the two accumulation modes
 MODES = [dict(), dict(deterministic=False), dict(tile_kernels=True), dict(tile_kernels=True, deterministic=False),
-         dict(tiles=False), dict(tiles=False, deterministic=False)]
-MODE_IDS = ["default", "default-plain", "tilekernels-det", "tilekernels-plain", "fileorder-det", "fileorder-plain"]
+         dict(tiles=False), dict(tiles=False, deterministic=False), dict(step_index=False)]
+MODE_IDS = ["default", "default-plain", "tilekernels-det", "tilekernels-plain", "fileorder-det", "fileorder-plain",
+            "occurrence-index-match"]
 all_modes = pytest.mark.parametrize("mode", MODES, ids=MODE_IDS)
 
 
@@ -132,10 +133,14 @@ def test_explicit_coverage_records(mode):
     check_against_oracle(graph, reads, res, orc)
 
 
-def test_match_lists_equal_oracle():
+@pytest.mark.parametrize("mode", [dict(tiles=False), dict(), dict(step_index=False)],
+                         ids=["fileorder-occurrence-index", "tileorder-step-index", "tileorder-occurrence-index"])
+def test_match_lists_equal_oracle(mode):
     need_gpu()
     graph, reads = synth.make_config("tiny")
-    res = engine.abundance_pass(graph, reads, tiles=False)      # the tile kernels keep their match lists in shared memory
+    eng = engine.AbundanceEngine(graph, **mode)                 # (the tile kernels keep their match lists in shared memory)
+    assert eng.step_index == (mode == dict())
+    res = eng.run(reads)
     orc = oa.AbundanceOracle(graph.as_dict(), reads.as_dict())
     for a in range(reads.n_alns):
         mine = engine.decode_matches(res, a)
@@ -215,6 +220,96 @@ def test_match_corner_cases_equal_oracle(seed, alphabet):
     eng = engine.AbundanceEngine(graph, tile_kernels=True)
     assert eng.tiling is not None and eng.tiling.n_tiles == 1 and eng.tile_kernels
     check_against_oracle(graph, reads, eng.run(reads), orc)
+
+
+def _mixed_case(seed):
+    """A graph whose first cluster is not a simple tile (repeated nodes inside paths) next to clusters that are: the
+    step-index kernel matches the walks that start in the simple part and lists the others for the occurrence-index
+    kernel; walks that cross from one part into the other match nothing either way."""
+    rng = np.random.default_rng(seed)
+    g0, r0 = _repetitive_case(seed, n_paths=12, alphabet=5, n_walks=600)
+    base = g0.n_nodes
+    paths = [g0.path_nodes[g0.path_off[p]:g0.path_off[p + 1]].tolist() for p in range(g0.n_paths)]
+    n_rep = len(paths)
+    clusters = [list(range(n_rep))]
+    node_len = list(g0.node_len)
+    for c in range(3):                                         # bubble chains: position i has one or two alleles
+        alle = []
+        for i in range(14):
+            k = 2 if rng.random() < 0.5 else 1
+            alle.append(list(range(base, base + k)))
+            base += k
+            node_len.extend(int(x) for x in rng.integers(1, 40, k))
+        mine, seen = [], set()
+        for _ in range(6):
+            pth = tuple(int(a[int(rng.integers(0, len(a)))]) for a in alle)
+            if rng.random() < 0.4:
+                pth = pth[::-1]
+            if pth not in seen:
+                seen.add(pth)
+                mine.append(len(paths))
+                paths.append(list(pth))
+        clusters.append(mine)
+    P = len(paths)
+    node_len = np.asarray(node_len, np.int32)
+    plen = np.array([len(x) for x in paths])
+    graph = Graph(
+        node_ids=np.arange(1, base + 1), node_len=node_len, path_off=np.concatenate(([0], np.cumsum(plen))).astype(np.int64),
+        path_nodes=np.concatenate(paths).astype(np.int32), path_seq_len=np.array([int(node_len[x].sum()) for x in paths]),
+        pstr_off=np.arange(P + 1), pstr_id=(np.arange(P) % 3).astype(np.int32), pstr_cnt=np.ones(P, np.int32),
+        path_cluster=np.concatenate([np.full(len(m), c, np.int32) for c, m in enumerate(clusters)]),
+        clu_off=np.concatenate(([0], np.cumsum([len(m) for m in clusters]))), clu_paths=np.arange(P, dtype=np.int32),
+        strain_names=["NC_1.1", "NC_2.1", "NC_3.1"], header_strains=[0, 1, 2], path_names=None)
+    walks = [r0.walk_node[r0.aln_walk_off[a]:r0.aln_walk_off[a + 1]].tolist() for a in range(r0.n_alns)]
+    crossed = np.unique(np.concatenate(paths))                 # (a walk that starts on a node no path crosses raises, Q10)
+
+    def any_node():
+        return int(crossed[int(rng.integers(0, len(crossed)))])
+    for _ in range(2400):
+        pth = paths[int(rng.integers(n_rep, P))]
+        i = int(rng.integers(0, len(pth)))
+        j = int(rng.integers(i + 1, min(len(pth), i + 9) + 1))
+        wk = list(pth[i:j])
+        kind = rng.random()
+        if kind < 0.4:
+            wk = wk[::-1]
+        elif kind < 0.5:
+            wk = wk + [any_node()]                             # onto any node, the non-simple part included
+        elif kind < 0.6:
+            wk = [any_node()] + wk
+        elif kind < 0.7:
+            wk[int(rng.integers(0, len(wk)))] = any_node()
+        walks.append(wk)
+    order = rng.permutation(len(walks))
+    walks = [walks[k] for k in order]
+    A = len(walks)
+    wl = np.array([len(x) for x in walks])
+    walk_node = np.concatenate(walks).astype(np.int32)
+    reads = Reads(
+        grp_nmates=np.ones(A, np.uint8), grp_aln_off=np.minimum(np.arange(2 * A + 1) + 1, 2 * A + 1) // 2,
+        mate_seq_len=np.full(2 * A, 100, np.int32), aln_walk_off=np.concatenate(([0], np.cumsum(wl))),
+        aln_read_len=np.full(A, 100, np.int32), aln_bins=np.zeros((A, 5), np.uint8), walk_node=walk_node,
+        walk_alen=(1 | (node_len[walk_node].astype(np.int32) << 16)), exc_cov=np.zeros(0), mate_names=None)
+    return graph, reads
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_step_index_with_occurrence_index_leftovers(seed):
+    need_gpu()
+    graph, reads = _mixed_case(seed)
+    eng = engine.AbundanceEngine(graph)
+    assert eng.step_index and eng.dg.steps["steps_partial"]
+    res = eng.run(reads)
+    orc = oa.AbundanceOracle(graph.as_dict(), reads.as_dict())
+    n_match = 0
+    for a in range(reads.n_alns):
+        mine = engine.decode_matches(res, a)
+        assert [(p, pos) for p, pos, _ in mine] == orc.match(a), (a, reads.walk_node[reads.aln_walk_off[a]:reads.aln_walk_off[a + 1]])
+        n_match += len(mine)
+    assert n_match > reads.n_alns // 2
+    orc.run()
+    check_against_oracle(graph, reads, res, orc)
+    check_against_oracle(graph, reads, engine.abundance_pass(graph, reads, step_index=False), orc)
 
 
 def test_match_buffer_regrows():

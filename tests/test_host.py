@@ -446,19 +446,24 @@ def test_group_permutation_keeps_every_result():
 
 
 def _tile_keys(reads, tiling):
-    """numpy statement of sfb_tile_permute's key: the tile holding the first and last node of every alignment."""
+    """numpy statement of sfb_tile_permute's keys: the tile holding the first and last node of every alignment, and (inside
+    a tile) the first node of the group's first alignment with a walk."""
     keys = np.full(reads.n_groups, tiling.n_tiles, np.int64)
+    first = np.zeros(reads.n_groups, np.int64)
     for g in range(reads.n_groups):
         a0, a1 = int(reads.grp_aln_off[2 * g]), int(reads.grp_aln_off[2 * g + 2])
-        tiles = set()
+        tiles, node = set(), None
         for a in range(a0, a1):
             w0, w1 = int(reads.aln_walk_off[a]), int(reads.aln_walk_off[a + 1])
             if w1 > w0:
                 tiles.add(int(tiling.node_tile[reads.walk_node[w0]]))
                 tiles.add(int(tiling.node_tile[reads.walk_node[w1 - 1]]))
+                if node is None:
+                    node = int(reads.walk_node[w0])
         if len(tiles) == 1 and -1 not in tiles:
             keys[g] = tiles.pop()
-    return keys
+            first[g] = node
+    return keys, first
 
 
 def test_tiling_of_the_synthetic_graph():
@@ -511,8 +516,8 @@ def test_tile_staging_and_file_order_restoration():
     host = engine.HostReads(reads, pin=False, wire=True, tiling=tl)
     plain = engine.HostReads(reads, pin=False, wire=True)
     assert plain.order is None and plain.items is None and host.order is not None and host.wire
-    keys = _tile_keys(reads, tl)
-    want = np.argsort(keys, kind="stable")
+    keys, first = _tile_keys(reads, tl)
+    want = np.lexsort((first, keys))                 # by tile, inside a tile by first node, stable
     assert np.array_equal(host.order, want)
     moved, aln_index = reads.permute_groups(host.order, return_index=True)
     assert np.array_equal(host.reads.walk_node, moved.walk_node) and np.array_equal(host.aln_index, aln_index)
