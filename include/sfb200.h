@@ -214,6 +214,9 @@ typedef struct sfb_work {
                                            share}: scratch between the two kernels of sfb_pass2; the number
                                            of matches of a shard (<= A + match_cap) always suffices     */
     int64_t   app_cap;
+    int64_t   p2_begin;           /* sfb_classify lists the deferred groups from this one on in `deferred` (and counts the
+                                           earlier ones in cursor[7]): the groups before it, staged in tile order, are
+                                           resolved by sfb_tile_share, which finds them by their grp_code.  0 without    */
     int64_t   grp_begin, aln_begin; /* first read group / alignment owned by the global-memory kernels (sfb_match,
                                            sfb_classify, sfb_pass1_scatter); the groups before it are in tile order and
                                            belong to sfb_tile_pass1 / sfb_tile_pass2.  0, 0 without tiles             */
@@ -342,6 +345,20 @@ int sfb_pass2_scatter(const sfb_graph* g, const sfb_reads* r, sfb_work* w, sfb_a
  * node loops itself and leaves their deferred ones to sfb_pass2). */
 int sfb_tile_pass1(const sfb_graph* g, const sfb_tiles* t, const sfb_reads* r, sfb_work* w, sfb_accum* acc, void* stream);
 int sfb_tile_pass2(const sfb_graph* g, const sfb_tiles* t, const sfb_reads* r, sfb_work* w, sfb_accum* acc,
+                   const long long* uniq_reads_global, void* stream);
+/* Node-level sums in shared memory on top of the path-set kernels (sfb_match_steps, sfb_classify), for the read groups of
+ * t->items (staged in tile order): the slot accumulators of the item's tile are 96-bit fixed-point bins in shared memory,
+ * flushed once per item -- 32-bit shared-memory atomics instead of 64-bit REDs at the L2, whose rate bounds
+ * sfb_pass1_scatter / sfb_pass2_scatter.  Only tile_desc, items, max_slots and max_paths of `t` are used.
+ *   sfb_tile_scatter1  the node loop of fill_abund_dist (json2csv.py:329-330) for the alignments of the items' groups with
+ *                      aln_assign >= 0 (call sfb_pass1_scatter with w->aln_begin = first alignment after the items for
+ *                      the rest); takes its items through cursor[5]
+ *   sfb_tile_share     pass 2 (json2csv.py:1085-1274) for the items' groups that sfb_classify deferred (w->p2_begin = first
+ *                      group after the items): candidate selection and ratios on the path sets, per-path sums and node
+ *                      loops into the bins; a deferred group that holds tuple lists is appended to w->deferred for
+ *                      sfb_pass2_resolve, which must run afterwards; takes its items through cursor[6] */
+int sfb_tile_scatter1(const sfb_graph* g, const sfb_tiles* t, const sfb_reads* r, sfb_work* w, sfb_accum* acc, void* stream);
+int sfb_tile_share(const sfb_graph* g, const sfb_tiles* t, const sfb_reads* r, sfb_work* w, sfb_accum* acc,
                    const long long* uniq_reads_global, void* stream);
 /* Dynamic shared memory (bytes) the tile kernels need for these tiles; SFB_E_ARG when a tile exceeds the limits. */
 int64_t sfb_tile_smem_bytes(const sfb_tiles* t);

@@ -53,7 +53,7 @@ class SfbWork(C.Structure):
         ("aln_match", C.c_void_p), ("aln_sets", C.c_void_p), ("match_buf", C.c_void_p), ("match_cap", C.c_int64), ("cursor", C.c_void_p),
         ("grp_code", C.c_void_p), ("grp_code2", C.c_void_p), ("aln_assign", C.c_void_p), ("deferred", C.c_void_p),
         ("slow", C.c_void_p), ("app_buf", C.c_void_p), ("app_cap", C.c_int64),
-        ("grp_begin", C.c_int64), ("aln_begin", C.c_int64),
+        ("p2_begin", C.c_int64), ("grp_begin", C.c_int64), ("aln_begin", C.c_int64),
     ]
 
 
@@ -110,7 +110,7 @@ ABI_VERSION = 12
 
 EXPORTS = ("sfb_abi_version", "sfb_version", "sfb_last_error", "sfb_expand_reads", "sfb_match", "sfb_match_steps", "sfb_classify", "sfb_pass1_scatter",
            "sfb_pass2", "sfb_pass2_resolve", "sfb_pass2_scatter", "sfb_accum_collapse", "sfb_path_reduce", "sfb_cluster_strain_counts", "sfb_strain_aggregate",
-           "sfb_tile_pass1", "sfb_tile_pass2", "sfb_tile_smem_bytes", "sfb_tile_permute", "sfb_workspace_bytes",
+           "sfb_tile_pass1", "sfb_tile_pass2", "sfb_tile_scatter1", "sfb_tile_share", "sfb_tile_smem_bytes", "sfb_tile_permute", "sfb_workspace_bytes",
            "sfb_decode_json", "sfb_decode_gamp", "sfb_decoded_error", "sfb_decoded_size", "sfb_decoded_copy", "sfb_decoded_free",
            "sfb_min_strains", "sfb_wire_pack", "sfb_packed_status", "sfb_packed_size", "sfb_packed_copy", "sfb_packed_free",
            "sfb_load_gfa", "sfb_gfa_error", "sfb_gfa_size", "sfb_gfa_copy", "sfb_gfa_free", "sfb_locality_permute")
@@ -167,6 +167,10 @@ def load(build_if_missing=True):
     lib.sfb_tile_pass1.restype = C.c_int
     lib.sfb_tile_pass2.argtypes = [G, TL, R, W, A, vp, vp]
     lib.sfb_tile_pass2.restype = C.c_int
+    lib.sfb_tile_scatter1.argtypes = [G, TL, R, W, A, vp]
+    lib.sfb_tile_scatter1.restype = C.c_int
+    lib.sfb_tile_share.argtypes = [G, TL, R, W, A, vp, vp]
+    lib.sfb_tile_share.restype = C.c_int
     lib.sfb_tile_smem_bytes.argtypes = [TL]
     lib.sfb_tile_smem_bytes.restype = C.c_int64
     lib.sfb_tile_permute.argtypes = [R, vp, i64, C.c_int, vp, vp, R, vp]

@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SOURCES = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "match.cu", "steps.cu", "group.cu", "scatter.cu", "tile.cu", "reduce.cu", "expand.cu", "decode.cpp", "gfa.cpp", "wire.cpp", "unassigned.cpp", "locality.cpp")]
+SOURCES = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "match.cu", "steps.cu", "group.cu", "scatter.cu", "tile.cu", "tilesets.cu", "reduce.cu", "expand.cu", "decode.cpp", "gfa.cpp", "wire.cpp", "unassigned.cpp", "locality.cpp")]
 import glob
 HEADERS = sorted(glob.glob(os.path.join(HERE, "csrc", "*.cuh"))) + sorted(glob.glob(os.path.join(ROOT, "include", "*.h")))
 LIB = os.path.join(HERE, "libsfb200.so")

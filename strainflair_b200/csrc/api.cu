@@ -29,6 +29,8 @@ int launch_pass2_resolve(const Dev&, const long long*, cudaStream_t);
 int launch_pass1_scatter(const sfb_graph*, const sfb_reads*, const sfb_work*, sfb_accum*, cudaStream_t);
 int launch_pass2_scatter(const sfb_graph*, const sfb_reads*, const sfb_work*, sfb_accum*, cudaStream_t);
 int launch_tile_pass(int, const Dev&, const sfb_tiles*, const long long*, cudaStream_t);
+int launch_tile_scatter1(const Dev&, const sfb_tiles*, cudaStream_t);
+int launch_tile_share(const Dev&, const sfb_tiles*, const long long*, cudaStream_t);
 i64 tile_smem_bytes(const sfb_tiles*);
 int launch_expand(const sfb_wire*, const int32_t*, const sfb_reads*, i64*, cudaStream_t);
 int launch_collapse(double*, i64, i64, cudaStream_t);
@@ -79,8 +81,9 @@ static int check_all(const sfb_graph* g, const sfb_reads* r, const sfb_work* w, 
     SFB_TRY(check_graph(g));
     SFB_TRY(check_reads(r));
     SFB_TRY(check_work(w));
-    SFB_REQUIRE(w->grp_begin >= 0 && w->grp_begin <= r->n_groups && w->aln_begin >= 0 && w->aln_begin <= r->n_alns,
-                "grp_begin / aln_begin outside the shard");
+    SFB_REQUIRE(w->grp_begin >= 0 && w->grp_begin <= r->n_groups && w->aln_begin >= 0 && w->aln_begin <= r->n_alns &&
+                    w->p2_begin >= 0 && w->p2_begin <= r->n_groups,
+                "grp_begin / aln_begin / p2_begin outside the shard");
     return check_accum(a);
 }
 
@@ -158,6 +161,21 @@ int sfb_tile_pass2(const sfb_graph* g, const sfb_tiles* t, const sfb_reads* r, s
     SFB_REQUIRE(uniq_reads_global, "uniq_reads_global is null");
     Dev d{*g, *r, *w, *acc};
     return launch_tile_pass(2, d, t, uniq_reads_global, (cudaStream_t)stream);
+}
+
+int sfb_tile_scatter1(const sfb_graph* g, const sfb_tiles* t, const sfb_reads* r, sfb_work* w, sfb_accum* acc, void* stream) {
+    SFB_TRY(check_all(g, r, w, acc));
+    Dev d{*g, *r, *w, *acc};
+    return launch_tile_scatter1(d, t, (cudaStream_t)stream);
+}
+
+int sfb_tile_share(const sfb_graph* g, const sfb_tiles* t, const sfb_reads* r, sfb_work* w, sfb_accum* acc,
+                   const long long* uniq_reads_global, void* stream) {
+    SFB_TRY(check_all(g, r, w, acc));
+    SFB_REQUIRE(uniq_reads_global, "uniq_reads_global is null");
+    SFB_REQUIRE(g->node_mask && w->aln_sets, "sfb_tile_share works on the path sets of sfb_match_steps");
+    Dev d{*g, *r, *w, *acc};
+    return launch_tile_share(d, t, uniq_reads_global, (cudaStream_t)stream);
 }
 
 int64_t sfb_tile_smem_bytes(const sfb_tiles* t) { return tile_smem_bytes(t); }

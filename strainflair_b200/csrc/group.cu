@@ -8,64 +8,9 @@
 #include "common.cuh"
 #include "group_fast.cuh"
 #include "group_logic.cuh"
+#include "group_ops.cuh"
 
 namespace sfb {
-
-// ---- shared pieces --------------------------------------------------------------------------
-__device__ __forceinline__ void hist_add(const Dev& d, BlockCounters& sc, int pid, i64 a) {
-    if (d.g.path_nstrain[pid] != 1) return;                       // json2csv.py:333 / :1246
-    const int s = d.g.path_strain0[pid];
-    SFB_COUNT(sc, SFB_C_ST_HIST, 1);
-    for (int k = 0; k < SFB_N_HIST; ++k) {
-        const int b = d.r.aln_bins[a * SFB_N_HIST + k];
-        if (b >= SFB_N_BINS) { SFB_COUNT(sc, SFB_C_BAD_BIN, 1); continue; }
-        atomicAdd(&d.acc.hist[((size_t)k * d.g.n_strains + s) * SFB_N_BINS + b], 1ull);
-    }
-}
-
-// fill_abund_dist, per-read part (json2csv.py:326-327, 333-339); the node loop (:329-330) is k_pass1_scatter
-__device__ __forceinline__ void assign_unique(const Dev& d, BlockCounters& sc, i64 a, uint32_t code, int pid,
-                                           int seq_len) {
-    d.w.aln_assign[a] = (int32_t)code;
-    atomicAdd((u64*)&d.acc.uniq_reads[pid], 1ull);
-    acc_add(&d.acc.uniq_norm[pid], d.acc.det_stride, (double)seq_len / (double)d.g.path_seq_len[pid]);
-    hist_add(d, sc, pid, a);
-    if (a < d.w.aln_begin) {
-        // a read group of the tile range that sfb_tile_pass1 handed over (more match tuples than its buffers hold):
-        // k_pass1_scatter does not visit it, the node loop (json2csv.py:329-330) runs here
-        const i64 w0 = d.r.aln_walk_off[a];
-        const int L = (int)(d.r.aln_walk_off[a + 1] - w0);
-        double* dst = d.acc.uniq_abund + (code & SFB_SLOT_MASK);
-        for (int i = 0; i < L; ++i) acc_add(dst + i, d.acc.det_stride, record_cov(d.r, w0 + i));
-        SFB_COUNT(sc, SFB_C_ST_P1_RECORDS, L);
-    }
-}
-
-// cluster of the first path through the walk's first node (json2csv.py:875,901,1036); -1 = None, -2 = no path
-__device__ __forceinline__ int first_cluster(const Dev& d, i64 a) {
-    const int n0 = d.r.walk_node[d.r.aln_walk_off[a]];
-    const int o = d.g.occ_off[n0];
-    if (o == d.g.occ_off[n0 + 1]) return -2;
-    return d.g.path_cluster[path_of_slot(d.g, d.g.occ_pair[2 * (size_t)o])];
-}
-__device__ __forceinline__ void book(const Dev& d, BlockCounters& sc, const Mate& mt, int cluster) {
-    if (cluster < 0) { SFB_COUNT(sc, SFB_C_NO_CLUSTER, 1); return; }
-    d.w.aln_assign[mt.a0] = -(cluster + 2);
-}
-
-// json2csv.py:1155-1156 (and :1207-1208, :1265-1266) + the work item for the node loop (:1157-1158)
-__device__ __forceinline__ void emit_app(const Dev& d, App* out, i64 a, uint32_t code, int pid, int seq_len,
-                                      double ratio, int times) {
-    acc_add(&d.acc.mult_reads[pid], d.acc.det_stride, ratio * (double)times);
-    acc_add(&d.acc.mult_norm[pid], d.acc.det_stride,
-            (ratio * (double)seq_len / (double)d.g.path_seq_len[pid]) * (double)times);
-    d.acc.mult_hits[pid] = 1u;           // "touched" flag: same value from every writer, no atomic needed
-    App app;
-    app.aln = (int32_t)a;
-    app.code = code;
-    app.weight = ratio * (double)times;
-    *out = app;
-}
 
 // Effects of the decision logic (group_logic.cuh) for the global-memory kernels: atomics on the accumulators in HBM,
 // pass-2 work items into app_buf (the node loops run in k_pass1_scatter / k_pass2_scatter).
@@ -87,6 +32,15 @@ struct GlobalOps {
 }  // namespace sfb
 #include "group_sets.cuh"
 namespace sfb {
+
+// the work item of a share found on path sets: it names its path, k_pass2_scatter finds the slot (group_sets.cuh)
+struct AppEmit {
+    const Dev& d;
+    App* out;
+    __device__ __forceinline__ void operator()(i64 a, bool rev, int pid, int seq_len, double ratio, int times) {
+        emit_app(d, out++, a, kAppPath | (rev ? SFB_MATCH_REV : 0u) | (uint32_t)pid, pid, seq_len, ratio, times);
+    }
+};
 
 // =============================================================================================
 // classify
@@ -295,9 +249,13 @@ __global__ void __launch_bounds__(128, SFB_CLS_MINBLK) k_classify(Dev d) {
                 d.w.grp_code[g] = (uint8_t)(code[0] | (code[1] << 4));
             }
         }
-        // warp-aggregated appends: deferred groups (pass 2) and groups for the generic kernel
-        const u64 pos = warp_claim(d.w.cursor + 1, defer ? 1u : 0u);
-        if (defer) d.w.deferred[pos] = (int32_t)g;
+        // warp-aggregated appends: deferred groups (pass 2; those before p2_begin are found by sfb_tile_share through
+        // their grp_code and only counted) and groups for the generic kernel
+        const bool list = defer && g >= d.w.p2_begin;
+        const u64 pos = warp_claim(d.w.cursor + 1, list ? 1u : 0u);
+        if (list) d.w.deferred[pos] = (int32_t)g;
+        const unsigned held = __ballot_sync(0xffffffffu, defer && !list);
+        if (held && lane_id() == 0) atomicAdd(d.w.cursor + 7, (u64)__popc(held));
         const u64 spos = warp_claim(d.w.cursor + 3, slow ? 1u : 0u);
         if (slow) d.w.slow[spos] = (int32_t)g;
     }
@@ -327,8 +285,11 @@ __global__ void __launch_bounds__(128) k_classify_slow(Dev d) {
             if (single >= 0) code[single] = classify_single(d, sc, mt[single], defer);
             d.w.grp_code[g] = (uint8_t)(code[0] | (code[1] << 4));
         }
-        const u64 pos = warp_claim(d.w.cursor + 1, defer ? 1u : 0u);
-        if (defer) d.w.deferred[pos] = (int32_t)g;
+        const bool list = defer && g >= d.w.p2_begin;
+        const u64 pos = warp_claim(d.w.cursor + 1, list ? 1u : 0u);
+        if (list) d.w.deferred[pos] = (int32_t)g;
+        const unsigned held = __ballot_sync(0xffffffffu, defer && !list);
+        if (held && lane_id() == 0) atomicAdd(d.w.cursor + 7, (u64)__popc(held));
     }
     __syncthreads();
     block_counters_flush(sc, d.acc.counters);
@@ -521,8 +482,9 @@ __global__ void __launch_bounds__(128, SFB_P2_MINBLK) k_pass2_resolve(Dev d, con
             SFB_COUNT(sc, SFB_C_ST_P2_APPLIED, (int)need);
             if (pos + need <= (u64)d.w.app_cap) {
                 if (SETS) {
-                    App* out = sets_p2_emit(d, sc, mt[0], sm[0], sp, 0, U, apps + pos);
-                    sets_p2_emit(d, sc, mt[1], sm[1], sp, 1, U, out);
+                    AppEmit emit{d, apps + pos};
+                    sets_p2_emit(d, sc, mt[0], sm[0], sp, 0, U, emit);
+                    sets_p2_emit(d, sc, mt[1], sm[1], sp, 1, U, emit);
                 } else {
                     App* out = p2_fast_emit(d, sc, mt[0], A, fp.mode[0], fp.sel[0], fp, 0, U, apps + pos);
                     p2_fast_emit(d, sc, mt[1], B, fp.mode[1], fp.sel[1], fp, 1, U, out);

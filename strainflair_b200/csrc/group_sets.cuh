@@ -9,10 +9,10 @@
 //     paths of a mate            S = OR of its sets          paths with several tuples   dup
 //     common paths               S0 & S1 (same tile)         list.count(p)               number of sets holding p
 //     strains of a mate          OR of path_smask over S     strain-reduced list         count(p) * popcount(smask[p] & common)
-// Included by group.cu after its effect helpers (assign_unique, hist_add, first_cluster, book, emit_app).
 #pragma once
 #include "common.cuh"
 #include "group_logic.cuh"
+#include "group_ops.cuh"
 
 namespace sfb {
 
@@ -229,25 +229,16 @@ __device__ __forceinline__ int sets_p2_need(const SetMate& s, int mode, u64 sel)
     if (mode == kSingle) return s.nt;
     return __popcll(s.m[0] & sel) + __popcll(s.m[1] & sel) + __popcll(s.m[2] & sel) + __popcll(s.m[3] & sel);
 }
-// The work items of one mate (json2csv.py:1155-1158, :1207-1210, :1246-1268).  An item names its path, not its slot
-// (kAppPath): k_pass2_scatter, one thread per item with every lane busy, looks the slot up next to the walk it reads
-// anyway; here a tuple costs its share and the per-path sums, no gather into the index.  One loop over the tuples of the
-// mate's four sets, so that lanes whose tuples sit in different sets (forward for one read, reverse for the next) run
+// The shares of one mate (json2csv.py:1155-1158, :1207-1210, :1246-1268): emit(alignment, reversed, path id, len(sequence),
+// ratio, times) for every tuple that receives one.  A share names its path, not its slot: the global-memory kernels write
+// work items (kAppPath) and k_pass2_scatter, one thread per item with every lane busy, looks the slot up next to the
+// walk it reads anyway; the shared-memory kernel (tilesets.cu) adds it to its bins at once.  One loop over the tuples of
+// the mate's four sets, so that lanes whose tuples sit in different sets (forward for one read, reverse for the next) run
 // together.
 constexpr uint32_t kAppPath = 0x80000000u;      // App.code = kAppPath | SFB_MATCH_REV? | path id
-__device__ __forceinline__ App* sets_p2_emit(const Dev& d, BlockCounters& sc, const Mate& mt, const SetMate& s, const SetPlan& pl,
-                                             int k, const long long* U, App* out) {
-    const int mode = pl.mode[k];
-    if (mode == kNone) return out;
-    const u64 sel = mode == kSingle ? ~0ull : pl.sel[k];
-    long long tot0 = 0, tot1 = 0;
-    if (mode == kSingle) {                       // every alignment separately: its own total and count
-        for (u64 rest = s.m[0]; rest; rest &= rest - 1) tot0 += U[s.p0 + __ffsll((long long)rest) - 1];
-        for (u64 rest = s.m[1]; rest; rest &= rest - 1) tot0 += U[s.p0 + __ffsll((long long)rest) - 1];
-        for (u64 rest = s.m[2]; rest; rest &= rest - 1) tot1 += U[s.p0 + __ffsll((long long)rest) - 1];
-        for (u64 rest = s.m[3]; rest; rest &= rest - 1) tot1 += U[s.p0 + __ffsll((long long)rest) - 1];
-    }
-    const int cnt0 = __popcll(s.m[0]) + __popcll(s.m[1]), cnt1 = __popcll(s.m[2]) + __popcll(s.m[3]);
+// every tuple of the mate whose path lies in `sel`, in the reference's order: f(set index q = 2 * alignment + reversed, path id)
+template <class F>
+__device__ __forceinline__ void sets_for_tuples(const SetMate& s, u64 sel, F&& f) {
     int q = 0;
     u64 cur = s.m[0] & sel;
     for (;;) {
@@ -258,6 +249,26 @@ __device__ __forceinline__ App* sets_p2_emit(const Dev& d, BlockCounters& sc, co
         if (!cur) break;
         const int pid = s.p0 + __ffsll((long long)cur) - 1;
         cur &= cur - 1;
+        f(q, pid);
+    }
+}
+// single-end style: sum of the unique counts over the tuples of each alignment (json2csv.py:1240-1245)
+__device__ __forceinline__ void sets_single_totals(const SetMate& s, const long long* U, long long& tot0, long long& tot1) {
+    tot0 = tot1 = 0;
+    for (u64 rest = s.m[0]; rest; rest &= rest - 1) tot0 += U[s.p0 + __ffsll((long long)rest) - 1];
+    for (u64 rest = s.m[1]; rest; rest &= rest - 1) tot0 += U[s.p0 + __ffsll((long long)rest) - 1];
+    for (u64 rest = s.m[2]; rest; rest &= rest - 1) tot1 += U[s.p0 + __ffsll((long long)rest) - 1];
+    for (u64 rest = s.m[3]; rest; rest &= rest - 1) tot1 += U[s.p0 + __ffsll((long long)rest) - 1];
+}
+template <class Emit>
+__device__ __forceinline__ void sets_p2_emit(const Dev& d, BlockCounters& sc, const Mate& mt, const SetMate& s, const SetPlan& pl,
+                                             int k, const long long* U, Emit& emit) {
+    const int mode = pl.mode[k];
+    if (mode == kNone) return;
+    long long tot0 = 0, tot1 = 0;
+    if (mode == kSingle) sets_single_totals(s, U, tot0, tot1);     // every alignment separately: its own total and count
+    const int cnt0 = __popcll(s.m[0]) + __popcll(s.m[1]), cnt1 = __popcll(s.m[2]) + __popcll(s.m[3]);
+    sets_for_tuples(s, mode == kSingle ? ~0ull : pl.sel[k], [&](int q, int pid) {
         const i64 a = mt.a0 + (q >> 1);
         const long long u = U[pid];
         double wgt;
@@ -271,9 +282,8 @@ __device__ __forceinline__ App* sets_p2_emit(const Dev& d, BlockCounters& sc, co
             hist_add(d, sc, pid, a);                                                   // json2csv.py:1246-1252
             wgt = (q >> 1) ? ratio_of(u, tot1, cnt1) : ratio_of(u, tot0, cnt0);
         }
-        emit_app(d, out++, a, kAppPath | ((q & 1) ? SFB_MATCH_REV : 0u) | (uint32_t)pid, pid, mt.seq_len, wgt, times);
-    }
-    return out;
+        emit(a, (q & 1) != 0, pid, mt.seq_len, wgt, times);
+    });
 }
 
 }  // namespace sfb

@@ -19,6 +19,7 @@
 // carries: integer sums do not depend on the order of the additions), flushed once per work item with 64-bit integer
 // REDs; histogram updates are aggregated per block in a small hash table keyed by (strain, five bins).
 #include "common.cuh"
+#include "bins.cuh"
 #include "group_logic.cuh"
 
 namespace sfb {
@@ -156,37 +157,6 @@ struct TileStats {
     int cand, cmp, tuples, rec, app, deferred;
 };
 
-// ---- fixed-point bins in shared memory ---------------------------------------------------------------------------
-// b[0..2] += (x0, x1, x2) as one 96-bit integer: every limb add is a native 32-bit ATOMS.ADD that returns the old
-// value, a wrap of a limb is carried into the next one by the thread that caused it -- exactly once per wrap, so
-// the 96-bit total is exact whatever the interleaving of the threads.
-__device__ __forceinline__ void fx_smem_add(uint32_t* b, Fx f) {
-    uint32_t carry = 0;
-    if (f.x0) {
-        const uint32_t old = atomicAdd(b, f.x0);
-        carry = (uint32_t)(old + f.x0 < old);
-    }
-    uint32_t t1 = f.x1 + carry;
-    uint32_t c1 = (uint32_t)(t1 < carry);          // x1 = 2^32 - 1 and a carry: t1 wraps to 0
-    if (t1) {
-        const uint32_t old = atomicAdd(b + 1, t1);
-        c1 |= (uint32_t)(old + t1 < old);
-    }
-    const uint32_t t2 = f.x2 + c1;
-    if (t2) atomicAdd(b + 2, t2);
-}
-// one accumulator out to the global planes (or to the fp64 array in the plain mode)
-__device__ __forceinline__ void fx_flush(double* p, i64 det_stride, const uint32_t* b) {
-    const uint32_t x0 = b[0], x1 = b[1], x2 = b[2];
-    if ((x0 | x1 | x2) == 0) return;
-    if (det_stride) {
-        Fx f;
-        f.x0 = x0; f.x1 = x1; f.x2 = x2;
-        fx_red(p, det_stride, f);
-    } else {
-        atomicAdd(p, (double)x2 + (double)x1 * 0x1p-32 + (double)x0 * 0x1p-64);
-    }
-}
 // The node loop: cov[i] * weight into the bins of slot + i.  Records that cover their node (aligned == node length)
 // add the weight itself, split once; with weight 1 that is the integer 1.
 __device__ __forceinline__ void tile_add_records(const TileS& T, const sfb_reads& r, i64 w0, int L, int slot, bool unit,

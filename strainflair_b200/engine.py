@@ -480,7 +480,7 @@ class AbundanceEngine:
     given, ``run`` treats ``reads`` as this rank's shard of the read groups."""
 
     def __init__(self, graph: Graph, device="cuda:0", comm=None, deterministic=True, tiles=True, tile_kernels=None,
-                 step_index=None):
+                 step_index=None, tile_bins=None):
         if not torch.cuda.is_available():
             raise _lib.SfbError("no CUDA device: the abundance engine has no CPU fallback")
         self.lib = _lib.load()
@@ -505,6 +505,11 @@ class AbundanceEngine:
             step_index = os.environ.get("SFB200_STEP_INDEX", "1").strip().lower() not in ("0", "false", "no", "off")
         self.step_index = bool(step_index) and self.dg.steps is not None
         self.gc = self.dg.c_steps if self.step_index else self.dg.c          # the sfb_graph every call of this engine gets
+        # node-level sums of the tile-ordered groups in shared-memory bins (sfb_tile_scatter1 / sfb_tile_share), on top
+        # of the path-set kernels; SFB200_TILE_BINS=0: every sum through the L2 (sfb_pass1_scatter / sfb_pass2_scatter)
+        if tile_bins is None:
+            tile_bins = os.environ.get("SFB200_TILE_BINS", "1").strip().lower() not in ("0", "false", "no", "off")
+        self.tile_bins = bool(tile_bins) and self.step_index and self.tiling is not None and not self.tile_kernels
         self.node_len = _to_dev(graph.node_len, self.device)
         self.comm = comm
         # order-independent sums (96-bit fixed point, the default): bit-identical across runs, shard counts and GPU
@@ -539,19 +544,45 @@ class AbundanceEngine:
         return HostReads(reads, pin=pin, wire=wire, tiling=self.tiling)
 
     def _bind(self, dr, work):
-        """The global-memory kernels own the groups / alignments after the tile range of this shard."""
-        work.c.grp_begin, work.c.aln_begin = dr.grp_begin, dr.aln_begin
+        """With the tile kernels, the global-memory kernels own the groups / alignments after the tile range of this
+        shard; with the shared-memory bins they match and classify everything and only the node-level sums of the tile
+        range go elsewhere (the deferred groups of that range are not listed: sfb_tile_share finds them)."""
+        if self.tile_kernels:
+            work.c.grp_begin, work.c.aln_begin, work.c.p2_begin = dr.grp_begin, dr.aln_begin, 0
+        else:
+            work.c.grp_begin, work.c.aln_begin = 0, 0
+            work.c.p2_begin = dr.grp_begin if (self.tile_bins and dr.tiles_c is not None) else 0
+
+    def tile_scatter1(self, dr, work):
+        """Pass-1 node loops: shared-memory bins for the tile range, the L2 for the rest."""
+        if self.tile_bins and dr.tiles_c is not None:
+            _lib.check(self.lib.sfb_tile_scatter1(C.byref(self.gc), C.byref(dr.tiles_c), C.byref(dr.c), C.byref(work.c),
+                                                  C.byref(self.acc.c), _stream()))
+            self.launches += 1
+            work.c.aln_begin = dr.aln_begin
+            self.pass1_scatter(dr, work)
+            work.c.aln_begin = 0
+        else:
+            self.pass1_scatter(dr, work)
+
+    def tile_share(self, dr, work, uniq_global=None):
+        if not (self.tile_bins and dr.tiles_c is not None):
+            return
+        u = self.acc.uniq_reads if uniq_global is None else uniq_global
+        _lib.check(self.lib.sfb_tile_share(C.byref(self.gc), C.byref(dr.tiles_c), C.byref(dr.c), C.byref(work.c),
+                                           C.byref(self.acc.c), C.c_void_p(u.data_ptr()), _stream()))
+        self.launches += 1
 
     def tile_pass1(self, dr, work):
-        if dr.tiles_c is None:
+        if dr.tiles_c is None or not self.tile_kernels:
             return
         _lib.check(self.lib.sfb_tile_pass1(C.byref(self.gc), C.byref(dr.tiles_c), C.byref(dr.c), C.byref(work.c),
                                            C.byref(self.acc.c), _stream()))
         self.launches += 1
 
     def tile_pass2(self, dr, work, uniq_global=None):
-        if dr.tiles_c is None:
-            return
+        if dr.tiles_c is None or not self.tile_kernels:
+            return self.tile_share(dr, work, uniq_global)
         u = self.acc.uniq_reads if uniq_global is None else uniq_global
         _lib.check(self.lib.sfb_tile_pass2(C.byref(self.gc), C.byref(dr.tiles_c), C.byref(dr.c), C.byref(work.c),
                                            C.byref(self.acc.c), C.c_void_p(u.data_ptr()), _stream()))
@@ -633,9 +664,9 @@ class AbundanceEngine:
         if self.overlap:
             self.side.wait_stream(main)
             with torch.cuda.stream(self.side):
-                self.pass1_scatter(dr, work)
+                self.tile_scatter1(dr, work)
         else:
-            self.pass1_scatter(dr, work)
+            self.tile_scatter1(dr, work)
             mark("pass1_scatter")
         uniq_global = None
         if self.comm is not None:
@@ -690,7 +721,7 @@ class AbundanceEngine:
     def upload(self, host: HostReads):
         """H2D of a staged shard (+ device-side expansion of the transfer layout), reusing the device buffers."""
         dr = DeviceReads(host, self.device, getattr(self, "_arena", None), getattr(self, "_wide", None), self.node_len,
-                         tile_desc=getattr(self.dg, "tile_desc", None) if self.tile_kernels else None,
+                         tile_desc=getattr(self.dg, "tile_desc", None) if (self.tile_kernels or self.tile_bins) else None,
                          tile_edges=getattr(self.dg, "tile_edges", None))
         self._arena, self._wide = dr.arena, dr.wide
         return dr
@@ -743,7 +774,7 @@ class AbundanceEngine:
             slot = job.slots.setdefault(k, {})
             with torch.cuda.stream(self._copy):
                 dr = DeviceReads(host, self.device, slot.get("arena"), slot.get("wide"), self.node_len, expand=False,
-                                 tile_desc=getattr(self.dg, "tile_desc", None) if self.tile_kernels else None,
+                                 tile_desc=getattr(self.dg, "tile_desc", None) if (self.tile_kernels or self.tile_bins) else None,
                          tile_edges=getattr(self.dg, "tile_edges", None))
                 arrived = torch.cuda.Event()
                 arrived.record(self._copy)
@@ -763,7 +794,7 @@ class AbundanceEngine:
             self.classify(dr, work)
             self.side.wait_stream(main)
             with torch.cuda.stream(self.side):
-                self.pass1_scatter(dr, work)
+                self.tile_scatter1(dr, work)
             live.append((dr, work))
         uniq_global = None
         if self.comm is not None:
@@ -924,7 +955,7 @@ class AbundanceEngine:
             res.grp_code = work.t["grp_code"][:dr.n_groups].cpu().numpy()
             res.grp_code2 = work.t["grp_code2"][:dr.n_groups].cpu().numpy()
             res.aln_assign = work.t["aln_assign"][:dr.n_alns].cpu().numpy()
-            if getattr(dr, "tiles_c", None) is None:      # the tile kernels keep the match lists in shared memory
+            if not self.tile_kernels or getattr(dr, "tiles_c", None) is None:      # (the tile kernels keep the match lists in shared memory)
                 res.aln_match = work.t["aln_match"][:dr.n_alns].cpu().numpy().view(np.uint32).reshape(-1, 2)
                 res.match_buf = work.t["match_buf"][:min(work.match_cap, max(0, res.match_fill))].cpu().numpy() \
                     .view(np.uint32).reshape(-1, 2)
@@ -968,10 +999,10 @@ def decode_matches(res, a):
 
 
 def abundance_pass(graph: Graph, reads: Reads, device="cuda:0", deterministic=True, tiles=True, tile_kernels=None,
-                   step_index=None) -> Result:
+                   step_index=None, tile_bins=None) -> Result:
     """One-call public API: decoded alignments + graph in, per-path abundances and counters out."""
     return AbundanceEngine(graph, device, deterministic=deterministic, tiles=tiles, tile_kernels=tile_kernels,
-                           step_index=step_index).run(reads)
+                           step_index=step_index, tile_bins=tile_bins).run(reads)
 
 
 def cluster_strain_counts(graph: Graph, device="cuda:0"):

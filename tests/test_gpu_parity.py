@@ -23,9 +23,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # the kernel families (global-memory kernels on tile-ordered reads = the default, shared-memory tile kernels,
 # global-memory kernels on reads in file order) and the two accumulation modes
 MODES = [dict(), dict(deterministic=False), dict(tile_kernels=True), dict(tile_kernels=True, deterministic=False),
-         dict(tiles=False), dict(tiles=False, deterministic=False), dict(step_index=False)]
+         dict(tiles=False), dict(tiles=False, deterministic=False), dict(step_index=False), dict(tile_bins=False),
+         dict(tile_bins=False, deterministic=False)]
 MODE_IDS = ["default", "default-plain", "tilekernels-det", "tilekernels-plain", "fileorder-det", "fileorder-plain",
-            "occurrence-index-match"]
+            "occurrence-index-match", "pathsets-l2sums-det", "pathsets-l2sums-plain"]
 all_modes = pytest.mark.parametrize("mode", MODES, ids=MODE_IDS)
 
 
