@@ -281,7 +281,7 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-KERNEL_STAGES = ("tile_pass1", "match", "classify", "tile_pass2", "pass2_resolve", "pass2_scatter", "path_reduce")
+KERNEL_STAGES = ("tile_pass1", "match", "classify", "tile_pass2", "tile_share", "pass2_resolve", "pass2_scatter", "path_reduce")
 
 
 def log_mem(tag):
@@ -377,8 +377,11 @@ def roofline_block(args, graph, eng, reads, host, stats, stage_ms, world):
     by = roofline.kernel_bytes(reads.n_groups, reads.n_alns, reads.n_records, graph.n_paths, eng.dg.n_slots,
                                Cr, stats.match_fill, stats.n_deferred, graph.n_strains,
                                tile_groups=host.grp_begin if eng.tile_kernels else 0,
-                               tile_alns=host.aln_begin if eng.tile_kernels else 0)
+                               tile_alns=host.aln_begin if eng.tile_kernels else 0, step_index=eng.step_index,
+                               bins_groups=host.grp_begin if eng.tile_bins else 0,
+                               bins_alns=host.aln_begin if eng.tile_bins else 0, n_nodes=graph.n_nodes)
     kernels = {k: v for k, v in stage_ms.items() if k in KERNEL_STAGES and by.get(k, 0) > 0}
+    r01_work = 19_772_806_676          # SURVEY 8d's closed form on the work the round-1 kernels did for this workload (BENCH_r01)
     top = max(kernels, key=kernels.get)
     peaks = {}
     try:
@@ -407,6 +410,10 @@ def roofline_block(args, graph, eng, reads, host, stats, stage_ms, world):
             "whole_pass_survey_formula": {"achieved": survey, "frac": survey / peak,
                                           "algorithmic_bytes": by["survey_total"],
                                           "bytes_per_record": by["survey_total"] / max(1, reads.n_records)},
+            "whole_pass_survey_formula_r01_work": None if not (args.config == "c3" and args.scale == 1.0) else {
+                "what": "the same closed form with the candidates / compares the occurrence-index kernels of round 1 needed "
+                        "for this workload (19.77 GB, BENCH_r01): comparable across rounds, the step index needs less",
+                "achieved": r01_work / t_all / 1e9, "frac": r01_work / t_all / 1e9 / peak, "algorithmic_bytes": r01_work},
             "whole_pass_streamed_bytes": {"what": "bytes the tile design must move through HBM: every input array once in "
                                                   "pass 1, the deferred groups again in pass 2, outputs, accumulator flushes",
                                           "achieved": stream, "frac": stream / peak, "bytes": by["stream_total"]},
@@ -506,8 +513,9 @@ def run_ours(args):
     parity = None
     if cpu_out is not None:
         parity = check_parity(eng.run(cpu_sample), cpu_out, f"oracle port on the first {cpu_sample.n_groups} read pairs of the workload")
-        parity["tile_kernels"] = check_parity(engine.AbundanceEngine(graph, device, tile_kernels=True).run(cpu_sample), cpu_out,
-                                              "same sample, shared-memory tile kernels")["status"]
+        for key, kw in (("path_sets_sums_at_l2", dict(tile_bins=False)), ("occurrence_index_tuple_lists", dict(step_index=False)),
+                        ("all_in_one_tile_kernels", dict(tile_kernels=True))):
+            parity[key] = check_parity(engine.AbundanceEngine(graph, device, **kw).run(cpu_sample), cpu_out, "same sample, " + key)["status"]
     elif world > 1:
         # rank-count independence: a fixed sample split over the ranks against the same sample on one rank
         sample = synth.make_reads(graph, synth.SEED0 + idx + 555, n_pairs=min(200_000, pairs), read_len=rkw["read_len"])
@@ -526,11 +534,14 @@ def run_ours(args):
                       "checked": f"counters, uniq_reads, histograms exact; per-path fp64 sums and the gene table bit-identical "
                                  f"between 1 and {world} ranks (order-independent accumulation)"}
 
-    # for comparison: the plain accumulation mode (fp64 REDs, not reproducible), reads in file order, the tile kernels
+    # for comparison: the plain accumulation mode (fp64 sums, not reproducible); every node-level sum through the L2
+    # instead of the shared-memory bins; matches from the occurrence index as tuple lists (the kernels of round 1 on
+    # tile-ordered reads); the same on reads in file order; the all-in-one shared-memory tile kernels
     alt = {}
     if not args.no_det:
-        for key, kw in (("plain_fp64_atomics", dict(deterministic=False)), ("file_order", dict(tiles=False)),
-                        ("shared_memory_tile_kernels", dict(tile_kernels=True))):
+        for key, kw in (("plain_fp64_sums", dict(deterministic=False)), ("path_sets_sums_at_l2", dict(tile_bins=False)),
+                        ("occurrence_index_tuple_lists", dict(step_index=False)), ("file_order", dict(tiles=False)),
+                        ("all_in_one_tile_kernels", dict(tile_kernels=True))):
             e2 = engine.AbundanceEngine(graph, device, comm=comm, **kw)
             e2.match_cap_hint, e2.app_cap_hint = eng.match_cap_hint, eng.app_cap_hint
             ms2, st2, _, _, _, _, dr2 = device_pass(e2, reads, max(3, args.steps // 4), 2, world, dist, device)
@@ -625,6 +636,9 @@ def run_ours(args):
             "config": config_dict(args, world),
             "workload_stats": workload_stats(args, world, _R, graph, eng, stats, Cr, host),
             "accumulation": "order-independent (96-bit fixed point): results bit-identical across runs, shard counts and GPU counts",
+            "kernels": ("sfb_match_steps (step index, path sets) -> sfb_classify on sets -> sfb_tile_scatter1 || sfb_tile_share "
+                        "(shared-memory bins) + global-memory kernels for the read groups outside the tile range")
+                       if eng.tile_bins else ("path sets, sums at the L2" if eng.step_index else "occurrence index, tuple lists"),
             "parity": parity,
             "records_per_s": total_records * args.steps / (ms * 1e-3),
             "alignments_per_s": total_alns * args.steps / (ms * 1e-3),
@@ -655,11 +669,12 @@ def workload_stats(args, world, R, graph, eng, stats, Cr, host):
     return {"groups_per_gpu": R.n_groups, "alignments_per_gpu": R.n_alns,
             "records_per_gpu": R.n_records, "paths": graph.n_paths, "nodes": graph.n_nodes,
             "slots": eng.dg.n_slots, "deferred_groups": stats.n_deferred,
-            "group_order": "tile order (host staging: read groups sorted by the graph tile that holds them, the rest last)",
+            "group_order": "tile order (host staging: read groups by the graph tile that holds them, inside a tile by first node, the rest last)",
             "tiles": 0 if eng.tiling is None else eng.tiling.n_tiles,
             "groups_in_tiles": host.grp_begin / max(1, R.n_groups),
             "tile_tuple_cap": None if eng.tiling is None else eng.tiling.tuple_cap,
             "mean_candidates_per_alignment": Cr["ST_CAND"] / max(1, R.n_alns),
+            "mean_steps_per_alignment": Cr["ST_COMPARES"] / max(1, R.n_alns) if eng.step_index else None,
             "mean_matches_per_alignment": Cr["ST_TUPLES"] / max(1, R.n_alns)}
 
 

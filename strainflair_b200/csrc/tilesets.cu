@@ -7,6 +7,8 @@
 //   k_tile_share     pass 2 (json2csv.py:1085-1274) for the deferred groups of the item: candidate selection and ratios on
 //                    the path sets (group_sets.cuh), per-path sums (:1155-1156) and node loops (:1157-1158) into the bins
 // Nothing of the graph is staged: the few index gathers (slot of a path on a node) stay in L1.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "bins.cuh"
 #include "group_sets.cuh"
@@ -310,11 +312,12 @@ static int bins_check(const sfb_tiles* t) {
     return SFB_OK;
 }
 template <class K>
-static unsigned bins_grid(K kern, int block, size_t smem, i64 n_items) {
+static unsigned bins_grid(K kern, int block, size_t smem, i64 n_items, int at_most = 1 << 30) {
     int per_sm = 0, dev = 0, sms = kSMs;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (per_sm > at_most) per_sm = at_most;
     return (unsigned)(n_items < (i64)per_sm * sms ? n_items : (i64)per_sm * sms);
 }
 
@@ -324,7 +327,11 @@ int launch_tile_scatter1(const Dev& d, const sfb_tiles* t, cudaStream_t st) {
     const size_t smem = 12 * (size_t)t->max_slots;
     if (cudaFuncSetAttribute(k_tile_scatter1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return check_launch("k_tile_scatter1 (shared memory size)");
-    k_tile_scatter1<<<bins_grid(k_tile_scatter1, kBinBlock, smem, t->n_items), kBinBlock, smem, st>>>(d, *t);
+    // (measured: capping the blocks per SM so that the kernel could run beside sfb_tile_share on another stream does not
+    // make them overlap -- it then simply runs longer afterwards; SFB200_SCATTER1_BLOCKS repeats the experiment)
+    const char* env = getenv("SFB200_SCATTER1_BLOCKS");
+    const int at_most = env ? atoi(env) : 0;
+    k_tile_scatter1<<<bins_grid(k_tile_scatter1, kBinBlock, smem, t->n_items, at_most > 0 ? at_most : 1 << 30), kBinBlock, smem, st>>>(d, *t);
     return check_launch("k_tile_scatter1");
 }
 int launch_tile_share(const Dev& d, const sfb_tiles* t, const long long* U, cudaStream_t st) {

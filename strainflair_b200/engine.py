@@ -658,9 +658,15 @@ class AbundanceEngine:
         mark("match")
         self.classify(dr, work)
         mark("classify")
-        # the node loop of pass 1 only writes uniq_abund, which nothing reads before the path reduction:
-        # it overlaps with the exchange of uniq_reads and with the pass-2 resolve kernels on a second stream
+        # exchange 1 first: the node loops below fill every SM (persistent grids), a collective enqueued behind them waits
         main = torch.cuda.current_stream()
+        uniq_global = None
+        if self.comm is not None:
+            uniq_global = self.acc.uniq_reads.clone()
+            dist.all_reduce(uniq_global, group=self.comm)          # exact integer sum over shards
+            mark("allreduce_uniq")
+        # the node loop of pass 1 only writes uniq_abund, which nothing reads before the path reduction:
+        # it runs beside pass 2 on a second stream
         if self.overlap:
             self.side.wait_stream(main)
             with torch.cuda.stream(self.side):
@@ -668,14 +674,10 @@ class AbundanceEngine:
         else:
             self.tile_scatter1(dr, work)
             mark("pass1_scatter")
-        uniq_global = None
         if self.comm is not None:
-            uniq_global = self.acc.uniq_reads.clone()
-            dist.all_reduce(uniq_global, group=self.comm)          # exact integer sum over shards
-            mark("allreduce_uniq")
             self._exchange_uniq(main)
         self.tile_pass2(dr, work, uniq_global)
-        mark("tile_pass2")
+        mark("tile_share" if self.tile_bins else "tile_pass2")
         self.pass2_resolve(dr, work, uniq_global)
         mark("pass2_resolve")
         if self.overlap:

@@ -19,7 +19,10 @@ The per-launch work statistics come from the ST_* counters the kernels maintain.
 
 
 def kernel_bytes(n_groups, n_alns, n_records, n_paths, n_slots, C, match_fill, n_deferred, n_strains, tile_groups=0,
-                 tile_alns=0):
+                 tile_alns=0, step_index=False, bins_groups=0, bins_alns=0, n_nodes=0):
+    if step_index:
+        return path_set_bytes(n_groups, n_alns, n_records, n_paths, n_slots, C, match_fill, n_deferred, n_strains,
+                              bins_groups, bins_alns, n_nodes)
     G, A, R = n_groups, n_alns, n_records
     cand, cmp_, tuples = C["ST_CAND"], C["ST_COMPARES"], C["ST_TUPLES"]
     r1, app, r2, hist = C["ST_P1_RECORDS"], C["ST_P2_APPLIED"], C["ST_P2_RECORDS"], C["ST_HIST"]
@@ -64,4 +67,52 @@ def kernel_bytes(n_groups, n_alns, n_records, n_paths, n_slots, C, match_fill, n
     # candidates+matches per alignment: R(8 + 4c + 16m) + A(24 + 8(cand+matches)/A) + 16G + 20T + 8(S+11)P
     out["survey_total"] = (8 * R + 4 * cmp_ + 16 * (r1 + r2)) + (24 * A + 8 * (cand + tuples)) + 16 * G \
         + 20 * n_slots + 8 * (n_strains + 11) * n_paths
+    return out
+
+
+def path_set_bytes(G, A, R, P, n_slots, C, match_fill, n_deferred, n_strains, bins_groups, bins_alns, n_nodes=0):
+    """The same accounting for the path-set kernels (sfb_match_steps, the group kernels on sets, the shared-memory bins):
+    ``steps`` = steps of the walks evaluated (ST_COMPARES), ``bins_groups`` / ``bins_alns`` = read groups / alignments of
+    the tile range whose node-level sums go through shared memory."""
+    steps, tuples = C["ST_COMPARES"], C["ST_TUPLES"]
+    r1, app, r2, hist = C["ST_P1_RECORDS"], C["ST_P2_APPLIED"], C["ST_P2_RECORDS"], C["ST_HIST"]
+    n1 = C["SAME_CP"] + C["DIFF_CP"]
+    fb = bins_alns / A if A else 0.0            # share of the alignments / groups in the tile range
+    fg = bins_groups / G if G else 0.0
+    out = {}
+    # match: walk offsets (8) + the id of every visited node (4; steps + one per walk) + the two path sets (16) and the match
+    #        word (8) per alignment + the step index ONCE (32 bytes per node of the graph: reads in tile order keep the
+    #        records of a tile in L1/L2, the 32 bytes gathered per visited node are reported beside, not as HBM bytes)
+    out["match"] = 8 * A + 4 * (steps + A) + 24 * A + 8 * match_fill + 32 * n_nodes
+    out["match_gathered_index_bytes"] = 32 * (steps + A)
+    # classify: group header (26) + per alignment match word (8), sets (16), aln_assign (4); per unique assignment the slot
+    #           look-up (walk offset 8, node 4, node_mask 8, occ_off 8, occurrence 8) + uniq_reads / uniq_norm RMW (32)
+    #           + path_seq_len (8) + 5 bins; per histogram read 5 RMW (16); deferred list (4)
+    out["classify"] = 26 * G + 28 * A + 8 * match_fill + 81 * n1 + 80 * hist + 4 * (1 - fg) * n_deferred
+    # pass-1 node loops: aln_assign (4) + walk offsets (8) per alignment; per added record the packed word (4); the sums:
+    #   tile range   shared-memory bins, flushed once per work item: two 8-byte RMWs per slot of the tile (32 per slot)
+    #   the rest     an fp64 / two int64 RMWs per record at the L2 (16)
+    out["tile_scatter1"] = fb * (12 * A + 4 * r1) + 32 * n_slots * (1 if fb else 0)
+    out["pass1_scatter"] = (1 - fb) * (12 * A + 20 * r1)
+    # pass 2 in the tile range: grp_code per group (1) + header (26), grp_code2 (1), match words and sets of the deferred
+    #   groups' alignments (~24 each, 2.2 per group); per share: uniq_reads (8), path_seq_len (8), strain word (8), walk
+    #   offsets (16), node (4), node_mask (8), occ_off (8), occurrence (8); per record the packed word (4); flush as above
+    #   (+ 40 per path)
+    d_in = fg * n_deferred
+    out["tile_share"] = fg * G + 27 * d_in + 24 * 2.2 * d_in + fg * (68 * app + 4 * r2) + (32 * n_slots + 40 * P) * (1 if fg else 0)
+    # pass 2 outside it: as before, with 16-byte work items that name their path
+    out["pass2_resolve"] = (1 - fg) * (30 * n_deferred + 96 * app)
+    out["pass2_scatter"] = (1 - fg) * (32 * app + 36 * app + 20 * r2)
+    out["pass2"] = out["tile_share"] + out["pass2_resolve"] + out["pass2_scatter"]
+    out["path_reduce"] = 16 * n_slots + (8 * 8 + 4 * 8 + 8) * P
+    out["tile_pass1"] = out["tile_pass2"] = 0.0
+    out["total"] = sum(v for k, v in out.items() if k not in ("pass2", "match_gathered_index_bytes"))
+    fd = n_deferred / G if G else 0.0
+    inputs = 25 * G + 13 * A + 8 * R
+    out["stream_total"] = inputs + G + 4 * A + fd * inputs + G + fd * G + 2 * (12 + 16) * n_slots + out["path_reduce"]
+    # SURVEY.md section 8d's closed form R(8 + 4c + 16m) + A(24 + 8 (cand + matches)/A) + 16G + 20T + 8(S+11)P with the
+    # realised work of THIS algorithm: c = steps per record (the step index tests no candidate occurrences: cand = 0),
+    # m = node-level additions per record (16 bytes each, wherever the accumulator lives)
+    out["survey_total"] = (8 * R + 4 * steps + 16 * (r1 + r2)) + (24 * A + 8 * tuples) + 16 * G \
+        + 20 * n_slots + 8 * (n_strains + 11) * P
     return out
