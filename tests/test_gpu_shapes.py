@@ -20,7 +20,8 @@ def test_config_shapes_match_oracle(name, pairs):
     graph = synth.make_graph(synth.SEED0 + idx, **gkw)
     reads = synth.make_reads(graph, synth.SEED0 + idx + 1000, n_pairs=pairs, read_len=rkw["read_len"])
     orc = oa.AbundanceOracle(graph.as_dict(), reads.as_dict()).run()
-    eng = engine.AbundanceEngine(graph)                                   # default: global-memory kernels, tile order
+    eng = engine.AbundanceEngine(graph)                   # default: path sets from the step index, shared-memory bins, tile order
+    assert eng.step_index and eng.tile_bins and not eng.dg.steps["steps_partial"]     # every tile of these graphs is simple
     assert eng.tiling is not None and eng.tiling.n_tiles >= 3000          # every cluster is a tile (or shares one)
     host = eng.stage(reads)
     assert host.grp_begin > 0.9 * reads.n_groups                          # ... and holds most read groups
@@ -28,6 +29,9 @@ def test_config_shapes_match_oracle(name, pairs):
     check_against_oracle(graph, reads, res, orc)
     if name == "c4":
         assert res.C["ST_TUPLES"] / reads.n_alns > 8 and res.n_deferred > 0.7 * reads.n_groups
-    # the shared-memory tile kernels, and the global-memory kernels on reads in file order, on the same sample
+    # the other kernel families on the same sample: path sets with every sum at the L2, tuple lists from the occurrence
+    # index, the all-in-one shared-memory tile kernels, and the global-memory kernels on reads in file order
+    check_against_oracle(graph, reads, engine.AbundanceEngine(graph, tile_bins=False).run(host), orc)
+    check_against_oracle(graph, reads, engine.AbundanceEngine(graph, step_index=False).run(host), orc)
     check_against_oracle(graph, reads, engine.AbundanceEngine(graph, tile_kernels=True).run(host), orc)
     check_against_oracle(graph, reads, engine.AbundanceEngine(graph, tiles=False).run(reads), orc)
