@@ -675,7 +675,10 @@ def workload_stats(args, world, R, graph, eng, stats, Cr, host):
             "tile_tuple_cap": None if eng.tiling is None else eng.tiling.tuple_cap,
             "mean_candidates_per_alignment": Cr["ST_CAND"] / max(1, R.n_alns),
             "mean_steps_per_alignment": Cr["ST_COMPARES"] / max(1, R.n_alns) if eng.step_index else None,
-            "mean_matches_per_alignment": Cr["ST_TUPLES"] / max(1, R.n_alns)}
+            "mean_matches_per_alignment": Cr["ST_TUPLES"] / max(1, R.n_alns),
+            "match_buf_pairs": stats.match_fill, "pass2_work_items": stats.app_fill,
+            "pass1_records": Cr["ST_P1_RECORDS"], "pass2_shares": Cr["ST_P2_APPLIED"], "pass2_records": Cr["ST_P2_RECORDS"],
+            "unique_assignments": Cr["SAME_CP"] + Cr["DIFF_CP"], "histogram_reads": Cr["ST_HIST"]}
 
 
 def main():

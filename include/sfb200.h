@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SFB_ABI_VERSION 12
+#define SFB_ABI_VERSION 13
 
 /* ---- status codes ---------------------------------------------------- */
 #define SFB_OK            0
@@ -160,8 +160,8 @@ typedef struct sfb_reads {
  *   offsets            as 1-byte counts (prefix sums on the device)
  *   read lengths       one common value + the mates that differ (or 16 bits per mate)
  *   histogram bins     one byte per alignment: index into a dictionary of the shard's frequent 5-tuples
- *   node ids           per alignment the first node; per record the step to the next id as a signed byte (walks
- *                      follow the graph, whose ids are locally consecutive)
+ *   node ids           per alignment the first node; per record the step from the previous node id of the walk in FOUR
+ *                      bits (walks follow the graph, whose ids are locally consecutive: a step is +1 or +2 almost always)
  *   aligned bases      one byte for the first and for the last record of a walk; the records in between cover
  *                      their node completely (aligned bases = node length, gathered on the device)
  *   anything else      explicit fp64 coverage of the record (exc_idx / exc_cov): any record may be shipped that way
@@ -183,8 +183,9 @@ typedef struct sfb_wire {
     const int32_t*  aln_node0;    /* [A]  first node of the walk                      */
     const uint8_t*  aln_al_first; /* [A]  aligned bases of the walk's first record, 255 = explicit coverage */
     const uint8_t*  aln_al_last;  /* [A]  ... of its last record (walks of two records or more)            */
-    const int8_t*   walk_step;    /* [R]  node id minus the previous node id of the walk (unused for a walk's first
-                                          record); -128: the id is wide_node[k] where wide_idx[k] is this record  */
+    const uint8_t*  walk_step;    /* [(R+1)/2] one nibble per record, record q in bits 4*(q&1).. of byte q/2: node id minus
+                                          the previous node id of the walk, + 8 (steps of -7 .. 7; unused for a walk's first
+                                          record); 0: the id is wide_node[k] where wide_idx[k] is this record     */
     const int64_t*  exc_idx;      /* [E]  record index of explicit coverage k, ascending */
     const double*   exc_cov;      /* [E]  */
     const int64_t*  wide_idx;     /* [W]  record indices of the wide steps, ascending */

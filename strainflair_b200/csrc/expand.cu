@@ -144,10 +144,11 @@ __global__ void __launch_bounds__(kWalkTile) k_expand_walks(sfb_wire w, const i6
                 int st[8];
                 int32_t nd[8], nl[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) st[k] = (c + k < hi && c + k > lo) ? (int)w.walk_step[c + k] : 0;
+                for (int k = 0; k < 8; ++k)           // the record's nibble: step + 8, 0 = listed
+                    st[k] = (c + k < hi && c + k > lo) ? (int)((w.walk_step[(c + k) >> 1] >> (4 * ((c + k) & 1))) & 15u) : 8;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    if (c + k < hi && c + k > lo) node = st[k] != -128 ? node + st[k] : wide_node_of(w, c + k);
+                    if (c + k < hi && c + k > lo) node = st[k] ? node + st[k] - 8 : wide_node_of(w, c + k);
                     nd[k] = node;
                 }
 #pragma unroll

@@ -198,9 +198,13 @@ __global__ void __launch_bounds__(128, SFB_CLS_MINBLK) k_classify(Dev d) {
     const i64 n_round = d.w.grp_begin + ((d.r.n_groups - d.w.grp_begin + 127) & ~(i64)127);
     for (i64 g = d.w.grp_begin + (i64)blockIdx.x * blockDim.x + threadIdx.x; g < n_round; g += (i64)gridDim.x * blockDim.x) {
         bool defer = false, slow = false;
+        Mate mt[2];
+        SetMate sm[2];
+        int want[2] = {-1, -1};                  // SETS: the path bit each mate is assigned to (sets_assign_pair below)
+        mt[0].seq_len = mt[1].seq_len = 0;
+        sm[0].p0 = sm[1].p0 = -1;
         if (g < d.r.n_groups) {
             const int nm = d.r.grp_nmates[g];
-            Mate mt[2];
             mate_load(d.r, g, 0, mt[0]);
             mate_load(d.r, g, 1, mt[1]);
             for (int k = 0; k < 2; ++k)
@@ -221,7 +225,6 @@ __global__ void __launch_bounds__(128, SFB_CLS_MINBLK) k_classify(Dev d) {
                     single = 1 - gone;
                 } else if (SETS) {
                     // path sets of the step index: any number of candidate paths in registers
-                    SetMate sm[2];
                     if (d.g.mask_words == 1 && sets_load(d.w, mt[0], sm[0]) && sets_load(d.w, mt[1], sm[1])) {
                         if (sm[0].nt == 0 && sm[1].nt == 0) {
                             GlobalOps ops{nullptr, nullptr};
@@ -231,7 +234,7 @@ __global__ void __launch_bounds__(128, SFB_CLS_MINBLK) k_classify(Dev d) {
                         } else if (sm[1].nt == 0) {
                             single = classify_one_without_path(d, sc, mt, 1, code);
                         } else {
-                            sets_classify_pair(d, sc, mt, sm, code, defer);
+                            sets_classify_pair(d, sc, mt, sm, code, defer, want);
                         }
                     } else {
                         slow = true;
@@ -249,6 +252,8 @@ __global__ void __launch_bounds__(128, SFB_CLS_MINBLK) k_classify(Dev d) {
                 d.w.grp_code[g] = (uint8_t)(code[0] | (code[1] << 4));
             }
         }
+        // the unique assignments the tree noted, both mates side by side, the whole warp together
+        if (SETS && __any_sync(0xffffffffu, want[0] >= 0 || want[1] >= 0)) sets_assign_pair(d, sc, mt, sm, want);
         // warp-aggregated appends: deferred groups (pass 2; those before p2_begin are found by sfb_tile_share through
         // their grp_code and only counted) and groups for the generic kernel
         const bool list = defer && g >= d.w.p2_begin;

@@ -14,6 +14,10 @@
 #include "group_logic.cuh"
 #include "group_ops.cuh"
 
+#ifndef SFB_CLS_AGG
+#define SFB_CLS_AGG 1
+#endif
+
 namespace sfb {
 
 struct SetMate {
@@ -55,14 +59,87 @@ __device__ __forceinline__ int sets_node(const sfb_reads& r, const Mate& mt, int
     const i64 a = mt.a0 + (q >> 1);
     return (q & 1) ? r.walk_node[r.aln_walk_off[a + 1] - 1] : r.walk_node[r.aln_walk_off[a]];
 }
-// fill_abund_dist for the first tuple of the mate on path bit p
-__device__ __forceinline__ void sets_assign(const Dev& d, BlockCounters& sc, const Mate& mt, const SetMate& s, int p) {
-    int q = 3;
+// fill_abund_dist (json2csv.py:321-339) for the first tuple of each mate on its path bit want[k] (-1: nothing to assign).
+// The decision tree only NOTES what it assigns; the two assignments of a pair then run here side by side, level by level --
+// walk offset -> node that carries the tuple -> node_mask / occ_off -> occurrence (= slot) are four dependent gathers, and
+// inside the branches of the tree they ran one mate after the other, in whatever lanes had taken that branch.
+__device__ __forceinline__ void sets_assign_pair(const Dev& d, BlockCounters& sc, const Mate* mt, const SetMate* sm, const int* want) {
+    i64 a[2], at[2];
+    int q[2], node[2], oo[2], plen[2], nstr[2];
+    u64 nm[2];
 #pragma unroll
-    for (int k = 2; k >= 0; --k)
-        if ((s.m[k] >> p) & 1ull) q = k;
-    const uint2 t = sets_tuple(d.g, sets_node(d.r, mt, q), s.p0, 1ull << p, (q & 1) != 0);
-    assign_unique(d, sc, mt.a0 + (q >> 1), t.x, (int)t.y, mt.seq_len);
+    for (int k = 0; k < 2; ++k) {
+        q[k] = 3;
+        a[k] = at[k] = 0;
+        if (want[k] < 0) continue;
+#pragma unroll
+        for (int j = 2; j >= 0; --j)
+            if ((sm[k].m[j] >> want[k]) & 1ull) q[k] = j;
+        a[k] = mt[k].a0 + (q[k] >> 1);
+        at[k] = d.r.aln_walk_off[a[k] + (q[k] & 1)] - (q[k] & 1);      // the walk's first record, its last for a reverse match
+        plen[k] = d.g.path_seq_len[sm[k].p0 + want[k]];
+        nstr[k] = d.g.path_nstrain[sm[k].p0 + want[k]];
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) node[k] = want[k] >= 0 ? d.r.walk_node[at[k]] : 0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        nm[k] = 0;
+        oo[k] = 0;
+        if (want[k] >= 0) {
+            nm[k] = d.g.node_mask[node[k]];
+            oo[k] = d.g.occ_off[node[k]];
+        }
+    }
+#if SFB_CLS_AGG
+    // uniq_reads / uniq_norm (json2csv.py:326-327): reads in tile order put neighbouring lanes on the same few paths, so
+    // the lanes of the warp that add the same term to the same path send ONE update -- the integer term times their
+    // number (exact: same sums as one update per lane); called by the whole warp
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const bool on = want[k] >= 0;
+        const int pid = on ? sm[k].p0 + want[k] : -1 - lane_id();
+        const unsigned peers = __match_any_sync(0xffffffffu, ((u64)(uint32_t)pid << 32) | (uint32_t)mt[k].seq_len);
+        if (on && lane_id() == __ffs((int)peers) - 1) {
+            const u64 cnt = (u64)__popc(peers);
+            atomicAdd((u64*)&d.acc.uniq_reads[pid], cnt);
+            const double v = (double)mt[k].seq_len / (double)plen[k];
+            double* dst = &d.acc.uniq_norm[pid];
+            if (d.acc.det_stride == 0) {
+                atomicAdd(dst, v * (double)cnt);
+            } else {
+                const Fx f = fx_split(v);
+                const u64 low = (u64)f.x0 * cnt;
+                atomicAdd(reinterpret_cast<u64*>(dst), ((((u64)f.x2 << 32) | f.x1) * cnt) + (low >> 32));
+                if ((uint32_t)low) atomicAdd(reinterpret_cast<u64*>(dst + d.acc.det_stride), (u64)(uint32_t)low);
+            }
+        }
+    }
+#endif
+    int slot[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+        slot[k] = want[k] >= 0 ? d.g.occ_pair[2 * (size_t)(oo[k] + __popcll(nm[k] & ((1ull << want[k]) - 1)))] : 0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        if (want[k] < 0) continue;
+        const int pid = sm[k].p0 + want[k];
+        const uint32_t code = (uint32_t)slot[k] | ((q[k] & 1) ? SFB_MATCH_REV : 0u);
+        d.w.aln_assign[a[k]] = (int32_t)code;
+#if !SFB_CLS_AGG
+        atomicAdd((u64*)&d.acc.uniq_reads[pid], 1ull);
+        acc_add(&d.acc.uniq_norm[pid], d.acc.det_stride, (double)mt[k].seq_len / (double)plen[k]);
+#endif
+        if (nstr[k] == 1) hist_add(d, sc, pid, a[k]);
+        if (a[k] < d.w.aln_begin) {
+            // a read group of the tile range that sfb_tile_pass1 handed over: its node loop runs here (see assign_unique)
+            const i64 w0 = d.r.aln_walk_off[a[k]];
+            const int L = (int)(d.r.aln_walk_off[a[k] + 1] - w0);
+            double* dst = d.acc.uniq_abund + (code & SFB_SLOT_MASK);
+            for (int i = 0; i < L; ++i) acc_add(dst + i, d.acc.det_stride, record_cov(d.r, w0 + i));
+            SFB_COUNT(sc, SFB_C_ST_P1_RECORDS, L);
+        }
+    }
 }
 // strains of the mate's candidate paths (mask_words == 1)
 __device__ __forceinline__ u64 sets_strains(const sfb_graph& g, const SetMate& s) {
@@ -81,8 +158,9 @@ __device__ __forceinline__ int sets_reduced(const sfb_graph& g, const SetMate& s
 }
 
 // both mates have colored paths (json2csv.py:918-1000); same decisions as classify_pair (group_logic.cuh)
+// (`want`: the path bit each mate is assigned to, for sets_assign_pair; -1 = none)
 __device__ __forceinline__ void sets_classify_pair(const Dev& d, BlockCounters& sc, const Mate* mt, const SetMate* sm, int* code,
-                                                   bool& defer) {
+                                                   bool& defer, int* want) {
     const u64 inter = sm[0].p0 == sm[1].p0 ? sm[0].S & sm[1].S : 0ull;
     const int n_inter = __popcll(inter);
     if (n_inter > 1) {
@@ -100,7 +178,7 @@ __device__ __forceinline__ void sets_classify_pair(const Dev& d, BlockCounters& 
                 code[k] = SFB_MULTI_ALIGN;
                 continue;
             }
-            sets_assign(d, sc, mt[k], sm[k], p);
+            want[k] = p;
             SFB_COUNT(sc, SFB_C_ASSIGNED_U, 1);
             SFB_COUNT(sc, SFB_C_SAME_CP, 1);
             if (sm[k].nt > 1) SFB_COUNT(sc, SFB_C_AMBIG_CP_RESOLVED, 1);
@@ -129,7 +207,7 @@ __device__ __forceinline__ void sets_classify_pair(const Dev& d, BlockCounters& 
             const int p = __ffsll((long long)rest) - 1;
             if ((d.g.path_smask[sm[k].p0 + p] & common) == 0) continue;
             if (sets_count(sm[k], p) == 1) {
-                sets_assign(d, sc, mt[k], sm[k], p);
+                want[k] = p;
                 SFB_COUNT(sc, SFB_C_ASSIGNED_U, 1);
                 SFB_COUNT(sc, SFB_C_DIFF_CP, 1);
                 code[k] = SFB_ASSIGN_DIFF;

@@ -49,8 +49,15 @@ __device__ __forceinline__ u64 step_mask(const sfb_graph& g, const StepRec& rc, 
 }
 
 constexpr int kStepBlock = 256;
+#ifndef SFB_STEPS_BATCH
+#define SFB_STEPS_BATCH 2
+#endif
+#ifndef SFB_STEPS_MINBLK
+#define SFB_STEPS_MINBLK 5
+#endif
+constexpr int kStepBatch = SFB_STEPS_BATCH ? SFB_STEPS_BATCH : 1;
 
-__global__ void __launch_bounds__(kStepBlock, 5) k_match_steps(sfb_graph g, sfb_reads r, sfb_work w, long long* counters) {
+__global__ void __launch_bounds__(kStepBlock, SFB_STEPS_MINBLK) k_match_steps(sfb_graph g, sfb_reads r, sfb_work w, long long* counters) {
     __shared__ BlockCounters sc;
     block_counters_zero(sc);
     __syncthreads();
@@ -84,6 +91,29 @@ __global__ void __launch_bounds__(kStepBlock, 5) k_match_steps(sfb_graph g, sfb_
                 } else {
                     f = rv = ~0ull;
                     int prev = first;
+#if SFB_STEPS_BATCH
+                    // kStepBatch nodes of the walk, then their records, in flight together: the walk costs two memory
+                    // latencies per batch instead of two per node (a step is only counted while a set is alive, as
+                    // the node-by-node loop with its early exit counts them)
+                    for (int k0 = 1; k0 < L && (f | rv); k0 += kStepBatch) {
+                        int n[kStepBatch];
+                        StepRec rn[kStepBatch];
+#pragma unroll
+                        for (int j = 0; j < kStepBatch; ++j) n[j] = k0 + j < L ? r.walk_node[w0 + k0 + j] : -1;
+#pragma unroll
+                        for (int j = 0; j < kStepBatch; ++j)
+                            if (n[j] >= 0) rn[j] = step_load(g, n[j]);
+#pragma unroll
+                        for (int j = 0; j < kStepBatch; ++j)
+                            if (n[j] >= 0 && (f | rv)) {
+                                f &= step_mask(g, rec, prev, n[j]);
+                                rv &= step_mask(g, rn[j], n[j], prev);
+                                st_steps += 1;
+                                rec = rn[j];
+                                prev = n[j];
+                            }
+                    }
+#else
                     for (int k = 1; k < L; ++k) {
                         const int n = r.walk_node[w0 + k];
                         const StepRec rn = step_load(g, n);
@@ -94,6 +124,7 @@ __global__ void __launch_bounds__(kStepBlock, 5) k_match_steps(sfb_graph g, sfb_
                         rec = rn;
                         prev = n;
                     }
+#endif
                 }
             }
             if (!fb) {

@@ -75,7 +75,10 @@ __global__ void __launch_bounds__(kBinBlock) k_tile_scatter1(Dev d, sfb_tiles t)
 constexpr int kShareBlock = SFB_SHARE_BLOCK;
 constexpr int kShareWarps = kShareBlock / 32;
 constexpr int kQueue = 64;                 // deferred groups waiting per warp (a scan adds at most 32)
-constexpr int kShares = 256;               // entries of a warp's share list
+#ifndef SFB_SHARE_LIST
+#define SFB_SHARE_LIST 256
+#endif
+constexpr int kShares = SFB_SHARE_LIST;    // entries of a warp's share list
 constexpr int kDirect = kShares;           // a group with more shares than this adds them itself (no list)
 constexpr uint32_t kShareHist = 0x80000000u;
 

@@ -163,8 +163,9 @@ void pack(sfb_packed& P, const sfb_reads& r, int T) {
 
     // ---- per alignment and per record -------------------------------------------------------------
     if (!P.arr[W_ALN_LEN].alloc((size_t)A) || !P.arr[W_ALN_CODE].alloc((size_t)A) || !P.arr[W_ALN_NODE0].alloc((size_t)A * 4) ||
-        !P.arr[W_ALN_AL_FIRST].alloc((size_t)A) || !P.arr[W_ALN_AL_LAST].alloc((size_t)A) || !P.arr[W_WALK_STEP].alloc((size_t)R))
+        !P.arr[W_ALN_AL_FIRST].alloc((size_t)A) || !P.arr[W_ALN_AL_LAST].alloc((size_t)A) || !P.arr[W_WALK_STEP].alloc(((size_t)R + 1) / 2))
         return oom();
+    if (R) memset(P.arr[W_WALK_STEP].p, 0, ((size_t)R + 1) / 2);        // nibbles are OR-ed in
     const size_t a_chunks = ((size_t)A + kGrain - 1) / kGrain;
     std::vector<std::vector<int64_t>> bins_idx(a_chunks), exc_idx(a_chunks), wide_idx(a_chunks);
     std::vector<std::vector<uint8_t>> bins_val(a_chunks);
@@ -176,7 +177,16 @@ void pack(sfb_packed& P, const sfb_reads& r, int T) {
         int32_t* node0 = P.arr[W_ALN_NODE0].as<int32_t>();
         uint8_t* al_first = P.arr[W_ALN_AL_FIRST].as<uint8_t>();
         uint8_t* al_last = P.arr[W_ALN_AL_LAST].as<uint8_t>();
-        int8_t* step = P.arr[W_WALK_STEP].as<int8_t>();
+        uint8_t* step = P.arr[W_WALK_STEP].as<uint8_t>();
+        // one nibble per record: the two bytes at the ends of this chunk's record range may be shared with the
+        // neighbouring chunks (another thread), so nibbles landing there are OR-ed in atomically
+        const int64_t first_byte = r.aln_walk_off[lo] >> 1, last_byte = (r.aln_walk_off[hi] - 1) >> 1;
+        auto put = [&](int64_t q, unsigned nib) {
+            const int64_t b = q >> 1;
+            const uint8_t v = (uint8_t)(nib << (4 * (q & 1)));
+            if (b == first_byte || b == last_byte) __atomic_fetch_or(step + b, v, __ATOMIC_RELAXED);
+            else step[b] |= v;
+        };
         for (size_t a = lo; a < hi; ++a) {
             const int64_t r0 = r.aln_walk_off[a], r1 = r.aln_walk_off[a + 1];
             if (r1 - r0 < 0 || r1 - r0 > 255) { fits = false; return; }
@@ -194,16 +204,13 @@ void pack(sfb_packed& P, const sfb_reads& r, int T) {
             al_first[a] = al_last[a] = 0;
             for (int64_t q = r0; q < r1; ++q) {
                 // node id: the step from the previous record of the walk
-                if (q == r0) {
-                    step[q] = 0;
-                } else {
+                if (q > r0) {
                     const int64_t d = (int64_t)r.walk_node[q] - (int64_t)r.walk_node[q - 1];
-                    if (d < -127 || d > 127) {
-                        step[q] = -128;
+                    if (d < -7 || d > 7) {                      // nibble 0: listed
                         wide_idx[c].push_back(q);
                         wide_node[c].push_back(r.walk_node[q]);
                     } else {
-                        step[q] = (int8_t)d;
+                        put(q, (unsigned)(d + 8));
                     }
                 }
                 // aligned bases: a byte at the two ends of the walk, the node length in between, else explicit

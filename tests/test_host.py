@@ -208,7 +208,8 @@ def _expand_on_host(w, common, n_nodes_len):
         cur = int(w["aln_node0"][a])
         for r in range(off[a], off[a + 1]):
             if r > off[a]:
-                cur = wide[r] if w["walk_step"][r] == -128 else cur + int(w["walk_step"][r])
+                nib = (int(w["walk_step"][r >> 1]) >> (4 * (r & 1))) & 15          # step + 8, 0 = listed
+                cur = wide[r] if nib == 0 else cur + nib - 8
             nl = int(n_nodes_len[cur])
             al = int(w["aln_al_first"][a]) if r == off[a] else int(w["aln_al_last"][a]) if r == off[a + 1] - 1 else nl & 0xFFFF
             node[r], word[r] = cur, np.int64(al | (nl << 16)).astype(np.int32)
