@@ -368,6 +368,11 @@ int64_t sfb_tile_smem_bytes(const sfb_tiles* t);
  * accumulators at x. */
 int sfb_accum_collapse(double* x, int64_t n, int64_t det_stride, void* stream);
 
+/* A slot array (uniq_abund / mult_abund: one sentinel slot after every path) without its sentinels, path after path:
+ * plain[n_slots - n_paths] = the per-node sums Path.unique_mapped_abundances / multiple_mapped_abundances hold in the
+ * reference (json2csv.py:107-108), for the read-back of the whole arrays. */
+int sfb_drop_sentinels(const sfb_graph* g, const double* slots, double* plain, void* stream);
+
 /* Pangenome.print_gene_table's per-path reductions (json2csv.py:440-469) for paths
  * [p_begin, p_end): table[(p-p_begin)*8 + k], k = 0 nb_uniq_mapped_normalized,
  * 1 nb_multimapped, 2 nb_multimapped_normalized, 3 mean_abund_uniq, 4 mean_abund_uniq_nz,

@@ -113,7 +113,7 @@ EXPORTS = ("sfb_abi_version", "sfb_version", "sfb_last_error", "sfb_expand_reads
            "sfb_tile_pass1", "sfb_tile_pass2", "sfb_tile_scatter1", "sfb_tile_share", "sfb_tile_smem_bytes", "sfb_tile_permute", "sfb_workspace_bytes",
            "sfb_decode_json", "sfb_decode_gamp", "sfb_decoded_error", "sfb_decoded_size", "sfb_decoded_copy", "sfb_decoded_free",
            "sfb_min_strains", "sfb_wire_pack", "sfb_packed_status", "sfb_packed_size", "sfb_packed_copy", "sfb_packed_free",
-           "sfb_load_gfa", "sfb_gfa_error", "sfb_gfa_size", "sfb_gfa_copy", "sfb_gfa_free", "sfb_locality_permute")
+           "sfb_load_gfa", "sfb_gfa_error", "sfb_gfa_size", "sfb_gfa_copy", "sfb_gfa_free", "sfb_locality_permute", "sfb_drop_sentinels")
 
 
 class SfbError(RuntimeError):
@@ -158,6 +158,8 @@ def load(build_if_missing=True):
     lib.sfb_pass2_scatter.argtypes = [G, R, W, A, vp]
     lib.sfb_accum_collapse.argtypes = [vp, i64, i64, vp]
     lib.sfb_path_reduce.argtypes = [G, A, i64, i64, vp, vp]
+    lib.sfb_drop_sentinels.argtypes = [G, vp, vp, vp]
+    lib.sfb_drop_sentinels.restype = C.c_int
     lib.sfb_cluster_strain_counts.argtypes = [i64, i64, vp, vp, vp, vp, vp, vp, vp]
     lib.sfb_strain_aggregate.argtypes = [i64, i64, vp, vp, vp, vp, vp, vp, f64, vp, vp, vp, vp, vp]
     for name in EXPORTS[3:15]:

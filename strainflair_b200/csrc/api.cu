@@ -34,6 +34,7 @@ int launch_tile_share(const Dev&, const sfb_tiles*, const long long*, cudaStream
 i64 tile_smem_bytes(const sfb_tiles*);
 int launch_expand(const sfb_wire*, const int32_t*, const sfb_reads*, i64*, cudaStream_t);
 int launch_collapse(double*, i64, i64, cudaStream_t);
+int launch_drop_sentinels(const sfb_graph*, const double*, double*, cudaStream_t);
 int launch_path_reduce(const sfb_graph*, const sfb_accum*, i64, i64, double*, cudaStream_t);
 int launch_cluster_counts(i64, i64, const int32_t*, const int32_t*, const int32_t*, const int32_t*, const int32_t*,
                           long long*, cudaStream_t);
@@ -211,6 +212,12 @@ int sfb_accum_collapse(double* x, int64_t n, int64_t det_stride, void* stream) {
     SFB_REQUIRE(n >= 0 && det_stride >= n, "bad sizes");
     SFB_REQUIRE(x || n == 0, "null array");
     return launch_collapse(x, n, det_stride, (cudaStream_t)stream);
+}
+
+int sfb_drop_sentinels(const sfb_graph* g, const double* slots, double* plain, void* stream) {
+    SFB_TRY(check_graph(g));
+    SFB_REQUIRE((slots && plain) || g->n_slots == 0, "null array");
+    return launch_drop_sentinels(g, slots, plain, (cudaStream_t)stream);
 }
 
 int sfb_path_reduce(const sfb_graph* g, const sfb_accum* acc, int64_t p_begin, int64_t p_end, double* table,

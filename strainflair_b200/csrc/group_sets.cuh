@@ -130,7 +130,7 @@ __device__ __forceinline__ void sets_assign_pair(const Dev& d, BlockCounters& sc
         atomicAdd((u64*)&d.acc.uniq_reads[pid], 1ull);
         acc_add(&d.acc.uniq_norm[pid], d.acc.det_stride, (double)mt[k].seq_len / (double)plen[k]);
 #endif
-        if (nstr[k] == 1) hist_add(d, sc, pid, a[k]);
+        if (nstr[k] == 1) hist_add(d, sc, pid, a[k]);      // (aggregating these too -- ten __match_any_sync per pass of the warp -- is slower: 2.49 ms)
         if (a[k] < d.w.aln_begin) {
             // a read group of the tile range that sfb_tile_pass1 handed over: its node loop runs here (see assign_unique)
             const i64 w0 = d.r.aln_walk_off[a[k]];

@@ -57,6 +57,20 @@ __global__ void k_collapse(double* x, i64 n, i64 stride) {
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
         x[i] = (double)reinterpret_cast<const u64*>(x)[i] * 0x1p-32 + (double)reinterpret_cast<const u64*>(x)[i + stride] * 0x1p-64;
 }
+// Per-node sums of every path without the sentinel slots, path after path: what Path.unique_mapped_abundances /
+// multiple_mapped_abundances hold in the reference (json2csv.py:107-108).  One thread per slot; the slot's path comes
+// from the 64-slot block table, its plain index is the slot minus the sentinels before it (one per earlier path).
+__global__ void k_drop_sentinels(sfb_graph g, const double* __restrict__ src, double* __restrict__ dst) {
+    for (i64 s = (i64)blockIdx.x * blockDim.x + threadIdx.x; s < g.n_slots; s += (i64)gridDim.x * blockDim.x) {
+        const int p = path_of_slot(g, (int)s);
+        if (s != (i64)g.path_off[p + 1] - 1) dst[s - p] = src[s];
+    }
+}
+int launch_drop_sentinels(const sfb_graph* g, const double* src, double* dst, cudaStream_t st) {
+    if (g->n_slots == 0) return SFB_OK;
+    k_drop_sentinels<<<kSMs * 8, 256, 0, st>>>(*g, src, dst);
+    return check_launch("k_drop_sentinels");
+}
 int launch_collapse(double* x, i64 n, i64 stride, cudaStream_t st) {
     if (n == 0) return SFB_OK;
     k_collapse<<<kSMs * 8, 256, 0, st>>>(x, n, stride);

@@ -70,15 +70,17 @@ __global__ void __launch_bounds__(kBinBlock) k_tile_scatter1(Dev d, sfb_tiles t)
 //           of the warp's share list (alignment, path, orientation, ratio, times, len(sequence))
 //   add     32 listed shares, lane = share: per-path sums, slot of the path on the walk's first / last node, node loop
 #ifndef SFB_SHARE_BLOCK
-#define SFB_SHARE_BLOCK 128                 /* few warps per block: a work item ends with a barrier and a partial round per warp */
+#define SFB_SHARE_BLOCK 256                 /* measured on C3 (profiles/README.md r02r-r02t): 8 warps share one set of bins, 4 blocks
+                                               per SM = 32 warps at 64 registers (some spills) beat 20-24 warps at 80-96 */
 #endif
 constexpr int kShareBlock = SFB_SHARE_BLOCK;
 constexpr int kShareWarps = kShareBlock / 32;
 constexpr int kQueue = 64;                 // deferred groups waiting per warp (a scan adds at most 32)
 #ifndef SFB_SHARE_LIST
-#define SFB_SHARE_LIST 256
+#define SFB_SHARE_LIST 160
 #endif
-constexpr int kShares = SFB_SHARE_LIST;    // entries of a warp's share list
+constexpr int kShares = SFB_SHARE_LIST;    // entries of a warp's share list (a round of 32 groups lists ~160 shares on C3; 256
+                                           // entries cost a block per SM, 128 / 96 are slower: 3.56 / 3.63 against 3.49 ms)
 constexpr int kDirect = kShares;           // a group with more shares than this adds them itself (no list)
 constexpr uint32_t kShareHist = 0x80000000u;
 
@@ -120,7 +122,7 @@ struct BinEmit {
 };
 
 #ifndef SFB_SHARE_MINBLK
-#define SFB_SHARE_MINBLK 5
+#define SFB_SHARE_MINBLK 4
 #endif
 __global__ void __launch_bounds__(kShareBlock, SFB_SHARE_MINBLK) k_tile_share(Dev d, sfb_tiles t, const long long* __restrict__ U) {
     extern __shared__ __align__(16) uint32_t s_mem[];           // bins [3 * max_slots] | plimb [7 * max_paths] | share lists

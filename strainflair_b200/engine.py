@@ -945,9 +945,12 @@ class AbundanceEngine:
         st["c"].copy_(work.t["cursor"], non_blocking=True)
         slots = None
         if keep_slots:
-            if getattr(self, "_plain_idx", None) is None:
-                self._plain_idx = torch.from_numpy(dg.slot_of_plain).to(self.device)
-            slots = (acc.uniq_abund[self._plain_idx].cpu(), acc.mult_abund[self._plain_idx].cpu())   # sentinels dropped on device
+            plain = torch.empty((2, max(1, self.graph.n_path_nodes)), dtype=torch.float64, device=self.device)
+            for k, arr in enumerate((acc.uniq_abund, acc.mult_abund)):                   # sentinels dropped on the device
+                _lib.check(self.lib.sfb_drop_sentinels(C.byref(self.gc), C.c_void_p(arr.data_ptr()),
+                                                       C.c_void_p(plain[k].data_ptr()), _stream()))
+                self.launches += 1
+            slots = (plain[0, :self.graph.n_path_nodes].cpu(), plain[1, :self.graph.n_path_nodes].cpu())
         torch.cuda.current_stream().synchronize()
         res = self._result_from(acc, st["f"].numpy(), st["i"].numpy(), st["t"].numpy())
         res.n_deferred, res.match_fill, res.app_fill = int(st["c"][1]) + int(st["c"][7]), int(st["c"][0]), int(st["c"][2])
