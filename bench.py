@@ -486,7 +486,12 @@ def run_ours(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     comm = None
+    numa_cores = None
     if world > 1:
+        # every rank on the host cores of its own GPU's NUMA node (pinned arenas, packer threads): the ranks' uploads
+        # share the host; the single-rank run keeps every core (its CPU baseline uses them)
+        from strainflair_b200 import dist as sfdist_
+        numa_cores = sfdist_.bind_to_gpu_numa(local)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
         comm = dist.group.WORLD
@@ -652,6 +657,7 @@ def run_ours(args):
             "other_modes": alt,
             "extra": extras,
             "host_staging_s": round(stage_s, 2),
+            "host_cores_bound": None if numa_cores is None else len(numa_cores),
             "gen_seconds": round(t_gen, 1),
         }
         print(json.dumps(line), flush=True)

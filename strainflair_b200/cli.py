@@ -44,7 +44,7 @@ def run_json2csv(graph_file, mapping_file, pickle_file, prefix, thr=0.95, device
     update_progress(1)                                                  # (the first pass is the decode + the kernels' pass 1)
     print("Parsing Alignment: second pass")
     update_progress(0)
-    res = eng.run(reads, keep_codes=True, keep_slots=False)
+    res = eng.run(reads, keep_codes=True, keep_slots=False, keep_matches=False)    # the reports need the codes, not the match lists
     update_progress(1)
     t["abundance_s"] = time.perf_counter() - t0
     t0 = t1 = time.perf_counter()

@@ -181,6 +181,9 @@ __device__ __forceinline__ void classify_aligned_pair_generic(const Dev& d, Bloc
     }
 }
 
+#ifndef SFB_CLS_PREFETCH
+#define SFB_CLS_PREFETCH 1
+#endif
 #ifndef SFB_CLS_MINBLK
 #define SFB_CLS_MINBLK 8      /* 80 registers; measured, see profiles/README.md */
 #endif
@@ -196,7 +199,26 @@ __global__ void __launch_bounds__(128, SFB_CLS_MINBLK) k_classify(Dev d) {
     block_counters_zero(sc);
     __syncthreads();
     const i64 n_round = d.w.grp_begin + ((d.r.n_groups - d.w.grp_begin + 127) & ~(i64)127);
-    for (i64 g = d.w.grp_begin + (i64)blockIdx.x * blockDim.x + threadIdx.x; g < n_round; g += (i64)gridDim.x * blockDim.x) {
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    // two passes ahead: the first alignment of the group this thread takes then; one pass ahead: its match words, path
+    // sets and walk offsets on their way to the L1 -- the chain header -> match word -> sets -> walk offset is four of the
+    // seven dependent gathers of a group
+    i64 a_next = -1;
+    {
+        const i64 g1 = d.w.grp_begin + (i64)blockIdx.x * blockDim.x + threadIdx.x + stride;
+        if (SFB_CLS_PREFETCH && g1 < d.r.n_groups) a_next = d.r.grp_aln_off[2 * g1];
+    }
+    for (i64 g = d.w.grp_begin + (i64)blockIdx.x * blockDim.x + threadIdx.x; g < n_round; g += stride) {
+        if (SFB_CLS_PREFETCH) {
+            if (a_next >= 0 && a_next < d.r.n_alns) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const uint2*>(d.w.aln_match) + a_next));
+                if (SETS) asm volatile("prefetch.global.L1 [%0];" ::"l"(d.w.aln_sets + 2 * a_next));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(d.r.aln_walk_off + a_next));
+            }
+            const i64 g2 = g + 2 * stride;
+            a_next = g2 < d.r.n_groups ? d.r.grp_aln_off[2 * g2] : -1;
+            if (g2 < d.r.n_groups) asm volatile("prefetch.global.L1 [%0];" ::"l"(d.r.mate_seq_len + 2 * g2));
+        }
         bool defer = false, slow = false;
         Mate mt[2];
         SetMate sm[2];

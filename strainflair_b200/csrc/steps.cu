@@ -52,6 +52,9 @@ constexpr int kStepBlock = 256;
 #ifndef SFB_STEPS_BATCH
 #define SFB_STEPS_BATCH 2
 #endif
+#ifndef SFB_STEPS_PREFETCH
+#define SFB_STEPS_PREFETCH 1
+#endif
 #ifndef SFB_STEPS_MINBLK
 #define SFB_STEPS_MINBLK 5
 #endif
@@ -71,9 +74,18 @@ __global__ void __launch_bounds__(kStepBlock, SFB_STEPS_MINBLK) k_match_steps(sf
     const i64 per = ((n_round / kStepBlock + gridDim.x - 1) / gridDim.x) * kStepBlock;
     const i64 b_lo = (i64)blockIdx.x * per, b_hi = min(b_lo + per, n_round);
     int st_steps = 0, st_tuples = 0;
+    // one pass ahead: the first record of the walk this thread takes next (its walk offset is loaded a pass earlier), so
+    // that the node ids of that walk are in the L1 when the pass begins
+    i64 w_next = -1;
+    if (SFB_STEPS_PREFETCH && a_lo + b_lo + threadIdx.x + kStepBlock < r.n_alns) w_next = r.aln_walk_off[a_lo + b_lo + threadIdx.x + kStepBlock];
     for (i64 base = b_lo + threadIdx.x; base < b_hi; base += kStepBlock) {
         const i64 a = a_lo + base;
         const bool live = a < r.n_alns;
+        if (SFB_STEPS_PREFETCH) {
+            if (w_next >= 0 && w_next < r.n_records) asm volatile("prefetch.global.L1 [%0];" ::"l"(r.walk_node + w_next));
+            const i64 a2 = a + 2 * kStepBlock;
+            w_next = (base + 2 * kStepBlock < b_hi && a2 < r.n_alns) ? r.aln_walk_off[a2] : -1;
+        }
         u64 f = 0, rv = 0;
         int p0 = 0;
         bool fb = false;

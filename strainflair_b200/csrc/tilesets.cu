@@ -16,6 +16,9 @@
 namespace sfb {
 
 constexpr int kBinBlock = 256;
+#ifndef SFB_SCATTER1_TWO
+#define SFB_SCATTER1_TWO 1
+#endif
 
 struct TileRange {
     int p0, np, s0, ns;
@@ -47,6 +50,43 @@ __global__ void __launch_bounds__(kBinBlock) k_tile_scatter1(Dev d, sfb_tiles t)
         for (int i = tid; i < 3 * tr.ns; i += kBinBlock) s_bins[i] = 0u;
         __syncthreads();
         const i64 a0 = d.r.grp_aln_off[2 * (i64)it.y], a1 = d.r.grp_aln_off[2 * (i64)it.z];
+#if SFB_SCATTER1_TWO
+        // two alignments per thread and pass: their codes, then their walk offsets, then their first records are in flight
+        // together (44 % of the alignments carry no assignment: one chain per thread leaves half the lanes without a load)
+        for (i64 a = a0 + tid; a < a1; a += 2 * kBinBlock) {
+            const i64 b = a + kBinBlock;
+            const int32_t c0 = d.w.aln_assign[a], c1 = b < a1 ? d.w.aln_assign[b] : -1;
+            i64 w0 = 0, w1 = 0;
+            int L0 = 0, L1 = 0;
+            if (c0 >= 0) {
+                w0 = d.r.aln_walk_off[a];
+                L0 = (int)(d.r.aln_walk_off[a + 1] - w0);
+            }
+            if (c1 >= 0) {
+                w1 = d.r.aln_walk_off[b];
+                L1 = (int)(d.r.aln_walk_off[b + 1] - w1);
+            }
+            int v0[4], v1[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                v0[u] = u < L0 ? d.r.walk_alen[w0 + u] : 0;
+                v1[u] = u < L1 ? d.r.walk_alen[w1 + u] : 0;
+            }
+            Fx one;
+            one.x0 = one.x1 = 0u;
+            one.x2 = 1u;
+            uint32_t* b0 = s_bins + 3 * (((uint32_t)c0 & SFB_SLOT_MASK) - tr.s0);
+            uint32_t* b1 = s_bins + 3 * (((uint32_t)c1 & SFB_SLOT_MASK) - tr.s0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (u < L0) bins_add_record(b0 + 3 * u, d.r, v0[u], true, 1.0, one);
+                if (u < L1) bins_add_record(b1 + 3 * u, d.r, v1[u], true, 1.0, one);
+            }
+            if (L0 > 4) bins_add_records(b0 + 12, d.r, w0 + 4, L0 - 4, true, 1.0);
+            if (L1 > 4) bins_add_records(b1 + 12, d.r, w1 + 4, L1 - 4, true, 1.0);
+            done += L0 + L1;
+        }
+#else
         for (i64 a = a0 + tid; a < a1; a += kBinBlock) {
             const int32_t code = d.w.aln_assign[a];
             if (code < 0) continue;
@@ -55,6 +95,7 @@ __global__ void __launch_bounds__(kBinBlock) k_tile_scatter1(Dev d, sfb_tiles t)
             bins_add_records(s_bins + 3 * (((uint32_t)code & SFB_SLOT_MASK) - tr.s0), d.r, w0, L, true, 1.0);
             done += L;
         }
+#endif
         __syncthreads();
         for (int i = tid; i < tr.ns; i += kBinBlock) fx_flush(d.acc.uniq_abund + tr.s0 + i, d.acc.det_stride, s_bins + 3 * i);
     }
@@ -187,7 +228,10 @@ __global__ void __launch_bounds__(kShareBlock, SFB_SHARE_MINBLK) k_tile_share(De
                     defer = (c1 & 0xf) == SFB_DEFER || (c1 >> 4) == SFB_DEFER;
                 }
                 const unsigned ball = __ballot_sync(0xffffffffu, defer);
-                if (defer) s_queue[wi][qn + __popc(ball & below)] = (int)(g - (i64)it.y);
+                if (defer) {
+                    s_queue[wi][qn + __popc(ball & below)] = (int)(g - (i64)it.y);
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(d.r.grp_aln_off + 2 * g));      // its header, for the decide step
+                }
                 qn += __popc(ball);
                 __syncwarp();
             }

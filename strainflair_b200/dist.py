@@ -94,3 +94,29 @@ def all_gather_rows(local_rows, row_bounds, group):
     recv = torch.empty((world, pad, width), dtype=local_rows.dtype, device=local_rows.device)
     dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=group)
     return torch.cat([recv[k, :counts[k]] for k in range(world)], dim=0)
+
+
+def bind_to_gpu_numa(device_index):
+    """One process per GPU: restrict this process to the host cores NVML lists as local to its GPU, so that the pinned
+    staging arenas it allocates afterwards (first touch) and the packer threads sit on the GPU's own NUMA node -- with
+    eight ranks pulling their shards from one host, uploads that cross the socket interconnect share its bandwidth.
+    Returns the cores bound to, or None when nothing was changed (no NVML, no affinity information, or the mask would
+    not narrow the current one)."""
+    import os
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+        handle = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpu + 63) // 64)
+        local = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        now = os.sched_getaffinity(0)
+        want = local & now
+        if not want or want == now or len(want) < 2:
+            return None
+        os.sched_setaffinity(0, want)
+        return sorted(want)
+    except Exception:
+        return None

@@ -82,7 +82,15 @@ class DeviceGraph:
         # tiles of the graph for the shared-memory kernels (tiles.py); none when the graph has no closed parts that fit
         from .tiles import Tiling
         import os
-        self.tiling = Tiling(graph, slot_cap=int(os.environ.get("SFB200_TILE_SLOTS", "4096"))) if tiles else None
+        self.tiling = None
+        if tiles:
+            # (the tiling only depends on the graph: engines on the same Graph object share it)
+            slot_cap = int(os.environ.get("SFB200_TILE_SLOTS", "4096"))
+            key = (slot_cap, os.environ.get("SFB200_TILE_K"))
+            cache = graph.__dict__.setdefault("_tiling_cache", {})
+            if key not in cache:
+                cache[key] = Tiling(graph, slot_cap=slot_cap)
+            self.tiling = cache[key]
         self.steps = None                        # pointers of the step index inside sfb_graph, when the graph has simple tiles
         if self.tiling is not None and self.tiling.n_tiles == 0:
             self.tiling = None
@@ -856,15 +864,16 @@ class AbundanceEngine:
         """End-to-end pass over a data set staged as several HostReads shards: ``collect(submit(shards))``."""
         return self.collect(self.submit(shards, depth=max(1, len(getattr(self, "_jobs", [])))))
 
-    def run(self, reads, keep_codes=True, keep_slots=True):
+    def run(self, reads, keep_codes=True, keep_slots=True, keep_matches=None):
         """Public entry: host arrays in, host results out (H2D and D2H included).  The reports need the
         per-path table, counters and histograms; ``keep_slots`` also brings the two per-node accumulator
-        arrays back, ``keep_codes`` the per-group leaf codes, assignments and match lists."""
+        arrays back, ``keep_codes`` the per-group leaf codes and assignments, ``keep_matches`` (default: as
+        ``keep_codes``) the match lists of every alignment -- diagnostics, written out in Python."""
         host = reads if isinstance(reads, HostReads) else self.stage(reads)
         for _ in range(3):
             dr = self.upload(host)
             work = self.run_device(dr)
-            res = self.fetch(work, dr, keep_codes, keep_slots)
+            res = self.fetch(work, dr, keep_codes, keep_slots, keep_matches)
             over = int(res.counters_raw[_lib.COUNTER_NAMES.index("MATCH_OVERFLOW")])
             if over == 0:
                 return res
@@ -920,8 +929,9 @@ class AbundanceEngine:
             table=table[:P].copy() if P else np.zeros((0, _lib.TABLE_COLS)),
         )
 
-    def fetch(self, work, dr, keep_codes=True, keep_slots=True):
+    def fetch(self, work, dr, keep_codes=True, keep_slots=True, keep_matches=None):
         acc, dg = self.acc, self.dg
+        keep_matches = keep_codes if keep_matches is None else (keep_matches and keep_codes)
         P, n_slots = acc.P, acc.n_slots
         if keep_slots and self.comm is not None:
             # whole slot arrays are wanted on the host: complete them from their owner ranks (not part of the pass)
@@ -960,7 +970,7 @@ class AbundanceEngine:
             res.grp_code = work.t["grp_code"][:dr.n_groups].cpu().numpy()
             res.grp_code2 = work.t["grp_code2"][:dr.n_groups].cpu().numpy()
             res.aln_assign = work.t["aln_assign"][:dr.n_alns].cpu().numpy()
-            if not self.tile_kernels or getattr(dr, "tiles_c", None) is None:      # (the tile kernels keep the match lists in shared memory)
+            if keep_matches and (not self.tile_kernels or getattr(dr, "tiles_c", None) is None):   # (the tile kernels keep the match lists in shared memory)
                 res.aln_match = work.t["aln_match"][:dr.n_alns].cpu().numpy().view(np.uint32).reshape(-1, 2)
                 res.match_buf = work.t["match_buf"][:min(work.match_cap, max(0, res.match_fill))].cpu().numpy() \
                     .view(np.uint32).reshape(-1, 2)

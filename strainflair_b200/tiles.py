@@ -90,7 +90,8 @@ class Tiling:
         ok = (count == pmax - pmin + 1) & (slots <= slot_cap) & (seg_hi - seg_lo <= node_cap) & (count <= path_cap)
         # a segment is "simple" when it has at most 64 paths and none of them visits a node twice
         seg_dup = np.zeros(n_seg, bool)
-        seg_dup[seg_of_path[self._dup_paths(graph)]] = True
+        self._dup = self._dup_paths(graph)
+        seg_dup[seg_of_path[self._dup]] = True
         seg_simple = (count <= 64) & ~seg_dup
         # neighbouring small segments (in node order AND path order) merge up to merge_target slots; a simple segment only
         # merges with simple ones, and only while the merged tile stays simple
@@ -149,7 +150,7 @@ class Tiling:
             np.repeat(np.arange(len(desc)), np_t)
         # a node twice in one path?  (path, node) pairs must be distinct
         dup_path = np.zeros(P, bool)
-        dup_path[self._dup_paths(graph)] = True
+        dup_path[self._dup] = True
         bad_tile = np.zeros(len(desc), bool)
         tp = tile_of_path[dup_path]
         bad_tile[tp[tp >= 0]] = True
@@ -186,6 +187,8 @@ class Tiling:
     def step_records(self, graph):
         """The per-node records of ``sfb_steps`` (include/sfb200.h) and whether any node with occurrences lies outside
         the simple tiles (its walks then need the occurrence-index kernel)."""
+        if getattr(self, "_steps", None) is not None:
+            return self._steps
         N = graph.n_nodes
         rec = np.zeros(N, self.STEP_DTYPE)
         rec["succ0"] = rec["succ1"] = -1
@@ -205,7 +208,8 @@ class Tiling:
             has = n_succ > k
             rec[sk][has] = self.edge_succ[e0[has] + k]
             rec[mk][has] = self.edge_mask[e0[has] + k]
-        return rec, bool((crossed & ~simple).any())
+        self._steps = (rec, bool((crossed & ~simple).any()))
+        return self._steps
 
     def items(self, tile_grp_off):
         """Work items int32[n, 4] = (tile, first group, end group, 0) of a read shard in tile order."""
