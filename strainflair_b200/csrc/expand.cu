@@ -1,11 +1,11 @@
 // sfb_expand_reads: compact transfer ("wire") layout of a read shard -> the arrays the kernels consume.
 //
-// The end-to-end path is bound by the host->device copy (PCIe, ~55 GB/s): CSR offsets travel as 1-byte counts and
-// become int64 offsets by a device prefix sum; read lengths travel as 16 bits; per record two bytes travel: the step
-// from the previous node id of the walk (walks follow the graph, ids are locally consecutive); aligned bases only for
-// the two end records of a walk (the others cover their node); histogram bins as a dictionary index; one common read
-// length.  Node ids are rebuilt by summing the steps along every walk, node lengths are gathered from the graph on
-// the device.  3.7 GB -> 0.8 GB per C3 shard.
+// The end-to-end path pays the host->device copy (PCIe, ~55 GB/s): CSR offsets travel as 1-byte counts and become int64
+// offsets by a device prefix sum; read lengths travel as 16 bits; per record four bits travel: the step from the previous
+// node id of the walk (walks follow the graph, ids are locally consecutive); aligned bases only for the two end records of
+// a walk (the others cover their node); histogram bins as a dictionary index; one common read length.  Node ids are
+// rebuilt by summing the steps along every walk, node lengths are gathered from the graph on the device.
+// 3.7 GB -> 0.65 GB per C3 shard.
 #include "common.cuh"
 
 namespace sfb {
