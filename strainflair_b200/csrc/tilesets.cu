@@ -117,6 +117,9 @@ __global__ void __launch_bounds__(kBinBlock) k_tile_scatter1(Dev d, sfb_tiles t)
 constexpr int kShareBlock = SFB_SHARE_BLOCK;
 constexpr int kShareWarps = kShareBlock / 32;
 constexpr int kQueue = 64;                 // deferred groups waiting per warp (a scan adds at most 32)
+#ifndef SFB_SHARE_FLAT
+#define SFB_SHARE_FLAT 1
+#endif
 #ifndef SFB_SHARE_LIST
 #define SFB_SHARE_LIST 160
 #endif
@@ -160,7 +163,59 @@ struct BinEmit {
         rec += L;
         app += 1;
     }
+    // the same without the node loop: where the share's records start (bin offset in words, first record, count) and its
+    // weight, for share_records below
+    __device__ __forceinline__ void share(i64 a, bool rev, int pid, int seq_len, double ratio, int times, uint32_t& bo, i64& w0,
+                                          int& L, double& weight) {
+        weight = ratio * (double)times;
+        uint32_t* l = plimb + 7 * (pid - tr.p0);
+        l[0] = 1u;
+        fx_smem_add(l + 1, fx_split(weight));
+        fx_smem_add(l + 4, fx_split((ratio * (double)seq_len / (double)d.g.path_seq_len[pid]) * (double)times));
+        w0 = d.r.aln_walk_off[a];
+        L = (int)(d.r.aln_walk_off[a + 1] - w0);
+        const int node = d.r.walk_node[rev ? w0 + L - 1 : w0];
+        const uint2 tup = sets_tuple(d.g, node, tr.p0, 1ull << (pid - tr.p0), rev);
+        bo = 3u * ((tup.x & SFB_SLOT_MASK) - (uint32_t)tr.s0);
+        rec += L;
+        app += 1;
+    }
 };
+// The node loops (json2csv.py:1157-1158) of the 32 shares a warp holds, one per lane (L = 0: none).  A lane that walked its
+// own records ran beside lanes with shorter walks (15 of 32 lanes busy, 45 % of the kernel's instructions): here the first
+// and the last record of every share -- the two that usually cover their node only in part, cov * weight with an fp64
+// division -- are taken lane = share, and the records in between, which add the share's weight as it is, are laid end to
+// end over the warp: lane = record, its share found by a binary search in the running sum of the interior counts
+// (shuffles), every lane busy whatever the walk lengths.  Called by the whole warp.
+__device__ __forceinline__ void share_records(uint32_t* bins, const sfb_reads& r, uint32_t bo, i64 w0, int L, double weight) {
+    const Fx whole = fx_split(weight);
+    int v0 = 0, v1 = 0;
+    if (L > 0) v0 = r.walk_alen[w0];
+    if (L > 1) v1 = r.walk_alen[w0 + L - 1];
+    if (L > 0) bins_add_record(bins + bo, r, v0, false, weight, whole);
+    if (L > 1) bins_add_record(bins + bo + 3 * (L - 1), r, v1, false, weight, whole);
+    const int inner = L > 2 ? L - 2 : 0;
+    const int incl = (int)warp_scan((unsigned)inner);
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int excl = incl - inner;
+    const uint32_t w_lo = (uint32_t)(u64)w0, w_hi = (uint32_t)((u64)w0 >> 32);
+    for (int r0 = 0; r0 < total; r0 += 32) {
+        const int q = r0 + lane_id();
+        int s = 0;                               // the lanes whose running sum is <= q: q belongs to the next one
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1)
+            if (__shfl_sync(0xffffffffu, incl, s + step - 1) <= q) s += step;
+        const int i = 1 + q - __shfl_sync(0xffffffffu, excl, s);
+        const i64 ws = (i64)(((u64)__shfl_sync(0xffffffffu, w_hi, s) << 32) | __shfl_sync(0xffffffffu, w_lo, s));
+        const uint32_t bs = __shfl_sync(0xffffffffu, bo, s);
+        Fx f;
+        f.x0 = __shfl_sync(0xffffffffu, whole.x0, s);
+        f.x1 = __shfl_sync(0xffffffffu, whole.x1, s);
+        f.x2 = __shfl_sync(0xffffffffu, whole.x2, s);
+        const double wt = __shfl_sync(0xffffffffu, weight, s);
+        if (q < total) bins_add_record(bins + bs + 3 * i, r, r.walk_alen[ws + i], false, wt, f);
+    }
+}
 
 #ifndef SFB_SHARE_MINBLK
 #define SFB_SHARE_MINBLK 4
@@ -201,6 +256,12 @@ __global__ void __launch_bounds__(kShareBlock, SFB_SHARE_MINBLK) k_tile_share(De
             __syncwarp();
             for (int e0 = 0; e0 < fill; e0 += 32) {
                 const int e = e0 + lane;
+#if SFB_SHARE_FLAT
+                uint32_t bo = 0;
+                i64 w0 = 0;
+                int L = 0;
+                double weight = 0.0;
+#endif
                 if (e < fill) {
                     const uint32_t pth = list.path[e];
                     const SharePlan pl = list.plan[list.plan_of[e]];
@@ -208,8 +269,16 @@ __global__ void __launch_bounds__(kShareBlock, SFB_SHARE_MINBLK) k_tile_share(De
                     const i64 a = a_item + list.a_off[e];
                     if (pth & kShareHist) hist_add(d, sc, pid, a);                                  // json2csv.py:1246-1252
                     const int times = pl.common ? __popcll(d.g.path_smask[pid] & pl.common) : 1;
+#if SFB_SHARE_FLAT
+                    add.share(a, (pth & SFB_MATCH_REV) != 0, pid, pl.seq_len, ratio_of(U[pid], pl.total, pl.n), times, bo, w0, L, weight);
+#else
                     add(a, (pth & SFB_MATCH_REV) != 0, pid, pl.seq_len, ratio_of(U[pid], pl.total, pl.n), times);
+#endif
                 }
+#if SFB_SHARE_FLAT
+                __syncwarp();
+                share_records(s_bins, d.r, bo, w0, L, weight);
+#endif
             }
             fill = 0;
             __syncwarp();
