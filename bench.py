@@ -486,12 +486,13 @@ def run_ours(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     comm = None
+    # from here on this process stays on the host cores of its own GPU's NUMA node (the pinned staging arenas are
+    # allocated and filled there, the packer threads run there); the CPU baseline above had every core
     numa_cores = None
-    if world > 1:
-        # every rank on the host cores of its own GPU's NUMA node (pinned arenas, packer threads): the ranks' uploads
-        # share the host; the single-rank run keeps every core (its CPU baseline uses them)
+    if not os.environ.get("SFB200_NO_NUMA"):
         from strainflair_b200 import dist as sfdist_
         numa_cores = sfdist_.bind_to_gpu_numa(local)
+    if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
         comm = dist.group.WORLD
@@ -563,10 +564,9 @@ def run_ours(args):
         del dr
         cuts = [sfdist.shard_bounds(reads.n_groups, args.e2e_shards, k) for k in range(args.e2e_shards)]
         t0 = time.perf_counter()
-        shards = []
-        for a, b in cuts:
-            shards.append(eng.stage(reads.slice_groups(a, b), pin=True))
-            shards[-1].reads = None
+        shards = eng.stage_shards(reads, len(cuts), pin=True)      # tile order first, shards cut at tile boundaries
+        for s_ in shards:
+            s_.reads = None
         pack_s = time.perf_counter() - t0
         log_mem("e2e shards staged")
         h2d = sum(s_.nbytes() for s_ in shards)

@@ -65,18 +65,41 @@ __global__ void __launch_bounds__(kScanBlock) k_scan_write(const uint8_t* cnt, i
     const i64 lo = (i64)blockIdx.x * kScanTile + (i64)threadIdx.x * kScanItems;
     int c[kScanItems];
     i64 s = 0;
+    // a thread's 16 counts with one 128-bit load, its 16 offsets with eight 128-bit stores (a warp's 8-byte stores, 128
+    // bytes apart, touch 32 sectors for 256 bytes) -- whenever the arrays are 16-byte aligned and the thread's stretch is whole
+    const bool wide = lo + kScanItems <= n && (((size_t)cnt | (size_t)off) & 15) == 0;
+    if (wide) {
+        const uint4 q = *reinterpret_cast<const uint4*>(cnt + lo);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-    for (int i = 0; i < kScanItems; ++i) {
-        c[i] = lo + i < n ? cnt[lo + i] : 0;
-        s += c[i];
+        for (int i = 0; i < kScanItems; ++i) {
+            c[i] = (int)((w[i >> 2] >> (8 * (i & 3))) & 0xffu);
+            s += c[i];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < kScanItems; ++i) {
+            c[i] = lo + i < n ? cnt[lo + i] : 0;
+            s += c[i];
+        }
     }
     i64 total;
     i64 run = partial[blockIdx.x] + block_excl_scan(s, s_warp, total);
+    if (wide) {
 #pragma unroll
-    for (int i = 0; i < kScanItems; ++i) {
-        if (lo + i < n) off[lo + i] = run;
-        run += c[i];
-        if (lo + i == n - 1) off[n] = run;
+        for (int i = 0; i < kScanItems; i += 2) {
+            const i64 a = run, b = run + c[i];
+            *reinterpret_cast<longlong2*>(off + lo + i) = make_longlong2(a, b);
+            run = b + c[i + 1];
+        }
+        if (lo + kScanItems == n) off[n] = run;
+    } else {
+#pragma unroll
+        for (int i = 0; i < kScanItems; ++i) {
+            if (lo + i < n) off[lo + i] = run;
+            run += c[i];
+            if (lo + i == n - 1) off[n] = run;
+        }
     }
 }
 

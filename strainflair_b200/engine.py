@@ -199,15 +199,18 @@ class HostReads:
     (the end-to-end path copies from here every step).  ``wire``: use the compact transfer layout when the shard
     allows it (offsets as 1-byte counts, 16-bit lengths; expanded on the device by sfb_expand_reads)."""
 
-    def __init__(self, reads: Reads, pin=True, wire=True, tiling=None):
+    def __init__(self, reads: Reads, pin=True, wire=True, tiling=None, tile_grp_off=None):
         # ``tiling`` (tiles.Tiling of the graph; AbundanceEngine.stage passes its own): the groups are staged in tile
         # order -- those whose alignments all start and end inside one tile first, tile by tile, the rest after them in
         # file order -- with the work items of the tile kernels.  The per-path results do not depend on the order;
         # per-group / per-alignment outputs are put back in file order by fetch.
+        # ``tile_grp_off``: the groups are in tile order already (a slice of a permuted data set, stage_shards), this is
+        # where each tile's groups start in it.
         self.order = self.aln_index = None
         self.tiling, self.items, self.grp_begin, self.aln_begin = tiling, None, 0, 0
         if tiling is not None and reads.n_groups > 0:
-            reads, self.order, self.aln_index, tile_grp_off = tile_permute(reads, tiling)
+            if tile_grp_off is None:
+                reads, self.order, self.aln_index, tile_grp_off = tile_permute(reads, tiling)
             self.items = tiling.items(tile_grp_off)
             self.grp_begin = int(tile_grp_off[tiling.n_tiles])
             self.aln_begin = int(reads.grp_aln_off[2 * self.grp_begin])
@@ -465,6 +468,35 @@ def tile_permute(reads: Reads, tiling, threads=None):
     return moved, order, aln_index, tile_grp_off
 
 
+def stage_shards(reads: Reads, tiling, n_shards, pin=True, wire=True):
+    """A data set staged as ``n_shards`` HostReads for AbundanceEngine.submit / run_stream: the read groups are put in tile
+    order FIRST and the shards cut at tile boundaries, so that every tile's groups sit in one shard (file-order slices
+    staged one by one spread every tile over all shards: as many work items, each a fraction of the size, in every
+    shard).  The groups outside the tile range follow in the last shards.  Without a tiling: file-order slices."""
+    from . import dist as sfdist
+    G = reads.n_groups
+    if tiling is None or G == 0:
+        return [HostReads(reads.slice_groups(*sfdist.shard_bounds(G, n_shards, k)), pin=pin, wire=wire) for k in range(n_shards)]
+    moved, _, _, tile_grp_off = tile_permute(reads, tiling)
+    edges = np.asarray(tile_grp_off[:tiling.n_tiles + 1], np.int64)          # group index where each tile starts; [-1] = end of the tile range
+    cuts = [0]
+    for k in range(1, n_shards):
+        want = sfdist.shard_bounds(G, n_shards, k)[0]
+        if want < edges[-1]:                                                 # inside the tile range: the nearest tile boundary
+            j = int(np.searchsorted(edges, want))
+            lo, hi = int(edges[max(j - 1, 0)]), int(edges[min(j, len(edges) - 1)])
+            want = lo if want - lo <= hi - want else hi
+        cuts.append(max(want, cuts[-1]))
+    cuts.append(G)
+    out = []
+    for g0, g1 in zip(cuts[:-1], cuts[1:]):
+        off = np.zeros(tiling.n_tiles + 2, np.int64)
+        off[:tiling.n_tiles + 1] = np.clip(edges, g0, g1) - g0
+        off[tiling.n_tiles + 1] = g1 - g0
+        out.append(HostReads(moved.slice_groups(g0, g1), pin=pin, wire=wire, tiling=tiling, tile_grp_off=off))
+    return out
+
+
 def restore_file_order(res, order, aln_index):
     """Per-group and per-alignment outputs of a pass over permuted read groups (``order[k]`` / ``aln_index[k]`` = old
     index of new group / alignment k), back in the order of the input file."""
@@ -546,6 +578,10 @@ class AbundanceEngine:
             self.work = None
             self.work = Work(dr.n_groups, dr.n_alns, cap, self.device, self.app_cap_hint)
         return self.work
+
+    def stage_shards(self, reads: Reads, n_shards, pin=True, wire=True):
+        """``reads`` as ``n_shards`` staged shards for submit / run_stream (tile order first, cut at tile boundaries)."""
+        return stage_shards(reads, self.tiling, n_shards, pin=pin, wire=wire)
 
     def stage(self, reads: Reads, pin=True, wire=True):
         """Host staging of a read shard for this engine's graph: tile order + work items, transfer layout, one pinned arena."""

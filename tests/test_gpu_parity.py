@@ -485,6 +485,24 @@ def test_streamed_shards_equal_single_pass():
             assert np.allclose(many.mult_reads, one.mult_reads, rtol=1e-9, atol=0)
 
 
+def test_shards_cut_at_tile_boundaries_equal_single_pass():
+    """run_stream over engine.stage_shards (tile order first, shards cut at tile boundaries) == run: integers exact, the
+    order-independent fp64 sums bit for bit."""
+    need_gpu()
+    graph, reads = synth.make_config("small", scale=0.5)
+    eng = engine.AbundanceEngine(graph)
+    one = eng.run(reads, keep_codes=False, keep_slots=False)
+    for k in (1, 2, 5):
+        many = eng.run_stream(eng.stage_shards(reads, k))
+        for name in oa.COUNTERS:
+            assert many.C[name] == one.C[name], (k, name)
+        assert np.array_equal(many.uniq_reads, one.uniq_reads) and np.array_equal(many.hist, one.hist)
+        assert many.n_deferred == one.n_deferred
+        assert np.array_equal(many.table, one.table, equal_nan=True)
+        for name in ("uniq_norm", "mult_reads", "mult_norm"):
+            assert np.array_equal(getattr(many, name), getattr(one, name)), (k, name)
+
+
 def test_pipelined_jobs_equal_single_passes():
     """submit/collect with two jobs in flight (uploads of job k+1 under pass 2 of job k, each job on its own
     accumulators and device buffers): every job returns what a plain run of its reads returns, in any interleaving,

@@ -561,3 +561,33 @@ def test_native_locality_permutation_equals_numpy(threads):
         assert np.array_equal(order, want_order) and np.array_equal(aln_index, want_index)
         for k in fields:
             assert np.array_equal(getattr(moved, k), getattr(want, k)), k
+
+
+@pytest.mark.parametrize("n_shards", [1, 3, 4, 9])
+def test_stage_shards_cuts_tile_ordered_groups_at_tile_boundaries(n_shards):
+    """engine.stage_shards: the data set in tile order first, then cut into shards at tile boundaries -- the shards
+    together hold every group once (the same permuted arrays, end to end), a tile's groups sit in one shard, and each
+    shard's work items and tile range describe its own slice."""
+    from strainflair_b200 import engine, synth
+    from strainflair_b200.tiles import Tiling
+    graph, reads = synth.make_config("small", scale=0.3)
+    tl = Tiling(graph)
+    whole = engine.HostReads(reads, pin=False, wire=True, tiling=tl)
+    shards = engine.stage_shards(reads, tl, n_shards, pin=False)
+    assert len(shards) == n_shards and sum(s.n_groups for s in shards) == reads.n_groups
+    assert np.array_equal(np.concatenate([s.reads.walk_node for s in shards]), whole.reads.walk_node)
+    assert np.array_equal(np.concatenate([s.reads.grp_nmates for s in shards]), whole.reads.grp_nmates)
+    owner, g_base = {}, 0
+    for k, s in enumerate(shards):
+        assert s.order is None                                  # (per-group outputs are not restored for staged shards)
+        covered = np.zeros(s.n_groups, np.int32)
+        for tile, g0, g1, _ in (s.items if s.items is not None else []):
+            assert owner.setdefault(int(tile), k) == k, "a tile in two shards"
+            covered[g0:g1] += 1
+        assert (covered[:s.grp_begin] == 1).all() and (covered[s.grp_begin:] == 0).all()
+        assert s.aln_begin == int(s.reads.grp_aln_off[2 * s.grp_begin])
+        g_base += s.n_groups
+    assert sum(s.grp_begin for s in shards) == whole.grp_begin
+    # without a tiling: plain file-order slices
+    flat = engine.stage_shards(reads, None, n_shards, pin=False)
+    assert np.array_equal(np.concatenate([s.reads.walk_node for s in flat]), reads.walk_node)
