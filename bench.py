@@ -34,7 +34,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-pairs", type=int, default=160_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-shards", type=int, default=4)
+    ap.add_argument("--e2e-shards", type=int, default=2)
     ap.add_argument("--no-det", action="store_true", help="skip the measurements of the other modes (plain fp64 atomics, global-memory kernels)")
     ap.add_argument("--no-extras", action="store_true", help="skip the C4 / C5 sub-measurements")
     return ap.parse_args()

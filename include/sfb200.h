@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SFB_ABI_VERSION 13
+#define SFB_ABI_VERSION 14
 
 /* ---- status codes ---------------------------------------------------- */
 #define SFB_OK            0
@@ -160,7 +160,8 @@ typedef struct sfb_reads {
  *   offsets            as 1-byte counts (prefix sums on the device)
  *   read lengths       one common value + the mates that differ (or 16 bits per mate)
  *   histogram bins     one byte per alignment: index into a dictionary of the shard's frequent 5-tuples
- *   node ids           per alignment the first node; per record the step from the previous node id of the walk in FOUR
+ *   node ids           per alignment the first node as 16 bits above the smallest one of its block of 256 alignments;
+ *                      per record the step from the previous node id of the walk in FOUR
  *                      bits (walks follow the graph, whose ids are locally consecutive: a step is +1 or +2 almost always)
  *   aligned bases      one byte for the first and for the last record of a walk; the records in between cover
  *                      their node completely (aligned bases = node length, gathered on the device)
@@ -180,7 +181,8 @@ typedef struct sfb_wire {
     const uint8_t*  bins_dict;    /* [255*5] */
     const int64_t*  bins_exc_idx; /* [n_bins_exc] alignment                           */
     const uint8_t*  bins_exc_val; /* [n_bins_exc*5] */
-    const int32_t*  aln_node0;    /* [A]  first node of the walk                      */
+    const uint16_t* aln_node0;    /* [A]  first node of the walk minus node0_anchor[a / 256]: read groups in tile order
+                                          start within a few hundred node ids of their neighbours (see node0_anchor) */
     const uint8_t*  aln_al_first; /* [A]  aligned bases of the walk's first record, 255 = explicit coverage */
     const uint8_t*  aln_al_last;  /* [A]  ... of its last record (walks of two records or more)            */
     const uint8_t*  walk_step;    /* [(R+1)/2] one nibble per record, record q in bits 4*(q&1).. of byte q/2: node id minus
@@ -190,6 +192,9 @@ typedef struct sfb_wire {
     const double*   exc_cov;      /* [E]  */
     const int64_t*  wide_idx;     /* [W]  record indices of the wide steps, ascending */
     const int32_t*  wide_node;    /* [W]  */
+    const int32_t*  node0_anchor; /* [(A+255)/256] per block of 256 alignments the smallest first node; -1 - k: the block's
+                                          first nodes span more than 65535 ids and are node0_wide[256 * k + (a & 255)]   */
+    const int32_t*  node0_wide;   /* [256 * number of such blocks] */
 } sfb_wire;
 
 /* ---- per-shard work arrays (outputs of match / classify) ----------------- */

@@ -14,10 +14,10 @@ c_f64p = C.POINTER(C.c_double)
 
 
 # arrays of the transfer layout, in struct order
-WIRE_DTYPES = ("u1", "u1", "u2", "i8", "i4", "u1", "u1", "u1", "i8", "u1", "i4", "u1", "u1", "u1", "i8", "f8", "i8", "i4")
+WIRE_DTYPES = ("u1", "u1", "u2", "i8", "i4", "u1", "u1", "u1", "i8", "u1", "u2", "u1", "u1", "u1", "i8", "f8", "i8", "i4", "i4", "i4")
 WIRE_ARRAYS = ("grp_nmates", "mate_naln", "mate_seq_len", "seq_exc_idx", "seq_exc_val", "aln_len", "aln_code", "bins_dict",
                "bins_exc_idx", "bins_exc_val", "aln_node0", "aln_al_first", "aln_al_last", "walk_step", "exc_idx", "exc_cov",
-               "wide_idx", "wide_node")
+               "wide_idx", "wide_node", "node0_anchor", "node0_wide")
 
 
 class SfbGraph(C.Structure):
@@ -106,7 +106,7 @@ SLOT_MASK, MATCH_REV, MATCH_MULTI, MATCH_NONE, MATCH_SETS = 0x3FFFFFFF, 0x400000
 MAX_SLOTS = 0x3FFFFFFF
 (ABSENT, FILTERED, UNASSIGNED, UNASSIGNED_BOOK, DEFER, ASSIGN_SAME, ASSIGN_DIFF, MULTI_ALIGN, INCONSIST,
  SE_COUNTED) = range(10)
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 EXPORTS = ("sfb_abi_version", "sfb_version", "sfb_last_error", "sfb_expand_reads", "sfb_match", "sfb_match_steps", "sfb_classify", "sfb_pass1_scatter",
            "sfb_pass2", "sfb_pass2_resolve", "sfb_pass2_scatter", "sfb_accum_collapse", "sfb_path_reduce", "sfb_cluster_strain_counts", "sfb_strain_aggregate",

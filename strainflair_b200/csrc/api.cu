@@ -122,7 +122,7 @@ int sfb_expand_reads(const sfb_wire* w, const int32_t* node_len, const sfb_reads
     SFB_REQUIRE(dst->grp_aln_off && dst->aln_walk_off && scratch, "null output");
     SFB_REQUIRE(w->n_groups == 0 || (w->grp_nmates && w->mate_naln && dst->mate_seq_len), "null array");
     SFB_REQUIRE(w->n_seq_exc == 0 || (w->seq_exc_idx && w->seq_exc_val), "null array");
-    SFB_REQUIRE(w->n_alns == 0 || (w->aln_len && w->aln_code && w->bins_dict && w->aln_node0 && w->aln_al_first &&
+    SFB_REQUIRE(w->n_alns == 0 || (w->aln_len && w->aln_code && w->bins_dict && w->aln_node0 && w->node0_anchor && w->aln_al_first &&
                                    w->aln_al_last && dst->aln_bins), "null array");
     SFB_REQUIRE(w->n_bins_exc == 0 || (w->bins_exc_idx && w->bins_exc_val), "null array");
     SFB_REQUIRE(w->n_records == 0 || (w->walk_step && dst->walk_node && dst->walk_alen && node_len), "null array");

@@ -21,7 +21,7 @@ namespace {
 enum Which {       // order of the arrays in sfb_wire
     W_GRP_NMATES, W_MATE_NALN, W_MATE_SEQ_LEN, W_SEQ_EXC_IDX, W_SEQ_EXC_VAL, W_ALN_LEN, W_ALN_CODE, W_BINS_DICT,
     W_BINS_EXC_IDX, W_BINS_EXC_VAL, W_ALN_NODE0, W_ALN_AL_FIRST, W_ALN_AL_LAST, W_WALK_STEP, W_EXC_IDX, W_EXC_COV,
-    W_WIDE_IDX, W_WIDE_NODE, W_COUNT
+    W_WIDE_IDX, W_WIDE_NODE, W_NODE0_ANCHOR, W_NODE0_WIDE, W_COUNT
 };
 
 struct Bytes {     // exact-size, uninitialised storage
@@ -162,10 +162,16 @@ void pack(sfb_packed& P, const sfb_reads& r, int T) {
         for (int k = 0; k < 5; ++k) P.arr[W_BINS_DICT].as<uint8_t>()[i * 5 + k] = (uint8_t)(top[i] >> (8 * k));
 
     // ---- per alignment and per record -------------------------------------------------------------
-    if (!P.arr[W_ALN_LEN].alloc((size_t)A) || !P.arr[W_ALN_CODE].alloc((size_t)A) || !P.arr[W_ALN_NODE0].alloc((size_t)A * 4) ||
+    if (!P.arr[W_ALN_LEN].alloc((size_t)A) || !P.arr[W_ALN_CODE].alloc((size_t)A) || !P.arr[W_ALN_NODE0].alloc((size_t)A * 2) ||
         !P.arr[W_ALN_AL_FIRST].alloc((size_t)A) || !P.arr[W_ALN_AL_LAST].alloc((size_t)A) || !P.arr[W_WALK_STEP].alloc(((size_t)R + 1) / 2))
         return oom();
     if (R) memset(P.arr[W_WALK_STEP].p, 0, ((size_t)R + 1) / 2);        // nibbles are OR-ed in
+    std::vector<int32_t> node0_full;                      // first nodes as they are; coded per block of 256 below
+    try {
+        node0_full.resize((size_t)A);
+    } catch (const std::bad_alloc&) {
+        return oom();
+    }
     const size_t a_chunks = ((size_t)A + kGrain - 1) / kGrain;
     std::vector<std::vector<int64_t>> bins_idx(a_chunks), exc_idx(a_chunks), wide_idx(a_chunks);
     std::vector<std::vector<uint8_t>> bins_val(a_chunks);
@@ -174,7 +180,7 @@ void pack(sfb_packed& P, const sfb_reads& r, int T) {
     run_parallel(T, (size_t)A, kGrain, [&](size_t c, size_t lo, size_t hi) {
         uint8_t* aln_len = P.arr[W_ALN_LEN].as<uint8_t>();
         uint8_t* code = P.arr[W_ALN_CODE].as<uint8_t>();
-        int32_t* node0 = P.arr[W_ALN_NODE0].as<int32_t>();
+        int32_t* node0 = node0_full.data();
         uint8_t* al_first = P.arr[W_ALN_AL_FIRST].as<uint8_t>();
         uint8_t* al_last = P.arr[W_ALN_AL_LAST].as<uint8_t>();
         uint8_t* step = P.arr[W_WALK_STEP].as<uint8_t>();
@@ -228,6 +234,38 @@ void pack(sfb_packed& P, const sfb_reads& r, int T) {
         }
     });
     if (!fits) return give_up("a walk of more than 255 nodes");
+    // ---- first nodes: 16 bits above the smallest one of the block of 256 alignments (blocks that span more: listed) ----
+    {
+        const size_t nb = ((size_t)A + 255) / 256;
+        if (!P.arr[W_NODE0_ANCHOR].alloc(nb * 4)) return oom();
+        int32_t* anchor = P.arr[W_NODE0_ANCHOR].as<int32_t>();
+        uint16_t* lo16 = P.arr[W_ALN_NODE0].as<uint16_t>();
+        run_parallel(T, nb, 256, [&](size_t, size_t b0, size_t b1) {
+            for (size_t b = b0; b < b1; ++b) {
+                const size_t a0 = b * 256, a1 = std::min((size_t)A, a0 + 256);
+                int32_t mn = node0_full[a0], mx = node0_full[a0];
+                for (size_t a = a0; a < a1; ++a) {
+                    mn = std::min(mn, node0_full[a]);
+                    mx = std::max(mx, node0_full[a]);
+                }
+                const bool narrow = mn >= 0 && (int64_t)mx - (int64_t)mn <= 65535;
+                anchor[b] = narrow ? mn : -1;
+                for (size_t a = a0; a < a1; ++a) lo16[a] = narrow ? (uint16_t)(node0_full[a] - mn) : (uint16_t)0;
+            }
+        });
+        size_t n_wide_blocks = 0;
+        for (size_t b = 0; b < nb; ++b)
+            if (anchor[b] < 0) anchor[b] = -1 - (int32_t)n_wide_blocks++;
+        if (!P.arr[W_NODE0_WIDE].alloc(n_wide_blocks * 256 * 4)) return oom();
+        int32_t* wide0 = P.arr[W_NODE0_WIDE].as<int32_t>();
+        run_parallel(T, nb, 256, [&](size_t, size_t b0, size_t b1) {
+            for (size_t b = b0; b < b1; ++b) {
+                if (anchor[b] >= 0) continue;
+                const size_t k = (size_t)(-1 - anchor[b]), a0 = b * 256;
+                for (size_t j = 0; j < 256; ++j) wide0[256 * k + j] = a0 + j < (size_t)A ? node0_full[a0 + j] : 0;
+            }
+        });
+    }
     size_t n_exc = 0, n_wide = 0;
     for (const auto& v : exc_idx) n_exc += v.size();
     for (const auto& v : wide_idx) n_wide += v.size();

@@ -70,7 +70,7 @@ def test_struct_sizes_are_pointer_and_int64_multiples():
         assert ctypes.sizeof(st) % 8 == 0
     assert ctypes.sizeof(_lib.SfbGraph) == 8 * 21
     assert ctypes.sizeof(_lib.SfbReads) == 8 * 12
-    assert ctypes.sizeof(_lib.SfbWire) == 8 * 26
+    assert ctypes.sizeof(_lib.SfbWire) == 8 * 28
     assert ctypes.sizeof(_lib.SfbWork) == 8 * 15
     assert ctypes.sizeof(_lib.SfbTiles) == 8 * 13
     assert ctypes.sizeof(_lib.SfbAccum) == 8 * 10

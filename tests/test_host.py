@@ -205,7 +205,8 @@ def _expand_on_host(w, common, n_nodes_len):
     node, word = np.empty(R, np.int32), np.empty(R, np.int32)
     wide = dict(zip(w["wide_idx"].tolist(), w["wide_node"].tolist()))
     for a in range(A):
-        cur = int(w["aln_node0"][a])
+        anchor = int(w["node0_anchor"][a >> 8])           # first node: 16 bits above the block's smallest one, or listed
+        cur = anchor + int(w["aln_node0"][a]) if anchor >= 0 else int(w["node0_wide"][256 * (-1 - anchor) + (a & 255)])
         for r in range(off[a], off[a + 1]):
             if r > off[a]:
                 nib = (int(w["walk_step"][r >> 1]) >> (4 * (r & 1))) & 15          # step + 8, 0 = listed
@@ -591,3 +592,29 @@ def test_stage_shards_cuts_tile_ordered_groups_at_tile_boundaries(n_shards):
     # without a tiling: plain file-order slices
     flat = engine.stage_shards(reads, None, n_shards, pin=False)
     assert np.array_equal(np.concatenate([s.reads.walk_node for s in flat]), reads.walk_node)
+
+
+def test_transfer_layout_first_nodes_wide_and_narrow_blocks():
+    """First nodes travel as 16 bits above the smallest one of their block of 256 alignments; a block that spans more than
+    65535 node ids lists its first nodes instead.  Node ids spread over millions, read groups in file order and sorted by
+    first node: both kinds of block occur and expand to the same arrays."""
+    from strainflair_b200 import engine, synth
+    gkw, _ = synth.CONFIGS["tiny"]
+    graph = synth.make_graph(21, **gkw)
+    reads = synth.make_reads(graph, 22, n_pairs=4000, read_len=150)
+    # the upper half of the node ids moved 70000 up: steps stay small, blocks of 256 alignments that hold first nodes of
+    # both halves span more than 16 bits
+    new_id = np.arange(graph.n_nodes, dtype=np.int64) + 70000 * (np.arange(graph.n_nodes, dtype=np.int64) >= graph.n_nodes // 2)
+    node_len = np.ones(int(new_id[-1]) + 1, graph.node_len.dtype)
+    node_len[new_id] = graph.node_len
+    reads.walk_node[:] = new_id[reads.walk_node]
+    seen = set()
+    for rd in (reads, reads.permute_groups(reads.locality_order())):
+        w, common = engine.wire_arrays(rd)
+        wide_blocks = int((w["node0_anchor"] < 0).sum())
+        seen.add("wide" if wide_blocks else "none")
+        seen.add("narrow" if wide_blocks < len(w["node0_anchor"]) else "all")
+        assert len(w["node0_wide"]) == 256 * wide_blocks
+        grp_aln_off, off, seq, bins, node, word = _expand_on_host(w, common, node_len)
+        assert np.array_equal(node, rd.walk_node) and np.array_equal(off, rd.aln_walk_off)
+    assert {"wide", "narrow"} <= seen
