@@ -158,38 +158,46 @@ __global__ void __launch_bounds__(kWalkTile) k_expand_walks(sfb_wire w, const i6
         const bool staged = r1 - r0 <= kWalkImage;
         const i64 a = a0 + threadIdx.x;
         if (a < a1) {
-            const i64 lo = walk_off[a], hi = walk_off[a + 1];
+            const i64 lo = walk_off[a];
+            const int L = (int)w.aln_len[a];                     // (<= 255: everything below in 32-bit arithmetic)
             const int32_t anchor = w.node0_anchor[a >> 8];       // (kWalkTile == 256: one anchor per block pass)
             int32_t node = anchor >= 0 ? anchor + (int32_t)w.aln_node0[a] : w.node0_wide[256 * (i64)(-1 - anchor) + (a & 255)];
             const int32_t al_first = w.aln_al_first[a], al_last = w.aln_al_last[a];
-            // eight records at a time: their steps, then their node lengths, are loaded together (a record-by-record
-            // loop would chain two dependent loads per record)
-            for (i64 c = lo; c < hi; c += 8) {
-                int st[8];
+            const int base = staged ? (int)(lo - r0) : 0;        // the walk's place in the shared-memory image
+            const uint8_t* sp = w.walk_step + (lo >> 1);         // its nibbles: number odd .. odd + L - 1 from here
+            const int odd = (int)(lo & 1);
+            // eight records at a time: their nibbles (five bytes at most), then their node lengths, are loaded together (a
+            // record-by-record loop would chain two dependent loads per record)
+            for (int c = 0; c < L; c += 8) {
+                const int b0 = (odd + c) >> 1;
+                u64 win = 0;
+#pragma unroll
+                for (int j = 0; j < 5; ++j)
+                    if (2 * (b0 + j) < odd + L) win |= (u64)sp[b0 + j] << (8 * j);
+                win >>= 4 * odd;
                 int32_t nd[8], nl[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k)           // the record's nibble: step + 8, 0 = listed
-                    st[k] = (c + k < hi && c + k > lo) ? (int)((w.walk_step[(c + k) >> 1] >> (4 * ((c + k) & 1))) & 15u) : 8;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    if (c + k < hi && c + k > lo) node = st[k] ? node + st[k] - 8 : wide_node_of(w, c + k);
+                for (int k = 0; k < 8; ++k) {                    // the record's nibble: step + 8, 0 = listed
+                    const int nib = (int)(win >> (4 * k)) & 15;
+                    if (c + k < L && c + k > 0) node = nib ? node + nib - 8 : wide_node_of(w, lo + c + k);
                     nd[k] = node;
                 }
 #pragma unroll
-                for (int k = 0; k < 8; ++k) nl[k] = c + k < hi ? node_len[nd[k]] : 0;
+                for (int k = 0; k < 8; ++k) nl[k] = c + k < L ? node_len[nd[k]] : 0;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    const i64 r = c + k;
-                    if (r >= hi) break;
-                    // first / last record: the shipped byte; in between the node is covered completely.  Records with
-                    // an explicit coverage (byte 255, or listed) are overwritten by k_apply_exceptions.
-                    const int32_t al = r == lo ? al_first : (r == hi - 1 ? al_last : (nl[k] & 0xFFFF));
-                    if (staged) {
-                        s_node[r - r0] = nd[k];
-                        s_alen[r - r0] = al | (nl[k] << 16);
-                    } else {
-                        walk_node[r] = nd[k];
-                        walk_alen[r] = al | (nl[k] << 16);
+                    const int i = c + k;
+                    if (i < L) {
+                        // first / last record: the shipped byte; in between the node is covered completely.  Records with
+                        // an explicit coverage (byte 255, or listed) are overwritten by k_apply_exceptions.
+                        const int32_t al = i == 0 ? al_first : (i == L - 1 ? al_last : (nl[k] & 0xFFFF));
+                        if (staged) {
+                            s_node[base + i] = nd[k];
+                            s_alen[base + i] = al | (nl[k] << 16);
+                        } else {
+                            walk_node[lo + i] = nd[k];
+                            walk_alen[lo + i] = al | (nl[k] << 16);
+                        }
                     }
                 }
             }
@@ -235,7 +243,11 @@ int launch_expand(const sfb_wire* w, const int32_t* node_len, const sfb_reads* d
     if (w->n_seq_exc) k_apply_seq_exceptions<<<blocks_for(w->n_seq_exc, 256), 256, 0, st>>>(*w, mate_seq_len);
     if (w->n_alns) k_expand_bins<<<kSMs * 8, 256, 0, st>>>(*w, aln_bins);
     if (w->n_bins_exc) k_apply_bins_exceptions<<<blocks_for(w->n_bins_exc, 256), 256, 0, st>>>(*w, aln_bins);
-    if (w->n_records) k_expand_walks<<<kSMs * 8, kWalkTile, 0, st>>>(*w, aln_walk_off, node_len, walk_node, walk_alen);
+    if (w->n_records) {
+        static OccCache cache;               // one wave of resident blocks (the block loop strides over the tiles of 256 walks)
+        const unsigned grid = persistent_grid(k_expand_walks, kWalkTile, blocks_for(w->n_alns, kWalkTile), cache);
+        k_expand_walks<<<grid, kWalkTile, 0, st>>>(*w, aln_walk_off, node_len, walk_node, walk_alen);
+    }
     if (w->n_exc) k_apply_exceptions<<<blocks_for(w->n_exc, 256), 256, 0, st>>>((const i64*)w->exc_idx, w->n_exc, walk_alen);
     return check_launch("expand_reads");
 }

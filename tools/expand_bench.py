@@ -8,7 +8,7 @@ from strainflair_b200 import engine, synth
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 0.125
 graph, reads = synth.make_config("c3", scale=scale)
 eng = engine.AbundanceEngine(graph, "cuda:0")
-host = engine.HostReads(reads)
+host = eng.stage(reads, pin=False) if not os.environ.get("SFB_FILE_ORDER") else engine.HostReads(reads)   # tile order, as the engine stages it
 dr = engine.DeviceReads(host, eng.device, None, None, eng.node_len, expand=False)
 torch.cuda.synchronize()
 ts = []
