@@ -474,10 +474,7 @@ def run_ours(args):
                "sample": f"first {sp} read pairs of the workload, oracle port (Python) sharded over {cores} processes, "
                          f"decode excluded, {secs:.1f} s"}
 
-    # decode, reported separately (north_star): native streaming decoder on all cores vs the oracle's Python decoder
-    dec = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        dec = decode_rates(graph, synth, idx, rkw, min(40_000, pairs))
+    dec = None          # (decode and the command-line job are timed after the GPU measurements, see below)
 
     import numpy as np
     import torch
@@ -627,6 +624,13 @@ def run_ours(args):
             extras["c5q"] = extra_config("c5", 0.25, 5, device, comm, world, rank, dist)
         else:
             extras["c5"] = extra_config("c5", 1.0, 5, device, comm, world, rank, dist, strong=True)
+
+    # decode, reported separately (north_star): native streaming decoder on all cores vs the oracle's Python decoder, and
+    # the whole json2csv job through the command line.  Last: the job runs its own engine in this process, and an engine
+    # that ran before the measured one made k_classify 35 % slower (2.51 against 1.85 ms, profiles/README.md r03e).
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        torch.cuda.empty_cache()
+        dec = decode_rates(graph, synth, idx, rkw, min(40_000, pairs))
 
     if rank == 0:
         reads_n = {"groups": host.n_groups, "alns": host.n_alns, "records": host.n_records}
