@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(kBinBlock) k_tile_scatter1(Dev d, sfb_tiles t)
 //   scan    32 read groups of the item: the deferred ones join the warp's queue
 //   decide  32 queued groups, lane = group: candidate selection and ratios on the path sets; every share becomes an entry
 //           of the warp's share list (alignment, path, orientation, ratio, times, len(sequence))
-//   add     32 listed shares, lane = share: per-path sums, slot of the path on the walk's first / last node, node loop
+//   add     32 listed shares, lane = share: per-path sums, slot of the path on the walk's first / last node; their node
+//           loops are then laid over the warp (share_records)
 #ifndef SFB_SHARE_BLOCK
 #define SFB_SHARE_BLOCK 256                 /* measured on C3 (profiles/README.md r02r-r02t): 8 warps share one set of bins, 4 blocks
                                                per SM = 32 warps at 64 registers (some spills) beat 20-24 warps at 80-96 */
