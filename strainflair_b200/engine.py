@@ -953,6 +953,13 @@ class AbundanceEngine:
     def _result_from(self, acc, f64, i64, table):
         """Host copies of the read-back buffers as a Result."""
         P = acc.P
+        if acc.planes > 1 and P:
+            # order-independent mode: terms and per-accumulator totals must stay below 2^31 (include/sfb200.h,
+            # sfb_accum.det_stride); the per-path totals bound the per-node ones
+            top = max(float(i64[0:P].max()), float(np.nanmax(f64[0:3 * P])))
+            if top >= 2.0 ** 31:
+                raise OverflowError(f"order-independent accumulation: a per-path total reached {top:.3g} >= 2^31; "
+                                    "shard the reads over more passes / GPUs or use deterministic=False")
         counters_raw = i64[P + acc.n_hist:P + acc.n_hist + _lib.N_COUNTERS].copy()
         return Result(
             g=self.graph.as_dict(),
