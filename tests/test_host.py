@@ -618,3 +618,52 @@ def test_transfer_layout_first_nodes_wide_and_narrow_blocks():
         grp_aln_off, off, seq, bins, node, word = _expand_on_host(w, common, node_len)
         assert np.array_equal(node, rd.walk_node) and np.array_equal(off, rd.aln_walk_off)
     assert {"wide", "narrow"} <= seen
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_transfer_layout_round_trip_random_shards(seed):
+    """The packer / expansion pair on random shards: random group order (file order, locality order or shuffled), shard
+    boundaries that fall anywhere (odd record offsets: the step nibbles of two shards' chunks share bytes), node ids
+    spread so that some blocks of first nodes are narrow and some wide, steps beyond the nibble range."""
+    from strainflair_b200 import engine, synth
+    rng = np.random.default_rng(1000 + seed)
+    gkw, _ = synth.CONFIGS["tiny"]
+    graph = synth.make_graph(31 + seed, **gkw)
+    reads = synth.make_reads(graph, 41 + seed, n_pairs=int(rng.integers(1, 1500)), read_len=150, p_exc=0.03)
+    gap = int(rng.choice([0, 9, 70000]))                       # ids of the upper part of the graph moved up by `gap`
+    cut = int(rng.integers(1, graph.n_nodes))
+    new_id = np.arange(graph.n_nodes, dtype=np.int64) + gap * (np.arange(graph.n_nodes) >= cut)
+    node_len = np.ones(int(new_id[-1]) + 1, graph.node_len.dtype)
+    node_len[new_id] = graph.node_len
+    reads.walk_node[:] = new_id[reads.walk_node]
+    order = [np.arange(reads.n_groups), reads.locality_order(), rng.permutation(reads.n_groups)][seed % 3]
+    rd = reads.permute_groups(order)
+    g0 = int(rng.integers(0, rd.n_groups))
+    g1 = int(rng.integers(g0, rd.n_groups + 1))
+    for part in (rd, rd.slice_groups(g0, g1), rd.slice_groups(0, g0)):
+        out = engine.wire_arrays(part)
+        if out is None:                                        # (the layout does not pay for this shard: plain arrays)
+            continue
+        w, common = out
+        grp_aln_off, off, seq, bins, node, word = _expand_on_host(w, common, node_len)
+        assert np.array_equal(grp_aln_off, part.grp_aln_off) and np.array_equal(off, part.aln_walk_off)
+        assert np.array_equal(seq, part.mate_seq_len) and np.array_equal(bins, part.aln_bins)
+        assert np.array_equal(node, part.walk_node)
+        assert np.array_equal(_coverage(word, w["exc_cov"]), _coverage(part.walk_alen, part.exc_cov))
+
+
+def test_transfer_layout_is_independent_of_the_thread_count():
+    """The packer works on chunks of 65536 alignments in parallel; step nibbles of neighbouring chunks share a byte.  More
+    than one chunk: the same bytes whatever the number of threads, and the round trip holds."""
+    from strainflair_b200 import engine, synth
+    graph, reads = synth.make_config("small", scale=1.0)
+    assert reads.n_alns > 65536
+    ref = None
+    for threads in (1, 3, 16):
+        w, common = engine.wire_arrays(reads, threads=threads)
+        if ref is None:
+            ref = w
+        else:
+            assert all(np.array_equal(ref[k], w[k]) for k in ref), threads
+    grp_aln_off, off, seq, bins, node, word = _expand_on_host(ref, common, graph.node_len)
+    assert np.array_equal(node, reads.walk_node) and np.array_equal(off, reads.aln_walk_off)
