@@ -33,5 +33,7 @@ def test_config_shapes_match_oracle(name, pairs):
     # index, the all-in-one shared-memory tile kernels, and the global-memory kernels on reads in file order
     check_against_oracle(graph, reads, engine.AbundanceEngine(graph, tile_bins=False).run(host), orc)
     check_against_oracle(graph, reads, engine.AbundanceEngine(graph, step_index=False).run(host), orc)
+    if name == "c5":          # (every engine rebuilds the device layout of the 74 M-slot graph on the host: two families more
+        return                #  would double the two minutes this case takes; they run on C3 and C4)
     check_against_oracle(graph, reads, engine.AbundanceEngine(graph, tile_kernels=True).run(host), orc)
     check_against_oracle(graph, reads, engine.AbundanceEngine(graph, tiles=False).run(reads), orc)
